@@ -1,0 +1,114 @@
+/* rdst_b200.h -- C ABI of librdst_b200.so: hand-written sm_100a kernels for the RDST super-resolution
+ * network hot path (GinZhu/RDST: networks/rdst_variations.py + networks/swin_transformer_sr.py).
+ *
+ * Conventions:
+ *   - plain device pointers + explicit shapes/strides, no torch types; the caller owns every buffer;
+ *   - every entry point returns 0 on success or a negative RDST_E_* code, never throws;
+ *     rdst_last_error() returns a thread-local message for the last failure on the calling thread;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*), never synchronise, allocate
+ *     nothing and keep no global state => safe to capture in a CUDA graph; the caller must have the
+ *     device that owns the pointers current (the Python wrapper holds a torch.cuda.device guard);
+ *   - `dtype` selects the STORAGE type of activations: RDST_F32 or RDST_BF16.  Arithmetic is always
+ *     fp32-accumulate; the *_tc entry points use bf16 tcgen05 tensor-core operands.
+ *
+ * Activation layout ("token-major, padded"): every activation is a 2-D array [T][ld] with T = B*H*W
+ * tokens in raster order and channels padded so that GEMM K is a multiple of 16/32:
+ *     dense buffer D  : ld = 160 ; trunk x0 at [0,60), growth g_j (30 ch) at [64+32(j-1), +30), pads are 0
+ *     STL work buffer : ld = Cp  ; Cp = 64/96/128 for C = 60/90/120 (same channel->position map, truncated)
+ *     conv feature map: ld = 64  ; 60 real channels
+ * Weights are pre-packed by the host into the same padded K order (zero columns at pads); LayerNorm
+ * affine (gamma, beta) and the attention scale are folded into the following linear layer by the host.
+ *
+ * Each declaration cites the reference code it replaces (paths relative to the reference repo).
+ */
+#ifndef RDST_B200_H
+#define RDST_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RDST_ABI_VERSION 1
+
+#define RDST_F32  0
+#define RDST_BF16 1
+
+#define RDST_OK             0
+#define RDST_E_INVALID     -1   /* bad argument (null pointer, unsupported size, misalignment) */
+#define RDST_E_CUDA        -2   /* a CUDA runtime call failed; see rdst_last_error()           */
+#define RDST_E_UNSUPPORTED -3   /* outside the supported envelope                              */
+
+int         rdst_abi_version(void);
+const char* rdst_last_error(void);
+/* 1 if the library was built with the tcgen05 (sm_100a) kernels and the current device can run them. */
+int         rdst_has_tcgen05(void);
+
+/* ---- generic CUDA-core ("simt") kernels: fp32 mode of the module, and the validation path -------------- */
+
+/* Y[t][n] = out_scale * act( LNhat(X[t][0:K]) . W[n][0:K] + bias[n] ) + R[t][n]
+ *   LNhat: if ln_creal > 0, x <- (x - mean) * rstd with statistics over the K stored values divided by
+ *          ln_creal real channels (pads are zero), eps 1e-5; gamma/beta pre-folded into W/bias.
+ *   act  : 0 none, 1 exact-erf GELU.   R may be NULL.
+ * Replaces nn.Linear (+ preceding nn.LayerNorm, + following nn.GELU / residual add):
+ *   swin_transformer_sr.py:117 (qkv), :139 (proj), :24-27 (Mlp), :240,:271-272 (norm1/2 + residuals),
+ *   rdst_variations.py:309-313,339-340 (DenseSTLayer tail LN+Linear, *dense_scale, in-place "cat"). */
+int rdst_linear_fwd(const void* x, int64_t ldx, const float* w, const float* bias,
+                    const void* resid, int64_t ldr, void* y, int64_t ldy,
+                    int64_t T, int K, int N, int ln_creal, int act, float out_scale,
+                    int dtype, void* stream);
+
+/* Windowed multi-head attention core on an 8x8 window grid with optional cyclic shift.
+ *   qkv : [T][ldq], q at [0,C), k at [C,2C), v at [2C,3C), head h owns channels [h*C/heads, (h+1)*C/heads);
+ *         q is already scaled (scale folded into the qkv weights).
+ *   out : [T][ldo], channel order (head, d) as in the reference's transpose(1,2).reshape (:138).
+ *   table: relative_position_bias_table (225, heads) fp32; index is (dh+7)*15+(dw+7) (:89-98).
+ *   shift: 0 or 4.  The roll(-s)/window_partition/window_reverse/roll(+s) of swin_transformer_sr.py:245-265
+ *   is index arithmetic; the {0,-100} mask of calculate_mask (:211-232) is evaluated in closed form.
+ * Replaces WindowAttention.forward :120-138 and SwinTransformerBlock.forward :243-268. */
+int rdst_window_attention_fwd(const void* qkv, int64_t ldq, const float* table, void* out, int64_t ldo,
+                              int B, int H, int W, int C, int heads, int shift, int dtype, void* stream);
+
+/* 3x3 same-padding convolution on token-major (NHWC) data as an implicit GEMM.
+ *   x : [B*H*W][ldx] (Cin stored channels), w : [N][9][Cin] (tap = ky*3+kx), bias : [N]
+ *   y[t][n] = out_scale * (conv + bias) + R[t][n]                           (shuffle == 0)
+ *   shuffle == 2: N = 4*G; output pixel (2y+dy, 2x+dx) of a [B*2H*2W][ldy] map receives channels
+ *                 n in [G*(2dy+dx), G*(2dy+dx)+G)  -- nn.PixelShuffle(2) folded into the store.
+ * Replaces RDSTB.conv (LFF) + patch_unembed/patch_embed transposes (rdst_variations.py:444-445),
+ * conv_after_body (:1349-1350) and UpSampler conv+PixelShuffle (common.py:129-132). */
+int rdst_conv3x3_fwd(const void* x, int64_t ldx, const float* w, const float* bias,
+                     const void* resid, int64_t ldr, void* y, int64_t ldy,
+                     int B, int H, int W, int Cin, int N, float out_scale, int shuffle,
+                     int dtype, void* stream);
+
+/* Shallow feature extraction: img (B,1,H,W) fp32 NCHW -> feat0[t][0:64] = conv3x3(1->60) (kept for the global
+ * residual) and dense[t][0:64] = LayerNorm_60(feat0) * gamma + beta (patch_embed.norm), pads zero.
+ * `in_scale`/`in_bias` fold sub_mean (MeanShift 1x1).  w : [60][9], bias/gamma/beta : [60].
+ * Replaces sub_mean + head + patch_embed (rdst_variations.py:1343-1344,1329; swin_transformer_sr.py:515-519). */
+int rdst_head_fwd(const float* img, float in_scale, float in_bias, const float* w, const float* bias,
+                  const float* gamma, const float* beta, void* feat0, int64_t ldf, void* dense, int64_t ldd,
+                  int B, int H, int W, int dtype, void* stream);
+
+/* Stand-alone LayerNorm over the first `creal` of `ld` stored channels with affine, times out_scale.
+ * Replaces RDSTSR.norm + *global_res_scale (rdst_variations.py:1337,1347). */
+int rdst_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
+                       int64_t T, int creal, float out_scale, int dtype, void* stream);
+
+/* Final reconstruction conv 3x3 (Cin stored channels -> 1) to an fp32 NCHW image, with add_mean folded
+ * (out = out_scale * conv + out_bias).  w : [9][Cin].  Replaces tail[-1] + add_mean (:1303,1358). */
+int rdst_last_conv_fwd(const void* x, int64_t ldx, const float* w, float bias, float out_scale, float out_bias,
+                       float* img, int B, int H, int W, int Cin, int dtype, void* stream);
+
+/* ---- tcgen05 / TMEM kernels (bf16 operands, fp32 accumulate), sm_100a only ---------------------------- */
+
+/* Self-test of the UMMA plumbing: D[M=128][N] = A[128][K] . B[N][K]^T with bf16 inputs, fp32 output.
+ * b_mn_major != 0 feeds B from an MN-major shared-memory image.  Used by tests/ only. */
+int rdst_umma_selftest(const void* a_bf16, const void* b_bf16, float* d, int N, int K, int b_mn_major,
+                       int m64, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RDST_B200_H */

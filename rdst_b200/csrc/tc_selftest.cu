@@ -1,0 +1,94 @@
+// UMMA plumbing self-test: one CTA computes D[128][N] = A[128][K] . B[N][K]^T on tcgen05 with the same
+// shared-memory images, descriptors, commit/mbarrier protocol and TMEM read-back that the fused kernels use.
+// tests/test_umma_selftest.py runs it over the (N, K, layout) combinations the network needs, so a descriptor
+// mistake shows up here and not as a silent numerical error deep inside the fused kernels.
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace rdst {
+using namespace umma;
+
+// A: [128][K] bf16 row-major, B: [N][K] bf16 row-major, D: [128][N] fp32 (all 128 TMEM lanes are dumped even
+// when m64 != 0 so the M=64 accumulator lane mapping can be inspected).
+__global__ void __launch_bounds__(128) umma_selftest_kernel(const __nv_bfloat16* __restrict__ A,
+                                                            const __nv_bfloat16* __restrict__ B, float* __restrict__ D,
+                                                            int N, int K, int b_mn_major, int m64) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* sA = smem;                         // K-major: (k/8)*2048 + r*16 + (k%8)*2
+  uint8_t* sB = smem + (size_t)128 * K * 2;   // K-major: (k/8)*(N*16) + n*16 + (k%8)*2 ; MN-major: see below
+
+  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+
+  // stage A (zero rows >= 64 when m64 so stale smem cannot leak in)
+  for (int idx = tid; idx < 128 * (K / 8); idx += 128) {
+    const int r = idx % 128, kc = idx / 128;
+    uint4 v = make_uint4(0, 0, 0, 0);
+    if (!m64 || r < 64) v = *reinterpret_cast<const uint4*>(A + (size_t)r * K + kc * 8);
+    *reinterpret_cast<uint4*>(sA + (size_t)kc * 2048 + r * 16) = v;
+  }
+  if (!b_mn_major) {
+    for (int idx = tid; idx < N * (K / 8); idx += 128) {
+      const int n = idx % N, kc = idx / N;
+      *reinterpret_cast<uint4*>(sB + (size_t)kc * (N * 16) + n * 16) =
+          *reinterpret_cast<const uint4*>(B + (size_t)n * K + kc * 8);
+    }
+  } else {
+    // MN-major image: element (k, n) at (k/8)*128 + (n/8)*(K/8*128) + (k%8)*16 + (n%8)*2
+    for (int idx = tid; idx < N * K; idx += 128) {
+      const int n = idx % N, k = idx / N;
+      *reinterpret_cast<__nv_bfloat16*>(sB + (size_t)(k / 8) * 128 + (size_t)(n / 8) * ((K / 8) * 128) + (k % 8) * 16 +
+                                        (n % 8) * 2) = B[(size_t)n * K + k];
+    }
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+
+  if (tid == 0) {
+    const uint32_t idesc = make_idesc_bf16(m64 ? 64 : 128, N, false, b_mn_major != 0);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      const uint64_t da = make_smem_desc(smem_u32(sA) + ks * 2 * 2048, 2048, 128);
+      uint64_t db;
+      if (!b_mn_major) db = make_smem_desc(smem_u32(sB) + ks * 2 * (N * 16), N * 16, 128);
+      else db = make_smem_desc(smem_u32(sB) + ks * 2 * 128, 128, (K / 8) * 128);
+      mma_bf16_ss(tmem, da, db, idesc, ks > 0 ? 1u : 0u);
+    }
+    commit(&bar);
+  }
+  mbar_wait(&bar, 0);
+  fence_after_sync();
+
+  for (int c0 = 0; c0 < N; c0 += 8) {
+    uint32_t v[8];
+    tmem_ld_x8(tmem + ((uint32_t)(warp * 32) << 16) + c0, v);
+    wait_ld();
+#pragma unroll
+    for (int j = 0; j < 8; ++j) D[(size_t)(warp * 32 + lane) * N + c0 + j] = __uint_as_float(v[j]);
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+}  // namespace rdst
+
+extern "C" int rdst_umma_selftest(const void* a_bf16, const void* b_bf16, float* d, int N, int K, int b_mn_major,
+                                  int m64, void* stream) {
+  using namespace rdst;
+  RDST_REQUIRE(a_bf16 && b_bf16 && d, "rdst_umma_selftest: null pointer");
+  RDST_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K % 16 == 0 && K <= 256,
+               "rdst_umma_selftest: need 16<=N<=256 (N%%16==0), 16<=K<=256 (K%%16==0); got N=%d K=%d", N, K);
+  const size_t smem = (size_t)128 * K * 2 + (size_t)N * K * 2;
+  cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) { set_error("rdst_umma_selftest: smem attr: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
+  umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16,
+                                                              d, N, K, b_mn_major, m64);
+  RDST_CHECK_LAUNCH("rdst_umma_selftest");
+  return RDST_OK;
+}

@@ -1,0 +1,194 @@
+"""Launch sequence of the RDST forward pass over librdst_b200 kernels.
+
+One `Executor` is bound to one RDSTSR module.  It owns (a) the packed-weight cache (rebuilt when a parameter's
+version counter changes, e.g. after optimizer.step() or load_state_dict) and (b) per-shape workspaces allocated
+through torch so the caching allocator / CUDA-graph pools see them.  Kernels are enqueued on torch's current
+stream; nothing here synchronises.
+
+Data flow per RDSTB (dense buffer D is [T][160], see include/rdst_b200.h):
+    for j in 0..2:  C = 60+30j
+        STL(shift 0):  D[:, :Cp] -> Y0          STL(shift 4): Y0 -> Y1
+        tail:          LN+Linear(Y1) * dense_scale -> D[:, 64+32j : 96+32j]        (the reference's torch.cat)
+    LFF: conv3x3(D, 150->60) * res_scale + D[:, :64]  ->  D'[:, :64]               (ping-pong buffer)
+"""
+import weakref
+
+import torch
+
+from . import _lib, packing
+
+
+def call(name, *args):
+    _lib.call(name, *args)
+
+
+def ptr(t):
+    return _lib.ptr(t)
+
+
+class Executor:
+    def __init__(self, module):
+        self._module = weakref.ref(module)
+        self._packed = None
+        self._packed_key = None
+        self._ws = {}
+
+    def __deepcopy__(self, memo):
+        return Executor.__new__(Executor)._reset()
+
+    def _reset(self):
+        self._module = lambda: None
+        self._packed = self._packed_key = None
+        self._ws = {}
+        return self
+
+    def bound_to(self, module):
+        return self._module() is module
+
+    # ------------------------------------------------------------------ packed weights
+    def _weights(self, device):
+        m = self._module()
+        key = (str(device),) + tuple((p.data_ptr(), p._version) for p in m.parameters())
+        if self._packed is not None and key == self._packed_key:
+            return self._packed
+        with torch.no_grad():
+            P = {"blocks": []}
+            for blk in m.body:
+                B = {"dstl": []}
+                c = packing.EMBED
+                for dstl in blk.body:
+                    B["dstl"].append(dict(
+                        c=c,
+                        stl=[packing.pack_stl(b, c) for b in dstl.body.blocks],
+                        shifts=[b.shift_size for b in dstl.body.blocks],
+                        tail=packing.pack_dstl_tail(dstl, c, m.dense_scale)))
+                    c += packing.GROWTH
+                pos = packing.channel_positions(c, device)
+                B["lff_w"], B["lff_b"] = packing.pack_conv(blk.conv.weight, blk.conv.bias, pos, packing.DENSE_LD, 64)
+                P["blocks"].append(B)
+            f = lambda t: t.detach().float().contiguous()
+            id60 = torch.arange(60, device=device)
+            P["head_w"] = f(m.head.weight).reshape(60, 9).contiguous()
+            P["head_b"] = f(m.head.bias)
+            P["pe_g"], P["pe_b"] = f(m.patch_embed.norm.weight), f(m.patch_embed.norm.bias)
+            P["norm_g"], P["norm_b"] = f(m.norm.weight), f(m.norm.bias)
+            P["cab_w"], P["cab_b"] = packing.pack_conv(m.conv_after_body.weight, m.conv_after_body.bias, id60, 64, 64)
+            P["up"] = [packing.pack_upconv(l.weight, l.bias) for l in m.tail[0] if isinstance(l, torch.nn.Conv2d)]
+            last = m.tail[1]
+            lw = last.weight.new_zeros(9, 64, dtype=torch.float32)
+            lw[:, :60] = last.weight.detach().float()[0].permute(1, 2, 0).reshape(9, 60)
+            P["last_w"] = lw.contiguous()
+            # scalars are read once per re-pack (a host sync only when weights changed)
+            P["last_b"] = float(last.bias.detach().float()[0])
+            P["in_scale"] = float(m.sub_mean.weight.detach().reshape(-1)[0])
+            P["in_bias"] = float(m.sub_mean.bias.detach().reshape(-1)[0])
+            P["out_scale"] = float(m.add_mean.weight.detach().reshape(-1)[0])
+            P["out_bias"] = float(m.add_mean.bias.detach().reshape(-1)[0])
+        self._packed, self._packed_key = P, key
+        return P
+
+    # ------------------------------------------------------------------ workspaces
+    def _workspace(self, B, H, W, dtype, device, scale):
+        key = (B, H, W, dtype, str(device), scale)
+        ws = self._ws.get(key)
+        if ws is None:
+            T = B * H * W
+            e = lambda *s: torch.empty(*s, dtype=dtype, device=device)
+            ws = dict(D=[e(T, 160), e(T, 160)], X1=e(T, 128), Y0=e(T, 128), Y1=e(T, 128),
+                      QKV=e(T, 360), O=e(T, 120), HID=e(T, 240),
+                      F0=e(T, 64), F1=e(T, 64),
+                      FN=torch.zeros(T, 64, dtype=dtype, device=device))   # LN writes 60 ch; pads stay 0
+            ups, t = [], T
+            s = scale
+            while s > 1:
+                t *= 4
+                ups.append(e(t, 64))
+                s //= 2
+            ws["UP"] = ups
+            if len(self._ws) > 8:
+                self._ws.clear()
+            self._ws[key] = ws
+        return ws
+
+    # ------------------------------------------------------------------ forward
+    def forward(self, x):
+        m = self._module()
+        if not x.is_cuda:
+            raise RuntimeError("rdst_b200: input must be a CUDA tensor; this package has no CPU path")
+        if x.dim() != 4 or x.shape[1] != 1:
+            raise ValueError(f"rdst_b200: expected input (B,1,H,W), got {tuple(x.shape)}")
+        B, _, H, W = x.shape
+        if H % 8 or W % 8:
+            raise RuntimeError(f"rdst_b200: H={H}, W={W} must be multiples of the window size 8 "
+                               "(the reference fails in window_partition's view for such inputs)")
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in m.parameters())):
+            from . import autograd
+            return autograd.forward_with_grad(self, x)
+        with torch.no_grad(), torch.cuda.device(x.device):
+            return self._forward_impl(x)
+
+    def _forward_impl(self, x):
+        m = self._module()
+        dev = x.device
+        adt = torch.float32 if m.precision == "fp32" else torch.bfloat16
+        dt = _lib.dtype_code(adt)
+        B, _, H, W = x.shape
+        T = B * H * W
+        P = self._weights(dev)
+        ws = self._workspace(B, H, W, adt, dev, m.sr_scale)
+        st = _lib.stream_ptr()
+        xin = x.detach().to(torch.float32).contiguous()
+        D = ws["D"]
+        cur = 0
+        call("rdst_head_fwd", ptr(xin), P["in_scale"], P["in_bias"], ptr(P["head_w"]), ptr(P["head_b"]),
+             ptr(P["pe_g"]), ptr(P["pe_b"]), ptr(ws["F0"]), 64, ptr(D[cur]), 160, B, H, W, dt, st)
+        for blk in P["blocks"]:
+            for j, ds in enumerate(blk["dstl"]):
+                src, lds = D[cur], 160
+                for k, (w, shift) in enumerate(zip(ds["stl"], ds["shifts"])):
+                    cp = w["cp"]
+                    dst = (ws["Y0"] if k == 0 else ws["Y1"]).view(-1)[:T * cp].view(T, cp)
+                    self._stl(src, lds, dst, w, shift, B, H, W, ws, dt, st)
+                    src, lds = dst, w["cp"]
+                t = ds["tail"]
+                off = 64 + 32 * j
+                call("rdst_linear_fwd", ptr(src), lds, ptr(t["w"]), ptr(t["b"]), None, 0,
+                     ptr(D[cur][:, off:]), 160, T, ds["stl"][0]["cp"], 32, ds["c"], 0, t["scale"], dt, st)
+            call("rdst_conv3x3_fwd", ptr(D[cur]), 160, ptr(blk["lff_w"]), ptr(blk["lff_b"]), ptr(D[cur]), 160,
+                 ptr(D[1 - cur]), 160, B, H, W, 160, 64, float(m.rdb_residual_scale), 0, dt, st)
+            cur = 1 - cur
+        call("rdst_layernorm_fwd", ptr(D[cur]), 160, ptr(P["norm_g"]), ptr(P["norm_b"]), ptr(ws["FN"]), 64,
+             T, 60, float(m.global_res_scale), dt, st)
+        if m.feature_last_operation:
+            call("rdst_conv3x3_fwd", ptr(ws["FN"]), 64, ptr(P["cab_w"]), ptr(P["cab_b"]), ptr(ws["F0"]), 64,
+                 ptr(ws["F1"]), 64, B, H, W, 64, 64, 1.0, 0, dt, st)
+            feat = ws["F1"]
+        else:
+            feat = ws["F1"]
+            torch.add(ws["FN"], ws["F0"], out=feat)
+        h, w_ = H, W
+        for (uw, ub), buf in zip(P["up"], ws["UP"]):
+            call("rdst_conv3x3_fwd", ptr(feat), 64, ptr(uw), ptr(ub), None, 0, ptr(buf), 64,
+                 B, h, w_, 64, 256, 1.0, 2, dt, st)
+            feat, h, w_ = buf, 2 * h, 2 * w_
+        out = torch.empty(B, 1, h, w_, dtype=torch.float32, device=dev)
+        call("rdst_last_conv_fwd", ptr(feat), 64, ptr(P["last_w"]), P["last_b"], P["out_scale"], P["out_bias"],
+             ptr(out), B, h, w_, 64, dt, st)
+        return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+    def _stl(self, src, lds, dst, w, shift, B, H, W, ws, dt, st):
+        """One Swin block: x1 = x + proj(attn(LN1 x)); y = x1 + fc2(gelu(fc1(LN2 x1)))."""
+        T = B * H * W
+        c, cp, hp = w["c"], w["cp"], w["hp"]
+        v = lambda buf, ld: buf.view(-1)[:T * ld].view(T, ld)       # compact [T][ld] view of a max-sized buffer
+        qkv, o, x1, hid = v(ws["QKV"], 3 * c), v(ws["O"], c), v(ws["X1"], cp), v(ws["HID"], hp)
+        call("rdst_linear_fwd", ptr(src), lds, ptr(w["wqkv"]), ptr(w["bqkv"]), None, 0, ptr(qkv), 3 * c,
+             T, cp, 3 * c, c, 0, 1.0, dt, st)
+        call("rdst_window_attention_fwd", ptr(qkv), 3 * c, ptr(w["table"]), ptr(o), c,
+             B, H, W, c, packing.HEADS, shift, dt, st)
+        call("rdst_linear_fwd", ptr(o), c, ptr(w["wproj"]), ptr(w["bproj"]), ptr(src), lds, ptr(x1), cp,
+             T, c, cp, 0, 0, 1.0, dt, st)
+        call("rdst_linear_fwd", ptr(x1), cp, ptr(w["w1"]), ptr(w["b1"]), None, 0, ptr(hid), hp,
+             T, cp, hp, c, 1, 1.0, dt, st)
+        call("rdst_linear_fwd", ptr(hid), hp, ptr(w["w2"]), ptr(w["b2"]), ptr(x1), cp, ptr(dst), cp,
+             T, hp, cp, 0, 0, 1.0, dt, st)

@@ -1,0 +1,122 @@
+"""Host-side weight packing for the librdst_b200 kernels.
+
+The kernels see activations in a token-major, padded channel layout (include/rdst_b200.h) and expect
+  * LayerNorm affine folded into the following Linear        (W' = W * gamma, b' = b + W @ beta),
+  * the attention scale head_dim**-0.5 folded into the q rows of qkv (reference scales q before q@k^T,
+    networks/swin_transformer_sr.py:120),
+  * K columns / N rows placed at padded channel positions with zeros at the pads,
+  * conv weights as [N][tap][Cin_padded] and the PixelShuffle permutation folded into the row order of
+    the up-sampling convs (networks/common.py:129-132).
+Everything here is tiny (4.5 M parameters) and runs as ordinary torch ops on the parameter's device; the
+result is a cache keyed on parameter versions, never part of state_dict.
+"""
+import torch
+
+EMBED = 60
+GROWTH = 30
+HEADS = 6
+DENSE_LD = 160          # 64 (trunk, 60 real) + 3 * 32 (growth, 30 real)
+FEAT_LD = 64
+
+
+def padded_width(c):
+    """Stored width of a dense-block activation with c = 60 + 30*j real channels."""
+    j = (c - EMBED) // GROWTH
+    assert c == EMBED + GROWTH * j and 0 <= j <= 3, f"unsupported channel count {c}"
+    return 64 + 32 * j
+
+
+def channel_positions(c, device=None):
+    """Stored position of every real channel: trunk at [0,60), growth block g at [64+32g, +30)."""
+    idx = torch.arange(c, device=device)
+    g = torch.clamp((idx - EMBED) // GROWTH, min=0)
+    return torch.where(idx < EMBED, idx, 64 + 32 * g + (idx - EMBED) % GROWTH)
+
+
+def hidden_width(h):
+    return (h + 15) // 16 * 16
+
+
+def scatter_cols(w, pos, width):
+    """[N][C] -> [N][width] with column c moved to pos[c]."""
+    out = w.new_zeros(w.shape[0], width)
+    out[:, pos] = w
+    return out
+
+
+def scatter_rows(w, pos, height):
+    out = w.new_zeros((height,) + tuple(w.shape[1:]))
+    out[pos] = w
+    return out
+
+
+def fold_ln(w, b, gamma, beta):
+    """Linear(LN(x)) with affine == Linear'(xhat):  W' = W*gamma,  b' = b + W@beta."""
+    return w * gamma[None, :], b + w @ beta
+
+
+def pack_stl(blk, c):
+    """blk: Swin block parameter container (norm1, attn.{qkv,proj,relative_position_bias_table}, norm2, mlp)."""
+    f = lambda t: t.detach().float()
+    cp = padded_width(c)
+    pos = channel_positions(c, blk.norm1.weight.device)
+    hd = c // HEADS
+    wq, bq = fold_ln(f(blk.attn.qkv.weight), f(blk.attn.qkv.bias), f(blk.norm1.weight), f(blk.norm1.bias))
+    scale = blk.attn.scale
+    wq = wq.clone(); bq = bq.clone()
+    wq[:c] *= scale
+    bq[:c] *= scale
+    hid = blk.mlp.fc1.weight.shape[0]
+    hp = hidden_width(hid)
+    w1, b1 = fold_ln(f(blk.mlp.fc1.weight), f(blk.mlp.fc1.bias), f(blk.norm2.weight), f(blk.norm2.bias))
+    w1p = w1.new_zeros(hp, cp); w1p[:hid] = scatter_cols(w1, pos, cp)
+    b1p = b1.new_zeros(hp); b1p[:hid] = b1
+    w2 = f(blk.mlp.fc2.weight)                     # [C][hid]
+    w2p = w2.new_zeros(cp, hp); w2p[pos, :hid] = w2
+    return dict(
+        c=c, cp=cp, hd=hd, hp=hp,
+        wqkv=scatter_cols(wq, pos, cp).contiguous(), bqkv=bq.contiguous(),                    # [3C][Cp], [3C]
+        wproj=scatter_rows(f(blk.attn.proj.weight), pos, cp).contiguous(),                    # [Cp][C]
+        bproj=scatter_rows(f(blk.attn.proj.bias), pos, cp).contiguous(),
+        w1=w1p.contiguous(), b1=b1p.contiguous(), w2=w2p.contiguous(),
+        b2=scatter_rows(f(blk.mlp.fc2.bias), pos, cp).contiguous(),
+        table=f(blk.attn.relative_position_bias_table).contiguous(),                           # [225][heads]
+    )
+
+
+def pack_dstl_tail(dstl, c, dense_scale):
+    """LN(C) -> Linear(C, growth), written as a 32-wide slice (30 real) of the dense buffer."""
+    f = lambda t: t.detach().float()
+    cp = padded_width(c)
+    pos = channel_positions(c, dstl.tail[0].weight.device)
+    w, b = fold_ln(f(dstl.tail[1].weight), f(dstl.tail[1].bias), f(dstl.tail[0].weight), f(dstl.tail[0].bias))
+    g = w.shape[0]
+    wp = w.new_zeros(32, cp); wp[:g] = scatter_cols(w, pos, cp)
+    bp = b.new_zeros(32); bp[:g] = b
+    return dict(w=wp.contiguous(), b=bp.contiguous(), scale=float(dense_scale))
+
+
+def pack_conv(weight, bias, cin_pos, cin_width, n_pad):
+    """Conv2d weight (N, Cin, 3, 3) -> [n_pad][9][cin_width] (tap = ky*3+kx), bias -> [n_pad]."""
+    w = weight.detach().float()
+    n, cin = w.shape[0], w.shape[1]
+    wt = w.permute(0, 2, 3, 1).reshape(n, 9, cin)
+    out = w.new_zeros(n_pad, 9, cin_width)
+    out[:n, :, cin_pos] = wt
+    b = w.new_zeros(n_pad)
+    b[:n] = bias.detach().float()
+    return out.contiguous(), b.contiguous()
+
+
+def pack_upconv(weight, bias, group=FEAT_LD):
+    """UpSampler conv (4*F, F, 3, 3) + PixelShuffle(2): row order becomes (sub-pixel s = 2*dy+dx, channel c),
+    s-major, each group padded to `group` rows; reference out-channel index is c*4 + s."""
+    w = weight.detach().float()
+    f4, fin = w.shape[0], w.shape[1]
+    fo = f4 // 4
+    wt = w.permute(0, 2, 3, 1).reshape(fo, 4, 9, fin)          # [c][s][tap][cin]
+    out = w.new_zeros(4, group, 9, FEAT_LD)
+    out[:, :fo, :, :fin] = wt.permute(1, 0, 2, 3)
+    b = w.new_zeros(4, group)
+    b[:, :fo] = bias.detach().float().reshape(fo, 4).t()
+    return out.reshape(4 * group, 9, FEAT_LD).contiguous(), b.reshape(-1).contiguous()

@@ -1,0 +1,121 @@
+"""CPU stand-ins for the librdst_b200 entry points.  TEST INFRASTRUCTURE ONLY (used by `-m "not gpu"` tests).
+
+Each function restates the *contract* written in include/rdst_b200.h with plain torch ops on CPU tensors, so the
+host-side logic (weight packing, padded layouts, launch order, buffer reuse) can be checked against the golden
+vectors in a container without a GPU.  It is never importable from the product package: tests monkeypatch
+`rdst_b200._lib.call/ptr/stream_ptr` for the duration of one test.  The real kernels are checked against the
+oracle on the GPU by the `-m gpu` tests.
+"""
+import contextlib
+
+import torch
+import torch.nn.functional as F
+
+
+def _store(y, val):
+    y[:, :val.shape[1]] = val.to(y.dtype)
+
+
+def _lnhat(x, creal):
+    k = x.shape[1]
+    mean = x.sum(1, keepdim=True) / creal
+    ss = ((x - mean) ** 2).sum(1, keepdim=True) - (k - creal) * mean * mean
+    return (x - mean) * torch.rsqrt(ss.clamp_min(0) / creal + 1e-5)
+
+
+def rdst_linear_fwd(x, ldx, w, bias, resid, ldr, y, ldy, T, K, N, ln_creal, act, out_scale, dt, st):
+    assert x.stride(0) == ldx and y.stride(0) == ldy and x.shape[0] == T
+    a = x[:, :K].float()
+    if ln_creal > 0:
+        a = _lnhat(a, ln_creal)
+    assert w.shape == (N, K), (w.shape, N, K)
+    v = a @ w.t() + bias
+    if act == 1:
+        v = F.gelu(v)
+    v = v * out_scale
+    if resid is not None:
+        assert resid.stride(0) == ldr
+        v = v + resid[:, :N].float()
+    _store(y, v)
+
+
+def rdst_window_attention_fwd(qkv, ldq, table, out, ldo, B, H, W, C, heads, shift, dt, st):
+    hd = C // heads
+    t = qkv[:, :3 * C].float().reshape(B, H, W, 3 * C)
+    if shift:
+        t = torch.roll(t, (-shift, -shift), (1, 2))
+    win = t.reshape(B, H // 8, 8, W // 8, 8, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(-1, 64, 3, heads, hd)
+    q, k, v = (win[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    att = q @ k.transpose(-1, -2)
+    r = torch.arange(8)
+    ih, iw = (g.reshape(-1) for g in torch.meshgrid(r, r, indexing="ij"))
+    idx = (ih[:, None] - ih[None, :] + 7) * 15 + (iw[:, None] - iw[None, :] + 7)
+    att = att + table[idx.reshape(-1)].reshape(64, 64, heads).permute(2, 0, 1)[None]
+    if shift:
+        hs = torch.arange(H)[:, None].expand(H, W)
+        ws = torch.arange(W)[None, :].expand(H, W)
+        reg = (torch.where(hs < H - 8, 0, torch.where(hs < H - shift, 1, 2)) * 3 +
+               torch.where(ws < W - 8, 0, torch.where(ws < W - shift, 1, 2)))
+        rw = reg.reshape(H // 8, 8, W // 8, 8).permute(0, 2, 1, 3).reshape(-1, 64)
+        mask = torch.where(rw[:, :, None] != rw[:, None, :], -100.0, 0.0)          # (nW,64,64)
+        att = att + mask.repeat(B, 1, 1)[:, None]
+    o = (torch.softmax(att, -1) @ v).permute(0, 2, 1, 3).reshape(-1, 64, C)
+    o = o.reshape(B, H // 8, W // 8, 8, 8, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, C)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    _store(out, o.reshape(-1, C))
+
+
+def rdst_conv3x3_fwd(x, ldx, w, bias, resid, ldr, y, ldy, B, H, W, Cin, N, out_scale, shuffle, dt, st):
+    a = x[:, :Cin].float().reshape(B, H, W, Cin).permute(0, 3, 1, 2)
+    assert w.shape == (N, 9, Cin)
+    wt = w.reshape(N, 3, 3, Cin).permute(0, 3, 1, 2)
+    v = F.conv2d(a, wt, bias, padding=1) * out_scale           # (B,N,H,W)
+    if shuffle == 2:
+        G = N // 4
+        v = v.reshape(B, 2, 2, G, H, W).permute(0, 4, 1, 5, 2, 3).reshape(B * 2 * H * 2 * W, G)
+        _store(y, v)
+    else:
+        v = v.permute(0, 2, 3, 1).reshape(-1, N)
+        if resid is not None:
+            v = v + resid[:, :N].float()
+        _store(y, v)
+
+
+def rdst_head_fwd(img, in_scale, in_bias, w, bias, gamma, beta, feat0, ldf, dense, ldd, B, H, W, dt, st):
+    a = img.float() * in_scale + in_bias
+    f = F.conv2d(a, w.reshape(60, 1, 3, 3), bias, padding=1).permute(0, 2, 3, 1).reshape(-1, 60)
+    z = torch.zeros(f.shape[0], 4)
+    _store(feat0, torch.cat([f, z], 1))
+    _store(dense, torch.cat([F.layer_norm(f, (60,), gamma, beta, 1e-5), z], 1))
+
+
+def rdst_layernorm_fwd(x, ldx, gamma, beta, y, ldy, T, creal, out_scale, dt, st):
+    _store(y, F.layer_norm(x[:, :creal].float(), (creal,), gamma, beta, 1e-5) * out_scale)
+
+
+def rdst_last_conv_fwd(x, ldx, w, bias, out_scale, out_bias, img, B, H, W, Cin, dt, st):
+    a = x[:, :Cin].float().reshape(B, H, W, Cin).permute(0, 3, 1, 2)
+    wt = w.reshape(1, 3, 3, Cin).permute(0, 3, 1, 2)
+    img.copy_((F.conv2d(a, wt, None, padding=1) + bias) * out_scale + out_bias)
+
+
+_TABLE = {k: v for k, v in globals().items() if k.startswith("rdst_")}
+
+
+@contextlib.contextmanager
+def emulated_abi(record=None):
+    """Route rdst_b200._lib.call to the CPU stand-ins above; pointers become the tensors themselves."""
+    from rdst_b200 import _lib
+
+    def call(name, *args):
+        if record is not None:
+            record.append(name)
+        _TABLE[name](*args)
+
+    saved = (_lib.call, _lib.ptr, _lib.stream_ptr)
+    _lib.call, _lib.ptr, _lib.stream_ptr = call, (lambda t: t), (lambda: None)
+    try:
+        yield
+    finally:
+        _lib.call, _lib.ptr, _lib.stream_ptr = saved

@@ -1,0 +1,55 @@
+"""Shared test helpers: golden loading, reference-format state_dict skeletons, module construction."""
+import os
+
+import numpy as np
+import torch
+
+import rdst_oracle as O
+from synth_weights import fill_state_dict, synth_input
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLDEN = os.path.join(ROOT, "tests", "golden")
+CASES = ["e1_x4_64x64", "e1_x4_16x24_b2", "e_x4_40x32", "e1_x2_24x24", "e2blk_x4_8x8"]
+
+
+def manifest():
+    rows = []
+    with open(os.path.join(GOLDEN, "e1_state_dict_manifest.txt")) as f:
+        for line in f:
+            k, shape, dt = line.rstrip("\n").split("\t")
+            rows.append((k, eval(shape), getattr(torch, dt)))
+    return rows
+
+
+def skeleton_state_dict(blocks=8, scale=4):
+    """Reference-format state_dict (zeros) for a `blocks`-RDSTB model, built from the committed manifest."""
+    sd = {}
+    for k, shape, dt in manifest():
+        if k.startswith("body.") and int(k.split(".")[1]) >= blocks:
+            continue
+        if scale == 2 and k.startswith("tail.0.2."):
+            continue
+        sd[k] = torch.zeros(shape, dtype=dt)
+    sd["sub_mean.weight"][:] = 1
+    sd["add_mean.weight"][:] = 1
+    for k in sd:
+        if k.endswith("relative_position_index"):
+            sd[k] = O.rel_pos_index()
+        if k.endswith("attn_mask"):
+            sd[k] = O.shift_mask(24, 24)
+    return sd
+
+
+def load_case(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    blocks, scale = int(g["meta_blocks"]), int(g["meta_scale"])
+    sd = fill_state_dict(skeleton_state_dict(blocks, scale), int(g["meta_wseed"]), bool(g["meta_perturbed"]))
+    x = synth_input(tuple(int(v) for v in g["shape"]), int(g["meta_xseed"]))
+    return dict(g=g, blocks=blocks, scale=scale, sd=sd, x=x)
+
+
+def make_module(blocks=8, scale=4, precision="fp32", img_size=24):
+    import rdst_b200
+    return rdst_b200.RDSTSR(img_size=img_size, sr_scale=scale, dense_layer_depths=[2] * blocks,
+                            num_heads=[6] * blocks, window_size=[8] * blocks, rdb_depths=[3] * blocks,
+                            mlp_ratio=2., pre_norm=True, feature_last_operation=True, precision=precision)
