@@ -1,0 +1,61 @@
+"""GPU parity of the whole drop-in module against the reference goldens and the oracle."""
+import pytest
+import torch
+
+import helpers
+import rdst_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("name", helpers.CASES)
+def test_fp32_matches_reference_golden(name):
+    """north_star: fp32 mode within 1e-4 max abs of the reference output on [0,1] images."""
+    c = helpers.load_case(name)
+    m = helpers.make_module(c["blocks"], c["scale"], "fp32").cuda().eval()
+    m.load_state_dict(c["sd"], strict=True)
+    with torch.no_grad():
+        y = m(c["x"].cuda())
+    ref = torch.from_numpy(c["g"]["y"])
+    assert y.shape == ref.shape and y.dtype == torch.float32
+    assert (y.cpu() - ref).abs().max().item() < 1e-4
+
+
+@pytest.mark.parametrize("name", ["e1_x4_64x64", "e_x4_40x32", "e1_x4_16x24_b2"])
+def test_bf16_matches_reference_golden(name):
+    """north_star: bf16 mode within 1e-2 max abs and 0.01 dB PSNR of the reference fp32 output."""
+    c = helpers.load_case(name)
+    m = helpers.make_module(c["blocks"], c["scale"], "bf16").cuda().eval()
+    m.load_state_dict(c["sd"], strict=True)
+    with torch.no_grad():
+        y = m(c["x"].cuda()).cpu()
+    ref = torch.from_numpy(c["g"]["y"])
+    assert (y - ref).abs().max().item() < 1e-2
+    target = torch.rand(ref.shape, generator=torch.Generator().manual_seed(123))
+    assert abs(O.psnr(y, target) - O.psnr(ref, target)) < 0.01
+
+
+def test_fp32_oracle_at_oasis_batch():
+    """Oracle comparison at the OASIS slice shape with a small batch (sizes the oracle finishes in seconds)."""
+    c = helpers.load_case("e1_x4_64x64")
+    x = torch.rand(4, 1, 40, 32, generator=torch.Generator().manual_seed(5))
+    ref = O.forward(c["sd"], x, 4)
+    m = helpers.make_module(8, 4, "fp32").cuda().eval()
+    m.load_state_dict(c["sd"])
+    with torch.no_grad():
+        y = m(x.cuda()).cpu()
+    assert (y - ref).abs().max().item() < 1e-4
+
+
+def test_batch_independence_full_volume():
+    """Size-independent property at the BASELINE size: slices never interact, so a 176-slice batch must equal
+    the same slices run in chunks (bit-exact: same kernels, same per-slice arithmetic)."""
+    c = helpers.load_case("e1_x4_64x64")
+    m = helpers.make_module(8, 4, "fp32").cuda().eval()
+    m.load_state_dict(c["sd"])
+    x = torch.rand(176, 1, 40, 32, generator=torch.Generator().manual_seed(9)).cuda()
+    with torch.no_grad():
+        y = m(x)
+        parts = torch.cat([m(x[i:i + 44]).clone() for i in range(0, 176, 44)])
+    assert torch.equal(y, parts)
+    assert torch.isfinite(y).all()

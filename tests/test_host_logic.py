@@ -68,10 +68,12 @@ def test_errors_mirror_reference():
     import rdst_b200
     with pytest.raises(NotImplementedError):
         rdst_b200.RDSTSR(img_size=24, window_size=[4] * 4)
+    ok = dict(img_size=24, sr_scale=4, dense_layer_depths=[2] * 2, num_heads=[6] * 2, window_size=[8] * 2,
+              rdb_depths=[3] * 2, mlp_ratio=2., pre_norm=True, feature_last_operation=True)
     with pytest.raises(ValueError):
-        rdst_b200.RDSTSR(img_size=24, act_in_conv="tanh")
+        rdst_b200.RDSTSR(act_in_conv="tanh", **ok)
     with pytest.raises(ValueError):
-        rdst_b200.RDSTSR(img_size=24, mean=[0., 0.], std=[1.])
+        rdst_b200.RDSTSR(mean=[0., 0.], std=[1.], **ok)
 
 
 def test_make_rdstsr_reads_reference_paras():
