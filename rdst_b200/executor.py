@@ -32,6 +32,7 @@ class Executor:
         self._packed = None
         self._packed_key = None
         self._ws = {}
+        self.use_tc = True          # bf16 mode: tcgen05 kernels (False = CUDA-core kernels on bf16 storage)
 
     def __deepcopy__(self, memo):
         return Executor.__new__(Executor)._reset()
@@ -40,6 +41,7 @@ class Executor:
         self._module = lambda: None
         self._packed = self._packed_key = None
         self._ws = {}
+        self.use_tc = True
         return self
 
     def bound_to(self, module):
@@ -59,7 +61,7 @@ class Executor:
                 for dstl in blk.body:
                     B["dstl"].append(dict(
                         c=c,
-                        stl=[packing.pack_stl(b, c) for b in dstl.body.blocks],
+                        stl=[packing.pack_stl_tc(packing.pack_stl(b, c)) for b in dstl.body.blocks],
                         shifts=[b.shift_size for b in dstl.body.blocks],
                         tail=packing.pack_dstl_tail(dstl, c, m.dense_scale)))
                     c += packing.GROWTH
@@ -188,6 +190,10 @@ class Executor:
              B, H, W, c, packing.HEADS, shift, dt, st)
         call("rdst_linear_fwd", ptr(o), c, ptr(w["wproj"]), ptr(w["bproj"]), ptr(src), lds, ptr(x1), cp,
              T, c, cp, 0, 0, 1.0, dt, st)
+        if dt == _lib.BF16 and self.use_tc:
+            call("rdst_stl_mlp_fwd_bf16", ptr(x1), cp, ptr(dst), cp, ptr(w["w1img"]), ptr(w["w2img"]), ptr(w["b1"]),
+                 ptr(w["b2"]), T, c, 0, st)
+            return
         call("rdst_linear_fwd", ptr(x1), cp, ptr(w["w1"]), ptr(w["b1"]), None, 0, ptr(hid), hp,
              T, cp, hp, c, 1, 1.0, dt, st)
         call("rdst_linear_fwd", ptr(hid), hp, ptr(w["w2"]), ptr(w["b2"]), ptr(x1), cp, ptr(dst), cp,

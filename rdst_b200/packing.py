@@ -120,3 +120,21 @@ def pack_upconv(weight, bias, group=FEAT_LD):
     b = w.new_zeros(4, group)
     b[:, :fo] = bias.detach().float().reshape(fo, 4).t()
     return out.reshape(4 * group, 9, FEAT_LD).contiguous(), b.reshape(-1).contiguous()
+
+
+# ---------------------------------------------------------------------------------------------------------
+# tcgen05 operand images (bf16).  A K-major SWIZZLE_NONE operand with R rows and K columns is stored as
+# [K/8][R][8]: 8x16-byte core matrices, consecutive rows 16 B apart, K-chunks R*16 B apart (rdst_b200/csrc/umma.cuh).
+# ---------------------------------------------------------------------------------------------------------
+def kmajor_image(w):
+    """[R][K] fp32 -> [K/8][R][8] bf16 (flat)."""
+    r, k = w.shape
+    assert k % 8 == 0
+    return w.to(torch.bfloat16).reshape(r, k // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
+
+
+def pack_stl_tc(p):
+    """Add tensor-core operand images to a pack_stl() dict."""
+    p["w1img"] = kmajor_image(p["w1"])
+    p["w2img"] = kmajor_image(p["w2"])
+    return p

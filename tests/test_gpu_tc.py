@@ -1,0 +1,68 @@
+"""GPU parity of the tcgen05 kernels (UMMA self-test, fused MLP, fused window attention) against contract
+restatements on seeded inputs."""
+import pytest
+import torch
+
+import abi_emulator as E
+
+pytestmark = pytest.mark.gpu
+
+
+def _L():
+    from rdst_b200 import _lib
+    return _lib
+
+
+def _rand(shape, seed, scale=1.0):
+    return torch.randn(*shape, generator=torch.Generator().manual_seed(seed)) * scale
+
+
+@pytest.mark.parametrize("N,K,mn", [(16, 16, 0), (64, 64, 0), (240, 128, 0), (128, 240, 0), (32, 128, 1), (16, 128, 1),
+                                    (128, 32, 0), (256, 256, 1)])
+def test_umma_selftest(N, K, mn):
+    L = _L()
+    A = _rand((128, K), 1, 0.5).to(torch.bfloat16).cuda()
+    B = _rand((N, K), 2, 0.5).to(torch.bfloat16).cuda()
+    D = torch.zeros(128, N, device="cuda")
+    L.call("rdst_umma_selftest", L.ptr(A), L.ptr(B), L.ptr(D), N, K, mn, 0, L.stream_ptr())
+    ref = A.float() @ B.float().t()
+    assert (D - ref).abs().max().item() < 1e-3
+
+
+def _padded_input(T, c, seed):
+    from rdst_b200 import packing
+    cp = packing.padded_width(c)
+    x = torch.zeros(T, cp)
+    x[:, packing.channel_positions(c)] = _rand((T, c), seed)
+    return x.to(torch.bfloat16), cp
+
+
+@pytest.mark.parametrize("c,T", [(60, 128), (60, 1000), (90, 640), (120, 128), (120, 19 * 128 + 64)])
+@pytest.mark.parametrize("exact", [0, 1])
+def test_fused_mlp(c, T, exact):
+    from rdst_b200 import packing
+    L = _L()
+    x, cp = _padded_input(T, c, 3)
+    hp = packing.hidden_width(2 * c)
+    pos = packing.channel_positions(c)
+    w1 = torch.zeros(hp, cp); w1[:2 * c, pos] = _rand((2 * c, c), 4, 0.08)
+    b1 = torch.zeros(hp); b1[:2 * c] = _rand((2 * c,), 5, 0.1)
+    w2 = torch.zeros(cp, hp); w2[pos, :2 * c] = _rand((c, 2 * c), 6, 0.08)
+    b2 = torch.zeros(cp); b2[pos] = _rand((c,), 7, 0.1)
+    w1b, w2b = w1.to(torch.bfloat16).float(), w2.to(torch.bfloat16).float()
+    # contract restatement (fp32 math on the same bf16-rounded weights / inputs)
+    hid = torch.zeros(T, hp)
+    E.rdst_linear_fwd(x, cp, w1b, b1, None, 0, hid, hp, T, cp, hp, c, 1, 1.0, 0, None)
+    ref = torch.zeros(T, cp)
+    E.rdst_linear_fwd(hid, hp, w2b, b2, x, cp, ref, cp, T, hp, cp, 0, 0, 1.0, 0, None)
+    xd = x.cuda()
+    yd = torch.full((T, cp), float("nan"), dtype=torch.bfloat16, device="cuda")
+    dev = [packing.kmajor_image(w1).cuda(), packing.kmajor_image(w2).cuda(), b1.cuda(), b2.cuda()]
+    L.call("rdst_stl_mlp_fwd_bf16", L.ptr(xd), cp, L.ptr(yd), cp, L.ptr(dev[0]), L.ptr(dev[1]), L.ptr(dev[2]),
+           L.ptr(dev[3]), T, c, exact, L.stream_ptr())
+    y = yd.cpu().float()
+    assert torch.isfinite(y).all()
+    err = (y - ref).abs()
+    assert err.max().item() < 6e-2 and err.mean().item() < 6e-3, (err.max().item(), err.mean().item())
+    padmask = torch.ones(cp, dtype=torch.bool); padmask[pos] = False
+    assert (y[:, padmask] == 0).all()            # pads stay exactly zero
