@@ -112,6 +112,20 @@ int rdst_last_conv_fwd(const void* x, int64_t ldx, const float* w, float bias, f
 int rdst_stl_mlp_fwd_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w1img, const void* w2img,
                           const float* b1, const float* b2, int64_t T, int C, int exact_gelu, void* stream);
 
+/* Fused shifted-window attention block:
+ *   Y[t] = X[t] + proj( softmax_j( q_i.k_j + bias(i,j) + mask(i,j) ) v_j ),  [q|k|v] = qkv(LNhat(X)), bf16 storage,
+ * over 8x8 windows of a (B,H,W) token grid with cyclic shift `shift` in {0,4}; C in {60,90,120}, 6 heads.
+ * The roll/window_partition/window_reverse/roll of the reference are index arithmetic in the gather/scatter; the
+ * {0,-100} mask is evaluated in closed form; scores/probabilities live only in TMEM/shared memory.
+ *   wqkv_img : 6 per-head K-major operand images [Cp/8][NH][8] bf16, rows = q_h | k_h | v_h | zero pad
+ *              (NH = 32/48/64), LN gamma, head_dim^-0.5 and log2(e) folded into the q rows
+ *   bqkv     : [6][NH] fp32 (LN beta folded);  wproj_img : [KPROJ/8][Cp][8] bf16 with K index = head*HDO + d
+ *              (HDO = 16/16/20, KPROJ = 96/96/128);  bproj : [Cp];  table : [6][225] fp32 = bias table^T * log2(e)
+ * Replaces swin_transformer_sr.py:239-271 (block) and :110-141 (WindowAttention).  X and Y must not alias. */
+int rdst_stl_attn_fwd_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const void* wqkv_img,
+                           const void* wproj_img, const float* bqkv, const float* bproj, const float* table,
+                           int B, int H, int W, int C, int shift, void* stream);
+
 /* Self-test of the UMMA plumbing: D[M=128][N] = A[128][K] . B[N][K]^T with bf16 inputs, fp32 output.
  * b_mn_major != 0 feeds B from an MN-major shared-memory image.  Used by tests/ only. */
 int rdst_umma_selftest(const void* a_bf16, const void* b_bf16, float* d, int N, int K, int b_mn_major,

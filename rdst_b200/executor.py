@@ -184,16 +184,18 @@ class Executor:
         c, cp, hp = w["c"], w["cp"], w["hp"]
         v = lambda buf, ld: buf.view(-1)[:T * ld].view(T, ld)       # compact [T][ld] view of a max-sized buffer
         qkv, o, x1, hid = v(ws["QKV"], 3 * c), v(ws["O"], c), v(ws["X1"], cp), v(ws["HID"], hp)
+        if dt == _lib.BF16 and self.use_tc:
+            call("rdst_stl_attn_fwd_bf16", ptr(src), lds, ptr(x1), cp, ptr(w["wqkv_img"]), ptr(w["wproj_img"]),
+                 ptr(w["bqkv_tc"]), ptr(w["bproj"]), ptr(w["table_tc"]), B, H, W, c, shift, st)
+            call("rdst_stl_mlp_fwd_bf16", ptr(x1), cp, ptr(dst), cp, ptr(w["w1img"]), ptr(w["w2img"]), ptr(w["b1"]),
+                 ptr(w["b2"]), T, c, 0, st)
+            return
         call("rdst_linear_fwd", ptr(src), lds, ptr(w["wqkv"]), ptr(w["bqkv"]), None, 0, ptr(qkv), 3 * c,
              T, cp, 3 * c, c, 0, 1.0, dt, st)
         call("rdst_window_attention_fwd", ptr(qkv), 3 * c, ptr(w["table"]), ptr(o), c,
              B, H, W, c, packing.HEADS, shift, dt, st)
         call("rdst_linear_fwd", ptr(o), c, ptr(w["wproj"]), ptr(w["bproj"]), ptr(src), lds, ptr(x1), cp,
              T, c, cp, 0, 0, 1.0, dt, st)
-        if dt == _lib.BF16 and self.use_tc:
-            call("rdst_stl_mlp_fwd_bf16", ptr(x1), cp, ptr(dst), cp, ptr(w["w1img"]), ptr(w["w2img"]), ptr(w["b1"]),
-                 ptr(w["b2"]), T, c, 0, st)
-            return
         call("rdst_linear_fwd", ptr(x1), cp, ptr(w["w1"]), ptr(w["b1"]), None, 0, ptr(hid), hp,
              T, cp, hp, c, 1, 1.0, dt, st)
         call("rdst_linear_fwd", ptr(hid), hp, ptr(w["w2"]), ptr(w["b2"]), ptr(x1), cp, ptr(dst), cp,

@@ -133,8 +133,43 @@ def kmajor_image(w):
     return w.to(torch.bfloat16).reshape(r, k // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
 
 
+LOG2E = 1.4426950408889634
+
+
+def attn_shapes(c):
+    hd = c // HEADS
+    nh = (3 * hd + 15) // 16 * 16
+    hdo = 20 if hd == 20 else 16
+    kproj = (HEADS * hdo + 15) // 16 * 16
+    return hd, nh, hdo, kproj
+
+
+def pack_attn_tc(wqkv, bqkv, wproj, bproj, table, c):
+    """wqkv [3C][Cp] / bqkv [3C] (LN-folded, q rows scaled), wproj [Cp][C], bproj [Cp], table [225][heads]
+    -> operand images of rdst_stl_attn_fwd_bf16 (include/rdst_b200.h)."""
+    hd, nh, hdo, kproj = attn_shapes(c)
+    cp = wqkv.shape[1]
+    imgs, biases = [], []
+    for h in range(HEADS):
+        wh = wqkv.new_zeros(nh, cp)
+        bh = bqkv.new_zeros(nh)
+        for s in range(3):                                   # q | k | v rows of this head
+            rows = slice(s * c + h * hd, s * c + (h + 1) * hd)
+            f = LOG2E if s == 0 else 1.0                     # softmax is evaluated with exp2
+            wh[s * hd:(s + 1) * hd] = wqkv[rows] * f
+            bh[s * hd:(s + 1) * hd] = bqkv[rows] * f
+        imgs.append(kmajor_image(wh))
+        biases.append(bh)
+    wp = wproj.new_zeros(cp, kproj)
+    for h in range(HEADS):
+        wp[:, h * hdo:h * hdo + hd] = wproj[:, h * hd:(h + 1) * hd]
+    return dict(wqkv_img=torch.cat(imgs).contiguous(), bqkv_tc=torch.cat(biases).contiguous(),
+                wproj_img=kmajor_image(wp), table_tc=(table.t() * LOG2E).contiguous())
+
+
 def pack_stl_tc(p):
     """Add tensor-core operand images to a pack_stl() dict."""
     p["w1img"] = kmajor_image(p["w1"])
     p["w2img"] = kmajor_image(p["w2"])
+    p.update(pack_attn_tc(p["wqkv"], p["bqkv"], p["wproj"], p["bproj"], p["table"], p["c"]))
     return p

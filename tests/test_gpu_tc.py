@@ -66,3 +66,41 @@ def test_fused_mlp(c, T, exact):
     assert err.max().item() < 6e-2 and err.mean().item() < 6e-3, (err.max().item(), err.mean().item())
     padmask = torch.ones(cp, dtype=torch.bool); padmask[pos] = False
     assert (y[:, padmask] == 0).all()            # pads stay exactly zero
+
+
+@pytest.mark.parametrize("c,B,H,W,shift", [(60, 2, 16, 24, 0), (60, 2, 16, 24, 4), (90, 1, 24, 24, 4), (120, 1, 8, 8, 4),
+                                            (120, 3, 40, 32, 4), (120, 3, 40, 32, 0), (90, 5, 8, 16, 0)])
+def test_fused_attention(c, B, H, W, shift):
+    from rdst_b200 import packing
+    L = _L()
+    T = B * H * W
+    x, cp = _padded_input(T, c, 11)
+    pos = packing.channel_positions(c)
+    hd = c // 6
+    wqkv = torch.zeros(3 * c, cp); wqkv[:, pos] = _rand((3 * c, c), 12, 0.12)
+    bqkv = _rand((3 * c,), 13, 0.2)
+    wqkv[:c] *= hd ** -0.5; bqkv[:c] *= hd ** -0.5
+    wproj = torch.zeros(cp, c); wproj[pos] = _rand((c, c), 14, 0.1)
+    bproj = torch.zeros(cp); bproj[pos] = _rand((c,), 15, 0.1)
+    table = _rand((225, 6), 16, 0.7)
+    rb = lambda t: t.to(torch.bfloat16).float()
+    # contract restatement on bf16-rounded weights
+    qkv = torch.zeros(T, 3 * c)
+    E.rdst_linear_fwd(x, cp, rb(wqkv), bqkv, None, 0, qkv, 3 * c, T, cp, 3 * c, c, 0, 1.0, 0, None)
+    o = torch.zeros(T, c)
+    E.rdst_window_attention_fwd(qkv, 3 * c, table, o, c, B, H, W, c, 6, shift, 0, None)
+    ref = torch.zeros(T, cp)
+    E.rdst_linear_fwd(o, c, rb(wproj), bproj, x, cp, ref, cp, T, c, cp, 0, 0, 1.0, 0, None)
+    pk = packing.pack_attn_tc(wqkv, bqkv, wproj, bproj, table, c)
+    xd = x.cuda()
+    yd = torch.full((T, cp), float("nan"), dtype=torch.bfloat16, device="cuda")
+    d = {k: v.cuda() for k, v in pk.items()}
+    bp = bproj.cuda()
+    L.call("rdst_stl_attn_fwd_bf16", L.ptr(xd), cp, L.ptr(yd), cp, L.ptr(d["wqkv_img"]), L.ptr(d["wproj_img"]),
+           L.ptr(d["bqkv_tc"]), L.ptr(bp), L.ptr(d["table_tc"]), B, H, W, c, shift, L.stream_ptr())
+    y = yd.cpu().float()
+    assert torch.isfinite(y).all()
+    err = (y - ref).abs()
+    assert err.max().item() < 6e-2 and err.mean().item() < 6e-3, (err.max().item(), err.mean().item())
+    padmask = torch.ones(cp, dtype=torch.bool); padmask[pos] = False
+    assert (y[:, padmask] == 0).all()
