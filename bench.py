@@ -1,0 +1,291 @@
+"""bench.py -- RDST-E1 x4 super-resolution throughput on B200 (HR output megapixels / second).
+
+Workload (BASELINE.json configs[1] / SURVEY 8d cfg2): RDST-E1 x4, bf16 mode, one synthetic OASIS-shaped volume
+per GPU per step = 176 LR slices of 1x40x32 -> 176 x 160x128 HR pixels (3.60 Mpix), random-init weights.
+Multi-GPU: every rank super-resolves its own volume (slices are independent; no data-path collective) => weak scaling.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
+
+Prints ONE JSON line (rank 0).  `value` times the forward with inputs resident in HBM; `e2e` times the module's
+public call with pinned HOST input and a device->host read of the HR result inside the timed region.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    if _p not in sys.path:
+        sys.path.insert(0, _p)
+
+import torch  # noqa: E402
+
+SLICES, LR_H, LR_W, SCALE = 176, 40, 32, 4
+HR_PIX_PER_VOLUME = SLICES * LR_H * SCALE * LR_W * SCALE
+FLOP_PER_LR_PX = 10_592_280                       # algorithmic, SURVEY 8(d)
+ATTN_FLOP_PER_WINDOW = {60: 2_826_240, 90: 5_621_760, 120: 9_338_880}   # 512 C^2 + 16384 C
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return float(p["bf16_tflops_sustained"]), float(p["hbm_gbs"]), "measured"
+    except Exception:  # noqa: BLE001
+        return 1400.0, 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled while the timed region runs."""
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+                 "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:  # noqa: BLE001
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:  # noqa: BLE001
+            self.proc.kill()
+        sm, names, reasons = [], ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 6:
+                    continue
+                sm.append(float(f[0]))
+                out["sm_max_mhz"] = float(f[1])
+                for n, v in zip(names, f[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            os.unlink(self.path)
+        except Exception:  # noqa: BLE001
+            pass
+        if sm:
+            sm.sort()
+            out["sm_mhz"] = sm[len(sm) // 2]
+        out["reasons"] = sorted(reasons)
+        return out
+
+
+def _dist_setup(n_gpus):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return world, rank, local
+
+
+def cpu_reference_run(sd, steps, warmup, sample_slices):
+    """Times the CPU restatement of the reference (oracle, PyTorch CPU fp32 -- the same aten ops the reference
+    module executes) on a bounded sample of the workload.  Returns (Mpix/s, seconds per step, threads)."""
+    import rdst_oracle as O
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    x = torch.rand(sample_slices, 1, LR_H, LR_W, generator=torch.Generator().manual_seed(1))
+    with torch.no_grad():
+        for _ in range(warmup):
+            O.forward(sd, x, SCALE)
+        ts = []
+        for _ in range(steps):
+            t0 = time.perf_counter()
+            O.forward(sd, x, SCALE)
+            ts.append(time.perf_counter() - t0)
+    sec = sum(ts) / len(ts)
+    return sample_slices * LR_H * SCALE * LR_W * SCALE / sec / 1e6, sec, threads
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+
+    import helpers
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    config = {"workload": f"RDST-E1 x4 inference, {SLICES} synthetic OASIS LR slices 1x{LR_H}x{LR_W} per GPU per step "
+                          f"(-> {SLICES}x{LR_H * SCALE}x{LR_W * SCALE} HR), random-init weights",
+              "slices_per_gpu": SLICES, "lr_hw": [LR_H, LR_W], "sr_scale": SCALE,
+              "parallelism": f"slice-sharded x{max(world, 1)} (no collective)", "precision": args.precision,
+              "l2": "256 MiB buffer written between timed steps (L2 flush)"}
+
+    # ------------------------------------------------------------------ reference arm (CPU)
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        m = helpers.make_module(8, SCALE, "fp32")
+        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        sample = 8
+        steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
+        val, sec, threads = cpu_reference_run(sd, steps, warm, sample)
+        line = {"impl": "reference", "metric": "HR output Mpix/s (RDST-E1 x4 inference)", "value": round(val, 4),
+                "unit": "Mpix/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+                "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic", "config": config,
+                "cpu_baseline": {"value": round(val, 4), "unit": "Mpix/s", "cores": threads, "kind": "port",
+                                 "sample": f"{sample} of {SLICES} slices per step (oracle = PyTorch-CPU restatement of "
+                                           "the reference module; the Python reference itself cannot travel to the box)"},
+                "e2e": {"value": round(val, 4), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    # ------------------------------------------------------------------ our arm (GPU)
+    world, rank, local = _dist_setup(args.gpus)
+    dev = torch.device("cuda", local)
+    torch.cuda.set_device(dev)
+    from rdst_b200 import executor as ex_mod
+    torch.manual_seed(0)
+    m = helpers.make_module(8, SCALE, args.precision).to(dev).eval()
+    x_host = torch.rand(SLICES, 1, LR_H, LR_W, generator=torch.Generator().manual_seed(1 + rank)).pin_memory()
+    x_dev = x_host.to(dev)
+    y_host = torch.empty(SLICES, 1, LR_H * SCALE, LR_W * SCALE).pin_memory()
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    launches = [0]
+    ktime = {"events": [], "on": False}
+    TOP = "rdst_stl_attn_fwd_bf16"
+    orig_call = ex_mod.call
+
+    def counting_call(name, *a):
+        launches[0] += 1
+        if ktime["on"] and name == TOP:
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            orig_call(name, *a)
+            e1.record()
+            ktime["events"].append((e0, e1, a[12]))          # a[12] = C of this launch
+        else:
+            orig_call(name, *a)
+
+    ex_mod.call = counting_call
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def run(step_fn, steps):
+        evs = []
+        for _ in range(steps):
+            flush.fill_(1)
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            step_fn()
+            e1.record()
+            evs.append((e0, e1))
+        torch.cuda.synchronize()
+        return sum(a.elapsed_time(b) for a, b in evs)          # ms over all steps (device time, flush excluded)
+
+    def step_resident():
+        with torch.no_grad():
+            m(x_dev)
+
+    def step_e2e():
+        with torch.no_grad():
+            xd = x_host.to(dev, non_blocking=True)
+            y = m(xd)
+            y_host.copy_(y, non_blocking=True)
+
+    with torch.no_grad():
+        for _ in range(args.warmup):
+            step_resident()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    launches[0] = 0
+    ktime["on"] = args.precision == "bf16"
+    ms_total = run(step_resident, args.steps)
+    ktime["on"] = False
+    n_launch = launches[0]
+    barrier()
+    clocks = sampler.stop()
+    for _ in range(2):
+        step_e2e()
+    barrier()
+    ms_e2e = run(step_e2e, args.steps)
+    barrier()
+
+    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    if world > 1:
+        import torch.distributed as dist
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+        return
+
+    ms_step = ms_total / args.steps
+    value = world * HR_PIX_PER_VOLUME / (ms_step * 1e-3) / 1e6
+    e2e_val = world * HR_PIX_PER_VOLUME / (ms_e2e / args.steps * 1e-3) / 1e6
+    tf_peak, hbm_peak, which = _peaks()
+    roof = None
+    if ktime["events"]:
+        # dominant tensor-core kernel: the fused window-attention kernel, all three widths pooled
+        nwin = SLICES * (LR_H // 8) * (LR_W // 8)
+        tot_ms = sum(a.elapsed_time(b) for a, b, _ in ktime["events"])
+        tot_flop = sum(ATTN_FLOP_PER_WINDOW[c] * nwin for _, _, c in ktime["events"])
+        ach = tot_flop / (tot_ms * 1e-3) / 1e12
+        roof = {"bound": "tensor", "kernel": "stl_attn_kernel<60|90|120> (fused LN+QKV+QK^T+softmax+PV+proj)",
+                "achieved": round(ach, 2), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(ach / tf_peak, 4),
+                "traffic": None, "peak_source": f"{which} (bf16_tflops_sustained)",
+                "launches_timed": len(ktime["events"]), "avg_launch_us": round(tot_ms * 1e3 / len(ktime["events"]), 2),
+                "share_of_step": round(tot_ms / ms_total, 4)}
+    whole = FLOP_PER_LR_PX * SLICES * LR_H * LR_W * world / (ms_step * 1e-3) / 1e12
+    line = {"metric": "HR output Mpix/s (RDST-E1 x4 inference)", "value": round(value, 2), "unit": "Mpix/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
+            "clocks": clocks, "gpu_launches": n_launch,
+            "e2e": {"value": round(e2e_val, 2), "unit": "Mpix/s", "h2d_bytes_per_step": x_host.numel() * 4,
+                    "d2h_bytes_per_step": y_host.numel() * 4},
+            "whole_net_tflops": round(whole, 2), "whole_net_frac_of_tensor_peak": round(whole / tf_peak / world, 4)}
+    if roof:
+        line["roofline"] = roof
+    if world == 1 and not args.no_cpu_baseline:
+        sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+        val, sec, threads = cpu_reference_run(sd, 3, 1, 8)
+        line["cpu_baseline"] = {"value": round(val, 4), "unit": "Mpix/s", "cores": threads, "kind": "port",
+                                "sample": f"8 of {SLICES} slices per step, 3 steps, {sec:.2f} s/step "
+                                          "(oracle = PyTorch-CPU restatement of the reference module)"}
+    print(json.dumps(line))
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
