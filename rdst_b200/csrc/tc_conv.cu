@@ -1,0 +1,224 @@
+// 3x3 convolution on token-major (NHWC, bf16) data as an implicit GEMM on tcgen05, without im2col:
+// a tile of TH x TW output pixels plus its 1-pixel halo is staged ONCE in shared memory as a K-major UMMA
+// operand image whose "rows" are halo positions in raster order (pitch LW = TW+2).  Because consecutive rows of a
+// SWIZZLE_NONE image are 16 bytes apart, the A operand of filter tap (dy,dx) is the same image with the descriptor
+// start address advanced by (dy*LW+dx)*16 bytes -- nine taps x Cin/16 k-steps accumulate into one TMEM tile.
+// Rows that fall on halo columns are computed and discarded ((TH-1)*LW+TW <= 128).
+// The weights of one N-slice (all 9 taps) stay resident in shared memory for the whole persistent CTA.
+// Epilogue: +bias, *scale, +residual, and for the up-sampler nn.PixelShuffle(2) folded into the store address.
+// Replaces RDSTB.conv (LFF, reference rdst_variations.py:444-445), conv_after_body (:1349-1350) and the UpSampler
+// convs + PixelShuffle (networks/common.py:129-132).
+#include "common.cuh"
+#include "umma.cuh"
+
+namespace rdst {
+using namespace umma;
+
+__device__ __forceinline__ uint32_t cpk2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 cup2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+
+constexpr int CONV_NP_MAX = 200;      // staged halo positions (2*LW+2+128 for TW<=32)
+
+struct ConvGeom {
+  int B, H, W, TW, TH, LW, NP, ntx, nty;
+  int shuffle;
+  float out_scale;
+};
+
+template <int CIN, int NT>
+struct ConvCfg {
+  static constexpr int NCH = CIN / 8;
+  static constexpr int W_BYTES = 9 * CIN * NT * 2;
+  static constexpr int A_BYTES = NCH * CONV_NP_MAX * 16;
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_A = W_BYTES;
+  static constexpr int OFF_BIAS = OFF_A + A_BYTES;
+  static constexpr int SMEM = OFF_BIAS + NT * 4;
+  static_assert(NCH % 4 == 0 && (NT == 32 || NT == 64), "shape");
+};
+
+template <int CIN, int NT>
+__global__ void __launch_bounds__(256)
+conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_t* __restrict__ wimg,
+                  const float* __restrict__ bias, const __nv_bfloat16* __restrict__ R, int64_t ldr,
+                  __nv_bfloat16* __restrict__ Y, int64_t ldy, ConvGeom g) {
+  using K = ConvCfg<CIN, NT>;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int slice = blockIdx.y;
+  uint8_t* sW = smem + K::OFF_W;
+  uint8_t* sA = smem + K::OFF_A;
+  float* sBias = reinterpret_cast<float*>(smem + K::OFF_BIAS);
+
+  if (warp == 0) tmem_alloc<64>(&tmem_base_s);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  {
+    const uint8_t* src = wimg + (size_t)slice * K::W_BYTES;
+    for (int i = tid; i < K::W_BYTES / 16; i += 256)
+      *reinterpret_cast<uint4*>(sW + (size_t)i * 16) = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    for (int i = tid; i < K::A_BYTES / 16; i += 256) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < NT; i += 256) sBias[i] = bias[slice * NT + i];
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
+  const uint32_t lboA = (uint32_t)g.NP * 16;
+  const int nps = (g.TH + 2) * g.LW;                       // halo positions actually staged
+  const int row = tid & 127, part = tid >> 7;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int64_t ntiles = (int64_t)g.B * g.nty * g.ntx;
+  uint32_t parity = 0;
+
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
+    const int b = (int)(tile / (g.nty * g.ntx));
+    const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
+    const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
+    // ---------------- stage halo tile as K-major image ----------------
+#pragma unroll 1
+    for (int pg = warp; pg * 8 < nps; pg += 8) {
+      const int pos = pg * 8 + (lane & 7);
+      const int hy = pos / g.LW, hx = pos - hy * g.LW;
+      const int y = y0 - 1 + hy, x = x0 - 1 + hx;
+      const bool ok = pos < nps && y >= 0 && y < g.H && x >= 0 && x < g.W;
+      const __nv_bfloat16* src = X + (((int64_t)b * g.H + y) * g.W + x) * ldx;
+#pragma unroll
+      for (int j = 0; j < K::NCH / 4; ++j) {
+        const int c = (lane >> 3) + 4 * j;
+        const uint4 v = ok ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
+        *reinterpret_cast<uint4*>(sA + (size_t)c * lboA + pos * 16) = v;
+      }
+    }
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (tid == 0) {
+      fence_after_sync();
+      constexpr uint32_t idesc = make_idesc_bf16(128, NT, false, false);
+#pragma unroll 1
+      for (int tap = 0; tap < 9; ++tap) {
+        const uint32_t a0 = aA + (uint32_t)((tap / 3) * g.LW + (tap % 3)) * 16;
+        const uint32_t w0 = aW + tap * (CIN * NT * 2);
+#pragma unroll
+        for (int ks = 0; ks < CIN / 16; ++ks)
+          mma_bf16_ss(tmem, make_smem_desc(a0 + ks * 2 * lboA, lboA, 128), make_smem_desc(w0 + ks * 2 * (NT * 16), NT * 16, 128),
+                      idesc, (tap | ks) > 0);
+      }
+      commit(&bar);
+    }
+    mbar_wait(&bar, parity);
+    fence_after_sync();
+    // ---------------- epilogue ----------------
+    {
+      const int oy = row / g.LW, ox = row - oy * g.LW;
+      const int y = y0 + oy, x = x0 + ox;
+      const bool ok = ox < g.TW && oy < g.TH && y < g.H && x < g.W;
+      constexpr int NC = NT / 2;                            // columns per thread
+      const int cb = part * NC;
+      int64_t tout;
+      if (g.shuffle) tout = ((int64_t)(b * 2 * g.H + 2 * y + (slice >> 1))) * (2 * g.W) + 2 * x + (slice & 1);
+      else tout = ((int64_t)b * g.H + y) * g.W + x;
+      const int ncol0 = (g.shuffle ? 0 : slice * NT) + cb;  // first output channel written by this thread
+#pragma unroll
+      for (int c0 = 0; c0 < NC; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(lane_addr + cb + c0, v);
+        wait_ld();
+        if (ok) {
+          float f[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = (__uint_as_float(v[j]) + sBias[cb + c0 + j]) * g.out_scale;
+          if (R != nullptr) {
+            const uint4* rp = reinterpret_cast<const uint4*>(R + tout * ldr + ncol0 + c0);
+            const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+            const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float2 t = cup2(rw[j]); f[2 * j] += t.x; f[2 * j + 1] += t.y; }
+          }
+          uint4* yp = reinterpret_cast<uint4*>(Y + tout * ldy + ncol0 + c0);
+          yp[0] = make_uint4(cpk2(f[0], f[1]), cpk2(f[2], f[3]), cpk2(f[4], f[5]), cpk2(f[6], f[7]));
+          yp[1] = make_uint4(cpk2(f[8], f[9]), cpk2(f[10], f[11]), cpk2(f[12], f[13]), cpk2(f[14], f[15]));
+        }
+      }
+    }
+    fence_before_sync();
+    __syncthreads();          // TMEM tile and the staged image are reused by the next tile
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+template <int CIN, int NT>
+static int launch_conv(const void* x, int64_t ldx, const void* wimg, const float* bias, const void* r, int64_t ldr,
+                       void* y, int64_t ldy, ConvGeom g, int nslices, int sms, cudaStream_t st) {
+  using K = ConvCfg<CIN, NT>;
+  auto k = conv3x3_tc_kernel<CIN, NT>;
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+  if (e != cudaSuccess) { set_error("rdst_conv3x3_fwd_bf16_tc: smem attr (%d B): %s", K::SMEM, cudaGetErrorString(e)); return RDST_E_CUDA; }
+  int occ = 1;
+  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 256, K::SMEM);
+  if (occ < 1) occ = 1;
+  if (occ > 4) occ = 4;
+  const int64_t ntiles = (int64_t)g.B * g.nty * g.ntx;
+  int64_t gx = (int64_t)occ * sms / nslices;
+  if (gx < 1) gx = 1;
+  if (gx > ntiles) gx = ntiles;
+  dim3 grid((unsigned)gx, (unsigned)nslices);
+  k<<<grid, 256, K::SMEM, st>>>((const __nv_bfloat16*)x, ldx, (const uint8_t*)wimg, bias, (const __nv_bfloat16*)r, ldr,
+                                (__nv_bfloat16*)y, ldy, g);
+  return RDST_OK;
+}
+
+}  // namespace rdst
+
+extern "C" int rdst_conv3x3_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, const float* bias,
+                                        const void* resid, int64_t ldr, void* y, int64_t ldy, int B, int H, int W,
+                                        int Cin, int N, float out_scale, int shuffle, void* stream) {
+  using namespace rdst;
+  RDST_REQUIRE(x && wimg && bias && y, "rdst_conv3x3_fwd_bf16_tc: null pointer");
+  RDST_REQUIRE(B >= 0 && H > 0 && W > 0, "rdst_conv3x3_fwd_bf16_tc: bad shape");
+  RDST_REQUIRE((Cin == 160 && N == 64) || (Cin == 64 && (N == 64 || N == 256)),
+               "rdst_conv3x3_fwd_bf16_tc: supported (Cin,N) = (160,64), (64,64), (64,256); got (%d,%d)", Cin, N);
+  RDST_REQUIRE(shuffle == 0 || (shuffle == 2 && N == 256 && resid == nullptr),
+               "rdst_conv3x3_fwd_bf16_tc: shuffle=2 needs N=256 and no residual");
+  RDST_REQUIRE(!(N == 256 && shuffle == 0), "rdst_conv3x3_fwd_bf16_tc: N=256 is only supported with shuffle=2");
+  RDST_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ldx % 8 == 0 && ldy % 8 == 0 &&
+                   (resid == nullptr || (((uintptr_t)resid % 16 == 0) && ldr % 8 == 0)),
+               "rdst_conv3x3_fwd_bf16_tc: pointers must be 16-byte aligned, strides multiples of 8 elements");
+  RDST_REQUIRE(ldx >= Cin, "rdst_conv3x3_fwd_bf16_tc: ldx < Cin");
+  if (B == 0) return RDST_OK;
+  ConvGeom g{};
+  g.B = B; g.H = H; g.W = W; g.shuffle = shuffle; g.out_scale = out_scale;
+  // tile shape: TW in {8,16,24,32}, TH = largest with (TH-1)*(TW+2)+TW <= 128; pick the fewest tiles
+  int64_t best = -1;
+  for (int tw = 8; tw <= 32; tw += 8) {
+    const int th = (128 - tw) / (tw + 2) + 1;
+    const int64_t nt = (int64_t)((W + tw - 1) / tw) * ((H + th - 1) / th);
+    if (best < 0 || nt < best) { best = nt; g.TW = tw; g.TH = th; }
+  }
+  g.LW = g.TW + 2;
+  g.NP = (2 * g.LW + 2 + 128 + 7) / 8 * 8;
+  g.ntx = (W + g.TW - 1) / g.TW;
+  g.nty = (H + g.TH - 1) / g.TH;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  if (Cin == 160) rc = launch_conv<160, 32>(x, ldx, wimg, bias, resid, ldr, y, ldy, g, 2, sms, st);
+  else rc = launch_conv<64, 64>(x, ldx, wimg, bias, resid, ldr, y, ldy, g, N / 64, sms, st);
+  if (rc) return rc;
+  RDST_CHECK_LAUNCH("rdst_conv3x3_fwd_bf16_tc");
+  return RDST_OK;
+}

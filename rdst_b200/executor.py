@@ -67,6 +67,7 @@ class Executor:
                     c += packing.GROWTH
                 pos = packing.channel_positions(c, device)
                 B["lff_w"], B["lff_b"] = packing.pack_conv(blk.conv.weight, blk.conv.bias, pos, packing.DENSE_LD, 64)
+                B["lff_img"] = packing.conv_tc_image(B["lff_w"])
                 P["blocks"].append(B)
             f = lambda t: t.detach().float().contiguous()
             id60 = torch.arange(60, device=device)
@@ -76,6 +77,8 @@ class Executor:
             P["norm_g"], P["norm_b"] = f(m.norm.weight), f(m.norm.bias)
             P["cab_w"], P["cab_b"] = packing.pack_conv(m.conv_after_body.weight, m.conv_after_body.bias, id60, 64, 64)
             P["up"] = [packing.pack_upconv(l.weight, l.bias) for l in m.tail[0] if isinstance(l, torch.nn.Conv2d)]
+            P["cab_img"] = packing.conv_tc_image(P["cab_w"])
+            P["up_img"] = [packing.conv_tc_image(w) for w, _ in P["up"]]
             last = m.tail[1]
             lw = last.weight.new_zeros(9, 64, dtype=torch.float32)
             lw[:, :60] = last.weight.detach().float()[0].permute(1, 2, 0).reshape(9, 60)
@@ -156,27 +159,34 @@ class Executor:
                 off = 64 + 32 * j
                 call("rdst_linear_fwd", ptr(src), lds, ptr(t["w"]), ptr(t["b"]), None, 0,
                      ptr(D[cur][:, off:]), 160, T, ds["stl"][0]["cp"], 32, ds["c"], 0, t["scale"], dt, st)
-            call("rdst_conv3x3_fwd", ptr(D[cur]), 160, ptr(blk["lff_w"]), ptr(blk["lff_b"]), ptr(D[cur]), 160,
-                 ptr(D[1 - cur]), 160, B, H, W, 160, 64, float(m.rdb_residual_scale), 0, dt, st)
+            self._conv(D[cur], 160, blk["lff_w"], blk["lff_img"], blk["lff_b"], D[cur], 160, D[1 - cur], 160,
+                       B, H, W, 160, 64, float(m.rdb_residual_scale), 0, dt, st)
             cur = 1 - cur
         call("rdst_layernorm_fwd", ptr(D[cur]), 160, ptr(P["norm_g"]), ptr(P["norm_b"]), ptr(ws["FN"]), 64,
              T, 60, float(m.global_res_scale), dt, st)
         if m.feature_last_operation:
-            call("rdst_conv3x3_fwd", ptr(ws["FN"]), 64, ptr(P["cab_w"]), ptr(P["cab_b"]), ptr(ws["F0"]), 64,
-                 ptr(ws["F1"]), 64, B, H, W, 64, 64, 1.0, 0, dt, st)
+            self._conv(ws["FN"], 64, P["cab_w"], P["cab_img"], P["cab_b"], ws["F0"], 64, ws["F1"], 64,
+                       B, H, W, 64, 64, 1.0, 0, dt, st)
             feat = ws["F1"]
         else:
             feat = ws["F1"]
             torch.add(ws["FN"], ws["F0"], out=feat)
         h, w_ = H, W
-        for (uw, ub), buf in zip(P["up"], ws["UP"]):
-            call("rdst_conv3x3_fwd", ptr(feat), 64, ptr(uw), ptr(ub), None, 0, ptr(buf), 64,
-                 B, h, w_, 64, 256, 1.0, 2, dt, st)
+        for (uw, ub), uimg, buf in zip(P["up"], P["up_img"], ws["UP"]):
+            self._conv(feat, 64, uw, uimg, ub, None, 0, buf, 64, B, h, w_, 64, 256, 1.0, 2, dt, st)
             feat, h, w_ = buf, 2 * h, 2 * w_
         out = torch.empty(B, 1, h, w_, dtype=torch.float32, device=dev)
         call("rdst_last_conv_fwd", ptr(feat), 64, ptr(P["last_w"]), P["last_b"], P["out_scale"], P["out_bias"],
              ptr(out), B, h, w_, 64, dt, st)
         return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+    def _conv(self, x, ldx, w, wimg, b, r, ldr, y, ldy, B, H, W, cin, n, scale, shuffle, dt, st):
+        if dt == _lib.BF16 and self.use_tc:
+            call("rdst_conv3x3_fwd_bf16_tc", ptr(x), ldx, ptr(wimg), ptr(b), ptr(r), ldr, ptr(y), ldy,
+                 B, H, W, cin, n, scale, shuffle, st)
+        else:
+            call("rdst_conv3x3_fwd", ptr(x), ldx, ptr(w), ptr(b), ptr(r), ldr, ptr(y), ldy,
+                 B, H, W, cin, n, scale, shuffle, dt, st)
 
     def _stl(self, src, lds, dst, w, shift, B, H, W, ws, dt, st):
         """One Swin block: x1 = x + proj(attn(LN1 x)); y = x1 + fc2(gelu(fc1(LN2 x1)))."""

@@ -104,3 +104,28 @@ def test_fused_attention(c, B, H, W, shift):
     assert err.max().item() < 6e-2 and err.mean().item() < 6e-3, (err.max().item(), err.mean().item())
     padmask = torch.ones(cp, dtype=torch.bool); padmask[pos] = False
     assert (y[:, padmask] == 0).all()
+
+
+@pytest.mark.parametrize("B,H,W,Cin,N,shuffle,res", [(2, 8, 16, 160, 64, 0, True), (3, 40, 32, 160, 64, 0, True),
+                                                      (1, 24, 24, 64, 64, 0, True), (2, 8, 8, 64, 256, 2, False),
+                                                      (1, 80, 64, 64, 256, 2, False), (1, 16, 40, 64, 64, 0, False),
+                                                      (1, 64, 64, 160, 64, 0, True)])
+def test_conv3x3_tc(B, H, W, Cin, N, shuffle, res):
+    from rdst_b200 import packing
+    L = _L()
+    T = B * H * W
+    x = _rand((T, Cin), 21).to(torch.bfloat16)
+    w, b = _rand((N, 9, Cin), 22, 0.05), _rand((N,), 23, 0.1)
+    To, ldy = (4 * T, N // 4) if shuffle else (T, N)
+    r = _rand((T, ldy), 24).to(torch.bfloat16) if res else None
+    ref = torch.zeros(To, ldy)
+    E.rdst_conv3x3_fwd(x, Cin, w.to(torch.bfloat16).float(), b, r, ldy, ref, ldy, B, H, W, Cin, N, 0.75, shuffle, 0, None)
+    xd, bd, wimg = x.cuda(), b.cuda(), packing.conv_tc_image(w).cuda()
+    rd = r.cuda() if res else None
+    yd = torch.full((To, ldy), float("nan"), dtype=torch.bfloat16, device="cuda")
+    L.call("rdst_conv3x3_fwd_bf16_tc", L.ptr(xd), Cin, L.ptr(wimg), L.ptr(bd), L.ptr(rd), ldy, L.ptr(yd), ldy,
+           B, H, W, Cin, N, 0.75, shuffle, L.stream_ptr())
+    y = yd.cpu().float()
+    assert torch.isfinite(y).all()
+    err = (y - ref).abs()
+    assert err.max().item() < 8e-2 and err.mean().item() < 8e-3, (err.max().item(), err.mean().item())
