@@ -112,6 +112,15 @@ int rdst_last_conv_fwd(const void* x, int64_t ldx, const float* w, float bias, f
 int rdst_stl_mlp_fwd_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w1img, const void* w2img,
                           const float* b1, const float* b2, int64_t T, int C, int exact_gelu, void* stream);
 
+/* Same MLP, fused with the DenseSTLayer tail: the block output y is not stored; instead
+ *   dense[t][0:32] = dense_scale * ( LNhat(y[t]) . Wt^T + bt )     (30 real growth channels + 2 zero pads)
+ * is written into the dense buffer slice (`dense` points at &D[0][64+32j], row stride ldd) -- the reference's
+ * tail LayerNorm + Linear + mul + torch.cat (rdst_variations.py:339-340) without materialising y or the concat.
+ *   wtimg : [Cp/8][32][8] bf16 K-major image of the tail Linear (LN gamma folded), bt [32] fp32 (beta folded). */
+int rdst_stl_mlp_tail_fwd_bf16(const void* x, int64_t ldx, const void* w1img, const void* w2img, const float* b1,
+                               const float* b2, const void* wtimg, const float* bt, void* dense, int64_t ldd,
+                               float dense_scale, int64_t T, int C, int exact_gelu, void* stream);
+
 /* Fused shifted-window attention block:
  *   Y[t] = X[t] + proj( softmax_j( q_i.k_j + bias(i,j) + mask(i,j) ) v_j ),  [q|k|v] = qkv(LNhat(X)), bf16 storage,
  * over 8x8 windows of a (B,H,W) token grid with cyclic shift `shift` in {0,4}; C in {60,90,120}, 6 heads.
@@ -134,6 +143,13 @@ int rdst_stl_attn_fwd_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, con
 int rdst_conv3x3_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, const float* bias, const void* resid,
                              int64_t ldr, void* y, int64_t ldy, int B, int H, int W, int Cin, int N,
                              float out_scale, int shuffle, void* stream);
+
+/* Final reconstruction conv (64 stored channels -> 1) on tcgen05 (N padded to 16), fp32 NCHW image out,
+ * add_mean folded: img = (conv + bias) * out_scale + out_bias.
+ *   wimg : 9 taps of a K-major operand image [8][16][8] bf16, row 0 = the real filter, rows 1..15 zero.
+ * Same contract as rdst_last_conv_fwd with Cin = 64.  Replaces tail[-1] + add_mean (rdst_variations.py:1303,1358). */
+int rdst_last_conv_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, float bias, float out_scale,
+                               float out_bias, float* img, int B, int H, int W, void* stream);
 
 /* Self-test of the UMMA plumbing: D[M=128][N] = A[128][K] . B[N][K]^T with bf16 inputs, fp32 output.
  * b_mn_major != 0 feeds B from an MN-major shared-memory image.  Used by tests/ only. */

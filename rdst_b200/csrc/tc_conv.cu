@@ -29,6 +29,7 @@ struct ConvGeom {
   int B, H, W, TW, TH, LW, NP, ntx, nty;
   int shuffle;
   float out_scale;
+  float out_bias;      // NT == 16 ("last conv" mode): img = (acc + bias0) * out_scale + out_bias, fp32 NCHW, 1 channel
 };
 
 template <int CIN, int NT>
@@ -40,7 +41,7 @@ struct ConvCfg {
   static constexpr int OFF_A = W_BYTES;
   static constexpr int OFF_BIAS = OFF_A + A_BYTES;
   static constexpr int SMEM = OFF_BIAS + NT * 4;
-  static_assert(NCH % 4 == 0 && (NT == 32 || NT == 64), "shape");
+  static_assert(NCH % 4 == 0 && (NT == 16 || NT == 32 || NT == 64), "shape");
 };
 
 template <int CIN, int NT>
@@ -65,7 +66,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
     for (int i = tid; i < K::W_BYTES / 16; i += 256)
       *reinterpret_cast<uint4*>(sW + (size_t)i * 16) = __ldg(reinterpret_cast<const uint4*>(src) + i);
     for (int i = tid; i < K::A_BYTES / 16; i += 256) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < NT; i += 256) sBias[i] = bias[slice * NT + i];
+    for (int i = tid; i < NT; i += 256) sBias[i] = (NT == 16) ? 0.f : bias[slice * NT + i];
   }
   fence_proxy_async();
   fence_before_sync();
@@ -119,7 +120,17 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
     mbar_wait(&bar, parity);
     fence_after_sync();
     // ---------------- epilogue ----------------
-    {
+    if constexpr (NT == 16) {
+      // last conv: one real output channel, fp32 image
+      const int oy = row / g.LW, ox = row - oy * g.LW;
+      const int y = y0 + oy, x = x0 + ox;
+      const bool ok = part == 0 && ox < g.TW && oy < g.TH && y < g.H && x < g.W;
+      uint32_t v[4];
+      tmem_ld_x4(lane_addr, v);
+      wait_ld();
+      if (ok)
+        reinterpret_cast<float*>(Y)[((int64_t)b * g.H + y) * g.W + x] = (__uint_as_float(v[0]) + sBias[0]) * g.out_scale + g.out_bias;
+    } else {
       const int oy = row / g.LW, ox = row - oy * g.LW;
       const int y = y0 + oy, x = x0 + ox;
       const bool ok = ox < g.TW && oy < g.TH && y < g.H && x < g.W;
@@ -181,6 +192,35 @@ static int launch_conv(const void* x, int64_t ldx, const void* wimg, const float
 }
 
 }  // namespace rdst
+
+extern "C" int rdst_last_conv_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, float bias, float out_scale,
+                                          float out_bias, float* img, int B, int H, int W, void* stream) {
+  using namespace rdst;
+  RDST_REQUIRE(x && wimg && img, "rdst_last_conv_fwd_bf16_tc: null pointer");
+  RDST_REQUIRE(B >= 0 && H > 0 && W > 0 && ldx >= 64 && ldx % 8 == 0 && ((uintptr_t)x % 16 == 0),
+               "rdst_last_conv_fwd_bf16_tc: bad shape / alignment");
+  if (B == 0) return RDST_OK;
+  ConvGeom g{};
+  g.B = B; g.H = H; g.W = W; g.shuffle = 0; g.out_scale = out_scale; g.out_bias = out_bias;
+  int64_t best = -1;
+  for (int tw = 8; tw <= 32; tw += 8) {
+    const int th = (128 - tw) / (tw + 2) + 1;
+    const int64_t nt = (int64_t)((W + tw - 1) / tw) * ((H + th - 1) / th);
+    if (best < 0 || nt < best) { best = nt; g.TW = tw; g.TH = th; }
+  }
+  g.LW = g.TW + 2;
+  g.NP = (2 * g.LW + 2 + 128 + 7) / 8 * 8;
+  g.ntx = (W + g.TW - 1) / g.TW;
+  g.nty = (H + g.TH - 1) / g.TH;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  g.out_bias = out_bias + bias * out_scale;      // scalar conv bias folded into the output affine (no device read)
+  int rc = launch_conv<64, 16>(x, ldx, wimg, nullptr, nullptr, 0, (void*)img, 0, g, 1, sms, (cudaStream_t)stream);
+  if (rc) return rc;
+  RDST_CHECK_LAUNCH("rdst_last_conv_fwd_bf16_tc");
+  return RDST_OK;
+}
 
 extern "C" int rdst_conv3x3_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, const float* bias,
                                         const void* resid, int64_t ldr, void* y, int64_t ldy, int B, int H, int W,

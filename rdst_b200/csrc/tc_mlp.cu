@@ -55,7 +55,12 @@ struct MlpCfg {
   static constexpr int OFF_A2 = OFF_A1 + A1_BYTES;
   static constexpr int OFF_B1 = OFF_A2 + A2_BYTES;
   static constexpr int OFF_B2 = OFF_B1 + HP * 4;
-  static constexpr int SMEM = OFF_B2 + CP * 4;
+  static constexpr int OFF_WT = OFF_B2 + CP * 4;           // fused DenseSTLayer tail: Linear(C -> 30, padded 32) image
+  static constexpr int WT_BYTES = 32 * CP * 2;
+  static constexpr int OFF_BT = OFF_WT + WT_BYTES;
+  static constexpr int SMEM_PLAIN = OFF_WT;
+  static constexpr int SMEM_TAIL = OFF_BT + 32 * 4;
+  static constexpr int SMEM = SMEM_PLAIN;
   static constexpr int TM_FC1 = 0;                        // TMEM columns: fc1 accumulator [0,HP), fc2 at 256
   static constexpr int TM_FC2 = 256;
   static_assert(HP % 16 == 0 && CP % 32 == 0 && H1 % 16 == 0 && H1 > 0, "tile shape");
@@ -81,14 +86,22 @@ __device__ __forceinline__ void epi16(uint32_t taddr, const float* __restrict__ 
   *reinterpret_cast<uint4*>(dst1) = make_uint4(o[4], o[5], o[6], o[7]);
 }
 
-template <int CP, int HP, bool EXACT>
+struct TailArgs {
+  const uint8_t* wtimg;      // [CP/8][32][8] bf16, LN gamma folded
+  const float* bt;           // [32]
+  __nv_bfloat16* dense;      // &D[0][64 + 32 j]
+  int64_t ldd;
+  float scale;               // dense_scale
+};
+
+template <int CP, int HP, bool EXACT, bool TAIL>
 __global__ void __launch_bounds__(256, 1)
 stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* __restrict__ Y, int64_t ldy,
                const uint8_t* __restrict__ w1img, const uint8_t* __restrict__ w2img,
-               const float* __restrict__ b1, const float* __restrict__ b2, int64_t T, int creal) {
+               const float* __restrict__ b1, const float* __restrict__ b2, int64_t T, int creal, TailArgs ta) {
   using C = MlpCfg<CP, HP>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[4];
+  __shared__ uint64_t bars[5];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* sW1 = smem + C::OFF_W1;
@@ -100,7 +113,7 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) {
-    for (int i = 0; i < 4; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
   }
   // resident weights (ready-made operand images) + biases
@@ -110,6 +123,11 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
   }
   for (int i = tid; i < HP; i += 256) sB1[i] = b1[i];
   for (int i = tid; i < CP; i += 256) sB2[i] = b2[i];
+  if (TAIL) {
+    for (int i = tid; i < C::WT_BYTES / 16; i += 256)
+      *reinterpret_cast<uint4*>(smem + C::OFF_WT + (size_t)i * 16) = __ldg(reinterpret_cast<const uint4*>(ta.wtimg) + i);
+    for (int i = tid; i < 32; i += 256) reinterpret_cast<float*>(smem + C::OFF_BT)[i] = ta.bt[i];
+  }
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
@@ -232,22 +250,84 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
     for (int g = warp; g < 16; g += 8) {
       const int r = g * 8 + (lane & 7);
       const int64_t t = t0 + r;
-      if (t < T) {
+      float yv[C::NCH / 4][8];
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < C::NCH / 4; ++j) {
+        const int c = (lane >> 3) + 4 * j;
+        const uint4 m = *reinterpret_cast<const uint4*>(stg + r * C::PITCH + c * 16);
+        const uint4 x = t < T ? __ldg(reinterpret_cast<const uint4*>(X + t * ldx) + c) : make_uint4(0, 0, 0, 0);
+        const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, xw[4] = {x.x, x.y, x.z, x.w};
+        uint32_t o[4];
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 a = unpack_bf16x2(mw[q]), b = unpack_bf16x2(xw[q]);
+          yv[j][2 * q] = a.x + b.x;
+          yv[j][2 * q + 1] = a.y + b.y;
+          s += yv[j][2 * q] + yv[j][2 * q + 1];
+          o[q] = pack_bf16x2(yv[j][2 * q], yv[j][2 * q + 1]);
+        }
+        if (!TAIL && t < T) *(reinterpret_cast<uint4*>(Y + t * ldy) + c) = make_uint4(o[0], o[1], o[2], o[3]);
+      }
+      if (TAIL) {
+        // LayerNorm of the block output (fp32, never rounded) -> A image for the growth projection
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        const float mean = s * inv_c;
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < C::NCH / 4; ++j)
+#pragma unroll
+          for (int q = 0; q < 8; ++q) ss += (yv[j][q] - mean) * (yv[j][q] - mean);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+        ss -= (float)(CP - creal) * mean * mean;
+        const float rstd = rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f);
 #pragma unroll
         for (int j = 0; j < C::NCH / 4; ++j) {
           const int c = (lane >> 3) + 4 * j;
-          const uint4 m = *reinterpret_cast<const uint4*>(stg + r * C::PITCH + c * 16);
-          const uint4 x = __ldg(reinterpret_cast<const uint4*>(X + t * ldx) + c);
-          const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, xw[4] = {x.x, x.y, x.z, x.w};
           uint32_t o[4];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 a = unpack_bf16x2(mw[q]), b = unpack_bf16x2(xw[q]);
-            o[q] = pack_bf16x2(a.x + b.x, a.y + b.y);
-          }
-          *(reinterpret_cast<uint4*>(Y + t * ldy) + c) = make_uint4(o[0], o[1], o[2], o[3]);
+          for (int q = 0; q < 4; ++q)
+            o[q] = pack_bf16x2((yv[j][2 * q] - mean) * rstd, (yv[j][2 * q + 1] - mean) * rstd);
+          *reinterpret_cast<uint4*>(sA1 + c * 2048 + r * 16) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
+    }
+    if (TAIL) {
+      fence_proxy_async();
+      fence_before_sync();
+      __syncthreads();
+      if (tid == 0) {
+        fence_after_sync();
+        constexpr uint32_t idt = make_idesc_bf16(128, 32, false, false);
+        const uint32_t aWT = smem_u32(smem + C::OFF_WT);
+#pragma unroll
+        for (int ks = 0; ks < CP / 16; ++ks)
+          mma_bf16_ss(tmem + C::TM_FC1, make_smem_desc(aA1 + ks * 4096, 2048, 128),
+                      make_smem_desc(aWT + ks * 2 * (32 * 16), 32 * 16, 128), idt, ks > 0);
+        commit(&bars[4]);
+      }
+      mbar_wait(&bars[4], parity);
+      fence_after_sync();
+      if (half == 0) {
+        const float* sBT = reinterpret_cast<const float*>(smem + C::OFF_BT);
+        uint32_t v[32];
+        tmem_ld_x32(lane_addr + C::TM_FC1, v);
+        wait_ld();
+        const int64_t t = t0 + row;
+        if (t < T) {
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            o[j] = pack_bf16x2((__uint_as_float(v[2 * j]) + sBT[2 * j]) * ta.scale,
+                               (__uint_as_float(v[2 * j + 1]) + sBT[2 * j + 1]) * ta.scale);
+          uint4* dp = reinterpret_cast<uint4*>(ta.dense + t * ta.ldd);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dp[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        }
+      }
+      fence_before_sync();
     }
     __syncthreads();        // staging (A2) and TMEM are reused by the next tile
   }
@@ -258,18 +338,41 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
 
 template <int CP, int HP>
 static int launch_mlp(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w1, const void* w2, const float* b1,
-                      const float* b2, int64_t T, int creal, int exact_gelu, int sms, cudaStream_t st) {
+                      const float* b2, int64_t T, int creal, int exact_gelu, const TailArgs* tail, int sms, cudaStream_t st) {
   using C = MlpCfg<CP, HP>;
   const int64_t ntiles = (T + 127) / 128;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
-  auto kf = stl_mlp_kernel<CP, HP, false>;
-  auto ke = stl_mlp_kernel<CP, HP, true>;
-  auto k = exact_gelu ? ke : kf;
-  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM);
-  if (e != cudaSuccess) { set_error("rdst_stl_mlp_fwd_bf16: smem attr (%d B): %s", C::SMEM, cudaGetErrorString(e)); return RDST_E_CUDA; }
-  k<<<grid, 256, C::SMEM, st>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const uint8_t*)w1,
-                                (const uint8_t*)w2, b1, b2, T, creal);
+  TailArgs ta{};
+  int smem = C::SMEM_PLAIN;
+  void (*k)(const __nv_bfloat16*, int64_t, __nv_bfloat16*, int64_t, const uint8_t*, const uint8_t*, const float*,
+            const float*, int64_t, int, TailArgs);
+  if (tail) {
+    ta = *tail;
+    smem = C::SMEM_TAIL;
+    k = exact_gelu ? stl_mlp_kernel<CP, HP, true, true> : stl_mlp_kernel<CP, HP, false, true>;
+  } else {
+    k = exact_gelu ? stl_mlp_kernel<CP, HP, true, false> : stl_mlp_kernel<CP, HP, false, false>;
+  }
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { set_error("rdst_stl_mlp_fwd_bf16: smem attr (%d B): %s", smem, cudaGetErrorString(e)); return RDST_E_CUDA; }
+  k<<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const uint8_t*)w1,
+                             (const uint8_t*)w2, b1, b2, T, creal, ta);
   return RDST_OK;
+}
+
+static int mlp_dispatch(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w1img, const void* w2img,
+                        const float* b1, const float* b2, int64_t T, int C, int exact_gelu, const TailArgs* tail,
+                        void* stream) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (C) {
+    case 60:  return launch_mlp<64, 128>(x, ldx, y, ldy, w1img, w2img, b1, b2, T, 60, exact_gelu, tail, sms, st);
+    case 90:  return launch_mlp<96, 192>(x, ldx, y, ldy, w1img, w2img, b1, b2, T, 90, exact_gelu, tail, sms, st);
+    case 120: return launch_mlp<128, 240>(x, ldx, y, ldy, w1img, w2img, b1, b2, T, 120, exact_gelu, tail, sms, st);
+    default: set_error("rdst_stl_mlp_fwd_bf16: C=%d unsupported (60, 90, 120 with mlp_ratio 2)", C); return RDST_E_UNSUPPORTED;
+  }
 }
 
 }  // namespace rdst
@@ -282,19 +385,30 @@ extern "C" int rdst_stl_mlp_fwd_bf16(const void* x, int64_t ldx, void* y, int64_
   RDST_REQUIRE(T >= 0, "rdst_stl_mlp_fwd_bf16: negative T");
   RDST_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ldx % 8 == 0 && ldy % 8 == 0,
                "rdst_stl_mlp_fwd_bf16: x/y must be 16-byte aligned with row strides multiple of 8 elements");
+  RDST_REQUIRE(C == 60 || C == 90 || C == 120, "rdst_stl_mlp_fwd_bf16: C=%d unsupported (60, 90, 120)", C);
+  RDST_REQUIRE(ldx >= 64 + 32 * ((C - 60) / 30) && ldy >= 64 + 32 * ((C - 60) / 30), "rdst_stl_mlp_fwd_bf16: ld too small");
   if (T == 0) return RDST_OK;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  int rc;
-  cudaStream_t st = (cudaStream_t)stream;
-  switch (C) {
-    case 60:  RDST_REQUIRE(ldx >= 64 && ldy >= 64, "ld too small");   rc = launch_mlp<64, 128>(x, ldx, y, ldy, w1img, w2img, b1, b2, T, 60, exact_gelu, sms, st); break;
-    case 90:  RDST_REQUIRE(ldx >= 96 && ldy >= 96, "ld too small");   rc = launch_mlp<96, 192>(x, ldx, y, ldy, w1img, w2img, b1, b2, T, 90, exact_gelu, sms, st); break;
-    case 120: RDST_REQUIRE(ldx >= 128 && ldy >= 128, "ld too small"); rc = launch_mlp<128, 240>(x, ldx, y, ldy, w1img, w2img, b1, b2, T, 120, exact_gelu, sms, st); break;
-    default: set_error("rdst_stl_mlp_fwd_bf16: C=%d unsupported (60, 90, 120 with mlp_ratio 2)", C); return RDST_E_UNSUPPORTED;
-  }
+  int rc = mlp_dispatch(x, ldx, y, ldy, w1img, w2img, b1, b2, T, C, exact_gelu, nullptr, stream);
   if (rc) return rc;
   RDST_CHECK_LAUNCH("rdst_stl_mlp_fwd_bf16");
+  return RDST_OK;
+}
+
+extern "C" int rdst_stl_mlp_tail_fwd_bf16(const void* x, int64_t ldx, const void* w1img, const void* w2img,
+                                          const float* b1, const float* b2, const void* wtimg, const float* bt,
+                                          void* dense, int64_t ldd, float dense_scale, int64_t T, int C,
+                                          int exact_gelu, void* stream) {
+  using namespace rdst;
+  RDST_REQUIRE(x && w1img && w2img && b1 && b2 && wtimg && bt && dense, "rdst_stl_mlp_tail_fwd_bf16: null pointer");
+  RDST_REQUIRE(T >= 0, "rdst_stl_mlp_tail_fwd_bf16: negative T");
+  RDST_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)dense % 16 == 0) && ldx % 8 == 0 && ldd % 8 == 0,
+               "rdst_stl_mlp_tail_fwd_bf16: x/dense must be 16-byte aligned with row strides multiple of 8 elements");
+  RDST_REQUIRE(C == 60 || C == 90 || C == 120, "rdst_stl_mlp_tail_fwd_bf16: C=%d unsupported (60, 90, 120)", C);
+  RDST_REQUIRE(ldx >= 64 + 32 * ((C - 60) / 30) && ldd >= 32, "rdst_stl_mlp_tail_fwd_bf16: ld too small");
+  if (T == 0) return RDST_OK;
+  TailArgs ta{(const uint8_t*)wtimg, bt, (__nv_bfloat16*)dense, ldd, dense_scale};
+  int rc = mlp_dispatch(x, ldx, nullptr, 0, w1img, w2img, b1, b2, T, C, exact_gelu, &ta, stream);
+  if (rc) return rc;
+  RDST_CHECK_LAUNCH("rdst_stl_mlp_tail_fwd_bf16");
   return RDST_OK;
 }

@@ -83,6 +83,7 @@ class Executor:
             lw = last.weight.new_zeros(9, 64, dtype=torch.float32)
             lw[:, :60] = last.weight.detach().float()[0].permute(1, 2, 0).reshape(9, 60)
             P["last_w"] = lw.contiguous()
+            P["last_img"] = packing.last_conv_tc_image(P["last_w"])
             # scalars are read once per re-pack (a host sync only when weights changed)
             P["last_b"] = float(last.bias.detach().float()[0])
             P["in_scale"] = float(m.sub_mean.weight.detach().reshape(-1)[0])
@@ -150,15 +151,19 @@ class Executor:
         for blk in P["blocks"]:
             for j, ds in enumerate(blk["dstl"]):
                 src, lds = D[cur], 160
+                t = ds["tail"]
+                off = 64 + 32 * j
+                fuse_tail = dt == _lib.BF16 and self.use_tc
                 for k, (w, shift) in enumerate(zip(ds["stl"], ds["shifts"])):
                     cp = w["cp"]
                     dst = (ws["Y0"] if k == 0 else ws["Y1"]).view(-1)[:T * cp].view(T, cp)
-                    self._stl(src, lds, dst, w, shift, B, H, W, ws, dt, st)
+                    last = k == len(ds["stl"]) - 1
+                    self._stl(src, lds, dst, w, shift, B, H, W, ws, dt, st,
+                              tail=(t, D[cur][:, off:]) if (fuse_tail and last) else None)
                     src, lds = dst, w["cp"]
-                t = ds["tail"]
-                off = 64 + 32 * j
-                call("rdst_linear_fwd", ptr(src), lds, ptr(t["w"]), ptr(t["b"]), None, 0,
-                     ptr(D[cur][:, off:]), 160, T, ds["stl"][0]["cp"], 32, ds["c"], 0, t["scale"], dt, st)
+                if not fuse_tail:
+                    call("rdst_linear_fwd", ptr(src), lds, ptr(t["w"]), ptr(t["b"]), None, 0,
+                         ptr(D[cur][:, off:]), 160, T, ds["stl"][0]["cp"], 32, ds["c"], 0, t["scale"], dt, st)
             self._conv(D[cur], 160, blk["lff_w"], blk["lff_img"], blk["lff_b"], D[cur], 160, D[1 - cur], 160,
                        B, H, W, 160, 64, float(m.rdb_residual_scale), 0, dt, st)
             cur = 1 - cur
@@ -176,8 +181,12 @@ class Executor:
             self._conv(feat, 64, uw, uimg, ub, None, 0, buf, 64, B, h, w_, 64, 256, 1.0, 2, dt, st)
             feat, h, w_ = buf, 2 * h, 2 * w_
         out = torch.empty(B, 1, h, w_, dtype=torch.float32, device=dev)
-        call("rdst_last_conv_fwd", ptr(feat), 64, ptr(P["last_w"]), P["last_b"], P["out_scale"], P["out_bias"],
-             ptr(out), B, h, w_, 64, dt, st)
+        if dt == _lib.BF16 and self.use_tc:
+            call("rdst_last_conv_fwd_bf16_tc", ptr(feat), 64, ptr(P["last_img"]), P["last_b"], P["out_scale"],
+                 P["out_bias"], ptr(out), B, h, w_, st)
+        else:
+            call("rdst_last_conv_fwd", ptr(feat), 64, ptr(P["last_w"]), P["last_b"], P["out_scale"], P["out_bias"],
+                 ptr(out), B, h, w_, 64, dt, st)
         return out if x.dtype == torch.float32 else out.to(x.dtype)
 
     def _conv(self, x, ldx, w, wimg, b, r, ldr, y, ldy, B, H, W, cin, n, scale, shuffle, dt, st):
@@ -188,7 +197,7 @@ class Executor:
             call("rdst_conv3x3_fwd", ptr(x), ldx, ptr(w), ptr(b), ptr(r), ldr, ptr(y), ldy,
                  B, H, W, cin, n, scale, shuffle, dt, st)
 
-    def _stl(self, src, lds, dst, w, shift, B, H, W, ws, dt, st):
+    def _stl(self, src, lds, dst, w, shift, B, H, W, ws, dt, st, tail=None):
         """One Swin block: x1 = x + proj(attn(LN1 x)); y = x1 + fc2(gelu(fc1(LN2 x1)))."""
         T = B * H * W
         c, cp, hp = w["c"], w["cp"], w["hp"]
@@ -197,8 +206,13 @@ class Executor:
         if dt == _lib.BF16 and self.use_tc:
             call("rdst_stl_attn_fwd_bf16", ptr(src), lds, ptr(x1), cp, ptr(w["wqkv_img"]), ptr(w["wproj_img"]),
                  ptr(w["bqkv_tc"]), ptr(w["bproj"]), ptr(w["table_tc"]), B, H, W, c, shift, st)
-            call("rdst_stl_mlp_fwd_bf16", ptr(x1), cp, ptr(dst), cp, ptr(w["w1img"]), ptr(w["w2img"]), ptr(w["b1"]),
-                 ptr(w["b2"]), T, c, 0, st)
+            if tail is None:
+                call("rdst_stl_mlp_fwd_bf16", ptr(x1), cp, ptr(dst), cp, ptr(w["w1img"]), ptr(w["w2img"]),
+                     ptr(w["b1"]), ptr(w["b2"]), T, c, 0, st)
+            else:   # second block of a DenseSTLayer: its output only feeds the tail LN+Linear -> dense slice
+                t, dslice = tail
+                call("rdst_stl_mlp_tail_fwd_bf16", ptr(x1), cp, ptr(w["w1img"]), ptr(w["w2img"]), ptr(w["b1"]),
+                     ptr(w["b2"]), ptr(t["wimg"]), ptr(t["b"]), ptr(dslice), 160, t["scale"], T, c, 0, st)
             return
         call("rdst_linear_fwd", ptr(src), lds, ptr(w["wqkv"]), ptr(w["bqkv"]), None, 0, ptr(qkv), 3 * c,
              T, cp, 3 * c, c, 0, 1.0, dt, st)

@@ -93,7 +93,7 @@ def pack_dstl_tail(dstl, c, dense_scale):
     g = w.shape[0]
     wp = w.new_zeros(32, cp); wp[:g] = scatter_cols(w, pos, cp)
     bp = b.new_zeros(32); bp[:g] = b
-    return dict(w=wp.contiguous(), b=bp.contiguous(), scale=float(dense_scale))
+    return dict(w=wp.contiguous(), b=bp.contiguous(), scale=float(dense_scale), wimg=kmajor_image(wp))
 
 
 def pack_conv(weight, bias, cin_pos, cin_width, n_pad):
@@ -180,4 +180,14 @@ def conv_tc_image(w):
     n, _, cin = w.shape
     nt = 32 if cin == 160 else 64
     parts = [kmajor_image(w[s * nt:(s + 1) * nt, tap, :]) for s in range(n // nt) for tap in range(9)]
+    return torch.cat(parts).contiguous()
+
+
+def last_conv_tc_image(w9):
+    """[9][64] fp32 filter of the final 64->1 conv -> 9 taps x [8][16][8] bf16 (row 0 real, rows 1..15 zero)."""
+    parts = []
+    for tap in range(9):
+        m = w9.new_zeros(16, w9.shape[1])
+        m[0] = w9[tap]
+        parts.append(kmajor_image(m))
     return torch.cat(parts).contiguous()

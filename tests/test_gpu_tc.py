@@ -129,3 +129,49 @@ def test_conv3x3_tc(B, H, W, Cin, N, shuffle, res):
     assert torch.isfinite(y).all()
     err = (y - ref).abs()
     assert err.max().item() < 8e-2 and err.mean().item() < 8e-3, (err.max().item(), err.mean().item())
+
+
+@pytest.mark.parametrize("c,T", [(60, 640), (90, 128 * 3 + 64), (120, 1280)])
+def test_fused_mlp_with_dense_tail(c, T):
+    from rdst_b200 import packing
+    L = _L()
+    x, cp = _padded_input(T, c, 31)
+    hp = packing.hidden_width(2 * c)
+    pos = packing.channel_positions(c)
+    w1 = torch.zeros(hp, cp); w1[:2 * c, pos] = _rand((2 * c, c), 32, 0.08)
+    b1 = torch.zeros(hp); b1[:2 * c] = _rand((2 * c,), 33, 0.1)
+    w2 = torch.zeros(cp, hp); w2[pos, :2 * c] = _rand((c, 2 * c), 34, 0.08)
+    b2 = torch.zeros(cp); b2[pos] = _rand((c,), 35, 0.1)
+    wt = torch.zeros(32, cp); wt[:30, pos] = _rand((30, c), 36, 0.1)
+    bt = torch.zeros(32); bt[:30] = _rand((30,), 37, 0.1)
+    rb = lambda t: t.to(torch.bfloat16).float()
+    hid = torch.zeros(T, hp)
+    E.rdst_linear_fwd(x, cp, rb(w1), b1, None, 0, hid, hp, T, cp, hp, c, 1, 1.0, 0, None)
+    y = torch.zeros(T, cp)
+    E.rdst_linear_fwd(hid, hp, rb(w2), b2, x, cp, y, cp, T, hp, cp, 0, 0, 1.0, 0, None)
+    ref = torch.zeros(T, 32)
+    E.rdst_linear_fwd(y, cp, rb(wt), bt, None, 0, ref, 32, T, cp, 32, c, 0, 0.5, 0, None)
+    dense = torch.full((T, 160), 7.0, dtype=torch.bfloat16, device="cuda")
+    dev = [t.cuda() for t in (x, packing.kmajor_image(w1), packing.kmajor_image(w2), b1, b2, packing.kmajor_image(wt), bt)]
+    L.call("rdst_stl_mlp_tail_fwd_bf16", L.ptr(dev[0]), cp, L.ptr(dev[1]), L.ptr(dev[2]), L.ptr(dev[3]), L.ptr(dev[4]),
+           L.ptr(dev[5]), L.ptr(dev[6]), L.ptr(dense[:, 96:]), 160, 0.5, T, c, 0, L.stream_ptr())
+    d = dense.cpu().float()
+    err = (d[:, 96:128] - ref).abs()
+    assert err.max().item() < 6e-2 and err.mean().item() < 6e-3, (err.max().item(), err.mean().item())
+    assert (d[:, :96] == 7.0).all() and (d[:, 128:] == 7.0).all()      # only the 32-wide slice is written
+    assert (d[:, 126:128] == 0).all()
+
+
+def test_last_conv_tc():
+    from rdst_b200 import packing
+    L = _L()
+    B, H, W = 2, 32, 48
+    T = B * H * W
+    x = _rand((T, 64), 41).to(torch.bfloat16)
+    lw = torch.zeros(9, 64); lw[:, :60] = _rand((9, 60), 42, 0.1)
+    ref = torch.zeros(B, 1, H, W)
+    E.rdst_last_conv_fwd(x, 64, lw.to(torch.bfloat16).float(), 0.3, 2.0, 0.1, ref, B, H, W, 64, 0, None)
+    xd, img = x.cuda(), packing.last_conv_tc_image(lw).cuda()
+    od = torch.full((B, 1, H, W), float("nan"), device="cuda")
+    L.call("rdst_last_conv_fwd_bf16_tc", L.ptr(xd), 64, L.ptr(img), 0.3, 2.0, 0.1, L.ptr(od), B, H, W, L.stream_ptr())
+    assert (od.cpu() - ref).abs().max().item() < 2e-3
