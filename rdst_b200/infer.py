@@ -1,0 +1,47 @@
+"""Batched, slice-sharded inference driver.
+
+The reference tester feeds one LR slice per forward call and synchronises device->host after each
+(models/trans_sr_tester.py:124-166, models/basic_tester.py:104-115).  Slices never interact (attention is per 8x8
+window, convolutions per image), so this driver
+  * splits the slice axis of a volume into contiguous ranges, one per rank (no collective on the data path),
+  * runs each rank's range in large batches through the drop-in module,
+  * keeps host<->device copies asynchronous on pinned buffers.
+"""
+import torch
+
+
+def shard_range(n_items, world_size, rank):
+    """Contiguous, balanced [begin, end) range of `n_items` for `rank` (first n%world ranks get one extra)."""
+    if not 0 <= rank < world_size:
+        raise ValueError(f"rank {rank} outside world of {world_size}")
+    base, extra = divmod(n_items, world_size)
+    begin = rank * base + min(rank, extra)
+    return begin, begin + base + (1 if rank < extra else 0)
+
+
+@torch.no_grad()
+def super_resolve_slices(model, lr_slices, batch_size=176, out=None):
+    """lr_slices: (N,1,H,W) float tensor on the HOST (ideally pinned) or on the model's device.
+    Returns (N,1,sH,sW) on the same side as the input.  One H2D + one D2H per batch, both asynchronous."""
+    dev = next(model.parameters()).device
+    n = lr_slices.shape[0]
+    s = model.sr_scale
+    on_host = not lr_slices.is_cuda
+    if out is None:
+        out = torch.empty(n, 1, lr_slices.shape[2] * s, lr_slices.shape[3] * s, dtype=torch.float32,
+                          device=lr_slices.device, pin_memory=on_host and torch.cuda.is_available())
+    for b0 in range(0, n, batch_size):
+        x = lr_slices[b0:b0 + batch_size]
+        if on_host:
+            x = x.to(dev, non_blocking=True)
+        y = model(x)
+        out[b0:b0 + batch_size].copy_(y, non_blocking=True)
+    if on_host and torch.cuda.is_available():
+        torch.cuda.current_stream(dev).synchronize()
+    return out
+
+
+def super_resolve_volume_sharded(model, lr_volume, rank=0, world_size=1, batch_size=176):
+    """Each rank super-resolves its contiguous share of the slice axis; returns (begin, end, hr_slices)."""
+    b, e = shard_range(lr_volume.shape[0], world_size, rank)
+    return b, e, super_resolve_slices(model, lr_volume[b:e], batch_size)
