@@ -35,7 +35,6 @@ __device__ __forceinline__ float ex2(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
-__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(id) : "memory"); }
 
 template <int C_>
 struct AttnCfg {
@@ -48,6 +47,7 @@ struct AttnCfg {
   static constexpr int HDO = HD == 20 ? 20 : 16;            // stride of one head inside the proj A operand
   static constexpr int KPROJ = (6 * HDO + 15) / 16 * 16;    // 96 / 96 / 128
   static constexpr int NCH = CP / 8;
+  static constexpr int TBL = 15 * 24;                       // bias table per head, row pitch 24 (bank-conflict free)
   static constexpr int WQKV_BYTES = 6 * NH * CP * 2;
   static constexpr int WPROJ_BYTES = CP * KPROJ * 2;
   static constexpr int A1_BYTES = 128 * CP * 2;
@@ -57,26 +57,20 @@ struct AttnCfg {
   static constexpr int STG_BYTES = 128 * PITCH;
   static constexpr int AREG0 = A1_BYTES > AO_BYTES ? A1_BYTES : AO_BYTES;
   static constexpr int AREG_BYTES = AREG0 > STG_BYTES ? AREG0 : STG_BYTES;       // A1, later Ao, later staging
-  static constexpr int P_BYTES = 128 * 128 * 2;
-  static constexpr int AQ_BYTES = 128 * HDP * 2;
+  static constexpr int AQ_BYTES = 128 * HDP * 2;            // Q image == K image size
   static constexpr int BV_BYTES = 128 * HDV * 2;
+  static constexpr int QKV_BYTES = 2 * AQ_BYTES + BV_BYTES; // per warpgroup: Q, K, V images of the head in flight
   static constexpr int OFF_WQKV = 0;
   static constexpr int OFF_WPROJ = OFF_WQKV + WQKV_BYTES;
   static constexpr int OFF_A = OFF_WPROJ + WPROJ_BYTES;
-  static constexpr int OFF_P = OFF_A + AREG_BYTES;
-  static constexpr int OFF_AQ = OFF_P + P_BYTES;
-  static constexpr int OFF_BK = OFF_AQ + AQ_BYTES;
-  static constexpr int OFF_BV = OFF_BK + AQ_BYTES;
-  static constexpr int OFF_TAB = OFF_BV + BV_BYTES;
-  static constexpr int OFF_BQKV = OFF_TAB + 6 * 225 * 4;
+  static constexpr int OFF_QKV = OFF_A + AREG_BYTES;        // [2 warpgroups][Q | K | V]
+  static constexpr int OFF_TAB = OFF_QKV + 2 * QKV_BYTES;
+  static constexpr int OFF_BQKV = OFF_TAB + 6 * TBL * 4;
   static constexpr int OFF_BPROJ = OFF_BQKV + 6 * NH * 4;
   static constexpr int OFF_SREG = OFF_BPROJ + CP * 4;
-  static constexpr int OFF_SRED = OFF_SREG + 128 * 4;
-  static constexpr int SMEM = OFF_SRED + 2 * 128 * 4;
-  // TMEM columns
-  static constexpr int TM_QKV0 = 0, TM_QKV1 = 64, TM_S = 128, TM_O = 256, TM_PROJ = 128;
-  static_assert(2 * AQ_BYTES >= 2 * 6 * 128 * 4, "row-sum exchange must fit in the dead Q/K images");
-  static_assert(HDP == 16 || 2 * 6 * 128 * 4 <= 3 * 2048, "row-sum exchange must not touch the zero K-pad chunk of Q");
+  static constexpr int SMEM = OFF_SREG + 128 * 4;
+  // TMEM columns: per-warpgroup qkv [0,64),[64,128); per-warpgroup S/P [128,192),[192,256); O [256, 256+6*HDV); proj [0,CP)
+  static constexpr int TM_QKV = 0, TM_S = 128, TM_O = 256, TM_PROJ = 0;
   static_assert(SMEM <= 232448, "shared memory budget");
 };
 
@@ -113,6 +107,22 @@ __device__ __forceinline__ int64_t win_token(const WinGeom& g, int64_t win, int 
   return ((int64_t)b * g.H + hh) * g.W + ww;
 }
 
+__device__ __forceinline__ void wg_barrier(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
+
+// bf16 pairs of 8 consecutive accumulator values (+bias), zero beyond `valid`
+template <int OFFSET, int HD>
+__device__ __forceinline__ uint4 pack8(const float* f, const float* bias, int c8) {
+  uint32_t o[4];
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const int d0 = c8 * 8 + 2 * q, d1 = d0 + 1;
+    const float a = d0 < HD ? f[OFFSET + d0] + bias[OFFSET + d0] : 0.f;
+    const float b = d1 < HD ? f[OFFSET + d1] + bias[OFFSET + d1] : 0.f;
+    o[q] = pk2(a, b);
+  }
+  return make_uint4(o[0], o[1], o[2], o[3]);
+}
+
 template <int C_>
 __global__ void __launch_bounds__(256, 1)
 stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* __restrict__ Y, int64_t ldy,
@@ -122,24 +132,23 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   using K = AttnCfg<C_>;
   constexpr int CP = K::CP, HD = K::HD, NH = K::NH;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[5];          // 0,1: qkv ping/pong  2: S  3: PV  4: proj
+  __shared__ uint64_t bars[7];          // [0,1] qkv per warpgroup, [2,3] S, [4,5] PV, [6] proj
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = tid >> 7;              // warpgroup: owns heads wg, wg+2, wg+4
+  const int row = tid & 127;
   uint8_t* sA = smem + K::OFF_A;
-  uint8_t* sP = smem + K::OFF_P;
-  uint8_t* sAq = smem + K::OFF_AQ;
-  uint8_t* sBk = smem + K::OFF_BK;
-  uint8_t* sBv = smem + K::OFF_BV;
+  uint8_t* sAq = smem + K::OFF_QKV + wg * K::QKV_BYTES;
+  uint8_t* sBk = sAq + K::AQ_BYTES;
+  uint8_t* sBv = sBk + K::AQ_BYTES;
   float* sTab = reinterpret_cast<float*>(smem + K::OFF_TAB);
   float* sBqkv = reinterpret_cast<float*>(smem + K::OFF_BQKV);
   float* sBproj = reinterpret_cast<float*>(smem + K::OFF_BPROJ);
   int* sReg = reinterpret_cast<int*>(smem + K::OFF_SREG);
-  float* sRed = reinterpret_cast<float*>(smem + K::OFF_SRED);
-  float* sSum = reinterpret_cast<float*>(sAq);              // [2][6][128] exchange of row sums (Aq/Bk dead by then)
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
   }
   for (int i = tid; i < (K::WQKV_BYTES + K::WPROJ_BYTES) / 16; i += 256) {
@@ -147,10 +156,10 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
                                                 : wproj_img + (size_t)(i - K::WQKV_BYTES / 16) * 16;
     *reinterpret_cast<uint4*>(smem + (size_t)i * 16) = __ldg(reinterpret_cast<const uint4*>(src));
   }
-  // zero P (off-diagonal blocks stay zero forever), Q/K/V images (K / N pads stay zero forever)
-  for (int i = tid; i < (K::P_BYTES + 2 * K::AQ_BYTES + K::BV_BYTES) / 16; i += 256)
-    *reinterpret_cast<uint4*>(sP + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 6 * 225; i += 256) sTab[i] = table[i];
+  // Q/K/V images: K / N pads must be (and stay) zero
+  for (int i = tid; i < 2 * K::QKV_BYTES / 16; i += 256)
+    *reinterpret_cast<uint4*>(smem + K::OFF_QKV + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < 6 * K::TBL; i += 256) sTab[i] = table[i];
   for (int i = tid; i < 6 * NH; i += 256) sBqkv[i] = bqkv[i];
   for (int i = tid; i < CP; i += 256) sBproj[i] = bproj[i];
   fence_proxy_async();
@@ -158,236 +167,226 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t aA = smem_u32(sA), aP = smem_u32(sP), aAq = smem_u32(sAq), aBk = smem_u32(sBk), aBv = smem_u32(sBv);
+  const uint32_t aA = smem_u32(sA), aAq = smem_u32(sAq), aBk = smem_u32(sBk), aBv = smem_u32(sBv);
   const uint32_t aWqkv = smem_u32(smem + K::OFF_WQKV), aWproj = smem_u32(smem + K::OFF_WPROJ);
 
-  const int row = tid & 127, part = tid >> 7;
   const int wsel = row >> 6, irow = row & 63, iy = irow >> 3, ix = irow & 7;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const uint32_t tS = K::TM_S + 64 * wg, tQ = K::TM_QKV + 64 * wg;
   const float inv_c = 1.0f / (float)C_;
   const int64_t ntiles = (geo.nwt + 1) / 2;
-  uint32_t ph_q0 = 0, ph_q1 = 0, ph_s = 0, ph_o = 0, ph_p = 0;
+  uint32_t ph_q = 0, ph_s = 0, ph_o = 0, ph_p = 0;
+  uint64_t* bar_q = &bars[wg];
+  uint64_t* bar_s = &bars[2 + wg];
+  uint64_t* bar_o = &bars[4 + wg];
+  const bool issuer = row == 0;
 
-  auto issue_qkv = [&](int h) {      // thread 0 only
+  auto issue_qkv = [&](int h) {      // warpgroup issuer only
     constexpr uint32_t idq = make_idesc_bf16(128, NH, false, false);
-    const uint32_t d = tmem + ((h & 1) ? K::TM_QKV1 : K::TM_QKV0);
     const uint32_t wb = aWqkv + h * (NH * CP * 2);
 #pragma unroll
     for (int ks = 0; ks < CP / 16; ++ks)
-      mma_bf16_ss(d, make_smem_desc(aA + ks * 4096, 2048, 128), make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128),
+      mma_bf16_ss(tmem + tQ, make_smem_desc(aA + ks * 4096, 2048, 128), make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128),
                   idq, ks > 0);
-    commit(&bars[h & 1]);
+    commit(bar_q);
   };
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // ---------------- P1: gather two windows + LayerNorm -> A image ----------------
-#pragma unroll 1
-    for (int g = warp; g < 16; g += 8) {
-      const int r = g * 8 + (lane & 7);
-      const int64_t win = tile * 2 + (g >> 3);
-      int region = 0; bool edge = false;
-      int64_t t = -1;
-      if (win < geo.nwt) t = win_token(geo, win, g & 7, lane & 7, region, edge);
-      if ((lane >> 3) == 0) sReg[r] = edge ? region : -1;
-      uint4 raw[K::NCH / 4];
-      float s = 0.f;
+    {
+      uint4 raw[2][K::NCH / 4];
+      int64_t tok[2];
 #pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j) {
-        const int c = (lane >> 3) + 4 * j;
-        raw[j] = t >= 0 ? __ldg(reinterpret_cast<const uint4*>(X + t * ldx) + c) : make_uint4(0, 0, 0, 0);
-        const float2 f0 = up2(raw[j].x), f1 = up2(raw[j].y), f2 = up2(raw[j].z), f3 = up2(raw[j].w);
-        s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
-      }
-      s += __shfl_xor_sync(0xffffffffu, s, 8);
-      s += __shfl_xor_sync(0xffffffffu, s, 16);
-      const float mean = s * inv_c;
-      float ss = 0.f;
+      for (int gi = 0; gi < 2; ++gi) {
+        const int g = warp + 8 * gi;
+        const int64_t win = tile * 2 + (g >> 3);
+        int region = 0; bool edge = false;
+        tok[gi] = -1;
+        if (win < geo.nwt) tok[gi] = win_token(geo, win, g & 7, lane & 7, region, edge);
+        if ((lane >> 3) == 0) sReg[g * 8 + (lane & 7)] = edge ? region : -1;
 #pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j) {
-        const uint32_t w4[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 f = up2(w4[q]);
-          ss += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+        for (int j = 0; j < K::NCH / 4; ++j) {
+          const int c = (lane >> 3) + 4 * j;
+          raw[gi][j] = tok[gi] >= 0 ? __ldg(reinterpret_cast<const uint4*>(X + tok[gi] * ldx) + c) : make_uint4(0, 0, 0, 0);
         }
       }
-      ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-      ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-      ss -= (float)(CP - C_) * mean * mean;
-      const float rstd = rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f);
 #pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j) {
-        const int c = (lane >> 3) + 4 * j;
-        const uint32_t w4[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
-        uint32_t o[4];
+      for (int gi = 0; gi < 2; ++gi) {
+        const int r = (warp + 8 * gi) * 8 + (lane & 7);
+        float s = 0.f;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 f = up2(w4[q]);
-          o[q] = pk2((f.x - mean) * rstd, (f.y - mean) * rstd);
+        for (int j = 0; j < K::NCH / 4; ++j) {
+          const float2 f0 = up2(raw[gi][j].x), f1 = up2(raw[gi][j].y), f2 = up2(raw[gi][j].z), f3 = up2(raw[gi][j].w);
+          s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
         }
-        *reinterpret_cast<uint4*>(sA + c * 2048 + r * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        const float mean = s * inv_c;
+        float ss = 0.f;
+#pragma unroll
+        for (int j = 0; j < K::NCH / 4; ++j) {
+          const uint32_t w4[4] = {raw[gi][j].x, raw[gi][j].y, raw[gi][j].z, raw[gi][j].w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = up2(w4[q]);
+            ss += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+          }
+        }
+        ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+        ss -= (float)(CP - C_) * mean * mean;
+        const float rstd = rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f);
+#pragma unroll
+        for (int j = 0; j < K::NCH / 4; ++j) {
+          const int c = (lane >> 3) + 4 * j;
+          const uint32_t w4[4] = {raw[gi][j].x, raw[gi][j].y, raw[gi][j].z, raw[gi][j].w};
+          uint32_t o[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = up2(w4[q]);
+            o[q] = pk2((f.x - mean) * rstd, (f.y - mean) * rstd);
+          }
+          *reinterpret_cast<uint4*>(sA + c * 2048 + r * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
       }
     }
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (issuer) {
       fence_after_sync();
-      issue_qkv(0);
-      issue_qkv(1);
+      issue_qkv(wg);
     }
+    // shift mask of this row as a 64-bit set of keys that belong to another region (edge windows only)
     const int myreg = sReg[row];
-    const bool wmask = myreg >= 0;                 // warp-uniform: a warp covers 32 rows of one window
-    float psum[6];
+    uint32_t mlo = 0, mhi = 0;
+    if (myreg >= 0) {
+      const int* rg = sReg + 64 * wsel;
+#pragma unroll
+      for (int j = 0; j < 32; ++j) {
+        mlo |= (rg[j] != myreg) ? (1u << j) : 0u;
+        mhi |= (rg[32 + j] != myreg) ? (1u << j) : 0u;
+      }
+    }
+    float psum[3];
 
-    // ---------------- heads ----------------
+    // ---------------- heads of this warpgroup ----------------
 #pragma unroll
-    for (int h = 0; h < 6; ++h) {
-      // drain qkv_h : part 0 takes q,k ; part 1 takes v
-      if (h & 1) { mbar_wait(&bars[1], ph_q1 & 1); ph_q1++; } else { mbar_wait(&bars[0], ph_q0 & 1); ph_q0++; }
+    for (int i = 0; i < 3; ++i) {
+      const int h = wg + 2 * i;
+      mbar_wait(bar_q, ph_q & 1); ph_q++;
       fence_after_sync();
-      const uint32_t tq = lane_addr + ((h & 1) ? K::TM_QKV1 : K::TM_QKV0);
-      const float* bq = sBqkv + h * NH;
-      if (part == 0) {
-        constexpr int NC = (2 * HD + 7) / 8 * 8;
+      {
+        constexpr int NC = (3 * HD + 7) / 8 * 8;
         float f[NC];
-        tmem_load_cols<NC>(tq, f);
-#pragma unroll
-        for (int sel = 0; sel < 2; ++sel) {          // 0: q -> Aq, 1: k -> Bk
-          uint8_t* dst = (sel == 0 ? sAq : sBk) + row * 16;
-#pragma unroll
-          for (int c8 = 0; c8 < (HD + 7) / 8; ++c8) {
-            uint32_t o[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int d0 = c8 * 8 + 2 * q, d1 = d0 + 1;
-              const float a = d0 < HD ? f[sel * HD + d0] + bq[sel * HD + d0] : 0.f;
-              const float b = d1 < HD ? f[sel * HD + d1] + bq[sel * HD + d1] : 0.f;
-              o[q] = pk2(a, b);
-            }
-            *reinterpret_cast<uint4*>(dst + c8 * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
-          }
-        }
-      } else {
-        // v columns start at 2*HD (not 8-aligned in general): load an aligned superset
-        constexpr int C0 = (2 * HD) / 8 * 8;
-        constexpr int NC = (3 * HD - C0 + 7) / 8 * 8;
-        float f[NC];
-        tmem_load_cols<NC>(tq + C0, f);
-        if (h > 0) { mbar_wait(&bars[3], (ph_o - 1) & 1); }     // PV of head h-1 must have finished reading V
+        tmem_load_cols<NC>(lane_addr + tQ, f);
+        const float* bq = sBqkv + h * NH;
 #pragma unroll
         for (int c8 = 0; c8 < (HD + 7) / 8; ++c8) {
-          uint32_t o[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int d0 = c8 * 8 + 2 * q, d1 = d0 + 1;
-            const float a = d0 < HD ? f[2 * HD - C0 + d0] + bq[2 * HD + d0] : 0.f;
-            const float b = d1 < HD ? f[2 * HD - C0 + d1] + bq[2 * HD + d1] : 0.f;
-            o[q] = pk2(a, b);
-          }
-          // MN-major V image: (token k=row, n=d) at (row/8)*128 + (d/8)*2048 + (row%8)*16 + (d%8)*2  == row*16 + c8*2048
-          *reinterpret_cast<uint4*>(sBv + row * 16 + c8 * 2048) = make_uint4(o[0], o[1], o[2], o[3]);
+          *reinterpret_cast<uint4*>(sAq + c8 * 2048 + row * 16) = pack8<0, HD>(f, bq, c8);
+          *reinterpret_cast<uint4*>(sBk + c8 * 2048 + row * 16) = pack8<HD, HD>(f, bq, c8);
         }
+        if (i > 0) mbar_wait(bar_o, (ph_o - 1) & 1);          // PV of the previous head has finished reading V
+#pragma unroll
+        for (int c8 = 0; c8 < (HD + 7) / 8; ++c8)
+          *reinterpret_cast<uint4*>(sBv + c8 * 2048 + row * 16) = pack8<2 * HD, HD>(f, bq, c8);   // MN-major V image
       }
       fence_proxy_async();
       fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
+      wg_barrier(wg);
+      if (issuer) {
         fence_after_sync();
-        constexpr uint32_t ids = make_idesc_bf16(128, 128, false, false);
+        constexpr uint32_t ids = make_idesc_bf16(128, 64, false, false);
 #pragma unroll
-        for (int ks = 0; ks < K::HDP / 16; ++ks)
-          mma_bf16_ss(tmem + K::TM_S, make_smem_desc(aAq + ks * 4096, 2048, 128), make_smem_desc(aBk + ks * 4096, 2048, 128),
-                      ids, ks > 0);
-        commit(&bars[2]);
-        if (h + 2 < 6) issue_qkv(h + 2);
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+          for (int ks = 0; ks < K::HDP / 16; ++ks)
+            mma_bf16_ss_masked(tmem + tS, make_smem_desc(aAq + ks * 4096, 2048, 128),
+                               make_smem_desc(aBk + w * 1024 + ks * 4096, 2048, 128), ids, ks > 0,
+                               w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
+        commit(bar_s);
+        if (i < 2) issue_qkv(h + 2);
       }
-      // ---- softmax on this thread's half row (32 of the 64 keys of its own window) ----
-      mbar_wait(&bars[2], ph_s & 1); ph_s++;
+      // ---- softmax over the 64 keys of this row's window ----
+      mbar_wait(bar_s, ph_s & 1); ph_s++;
       fence_after_sync();
       {
-        uint32_t v[32];
-        tmem_ld_x32(lane_addr + K::TM_S + 64 * wsel + 32 * part, v);
-        wait_ld();
-        const float* tb = sTab + h * 225 + ((iy + 7) * 15 + ix + 7) - 60 * part;
-        float mx = -INFINITY;
+        uint32_t v[64];
+        {
+          uint32_t a[32], b[32];
+          tmem_ld_x32(lane_addr + tS, a);
+          tmem_ld_x32(lane_addr + tS + 32, b);
+          wait_ld();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) { v[j] = a[j]; v[32 + j] = b[j]; }
+        }
+        const float* tb = sTab + h * K::TBL + (iy + 7) * 24 + ix + 7;
+#pragma unroll
+        for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + tb[-((j >> 3) * 24 + (j & 7))]);
+        if (myreg >= 0) {
+#pragma unroll
+          for (int j = 0; j < 64; ++j)
+            if ((j < 32 ? mlo : mhi) & (1u << (j & 31))) v[j] = __float_as_uint(__uint_as_float(v[j]) + mask_val);
+        }
+        float mx = __uint_as_float(v[0]);
+#pragma unroll
+        for (int j = 1; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
+        float sum = 0.f;
+        uint32_t o[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          float t = __uint_as_float(v[j]) + tb[-((j >> 3) * 15 + (j & 7))];
-          v[j] = __float_as_uint(t);
-        }
-        if (wmask) {
-          const int* rg = sReg + 64 * wsel + 32 * part;
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (rg[j] != myreg) v[j] = __float_as_uint(__uint_as_float(v[j]) + mask_val);
-        }
-#pragma unroll
-        for (int j = 0; j < 32; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-        sRed[part * 128 + row] = mx;
-        pair_barrier(1 + (warp & 3));
-        mx = fmaxf(mx, sRed[(1 - part) * 128 + row]);
-        float sum = 0.f;
-        uint32_t o[16];
-#pragma unroll
-        for (int j = 0; j < 16; ++j) {
           const float p0 = ex2(__uint_as_float(v[2 * j]) - mx), p1 = ex2(__uint_as_float(v[2 * j + 1]) - mx);
           sum += p0 + p1;
           o[j] = pk2(p0, p1);
         }
-        psum[h] = sum;
-        uint8_t* dst = sP + (8 * wsel + 4 * part) * 2048 + row * 16;
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          *reinterpret_cast<uint4*>(dst + q * 2048) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+        psum[i] = sum;
+        tmem_st_x32(lane_addr + tS, o);                     // P (bf16 pairs) overwrites the first 32 columns of S
+        wait_st();
       }
-      fence_proxy_async();
       fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
+      wg_barrier(wg);
+      if (issuer) {
         fence_after_sync();
         constexpr uint32_t idv = make_idesc_bf16(128, K::HDV, false, true);
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks)
-          mma_bf16_ss(tmem + K::TM_O + h * K::HDV, make_smem_desc(aP + ks * 4096, 2048, 128),
-                      make_smem_desc(aBv + ks * 256, 128, 2048), idv, ks > 0);
-        commit(&bars[3]);
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_bf16_ts_masked(tmem + K::TM_O + h * K::HDV, tmem + tS + ks * 8,
+                               make_smem_desc(aBv + w * 1024 + ks * 256, 128, 2048), idv, ks > 0,
+                               w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
+        commit(bar_o);
       }
       ph_o++;
     }
-    // ---------------- O / rowsum -> A image for proj ----------------
-    mbar_wait(&bars[3], (ph_o - 1) & 1);
+    // ---------------- O / rowsum -> A image for proj (each warpgroup normalises its own three heads) ----------------
+    mbar_wait(bar_o, (ph_o - 1) & 1);
     fence_after_sync();
+    __syncthreads();                    // both warpgroups are past their last qkv MMA: the A image is dead
 #pragma unroll
-    for (int h = 0; h < 6; ++h) sSum[(part * 6 + h) * 128 + row] = psum[h];
-    __syncthreads();
-    {
+    for (int i = 0; i < 3; ++i) {
+      const int h = wg + 2 * i;
       constexpr int NC = (HD + 7) / 8 * 8;
+      float f[NC];
+      tmem_load_cols<NC>(lane_addr + K::TM_O + h * K::HDV, f);
+      const float inv = 1.0f / psum[i];
+      if (K::HDO == 16) {
 #pragma unroll
-      for (int hh = 0; hh < 3; ++hh) {
-        const int h = part * 3 + hh;
-        float f[NC];
-        tmem_load_cols<NC>(lane_addr + K::TM_O + h * K::HDV, f);
-        const float own = part ? psum[3 + hh] : psum[hh];
-        const float inv = 1.0f / (own + sSum[((1 - part) * 6 + h) * 128 + row]);
-        if (K::HDO == 16) {
+        for (int c8 = 0; c8 < 2; ++c8) {
+          uint32_t o[4];
 #pragma unroll
-          for (int c8 = 0; c8 < 2; ++c8) {
-            uint32_t o[4];
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const int d0 = c8 * 8 + 2 * q, d1 = d0 + 1;
-              o[q] = pk2(d0 < HD ? f[d0] * inv : 0.f, d1 < HD ? f[d1] * inv : 0.f);
-            }
-            *reinterpret_cast<uint4*>(sA + (2 * h + c8) * 2048 + row * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+          for (int q = 0; q < 4; ++q) {
+            const int d0 = c8 * 8 + 2 * q, d1 = d0 + 1;
+            o[q] = pk2(d0 < HD ? f[d0] * inv : 0.f, d1 < HD ? f[d1] * inv : 0.f);
           }
-        } else {   // HDO == 20: element k = 20h + d, written as 5 groups of 4 bf16 (8 bytes)
+          *reinterpret_cast<uint4*>(sA + (2 * h + c8) * 2048 + row * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      } else {   // HDO == 20: element k = 20h + d, written as 5 groups of 4 bf16 (8 bytes)
 #pragma unroll
-          for (int m = 0; m < 5; ++m) {
-            const int k = 20 * h + 4 * m;
-            const uint2 val = make_uint2(pk2(f[4 * m] * inv, f[4 * m + 1] * inv), pk2(f[4 * m + 2] * inv, f[4 * m + 3] * inv));
-            *reinterpret_cast<uint2*>(sA + (k >> 3) * 2048 + row * 16 + (k & 7) * 2) = val;
-          }
+        for (int m = 0; m < 5; ++m) {
+          const int k = 20 * h + 4 * m;
+          const uint2 val = make_uint2(pk2(f[4 * m] * inv, f[4 * m + 1] * inv), pk2(f[4 * m + 2] * inv, f[4 * m + 3] * inv));
+          *reinterpret_cast<uint2*>(sA + (k >> 3) * 2048 + row * 16 + (k & 7) * 2) = val;
         }
       }
     }
@@ -401,14 +400,14 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       for (int ks = 0; ks < K::KPROJ / 16; ++ks)
         mma_bf16_ss(tmem + K::TM_PROJ, make_smem_desc(aA + ks * 4096, 2048, 128),
                     make_smem_desc(aWproj + ks * 2 * (CP * 16), CP * 16, 128), idp, ks > 0);
-      commit(&bars[4]);
+      commit(&bars[6]);
     }
-    mbar_wait(&bars[4], ph_p & 1); ph_p++;
+    mbar_wait(&bars[6], ph_p & 1); ph_p++;
     fence_after_sync();
-    // ---------------- proj epilogue -> swizzled staging (in the dead A region) -> coalesced residual store ----------------
+    // ---------------- proj epilogue -> staging (in the dead A region) -> coalesced residual store ----------------
     {
       constexpr int NC = CP / 2;
-      const int cbeg = part * NC;
+      const int cbeg = wg * NC;
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 16) {
         uint32_t v[16];
@@ -426,8 +425,9 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     }
     fence_before_sync();
     __syncthreads();
-#pragma unroll 1
-    for (int g = warp; g < 16; g += 8) {
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+      const int g = warp + 8 * gi;
       const int r = g * 8 + (lane & 7);
       const int64_t win = tile * 2 + (g >> 3);
       if (win < geo.nwt) {

@@ -20,17 +20,24 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __nv_bfloat16*
   uint8_t* sA = smem;                         // K-major: (k/8)*2048 + r*16 + (k%8)*2
   uint8_t* sB = smem + (size_t)128 * K * 2;   // K-major: (k/8)*(N*16) + n*16 + (k%8)*2 ; MN-major: see below
 
-  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
 
   // stage A (zero rows >= 64 when m64 so stale smem cannot leak in)
   for (int idx = tid; idx < 128 * (K / 8); idx += 128) {
     const int r = idx % 128, kc = idx / 128;
     uint4 v = make_uint4(0, 0, 0, 0);
-    if (!m64 || r < 64) v = *reinterpret_cast<const uint4*>(A + (size_t)r * K + kc * 8);
+    if (m64 != 1 || r < 64) v = *reinterpret_cast<const uint4*>(A + (size_t)r * K + kc * 8);
     *reinterpret_cast<uint4*>(sA + (size_t)kc * 2048 + r * 16) = v;
   }
-  if (!b_mn_major) {
+  if (m64 == 2) {
+    const int N2 = 2 * N;
+    for (int idx = tid; idx < N2 * (K / 8); idx += 128) {
+      const int n = idx % N2, kc = idx / N2;
+      *reinterpret_cast<uint4*>(sB + (size_t)kc * (N2 * 16) + n * 16) =
+          *reinterpret_cast<const uint4*>(B + (size_t)n * K + kc * 8);
+    }
+  } else if (!b_mn_major) {
     for (int idx = tid; idx < N * (K / 8); idx += 128) {
       const int n = idx % N, kc = idx / N;
       *reinterpret_cast<uint4*>(sB + (size_t)kc * (N * 16) + n * 16) =
@@ -50,7 +57,40 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __nv_bfloat16*
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
 
-  if (tid == 0) {
+  if (m64 == 3) {
+    // stage A into TMEM columns [256, 256 + K/2): thread = row, packed bf16 pairs (k even in the low half)
+    for (int c0 = 0; c0 < K / 2; c0 += 8) {
+      uint32_t v[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = *reinterpret_cast<const uint32_t*>(A + (size_t)tid * K + 2 * (c0 + j));
+      tmem_st_x8(tmem + ((uint32_t)(warp * 32) << 16) + 256 + c0, v);
+    }
+    wait_st();
+    fence_before_sync();
+    __syncthreads();
+    fence_after_sync();
+  }
+  if (tid == 0 && m64 == 2) {
+    // lane-mask probe: rows 0-63 use B[0:N), rows 64-127 use B[N:2N), both into the same N columns
+    const uint32_t idesc = make_idesc_bf16(128, N, false, false);
+    for (int half = 0; half < 2; ++half)
+      for (int ks = 0; ks < K / 16; ++ks) {
+        const uint64_t da = make_smem_desc(smem_u32(sA) + ks * 2 * 2048, 2048, 128);
+        const uint64_t db = make_smem_desc(smem_u32(sB) + half * N * 16 + ks * 2 * (2 * N * 16), 2 * N * 16, 128);
+        mma_bf16_ss_masked(tmem, da, db, idesc, ks > 0 ? 1u : 0u, half ? 0xFFFFFFFFu : 0u, half ? 0xFFFFFFFFu : 0u,
+                           half ? 0u : 0xFFFFFFFFu, half ? 0u : 0xFFFFFFFFu);
+      }
+    commit(&bar);
+  } else if (tid == 0 && m64 == 3) {
+    const uint32_t idesc = make_idesc_bf16(128, N, false, b_mn_major != 0);
+    for (int ks = 0; ks < K / 16; ++ks) {
+      uint64_t db;
+      if (!b_mn_major) db = make_smem_desc(smem_u32(sB) + ks * 2 * (N * 16), N * 16, 128);
+      else db = make_smem_desc(smem_u32(sB) + ks * 2 * 128, 128, (K / 8) * 128);
+      mma_bf16_ts_masked(tmem, tmem + 256 + ks * 8, db, idesc, ks > 0 ? 1u : 0u, 0, 0, 0, 0);
+    }
+    commit(&bar);
+  } else if (tid == 0) {
     const uint32_t idesc = make_idesc_bf16(m64 ? 64 : 128, N, false, b_mn_major != 0);
     for (int ks = 0; ks < K / 16; ++ks) {
       const uint64_t da = make_smem_desc(smem_u32(sA) + ks * 2 * 2048, 2048, 128);
@@ -73,7 +113,7 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __nv_bfloat16*
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
+  if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 }  // namespace rdst
@@ -84,7 +124,7 @@ extern "C" int rdst_umma_selftest(const void* a_bf16, const void* b_bf16, float*
   RDST_REQUIRE(a_bf16 && b_bf16 && d, "rdst_umma_selftest: null pointer");
   RDST_REQUIRE(N >= 16 && N <= 256 && N % 16 == 0 && K >= 16 && K % 16 == 0 && K <= 256,
                "rdst_umma_selftest: need 16<=N<=256 (N%%16==0), 16<=K<=256 (K%%16==0); got N=%d K=%d", N, K);
-  const size_t smem = (size_t)128 * K * 2 + (size_t)N * K * 2;
+  const size_t smem = (size_t)128 * K * 2 + (size_t)(m64 == 2 ? 2 : 1) * N * K * 2;
   cudaError_t e = cudaFuncSetAttribute(umma_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) { set_error("rdst_umma_selftest: smem attr: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   umma_selftest_kernel<<<1, 128, smem, (cudaStream_t)stream>>>((const __nv_bfloat16*)a_bf16, (const __nv_bfloat16*)b_bf16,

@@ -163,8 +163,10 @@ def pack_attn_tc(wqkv, bqkv, wproj, bproj, table, c):
     wp = wproj.new_zeros(cp, kproj)
     for h in range(HEADS):
         wp[:, h * hdo:h * hdo + hd] = wproj[:, h * hd:(h + 1) * hd]
+    tab = table.new_zeros(HEADS, 15, 24)
+    tab[:, :, :15] = (table.t() * LOG2E).reshape(HEADS, 15, 15)
     return dict(wqkv_img=torch.cat(imgs).contiguous(), bqkv_tc=torch.cat(biases).contiguous(),
-                wproj_img=kmajor_image(wp), table_tc=(table.t() * LOG2E).contiguous())
+                wproj_img=kmajor_image(wp), table_tc=tab.contiguous())
 
 
 def pack_stl_tc(p):
