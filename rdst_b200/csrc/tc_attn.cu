@@ -89,13 +89,13 @@ __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, float (&f)[NCOL])
 
 struct WinGeom {
   int H, W, shift, nwx, nw_img;
-  int64_t nwt;
+  int nwt;             // total windows (B * nw_img), < 2^31
 };
 
 // token index (in the un-shifted, raster-ordered activation) of position (iy,ix) of window `win`; region id for the mask
-__device__ __forceinline__ int64_t win_token(const WinGeom& g, int64_t win, int iy, int ix, int& region, bool& edge) {
-  const int b = (int)(win / g.nw_img);
-  const int wl = (int)(win - (int64_t)b * g.nw_img);
+__device__ __forceinline__ int64_t win_token(const WinGeom& g, int win, int iy, int ix, int& region, bool& edge) {
+  const int b = win / g.nw_img;
+  const int wl = win - b * g.nw_img;
   const int wy = wl / g.nwx, wx = wl - wy * g.nwx;
   const int hs = wy * 8 + iy, ws = wx * 8 + ix;             // coordinates on the shifted frame
   int hh = hs + g.shift; if (hh >= g.H) hh -= g.H;          // shifted[h'] = x[(h'+s) mod H]   (:245)
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(256, 1)
 stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* __restrict__ Y, int64_t ldy,
                 const uint8_t* __restrict__ wqkv_img, const uint8_t* __restrict__ wproj_img,
                 const float* __restrict__ bqkv, const float* __restrict__ bproj, const float* __restrict__ table,
-                WinGeom geo, float mask_val) {
+                WinGeom geo, float mask_val, unsigned long long* __restrict__ dbg) {
   using K = AttnCfg<C_>;
   constexpr int CP = K::CP, HD = K::HD, NH = K::NH;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -174,32 +174,49 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t tS = K::TM_S + 64 * wg, tQ = K::TM_QKV + 64 * wg;
   const float inv_c = 1.0f / (float)C_;
-  const int64_t ntiles = (geo.nwt + 1) / 2;
+  const int ntiles = (geo.nwt + 1) / 2;
   uint32_t ph_q = 0, ph_s = 0, ph_o = 0, ph_p = 0;
   uint64_t* bar_q = &bars[wg];
   uint64_t* bar_s = &bars[2 + wg];
   uint64_t* bar_o = &bars[4 + wg];
   const bool issuer = row == 0;
+  // warp-uniform copies (shuffle broadcast) so that MMA descriptors live in uniform registers
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const int wg_u = warp_u >> 2;
+  const bool issuer_warp = (warp_u & 3) == 0;          // warp 0 of each warpgroup issues that warpgroup's MMAs
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+  const uint32_t tS_u = K::TM_S + 64 * wg_u, tQ_u = K::TM_QKV + 64 * wg_u;
+  const uint32_t aAq_u = smem_u32(smem + K::OFF_QKV) + wg_u * K::QKV_BYTES, aBk_u = aAq_u + K::AQ_BYTES, aBv_u = aBk_u + K::AQ_BYTES;
+  uint64_t* bar_q_u = &bars[wg_u];
+  uint64_t* bar_s_u = &bars[2 + wg_u];
+  uint64_t* bar_o_u = &bars[4 + wg_u];
 
-  auto issue_qkv = [&](int h) {      // warpgroup issuer only
+  int dbg_n = 0;
+  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && issuer;
+#define RDST_TSTAMP()                                                         \
+  do {                                                                        \
+    if (dbg_on && dbg_n < 64) dbg[wg * 64 + dbg_n++] = clock64();             \
+  } while (0)
+  auto issue_qkv = [&](int h) {      // one elected lane of the warpgroup's issuer warp; h is warp-uniform
     constexpr uint32_t idq = make_idesc_bf16(128, NH, false, false);
     const uint32_t wb = aWqkv + h * (NH * CP * 2);
 #pragma unroll
     for (int ks = 0; ks < CP / 16; ++ks)
-      mma_bf16_ss(tmem + tQ, make_smem_desc(aA + ks * 4096, 2048, 128), make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128),
+      mma_bf16_ss(tmem_u + tQ_u, make_smem_desc(aA + ks * 4096, 2048, 128), make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128),
                   idq, ks > 0);
-    commit(bar_q);
+    commit(bar_q_u);
   };
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     // ---------------- P1: gather two windows + LayerNorm -> A image ----------------
+    RDST_TSTAMP();   // 0: tile start
+    int64_t tok[2];
     {
       uint4 raw[2][K::NCH / 4];
-      int64_t tok[2];
 #pragma unroll
       for (int gi = 0; gi < 2; ++gi) {
         const int g = warp + 8 * gi;
-        const int64_t win = tile * 2 + (g >> 3);
+        const int win = tile * 2 + (g >> 3);
         int region = 0; bool edge = false;
         tok[gi] = -1;
         if (win < geo.nwt) tok[gi] = win_token(geo, win, g & 7, lane & 7, region, edge);
@@ -210,6 +227,7 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
           raw[gi][j] = tok[gi] >= 0 ? __ldg(reinterpret_cast<const uint4*>(X + tok[gi] * ldx) + c) : make_uint4(0, 0, 0, 0);
         }
       }
+      RDST_TSTAMP();   // P1a: loads issued
 #pragma unroll
       for (int gi = 0; gi < 2; ++gi) {
         const int r = (warp + 8 * gi) * 8 + (lane & 7);
@@ -250,12 +268,15 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
         }
       }
     }
+    RDST_TSTAMP();   // P1b: LN + STS done (this warp)
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (issuer) {
+    RDST_TSTAMP();   // 1: after P1 + sync
+    if (issuer_warp) {
       fence_after_sync();
-      issue_qkv(wg);
+      if (elect_one()) issue_qkv(wg_u);
+      __syncwarp();
     }
     // shift mask of this row as a 64-bit set of keys that belong to another region (edge windows only)
     const int myreg = sReg[row];
@@ -274,8 +295,10 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int h = wg + 2 * i;
+      RDST_TSTAMP();   // 2+6i: before qkv wait
       mbar_wait(bar_q, ph_q & 1); ph_q++;
       fence_after_sync();
+      RDST_TSTAMP();   // 3+6i: qkv ready
       {
         constexpr int NC = (3 * HD + 7) / 8 * 8;
         float f[NC];
@@ -294,22 +317,27 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       fence_proxy_async();
       fence_before_sync();
       wg_barrier(wg);
-      if (issuer) {
+      RDST_TSTAMP();   // 4+6i: drained + barrier
+      if (issuer_warp) {
         fence_after_sync();
-        constexpr uint32_t ids = make_idesc_bf16(128, 64, false, false);
+        if (elect_one()) {
+          constexpr uint32_t ids = make_idesc_bf16(128, 64, false, false);
 #pragma unroll
-        for (int w = 0; w < 2; ++w)
+          for (int w = 0; w < 2; ++w)
 #pragma unroll
-          for (int ks = 0; ks < K::HDP / 16; ++ks)
-            mma_bf16_ss_masked(tmem + tS, make_smem_desc(aAq + ks * 4096, 2048, 128),
-                               make_smem_desc(aBk + w * 1024 + ks * 4096, 2048, 128), ids, ks > 0,
-                               w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
-        commit(bar_s);
-        if (i < 2) issue_qkv(h + 2);
+            for (int ks = 0; ks < K::HDP / 16; ++ks)
+              mma_bf16_ss_masked(tmem_u + tS_u, make_smem_desc(aAq_u + ks * 4096, 2048, 128),
+                                 make_smem_desc(aBk_u + w * 1024 + ks * 4096, 2048, 128), ids, ks > 0,
+                                 w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
+          commit(bar_s_u);
+          if (i < 2) issue_qkv(wg_u + 2 * i + 2);
+        }
+        __syncwarp();
       }
       // ---- softmax over the 64 keys of this row's window ----
       mbar_wait(bar_s, ph_s & 1); ph_s++;
       fence_after_sync();
+      RDST_TSTAMP();   // 5+6i: S ready
       {
         uint32_t v[64];
         {
@@ -320,6 +348,7 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
 #pragma unroll
           for (int j = 0; j < 32; ++j) { v[j] = a[j]; v[32 + j] = b[j]; }
         }
+        RDST_TSTAMP();   // S loaded into registers
         const float* tb = sTab + h * K::TBL + (iy + 7) * 24 + ix + 7;
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + tb[-((j >> 3) * 24 + (j & 7))]);
@@ -328,41 +357,51 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
           for (int j = 0; j < 64; ++j)
             if ((j < 32 ? mlo : mhi) & (1u << (j & 31))) v[j] = __float_as_uint(__uint_as_float(v[j]) + mask_val);
         }
-        float mx = __uint_as_float(v[0]);
+        float m4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
 #pragma unroll
-        for (int j = 1; j < 64; ++j) mx = fmaxf(mx, __uint_as_float(v[j]));
-        float sum = 0.f;
+        for (int j = 4; j < 64; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
+        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        RDST_TSTAMP();   // bias + max done
+        float s4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t o[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
           const float p0 = ex2(__uint_as_float(v[2 * j]) - mx), p1 = ex2(__uint_as_float(v[2 * j + 1]) - mx);
-          sum += p0 + p1;
+          s4[j & 3] += p0 + p1;
           o[j] = pk2(p0, p1);
         }
-        psum[i] = sum;
+        psum[i] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
+        RDST_TSTAMP();   // exp + pack done
         tmem_st_x32(lane_addr + tS, o);                     // P (bf16 pairs) overwrites the first 32 columns of S
         wait_st();
       }
+      RDST_TSTAMP();   // 6+6i: softmax done (this thread)
       fence_before_sync();
       wg_barrier(wg);
-      if (issuer) {
+      RDST_TSTAMP();   // 7+6i: P barrier
+      if (issuer_warp) {
         fence_after_sync();
-        constexpr uint32_t idv = make_idesc_bf16(128, K::HDV, false, true);
+        if (elect_one()) {
+          constexpr uint32_t idv = make_idesc_bf16(128, K::HDV, false, true);
+          const uint32_t dO = tmem_u + K::TM_O + (wg_u + 2 * i) * K::HDV;
 #pragma unroll
-        for (int w = 0; w < 2; ++w)
+          for (int w = 0; w < 2; ++w)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            mma_bf16_ts_masked(tmem + K::TM_O + h * K::HDV, tmem + tS + ks * 8,
-                               make_smem_desc(aBv + w * 1024 + ks * 256, 128, 2048), idv, ks > 0,
-                               w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
-        commit(bar_o);
+            for (int ks = 0; ks < 4; ++ks)
+              mma_bf16_ts_masked(dO, tmem_u + tS_u + ks * 8, make_smem_desc(aBv_u + w * 1024 + ks * 256, 128, 2048), idv,
+                                 ks > 0, w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
+          commit(bar_o_u);
+        }
+        __syncwarp();
       }
       ph_o++;
     }
     // ---------------- O / rowsum -> A image for proj (each warpgroup normalises its own three heads) ----------------
+    RDST_TSTAMP();   // 20: heads issued
     mbar_wait(bar_o, (ph_o - 1) & 1);
     fence_after_sync();
     __syncthreads();                    // both warpgroups are past their last qkv MMA: the A image is dead
+    RDST_TSTAMP();   // 21: PV done + CTA sync
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int h = wg + 2 * i;
@@ -393,17 +432,30 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {
       fence_after_sync();
-      constexpr uint32_t idp = make_idesc_bf16(128, CP, false, false);
+      if (elect_one()) {
+        constexpr uint32_t idp = make_idesc_bf16(128, CP, false, false);
 #pragma unroll
-      for (int ks = 0; ks < K::KPROJ / 16; ++ks)
-        mma_bf16_ss(tmem + K::TM_PROJ, make_smem_desc(aA + ks * 4096, 2048, 128),
-                    make_smem_desc(aWproj + ks * 2 * (CP * 16), CP * 16, 128), idp, ks > 0);
-      commit(&bars[6]);
+        for (int ks = 0; ks < K::KPROJ / 16; ++ks)
+          mma_bf16_ss(tmem_u + K::TM_PROJ, make_smem_desc(aA + ks * 4096, 2048, 128),
+                      make_smem_desc(aWproj + ks * 2 * (CP * 16), CP * 16, 128), idp, ks > 0);
+        commit(&bars[6]);
+      }
+      __syncwarp();
     }
+    // residual rows: issue the global loads now so their latency hides under the proj MMA and its epilogue
+    uint4 xres[2][K::NCH / 4];
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi)
+#pragma unroll
+      for (int j = 0; j < K::NCH / 4; ++j)
+        xres[gi][j] = tok[gi] >= 0 ? __ldg(reinterpret_cast<const uint4*>(X + tok[gi] * ldx) + (lane >> 3) + 4 * j)
+                                   : make_uint4(0, 0, 0, 0);
+    RDST_TSTAMP();   // 22: O epilogue + sync + proj issued
     mbar_wait(&bars[6], ph_p & 1); ph_p++;
     fence_after_sync();
+    RDST_TSTAMP();   // 23: proj ready
     // ---------------- proj epilogue -> staging (in the dead A region) -> coalesced residual store ----------------
     {
       constexpr int NC = CP / 2;
@@ -425,19 +477,16 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     }
     fence_before_sync();
     __syncthreads();
+    RDST_TSTAMP();   // 24: staging written
 #pragma unroll
     for (int gi = 0; gi < 2; ++gi) {
-      const int g = warp + 8 * gi;
-      const int r = g * 8 + (lane & 7);
-      const int64_t win = tile * 2 + (g >> 3);
-      if (win < geo.nwt) {
-        int region; bool edge;
-        const int64_t t = win_token(geo, win, g & 7, lane & 7, region, edge);
+      const int r = (warp + 8 * gi) * 8 + (lane & 7);
+      if (tok[gi] >= 0) {
 #pragma unroll
         for (int j = 0; j < K::NCH / 4; ++j) {
           const int c = (lane >> 3) + 4 * j;
           const uint4 m = *reinterpret_cast<const uint4*>(sA + r * K::PITCH + ((c ^ (K::SWZ ? (r & 7) : 0)) * 16));
-          const uint4 x = __ldg(reinterpret_cast<const uint4*>(X + t * ldx) + c);
+          const uint4 x = xres[gi][j];
           const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, xw[4] = {x.x, x.y, x.z, x.w};
           uint32_t o[4];
 #pragma unroll
@@ -445,16 +494,20 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
             const float2 a = up2(mw[q]), b = up2(xw[q]);
             o[q] = pk2(a.x + b.x, a.y + b.y);
           }
-          *(reinterpret_cast<uint4*>(Y + t * ldy) + c) = make_uint4(o[0], o[1], o[2], o[3]);
+          *(reinterpret_cast<uint4*>(Y + tok[gi] * ldy) + c) = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
     }
     __syncthreads();
+    RDST_TSTAMP();   // 25: tile done
   }
+#undef RDST_TSTAMP
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
+
+static unsigned long long* g_attn_dbg = nullptr;
 
 template <int C_>
 static int launch_attn(const void* x, int64_t ldx, void* y, int64_t ldy, const void* wqkv, const void* wproj,
@@ -463,18 +516,23 @@ static int launch_attn(const void* x, int64_t ldx, void* y, int64_t ldy, const v
   using K = AttnCfg<C_>;
   WinGeom g;
   g.H = H; g.W = W; g.shift = shift; g.nwx = W / 8; g.nw_img = (H / 8) * (W / 8);
-  g.nwt = (int64_t)B * g.nw_img;
-  const int64_t ntiles = (g.nwt + 1) / 2;
+  g.nwt = B * g.nw_img;
+  const int64_t ntiles = ((int64_t)g.nwt + 1) / 2;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   auto k = stl_attn_kernel<C_>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) { set_error("rdst_stl_attn_fwd_bf16: smem attr (%d B): %s", K::SMEM, cudaGetErrorString(e)); return RDST_E_CUDA; }
   k<<<grid, 256, K::SMEM, st>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const uint8_t*)wqkv,
-                                (const uint8_t*)wproj, bqkv, bproj, table, g, -100.0f * 1.4426950408889634f);
+                                (const uint8_t*)wproj, bqkv, bproj, table, g, -100.0f * 1.4426950408889634f, g_attn_dbg);
   return RDST_OK;
 }
 
 }  // namespace rdst
+
+extern "C" int rdst_debug_attn_timing(void* device_buffer_128_u64) {
+  rdst::g_attn_dbg = (unsigned long long*)device_buffer_128_u64;
+  return RDST_OK;
+}
 
 extern "C" int rdst_stl_attn_fwd_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const void* wqkv_img,
                                       const void* wproj_img, const float* bqkv, const float* bproj, const float* table,

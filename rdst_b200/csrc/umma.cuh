@@ -68,6 +68,20 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
                : "memory");
 }
 
+// true in exactly one lane of a fully converged warp (use inside warp-uniform branches so that MMA operands
+// stay in uniform registers instead of being broadcast lane by lane)
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 __device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
 // generic-proxy smem writes -> visible to the async proxy (tcgen05.mma / bulk copies)
