@@ -3,12 +3,16 @@
 // Replaces norm2 + Mlp + residual of SwinTransformerBlock.forward (reference swin_transformer_sr.py:272, :23-29).
 // One persistent CTA per SM keeps both weight matrices resident in shared memory as ready-made UMMA operand
 // images and walks over 128-token tiles:
-//   P1  coalesced load of the tile (8 rows x 64 B per warp instruction), LayerNorm statistics by 2 shuffles,
-//       normalised bf16 rows written straight into the K-major A-operand image (conflict-free 128 B core matrices)
-//   P2  fc1 as two N-halves of tcgen05.mma (accumulators in TMEM), each committed to its own mbarrier
-//   P3  per half: tcgen05.ld -> +bias -> GELU -> bf16 -> second A-operand image; fc2's K-half is issued as soon as
-//       its hidden half is staged, so the tensor pipe runs under the GELU of the other half
-//   P5  tcgen05.ld of the fc2 accumulator -> +bias -> bf16 staging -> coalesced residual add and store
+//   P1a coalesced load of the tile (8 rows x 64 B per warp instruction) into a swizzled raw tile in shared memory,
+//       LayerNorm statistics by 2 shuffles
+//   P1b thread = token row: normalise -> packed bf16 pairs -> tcgen05.st: the A operand of fc1 lives in TMEM, so
+//       the MMAs read only the weights from shared memory (SS-mode A reads were the bottleneck: 4 KB per k-step)
+//   P2  fc1 as two N-halves of tcgen05.mma (A from TMEM), each committed to its own mbarrier; issue is warp-uniform
+//       (elect.sync) so descriptors stay in uniform registers
+//   P3  per half: tcgen05.ld -> +bias -> GELU -> packed bf16 -> tcgen05.st (hidden stays in TMEM as the A operand of
+//       fc2); fc2's K-half is issued as soon as its hidden half is staged
+//   P5  tcgen05.ld of the fc2 accumulator -> +bias +residual (raw tile) in the row mapping -> in-place bf16 ->
+//       coalesced copy out; TAIL variant: LayerNorm(y) -> TMEM -> growth projection MMA -> dense slice
 // Hidden activations never leave the SM.  LayerNorm gamma/beta are folded into fc1 by the host.
 #include "common.cuh"
 #include "umma.cuh"
@@ -46,44 +50,36 @@ struct MlpCfg {
   static constexpr int H1 = HP - H0;
   static constexpr int W1_BYTES = HP * CP * 2;
   static constexpr int W2_BYTES = CP * HP * 2;
-  static constexpr int A1_BYTES = 128 * CP * 2;
-  static constexpr int A2_BYTES = 128 * HP * 2;
-  static constexpr int PITCH = CP * 2 + 16;               // staging row pitch (bytes), conflict-free for 16 B accesses
+  static constexpr bool SWZ = (NCH == 8 || NCH == 16);    // raw tile rows: XOR-swizzled when NCH is a power of two
+  static constexpr int PITCH = SWZ ? CP * 2 : CP * 2 + 16;
+  static constexpr int XT_BYTES = 128 * PITCH;
+  static constexpr int WT_BYTES = 32 * CP * 2;
   static constexpr int OFF_W1 = 0;
   static constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
-  static constexpr int OFF_A1 = OFF_W2 + W2_BYTES;
-  static constexpr int OFF_A2 = OFF_A1 + A1_BYTES;
-  static constexpr int OFF_B1 = OFF_A2 + A2_BYTES;
+  static constexpr int OFF_XT = OFF_W2 + W2_BYTES;         // raw bf16 tile (residual source, later the output staging)
+  static constexpr int OFF_B1 = OFF_XT + XT_BYTES;
   static constexpr int OFF_B2 = OFF_B1 + HP * 4;
-  static constexpr int OFF_WT = OFF_B2 + CP * 4;           // fused DenseSTLayer tail: Linear(C -> 30, padded 32) image
-  static constexpr int WT_BYTES = 32 * CP * 2;
+  static constexpr int OFF_STAT = OFF_B2 + CP * 4;         // [128] (mean, rstd)
+  static constexpr int OFF_XCH = OFF_STAT + 128 * 8;       // [2][128] (sum, sumsq) exchange for the tail LayerNorm
+  static constexpr int OFF_WT = OFF_XCH + 2 * 128 * 8;     // fused DenseSTLayer tail: Linear(C -> 30, padded 32) image
   static constexpr int OFF_BT = OFF_WT + WT_BYTES;
   static constexpr int SMEM_PLAIN = OFF_WT;
   static constexpr int SMEM_TAIL = OFF_BT + 32 * 4;
-  static constexpr int SMEM = SMEM_PLAIN;
-  static constexpr int TM_FC1 = 0;                        // TMEM columns: fc1 accumulator [0,HP), fc2 at 256
-  static constexpr int TM_FC2 = 256;
+  // TMEM columns.  A operands live in TMEM (packed bf16 pairs, lane = token row): only weights are read from smem.
+  static constexpr int TM_FC1 = 0;                         // fc1 accumulator [0,HP); later the tail accumulator [0,32)
+  static constexpr int TM_FC2 = 256;                       // fc2 accumulator [256,256+CP)
+  static constexpr int TM_XH = 256;                        // normalised input [256,256+CP/2): dead before fc2 starts (in-order MMAs)
+  static constexpr int TM_HID = 384;                       // GELU(hidden) packed [384,384+HP/2)
   static_assert(HP % 16 == 0 && CP % 32 == 0 && H1 % 16 == 0 && H1 > 0, "tile shape");
-  static_assert(128 * PITCH <= A2_BYTES, "staging must fit in the dead A2 image");
-  static_assert(HP <= 256 && CP <= 128, "TMEM budget");
+  static_assert(HP <= 240 && CP <= 128 && TM_HID + HP / 2 <= 512, "TMEM budget");
 };
 
-// epilogue helper: 16 accumulator columns -> +bias -> (GELU) -> 16 bf16 = two 16-byte stores
-template <bool GELU, bool EXACT>
-__device__ __forceinline__ void epi16(uint32_t taddr, const float* __restrict__ bias, uint8_t* dst0, uint8_t* dst1) {
-  uint32_t v[16];
-  tmem_ld_x16(taddr, v);
-  wait_ld();
-  uint32_t o[8];
+// store 8 packed columns held in a larger register array
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
+  uint32_t a[8];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    float a = __uint_as_float(v[2 * j]) + bias[2 * j];
-    float b = __uint_as_float(v[2 * j + 1]) + bias[2 * j + 1];
-    if (GELU) { a = gelu_fn<EXACT>(a); b = gelu_fn<EXACT>(b); }
-    o[j] = pack_bf16x2(a, b);
-  }
-  *reinterpret_cast<uint4*>(dst0) = make_uint4(o[0], o[1], o[2], o[3]);
-  *reinterpret_cast<uint4*>(dst1) = make_uint4(o[4], o[5], o[6], o[7]);
+  for (int i = 0; i < 8; ++i) a[i] = v[i];
+  tmem_st_x8(taddr, a);
 }
 
 struct TailArgs {
@@ -104,12 +100,11 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
   __shared__ uint64_t bars[5];
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* sW1 = smem + C::OFF_W1;
-  uint8_t* sW2 = smem + C::OFF_W2;
-  uint8_t* sA1 = smem + C::OFF_A1;
-  uint8_t* sA2 = smem + C::OFF_A2;
+  uint8_t* sXT = smem + C::OFF_XT;
   float* sB1 = reinterpret_cast<float*>(smem + C::OFF_B1);
   float* sB2 = reinterpret_cast<float*>(smem + C::OFF_B2);
+  float2* sStat = reinterpret_cast<float2*>(smem + C::OFF_STAT);
+  float2* sXch = reinterpret_cast<float2*>(smem + C::OFF_XCH);
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) {
@@ -134,80 +129,104 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
 
-  const uint32_t aA1 = smem_u32(sA1), aA2 = smem_u32(sA2), aW1 = smem_u32(sW1), aW2 = smem_u32(sW2);
   const int row = tid & 127, half = tid >> 7;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int rsw = C::SWZ ? (row & 7) : 0;
+  // warp-uniform values for the MMA issuer (warp 0): descriptors stay in uniform registers
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+  const uint32_t aW1 = smem_u32(smem + C::OFF_W1), aW2 = smem_u32(smem + C::OFF_W2), aWT = smem_u32(smem + C::OFF_WT);
   const float inv_c = 1.0f / (float)creal;
   const int64_t ntiles = (T + 127) / 128;
   uint32_t parity = 0;
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
     const int64_t t0 = tile * 128;
-    // ---------------- P1: load + LayerNorm -> A1 ----------------
-#pragma unroll 1
-    for (int g = warp; g < 16; g += 8) {
-      const int r = g * 8 + (lane & 7);
-      const int64_t t = t0 + r;
-      uint4 raw[C::NCH / 4];
-      float s = 0.f;
+    // ---------------- P1a: coalesced load -> raw tile in smem, LayerNorm statistics ----------------
+    {
+      uint4 raw[2][C::NCH / 4];
 #pragma unroll
-      for (int j = 0; j < C::NCH / 4; ++j) {
-        const int c = (lane >> 3) + 4 * j;
-        raw[j] = t < T ? __ldg(reinterpret_cast<const uint4*>(X + t * ldx) + c) : make_uint4(0, 0, 0, 0);
-        const float2 f0 = unpack_bf16x2(raw[j].x), f1 = unpack_bf16x2(raw[j].y), f2 = unpack_bf16x2(raw[j].z),
-                     f3 = unpack_bf16x2(raw[j].w);
-        s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
+      for (int gi = 0; gi < 2; ++gi) {
+        const int64_t t = t0 + (warp + 8 * gi) * 8 + (lane & 7);
+#pragma unroll
+        for (int j = 0; j < C::NCH / 4; ++j)
+          raw[gi][j] = t < T ? __ldg(reinterpret_cast<const uint4*>(X + t * ldx) + (lane >> 3) + 4 * j) : make_uint4(0, 0, 0, 0);
       }
-      s += __shfl_xor_sync(0xffffffffu, s, 8);
-      s += __shfl_xor_sync(0xffffffffu, s, 16);
-      const float mean = s * inv_c;
-      float ss = 0.f;
 #pragma unroll
-      for (int j = 0; j < C::NCH / 4; ++j) {
-        const uint32_t w4[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+      for (int gi = 0; gi < 2; ++gi) {
+        const int r = (warp + 8 * gi) * 8 + (lane & 7);
+        const int sw = C::SWZ ? (r & 7) : 0;
+        float s = 0.f;
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 f = unpack_bf16x2(w4[q]);
-          ss += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+        for (int j = 0; j < C::NCH / 4; ++j) {
+          const float2 f0 = unpack_bf16x2(raw[gi][j].x), f1 = unpack_bf16x2(raw[gi][j].y), f2 = unpack_bf16x2(raw[gi][j].z),
+                       f3 = unpack_bf16x2(raw[gi][j].w);
+          s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
+          *reinterpret_cast<uint4*>(sXT + r * C::PITCH + ((((lane >> 3) + 4 * j) ^ sw) * 16)) = raw[gi][j];
         }
-      }
-      ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-      ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-      ss -= (float)(CP - creal) * mean * mean;                 // zero pads contributed mean^2 each
-      const float rstd = rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f);
+        s += __shfl_xor_sync(0xffffffffu, s, 8);
+        s += __shfl_xor_sync(0xffffffffu, s, 16);
+        const float mean = s * inv_c;
+        float ss = 0.f;
 #pragma unroll
-      for (int j = 0; j < C::NCH / 4; ++j) {
-        const int c = (lane >> 3) + 4 * j;
-        const uint32_t w4[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
-        uint32_t o[4];
+        for (int j = 0; j < C::NCH / 4; ++j) {
+          const uint32_t w4[4] = {raw[gi][j].x, raw[gi][j].y, raw[gi][j].z, raw[gi][j].w};
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 f = unpack_bf16x2(w4[q]);
-          o[q] = pack_bf16x2((f.x - mean) * rstd, (f.y - mean) * rstd);
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = unpack_bf16x2(w4[q]);
+            ss += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+          }
         }
-        *reinterpret_cast<uint4*>(sA1 + c * 2048 + r * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+        ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+        ss -= (float)(CP - creal) * mean * mean;                 // zero pads contributed mean^2 each
+        if ((lane >> 3) == 0) sStat[r] = make_float2(mean, rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f));
       }
     }
-    fence_proxy_async();
+    __syncthreads();
+    // ---------------- P1b: thread = token row: normalise its half row -> packed bf16 A operand in TMEM ----------------
+    {
+      const float2 st = sStat[row];
+      constexpr int NC = C::NCH / 2;                            // chunks per thread
+      uint32_t o[NC * 4];
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc) {
+        const int c = half * NC + cc;
+        const uint4 v = *reinterpret_cast<const uint4*>(sXT + row * C::PITCH + ((c ^ rsw) * 16));
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16x2(w4[q]);
+          o[cc * 4 + q] = pack_bf16x2((f.x - st.x) * st.y, (f.y - st.x) * st.y);
+        }
+      }
+      const uint32_t dst = lane_addr + C::TM_XH + half * NC * 4;
+#pragma unroll
+      for (int c0 = 0; c0 < NC * 4; c0 += 8) tmem_st8(dst + c0, o + c0);
+      wait_st();
+    }
     fence_before_sync();
     __syncthreads();
-    // ---------------- P2: fc1 (two N-halves) ----------------
-    if (tid == 0) {
+    // ---------------- P2: fc1 (two N-halves), A from TMEM ----------------
+    if (warp_u == 0) {
       fence_after_sync();
-      constexpr uint32_t id0 = make_idesc_bf16(128, C::H0, false, false);
-      constexpr uint32_t id1 = make_idesc_bf16(128, C::H1, false, false);
+      if (elect_one()) {
+        constexpr uint32_t id0 = make_idesc_bf16(128, C::H0, false, false);
+        constexpr uint32_t id1 = make_idesc_bf16(128, C::H1, false, false);
 #pragma unroll
-      for (int ks = 0; ks < CP / 16; ++ks)
-        mma_bf16_ss(tmem + C::TM_FC1, make_smem_desc(aA1 + ks * 4096, 2048, 128),
-                    make_smem_desc(aW1 + ks * 2 * (HP * 16), HP * 16, 128), id0, ks > 0);
-      commit(&bars[0]);
+        for (int ks = 0; ks < CP / 16; ++ks)
+          mma_bf16_ts_masked(tmem_u + C::TM_FC1, tmem_u + C::TM_XH + ks * 8,
+                             make_smem_desc(aW1 + ks * 2 * (HP * 16), HP * 16, 128), id0, ks > 0, 0, 0, 0, 0);
+        commit(&bars[0]);
 #pragma unroll
-      for (int ks = 0; ks < CP / 16; ++ks)
-        mma_bf16_ss(tmem + C::TM_FC1 + C::H0, make_smem_desc(aA1 + ks * 4096, 2048, 128),
-                    make_smem_desc(aW1 + C::H0 * 16 + ks * 2 * (HP * 16), HP * 16, 128), id1, ks > 0);
-      commit(&bars[1]);
+        for (int ks = 0; ks < CP / 16; ++ks)
+          mma_bf16_ts_masked(tmem_u + C::TM_FC1 + C::H0, tmem_u + C::TM_XH + ks * 8,
+                             make_smem_desc(aW1 + C::H0 * 16 + ks * 2 * (HP * 16), HP * 16, 128), id1, ks > 0, 0, 0, 0, 0);
+        commit(&bars[1]);
+      }
+      __syncwarp();
     }
-    // ---------------- P3: GELU epilogue per half, fc2 K-half issued behind it ----------------
+    // ---------------- P3: GELU epilogue per half -> packed hidden in TMEM; fc2 K-half issued behind it ----------------
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int hbase = h == 0 ? 0 : C::H0;
@@ -217,96 +236,96 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
       const int cend = hbase + (half == 0 ? w0 : hw);
       mbar_wait(&bars[h], parity);
       fence_after_sync();
-      for (int c0 = cbeg; c0 < cend; c0 += 16)
-        epi16<true, EXACT>(lane_addr + C::TM_FC1 + c0, sB1 + c0, sA2 + (c0 / 8) * 2048 + row * 16,
-                           sA2 + (c0 / 8 + 1) * 2048 + row * 16);
-      fence_proxy_async();
+      for (int c0 = cbeg; c0 < cend; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(lane_addr + C::TM_FC1 + c0, v);
+        wait_ld();
+        uint32_t o[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+          o[j] = pack_bf16x2(gelu_fn<EXACT>(__uint_as_float(v[2 * j]) + sB1[c0 + 2 * j]),
+                             gelu_fn<EXACT>(__uint_as_float(v[2 * j + 1]) + sB1[c0 + 2 * j + 1]));
+        tmem_st_x8(lane_addr + C::TM_HID + c0 / 2, o);
+      }
+      wait_st();
       fence_before_sync();
       __syncthreads();
-      if (tid == 0) {
+      if (warp_u == 0) {
         fence_after_sync();
-        constexpr uint32_t id2 = make_idesc_bf16(128, CP, false, false);
-        const int ks0 = hbase / 16, ks1 = (hbase + hw) / 16;
-        for (int ks = ks0; ks < ks1; ++ks)
-          mma_bf16_ss(tmem + C::TM_FC2, make_smem_desc(aA2 + ks * 4096, 2048, 128),
-                      make_smem_desc(aW2 + ks * 2 * (CP * 16), CP * 16, 128), id2, ks > 0);
-        commit(&bars[2 + h]);
+        if (elect_one()) {
+          constexpr uint32_t id2 = make_idesc_bf16(128, CP, false, false);
+          const int ks0 = hbase / 16, ks1 = (hbase + hw) / 16;
+          for (int ks = ks0; ks < ks1; ++ks)
+            mma_bf16_ts_masked(tmem_u + C::TM_FC2, tmem_u + C::TM_HID + ks * 8,
+                               make_smem_desc(aW2 + ks * 2 * (CP * 16), CP * 16, 128), id2, ks > 0, 0, 0, 0, 0);
+          commit(&bars[2 + h]);
+        }
+        __syncwarp();
       }
     }
-    // ---------------- P5: fc2 epilogue -> staging -> coalesced residual add + store ----------------
+    // ---------------- P5: fc2 epilogue in the row mapping: y = acc + b2 + x (raw tile) ----------------
     mbar_wait(&bars[2], parity);
     mbar_wait(&bars[3], parity);
     fence_after_sync();
-    uint8_t* stg = sA2;                                       // A2 is dead once fc2 has completed
     {
-      const int cbeg = half * (CP / 2), cend = cbeg + CP / 2;
-      for (int c0 = cbeg; c0 < cend; c0 += 16)
-        epi16<false, false>(lane_addr + C::TM_FC2 + c0, sB2 + c0, stg + row * C::PITCH + c0 * 2,
-                            stg + row * C::PITCH + c0 * 2 + 16);
+      constexpr int NC = CP / 2;                               // columns per thread
+      const int cb = half * NC;
+      float y[NC];
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int c0 = 0; c0 < NC; c0 += 16) {
+        uint32_t v[16];
+        tmem_ld_x16(lane_addr + C::TM_FC2 + cb + c0, v);
+        wait_ld();
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+          const int ch = (cb + c0) / 8 + q;
+          const uint4 xv = *reinterpret_cast<const uint4*>(sXT + row * C::PITCH + ((ch ^ rsw) * 16));
+          const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 xf = unpack_bf16x2(xw[e]);
+            const int k = c0 + q * 8 + 2 * e;
+            y[k] = __uint_as_float(v[q * 8 + 2 * e]) + sB2[cb + k] + xf.x;
+            y[k + 1] = __uint_as_float(v[q * 8 + 2 * e + 1]) + sB2[cb + k + 1] + xf.y;
+            s1 += y[k] + y[k + 1];
+            s2 += y[k] * y[k] + y[k + 1] * y[k + 1];
+            o[e] = pack_bf16x2(y[k], y[k + 1]);
+          }
+          if (!TAIL) *reinterpret_cast<uint4*>(sXT + row * C::PITCH + ((ch ^ rsw) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+      }
+      if (TAIL) {
+        // LayerNorm of the block output over the full row: the two column halves live in two warpgroups
+        sXch[half * 128 + row] = make_float2(s1, s2);
+        __syncthreads();
+        const float2 other = sXch[(1 - half) * 128 + row];
+        const float mean = (s1 + other.x) * inv_c;
+        const float var = fmaxf((s2 + other.y) * inv_c - mean * mean, 0.f);   // pads are exact zeros: they add nothing
+        const float rstd = rsqrtf(var + 1e-5f);
+        uint32_t o[NC / 2];
+#pragma unroll
+        for (int k = 0; k < NC; k += 2) o[k / 2] = pack_bf16x2((y[k] - mean) * rstd, (y[k + 1] - mean) * rstd);
+#pragma unroll
+        for (int c0 = 0; c0 < NC / 2; c0 += 8) tmem_st8(lane_addr + C::TM_XH + cb / 2 + c0, o + c0);
+        wait_st();
+      }
     }
     fence_before_sync();
     __syncthreads();
-#pragma unroll 1
-    for (int g = warp; g < 16; g += 8) {
-      const int r = g * 8 + (lane & 7);
-      const int64_t t = t0 + r;
-      float yv[C::NCH / 4][8];
-      float s = 0.f;
-#pragma unroll
-      for (int j = 0; j < C::NCH / 4; ++j) {
-        const int c = (lane >> 3) + 4 * j;
-        const uint4 m = *reinterpret_cast<const uint4*>(stg + r * C::PITCH + c * 16);
-        const uint4 x = t < T ? __ldg(reinterpret_cast<const uint4*>(X + t * ldx) + c) : make_uint4(0, 0, 0, 0);
-        const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, xw[4] = {x.x, x.y, x.z, x.w};
-        uint32_t o[4];
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 a = unpack_bf16x2(mw[q]), b = unpack_bf16x2(xw[q]);
-          yv[j][2 * q] = a.x + b.x;
-          yv[j][2 * q + 1] = a.y + b.y;
-          s += yv[j][2 * q] + yv[j][2 * q + 1];
-          o[q] = pack_bf16x2(yv[j][2 * q], yv[j][2 * q + 1]);
-        }
-        if (!TAIL && t < T) *(reinterpret_cast<uint4*>(Y + t * ldy) + c) = make_uint4(o[0], o[1], o[2], o[3]);
-      }
-      if (TAIL) {
-        // LayerNorm of the block output (fp32, never rounded) -> A image for the growth projection
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        const float mean = s * inv_c;
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < C::NCH / 4; ++j)
-#pragma unroll
-          for (int q = 0; q < 8; ++q) ss += (yv[j][q] - mean) * (yv[j][q] - mean);
-        ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-        ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-        ss -= (float)(CP - creal) * mean * mean;
-        const float rstd = rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f);
-#pragma unroll
-        for (int j = 0; j < C::NCH / 4; ++j) {
-          const int c = (lane >> 3) + 4 * j;
-          uint32_t o[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            o[q] = pack_bf16x2((yv[j][2 * q] - mean) * rstd, (yv[j][2 * q + 1] - mean) * rstd);
-          *reinterpret_cast<uint4*>(sA1 + c * 2048 + r * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-      }
-    }
     if (TAIL) {
-      fence_proxy_async();
-      fence_before_sync();
-      __syncthreads();
-      if (tid == 0) {
+      if (warp_u == 0) {
         fence_after_sync();
-        constexpr uint32_t idt = make_idesc_bf16(128, 32, false, false);
-        const uint32_t aWT = smem_u32(smem + C::OFF_WT);
+        if (elect_one()) {
+          constexpr uint32_t idt = make_idesc_bf16(128, 32, false, false);
 #pragma unroll
-        for (int ks = 0; ks < CP / 16; ++ks)
-          mma_bf16_ss(tmem + C::TM_FC1, make_smem_desc(aA1 + ks * 4096, 2048, 128),
-                      make_smem_desc(aWT + ks * 2 * (32 * 16), 32 * 16, 128), idt, ks > 0);
-        commit(&bars[4]);
+          for (int ks = 0; ks < CP / 16; ++ks)
+            mma_bf16_ts_masked(tmem_u + C::TM_FC1, tmem_u + C::TM_XH + ks * 8,
+                               make_smem_desc(aWT + ks * 2 * (32 * 16), 32 * 16, 128), idt, ks > 0, 0, 0, 0, 0);
+          commit(&bars[4]);
+        }
+        __syncwarp();
       }
       mbar_wait(&bars[4], parity);
       fence_after_sync();
@@ -328,8 +347,23 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
         }
       }
       fence_before_sync();
+    } else {
+      // coalesced copy of the finished tile to global memory
+#pragma unroll
+      for (int gi = 0; gi < 2; ++gi) {
+        const int r = (warp + 8 * gi) * 8 + (lane & 7);
+        const int64_t t = t0 + r;
+        const int sw = C::SWZ ? (r & 7) : 0;
+        if (t < T) {
+#pragma unroll
+          for (int j = 0; j < C::NCH / 4; ++j) {
+            const int c = (lane >> 3) + 4 * j;
+            *(reinterpret_cast<uint4*>(Y + t * ldy) + c) = *reinterpret_cast<const uint4*>(sXT + r * C::PITCH + ((c ^ sw) * 16));
+          }
+        }
+      }
     }
-    __syncthreads();        // staging (A2) and TMEM are reused by the next tile
+    __syncthreads();        // raw tile / TMEM are reused by the next tile
   }
   fence_before_sync();
   __syncthreads();
