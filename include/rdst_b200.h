@@ -101,6 +101,47 @@ int rdst_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const flo
 int rdst_last_conv_fwd(const void* x, int64_t ldx, const float* w, float bias, float out_scale, float out_bias,
                        float* img, int B, int H, int W, int Cin, int dtype, void* stream);
 
+/* ---- backward kernels (fp32, CUDA cores): the training path of the module ------------------------------ */
+/* Data gradients reuse the forward kernels: dX = dY.W is rdst_linear_fwd with the transposed weight; the conv
+ * data gradient is rdst_conv3x3_fwd with the flipped/transposed filter.  The entry points below add the rest. */
+
+/* dW[n][k] += sum_t dY[t][n] * X[t][k]  and, if db != NULL, db[n] += sum_t dY[t][n]   (fp32 atomics over token splits).
+ * conv != 0: X rows are 3x3 neighbourhoods gathered from a [B*H*W][ldx] map (K = 9*Cin, Cin % 64 == 0), i.e. the
+ * weight gradient of rdst_conv3x3_fwd.  Weight gradient of nn.Linear / nn.Conv2d on the path. */
+int rdst_gemm_tn_acc(const float* dy, int64_t ldy, const float* x, int64_t ldx, float* dw, float* db, int64_t T,
+                     int N, int K, int conv, int B, int H, int W, int Cin, void* stream);
+
+/* Affine-free LayerNorm over `creal` real of K stored channels (dense_layout != 0: pads at [60,64) and the last two
+ * of every 32-block after 64): y = (x-mean)*rstd, pads 0.  Backward: dx = rstd*(g - mean(g) - xhat*mean(g*xhat)) + resid + resid2
+ * (both optional; dx may alias resid2 for in-place accumulation). */
+int rdst_lnhat_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t T, int K, int creal, int dense_layout,
+                   void* stream);
+int rdst_lnhat_bwd(const float* dxhat, int64_t ldd, const float* x, int64_t ldx, const float* resid, int64_t ldr,
+                   const float* resid2, int64_t ldr2, float* dx, int64_t ldo, int64_t T, int K, int creal,
+                   int dense_layout, void* stream);
+
+/* Backward of rdst_layernorm_fwd (affine, * scale): dx (may be NULL), dgamma += , dbeta += . */
+int rdst_layernorm_bwd(const float* dy, int64_t ldd, const float* x, int64_t ldx, const float* gamma, float* dx,
+                       int64_t ldo, float* dgamma, float* dbeta, int64_t T, int creal, float scale, void* stream);
+
+/* y[t][n] += alpha * x[t][n] (gradient accumulation at residual joins). */
+int rdst_axpy(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t T, int N, float alpha, void* stream);
+
+/* Inverse of the pixel-shuffle store of rdst_conv3x3_fwd(shuffle=2): z[t][s*G+c] = u[(b,2y+dy,2x+dx)][c], s = 2dy+dx
+ * (gradient of nn.PixelShuffle(2) in the token-major layout). */
+int rdst_pixel_unshuffle2(const float* u, int64_t ldu, float* z, int64_t ldz, int B, int H, int W, int G, void* stream);
+
+/* Exact-erf GELU on a [T][N] matrix, forward and backward (dx = dy * gelu'(x)). */
+int rdst_gelu_fwd(const float* x, int64_t ldx, float* y, int64_t ldy, int64_t T, int N, void* stream);
+int rdst_gelu_bwd(const float* x, int64_t ldx, const float* dy, int64_t ldd, float* dx, int64_t ldo, int64_t T, int N,
+                  void* stream);
+
+/* Backward of rdst_window_attention_fwd: dqkv [T][ldg] (q|k|v gradients, same layout as qkv) is overwritten,
+ * dtable (225, heads) is accumulated. */
+int rdst_window_attention_bwd(const float* qkv, int64_t ldq, const float* table, const float* dout, int64_t ldo,
+                              float* dqkv, int64_t ldg, float* dtable, int B, int H, int W, int C, int heads, int shift,
+                              void* stream);
+
 /* ---- tcgen05 / TMEM kernels (bf16 operands, fp32 accumulate), sm_100a only ---------------------------- */
 
 /* Fused Swin MLP:  Y[t] = X[t] + fc2( GELU( fc1( LNhat(X[t]) ) ) ),  bf16 storage, T tokens, C in {60,90,120}

@@ -26,6 +26,15 @@ _SIGNATURES = {
     "rdst_head_fwd": (C.c_int, [_vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]),
     "rdst_layernorm_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _f, _i, _vp]),
     "rdst_last_conv_fwd": (C.c_int, [_vp, _i64, _vp, _f, _f, _f, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rdst_gemm_tn_acc": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rdst_lnhat_fwd": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp]),
+    "rdst_lnhat_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _vp]),
+    "rdst_axpy": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i, _f, _vp]),
+    "rdst_pixel_unshuffle2": (C.c_int, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]),
+    "rdst_layernorm_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _vp, _vp, _i64, _i, _f, _vp]),
+    "rdst_gelu_fwd": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i, _vp]),
+    "rdst_gelu_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp]),
+    "rdst_window_attention_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rdst_stl_mlp_fwd_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "rdst_stl_attn_fwd_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rdst_conv3x3_fwd_bf16_tc": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _i, _vp]),

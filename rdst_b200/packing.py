@@ -19,6 +19,25 @@ DENSE_LD = 160          # 64 (trunk, 60 real) + 3 * 32 (growth, 30 real)
 FEAT_LD = 64
 
 
+_DIFFERENTIABLE = False
+
+
+class differentiable:
+    """Context manager: packing keeps the autograd graph to the parameters (training path)."""
+
+    def __enter__(self):
+        global _DIFFERENTIABLE
+        self._old, _DIFFERENTIABLE = _DIFFERENTIABLE, True
+
+    def __exit__(self, *exc):
+        global _DIFFERENTIABLE
+        _DIFFERENTIABLE = self._old
+
+
+def _f(t):
+    return t.float() if _DIFFERENTIABLE else t.detach().float()
+
+
 def padded_width(c):
     """Stored width of a dense-block activation with c = 60 + 30*j real channels."""
     j = (c - EMBED) // GROWTH
@@ -57,7 +76,7 @@ def fold_ln(w, b, gamma, beta):
 
 def pack_stl(blk, c):
     """blk: Swin block parameter container (norm1, attn.{qkv,proj,relative_position_bias_table}, norm2, mlp)."""
-    f = lambda t: t.detach().float()
+    f = _f
     cp = padded_width(c)
     pos = channel_positions(c, blk.norm1.weight.device)
     hd = c // HEADS
@@ -86,7 +105,7 @@ def pack_stl(blk, c):
 
 def pack_dstl_tail(dstl, c, dense_scale):
     """LN(C) -> Linear(C, growth), written as a 32-wide slice (30 real) of the dense buffer."""
-    f = lambda t: t.detach().float()
+    f = _f
     cp = padded_width(c)
     pos = channel_positions(c, dstl.tail[0].weight.device)
     w, b = fold_ln(f(dstl.tail[1].weight), f(dstl.tail[1].bias), f(dstl.tail[0].weight), f(dstl.tail[0].bias))
@@ -98,27 +117,27 @@ def pack_dstl_tail(dstl, c, dense_scale):
 
 def pack_conv(weight, bias, cin_pos, cin_width, n_pad):
     """Conv2d weight (N, Cin, 3, 3) -> [n_pad][9][cin_width] (tap = ky*3+kx), bias -> [n_pad]."""
-    w = weight.detach().float()
+    w = _f(weight)
     n, cin = w.shape[0], w.shape[1]
     wt = w.permute(0, 2, 3, 1).reshape(n, 9, cin)
     out = w.new_zeros(n_pad, 9, cin_width)
     out[:n, :, cin_pos] = wt
     b = w.new_zeros(n_pad)
-    b[:n] = bias.detach().float()
+    b[:n] = _f(bias)
     return out.contiguous(), b.contiguous()
 
 
 def pack_upconv(weight, bias, group=FEAT_LD):
     """UpSampler conv (4*F, F, 3, 3) + PixelShuffle(2): row order becomes (sub-pixel s = 2*dy+dx, channel c),
     s-major, each group padded to `group` rows; reference out-channel index is c*4 + s."""
-    w = weight.detach().float()
+    w = _f(weight)
     f4, fin = w.shape[0], w.shape[1]
     fo = f4 // 4
     wt = w.permute(0, 2, 3, 1).reshape(fo, 4, 9, fin)          # [c][s][tap][cin]
     out = w.new_zeros(4, group, 9, FEAT_LD)
     out[:, :fo, :, :fin] = wt.permute(1, 0, 2, 3)
     b = w.new_zeros(4, group)
-    b[:, :fo] = bias.detach().float().reshape(fo, 4).t()
+    b[:, :fo] = _f(bias).reshape(fo, 4).t()
     return out.reshape(4 * group, 9, FEAT_LD).contiguous(), b.reshape(-1).contiguous()
 
 
