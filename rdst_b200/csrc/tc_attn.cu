@@ -5,7 +5,10 @@
 // :110-141, :211-232).
 //
 // One persistent CTA per SM keeps the qkv / proj weights resident in shared memory as UMMA operand images and
-// walks over tiles of 128 tokens = two 8x8 windows stacked on the 128 TMEM lanes:
+// walks over tiles of 128 tokens = two 8x8 windows stacked on the 128 TMEM lanes.  Two warpgroups work on alternate
+// heads.  All A operands (normalised input, Q, P, normalised O) are packed 16-bit pairs in TMEM written by the thread
+// that owns the token row, so tcgen05.mma only reads weights / K / V from shared memory; the two windows of a tile
+// share accumulator columns through the MMA's disable-output-lane mask (rows 0-63 / 64-127):
 //   P1   gather of the two windows by index arithmetic (cyclic shift and window partition never materialise),
 //        LayerNorm statistics by 2 shuffles, normalised bf16 rows -> K-major A image
 //   per head h (6):
@@ -50,28 +53,32 @@ struct AttnCfg {
   static constexpr int TBL = 15 * 24;                       // bias table per head, row pitch 24 (bank-conflict free)
   static constexpr int WQKV_BYTES = 6 * NH * CP * 2;
   static constexpr int WPROJ_BYTES = CP * KPROJ * 2;
-  static constexpr int A1_BYTES = 128 * CP * 2;
-  static constexpr int AO_BYTES = 128 * KPROJ * 2;
-  static constexpr bool SWZ = (CP == 128);                  // staging: XOR-swizzled 256 B rows, else padded rows
+  static constexpr bool SWZ = (NCH == 8 || NCH == 16);      // raw tile: XOR-swizzled rows, else padded rows
   static constexpr int PITCH = SWZ ? CP * 2 : CP * 2 + 16;
-  static constexpr int STG_BYTES = 128 * PITCH;
-  static constexpr int AREG0 = A1_BYTES > AO_BYTES ? A1_BYTES : AO_BYTES;
-  static constexpr int AREG_BYTES = AREG0 > STG_BYTES ? AREG0 : STG_BYTES;       // A1, later Ao, later staging
-  static constexpr int AQ_BYTES = 128 * HDP * 2;            // Q image == K image size
-  static constexpr int BV_BYTES = 128 * HDV * 2;
-  static constexpr int QKV_BYTES = 2 * AQ_BYTES + BV_BYTES; // per warpgroup: Q, K, V images of the head in flight
+  static constexpr int XT_BYTES = 128 * PITCH;
+  static constexpr int BK_BYTES = 128 * HDP * 2;            // K image (K-major)
+  static constexpr int BV_BYTES = 128 * HDV * 2;            // V image (MN-major, fp16)
+  static constexpr int KV_BYTES = BK_BYTES + BV_BYTES;      // per warpgroup
   static constexpr int OFF_WQKV = 0;
   static constexpr int OFF_WPROJ = OFF_WQKV + WQKV_BYTES;
-  static constexpr int OFF_A = OFF_WPROJ + WPROJ_BYTES;
-  static constexpr int OFF_QKV = OFF_A + AREG_BYTES;        // [2 warpgroups][Q | K | V]
-  static constexpr int OFF_TAB = OFF_QKV + 2 * QKV_BYTES;
+  static constexpr int OFF_XT = OFF_WPROJ + WPROJ_BYTES;    // raw bf16 tile: LN source, residual, output staging
+  static constexpr int OFF_KV = OFF_XT + XT_BYTES;          // [2 warpgroups][K | V]
+  static constexpr int OFF_TAB = OFF_KV + 2 * KV_BYTES;
   static constexpr int OFF_BQKV = OFF_TAB + 6 * TBL * 4;
   static constexpr int OFF_BPROJ = OFF_BQKV + 6 * NH * 4;
   static constexpr int OFF_SREG = OFF_BPROJ + CP * 4;
-  static constexpr int SMEM = OFF_SREG + 128 * 4;
-  // TMEM columns: per-warpgroup qkv [0,64),[64,128); per-warpgroup S/P [128,192),[192,256); O [256, 256+6*HDV); proj [0,CP)
-  static constexpr int TM_QKV = 0, TM_S = 128, TM_O = 256, TM_PROJ = 0;
+  static constexpr int OFF_STAT = OFF_SREG + 128 * 4;
+  static constexpr int SMEM = OFF_STAT + 128 * 8;
+  // TMEM columns.  Every A operand lives in TMEM (packed 16-bit pairs, lane = token row); shared memory only
+  // feeds the B operands (weights, K, V).
+  static constexpr int TM_QKV = 0;      // per-warpgroup qkv accumulator [0,64),[64,128); its first HDP/2 columns are
+                                        // then overwritten with the packed Q operand of S = Q K^T
+  static constexpr int TM_S = 128;      // per-warpgroup S [128,192),[192,256); first 32 columns become packed fp16 P
+  static constexpr int TM_O = 256;      // O accumulators, 6 heads x HDV columns
+  static constexpr int TM_XH = 448;     // normalised input (A of qkv), later normalised O (A of proj): <= 64 columns
+  static constexpr int TM_PROJ = 0;     // proj accumulator [0,CP) (qkv accumulators are dead by then)
   static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(TM_O + 6 * HDV <= TM_XH && CP / 2 <= 64 && KPROJ / 2 <= 64, "TMEM budget");
 };
 
 // load NCOL (multiple of 8) consecutive accumulator columns of this thread's TMEM lane
@@ -109,8 +116,18 @@ __device__ __forceinline__ int64_t win_token(const WinGeom& g, int win, int iy, 
 
 __device__ __forceinline__ void wg_barrier(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
 
-// bf16 pairs of 8 consecutive accumulator values (+bias), zero beyond `valid`
-template <int OFFSET, int HD>
+__device__ __forceinline__ uint32_t pk2h(float a, float b) {          // two floats -> packed fp16 pair
+  __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {              // two fp16 exp2 per MUFU op
+  uint32_t y;
+  asm("ex2.approx.f16x2 %0, %1;" : "=r"(y) : "r"(x));
+  return y;
+}
+
+// 8 consecutive accumulator values (+bias) as four packed 16-bit pairs, zero beyond HD
+template <int OFFSET, int HD, bool HALF>
 __device__ __forceinline__ uint4 pack8(const float* f, const float* bias, int c8) {
   uint32_t o[4];
 #pragma unroll
@@ -118,7 +135,7 @@ __device__ __forceinline__ uint4 pack8(const float* f, const float* bias, int c8
     const int d0 = c8 * 8 + 2 * q, d1 = d0 + 1;
     const float a = d0 < HD ? f[OFFSET + d0] + bias[OFFSET + d0] : 0.f;
     const float b = d1 < HD ? f[OFFSET + d1] + bias[OFFSET + d1] : 0.f;
-    o[q] = pk2(a, b);
+    o[q] = HALF ? pk2h(a, b) : pk2(a, b);
   }
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
@@ -137,14 +154,14 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = tid >> 7;              // warpgroup: owns heads wg, wg+2, wg+4
   const int row = tid & 127;
-  uint8_t* sA = smem + K::OFF_A;
-  uint8_t* sAq = smem + K::OFF_QKV + wg * K::QKV_BYTES;
-  uint8_t* sBk = sAq + K::AQ_BYTES;
-  uint8_t* sBv = sBk + K::AQ_BYTES;
+  uint8_t* sXT = smem + K::OFF_XT;
+  uint8_t* sBk = smem + K::OFF_KV + wg * K::KV_BYTES;
+  uint8_t* sBv = sBk + K::BK_BYTES;
   float* sTab = reinterpret_cast<float*>(smem + K::OFF_TAB);
   float* sBqkv = reinterpret_cast<float*>(smem + K::OFF_BQKV);
   float* sBproj = reinterpret_cast<float*>(smem + K::OFF_BPROJ);
   int* sReg = reinterpret_cast<int*>(smem + K::OFF_SREG);
+  float2* sStat = reinterpret_cast<float2*>(smem + K::OFF_STAT);
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) {
@@ -156,9 +173,9 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
                                                 : wproj_img + (size_t)(i - K::WQKV_BYTES / 16) * 16;
     *reinterpret_cast<uint4*>(smem + (size_t)i * 16) = __ldg(reinterpret_cast<const uint4*>(src));
   }
-  // Q/K/V images: K / N pads must be (and stay) zero
-  for (int i = tid; i < 2 * K::QKV_BYTES / 16; i += 256)
-    *reinterpret_cast<uint4*>(smem + K::OFF_QKV + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+  // K / V images: K-dim / N-dim pads must be (and stay) zero
+  for (int i = tid; i < 2 * K::KV_BYTES / 16; i += 256)
+    *reinterpret_cast<uint4*>(smem + K::OFF_KV + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 6 * K::TBL; i += 256) sTab[i] = table[i];
   for (int i = tid; i < 6 * NH; i += 256) sBqkv[i] = bqkv[i];
   for (int i = tid; i < CP; i += 256) sBproj[i] = bproj[i];
@@ -167,112 +184,131 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t aA = smem_u32(sA), aAq = smem_u32(sAq), aBk = smem_u32(sBk), aBv = smem_u32(sBv);
-  const uint32_t aWqkv = smem_u32(smem + K::OFF_WQKV), aWproj = smem_u32(smem + K::OFF_WPROJ);
 
   const int wsel = row >> 6, irow = row & 63, iy = irow >> 3, ix = irow & 7;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t tS = K::TM_S + 64 * wg, tQ = K::TM_QKV + 64 * wg;
+  const int rsw = K::SWZ ? (row & 7) : 0;
   const float inv_c = 1.0f / (float)C_;
   const int ntiles = (geo.nwt + 1) / 2;
   uint32_t ph_q = 0, ph_s = 0, ph_o = 0, ph_p = 0;
   uint64_t* bar_q = &bars[wg];
   uint64_t* bar_s = &bars[2 + wg];
   uint64_t* bar_o = &bars[4 + wg];
-  const bool issuer = row == 0;
   // warp-uniform copies (shuffle broadcast) so that MMA descriptors live in uniform registers
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const int wg_u = warp_u >> 2;
   const bool issuer_warp = (warp_u & 3) == 0;          // warp 0 of each warpgroup issues that warpgroup's MMAs
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
   const uint32_t tS_u = K::TM_S + 64 * wg_u, tQ_u = K::TM_QKV + 64 * wg_u;
-  const uint32_t aAq_u = smem_u32(smem + K::OFF_QKV) + wg_u * K::QKV_BYTES, aBk_u = aAq_u + K::AQ_BYTES, aBv_u = aBk_u + K::AQ_BYTES;
+  const uint32_t aWqkv = smem_u32(smem + K::OFF_WQKV), aWproj = smem_u32(smem + K::OFF_WPROJ);
+  const uint32_t aBk_u = smem_u32(smem + K::OFF_KV) + wg_u * K::KV_BYTES, aBv_u = aBk_u + K::BK_BYTES;
   uint64_t* bar_q_u = &bars[wg_u];
   uint64_t* bar_s_u = &bars[2 + wg_u];
   uint64_t* bar_o_u = &bars[4 + wg_u];
+  const bool stamper = row == 0;
 
   int dbg_n = 0;
-  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && issuer;
+  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && stamper;
 #define RDST_TSTAMP()                                                         \
   do {                                                                        \
     if (dbg_on && dbg_n < 64) dbg[wg * 64 + dbg_n++] = clock64();             \
   } while (0)
+
   auto issue_qkv = [&](int h) {      // one elected lane of the warpgroup's issuer warp; h is warp-uniform
     constexpr uint32_t idq = make_idesc_bf16(128, NH, false, false);
     const uint32_t wb = aWqkv + h * (NH * CP * 2);
 #pragma unroll
     for (int ks = 0; ks < CP / 16; ++ks)
-      mma_bf16_ss(tmem_u + tQ_u, make_smem_desc(aA + ks * 4096, 2048, 128), make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128),
-                  idq, ks > 0);
+      mma_bf16_ts_masked(tmem_u + tQ_u, tmem_u + K::TM_XH + ks * 8, make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128),
+                         idq, ks > 0, 0, 0, 0, 0);
     commit(bar_q_u);
   };
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
-    // ---------------- P1: gather two windows + LayerNorm -> A image ----------------
-    RDST_TSTAMP();   // 0: tile start
-    int64_t tok[2];
-    {
-      uint4 raw[2][K::NCH / 4];
+  // coalesced-mapping state of the tile in flight and of the prefetched next tile
+  uint4 raw[2][K::NCH / 4];
+  int64_t tok[2];
+  int regv[2];
+  auto prefetch = [&](int tile) {
 #pragma unroll
-      for (int gi = 0; gi < 2; ++gi) {
-        const int g = warp + 8 * gi;
-        const int win = tile * 2 + (g >> 3);
-        int region = 0; bool edge = false;
-        tok[gi] = -1;
-        if (win < geo.nwt) tok[gi] = win_token(geo, win, g & 7, lane & 7, region, edge);
-        if ((lane >> 3) == 0) sReg[g * 8 + (lane & 7)] = edge ? region : -1;
+    for (int gi = 0; gi < 2; ++gi) {
+      const int g = warp + 8 * gi;
+      const int win = tile * 2 + (g >> 3);
+      int region = 0; bool edge = false;
+      tok[gi] = -1;
+      if (tile < ntiles && win < geo.nwt) tok[gi] = win_token(geo, win, g & 7, lane & 7, region, edge);
+      regv[gi] = edge ? region : -1;
 #pragma unroll
-        for (int j = 0; j < K::NCH / 4; ++j) {
-          const int c = (lane >> 3) + 4 * j;
-          raw[gi][j] = tok[gi] >= 0 ? __ldg(reinterpret_cast<const uint4*>(X + tok[gi] * ldx) + c) : make_uint4(0, 0, 0, 0);
-        }
-      }
-      RDST_TSTAMP();   // P1a: loads issued
-#pragma unroll
-      for (int gi = 0; gi < 2; ++gi) {
-        const int r = (warp + 8 * gi) * 8 + (lane & 7);
-        float s = 0.f;
-#pragma unroll
-        for (int j = 0; j < K::NCH / 4; ++j) {
-          const float2 f0 = up2(raw[gi][j].x), f1 = up2(raw[gi][j].y), f2 = up2(raw[gi][j].z), f3 = up2(raw[gi][j].w);
-          s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        const float mean = s * inv_c;
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < K::NCH / 4; ++j) {
-          const uint32_t w4[4] = {raw[gi][j].x, raw[gi][j].y, raw[gi][j].z, raw[gi][j].w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 f = up2(w4[q]);
-            ss += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
-          }
-        }
-        ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-        ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-        ss -= (float)(CP - C_) * mean * mean;
-        const float rstd = rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f);
-#pragma unroll
-        for (int j = 0; j < K::NCH / 4; ++j) {
-          const int c = (lane >> 3) + 4 * j;
-          const uint32_t w4[4] = {raw[gi][j].x, raw[gi][j].y, raw[gi][j].z, raw[gi][j].w};
-          uint32_t o[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 f = up2(w4[q]);
-            o[q] = pk2((f.x - mean) * rstd, (f.y - mean) * rstd);
-          }
-          *reinterpret_cast<uint4*>(sA + c * 2048 + r * 16) = make_uint4(o[0], o[1], o[2], o[3]);
-        }
-      }
+      for (int j = 0; j < K::NCH / 4; ++j)
+        raw[gi][j] = tok[gi] >= 0 ? __ldg(reinterpret_cast<const uint4*>(X + tok[gi] * ldx) + (lane >> 3) + 4 * j)
+                                  : make_uint4(0, 0, 0, 0);
     }
-    RDST_TSTAMP();   // P1b: LN + STS done (this warp)
-    fence_proxy_async();
+  };
+  prefetch(blockIdx.x);
+
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+    // ---------------- P1a: (prefetched) rows of two windows -> raw tile in smem + LayerNorm statistics ----------------
+    RDST_TSTAMP();   // tile start
+    int64_t tok_cur[2] = {tok[0], tok[1]};
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+      const int r = (warp + 8 * gi) * 8 + (lane & 7);
+      const int sw = K::SWZ ? (r & 7) : 0;
+      if ((lane >> 3) == 0) sReg[r] = regv[gi];
+      float s = 0.f;
+#pragma unroll
+      for (int j = 0; j < K::NCH / 4; ++j) {
+        const float2 f0 = up2(raw[gi][j].x), f1 = up2(raw[gi][j].y), f2 = up2(raw[gi][j].z), f3 = up2(raw[gi][j].w);
+        s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
+        *reinterpret_cast<uint4*>(sXT + r * K::PITCH + ((((lane >> 3) + 4 * j) ^ sw) * 16)) = raw[gi][j];
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      const float mean = s * inv_c;
+      float ss = 0.f;
+#pragma unroll
+      for (int j = 0; j < K::NCH / 4; ++j) {
+        const uint32_t w4[4] = {raw[gi][j].x, raw[gi][j].y, raw[gi][j].z, raw[gi][j].w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = up2(w4[q]);
+          ss += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+        }
+      }
+      ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+      ss -= (float)(CP - C_) * mean * mean;
+      if ((lane >> 3) == 0) sStat[r] = make_float2(mean, rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f));
+    }
+    __syncthreads();
+    RDST_TSTAMP();   // P1a done
+    // ---------------- P1b: thread = token row: normalise half a row -> packed bf16 A operand in TMEM ----------------
+    {
+      const float2 st = sStat[row];
+      constexpr int NC = K::NCH / 2;
+      uint32_t o[NC * 4];
+#pragma unroll
+      for (int cc = 0; cc < NC; ++cc) {
+        const uint4 v = *reinterpret_cast<const uint4*>(sXT + row * K::PITCH + (((wg * NC + cc) ^ rsw) * 16));
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = up2(w4[q]);
+          o[cc * 4 + q] = pk2((f.x - st.x) * st.y, (f.y - st.x) * st.y);
+        }
+      }
+#pragma unroll
+      for (int c0 = 0; c0 < NC * 4; c0 += 8) {
+        uint32_t a[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] = o[c0 + e];
+        tmem_st_x8(lane_addr + K::TM_XH + wg * NC * 4 + c0, a);
+      }
+      wait_st();
+    }
     fence_before_sync();
     __syncthreads();
-    RDST_TSTAMP();   // 1: after P1 + sync
+    RDST_TSTAMP();   // P1b done
     if (issuer_warp) {
       fence_after_sync();
       if (elect_one()) issue_qkv(wg_u);
@@ -295,29 +331,43 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int h = wg + 2 * i;
-      RDST_TSTAMP();   // 2+6i: before qkv wait
+      RDST_TSTAMP();   // before qkv wait
       mbar_wait(bar_q, ph_q & 1); ph_q++;
       fence_after_sync();
-      RDST_TSTAMP();   // 3+6i: qkv ready
       {
         constexpr int NC = (3 * HD + 7) / 8 * 8;
         float f[NC];
         tmem_load_cols<NC>(lane_addr + tQ, f);
         const float* bq = sBqkv + h * NH;
+        // Q: packed bf16 pairs back into the (now consumed) accumulator columns -> A operand of S straight from TMEM
+        {
+          uint32_t qp[K::HDP / 2];
 #pragma unroll
-        for (int c8 = 0; c8 < (HD + 7) / 8; ++c8) {
-          *reinterpret_cast<uint4*>(sAq + c8 * 2048 + row * 16) = pack8<0, HD>(f, bq, c8);
-          *reinterpret_cast<uint4*>(sBk + c8 * 2048 + row * 16) = pack8<HD, HD>(f, bq, c8);
+          for (int e = 0; e < K::HDP / 2; ++e) {
+            const int d0 = 2 * e, d1 = d0 + 1;
+            qp[e] = pk2(d0 < HD ? f[d0] + bq[d0] : 0.f, d1 < HD ? f[d1] + bq[d1] : 0.f);
+          }
+#pragma unroll
+          for (int c0 = 0; c0 < K::HDP / 2; c0 += 8) {
+            uint32_t a[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] = qp[c0 + e];
+            tmem_st_x8(lane_addr + tQ + c0, a);
+          }
         }
+#pragma unroll
+        for (int c8 = 0; c8 < (HD + 7) / 8; ++c8)
+          *reinterpret_cast<uint4*>(sBk + c8 * 2048 + row * 16) = pack8<HD, HD, false>(f, bq, c8);
         if (i > 0) mbar_wait(bar_o, (ph_o - 1) & 1);          // PV of the previous head has finished reading V
 #pragma unroll
         for (int c8 = 0; c8 < (HD + 7) / 8; ++c8)
-          *reinterpret_cast<uint4*>(sBv + c8 * 2048 + row * 16) = pack8<2 * HD, HD>(f, bq, c8);   // MN-major V image
+          *reinterpret_cast<uint4*>(sBv + c8 * 2048 + row * 16) = pack8<2 * HD, HD, true>(f, bq, c8);   // MN-major, fp16
+        wait_st();
       }
       fence_proxy_async();
       fence_before_sync();
       wg_barrier(wg);
-      RDST_TSTAMP();   // 4+6i: drained + barrier
+      RDST_TSTAMP();   // drained
       if (issuer_warp) {
         fence_after_sync();
         if (elect_one()) {
@@ -326,9 +376,9 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
           for (int w = 0; w < 2; ++w)
 #pragma unroll
             for (int ks = 0; ks < K::HDP / 16; ++ks)
-              mma_bf16_ss_masked(tmem_u + tS_u, make_smem_desc(aAq_u + ks * 4096, 2048, 128),
-                                 make_smem_desc(aBk_u + w * 1024 + ks * 4096, 2048, 128), ids, ks > 0,
-                                 w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
+              mma_bf16_ts_masked(tmem_u + tS_u, tmem_u + tQ_u + ks * 8, make_smem_desc(aBk_u + w * 1024 + ks * 4096, 2048, 128),
+                                 ids, ks > 0, w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu,
+                                 w ? 0u : 0xFFFFFFFFu);
           commit(bar_s_u);
           if (i < 2) issue_qkv(wg_u + 2 * i + 2);
         }
@@ -337,7 +387,7 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       // ---- softmax over the 64 keys of this row's window ----
       mbar_wait(bar_s, ph_s & 1); ph_s++;
       fence_after_sync();
-      RDST_TSTAMP();   // 5+6i: S ready
+      RDST_TSTAMP();   // S ready
       {
         uint32_t v[64];
         {
@@ -348,7 +398,6 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
 #pragma unroll
           for (int j = 0; j < 32; ++j) { v[j] = a[j]; v[32 + j] = b[j]; }
         }
-        RDST_TSTAMP();   // S loaded into registers
         const float* tb = sTab + h * K::TBL + (iy + 7) * 24 + ix + 7;
 #pragma unroll
         for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + tb[-((j >> 3) * 24 + (j & 7))]);
@@ -361,28 +410,27 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
 #pragma unroll
         for (int j = 4; j < 64; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
         const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
-        RDST_TSTAMP();   // bias + max done
+        RDST_TSTAMP();   // bias + max
+        // exp2 on packed fp16 pairs: one MUFU op per two probabilities; P stays fp16 (V is fp16 as well)
         float s4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t o[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) {
-          const float p0 = ex2(__uint_as_float(v[2 * j]) - mx), p1 = ex2(__uint_as_float(v[2 * j + 1]) - mx);
-          s4[j & 3] += p0 + p1;
-          o[j] = pk2(p0, p1);
+          o[j] = ex2_h2(pk2h(__uint_as_float(v[2 * j]) - mx, __uint_as_float(v[2 * j + 1]) - mx));
+          const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&o[j]));
+          s4[j & 3] += pf.x + pf.y;
         }
         psum[i] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
-        RDST_TSTAMP();   // exp + pack done
-        tmem_st_x32(lane_addr + tS, o);                     // P (bf16 pairs) overwrites the first 32 columns of S
+        tmem_st_x32(lane_addr + tS, o);                     // P overwrites the first 32 columns of S
         wait_st();
       }
-      RDST_TSTAMP();   // 6+6i: softmax done (this thread)
+      RDST_TSTAMP();   // softmax done
       fence_before_sync();
       wg_barrier(wg);
-      RDST_TSTAMP();   // 7+6i: P barrier
       if (issuer_warp) {
         fence_after_sync();
         if (elect_one()) {
-          constexpr uint32_t idv = make_idesc_bf16(128, K::HDV, false, true);
+          constexpr uint32_t idv = make_idesc_f16(128, K::HDV, false, true);
           const uint32_t dO = tmem_u + K::TM_O + (wg_u + 2 * i) * K::HDV;
 #pragma unroll
           for (int w = 0; w < 2; ++w)
@@ -396,12 +444,11 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       }
       ph_o++;
     }
-    // ---------------- O / rowsum -> A image for proj (each warpgroup normalises its own three heads) ----------------
-    RDST_TSTAMP();   // 20: heads issued
+    // ---------------- O / rowsum -> packed bf16 A operand of proj in TMEM (each warpgroup: its own three heads) -------
+    RDST_TSTAMP();   // heads issued
     mbar_wait(bar_o, (ph_o - 1) & 1);
     fence_after_sync();
-    __syncthreads();                    // both warpgroups are past their last qkv MMA: the A image is dead
-    RDST_TSTAMP();   // 21: PV done + CTA sync
+    __syncthreads();                    // both warpgroups are past their last qkv MMA: the normalised input is dead
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int h = wg + 2 * i;
@@ -410,26 +457,28 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       tmem_load_cols<NC>(lane_addr + K::TM_O + h * K::HDV, f);
       const float inv = 1.0f / psum[i];
       if (K::HDO == 16) {
+        uint32_t a[8];
 #pragma unroll
-        for (int c8 = 0; c8 < 2; ++c8) {
-          uint32_t o[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const int d0 = c8 * 8 + 2 * q, d1 = d0 + 1;
-            o[q] = pk2(d0 < HD ? f[d0] * inv : 0.f, d1 < HD ? f[d1] * inv : 0.f);
-          }
-          *reinterpret_cast<uint4*>(sA + (2 * h + c8) * 2048 + row * 16) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int e = 0; e < 8; ++e) {
+          const int d0 = 2 * e, d1 = d0 + 1;
+          a[e] = pk2(d0 < HD ? f[d0] * inv : 0.f, d1 < HD ? f[d1] * inv : 0.f);
         }
-      } else {   // HDO == 20: element k = 20h + d, written as 5 groups of 4 bf16 (8 bytes)
+        tmem_st_x8(lane_addr + K::TM_XH + 8 * h, a);
+      } else {   // HDO == 20: 10 columns per head
+        uint32_t a[8], b[2];
 #pragma unroll
-        for (int m = 0; m < 5; ++m) {
-          const int k = 20 * h + 4 * m;
-          const uint2 val = make_uint2(pk2(f[4 * m] * inv, f[4 * m + 1] * inv), pk2(f[4 * m + 2] * inv, f[4 * m + 3] * inv));
-          *reinterpret_cast<uint2*>(sA + (k >> 3) * 2048 + row * 16 + (k & 7) * 2) = val;
-        }
+        for (int e = 0; e < 8; ++e) a[e] = pk2(f[2 * e] * inv, f[2 * e + 1] * inv);
+        b[0] = pk2(f[16] * inv, f[17] * inv);
+        b[1] = pk2(f[18] * inv, f[19] * inv);
+        tmem_st_x8(lane_addr + K::TM_XH + 10 * h, a);
+        tmem_st_x2(lane_addr + K::TM_XH + 10 * h + 8, b);
       }
     }
-    fence_proxy_async();
+    if (K::HDO == 20 && wg == 0) {      // K pad of proj (elements 120..127): must be finite; weights there are zero
+      uint32_t zz[4] = {0, 0, 0, 0};
+      tmem_st_x4(lane_addr + K::TM_XH + 60, zz);
+    }
+    wait_st();
     fence_before_sync();
     __syncthreads();
     if (warp_u == 0) {
@@ -438,68 +487,56 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
         constexpr uint32_t idp = make_idesc_bf16(128, CP, false, false);
 #pragma unroll
         for (int ks = 0; ks < K::KPROJ / 16; ++ks)
-          mma_bf16_ss(tmem_u + K::TM_PROJ, make_smem_desc(aA + ks * 4096, 2048, 128),
-                      make_smem_desc(aWproj + ks * 2 * (CP * 16), CP * 16, 128), idp, ks > 0);
+          mma_bf16_ts_masked(tmem_u + K::TM_PROJ, tmem_u + K::TM_XH + ks * 8,
+                             make_smem_desc(aWproj + ks * 2 * (CP * 16), CP * 16, 128), idp, ks > 0, 0, 0, 0, 0);
         commit(&bars[6]);
       }
       __syncwarp();
     }
-    // residual rows: issue the global loads now so their latency hides under the proj MMA and its epilogue
-    uint4 xres[2][K::NCH / 4];
-#pragma unroll
-    for (int gi = 0; gi < 2; ++gi)
-#pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j)
-        xres[gi][j] = tok[gi] >= 0 ? __ldg(reinterpret_cast<const uint4*>(X + tok[gi] * ldx) + (lane >> 3) + 4 * j)
-                                   : make_uint4(0, 0, 0, 0);
-    RDST_TSTAMP();   // 22: O epilogue + sync + proj issued
+    // prefetch the next tile's rows: the global-load latency hides under proj and the copy-out
+    prefetch(tile + gridDim.x);
+    RDST_TSTAMP();   // O epilogue + proj issued
     mbar_wait(&bars[6], ph_p & 1); ph_p++;
     fence_after_sync();
-    RDST_TSTAMP();   // 23: proj ready
-    // ---------------- proj epilogue -> staging (in the dead A region) -> coalesced residual store ----------------
+    // ---------------- proj epilogue in the row mapping: y = proj + bias + x, in place in the raw tile ----------------
     {
       constexpr int NC = CP / 2;
-      const int cbeg = wg * NC;
+      const int cb = wg * NC;
 #pragma unroll
-      for (int c0 = 0; c0 < NC; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(lane_addr + K::TM_PROJ + cbeg + c0, v);
+      for (int c0 = 0; c0 < NC; c0 += 8) {
+        uint32_t v[8];
+        tmem_ld_x8(lane_addr + K::TM_PROJ + cb + c0, v);
         wait_ld();
-        uint32_t o[8];
+        uint8_t* xp = sXT + row * K::PITCH + ((((cb + c0) >> 3) ^ rsw) * 16);
+        const uint4 xv = *reinterpret_cast<const uint4*>(xp);
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+        uint32_t o[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = pk2(__uint_as_float(v[2 * j]) + sBproj[cbeg + c0 + 2 * j], __uint_as_float(v[2 * j + 1]) + sBproj[cbeg + c0 + 2 * j + 1]);
-        const int ch = (cbeg + c0) >> 3;
-        const int sw = K::SWZ ? (row & 7) : 0;
-        *reinterpret_cast<uint4*>(sA + row * K::PITCH + ((ch ^ sw) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
-        *reinterpret_cast<uint4*>(sA + row * K::PITCH + (((ch + 1) ^ sw) * 16)) = make_uint4(o[4], o[5], o[6], o[7]);
+        for (int e = 0; e < 4; ++e) {
+          const float2 xf = up2(xw[e]);
+          o[e] = pk2(__uint_as_float(v[2 * e]) + sBproj[cb + c0 + 2 * e] + xf.x,
+                     __uint_as_float(v[2 * e + 1]) + sBproj[cb + c0 + 2 * e + 1] + xf.y);
+        }
+        *reinterpret_cast<uint4*>(xp) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
     fence_before_sync();
     __syncthreads();
-    RDST_TSTAMP();   // 24: staging written
+    RDST_TSTAMP();   // y staged
 #pragma unroll
     for (int gi = 0; gi < 2; ++gi) {
       const int r = (warp + 8 * gi) * 8 + (lane & 7);
-      if (tok[gi] >= 0) {
+      const int sw = K::SWZ ? (r & 7) : 0;
+      if (tok_cur[gi] >= 0) {
 #pragma unroll
         for (int j = 0; j < K::NCH / 4; ++j) {
           const int c = (lane >> 3) + 4 * j;
-          const uint4 m = *reinterpret_cast<const uint4*>(sA + r * K::PITCH + ((c ^ (K::SWZ ? (r & 7) : 0)) * 16));
-          const uint4 x = xres[gi][j];
-          const uint32_t mw[4] = {m.x, m.y, m.z, m.w}, xw[4] = {x.x, x.y, x.z, x.w};
-          uint32_t o[4];
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 a = up2(mw[q]), b = up2(xw[q]);
-            o[q] = pk2(a.x + b.x, a.y + b.y);
-          }
-          *(reinterpret_cast<uint4*>(Y + tok[gi] * ldy) + c) = make_uint4(o[0], o[1], o[2], o[3]);
+          *(reinterpret_cast<uint4*>(Y + tok_cur[gi] * ldy) + c) = *reinterpret_cast<const uint4*>(sXT + r * K::PITCH + ((c ^ sw) * 16));
         }
       }
     }
     __syncthreads();
-    RDST_TSTAMP();   // 25: tile done
+    RDST_TSTAMP();   // tile done
   }
 #undef RDST_TSTAMP
   fence_before_sync();

@@ -28,16 +28,15 @@ _lib.call("rdst_debug_attn_timing", _lib.ptr(dbg))
 run(); torch.cuda.synchronize()
 _lib.call("rdst_debug_attn_timing", None)
 d = dbg.cpu().tolist()
-names = ["tile start", "P1 loads issued", "P1 LN+STS done", "P1 sync done"]
+names = ["tile start", "P1a done", "P1b done"]
 for i in range(3):
-    names += [f"h{i} wait qkv", f"h{i} qkv ready", f"h{i} drained", f"h{i} S ready", f"h{i} S in regs", f"h{i} bias+max", f"h{i} exp+pack",
-              f"h{i} softmax done", f"h{i} P barrier"]
-names += ["heads issued", "PV done+sync", "O epi+proj issued", "proj ready", "staging written", "tile done"]
+    names += [f"h{i} before qkv wait", f"h{i} drained", f"h{i} S ready", f"h{i} bias+max", f"h{i} softmax done"]
+names += ["heads issued", "O epi+proj issued", "y staged", "tile done"]
 for wg in range(2):
     t = d[wg * 64: wg * 64 + 64]
     print(f"--- warpgroup {wg} (C={c}, shift={shift}); first two tiles")
     n = len(names)
-    for tile in range(1):
+    for tile in range(2):
         base = t[tile * n]
         prev = base
         for k, nm in enumerate(names):
