@@ -220,8 +220,8 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     const uint32_t wb = aWqkv + h * (NH * CP * 2);
 #pragma unroll
     for (int ks = 0; ks < CP / 16; ++ks)
-      mma_bf16_ts_masked(tmem_u + tQ_u, tmem_u + K::TM_XH + ks * 8, make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128),
-                         idq, ks > 0, 0, 0, 0, 0);
+      mma_ts(tmem_u + tQ_u, tmem_u + K::TM_XH + ks * 8, make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128),
+                         idq, ks > 0);
     commit(bar_q_u);
   };
 
@@ -449,12 +449,22 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     mbar_wait(bar_o, (ph_o - 1) & 1);
     fence_after_sync();
     __syncthreads();                    // both warpgroups are past their last qkv MMA: the normalised input is dead
+    constexpr int NCO = (HD + 7) / 8 * 8;
+    float fo[3][NCO];
+#pragma unroll
+    for (int i = 0; i < 3; ++i)
+#pragma unroll
+      for (int c = 0; c < NCO; c += 8) {
+        uint32_t t8[8];
+        tmem_ld_x8(lane_addr + K::TM_O + (wg + 2 * i) * K::HDV + c, t8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) fo[i][c + e] = __uint_as_float(t8[e]);
+      }
+    wait_ld();
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
       const int h = wg + 2 * i;
-      constexpr int NC = (HD + 7) / 8 * 8;
-      float f[NC];
-      tmem_load_cols<NC>(lane_addr + K::TM_O + h * K::HDV, f);
+      const float* f = fo[i];
       const float inv = 1.0f / psum[i];
       if (K::HDO == 16) {
         uint32_t a[8];
@@ -487,8 +497,8 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
         constexpr uint32_t idp = make_idesc_bf16(128, CP, false, false);
 #pragma unroll
         for (int ks = 0; ks < K::KPROJ / 16; ++ks)
-          mma_bf16_ts_masked(tmem_u + K::TM_PROJ, tmem_u + K::TM_XH + ks * 8,
-                             make_smem_desc(aWproj + ks * 2 * (CP * 16), CP * 16, 128), idp, ks > 0, 0, 0, 0, 0);
+          mma_ts(tmem_u + K::TM_PROJ, tmem_u + K::TM_XH + ks * 8,
+                             make_smem_desc(aWproj + ks * 2 * (CP * 16), CP * 16, 128), idp, ks > 0);
         commit(&bars[6]);
       }
       __syncwarp();
@@ -502,11 +512,18 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     {
       constexpr int NC = CP / 2;
       const int cb = wg * NC;
+      uint32_t acc[NC];
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 8) {
-        uint32_t v[8];
-        tmem_ld_x8(lane_addr + K::TM_PROJ + cb + c0, v);
-        wait_ld();
+        uint32_t t8[8];
+        tmem_ld_x8(lane_addr + K::TM_PROJ + cb + c0, t8);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) acc[c0 + e] = t8[e];
+      }
+      wait_ld();
+#pragma unroll
+      for (int c0 = 0; c0 < NC; c0 += 8) {
+        const uint32_t* v = acc + c0;
         uint8_t* xp = sXT + row * K::PITCH + ((((cb + c0) >> 3) ^ rsw) * 16);
         const uint4 xv = *reinterpret_cast<const uint4*>(xp);
         const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};

@@ -41,7 +41,8 @@ struct ConvCfg {
   static constexpr int OFF_A = W_BYTES;
   static constexpr int OFF_BIAS = OFF_A + A_BYTES;
   static constexpr int SMEM = OFF_BIAS + NT * 4;
-  static_assert(NCH % 4 == 0 && (NT == 16 || NT == 32 || NT == 64), "shape");
+  static constexpr int TMEM_COLS = NT <= 64 ? 64 : 128;
+  static_assert(NCH % 4 == 0 && (NT == 16 || NT == 32 || NT == 64 || NT == 128), "shape");
 };
 
 template <int CIN, int NT>
@@ -59,7 +60,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
   uint8_t* sA = smem + K::OFF_A;
   float* sBias = reinterpret_cast<float*>(smem + K::OFF_BIAS);
 
-  if (warp == 0) tmem_alloc<64>(&tmem_base_s);
+  if (warp == 0) tmem_alloc<K::TMEM_COLS>(&tmem_base_s);
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   {
     const uint8_t* src = wimg + (size_t)slice * K::W_BYTES;
@@ -80,6 +81,8 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int64_t ntiles = (int64_t)g.B * g.nty * g.ntx;
   uint32_t parity = 0;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
     const int b = (int)(tile / (g.nty * g.ntx));
@@ -103,19 +106,22 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (tid == 0) {
+    if (warp_u == 0) {
       fence_after_sync();
-      constexpr uint32_t idesc = make_idesc_bf16(128, NT, false, false);
+      if (elect_one()) {
+        constexpr uint32_t idesc = make_idesc_bf16(128, NT, false, false);
 #pragma unroll 1
-      for (int tap = 0; tap < 9; ++tap) {
-        const uint32_t a0 = aA + (uint32_t)((tap / 3) * g.LW + (tap % 3)) * 16;
-        const uint32_t w0 = aW + tap * (CIN * NT * 2);
+        for (int tap = 0; tap < 9; ++tap) {
+          const uint32_t a0 = aA + (uint32_t)((tap / 3) * g.LW + (tap % 3)) * 16;
+          const uint32_t w0 = aW + tap * (CIN * NT * 2);
 #pragma unroll
-        for (int ks = 0; ks < CIN / 16; ++ks)
-          mma_bf16_ss(tmem, make_smem_desc(a0 + ks * 2 * lboA, lboA, 128), make_smem_desc(w0 + ks * 2 * (NT * 16), NT * 16, 128),
-                      idesc, (tap | ks) > 0);
+          for (int ks = 0; ks < CIN / 16; ++ks)
+            mma_bf16_ss(tmem_u, make_smem_desc(a0 + ks * 2 * lboA, lboA, 128),
+                        make_smem_desc(w0 + ks * 2 * (NT * 16), NT * 16, 128), idesc, (tap | ks) > 0);
+        }
+        commit(&bar);
       }
-      commit(&bar);
+      __syncwarp();
     }
     mbar_wait(&bar, parity);
     fence_after_sync();
@@ -136,10 +142,12 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
       const bool ok = ox < g.TW && oy < g.TH && y < g.H && x < g.W;
       constexpr int NC = NT / 2;                            // columns per thread
       const int cb = part * NC;
+      // shuffle: accumulator columns are (sub-pixel s, channel) with 64 channels per s
+      const int sp = (slice * NT + cb) >> 6;                // sub-pixel index 2*dy+dx of this thread's columns
       int64_t tout;
-      if (g.shuffle) tout = ((int64_t)(b * 2 * g.H + 2 * y + (slice >> 1))) * (2 * g.W) + 2 * x + (slice & 1);
+      if (g.shuffle) tout = ((int64_t)(b * 2 * g.H + 2 * y + (sp >> 1))) * (2 * g.W) + 2 * x + (sp & 1);
       else tout = ((int64_t)b * g.H + y) * g.W + x;
-      const int ncol0 = (g.shuffle ? 0 : slice * NT) + cb;  // first output channel written by this thread
+      const int ncol0 = g.shuffle ? ((slice * NT + cb) & 63) : slice * NT + cb;   // first output channel of this thread
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 16) {
         uint32_t v[16];
@@ -167,7 +175,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<64>(tmem);
+  if (warp == 0) tmem_dealloc<K::TMEM_COLS>(tmem);
 }
 
 template <int CIN, int NT>
@@ -257,7 +265,8 @@ extern "C" int rdst_conv3x3_fwd_bf16_tc(const void* x, int64_t ldx, const void* 
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   if (Cin == 160) rc = launch_conv<160, 32>(x, ldx, wimg, bias, resid, ldr, y, ldy, g, 2, sms, st);
-  else rc = launch_conv<64, 64>(x, ldx, wimg, bias, resid, ldr, y, ldy, g, N / 64, sms, st);
+  else if (N == 256) rc = launch_conv<64, 128>(x, ldx, wimg, bias, resid, ldr, y, ldy, g, 2, sms, st);
+  else rc = launch_conv<64, 64>(x, ldx, wimg, bias, resid, ldr, y, ldy, g, 1, sms, st);
   if (rc) return rc;
   RDST_CHECK_LAUNCH("rdst_conv3x3_fwd_bf16_tc");
   return RDST_OK;

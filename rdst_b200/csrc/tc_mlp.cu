@@ -215,13 +215,13 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
         constexpr uint32_t id1 = make_idesc_bf16(128, C::H1, false, false);
 #pragma unroll
         for (int ks = 0; ks < CP / 16; ++ks)
-          mma_bf16_ts_masked(tmem_u + C::TM_FC1, tmem_u + C::TM_XH + ks * 8,
-                             make_smem_desc(aW1 + ks * 2 * (HP * 16), HP * 16, 128), id0, ks > 0, 0, 0, 0, 0);
+          mma_ts(tmem_u + C::TM_FC1, tmem_u + C::TM_XH + ks * 8,
+                             make_smem_desc(aW1 + ks * 2 * (HP * 16), HP * 16, 128), id0, ks > 0);
         commit(&bars[0]);
 #pragma unroll
         for (int ks = 0; ks < CP / 16; ++ks)
-          mma_bf16_ts_masked(tmem_u + C::TM_FC1 + C::H0, tmem_u + C::TM_XH + ks * 8,
-                             make_smem_desc(aW1 + C::H0 * 16 + ks * 2 * (HP * 16), HP * 16, 128), id1, ks > 0, 0, 0, 0, 0);
+          mma_ts(tmem_u + C::TM_FC1 + C::H0, tmem_u + C::TM_XH + ks * 8,
+                             make_smem_desc(aW1 + C::H0 * 16 + ks * 2 * (HP * 16), HP * 16, 128), id1, ks > 0);
         commit(&bars[1]);
       }
       __syncwarp();
@@ -236,16 +236,30 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
       const int cend = hbase + (half == 0 ? w0 : hw);
       mbar_wait(&bars[h], parity);
       fence_after_sync();
-      for (int c0 = cbeg; c0 < cend; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(lane_addr + C::TM_FC1 + c0, v);
-        wait_ld();
-        uint32_t o[8];
+      {
+        // all accumulator columns of this thread are requested up front (one wait), then GELU -> packed hidden
+        constexpr int MAXC = 64;
+        uint32_t v[MAXC];
 #pragma unroll
-        for (int j = 0; j < 8; ++j)
-          o[j] = pack_bf16x2(gelu_fn<EXACT>(__uint_as_float(v[2 * j]) + sB1[c0 + 2 * j]),
-                             gelu_fn<EXACT>(__uint_as_float(v[2 * j + 1]) + sB1[c0 + 2 * j + 1]));
-        tmem_st_x8(lane_addr + C::TM_HID + c0 / 2, o);
+        for (int q = 0; q < MAXC / 16; ++q)
+          if (cbeg + q * 16 < cend) {
+            uint32_t t16[16];
+            tmem_ld_x16(lane_addr + C::TM_FC1 + cbeg + q * 16, t16);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[q * 16 + e] = t16[e];
+          }
+        wait_ld();
+#pragma unroll
+        for (int q = 0; q < MAXC / 16; ++q)
+          if (cbeg + q * 16 < cend) {
+            const int c0 = cbeg + q * 16;
+            uint32_t o[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o[j] = pack_bf16x2(gelu_fn<EXACT>(__uint_as_float(v[q * 16 + 2 * j]) + sB1[c0 + 2 * j]),
+                                 gelu_fn<EXACT>(__uint_as_float(v[q * 16 + 2 * j + 1]) + sB1[c0 + 2 * j + 1]));
+            tmem_st_x8(lane_addr + C::TM_HID + c0 / 2, o);
+          }
       }
       wait_st();
       fence_before_sync();
@@ -256,8 +270,8 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
           constexpr uint32_t id2 = make_idesc_bf16(128, CP, false, false);
           const int ks0 = hbase / 16, ks1 = (hbase + hw) / 16;
           for (int ks = ks0; ks < ks1; ++ks)
-            mma_bf16_ts_masked(tmem_u + C::TM_FC2, tmem_u + C::TM_HID + ks * 8,
-                               make_smem_desc(aW2 + ks * 2 * (CP * 16), CP * 16, 128), id2, ks > 0, 0, 0, 0, 0);
+            mma_ts(tmem_u + C::TM_FC2, tmem_u + C::TM_HID + ks * 8,
+                               make_smem_desc(aW2 + ks * 2 * (CP * 16), CP * 16, 128), id2, ks > 0);
           commit(&bars[2 + h]);
         }
         __syncwarp();
@@ -272,11 +286,18 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
       const int cb = half * NC;
       float y[NC];
       float s1 = 0.f, s2 = 0.f;
+      uint32_t acc[NC];
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 16) {
-        uint32_t v[16];
-        tmem_ld_x16(lane_addr + C::TM_FC2 + cb + c0, v);
-        wait_ld();
+        uint32_t t16[16];
+        tmem_ld_x16(lane_addr + C::TM_FC2 + cb + c0, t16);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[c0 + e] = t16[e];
+      }
+      wait_ld();
+#pragma unroll
+      for (int c0 = 0; c0 < NC; c0 += 16) {
+        const uint32_t* v = acc + c0;
 #pragma unroll
         for (int q = 0; q < 2; ++q) {
           const int ch = (cb + c0) / 8 + q;
@@ -321,8 +342,8 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
           constexpr uint32_t idt = make_idesc_bf16(128, 32, false, false);
 #pragma unroll
           for (int ks = 0; ks < CP / 16; ++ks)
-            mma_bf16_ts_masked(tmem_u + C::TM_FC1, tmem_u + C::TM_XH + ks * 8,
-                               make_smem_desc(aWT + ks * 2 * (32 * 16), 32 * 16, 128), idt, ks > 0, 0, 0, 0, 0);
+            mma_ts(tmem_u + C::TM_FC1, tmem_u + C::TM_XH + ks * 8,
+                               make_smem_desc(aWT + ks * 2 * (32 * 16), 32 * 16, 128), idt, ks > 0);
           commit(&bars[4]);
         }
         __syncwarp();

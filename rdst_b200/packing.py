@@ -199,7 +199,7 @@ def pack_stl_tc(p):
 def conv_tc_image(w):
     """[N][9][Cin] fp32 conv weight -> operand images of rdst_conv3x3_fwd_bf16_tc: N/NT slices x 9 taps x [Cin/8][NT][8]."""
     n, _, cin = w.shape
-    nt = 32 if cin == 160 else 64
+    nt = 32 if cin == 160 else (128 if n == 256 else 64)
     parts = [kmajor_image(w[s * nt:(s + 1) * nt, tap, :]) for s in range(n // nt) for tap in range(9)]
     return torch.cat(parts).contiguous()
 
