@@ -38,8 +38,8 @@ struct ConvCfg {
   static constexpr int W_BYTES = 9 * CIN * NT * 2;
   static constexpr int A_BYTES = NCH * CONV_NP_MAX * 16;
   static constexpr int OFF_W = 0;
-  static constexpr int OFF_A = W_BYTES;
-  static constexpr int OFF_BIAS = OFF_A + A_BYTES;
+  static constexpr int OFF_A = W_BYTES;                  // two staging buffers: tile n+1 is staged while tile n's MMAs run
+  static constexpr int OFF_BIAS = OFF_A + 2 * A_BYTES;
   static constexpr int SMEM = OFF_BIAS + NT * 4;
   static constexpr int TMEM_COLS = NT <= 64 ? 64 : 128;
   static_assert(NCH % 4 == 0 && (NT == 16 || NT == 32 || NT == 64 || NT == 128), "shape");
@@ -66,7 +66,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
     const uint8_t* src = wimg + (size_t)slice * K::W_BYTES;
     for (int i = tid; i < K::W_BYTES / 16; i += 256)
       *reinterpret_cast<uint4*>(sW + (size_t)i * 16) = __ldg(reinterpret_cast<const uint4*>(src) + i);
-    for (int i = tid; i < K::A_BYTES / 16; i += 256) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < 2 * K::A_BYTES / 16; i += 256) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < NT; i += 256) sBias[i] = (NT == 16) ? 0.f : bias[slice * NT + i];
   }
   fence_proxy_async();
@@ -84,11 +84,12 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
+  // stage the halo tile of `tile` into staging buffer `buf` as a K-major image
+  auto stage = [&](int64_t tile, int buf) {
     const int b = (int)(tile / (g.nty * g.ntx));
     const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
     const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
-    // ---------------- stage halo tile as K-major image ----------------
+    uint8_t* dst = sA + (size_t)buf * K::A_BYTES;
 #pragma unroll 1
     for (int pg = warp; pg * 8 < nps; pg += 8) {
       const int pos = pg * 8 + (lane & 7);
@@ -96,32 +97,50 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
       const int y = y0 - 1 + hy, x = x0 - 1 + hx;
       const bool ok = pos < nps && y >= 0 && y < g.H && x >= 0 && x < g.W;
       const __nv_bfloat16* src = X + (((int64_t)b * g.H + y) * g.W + x) * ldx;
+      uint4 v[K::NCH / 4];
 #pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j) {
-        const int c = (lane >> 3) + 4 * j;
-        const uint4 v = ok ? __ldg(reinterpret_cast<const uint4*>(src) + c) : make_uint4(0, 0, 0, 0);
-        *reinterpret_cast<uint4*>(sA + (size_t)c * lboA + pos * 16) = v;
-      }
+      for (int j = 0; j < K::NCH / 4; ++j)
+        v[j] = ok ? __ldg(reinterpret_cast<const uint4*>(src) + (lane >> 3) + 4 * j) : make_uint4(0, 0, 0, 0);
+#pragma unroll
+      for (int j = 0; j < K::NCH / 4; ++j)
+        *reinterpret_cast<uint4*>(dst + (size_t)((lane >> 3) + 4 * j) * lboA + pos * 16) = v[j];
     }
+  };
+  auto issue = [&](int buf) {        // warp 0, one elected lane
+    constexpr uint32_t idesc = make_idesc_bf16(128, NT, false, false);
+    const uint32_t ab = aA + buf * K::A_BYTES;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const uint32_t a0 = ab + (uint32_t)((tap / 3) * g.LW + (tap % 3)) * 16;
+      const uint32_t w0 = aW + tap * (CIN * NT * 2);
+#pragma unroll
+      for (int ks = 0; ks < CIN / 16; ++ks)
+        mma_bf16_ss(tmem_u, make_smem_desc(a0 + ks * 2 * lboA, lboA, 128),
+                    make_smem_desc(w0 + ks * 2 * (NT * 16), NT * 16, 128), idesc, (tap | ks) > 0);
+    }
+    commit(&bar);
+  };
+
+  int buf = 0;
+  if ((int64_t)blockIdx.x < ntiles) {
+    stage(blockIdx.x, 0);
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
     if (warp_u == 0) {
       fence_after_sync();
-      if (elect_one()) {
-        constexpr uint32_t idesc = make_idesc_bf16(128, NT, false, false);
-#pragma unroll 1
-        for (int tap = 0; tap < 9; ++tap) {
-          const uint32_t a0 = aA + (uint32_t)((tap / 3) * g.LW + (tap % 3)) * 16;
-          const uint32_t w0 = aW + tap * (CIN * NT * 2);
-#pragma unroll
-          for (int ks = 0; ks < CIN / 16; ++ks)
-            mma_bf16_ss(tmem_u, make_smem_desc(a0 + ks * 2 * lboA, lboA, 128),
-                        make_smem_desc(w0 + ks * 2 * (NT * 16), NT * 16, 128), idesc, (tap | ks) > 0);
-        }
-        commit(&bar);
-      }
+      if (elect_one()) issue(0);
       __syncwarp();
+    }
+  }
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1, buf ^= 1) {
+    const int b = (int)(tile / (g.nty * g.ntx));
+    const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
+    const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
+    const int64_t next = tile + gridDim.x;
+    if (next < ntiles) {               // overlaps with the MMAs of the current tile
+      stage(next, buf ^ 1);
+      fence_proxy_async();
     }
     mbar_wait(&bar, parity);
     fence_after_sync();
@@ -171,7 +190,12 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
       }
     }
     fence_before_sync();
-    __syncthreads();          // TMEM tile and the staged image are reused by the next tile
+    __syncthreads();          // accumulator drained, next halo tile staged
+    if (next < ntiles && warp_u == 0) {
+      fence_after_sync();
+      if (elect_one()) issue(buf ^ 1);
+      __syncwarp();
+    }
   }
   fence_before_sync();
   __syncthreads();
@@ -185,8 +209,8 @@ static int launch_conv(const void* x, int64_t ldx, const void* wimg, const float
   auto k = conv3x3_tc_kernel<CIN, NT>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) { set_error("rdst_conv3x3_fwd_bf16_tc: smem attr (%d B): %s", K::SMEM, cudaGetErrorString(e)); return RDST_E_CUDA; }
-  int occ = 1;
-  cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, 256, K::SMEM);
+  int occ = (int)(232448 / (K::SMEM + 2048));          // shared memory, TMEM columns and a cap of 4 CTAs per SM
+  if (occ > 512 / K::TMEM_COLS) occ = 512 / K::TMEM_COLS;
   if (occ < 1) occ = 1;
   if (occ > 4) occ = 4;
   const int64_t ntiles = (int64_t)g.B * g.nty * g.ntx;

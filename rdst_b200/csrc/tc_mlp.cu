@@ -140,18 +140,24 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
   const int64_t ntiles = (T + 127) / 128;
   uint32_t parity = 0;
 
+  // rows of the next tile are requested one tile ahead (registers), so their latency hides under the GEMM pair
+  uint4 raw[2][C::NCH / 4];
+  auto prefetch = [&](int64_t tile) {
+#pragma unroll
+    for (int gi = 0; gi < 2; ++gi) {
+      const int64_t t = tile * 128 + (warp + 8 * gi) * 8 + (lane & 7);
+#pragma unroll
+      for (int j = 0; j < C::NCH / 4; ++j)
+        raw[gi][j] = (tile < ntiles && t < T) ? __ldg(reinterpret_cast<const uint4*>(X + t * ldx) + (lane >> 3) + 4 * j)
+                                              : make_uint4(0, 0, 0, 0);
+    }
+  };
+  prefetch(blockIdx.x);
+
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
     const int64_t t0 = tile * 128;
-    // ---------------- P1a: coalesced load -> raw tile in smem, LayerNorm statistics ----------------
+    // ---------------- P1a: (prefetched) rows -> raw tile in smem, LayerNorm statistics ----------------
     {
-      uint4 raw[2][C::NCH / 4];
-#pragma unroll
-      for (int gi = 0; gi < 2; ++gi) {
-        const int64_t t = t0 + (warp + 8 * gi) * 8 + (lane & 7);
-#pragma unroll
-        for (int j = 0; j < C::NCH / 4; ++j)
-          raw[gi][j] = t < T ? __ldg(reinterpret_cast<const uint4*>(X + t * ldx) + (lane >> 3) + 4 * j) : make_uint4(0, 0, 0, 0);
-      }
 #pragma unroll
       for (int gi = 0; gi < 2; ++gi) {
         const int r = (warp + 8 * gi) * 8 + (lane & 7);
@@ -276,6 +282,7 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
         }
         __syncwarp();
       }
+      if (h == 1) prefetch(tile + gridDim.x);
     }
     // ---------------- P5: fc2 epilogue in the row mapping: y = acc + b2 + x (raw tile) ----------------
     mbar_wait(&bars[2], parity);
