@@ -59,3 +59,39 @@ def test_batch_independence_full_volume():
         parts = torch.cat([m(x[i:i + 44]).clone() for i in range(0, 176, 44)])
     assert torch.equal(y, parts)
     assert torch.isfinite(y).all()
+
+
+def test_large_input_matches_oracle_128():
+    """cfg5 shape (LR 128x128) in fp32 against the oracle; bf16 against the same output within the bf16 bar."""
+    c = helpers.load_case("e2blk_x4_8x8")
+    x = torch.rand(1, 1, 128, 128, generator=torch.Generator().manual_seed(21))
+    ref = O.forward(c["sd"], x, 4)
+    for prec, tol in (("fp32", 1e-4), ("bf16", 1e-2)):
+        m = helpers.make_module(c["blocks"], 4, prec).cuda().eval()
+        m.load_state_dict(c["sd"])
+        with torch.no_grad():
+            y = m(x.cuda()).cpu()
+        assert (y - ref).abs().max().item() < tol, prec
+
+
+def test_forward_is_cuda_graph_capturable():
+    """The C ABI promises stream-ordered, allocation-free kernels: a captured graph must replay to the same result."""
+    c = helpers.load_case("e2blk_x4_8x8")
+    m = helpers.make_module(c["blocks"], 4, "bf16").cuda().eval()
+    m.load_state_dict(c["sd"])
+    x = torch.rand(4, 1, 16, 16, device="cuda")
+    with torch.no_grad():
+        eager = m(x).clone()          # also builds the packed-weight cache and the workspace outside the capture
+        s = torch.cuda.Stream()
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            m(x)
+        torch.cuda.current_stream().wait_stream(s)
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            out = m(x)
+        x.copy_(torch.rand(4, 1, 16, 16, device="cuda"))
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out, m(x))
+    assert torch.isfinite(eager).all()
