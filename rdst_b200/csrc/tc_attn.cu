@@ -149,7 +149,7 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   using K = AttnCfg<C_>;
   constexpr int CP = K::CP, HD = K::HD, NH = K::NH;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[7];          // [0,1] qkv per warpgroup, [2,3] S, [4,5] PV, [6] proj
+  __shared__ uint64_t bars[8];          // [0,1] qkv per warpgroup, [2,3] S, [4,5] PV, [6] proj, [7] weights landed
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = tid >> 7;              // warpgroup: owns heads wg, wg+2, wg+4
@@ -165,13 +165,15 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) {
-    for (int i = 0; i < 7; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
-  }
-  for (int i = tid; i < (K::WQKV_BYTES + K::WPROJ_BYTES) / 16; i += 256) {
-    const uint8_t* src = i < K::WQKV_BYTES / 16 ? wqkv_img + (size_t)i * 16
-                                                : wproj_img + (size_t)(i - K::WQKV_BYTES / 16) * 16;
-    *reinterpret_cast<uint4*>(smem + (size_t)i * 16) = __ldg(reinterpret_cast<const uint4*>(src));
+    // resident weights arrive by bulk async copies (UBLKCP) that overlap the rest of the prologue and the first
+    // tile's load + LayerNorm; the MMA issuers wait on bars[7] once, right before their first tcgen05.mma
+    mbar_arrive_expect_tx(&bars[7], K::WQKV_BYTES + K::WPROJ_BYTES);
+    for (int off = 0; off < K::WQKV_BYTES; off += 32768)
+      bulk_g2s(smem + K::OFF_WQKV + off, wqkv_img + off, min(32768, K::WQKV_BYTES - off), &bars[7]);
+    for (int off = 0; off < K::WPROJ_BYTES; off += 32768)
+      bulk_g2s(smem + K::OFF_WPROJ + off, wproj_img + off, min(32768, K::WPROJ_BYTES - off), &bars[7]);
   }
   // K / V images: K-dim / N-dim pads must be (and stay) zero
   for (int i = tid; i < 2 * K::KV_BYTES / 16; i += 256)
@@ -310,6 +312,7 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     __syncthreads();
     RDST_TSTAMP();   // P1b done
     if (issuer_warp) {
+      if (tile == (int)blockIdx.x) mbar_wait(&bars[7], 0);     // weights have landed (first tile only)
       fence_after_sync();
       if (elect_one()) issue_qkv(wg_u);
       __syncwarp();

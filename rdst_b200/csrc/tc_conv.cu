@@ -53,6 +53,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
   using K = ConvCfg<CIN, NT>;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
+  __shared__ uint64_t wbar;             // weights landed (bulk async copies)
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int slice = blockIdx.y;
@@ -61,11 +62,16 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
   float* sBias = reinterpret_cast<float*>(smem + K::OFF_BIAS);
 
   if (warp == 0) tmem_alloc<K::TMEM_COLS>(&tmem_base_s);
-  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-  {
+  if (tid == 0) {
+    mbar_init(&bar, 1);
+    mbar_init(&wbar, 1);
+    fence_mbar_init();
+    // the filter slice arrives by bulk async copies that overlap the staging of the first halo tile
     const uint8_t* src = wimg + (size_t)slice * K::W_BYTES;
-    for (int i = tid; i < K::W_BYTES / 16; i += 256)
-      *reinterpret_cast<uint4*>(sW + (size_t)i * 16) = __ldg(reinterpret_cast<const uint4*>(src) + i);
+    mbar_arrive_expect_tx(&wbar, K::W_BYTES);
+    for (int off = 0; off < K::W_BYTES; off += 32768) bulk_g2s(sW + off, src + off, min(32768, K::W_BYTES - off), &wbar);
+  }
+  {
     for (int i = tid; i < 2 * K::A_BYTES / 16; i += 256) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < NT; i += 256) sBias[i] = (NT == 16) ? 0.f : bias[slice * NT + i];
   }
@@ -128,6 +134,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
     fence_before_sync();
     __syncthreads();
     if (warp_u == 0) {
+      mbar_wait(&wbar, 0);             // filter slice has landed
       fence_after_sync();
       if (elect_one()) issue(0);
       __syncwarp();

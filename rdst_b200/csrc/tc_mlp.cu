@@ -94,10 +94,11 @@ template <int CP, int HP, bool EXACT, bool TAIL>
 __global__ void __launch_bounds__(256, 1)
 stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* __restrict__ Y, int64_t ldy,
                const uint8_t* __restrict__ w1img, const uint8_t* __restrict__ w2img,
-               const float* __restrict__ b1, const float* __restrict__ b2, int64_t T, int creal, TailArgs ta) {
+               const float* __restrict__ b1, const float* __restrict__ b2, int64_t T, int creal, TailArgs ta,
+               unsigned long long* __restrict__ dbg) {
   using C = MlpCfg<CP, HP>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[5];
+  __shared__ uint64_t bars[6];          // [0,1] fc1 halves, [2,3] fc2 halves, [4] tail, [5] weights landed
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   uint8_t* sXT = smem + C::OFF_XT;
@@ -108,19 +109,20 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) {
-    for (int i = 0; i < 5; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
     fence_mbar_init();
-  }
-  // resident weights (ready-made operand images) + biases
-  for (int i = tid; i < (C::W1_BYTES + C::W2_BYTES) / 16; i += 256) {
-    const uint8_t* src = i < C::W1_BYTES / 16 ? w1img + (size_t)i * 16 : w2img + (size_t)(i - C::W1_BYTES / 16) * 16;
-    *reinterpret_cast<uint4*>(smem + (size_t)i * 16) = __ldg(reinterpret_cast<const uint4*>(src));
+    // resident weights (ready-made operand images) arrive by bulk async copies that overlap the prologue and the
+    // first tile's load + LayerNorm; the issuer waits on bars[5] once before its first tcgen05.mma
+    mbar_arrive_expect_tx(&bars[5], C::W1_BYTES + C::W2_BYTES + (TAIL ? C::WT_BYTES : 0));
+    for (int off = 0; off < C::W1_BYTES; off += 32768)
+      bulk_g2s(smem + C::OFF_W1 + off, w1img + off, min(32768, C::W1_BYTES - off), &bars[5]);
+    for (int off = 0; off < C::W2_BYTES; off += 32768)
+      bulk_g2s(smem + C::OFF_W2 + off, w2img + off, min(32768, C::W2_BYTES - off), &bars[5]);
+    if (TAIL) bulk_g2s(smem + C::OFF_WT, ta.wtimg, C::WT_BYTES, &bars[5]);
   }
   for (int i = tid; i < HP; i += 256) sB1[i] = b1[i];
   for (int i = tid; i < CP; i += 256) sB2[i] = b2[i];
   if (TAIL) {
-    for (int i = tid; i < C::WT_BYTES / 16; i += 256)
-      *reinterpret_cast<uint4*>(smem + C::OFF_WT + (size_t)i * 16) = __ldg(reinterpret_cast<const uint4*>(ta.wtimg) + i);
     for (int i = tid; i < 32; i += 256) reinterpret_cast<float*>(smem + C::OFF_BT)[i] = ta.bt[i];
   }
   fence_proxy_async();
@@ -141,6 +143,12 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
   uint32_t parity = 0;
 
   // rows of the next tile are requested one tile ahead (registers), so their latency hides under the GEMM pair
+  int dbg_n = 0;
+  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && (tid & 127) == 0;
+#define RDST_TSTAMP()                                                         \
+  do {                                                                        \
+    if (dbg_on && dbg_n < 64) dbg[half * 64 + dbg_n++] = clock64();           \
+  } while (0)
   uint4 raw[2][C::NCH / 4];
   auto prefetch = [&](int64_t tile) {
 #pragma unroll
@@ -156,6 +164,7 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
     const int64_t t0 = tile * 128;
+    RDST_TSTAMP();   // tile start
     // ---------------- P1a: (prefetched) rows -> raw tile in smem, LayerNorm statistics ----------------
     {
 #pragma unroll
@@ -190,6 +199,7 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
       }
     }
     __syncthreads();
+    RDST_TSTAMP();   // P1a done
     // ---------------- P1b: thread = token row: normalise its half row -> packed bf16 A operand in TMEM ----------------
     {
       const float2 st = sStat[row];
@@ -213,8 +223,10 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
     }
     fence_before_sync();
     __syncthreads();
+    RDST_TSTAMP();   // P1b done
     // ---------------- P2: fc1 (two N-halves), A from TMEM ----------------
     if (warp_u == 0) {
+      if (tile == (int64_t)blockIdx.x) mbar_wait(&bars[5], 0);  // weights have landed (first tile only)
       fence_after_sync();
       if (elect_one()) {
         constexpr uint32_t id0 = make_idesc_bf16(128, C::H0, false, false);
@@ -240,8 +252,10 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
       const int w0 = (hw / 2 + 15) / 16 * 16;                  // columns of this half taken by warpgroup 0
       const int cbeg = hbase + (half == 0 ? 0 : w0);
       const int cend = hbase + (half == 0 ? w0 : hw);
+      RDST_TSTAMP();   // before fc1 half wait
       mbar_wait(&bars[h], parity);
       fence_after_sync();
+      RDST_TSTAMP();   // fc1 half ready
       {
         // all accumulator columns of this thread are requested up front (one wait), then GELU -> packed hidden
         constexpr int MAXC = 64;
@@ -268,6 +282,7 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
           }
       }
       wait_st();
+      RDST_TSTAMP();   // GELU half done
       fence_before_sync();
       __syncthreads();
       if (warp_u == 0) {
@@ -285,9 +300,11 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
       if (h == 1) prefetch(tile + gridDim.x);
     }
     // ---------------- P5: fc2 epilogue in the row mapping: y = acc + b2 + x (raw tile) ----------------
+    RDST_TSTAMP();   // before fc2 wait
     mbar_wait(&bars[2], parity);
     mbar_wait(&bars[3], parity);
     fence_after_sync();
+    RDST_TSTAMP();   // fc2 ready
     {
       constexpr int NC = CP / 2;                               // columns per thread
       const int cb = half * NC;
@@ -342,6 +359,7 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
     }
     fence_before_sync();
     __syncthreads();
+    RDST_TSTAMP();   // P5 done
     if (TAIL) {
       if (warp_u == 0) {
         fence_after_sync();
@@ -392,11 +410,15 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
       }
     }
     __syncthreads();        // raw tile / TMEM are reused by the next tile
+    RDST_TSTAMP();   // tile done
   }
+#undef RDST_TSTAMP
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
 }
+
+static unsigned long long* g_mlp_dbg = nullptr;
 
 template <int CP, int HP>
 static int launch_mlp(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w1, const void* w2, const float* b1,
@@ -407,7 +429,7 @@ static int launch_mlp(const void* x, int64_t ldx, void* y, int64_t ldy, const vo
   TailArgs ta{};
   int smem = C::SMEM_PLAIN;
   void (*k)(const __nv_bfloat16*, int64_t, __nv_bfloat16*, int64_t, const uint8_t*, const uint8_t*, const float*,
-            const float*, int64_t, int, TailArgs);
+            const float*, int64_t, int, TailArgs, unsigned long long*);
   if (tail) {
     ta = *tail;
     smem = C::SMEM_TAIL;
@@ -418,7 +440,7 @@ static int launch_mlp(const void* x, int64_t ldx, void* y, int64_t ldy, const vo
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("rdst_stl_mlp_fwd_bf16: smem attr (%d B): %s", smem, cudaGetErrorString(e)); return RDST_E_CUDA; }
   k<<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const uint8_t*)w1,
-                             (const uint8_t*)w2, b1, b2, T, creal, ta);
+                             (const uint8_t*)w2, b1, b2, T, creal, ta, g_mlp_dbg);
   return RDST_OK;
 }
 
@@ -438,6 +460,11 @@ static int mlp_dispatch(const void* x, int64_t ldx, void* y, int64_t ldy, const 
 }
 
 }  // namespace rdst
+
+extern "C" int rdst_debug_mlp_timing(void* device_buffer_128_u64) {
+  rdst::g_mlp_dbg = (unsigned long long*)device_buffer_128_u64;
+  return RDST_OK;
+}
 
 extern "C" int rdst_stl_mlp_fwd_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w1img,
                                      const void* w2img, const float* b1, const float* b2, int64_t T, int C,
