@@ -28,6 +28,24 @@ void set_error(const char* fmt, ...);
     }                                                                             \
   } while (0)
 
+// Launch with programmatic stream serialization: the kernel may begin (prologue: barrier init, TMEM allocation, bulk
+// weight loads) while the previous kernel of the stream drains; it calls griddepcontrol.wait before touching
+// anything the previous kernel produced.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute at[1];
+  at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  at[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = at;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 __device__ __forceinline__ float ld_act(const float* p) { return __ldg(p); }
 __device__ __forceinline__ float ld_act(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ void st_act(float* p, float v) { *p = v; }

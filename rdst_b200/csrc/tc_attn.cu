@@ -246,6 +246,8 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
                                   : make_uint4(0, 0, 0, 0);
     }
   };
+  pdl_launch_dependents();       // the next kernel may start its own prologue as SMs free up
+  pdl_wait();                    // everything above touched only weights; from here on we read the producer's output
   prefetch(blockIdx.x);
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
@@ -579,8 +581,9 @@ static int launch_attn(const void* x, int64_t ldx, void* y, int64_t ldy, const v
   auto k = stl_attn_kernel<C_>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) { set_error("rdst_stl_attn_fwd_bf16: smem attr (%d B): %s", K::SMEM, cudaGetErrorString(e)); return RDST_E_CUDA; }
-  k<<<grid, 256, K::SMEM, st>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const uint8_t*)wqkv,
-                                (const uint8_t*)wproj, bqkv, bproj, table, g, -100.0f * 1.4426950408889634f, g_attn_dbg);
+  e = launch_pdl(k, dim3(grid), dim3(256), (size_t)K::SMEM, st, (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy,
+                 (const uint8_t*)wqkv, (const uint8_t*)wproj, bqkv, bproj, table, g, -100.0f * 1.4426950408889634f, g_attn_dbg);
+  if (e != cudaSuccess) { set_error("rdst_stl_attn_fwd_bf16: launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   return RDST_OK;
 }
 

@@ -127,6 +127,8 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
     commit(&bar);
   };
 
+  pdl_launch_dependents();
+  pdl_wait();                    // only the filter slice was touched so far; activations come from the previous kernel
   int buf = 0;
   if ((int64_t)blockIdx.x < ntiles) {
     stage(blockIdx.x, 0);
@@ -225,8 +227,9 @@ static int launch_conv(const void* x, int64_t ldx, const void* wimg, const float
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
   dim3 grid((unsigned)gx, (unsigned)nslices);
-  k<<<grid, 256, K::SMEM, st>>>((const __nv_bfloat16*)x, ldx, (const uint8_t*)wimg, bias, (const __nv_bfloat16*)r, ldr,
-                                (__nv_bfloat16*)y, ldy, g);
+  e = launch_pdl(k, grid, dim3(256), (size_t)K::SMEM, st, (const __nv_bfloat16*)x, ldx, (const uint8_t*)wimg, bias,
+                 (const __nv_bfloat16*)r, ldr, (__nv_bfloat16*)y, ldy, g);
+  if (e != cudaSuccess) { set_error("rdst_conv3x3_fwd_bf16_tc: launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   return RDST_OK;
 }
 

@@ -160,6 +160,8 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
                                               : make_uint4(0, 0, 0, 0);
     }
   };
+  pdl_launch_dependents();
+  pdl_wait();                    // prologue above touched only weights; the rows below come from the previous kernel
   prefetch(blockIdx.x);
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
@@ -439,8 +441,9 @@ static int launch_mlp(const void* x, int64_t ldx, void* y, int64_t ldy, const vo
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("rdst_stl_mlp_fwd_bf16: smem attr (%d B): %s", smem, cudaGetErrorString(e)); return RDST_E_CUDA; }
-  k<<<grid, 256, smem, st>>>((const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy, (const uint8_t*)w1,
-                             (const uint8_t*)w2, b1, b2, T, creal, ta, g_mlp_dbg);
+  e = launch_pdl(k, dim3(grid), dim3(256), (size_t)smem, st, (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy,
+                 (const uint8_t*)w1, (const uint8_t*)w2, b1, b2, T, creal, ta, g_mlp_dbg);
+  if (e != cudaSuccess) { set_error("rdst_stl_mlp_fwd_bf16: launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   return RDST_OK;
 }
 

@@ -165,6 +165,10 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // all bulk stores of this thread have finished READING shared memory (the buffer may be overwritten)
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// Programmatic dependent launch: let the next kernel of the stream start its prologue early / wait for the producer
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // ---- TMEM <-> registers: 32 lanes x 32 bit, N consecutive columns per thread (thread i <-> lane base+i) -----
 // taddr = (lane << 16) | column; a warp may only touch lanes [32*(warp%4), +32).
 __device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, uint32_t (&v)[4]) {

@@ -95,3 +95,20 @@ def test_forward_is_cuda_graph_capturable():
         torch.cuda.synchronize()
         assert torch.equal(out, m(x))
     assert torch.isfinite(eager).all()
+
+
+def test_graphed_inference_driver_matches_eager():
+    from rdst_b200.infer import GraphedRDST, super_resolve_slices
+    c = helpers.load_case("e2blk_x4_8x8")
+    m = helpers.make_module(c["blocks"], 4, "bf16").cuda().eval()
+    m.load_state_dict(c["sd"])
+    gm = GraphedRDST(m)
+    for shape in ((1, 1, 40, 32), (3, 1, 16, 16), (1, 1, 40, 32)):
+        x = torch.rand(*shape, device="cuda")
+        with torch.no_grad():
+            assert torch.equal(gm(x), m(x))
+    vol = torch.rand(10, 1, 40, 32).pin_memory()
+    out = super_resolve_slices(m, vol, batch_size=4)
+    with torch.no_grad():
+        ref = m(vol.cuda()).cpu()
+    assert out.shape == (10, 1, 160, 128) and torch.equal(out, ref)
