@@ -43,6 +43,27 @@ __device__ __forceinline__ float gelu_fn(float x) {
   return fmaf(hx, t, hx);
 }
 
+// Two GELUs per instruction on packed fp16 (same fitted tanh form): a + bias pairs in, packed fp16 pair out.  The
+// fp16 chain is more accurate than rounding the exact value to bf16 (max 3.9e-3 vs 3.1e-2 on |x|<=10), and the hidden
+// activations stay fp16 (fc2 runs with fp16 A and fp16 weights).
+template <bool EXACT>
+__device__ __forceinline__ uint32_t gelu_pair(float a, float b) {
+  if (EXACT) {
+    __half2 r = __floats2half2_rn(gelu_erf(a), gelu_erf(b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  const __half2 x = __floats2half2_rn(a, b);
+  const __half2 u = __hmin2(__hmul2(x, x), __float2half2_rn(64.0f));
+  __half2 p = __hfma2(u, __float2half2_rn(-3.53076214e-04f), __float2half2_rn(3.70152568e-02f));
+  p = __hfma2(u, p, __float2half2_rn(7.97497252e-01f));
+  const __half2 inner = __hmul2(x, p);
+  uint32_t t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&inner)));
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const __half2 r = __hfma2(hx, *reinterpret_cast<const __half2*>(&t), hx);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
 template <int CP, int HP>
 struct MlpCfg {
   static constexpr int NCH = CP / 8;                      // 16-byte chunks per activation row
@@ -278,8 +299,8 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
             uint32_t o[8];
 #pragma unroll
             for (int j = 0; j < 8; ++j)
-              o[j] = pack_bf16x2(gelu_fn<EXACT>(__uint_as_float(v[q * 16 + 2 * j]) + sB1[c0 + 2 * j]),
-                                 gelu_fn<EXACT>(__uint_as_float(v[q * 16 + 2 * j + 1]) + sB1[c0 + 2 * j + 1]));
+              o[j] = gelu_pair<EXACT>(__uint_as_float(v[q * 16 + 2 * j]) + sB1[c0 + 2 * j],
+                                      __uint_as_float(v[q * 16 + 2 * j + 1]) + sB1[c0 + 2 * j + 1]);
             tmem_st_x8(lane_addr + C::TM_HID + c0 / 2, o);
           }
       }
@@ -290,7 +311,7 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
       if (warp_u == 0) {
         fence_after_sync();
         if (elect_one()) {
-          constexpr uint32_t id2 = make_idesc_bf16(128, CP, false, false);
+          constexpr uint32_t id2 = make_idesc_f16(128, CP, false, false);       // hidden and W2 are fp16
           const int ks0 = hbase / 16, ks1 = (hbase + hw) / 16;
           for (int ks = ks0; ks < ks1; ++ks)
             mma_ts(tmem_u + C::TM_FC2, tmem_u + C::TM_HID + ks * 8,

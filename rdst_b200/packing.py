@@ -145,11 +145,16 @@ def pack_upconv(weight, bias, group=FEAT_LD):
 # tcgen05 operand images (bf16).  A K-major SWIZZLE_NONE operand with R rows and K columns is stored as
 # [K/8][R][8]: 8x16-byte core matrices, consecutive rows 16 B apart, K-chunks R*16 B apart (rdst_b200/csrc/umma.cuh).
 # ---------------------------------------------------------------------------------------------------------
-def kmajor_image(w):
-    """[R][K] fp32 -> [K/8][R][8] bf16 (flat)."""
+def kmajor_image(w, dtype=torch.bfloat16):
+    """[R][K] fp32 -> [K/8][R][8] 16-bit (flat)."""
     r, k = w.shape
     assert k % 8 == 0
-    return w.to(torch.bfloat16).reshape(r, k // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
+    return w.to(dtype).reshape(r, k // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
+
+
+def fc2_image(w2):
+    """fc2 weight image: fp16 (the GELU hidden activations are kept in fp16, see tc_mlp.cu)."""
+    return kmajor_image(w2, torch.float16)
 
 
 LOG2E = 1.4426950408889634
@@ -191,7 +196,7 @@ def pack_attn_tc(wqkv, bqkv, wproj, bproj, table, c):
 def pack_stl_tc(p):
     """Add tensor-core operand images to a pack_stl() dict."""
     p["w1img"] = kmajor_image(p["w1"])
-    p["w2img"] = kmajor_image(p["w2"])
+    p["w2img"] = fc2_image(p["w2"])
     p.update(pack_attn_tc(p["wqkv"], p["bqkv"], p["wproj"], p["bproj"], p["table"], p["c"]))
     return p
 
