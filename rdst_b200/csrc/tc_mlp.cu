@@ -78,7 +78,7 @@ struct MlpCfg {
   static constexpr int OFF_W1 = 0;
   static constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
   static constexpr int OFF_XT = OFF_W2 + W2_BYTES;         // raw bf16 tile (residual source, later the output staging)
-  static constexpr int OFF_B1 = OFF_XT + XT_BYTES;
+  static constexpr int OFF_B1 = OFF_XT + 2 * XT_BYTES;     // two raw tiles: tile n+1 streams in (cp.async) while tile n computes
   static constexpr int OFF_B2 = OFF_B1 + HP * 4;
   static constexpr int OFF_STAT = OFF_B2 + CP * 4;         // [128] (mean, rstd)
   static constexpr int OFF_XCH = OFF_STAT + 128 * 8;       // [2][128] (sum, sumsq) exchange for the tail LayerNorm
@@ -122,7 +122,6 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
   __shared__ uint64_t bars[6];          // [0,1] fc1 halves, [2,3] fc2 halves, [4] tail, [5] weights landed
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* sXT = smem + C::OFF_XT;
   float* sB1 = reinterpret_cast<float*>(smem + C::OFF_B1);
   float* sB2 = reinterpret_cast<float*>(smem + C::OFF_B2);
   float2* sStat = reinterpret_cast<float2*>(smem + C::OFF_STAT);
@@ -170,37 +169,57 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
   do {                                                                        \
     if (dbg_on && dbg_n < 64) dbg[half * 64 + dbg_n++] = clock64();           \
   } while (0)
-  uint4 raw[2][C::NCH / 4];
-  auto prefetch = [&](int64_t tile) {
+  // The rows of the next tile stream into the other raw-tile buffer with cp.async (LDGSTS): no staging registers and no
+  // scoreboard slots are held while the loads are in flight (a register prefetch made the fc2 epilogue wait for the
+  // global loads, because LDG and tcgen05.ld share the long-scoreboard slots).
+  auto async_load = [&](int64_t tile, int b) {
+    uint8_t* dst = smem + C::OFF_XT + b * C::XT_BYTES;
 #pragma unroll
     for (int gi = 0; gi < 2; ++gi) {
-      const int64_t t = tile * 128 + (warp + 8 * gi) * 8 + (lane & 7);
+      const int r = (warp + 8 * gi) * 8 + (lane & 7);
+      const int64_t t = tile * 128 + r;
+      const bool ok = tile < ntiles && t < T;
+      const int sw = C::SWZ ? (r & 7) : 0;
 #pragma unroll
-      for (int j = 0; j < C::NCH / 4; ++j)
-        raw[gi][j] = (tile < ntiles && t < T) ? __ldg(reinterpret_cast<const uint4*>(X + t * ldx) + (lane >> 3) + 4 * j)
-                                              : make_uint4(0, 0, 0, 0);
+      for (int j = 0; j < C::NCH / 4; ++j) {
+        const int c = (lane >> 3) + 4 * j;
+        cp_async16(dst + r * C::PITCH + ((c ^ sw) * 16), reinterpret_cast<const uint4*>(X + (ok ? t : 0) * ldx) + c, ok ? 16u : 0u);
+      }
     }
+    cp_async_commit();
   };
   pdl_launch_dependents();
   pdl_wait();                    // prologue above touched only weights; the rows below come from the previous kernel
-  prefetch(blockIdx.x);
+  async_load(blockIdx.x, 0);
+  int buf = 0;
 
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1) {
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1, buf ^= 1) {
     const int64_t t0 = tile * 128;
+    uint8_t* sXT = smem + C::OFF_XT + buf * C::XT_BYTES;
+    cp_async_wait_all();           // this tile's rows have landed (issued one tile ago)
+    __syncthreads();
+    async_load(tile + gridDim.x, buf ^ 1);    // the other buffer was drained by the previous tile's copy-out
     RDST_TSTAMP();   // tile start
-    // ---------------- P1a: (prefetched) rows -> raw tile in smem, LayerNorm statistics ----------------
+    // ---------------- P1a: LayerNorm statistics of the landed raw tile (coalesced mapping, 2 shuffles) ----------------
     {
+      uint4 raw[2][C::NCH / 4];
 #pragma unroll
       for (int gi = 0; gi < 2; ++gi) {
         const int r = (warp + 8 * gi) * 8 + (lane & 7);
         const int sw = C::SWZ ? (r & 7) : 0;
+#pragma unroll
+        for (int j = 0; j < C::NCH / 4; ++j)
+          raw[gi][j] = *reinterpret_cast<const uint4*>(sXT + r * C::PITCH + ((((lane >> 3) + 4 * j) ^ sw) * 16));
+      }
+#pragma unroll
+      for (int gi = 0; gi < 2; ++gi) {
+        const int r = (warp + 8 * gi) * 8 + (lane & 7);
         float s = 0.f;
 #pragma unroll
         for (int j = 0; j < C::NCH / 4; ++j) {
           const float2 f0 = unpack_bf16x2(raw[gi][j].x), f1 = unpack_bf16x2(raw[gi][j].y), f2 = unpack_bf16x2(raw[gi][j].z),
                        f3 = unpack_bf16x2(raw[gi][j].w);
           s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
-          *reinterpret_cast<uint4*>(sXT + r * C::PITCH + ((((lane >> 3) + 4 * j) ^ sw) * 16)) = raw[gi][j];
         }
         s += __shfl_xor_sync(0xffffffffu, s, 8);
         s += __shfl_xor_sync(0xffffffffu, s, 16);
@@ -320,7 +339,6 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
         }
         __syncwarp();
       }
-      if (h == 1) prefetch(tile + gridDim.x);
     }
     // ---------------- P5: fc2 epilogue in the row mapping: y = acc + b2 + x (raw tile) ----------------
     RDST_TSTAMP();   // before fc2 wait

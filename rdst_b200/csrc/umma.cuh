@@ -165,6 +165,14 @@ __device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.comm
 // all bulk stores of this thread have finished READING shared memory (the buffer may be overwritten)
 __device__ __forceinline__ void bulk_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 
+// Ampere-style async copy (LDGSTS): 16 bytes global -> shared without staging registers or scoreboard slots;
+// src_bytes == 0 zero-fills.  Completion: cp_async_commit() + cp_async_wait_all().
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uint32_t src_bytes) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+
 // Programmatic dependent launch: let the next kernel of the stream start its prologue early / wait for the producer
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
