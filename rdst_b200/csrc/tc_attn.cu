@@ -56,13 +56,15 @@ struct AttnCfg {
   static constexpr bool SWZ = (NCH == 8 || NCH == 16);      // raw tile: XOR-swizzled rows, else padded rows
   static constexpr int PITCH = SWZ ? CP * 2 : CP * 2 + 16;
   static constexpr int XT_BYTES = 128 * PITCH;
+  static constexpr bool ASYNC = (C != 120);                 // C=60/90: a second raw tile fits -> cp.async prefetch; C=120: registers
+  static constexpr int NXT = ASYNC ? 2 : 1;
   static constexpr int BK_BYTES = 128 * HDP * 2;            // K image (K-major)
   static constexpr int BV_BYTES = 128 * HDV * 2;            // V image (MN-major, fp16)
   static constexpr int KV_BYTES = BK_BYTES + BV_BYTES;      // per warpgroup
   static constexpr int OFF_WQKV = 0;
   static constexpr int OFF_WPROJ = OFF_WQKV + WQKV_BYTES;
   static constexpr int OFF_XT = OFF_WPROJ + WPROJ_BYTES;    // raw bf16 tile: LN source, residual, output staging
-  static constexpr int OFF_KV = OFF_XT + XT_BYTES;          // [2 warpgroups][K | V]
+  static constexpr int OFF_KV = OFF_XT + NXT * XT_BYTES;    // [2 warpgroups][K | V]
   static constexpr int OFF_TAB = OFF_KV + 2 * KV_BYTES;
   static constexpr int OFF_BQKV = OFF_TAB + 6 * TBL * 4;
   static constexpr int OFF_BPROJ = OFF_BQKV + 6 * NH * 4;
@@ -154,7 +156,6 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = tid >> 7;              // warpgroup: owns heads wg, wg+2, wg+4
   const int row = tid & 127;
-  uint8_t* sXT = smem + K::OFF_XT;
   uint8_t* sBk = smem + K::OFF_KV + wg * K::KV_BYTES;
   uint8_t* sBv = sBk + K::BK_BYTES;
   float* sTab = reinterpret_cast<float*>(smem + K::OFF_TAB);
@@ -231,7 +232,7 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   uint4 raw[2][K::NCH / 4];
   int64_t tok[2];
   int regv[2];
-  auto prefetch = [&](int tile) {
+  auto prefetch = [&](int tile, int nbuf) {
 #pragma unroll
     for (int gi = 0; gi < 2; ++gi) {
       const int g = warp + 8 * gi;
@@ -240,31 +241,61 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       tok[gi] = -1;
       if (tile < ntiles && win < geo.nwt) tok[gi] = win_token(geo, win, g & 7, lane & 7, region, edge);
       regv[gi] = edge ? region : -1;
+      if (K::ASYNC) {
+        // cp.async straight into the other raw-tile buffer: no staging registers, no scoreboard slots in flight
+        const int r = g * 8 + (lane & 7);
+        const int sw = K::SWZ ? (r & 7) : 0;
+        uint8_t* dst = smem + K::OFF_XT + nbuf * K::XT_BYTES + r * K::PITCH;
 #pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j)
-        raw[gi][j] = tok[gi] >= 0 ? __ldg(reinterpret_cast<const uint4*>(X + tok[gi] * ldx) + (lane >> 3) + 4 * j)
-                                  : make_uint4(0, 0, 0, 0);
+        for (int j = 0; j < K::NCH / 4; ++j) {
+          const int c = (lane >> 3) + 4 * j;
+          cp_async16(dst + ((c ^ sw) * 16), reinterpret_cast<const uint4*>(X + (tok[gi] >= 0 ? tok[gi] : 0) * ldx) + c,
+                     tok[gi] >= 0 ? 16u : 0u);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < K::NCH / 4; ++j)
+          raw[gi][j] = tok[gi] >= 0 ? __ldg(reinterpret_cast<const uint4*>(X + tok[gi] * ldx) + (lane >> 3) + 4 * j)
+                                    : make_uint4(0, 0, 0, 0);
+      }
     }
+    if (K::ASYNC) cp_async_commit();
   };
   pdl_launch_dependents();       // the next kernel may start its own prologue as SMs free up
   pdl_wait();                    // everything above touched only weights; from here on we read the producer's output
-  prefetch(blockIdx.x);
+  prefetch(blockIdx.x, 0);
+  int buf = 0;
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= (K::ASYNC ? 1 : 0)) {
+    uint8_t* sXT = smem + K::OFF_XT + buf * K::XT_BYTES;
     // ---------------- P1a: (prefetched) rows of two windows -> raw tile in smem + LayerNorm statistics ----------------
     RDST_TSTAMP();   // tile start
     int64_t tok_cur[2] = {tok[0], tok[1]};
+    const int reg_cur[2] = {regv[0], regv[1]};
+    if (K::ASYNC) {
+      cp_async_wait_all();           // this tile's rows have landed (issued one tile ago)
+      __syncthreads();
+      prefetch(tile + gridDim.x, buf ^ 1);    // the other buffer was drained by the previous tile's copy-out
+#pragma unroll
+      for (int gi = 0; gi < 2; ++gi) {
+        const int r = (warp + 8 * gi) * 8 + (lane & 7);
+        const int sw = K::SWZ ? (r & 7) : 0;
+#pragma unroll
+        for (int j = 0; j < K::NCH / 4; ++j)
+          raw[gi][j] = *reinterpret_cast<const uint4*>(sXT + r * K::PITCH + ((((lane >> 3) + 4 * j) ^ sw) * 16));
+      }
+    }
 #pragma unroll
     for (int gi = 0; gi < 2; ++gi) {
       const int r = (warp + 8 * gi) * 8 + (lane & 7);
       const int sw = K::SWZ ? (r & 7) : 0;
-      if ((lane >> 3) == 0) sReg[r] = regv[gi];
+      if ((lane >> 3) == 0) sReg[r] = reg_cur[gi];
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < K::NCH / 4; ++j) {
         const float2 f0 = up2(raw[gi][j].x), f1 = up2(raw[gi][j].y), f2 = up2(raw[gi][j].z), f3 = up2(raw[gi][j].w);
         s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
-        *reinterpret_cast<uint4*>(sXT + r * K::PITCH + ((((lane >> 3) + 4 * j) ^ sw) * 16)) = raw[gi][j];
+        if (!K::ASYNC) *reinterpret_cast<uint4*>(sXT + r * K::PITCH + ((((lane >> 3) + 4 * j) ^ sw) * 16)) = raw[gi][j];
       }
       s += __shfl_xor_sync(0xffffffffu, s, 8);
       s += __shfl_xor_sync(0xffffffffu, s, 16);
@@ -508,8 +539,8 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       }
       __syncwarp();
     }
-    // prefetch the next tile's rows: the global-load latency hides under proj and the copy-out
-    prefetch(tile + gridDim.x);
+    // C=120 (no room for a second raw tile): prefetch the next tile's rows into registers under proj and the copy-out
+    if (!K::ASYNC) prefetch(tile + gridDim.x, 0);
     RDST_TSTAMP();   // O epilogue + proj issued
     mbar_wait(&bars[6], ph_p & 1); ph_p++;
     fence_after_sync();
