@@ -128,15 +128,17 @@ __device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {              // two fp1
   return y;
 }
 
-// 8 consecutive accumulator values (+bias) as four packed 16-bit pairs, zero beyond HD
-template <int OFFSET, int HD, bool HALF>
+// 8 consecutive accumulator values (+bias) as four packed 16-bit pairs, zero beyond HD.  ONES: element HD is 1.0, so
+// that column HD of O = P.V' accumulates the softmax row sum on the tensor core (exactly the fp16 P values that
+// enter the MMA) and the CUDA cores never add the probabilities up.
+template <int OFFSET, int HD, bool HALF, bool ONES = false>
 __device__ __forceinline__ uint4 pack8(const float* f, const float* bias, int c8) {
   uint32_t o[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int d0 = c8 * 8 + 2 * q, d1 = d0 + 1;
-    const float a = d0 < HD ? f[OFFSET + d0] + bias[OFFSET + d0] : 0.f;
-    const float b = d1 < HD ? f[OFFSET + d1] + bias[OFFSET + d1] : 0.f;
+    const float a = d0 < HD ? f[OFFSET + d0] + bias[OFFSET + d0] : ((ONES && d0 == HD) ? 1.f : 0.f);
+    const float b = d1 < HD ? f[OFFSET + d1] + bias[OFFSET + d1] : ((ONES && d1 == HD) ? 1.f : 0.f);
     o[q] = HALF ? pk2h(a, b) : pk2(a, b);
   }
   return make_uint4(o[0], o[1], o[2], o[3]);
@@ -361,7 +363,6 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
         mhi |= (rg[32 + j] != myreg) ? (1u << j) : 0u;
       }
     }
-    float psum[3];
 
     // ---------------- heads of this warpgroup ----------------
 #pragma unroll
@@ -396,8 +397,8 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
           *reinterpret_cast<uint4*>(sBk + c8 * 2048 + row * 16) = pack8<HD, HD, false>(f, bq, c8);
         if (i > 0) mbar_wait(bar_o, (ph_o - 1) & 1);          // PV of the previous head has finished reading V
 #pragma unroll
-        for (int c8 = 0; c8 < (HD + 7) / 8; ++c8)
-          *reinterpret_cast<uint4*>(sBv + c8 * 2048 + row * 16) = pack8<2 * HD, HD, true>(f, bq, c8);   // MN-major, fp16
+        for (int c8 = 0; c8 < (HD + 8) / 8; ++c8)      // covers column HD (the ones column)
+          *reinterpret_cast<uint4*>(sBv + c8 * 2048 + row * 16) = pack8<2 * HD, HD, true, true>(f, bq, c8);   // MN-major, fp16
         wait_st();
       }
       fence_proxy_async();
@@ -448,15 +449,10 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
         const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
         RDST_TSTAMP();   // bias + max
         // exp2 on packed fp16 pairs: one MUFU op per two probabilities; P stays fp16 (V is fp16 as well)
-        float s4[4] = {0.f, 0.f, 0.f, 0.f};
         uint32_t o[32];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < 32; ++j)
           o[j] = ex2_h2(pk2h(__uint_as_float(v[2 * j]) - mx, __uint_as_float(v[2 * j + 1]) - mx));
-          const float2 pf = __half22float2(*reinterpret_cast<const __half2*>(&o[j]));
-          s4[j & 3] += pf.x + pf.y;
-        }
-        psum[i] = (s4[0] + s4[1]) + (s4[2] + s4[3]);
         tmem_st_x32(lane_addr + tS, o);                     // P overwrites the first 32 columns of S
         wait_st();
       }
@@ -485,7 +481,7 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     mbar_wait(bar_o, (ph_o - 1) & 1);
     fence_after_sync();
     __syncthreads();                    // both warpgroups are past their last qkv MMA: the normalised input is dead
-    constexpr int NCO = (HD + 7) / 8 * 8;
+    constexpr int NCO = (HD + 8) / 8 * 8;      // head_dim values + the row-sum column
     float fo[3][NCO];
 #pragma unroll
     for (int i = 0; i < 3; ++i)
@@ -501,7 +497,7 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     for (int i = 0; i < 3; ++i) {
       const int h = wg + 2 * i;
       const float* f = fo[i];
-      const float inv = 1.0f / psum[i];
+      const float inv = 1.0f / f[HD];             // softmax row sum, accumulated by the PV MMA (ones column of V)
       if (K::HDO == 16) {
         uint32_t a[8];
 #pragma unroll
