@@ -29,20 +29,8 @@ __device__ __forceinline__ float2 unpack_bf16x2(uint32_t u) {
   return __bfloat1622float2(v);
 }
 
-// GELU(x) = x*Phi(x).  Fast form: Phi(x) ~ 0.5*(1+tanh(x*(a+b x^2+c x^4))) fitted to the exact erf form
-// (max abs deviation 2.6e-5 on |x|<=8, i.e. far below bf16 resolution); EXACT uses erff.
-template <bool EXACT>
-__device__ __forceinline__ float gelu_fn(float x) {
-  if (EXACT) return gelu_erf(x);
-  const float xc = fminf(fmaxf(x, -8.0f), 8.0f);
-  const float u = xc * xc;
-  const float inner = xc * fmaf(u, fmaf(u, -3.53076214e-04f, 3.70152568e-02f), 7.97497252e-01f);
-  float t;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(t) : "f"(inner));
-  const float hx = 0.5f * x;
-  return fmaf(hx, t, hx);
-}
-
+// GELU(x) = x*Phi(x) with Phi(x) ~ 0.5*(1+tanh(x*(a+b x^2+c x^4))), a/b/c fitted to the exact erf form
+// (max abs deviation 2.6e-5 on |x|<=8); EXACT evaluates erff instead.
 // Two GELUs per instruction on packed fp16 (same fitted tanh form): a + bias pairs in, packed fp16 pair out.  The
 // fp16 chain is more accurate than rounding the exact value to bf16 (max 3.9e-3 vs 3.1e-2 on |x|<=10), and the hidden
 // activations stay fp16 (fc2 runs with fp16 A and fp16 weights).
