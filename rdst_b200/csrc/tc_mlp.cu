@@ -69,8 +69,8 @@ struct MlpCfg {
   static constexpr int OFF_B1 = OFF_XT + 2 * XT_BYTES;     // two raw tiles: tile n+1 streams in (cp.async) while tile n computes
   static constexpr int OFF_B2 = OFF_B1 + HP * 4;
   static constexpr int OFF_STAT = OFF_B2 + CP * 4;         // [128] (mean, rstd)
-  static constexpr int OFF_XCH = OFF_STAT + 128 * 8;       // [2][128] (sum, sumsq) exchange for the tail LayerNorm
-  static constexpr int OFF_WT = OFF_XCH + 2 * 128 * 8;     // fused DenseSTLayer tail: Linear(C -> 30, padded 32) image
+  static constexpr int OFF_XCH = OFF_STAT + 128 * 8;       // [4][128] (sum, sumsq) exchange for the tail LayerNorm
+  static constexpr int OFF_WT = OFF_XCH + 4 * 128 * 8;     // fused DenseSTLayer tail: Linear(C -> 30, padded 32) image
   static constexpr int OFF_BT = OFF_WT + WT_BYTES;
   static constexpr int SMEM_PLAIN = OFF_WT;
   static constexpr int SMEM_TAIL = OFF_BT + 32 * 4;
@@ -99,8 +99,10 @@ struct TailArgs {
   float scale;               // dense_scale
 };
 
+constexpr int MLP_THREADS = 512;      // 16 warps: four threads (one per warpgroup) share a token row / TMEM lane
+
 template <int CP, int HP, bool EXACT, bool TAIL>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(MLP_THREADS, 1)
 stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* __restrict__ Y, int64_t ldy,
                const uint8_t* __restrict__ w1img, const uint8_t* __restrict__ w2img,
                const float* __restrict__ b1, const float* __restrict__ b2, int64_t T, int creal, TailArgs ta,
@@ -128,10 +130,10 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
       bulk_g2s(smem + C::OFF_W2 + off, w2img + off, min(32768, C::W2_BYTES - off), &bars[5]);
     if (TAIL) bulk_g2s(smem + C::OFF_WT, ta.wtimg, C::WT_BYTES, &bars[5]);
   }
-  for (int i = tid; i < HP; i += 256) sB1[i] = b1[i];
-  for (int i = tid; i < CP; i += 256) sB2[i] = b2[i];
+  for (int i = tid; i < HP; i += MLP_THREADS) sB1[i] = b1[i];
+  for (int i = tid; i < CP; i += MLP_THREADS) sB2[i] = b2[i];
   if (TAIL) {
-    for (int i = tid; i < 32; i += 256) reinterpret_cast<float*>(smem + C::OFF_BT)[i] = ta.bt[i];
+    for (int i = tid; i < 32; i += MLP_THREADS) reinterpret_cast<float*>(smem + C::OFF_BT)[i] = ta.bt[i];
   }
   fence_proxy_async();
   fence_before_sync();
@@ -139,7 +141,7 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
 
-  const int row = tid & 127, half = tid >> 7;
+  const int row = tid & 127, qtr = tid >> 7;             // token row (= TMEM lane) and column quarter of this thread
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int rsw = C::SWZ ? (row & 7) : 0;
   // warp-uniform values for the MMA issuer (warp 0): descriptors stay in uniform registers
@@ -149,30 +151,27 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
   const float inv_c = 1.0f / (float)creal;
   const int64_t ntiles = (T + 127) / 128;
   uint32_t parity = 0;
+  // coalesced mapping: warp w owns the 8-row group w; lane -> (row w*8 + lane%8, 16-byte chunk lane/8 + 4j)
+  const int cr = warp * 8 + (lane & 7);
+  const int csw = C::SWZ ? (cr & 7) : 0;
 
-  // rows of the next tile are requested one tile ahead (registers), so their latency hides under the GEMM pair
   int dbg_n = 0;
-  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && (tid & 127) == 0;
+  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && (tid & 127) == 0 && qtr < 2;
 #define RDST_TSTAMP()                                                         \
   do {                                                                        \
-    if (dbg_on && dbg_n < 64) dbg[half * 64 + dbg_n++] = clock64();           \
+    if (dbg_on && dbg_n < 64) dbg[qtr * 64 + dbg_n++] = clock64();            \
   } while (0)
   // The rows of the next tile stream into the other raw-tile buffer with cp.async (LDGSTS): no staging registers and no
   // scoreboard slots are held while the loads are in flight (a register prefetch made the fc2 epilogue wait for the
   // global loads, because LDG and tcgen05.ld share the long-scoreboard slots).
   auto async_load = [&](int64_t tile, int b) {
-    uint8_t* dst = smem + C::OFF_XT + b * C::XT_BYTES;
+    uint8_t* dst = smem + C::OFF_XT + b * C::XT_BYTES + cr * C::PITCH;
+    const int64_t t = tile * 128 + cr;
+    const bool ok = tile < ntiles && t < T;
 #pragma unroll
-    for (int gi = 0; gi < 2; ++gi) {
-      const int r = (warp + 8 * gi) * 8 + (lane & 7);
-      const int64_t t = tile * 128 + r;
-      const bool ok = tile < ntiles && t < T;
-      const int sw = C::SWZ ? (r & 7) : 0;
-#pragma unroll
-      for (int j = 0; j < C::NCH / 4; ++j) {
-        const int c = (lane >> 3) + 4 * j;
-        cp_async16(dst + r * C::PITCH + ((c ^ sw) * 16), reinterpret_cast<const uint4*>(X + (ok ? t : 0) * ldx) + c, ok ? 16u : 0u);
-      }
+    for (int j = 0; j < C::NCH / 4; ++j) {
+      const int c = (lane >> 3) + 4 * j;
+      cp_async16(dst + ((c ^ csw) * 16), reinterpret_cast<const uint4*>(X + (ok ? t : 0) * ldx) + c, ok ? 16u : 0u);
     }
     cp_async_commit();
   };
@@ -190,54 +189,45 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
     RDST_TSTAMP();   // tile start
     // ---------------- P1a: LayerNorm statistics of the landed raw tile (coalesced mapping, 2 shuffles) ----------------
     {
-      uint4 raw[2][C::NCH / 4];
+      uint4 raw[C::NCH / 4];
 #pragma unroll
-      for (int gi = 0; gi < 2; ++gi) {
-        const int r = (warp + 8 * gi) * 8 + (lane & 7);
-        const int sw = C::SWZ ? (r & 7) : 0;
+      for (int j = 0; j < C::NCH / 4; ++j)
+        raw[j] = *reinterpret_cast<const uint4*>(sXT + cr * C::PITCH + ((((lane >> 3) + 4 * j) ^ csw) * 16));
+      float s = 0.f;
 #pragma unroll
-        for (int j = 0; j < C::NCH / 4; ++j)
-          raw[gi][j] = *reinterpret_cast<const uint4*>(sXT + r * C::PITCH + ((((lane >> 3) + 4 * j) ^ sw) * 16));
+      for (int j = 0; j < C::NCH / 4; ++j) {
+        const float2 f0 = unpack_bf16x2(raw[j].x), f1 = unpack_bf16x2(raw[j].y), f2 = unpack_bf16x2(raw[j].z),
+                     f3 = unpack_bf16x2(raw[j].w);
+        s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
       }
+      s += __shfl_xor_sync(0xffffffffu, s, 8);
+      s += __shfl_xor_sync(0xffffffffu, s, 16);
+      const float mean = s * inv_c;
+      float ss = 0.f;
 #pragma unroll
-      for (int gi = 0; gi < 2; ++gi) {
-        const int r = (warp + 8 * gi) * 8 + (lane & 7);
-        float s = 0.f;
+      for (int j = 0; j < C::NCH / 4; ++j) {
+        const uint32_t w4[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
 #pragma unroll
-        for (int j = 0; j < C::NCH / 4; ++j) {
-          const float2 f0 = unpack_bf16x2(raw[gi][j].x), f1 = unpack_bf16x2(raw[gi][j].y), f2 = unpack_bf16x2(raw[gi][j].z),
-                       f3 = unpack_bf16x2(raw[gi][j].w);
-          s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = unpack_bf16x2(w4[q]);
+          ss += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
         }
-        s += __shfl_xor_sync(0xffffffffu, s, 8);
-        s += __shfl_xor_sync(0xffffffffu, s, 16);
-        const float mean = s * inv_c;
-        float ss = 0.f;
-#pragma unroll
-        for (int j = 0; j < C::NCH / 4; ++j) {
-          const uint32_t w4[4] = {raw[gi][j].x, raw[gi][j].y, raw[gi][j].z, raw[gi][j].w};
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float2 f = unpack_bf16x2(w4[q]);
-            ss += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
-          }
-        }
-        ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-        ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-        ss -= (float)(CP - creal) * mean * mean;                 // zero pads contributed mean^2 each
-        if ((lane >> 3) == 0) sStat[r] = make_float2(mean, rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f));
       }
+      ss += __shfl_xor_sync(0xffffffffu, ss, 8);
+      ss += __shfl_xor_sync(0xffffffffu, ss, 16);
+      ss -= (float)(CP - creal) * mean * mean;                 // zero pads contributed mean^2 each
+      if ((lane >> 3) == 0) sStat[cr] = make_float2(mean, rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f));
     }
     __syncthreads();
     RDST_TSTAMP();   // P1a done
-    // ---------------- P1b: thread = token row: normalise its half row -> packed bf16 A operand in TMEM ----------------
+    // ---------------- P1b: thread = (token row, quarter): normalise -> packed bf16 A operand in TMEM ----------------
     {
       const float2 st = sStat[row];
-      constexpr int NC = C::NCH / 2;                            // chunks per thread
+      constexpr int NC = C::NCH / 4;                            // 16-byte chunks per thread (2, 3 or 4)
       uint32_t o[NC * 4];
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc) {
-        const int c = half * NC + cc;
+        const int c = qtr * NC + cc;
         const uint4 v = *reinterpret_cast<const uint4*>(sXT + row * C::PITCH + ((c ^ rsw) * 16));
         const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
@@ -246,9 +236,13 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
           o[cc * 4 + q] = pack_bf16x2((f.x - st.x) * st.y, (f.y - st.x) * st.y);
         }
       }
-      const uint32_t dst = lane_addr + C::TM_XH + half * NC * 4;
+      const uint32_t dst = lane_addr + C::TM_XH + qtr * NC * 4;
 #pragma unroll
-      for (int c0 = 0; c0 < NC * 4; c0 += 8) tmem_st8(dst + c0, o + c0);
+      for (int c0 = 0; c0 + 8 <= NC * 4; c0 += 8) tmem_st8(dst + c0, o + c0);
+      if ((NC * 4) % 8 != 0) {
+        uint32_t a4[4] = {o[NC * 4 - 4], o[NC * 4 - 3], o[NC * 4 - 2], o[NC * 4 - 1]};
+        tmem_st_x4(dst + NC * 4 - 4, a4);
+      }
       wait_st();
     }
     fence_before_sync();
@@ -263,52 +257,51 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
         constexpr uint32_t id1 = make_idesc_bf16(128, C::H1, false, false);
 #pragma unroll
         for (int ks = 0; ks < CP / 16; ++ks)
-          mma_ts(tmem_u + C::TM_FC1, tmem_u + C::TM_XH + ks * 8,
-                             make_smem_desc(aW1 + ks * 2 * (HP * 16), HP * 16, 128), id0, ks > 0);
+          mma_ts(tmem_u + C::TM_FC1, tmem_u + C::TM_XH + ks * 8, make_smem_desc(aW1 + ks * 2 * (HP * 16), HP * 16, 128), id0, ks > 0);
         commit(&bars[0]);
 #pragma unroll
         for (int ks = 0; ks < CP / 16; ++ks)
           mma_ts(tmem_u + C::TM_FC1 + C::H0, tmem_u + C::TM_XH + ks * 8,
-                             make_smem_desc(aW1 + C::H0 * 16 + ks * 2 * (HP * 16), HP * 16, 128), id1, ks > 0);
+                 make_smem_desc(aW1 + C::H0 * 16 + ks * 2 * (HP * 16), HP * 16, 128), id1, ks > 0);
         commit(&bars[1]);
       }
       __syncwarp();
     }
-    // ---------------- P3: GELU epilogue per half -> packed hidden in TMEM; fc2 K-half issued behind it ----------------
+    // ---------------- P3: GELU epilogue per half -> packed fp16 hidden in TMEM; fc2 K-half issued behind it ----------------
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       const int hbase = h == 0 ? 0 : C::H0;
       const int hw = h == 0 ? C::H0 : C::H1;
-      const int w0 = (hw / 2 + 15) / 16 * 16;                  // columns of this half taken by warpgroup 0
-      const int cbeg = hbase + (half == 0 ? 0 : w0);
-      const int cend = hbase + (half == 0 ? w0 : hw);
+      const int qw = (hw / 4 + 7) / 8 * 8;                     // columns per quarter (multiple of 8), last one may be short
+      const int cbeg = hbase + min(qtr * qw, hw);
+      const int cend = hbase + min((qtr + 1) * qw, hw);
       RDST_TSTAMP();   // before fc1 half wait
       mbar_wait(&bars[h], parity);
       fence_after_sync();
       RDST_TSTAMP();   // fc1 half ready
       {
         // all accumulator columns of this thread are requested up front (one wait), then GELU -> packed hidden
-        constexpr int MAXC = 64;
+        constexpr int MAXC = 32;
         uint32_t v[MAXC];
 #pragma unroll
-        for (int q = 0; q < MAXC / 16; ++q)
-          if (cbeg + q * 16 < cend) {
-            uint32_t t16[16];
-            tmem_ld_x16(lane_addr + C::TM_FC1 + cbeg + q * 16, t16);
+        for (int q = 0; q < MAXC / 8; ++q)
+          if (cbeg + q * 8 < cend) {
+            uint32_t t8[8];
+            tmem_ld_x8(lane_addr + C::TM_FC1 + cbeg + q * 8, t8);
 #pragma unroll
-            for (int e = 0; e < 16; ++e) v[q * 16 + e] = t16[e];
+            for (int e = 0; e < 8; ++e) v[q * 8 + e] = t8[e];
           }
         wait_ld();
 #pragma unroll
-        for (int q = 0; q < MAXC / 16; ++q)
-          if (cbeg + q * 16 < cend) {
-            const int c0 = cbeg + q * 16;
-            uint32_t o[8];
+        for (int q = 0; q < MAXC / 8; ++q)
+          if (cbeg + q * 8 < cend) {
+            const int c0 = cbeg + q * 8;
+            uint32_t o[4];
 #pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o[j] = gelu_pair<EXACT>(__uint_as_float(v[q * 16 + 2 * j]) + sB1[c0 + 2 * j],
-                                      __uint_as_float(v[q * 16 + 2 * j + 1]) + sB1[c0 + 2 * j + 1]);
-            tmem_st_x8(lane_addr + C::TM_HID + c0 / 2, o);
+            for (int j = 0; j < 4; ++j)
+              o[j] = gelu_pair<EXACT>(__uint_as_float(v[q * 8 + 2 * j]) + sB1[c0 + 2 * j],
+                                      __uint_as_float(v[q * 8 + 2 * j + 1]) + sB1[c0 + 2 * j + 1]);
+            tmem_st_x4(lane_addr + C::TM_HID + c0 / 2, o);
           }
       }
       wait_st();
@@ -321,8 +314,7 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
           constexpr uint32_t id2 = make_idesc_f16(128, CP, false, false);       // hidden and W2 are fp16
           const int ks0 = hbase / 16, ks1 = (hbase + hw) / 16;
           for (int ks = ks0; ks < ks1; ++ks)
-            mma_ts(tmem_u + C::TM_FC2, tmem_u + C::TM_HID + ks * 8,
-                               make_smem_desc(aW2 + ks * 2 * (CP * 16), CP * 16, 128), id2, ks > 0);
+            mma_ts(tmem_u + C::TM_FC2, tmem_u + C::TM_HID + ks * 8, make_smem_desc(aW2 + ks * 2 * (CP * 16), CP * 16, 128), id2, ks > 0);
           commit(&bars[2 + h]);
         }
         __syncwarp();
@@ -335,54 +327,58 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
     fence_after_sync();
     RDST_TSTAMP();   // fc2 ready
     {
-      constexpr int NC = CP / 2;                               // columns per thread
-      const int cb = half * NC;
+      constexpr int NC = CP / 4;                               // columns per thread (16, 24 or 32)
+      const int cb = qtr * NC;
       float y[NC];
       float s1 = 0.f, s2 = 0.f;
       uint32_t acc[NC];
 #pragma unroll
-      for (int c0 = 0; c0 < NC; c0 += 16) {
-        uint32_t t16[16];
-        tmem_ld_x16(lane_addr + C::TM_FC2 + cb + c0, t16);
+      for (int c0 = 0; c0 < NC; c0 += 8) {
+        uint32_t t8[8];
+        tmem_ld_x8(lane_addr + C::TM_FC2 + cb + c0, t8);
 #pragma unroll
-        for (int e = 0; e < 16; ++e) acc[c0 + e] = t16[e];
+        for (int e = 0; e < 8; ++e) acc[c0 + e] = t8[e];
       }
       wait_ld();
 #pragma unroll
-      for (int c0 = 0; c0 < NC; c0 += 16) {
-        const uint32_t* v = acc + c0;
+      for (int c0 = 0; c0 < NC; c0 += 8) {
+        const int ch = (cb + c0) / 8;
+        uint8_t* xp = sXT + row * C::PITCH + ((ch ^ rsw) * 16);
+        const uint4 xv = *reinterpret_cast<const uint4*>(xp);
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+        uint32_t o[4];
 #pragma unroll
-        for (int q = 0; q < 2; ++q) {
-          const int ch = (cb + c0) / 8 + q;
-          const uint4 xv = *reinterpret_cast<const uint4*>(sXT + row * C::PITCH + ((ch ^ rsw) * 16));
-          const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-          uint32_t o[4];
-#pragma unroll
-          for (int e = 0; e < 4; ++e) {
-            const float2 xf = unpack_bf16x2(xw[e]);
-            const int k = c0 + q * 8 + 2 * e;
-            y[k] = __uint_as_float(v[q * 8 + 2 * e]) + sB2[cb + k] + xf.x;
-            y[k + 1] = __uint_as_float(v[q * 8 + 2 * e + 1]) + sB2[cb + k + 1] + xf.y;
-            s1 += y[k] + y[k + 1];
-            s2 += y[k] * y[k] + y[k + 1] * y[k + 1];
-            o[e] = pack_bf16x2(y[k], y[k + 1]);
-          }
-          if (!TAIL) *reinterpret_cast<uint4*>(sXT + row * C::PITCH + ((ch ^ rsw) * 16)) = make_uint4(o[0], o[1], o[2], o[3]);
+        for (int e = 0; e < 4; ++e) {
+          const float2 xf = unpack_bf16x2(xw[e]);
+          const int k = c0 + 2 * e;
+          y[k] = __uint_as_float(acc[k]) + sB2[cb + k] + xf.x;
+          y[k + 1] = __uint_as_float(acc[k + 1]) + sB2[cb + k + 1] + xf.y;
+          s1 += y[k] + y[k + 1];
+          s2 += y[k] * y[k] + y[k + 1] * y[k + 1];
+          o[e] = pack_bf16x2(y[k], y[k + 1]);
         }
+        if (!TAIL) *reinterpret_cast<uint4*>(xp) = make_uint4(o[0], o[1], o[2], o[3]);
       }
       if (TAIL) {
-        // LayerNorm of the block output over the full row: the two column halves live in two warpgroups
-        sXch[half * 128 + row] = make_float2(s1, s2);
+        // LayerNorm of the block output over the full row: its four column quarters live in four warpgroups
+        sXch[qtr * 128 + row] = make_float2(s1, s2);
         __syncthreads();
-        const float2 other = sXch[(1 - half) * 128 + row];
-        const float mean = (s1 + other.x) * inv_c;
-        const float var = fmaxf((s2 + other.y) * inv_c - mean * mean, 0.f);   // pads are exact zeros: they add nothing
+        float t1 = 0.f, t2 = 0.f;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) { const float2 p = sXch[q * 128 + row]; t1 += p.x; t2 += p.y; }
+        const float mean = t1 * inv_c;
+        const float var = fmaxf(t2 * inv_c - mean * mean, 0.f);   // pads are exact zeros: they add nothing
         const float rstd = rsqrtf(var + 1e-5f);
         uint32_t o[NC / 2];
 #pragma unroll
         for (int k = 0; k < NC; k += 2) o[k / 2] = pack_bf16x2((y[k] - mean) * rstd, (y[k + 1] - mean) * rstd);
+        const uint32_t dst = lane_addr + C::TM_XH + cb / 2;
 #pragma unroll
-        for (int c0 = 0; c0 < NC / 2; c0 += 8) tmem_st8(lane_addr + C::TM_XH + cb / 2 + c0, o + c0);
+        for (int c0 = 0; c0 + 8 <= NC / 2; c0 += 8) tmem_st8(dst + c0, o + c0);
+        if ((NC / 2) % 8 != 0) {
+          uint32_t a4[4] = {o[NC / 2 - 4], o[NC / 2 - 3], o[NC / 2 - 2], o[NC / 2 - 1]};
+          tmem_st_x4(dst + NC / 2 - 4, a4);
+        }
         wait_st();
       }
     }
@@ -396,45 +392,38 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
           constexpr uint32_t idt = make_idesc_bf16(128, 32, false, false);
 #pragma unroll
           for (int ks = 0; ks < CP / 16; ++ks)
-            mma_ts(tmem_u + C::TM_FC1, tmem_u + C::TM_XH + ks * 8,
-                               make_smem_desc(aWT + ks * 2 * (32 * 16), 32 * 16, 128), idt, ks > 0);
+            mma_ts(tmem_u + C::TM_FC1, tmem_u + C::TM_XH + ks * 8, make_smem_desc(aWT + ks * 2 * (32 * 16), 32 * 16, 128), idt, ks > 0);
           commit(&bars[4]);
         }
         __syncwarp();
       }
       mbar_wait(&bars[4], parity);
       fence_after_sync();
-      if (half == 0) {
+      {
+        // each quarter writes 8 of the 32 growth columns of its row (16 bytes)
         const float* sBT = reinterpret_cast<const float*>(smem + C::OFF_BT);
-        uint32_t v[32];
-        tmem_ld_x32(lane_addr + C::TM_FC1, v);
+        uint32_t v[8];
+        tmem_ld_x8(lane_addr + C::TM_FC1 + 8 * qtr, v);
         wait_ld();
         const int64_t t = t0 + row;
         if (t < T) {
-          uint32_t o[16];
+          uint32_t o[4];
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            o[j] = pack_bf16x2((__uint_as_float(v[2 * j]) + sBT[2 * j]) * ta.scale,
-                               (__uint_as_float(v[2 * j + 1]) + sBT[2 * j + 1]) * ta.scale);
-          uint4* dp = reinterpret_cast<uint4*>(ta.dense + t * ta.ldd);
-#pragma unroll
-          for (int q = 0; q < 4; ++q) dp[q] = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+          for (int j = 0; j < 4; ++j)
+            o[j] = pack_bf16x2((__uint_as_float(v[2 * j]) + sBT[8 * qtr + 2 * j]) * ta.scale,
+                               (__uint_as_float(v[2 * j + 1]) + sBT[8 * qtr + 2 * j + 1]) * ta.scale);
+          reinterpret_cast<uint4*>(ta.dense + t * ta.ldd)[qtr] = make_uint4(o[0], o[1], o[2], o[3]);
         }
       }
       fence_before_sync();
     } else {
       // coalesced copy of the finished tile to global memory
+      const int64_t t = t0 + cr;
+      if (t < T) {
 #pragma unroll
-      for (int gi = 0; gi < 2; ++gi) {
-        const int r = (warp + 8 * gi) * 8 + (lane & 7);
-        const int64_t t = t0 + r;
-        const int sw = C::SWZ ? (r & 7) : 0;
-        if (t < T) {
-#pragma unroll
-          for (int j = 0; j < C::NCH / 4; ++j) {
-            const int c = (lane >> 3) + 4 * j;
-            *(reinterpret_cast<uint4*>(Y + t * ldy) + c) = *reinterpret_cast<const uint4*>(sXT + r * C::PITCH + ((c ^ sw) * 16));
-          }
+        for (int j = 0; j < C::NCH / 4; ++j) {
+          const int c = (lane >> 3) + 4 * j;
+          *(reinterpret_cast<uint4*>(Y + t * ldy) + c) = *reinterpret_cast<const uint4*>(sXT + cr * C::PITCH + ((c ^ csw) * 16));
         }
       }
     }
@@ -468,7 +457,7 @@ static int launch_mlp(const void* x, int64_t ldx, void* y, int64_t ldy, const vo
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("rdst_stl_mlp_fwd_bf16: smem attr (%d B): %s", smem, cudaGetErrorString(e)); return RDST_E_CUDA; }
-  e = launch_pdl(k, dim3(grid), dim3(256), (size_t)smem, st, (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy,
+  e = launch_pdl(k, dim3(grid), dim3(MLP_THREADS), (size_t)smem, st, (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy,
                  (const uint8_t*)w1, (const uint8_t*)w2, b1, b2, T, creal, ta, g_mlp_dbg);
   if (e != cudaSuccess) { set_error("rdst_stl_mlp_fwd_bf16: launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   return RDST_OK;
