@@ -144,8 +144,13 @@ __device__ __forceinline__ uint4 pack8(const float* f, const float* bias, int c8
   return make_uint4(o[0], o[1], o[2], o[3]);
 }
 
+constexpr int ATTN_THREADS = 512;     // 16 warps = 4 warpgroups: (head slot s in {0,1}) x (key half p in {0,1})
+
+__device__ __forceinline__ void slot_barrier(int s) { asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory"); }
+__device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(3 + id) : "memory"); }
+
 template <int C_>
-__global__ void __launch_bounds__(256, 1)
+__global__ void __launch_bounds__(ATTN_THREADS, 1)
 stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* __restrict__ Y, int64_t ldy,
                 const uint8_t* __restrict__ wqkv_img, const uint8_t* __restrict__ wproj_img,
                 const float* __restrict__ bqkv, const float* __restrict__ bproj, const float* __restrict__ table,
@@ -153,12 +158,15 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   using K = AttnCfg<C_>;
   constexpr int CP = K::CP, HD = K::HD, NH = K::NH;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[8];          // [0,1] qkv per warpgroup, [2,3] S, [4,5] PV, [6] proj, [7] weights landed
+  __shared__ uint64_t bars[8];          // [0,1] qkv per head slot, [2,3] S, [4,5] PV, [6] proj, [7] weights landed
   __shared__ uint32_t tmem_base_s;
+  __shared__ float sRed[2][2][128];     // [slot][key half][row]: partial row maxima
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int wg = tid >> 7;              // warpgroup: owns heads wg, wg+2, wg+4
+  const int g4 = tid >> 7;              // warpgroup 0..3
+  const int slot = g4 & 1;              // head slot: owns heads slot, slot+2, slot+4
+  const int part = g4 >> 1;             // key half handled in the softmax; q/k (0) or v (1) in the drain
   const int row = tid & 127;
-  uint8_t* sBk = smem + K::OFF_KV + wg * K::KV_BYTES;
+  uint8_t* sBk = smem + K::OFF_KV + slot * K::KV_BYTES;
   uint8_t* sBv = sBk + K::BK_BYTES;
   float* sTab = reinterpret_cast<float*>(smem + K::OFF_TAB);
   float* sBqkv = reinterpret_cast<float*>(smem + K::OFF_BQKV);
@@ -179,11 +187,11 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       bulk_g2s(smem + K::OFF_WPROJ + off, wproj_img + off, min(32768, K::WPROJ_BYTES - off), &bars[7]);
   }
   // K / V images: K-dim / N-dim pads must be (and stay) zero
-  for (int i = tid; i < 2 * K::KV_BYTES / 16; i += 256)
+  for (int i = tid; i < 2 * K::KV_BYTES / 16; i += ATTN_THREADS)
     *reinterpret_cast<uint4*>(smem + K::OFF_KV + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 6 * K::TBL; i += 256) sTab[i] = table[i];
-  for (int i = tid; i < 6 * NH; i += 256) sBqkv[i] = bqkv[i];
-  for (int i = tid; i < CP; i += 256) sBproj[i] = bproj[i];
+  for (int i = tid; i < 6 * K::TBL; i += ATTN_THREADS) sTab[i] = table[i];
+  for (int i = tid; i < 6 * NH; i += ATTN_THREADS) sBqkv[i] = bqkv[i];
+  for (int i = tid; i < CP; i += ATTN_THREADS) sBproj[i] = bproj[i];
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
@@ -192,76 +200,69 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
 
   const int wsel = row >> 6, irow = row & 63, iy = irow >> 3, ix = irow & 7;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const uint32_t tS = K::TM_S + 64 * wg, tQ = K::TM_QKV + 64 * wg;
+  const uint32_t tS = K::TM_S + 64 * slot, tQ = K::TM_QKV + 64 * slot;
   const int rsw = K::SWZ ? (row & 7) : 0;
   const float inv_c = 1.0f / (float)C_;
   const int ntiles = (geo.nwt + 1) / 2;
   uint32_t ph_q = 0, ph_s = 0, ph_o = 0, ph_p = 0;
-  uint64_t* bar_q = &bars[wg];
-  uint64_t* bar_s = &bars[2 + wg];
-  uint64_t* bar_o = &bars[4 + wg];
+  uint64_t* bar_q = &bars[slot];
+  uint64_t* bar_s = &bars[2 + slot];
+  uint64_t* bar_o = &bars[4 + slot];
   // warp-uniform copies (shuffle broadcast) so that MMA descriptors live in uniform registers
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-  const int wg_u = warp_u >> 2;
-  const bool issuer_warp = (warp_u & 3) == 0;          // warp 0 of each warpgroup issues that warpgroup's MMAs
+  const int slot_u = (warp_u >> 2) & 1;
+  const bool issuer_warp = (warp_u & 3) == 0 && (warp_u >> 3) == 0;     // warp 0 / warp 4 issue for slot 0 / slot 1
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-  const uint32_t tS_u = K::TM_S + 64 * wg_u, tQ_u = K::TM_QKV + 64 * wg_u;
+  const uint32_t tS_u = K::TM_S + 64 * slot_u, tQ_u = K::TM_QKV + 64 * slot_u;
   const uint32_t aWqkv = smem_u32(smem + K::OFF_WQKV), aWproj = smem_u32(smem + K::OFF_WPROJ);
-  const uint32_t aBk_u = smem_u32(smem + K::OFF_KV) + wg_u * K::KV_BYTES, aBv_u = aBk_u + K::BK_BYTES;
-  uint64_t* bar_q_u = &bars[wg_u];
-  uint64_t* bar_s_u = &bars[2 + wg_u];
-  uint64_t* bar_o_u = &bars[4 + wg_u];
-  const bool stamper = row == 0;
+  const uint32_t aBk_u = smem_u32(smem + K::OFF_KV) + slot_u * K::KV_BYTES, aBv_u = aBk_u + K::BK_BYTES;
+  uint64_t* bar_q_u = &bars[slot_u];
+  uint64_t* bar_s_u = &bars[2 + slot_u];
+  uint64_t* bar_o_u = &bars[4 + slot_u];
+  // coalesced mapping: warp w owns the 8-row group w (= one window row); lane -> (row, 16-byte chunk lane/8 + 4j)
+  const int cr = warp * 8 + (lane & 7);
+  const int csw = K::SWZ ? (cr & 7) : 0;
 
   int dbg_n = 0;
-  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && stamper;
+  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && row == 0 && part == 0;
 #define RDST_TSTAMP()                                                         \
   do {                                                                        \
-    if (dbg_on && dbg_n < 64) dbg[wg * 64 + dbg_n++] = clock64();             \
+    if (dbg_on && dbg_n < 64) dbg[slot * 64 + dbg_n++] = clock64();           \
   } while (0)
 
-  auto issue_qkv = [&](int h) {      // one elected lane of the warpgroup's issuer warp; h is warp-uniform
+  auto issue_qkv = [&](int h) {      // one elected lane of the slot's issuer warp; h is warp-uniform
     constexpr uint32_t idq = make_idesc_bf16(128, NH, false, false);
     const uint32_t wb = aWqkv + h * (NH * CP * 2);
 #pragma unroll
     for (int ks = 0; ks < CP / 16; ++ks)
-      mma_ts(tmem_u + tQ_u, tmem_u + K::TM_XH + ks * 8, make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128),
-                         idq, ks > 0);
+      mma_ts(tmem_u + tQ_u, tmem_u + K::TM_XH + ks * 8, make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128), idq, ks > 0);
     commit(bar_q_u);
   };
 
   // coalesced-mapping state of the tile in flight and of the prefetched next tile
-  uint4 raw[2][K::NCH / 4];
-  int64_t tok[2];
-  int regv[2];
+  uint4 raw[K::NCH / 4];
+  int64_t tok;
+  int regv;
   auto prefetch = [&](int tile, int nbuf) {
+    const int win = tile * 2 + (warp >> 3);
+    int region = 0; bool edge = false;
+    tok = -1;
+    if (tile < ntiles && win < geo.nwt) tok = win_token(geo, win, warp & 7, lane & 7, region, edge);
+    regv = edge ? region : -1;
+    if (K::ASYNC) {
+      // cp.async straight into the other raw-tile buffer: no staging registers, no scoreboard slots in flight
+      uint8_t* dst = smem + K::OFF_XT + nbuf * K::XT_BYTES + cr * K::PITCH;
 #pragma unroll
-    for (int gi = 0; gi < 2; ++gi) {
-      const int g = warp + 8 * gi;
-      const int win = tile * 2 + (g >> 3);
-      int region = 0; bool edge = false;
-      tok[gi] = -1;
-      if (tile < ntiles && win < geo.nwt) tok[gi] = win_token(geo, win, g & 7, lane & 7, region, edge);
-      regv[gi] = edge ? region : -1;
-      if (K::ASYNC) {
-        // cp.async straight into the other raw-tile buffer: no staging registers, no scoreboard slots in flight
-        const int r = g * 8 + (lane & 7);
-        const int sw = K::SWZ ? (r & 7) : 0;
-        uint8_t* dst = smem + K::OFF_XT + nbuf * K::XT_BYTES + r * K::PITCH;
-#pragma unroll
-        for (int j = 0; j < K::NCH / 4; ++j) {
-          const int c = (lane >> 3) + 4 * j;
-          cp_async16(dst + ((c ^ sw) * 16), reinterpret_cast<const uint4*>(X + (tok[gi] >= 0 ? tok[gi] : 0) * ldx) + c,
-                     tok[gi] >= 0 ? 16u : 0u);
-        }
-      } else {
-#pragma unroll
-        for (int j = 0; j < K::NCH / 4; ++j)
-          raw[gi][j] = tok[gi] >= 0 ? __ldg(reinterpret_cast<const uint4*>(X + tok[gi] * ldx) + (lane >> 3) + 4 * j)
-                                    : make_uint4(0, 0, 0, 0);
+      for (int j = 0; j < K::NCH / 4; ++j) {
+        const int c = (lane >> 3) + 4 * j;
+        cp_async16(dst + ((c ^ csw) * 16), reinterpret_cast<const uint4*>(X + (tok >= 0 ? tok : 0) * ldx) + c, tok >= 0 ? 16u : 0u);
       }
+      cp_async_commit();
+    } else {
+#pragma unroll
+      for (int j = 0; j < K::NCH / 4; ++j)
+        raw[j] = tok >= 0 ? __ldg(reinterpret_cast<const uint4*>(X + tok * ldx) + (lane >> 3) + 4 * j) : make_uint4(0, 0, 0, 0);
     }
-    if (K::ASYNC) cp_async_commit();
   };
   pdl_launch_dependents();       // the next kernel may start its own prologue as SMs free up
   pdl_wait();                    // everything above touched only weights; from here on we read the producer's output
@@ -270,34 +271,26 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
 
   for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= (K::ASYNC ? 1 : 0)) {
     uint8_t* sXT = smem + K::OFF_XT + buf * K::XT_BYTES;
-    // ---------------- P1a: (prefetched) rows of two windows -> raw tile in smem + LayerNorm statistics ----------------
+    // ---------------- P1a: rows of two windows -> raw tile in smem + LayerNorm statistics (coalesced mapping) ---------
     RDST_TSTAMP();   // tile start
-    int64_t tok_cur[2] = {tok[0], tok[1]};
-    const int reg_cur[2] = {regv[0], regv[1]};
+    const int64_t tok_cur = tok;
+    const int reg_cur = regv;
     if (K::ASYNC) {
       cp_async_wait_all();           // this tile's rows have landed (issued one tile ago)
       __syncthreads();
       prefetch(tile + gridDim.x, buf ^ 1);    // the other buffer was drained by the previous tile's copy-out
 #pragma unroll
-      for (int gi = 0; gi < 2; ++gi) {
-        const int r = (warp + 8 * gi) * 8 + (lane & 7);
-        const int sw = K::SWZ ? (r & 7) : 0;
-#pragma unroll
-        for (int j = 0; j < K::NCH / 4; ++j)
-          raw[gi][j] = *reinterpret_cast<const uint4*>(sXT + r * K::PITCH + ((((lane >> 3) + 4 * j) ^ sw) * 16));
-      }
+      for (int j = 0; j < K::NCH / 4; ++j)
+        raw[j] = *reinterpret_cast<const uint4*>(sXT + cr * K::PITCH + ((((lane >> 3) + 4 * j) ^ csw) * 16));
     }
-#pragma unroll
-    for (int gi = 0; gi < 2; ++gi) {
-      const int r = (warp + 8 * gi) * 8 + (lane & 7);
-      const int sw = K::SWZ ? (r & 7) : 0;
-      if ((lane >> 3) == 0) sReg[r] = reg_cur[gi];
+    {
+      if ((lane >> 3) == 0) sReg[cr] = reg_cur;
       float s = 0.f;
 #pragma unroll
       for (int j = 0; j < K::NCH / 4; ++j) {
-        const float2 f0 = up2(raw[gi][j].x), f1 = up2(raw[gi][j].y), f2 = up2(raw[gi][j].z), f3 = up2(raw[gi][j].w);
+        const float2 f0 = up2(raw[j].x), f1 = up2(raw[j].y), f2 = up2(raw[j].z), f3 = up2(raw[j].w);
         s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
-        if (!K::ASYNC) *reinterpret_cast<uint4*>(sXT + r * K::PITCH + ((((lane >> 3) + 4 * j) ^ sw) * 16)) = raw[gi][j];
+        if (!K::ASYNC) *reinterpret_cast<uint4*>(sXT + cr * K::PITCH + ((((lane >> 3) + 4 * j) ^ csw) * 16)) = raw[j];
       }
       s += __shfl_xor_sync(0xffffffffu, s, 8);
       s += __shfl_xor_sync(0xffffffffu, s, 16);
@@ -305,7 +298,7 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       float ss = 0.f;
 #pragma unroll
       for (int j = 0; j < K::NCH / 4; ++j) {
-        const uint32_t w4[4] = {raw[gi][j].x, raw[gi][j].y, raw[gi][j].z, raw[gi][j].w};
+        const uint32_t w4[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float2 f = up2(w4[q]);
@@ -315,18 +308,18 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       ss += __shfl_xor_sync(0xffffffffu, ss, 8);
       ss += __shfl_xor_sync(0xffffffffu, ss, 16);
       ss -= (float)(CP - C_) * mean * mean;
-      if ((lane >> 3) == 0) sStat[r] = make_float2(mean, rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f));
+      if ((lane >> 3) == 0) sStat[cr] = make_float2(mean, rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f));
     }
     __syncthreads();
     RDST_TSTAMP();   // P1a done
-    // ---------------- P1b: thread = token row: normalise half a row -> packed bf16 A operand in TMEM ----------------
+    // ---------------- P1b: thread = (token row, quarter): normalise -> packed bf16 A operand in TMEM ----------------
     {
       const float2 st = sStat[row];
-      constexpr int NC = K::NCH / 2;
+      constexpr int NC = K::NCH / 4;                          // 16-byte chunks per thread (2, 3 or 4)
       uint32_t o[NC * 4];
 #pragma unroll
       for (int cc = 0; cc < NC; ++cc) {
-        const uint4 v = *reinterpret_cast<const uint4*>(sXT + row * K::PITCH + (((wg * NC + cc) ^ rsw) * 16));
+        const uint4 v = *reinterpret_cast<const uint4*>(sXT + row * K::PITCH + (((g4 * NC + cc) ^ rsw) * 16));
         const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -334,12 +327,17 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
           o[cc * 4 + q] = pk2((f.x - st.x) * st.y, (f.y - st.x) * st.y);
         }
       }
+      const uint32_t dst = lane_addr + K::TM_XH + g4 * NC * 4;
 #pragma unroll
-      for (int c0 = 0; c0 < NC * 4; c0 += 8) {
+      for (int c0 = 0; c0 + 8 <= NC * 4; c0 += 8) {
         uint32_t a[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) a[e] = o[c0 + e];
-        tmem_st_x8(lane_addr + K::TM_XH + wg * NC * 4 + c0, a);
+        tmem_st_x8(dst + c0, a);
+      }
+      if ((NC * 4) % 8 != 0) {
+        uint32_t a4[4] = {o[NC * 4 - 4], o[NC * 4 - 3], o[NC * 4 - 2], o[NC * 4 - 1]};
+        tmem_st_x4(dst + NC * 4 - 4, a4);
       }
       wait_st();
     }
@@ -349,35 +347,32 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     if (issuer_warp) {
       if (tile == (int)blockIdx.x) mbar_wait(&bars[7], 0);     // weights have landed (first tile only)
       fence_after_sync();
-      if (elect_one()) issue_qkv(wg_u);
+      if (elect_one()) issue_qkv(slot_u);
       __syncwarp();
     }
-    // shift mask of this row as a 64-bit set of keys that belong to another region (edge windows only)
+    // shift mask of this thread's 32 keys: bit j set = key belongs to another region (edge windows only)
     const int myreg = sReg[row];
-    uint32_t mlo = 0, mhi = 0;
+    uint32_t mbits = 0;
     if (myreg >= 0) {
-      const int* rg = sReg + 64 * wsel;
+      const int* rg = sReg + 64 * wsel + 32 * part;
 #pragma unroll
-      for (int j = 0; j < 32; ++j) {
-        mlo |= (rg[j] != myreg) ? (1u << j) : 0u;
-        mhi |= (rg[32 + j] != myreg) ? (1u << j) : 0u;
-      }
+      for (int j = 0; j < 32; ++j) mbits |= (rg[j] != myreg) ? (1u << j) : 0u;
     }
 
-    // ---------------- heads of this warpgroup ----------------
+    // ---------------- heads of this slot ----------------
 #pragma unroll
     for (int i = 0; i < 3; ++i) {
-      const int h = wg + 2 * i;
+      const int h = slot + 2 * i;
       RDST_TSTAMP();   // before qkv wait
       mbar_wait(bar_q, ph_q & 1); ph_q++;
       fence_after_sync();
       {
-        constexpr int NC = (3 * HD + 7) / 8 * 8;
-        float f[NC];
-        tmem_load_cols<NC>(lane_addr + tQ, f);
         const float* bq = sBqkv + h * NH;
-        // Q: packed bf16 pairs back into the (now consumed) accumulator columns -> A operand of S straight from TMEM
-        {
+        if (part == 0) {
+          // q -> packed bf16 back into the consumed accumulator columns (A operand of S), k -> K-major image
+          constexpr int NC = (2 * HD + 7) / 8 * 8;
+          float f[NC];
+          tmem_load_cols<NC>(lane_addr + tQ, f);
           uint32_t qp[K::HDP / 2];
 #pragma unroll
           for (int e = 0; e < K::HDP / 2; ++e) {
@@ -391,19 +386,25 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
             for (int e = 0; e < 8; ++e) a[e] = qp[c0 + e];
             tmem_st_x8(lane_addr + tQ + c0, a);
           }
+#pragma unroll
+          for (int c8 = 0; c8 < (HD + 7) / 8; ++c8)
+            *reinterpret_cast<uint4*>(sBk + c8 * 2048 + row * 16) = pack8<HD, HD, false>(f, bq, c8);
+          wait_st();
+        } else {
+          // v (+ ones column) -> MN-major fp16 image; the v columns start at 2*HD: load an 8-aligned superset
+          constexpr int C0 = (2 * HD) / 8 * 8;
+          constexpr int NC = (3 * HD - C0 + 7) / 8 * 8;
+          float f[NC];
+          tmem_load_cols<NC>(lane_addr + tQ + C0, f);
+          if (i > 0) mbar_wait(bar_o, (ph_o - 1) & 1);        // PV of the previous head has finished reading V
+#pragma unroll
+          for (int c8 = 0; c8 < (HD + 8) / 8; ++c8)
+            *reinterpret_cast<uint4*>(sBv + c8 * 2048 + row * 16) = pack8<2 * HD - C0, HD, true, true>(f, bq + C0, c8);
         }
-#pragma unroll
-        for (int c8 = 0; c8 < (HD + 7) / 8; ++c8)
-          *reinterpret_cast<uint4*>(sBk + c8 * 2048 + row * 16) = pack8<HD, HD, false>(f, bq, c8);
-        if (i > 0) mbar_wait(bar_o, (ph_o - 1) & 1);          // PV of the previous head has finished reading V
-#pragma unroll
-        for (int c8 = 0; c8 < (HD + 8) / 8; ++c8)      // covers column HD (the ones column)
-          *reinterpret_cast<uint4*>(sBv + c8 * 2048 + row * 16) = pack8<2 * HD, HD, true, true>(f, bq, c8);   // MN-major, fp16
-        wait_st();
       }
       fence_proxy_async();
       fence_before_sync();
-      wg_barrier(wg);
+      slot_barrier(slot);
       RDST_TSTAMP();   // drained
       if (issuer_warp) {
         fence_after_sync();
@@ -417,53 +418,51 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
                                  ids, ks > 0, w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu,
                                  w ? 0u : 0xFFFFFFFFu);
           commit(bar_s_u);
-          if (i < 2) issue_qkv(wg_u + 2 * i + 2);
+          if (i < 2) issue_qkv(slot_u + 2 * i + 2);
         }
         __syncwarp();
       }
-      // ---- softmax over the 64 keys of this row's window ----
+      // ---- softmax: this thread owns 32 of the 64 keys of its row; the row maximum is exchanged with its partner ----
       mbar_wait(bar_s, ph_s & 1); ph_s++;
       fence_after_sync();
       RDST_TSTAMP();   // S ready
       {
-        uint32_t v[64];
-        {
-          uint32_t a[32], b[32];
-          tmem_ld_x32(lane_addr + tS, a);
-          tmem_ld_x32(lane_addr + tS + 32, b);
-          wait_ld();
+        uint32_t v[32];
+        tmem_ld_x32(lane_addr + tS + 32 * part, v);
+        wait_ld();
+        const float* tb = sTab + h * K::TBL + (iy + 7 - 4 * part) * 24 + ix + 7;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) { v[j] = a[j]; v[32 + j] = b[j]; }
-        }
-        const float* tb = sTab + h * K::TBL + (iy + 7) * 24 + ix + 7;
-#pragma unroll
-        for (int j = 0; j < 64; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + tb[-((j >> 3) * 24 + (j & 7))]);
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + tb[-((j >> 3) * 24 + (j & 7))]);
         if (myreg >= 0) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j)
-            if ((j < 32 ? mlo : mhi) & (1u << (j & 31))) v[j] = __float_as_uint(__uint_as_float(v[j]) + mask_val);
+          for (int j = 0; j < 32; ++j)
+            if (mbits & (1u << j)) v[j] = __float_as_uint(__uint_as_float(v[j]) + mask_val);
         }
         float m4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
 #pragma unroll
-        for (int j = 4; j < 64; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
-        const float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        for (int j = 4; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
+        float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+        sRed[slot][part][row] = mx;
+        pair_barrier(slot * 4 + (warp & 3));
+        mx = fmaxf(mx, sRed[slot][1 - part][row]);
         RDST_TSTAMP();   // bias + max
-        // exp2 on packed fp16 pairs: one MUFU op per two probabilities; P stays fp16 (V is fp16 as well)
-        uint32_t o[32];
+        // exp2 on packed fp16 pairs: one MUFU op per two probabilities; P stays fp16 (V is fp16 as well); the row sum
+        // comes out of the PV MMA (ones column of V)
+        uint32_t o[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j)
+        for (int j = 0; j < 16; ++j)
           o[j] = ex2_h2(pk2h(__uint_as_float(v[2 * j]) - mx, __uint_as_float(v[2 * j + 1]) - mx));
-        tmem_st_x32(lane_addr + tS, o);                     // P overwrites the first 32 columns of S
+        tmem_st_x16(lane_addr + tS + 16 * part, o);         // P overwrites the first 32 columns of S (16 per key half)
         wait_st();
       }
       RDST_TSTAMP();   // softmax done
       fence_before_sync();
-      wg_barrier(wg);
+      slot_barrier(slot);
       if (issuer_warp) {
         fence_after_sync();
         if (elect_one()) {
           constexpr uint32_t idv = make_idesc_f16(128, K::HDV, false, true);
-          const uint32_t dO = tmem_u + K::TM_O + (wg_u + 2 * i) * K::HDV;
+          const uint32_t dO = tmem_u + K::TM_O + (slot_u + 2 * i) * K::HDV;
 #pragma unroll
           for (int w = 0; w < 2; ++w)
 #pragma unroll
@@ -476,51 +475,46 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       }
       ph_o++;
     }
-    // ---------------- O / rowsum -> packed bf16 A operand of proj in TMEM (each warpgroup: its own three heads) -------
+    // ---------------- O / rowsum -> packed bf16 A operand of proj in TMEM ----------------
     RDST_TSTAMP();   // heads issued
     mbar_wait(bar_o, (ph_o - 1) & 1);
     fence_after_sync();
-    __syncthreads();                    // both warpgroups are past their last qkv MMA: the normalised input is dead
-    constexpr int NCO = (HD + 8) / 8 * 8;      // head_dim values + the row-sum column
-    float fo[3][NCO];
+    __syncthreads();                    // both slots are past their last qkv MMA: the normalised input is dead
+    {
+      // the three heads of a slot are split between its two warpgroups: part 0 takes two heads, part 1 one
+      constexpr int NCO = (HD + 8) / 8 * 8;      // head_dim values + the row-sum column
 #pragma unroll
-    for (int i = 0; i < 3; ++i)
+      for (int ii = 0; ii < 2; ++ii) {
+        const int i = part == 0 ? ii : 2;
+        if (part == 1 && ii == 1) break;
+        const int h = slot + 2 * i;
+        float f[NCO];
+        tmem_load_cols<NCO>(lane_addr + K::TM_O + h * K::HDV, f);
+        const float inv = 1.0f / f[HD];             // softmax row sum, accumulated by the PV MMA (ones column of V)
+        if (K::HDO == 16) {
+          uint32_t a[8];
 #pragma unroll
-      for (int c = 0; c < NCO; c += 8) {
-        uint32_t t8[8];
-        tmem_ld_x8(lane_addr + K::TM_O + (wg + 2 * i) * K::HDV + c, t8);
+          for (int e = 0; e < 8; ++e) {
+            const int d0 = 2 * e, d1 = d0 + 1;
+            a[e] = pk2(d0 < HD ? f[d0] * inv : 0.f, d1 < HD ? f[d1] * inv : 0.f);
+          }
+          tmem_st_x8(lane_addr + K::TM_XH + 8 * h, a);
+        } else {   // HDO == 20: 10 columns per head
+          uint32_t a[8], b[2];
 #pragma unroll
-        for (int e = 0; e < 8; ++e) fo[i][c + e] = __uint_as_float(t8[e]);
-      }
-    wait_ld();
-#pragma unroll
-    for (int i = 0; i < 3; ++i) {
-      const int h = wg + 2 * i;
-      const float* f = fo[i];
-      const float inv = 1.0f / f[HD];             // softmax row sum, accumulated by the PV MMA (ones column of V)
-      if (K::HDO == 16) {
-        uint32_t a[8];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          const int d0 = 2 * e, d1 = d0 + 1;
-          a[e] = pk2(d0 < HD ? f[d0] * inv : 0.f, d1 < HD ? f[d1] * inv : 0.f);
+          for (int e = 0; e < 8; ++e) a[e] = pk2(f[2 * e] * inv, f[2 * e + 1] * inv);
+          b[0] = pk2(f[16] * inv, f[17] * inv);
+          b[1] = pk2(f[18] * inv, f[19] * inv);
+          tmem_st_x8(lane_addr + K::TM_XH + 10 * h, a);
+          tmem_st_x2(lane_addr + K::TM_XH + 10 * h + 8, b);
         }
-        tmem_st_x8(lane_addr + K::TM_XH + 8 * h, a);
-      } else {   // HDO == 20: 10 columns per head
-        uint32_t a[8], b[2];
-#pragma unroll
-        for (int e = 0; e < 8; ++e) a[e] = pk2(f[2 * e] * inv, f[2 * e + 1] * inv);
-        b[0] = pk2(f[16] * inv, f[17] * inv);
-        b[1] = pk2(f[18] * inv, f[19] * inv);
-        tmem_st_x8(lane_addr + K::TM_XH + 10 * h, a);
-        tmem_st_x2(lane_addr + K::TM_XH + 10 * h + 8, b);
       }
+      if (K::HDO == 20 && g4 == 3) {      // K pad of proj (elements 120..127): must be finite; weights there are zero
+        uint32_t zz[4] = {0, 0, 0, 0};
+        tmem_st_x4(lane_addr + K::TM_XH + 60, zz);
+      }
+      wait_st();
     }
-    if (K::HDO == 20 && wg == 0) {      // K pad of proj (elements 120..127): must be finite; weights there are zero
-      uint32_t zz[4] = {0, 0, 0, 0};
-      tmem_st_x4(lane_addr + K::TM_XH + 60, zz);
-    }
-    wait_st();
     fence_before_sync();
     __syncthreads();
     if (warp_u == 0) {
@@ -529,8 +523,7 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
         constexpr uint32_t idp = make_idesc_bf16(128, CP, false, false);
 #pragma unroll
         for (int ks = 0; ks < K::KPROJ / 16; ++ks)
-          mma_ts(tmem_u + K::TM_PROJ, tmem_u + K::TM_XH + ks * 8,
-                             make_smem_desc(aWproj + ks * 2 * (CP * 16), CP * 16, 128), idp, ks > 0);
+          mma_ts(tmem_u + K::TM_PROJ, tmem_u + K::TM_XH + ks * 8, make_smem_desc(aWproj + ks * 2 * (CP * 16), CP * 16, 128), idp, ks > 0);
         commit(&bars[6]);
       }
       __syncwarp();
@@ -542,8 +535,8 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     fence_after_sync();
     // ---------------- proj epilogue in the row mapping: y = proj + bias + x, in place in the raw tile ----------------
     {
-      constexpr int NC = CP / 2;
-      const int cb = wg * NC;
+      constexpr int NC = CP / 4;                               // columns per thread (16, 24 or 32)
+      const int cb = g4 * NC;
       uint32_t acc[NC];
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 8) {
@@ -572,16 +565,11 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     fence_before_sync();
     __syncthreads();
     RDST_TSTAMP();   // y staged
+    if (tok_cur >= 0) {
 #pragma unroll
-    for (int gi = 0; gi < 2; ++gi) {
-      const int r = (warp + 8 * gi) * 8 + (lane & 7);
-      const int sw = K::SWZ ? (r & 7) : 0;
-      if (tok_cur[gi] >= 0) {
-#pragma unroll
-        for (int j = 0; j < K::NCH / 4; ++j) {
-          const int c = (lane >> 3) + 4 * j;
-          *(reinterpret_cast<uint4*>(Y + tok_cur[gi] * ldy) + c) = *reinterpret_cast<const uint4*>(sXT + r * K::PITCH + ((c ^ sw) * 16));
-        }
+      for (int j = 0; j < K::NCH / 4; ++j) {
+        const int c = (lane >> 3) + 4 * j;
+        *(reinterpret_cast<uint4*>(Y + tok_cur * ldy) + c) = *reinterpret_cast<const uint4*>(sXT + cr * K::PITCH + ((c ^ csw) * 16));
       }
     }
     __syncthreads();
@@ -608,7 +596,7 @@ static int launch_attn(const void* x, int64_t ldx, void* y, int64_t ldy, const v
   auto k = stl_attn_kernel<C_>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) { set_error("rdst_stl_attn_fwd_bf16: smem attr (%d B): %s", K::SMEM, cudaGetErrorString(e)); return RDST_E_CUDA; }
-  e = launch_pdl(k, dim3(grid), dim3(256), (size_t)K::SMEM, st, (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy,
+  e = launch_pdl(k, dim3(grid), dim3(ATTN_THREADS), (size_t)K::SMEM, st, (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy,
                  (const uint8_t*)wqkv, (const uint8_t*)wproj, bqkv, bproj, table, g, -100.0f * 1.4426950408889634f, g_attn_dbg);
   if (e != cudaSuccess) { set_error("rdst_stl_attn_fwd_bf16: launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   return RDST_OK;
