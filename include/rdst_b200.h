@@ -171,8 +171,9 @@ int rdst_stl_mlp_tail_fwd_bf16(const void* x, int64_t ldx, const void* w1img, co
  *              (NH = 32/48/64), LN gamma, head_dim^-0.5 and log2(e) folded into the q rows
  *   bqkv     : [6][NH] fp32 (LN beta folded);  wproj_img : [KPROJ/8][Cp][8] bf16 with K index = head*HDO + d
  *              (HDO = 16/16/20, KPROJ = 96/96/128);  bproj : [Cp];
- *   table    : [6][15][24] fp32, table[h][dy+7][dx+7] = relative_position_bias_table[(dy+7)*15+(dx+7)][h] * log2(e)
- *              (row pitch 24 keeps the per-row lookups free of shared-memory bank conflicts)
+ *   table    : [6][15][24] 32-bit words, each a packed fp16 pair (t[h][dy+7][dx+7], t[h][dy+7][dx+6]) with
+ *              t = relative_position_bias_table[(dy+7)*15+(dx+7)][h] * log2(e)  (the softmax runs on packed fp16
+ *              pairs; row pitch 24 keeps the per-row lookups free of shared-memory bank conflicts)
  * Replaces swin_transformer_sr.py:239-271 (block) and :110-141 (WindowAttention).  X and Y must not alias. */
 int rdst_stl_attn_fwd_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const void* wqkv_img,
                            const void* wproj_img, const float* bqkv, const float* bproj, const float* table,

@@ -168,7 +168,8 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   const int row = tid & 127;
   uint8_t* sBk = smem + K::OFF_KV + slot * K::KV_BYTES;
   uint8_t* sBv = sBk + K::BK_BYTES;
-  float* sTab = reinterpret_cast<float*>(smem + K::OFF_TAB);
+  const uint32_t* sTab2 = reinterpret_cast<const uint32_t*>(smem + K::OFF_TAB);    // packed fp16 pairs (t[idx], t[idx-1])
+  uint32_t* sTabW = reinterpret_cast<uint32_t*>(smem + K::OFF_TAB);
   float* sBqkv = reinterpret_cast<float*>(smem + K::OFF_BQKV);
   float* sBproj = reinterpret_cast<float*>(smem + K::OFF_BPROJ);
   int* sReg = reinterpret_cast<int*>(smem + K::OFF_SREG);
@@ -189,7 +190,7 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   // K / V images: K-dim / N-dim pads must be (and stay) zero
   for (int i = tid; i < 2 * K::KV_BYTES / 16; i += ATTN_THREADS)
     *reinterpret_cast<uint4*>(smem + K::OFF_KV + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
-  for (int i = tid; i < 6 * K::TBL; i += ATTN_THREADS) sTab[i] = table[i];
+  for (int i = tid; i < 6 * K::TBL; i += ATTN_THREADS) sTabW[i] = reinterpret_cast<const uint32_t*>(table)[i];
   for (int i = tid; i < 6 * NH; i += ATTN_THREADS) sBqkv[i] = bqkv[i];
   for (int i = tid; i < CP; i += ATTN_THREADS) sBproj[i] = bproj[i];
   fence_proxy_async();
@@ -430,28 +431,41 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
         uint32_t v[32];
         tmem_ld_x32(lane_addr + tS + 32 * part, v);
         wait_ld();
-        const float* tb = sTab + h * K::TBL + (iy + 7 - 4 * part) * 24 + ix + 7;
+        // the whole softmax runs on packed fp16 pairs: logits -> half2, + bias pair (one 32-bit table read per two keys),
+        // row maximum, exp2: two keys per instruction throughout
+        const uint32_t* tb = sTab2 + h * K::TBL + (iy + 7 - 4 * part) * 24 + ix + 7;
+        __half2 hv[16];
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + tb[-((j >> 3) * 24 + (j & 7))]);
-        if (myreg >= 0) {
-#pragma unroll
-          for (int j = 0; j < 32; ++j)
-            if (mbits & (1u << j)) v[j] = __float_as_uint(__uint_as_float(v[j]) + mask_val);
+        for (int j = 0; j < 16; ++j) {
+          const uint32_t bp = tb[-(((2 * j) >> 3) * 24 + ((2 * j) & 7))];
+          hv[j] = __hadd2(__floats2half2_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])),
+                          *reinterpret_cast<const __half2*>(&bp));
         }
-        float m4[4] = {__uint_as_float(v[0]), __uint_as_float(v[1]), __uint_as_float(v[2]), __uint_as_float(v[3])};
+        if (myreg >= 0) {
+          const __half hm = __float2half_rn(mask_val);
+          const __half hz = __float2half_rn(0.f);
 #pragma unroll
-        for (int j = 4; j < 32; ++j) m4[j & 3] = fmaxf(m4[j & 3], __uint_as_float(v[j]));
-        float mx = fmaxf(fmaxf(m4[0], m4[1]), fmaxf(m4[2], m4[3]));
+          for (int j = 0; j < 16; ++j)
+            if ((mbits >> (2 * j)) & 3u)
+              hv[j] = __hadd2(hv[j], __halves2half2((mbits >> (2 * j)) & 1u ? hm : hz, (mbits >> (2 * j + 1)) & 1u ? hm : hz));
+        }
+        __half2 m2[4] = {hv[0], hv[1], hv[2], hv[3]};
+#pragma unroll
+        for (int j = 4; j < 16; ++j) m2[j & 3] = __hmax2(m2[j & 3], hv[j]);
+        const __half2 mm = __hmax2(__hmax2(m2[0], m2[1]), __hmax2(m2[2], m2[3]));
+        float mx = fmaxf(__low2float(mm), __high2float(mm));
         sRed[slot][part][row] = mx;
         pair_barrier(slot * 4 + (warp & 3));
         mx = fmaxf(mx, sRed[slot][1 - part][row]);
         RDST_TSTAMP();   // bias + max
-        // exp2 on packed fp16 pairs: one MUFU op per two probabilities; P stays fp16 (V is fp16 as well); the row sum
-        // comes out of the PV MMA (ones column of V)
+        // P stays fp16 (V is fp16 as well); the row sum comes out of the PV MMA (ones column of V)
+        const __half2 mx2 = __float2half2_rn(mx);
         uint32_t o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          o[j] = ex2_h2(pk2h(__uint_as_float(v[2 * j]) - mx, __uint_as_float(v[2 * j + 1]) - mx));
+        for (int j = 0; j < 16; ++j) {
+          const __half2 d = __hsub2(hv[j], mx2);
+          o[j] = ex2_h2(*reinterpret_cast<const uint32_t*>(&d));
+        }
         tmem_st_x16(lane_addr + tS + 16 * part, o);         // P overwrites the first 32 columns of S (16 per key half)
         wait_st();
       }

@@ -187,8 +187,14 @@ def pack_attn_tc(wqkv, bqkv, wproj, bproj, table, c):
     wp = wproj.new_zeros(cp, kproj)
     for h in range(HEADS):
         wp[:, h * hdo:h * hdo + hd] = wproj[:, h * hd:(h + 1) * hd]
-    tab = table.new_zeros(HEADS, 15, 24)
-    tab[:, :, :15] = (table.t() * LOG2E).reshape(HEADS, 15, 15)
+    # relative-position bias, pre-scaled by log2(e), as packed fp16 pairs (t[dy][dx], t[dy][dx-1]): the kernel adds the
+    # bias of two neighbouring keys with one 32-bit shared-memory read (row pitch 24 -> bank-conflict free)
+    t15 = (table.t() * LOG2E).reshape(HEADS, 15, 15)
+    lo = table.new_zeros(HEADS, 15, 24)
+    hi = table.new_zeros(HEADS, 15, 24)
+    lo[:, :, :15] = t15
+    hi[:, :, 1:15] = t15[:, :, :14]
+    tab = torch.stack([lo, hi], dim=-1).to(torch.float16).contiguous().view(torch.int32).reshape(HEADS, 15, 24)
     return dict(wqkv_img=torch.cat(imgs).contiguous(), bqkv_tc=torch.cat(biases).contiguous(),
                 wproj_img=kmajor_image(wp), table_tc=tab.contiguous())
 
