@@ -205,6 +205,13 @@ int rdst_debug_mlp_timing(void* device_buffer_128_u64);     /* same for rdst_stl
 int rdst_umma_selftest(const void* a_bf16, const void* b_bf16, float* d, int N, int K, int b_mn_major,
                        int m64, void* stream);
 
+/* Self-test of the TMA plumbing: loads the 8x8 window whose shifted-frame origin is (hs0, ws0) of image b from the
+ * token-major activation x ([B][H][W][ldx] bf16, C channels) as four 4x4-token boxes per 64-channel panel
+ * (SWIZZLE_128B), dumps the raw shared-memory image (ceil(C/64) * 8192 bytes) and stores the tile to the same
+ * window of y.  Used by tests/ only. */
+int rdst_tma_selftest(const void* x, int64_t ldx, void* y, int64_t ldy, int B, int H, int W, int C, int shift, int b,
+                      int hs0, int ws0, void* dump, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

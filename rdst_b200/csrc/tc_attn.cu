@@ -21,6 +21,7 @@
 // The (nW,6,64,64) score tensor of the reference never exists outside TMEM.
 #include "common.cuh"
 #include "umma.cuh"
+#include "tma.cuh"
 
 namespace rdst {
 using namespace umma;
@@ -53,11 +54,14 @@ struct AttnCfg {
   static constexpr int TBL = 15 * 24;                       // bias table per head, row pitch 24 (bank-conflict free)
   static constexpr int WQKV_BYTES = 6 * NH * CP * 2;
   static constexpr int WPROJ_BYTES = CP * KPROJ * 2;
-  static constexpr bool SWZ = (NCH == 8 || NCH == 16);      // raw tile: XOR-swizzled rows, else padded rows
-  static constexpr int PITCH = SWZ ? CP * 2 : CP * 2 + 16;
-  static constexpr int XT_BYTES = 128 * PITCH;
-  static constexpr bool ASYNC = (C != 120);                 // C=60/90: a second raw tile fits -> cp.async prefetch; C=120: registers
-  static constexpr int NXT = ASYNC ? 2 : 1;
+  // raw tile: NP panels of 64 channels, each [128 token rows][128 B] in the TMA SWIZZLE_128B pattern
+  static constexpr int NP = CP > 64 ? 2 : 1;
+  static constexpr int PANEL = 128 * 128;
+  static constexpr int XT_BYTES = NP * PANEL;
+  // C=60/90: two raw tiles (TMA lands tile n+1 in the other one).  C=120: no room for a second tile -- the next
+  // tile lands in the K/V image area, which is dead from the last PV MMA of a tile to the first drain of the next
+  static constexpr bool DBUF = (C != 120);
+  static constexpr int NXT = DBUF ? 2 : 1;
   static constexpr int BK_BYTES = 128 * HDP * 2;            // K image (K-major)
   static constexpr int BV_BYTES = 128 * HDV * 2;            // V image (MN-major, fp16)
   static constexpr int KV_BYTES = BK_BYTES + BV_BYTES;      // per warpgroup
@@ -70,7 +74,7 @@ struct AttnCfg {
   static constexpr int OFF_BPROJ = OFF_BQKV + 6 * NH * 4;
   static constexpr int OFF_SREG = OFF_BPROJ + CP * 4;
   static constexpr int OFF_STAT = OFF_SREG + 128 * 4;
-  static constexpr int SMEM = OFF_STAT + 128 * 8;
+  static constexpr int SMEM = OFF_STAT + 4 * 128 * 8;       // LayerNorm partial (sum, sum of squares) per (quarter, row)
   // TMEM columns.  Every A operand lives in TMEM (packed 16-bit pairs, lane = token row); shared memory only
   // feeds the B operands (weights, K, V).
   static constexpr int TM_QKV = 0;      // per-warpgroup qkv accumulator [0,64),[64,128); its first HDP/2 columns are
@@ -80,8 +84,14 @@ struct AttnCfg {
   static constexpr int TM_XH = 448;     // normalised input (A of qkv), later normalised O (A of proj): <= 64 columns
   static constexpr int TM_PROJ = 0;     // proj accumulator [0,CP) (qkv accumulators are dead by then)
   static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(OFF_XT % 1024 == 0 && OFF_KV % 1024 == 0 && (DBUF || 2 * KV_BYTES >= XT_BYTES), "raw tile placement");
   static_assert(TM_O + 6 * HDV <= TM_XH && CP / 2 <= 64 && KPROJ / 2 <= 64, "TMEM budget");
 };
+
+// byte offset of 16-byte chunk c (8 channels) of token row `row` inside a raw tile (TMA SWIZZLE_128B panels)
+__device__ __forceinline__ uint32_t xt_off(int row, int c) {
+  return (uint32_t)((c >> 3) * (128 * 128) + row * 128 + (((c & 7) ^ (row & 7)) << 4));
+}
 
 // load NCOL (multiple of 8) consecutive accumulator columns of this thread's TMEM lane
 template <int NCOL>
@@ -101,19 +111,18 @@ struct WinGeom {
   int nwt;             // total windows (B * nw_img), < 2^31
 };
 
-// token index (in the un-shifted, raster-ordered activation) of position (iy,ix) of window `win`; region id for the mask
-__device__ __forceinline__ int64_t win_token(const WinGeom& g, int win, int iy, int ix, int& region, bool& edge) {
-  const int b = win / g.nw_img;
-  const int wl = win - b * g.nw_img;
-  const int wy = wl / g.nwx, wx = wl - wy * g.nwx;
+// Rows of a window are kept in TMA box order: four 4x4-token boxes q = 2*(iy/4) + ix/4, 16 rows each.
+__device__ __forceinline__ int row_iy(int irow) { return ((irow >> 5) & 1) * 4 + ((irow >> 2) & 3); }
+__device__ __forceinline__ int row_ix(int irow) { return ((irow >> 4) & 1) * 4 + (irow & 3); }
+
+// shift-mask region (img_mask value of calculate_mask, :321-341) of position (iy,ix) of window (wy,wx), or -1 when the
+// window does not touch the wrapped border (no mask needed)
+__device__ __forceinline__ int win_region(const WinGeom& g, int wy, int wx, int iy, int ix) {
+  if (!(g.shift > 0 && (wy == g.H / 8 - 1 || wx == g.nwx - 1))) return -1;
   const int hs = wy * 8 + iy, ws = wx * 8 + ix;             // coordinates on the shifted frame
-  int hh = hs + g.shift; if (hh >= g.H) hh -= g.H;          // shifted[h'] = x[(h'+s) mod H]   (:245)
-  int ww = ws + g.shift; if (ww >= g.W) ww -= g.W;
   const int rh = hs < g.H - 8 ? 0 : (hs < g.H - g.shift ? 1 : 2);
   const int rw = ws < g.W - 8 ? 0 : (ws < g.W - g.shift ? 1 : 2);
-  region = rh * 3 + rw;
-  edge = g.shift > 0 && (wy == g.H / 8 - 1 || wx == g.nwx - 1);
-  return ((int64_t)b * g.H + hh) * g.W + ww;
+  return rh * 3 + rw;
 }
 
 __device__ __forceinline__ void wg_barrier(int g) { asm volatile("bar.sync %0, 128;" ::"r"(1 + g) : "memory"); }
@@ -151,7 +160,7 @@ __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0
 
 template <int C_>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
-stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* __restrict__ Y, int64_t ldy,
+stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                 const uint8_t* __restrict__ wqkv_img, const uint8_t* __restrict__ wproj_img,
                 const float* __restrict__ bqkv, const float* __restrict__ bproj, const float* __restrict__ table,
                 WinGeom geo, float mask_val, unsigned long long* __restrict__ dbg) {
@@ -159,6 +168,7 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   constexpr int CP = K::CP, HD = K::HD, NH = K::NH;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[8];          // [0,1] qkv per head slot, [2,3] S, [4,5] PV, [6] proj, [7] weights landed
+  __shared__ uint64_t xbar[2];          // raw tile landed (one per landing buffer)
   __shared__ uint32_t tmem_base_s;
   __shared__ float sRed[2][2][128];     // [slot][key half][row]: partial row maxima
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -173,11 +183,13 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   float* sBqkv = reinterpret_cast<float*>(smem + K::OFF_BQKV);
   float* sBproj = reinterpret_cast<float*>(smem + K::OFF_BPROJ);
   int* sReg = reinterpret_cast<int*>(smem + K::OFF_SREG);
-  float2* sStat = reinterpret_cast<float2*>(smem + K::OFF_STAT);
+  float2* sPart = reinterpret_cast<float2*>(smem + K::OFF_STAT);
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) {
     for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&xbar[0], 1);
+    mbar_init(&xbar[1], 1);
     fence_mbar_init();
     // resident weights arrive by bulk async copies (UBLKCP) that overlap the rest of the prologue and the first
     // tile's load + LayerNorm; the MMA issuers wait on bars[7] once, right before their first tcgen05.mma
@@ -199,10 +211,9 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
 
-  const int wsel = row >> 6, irow = row & 63, iy = irow >> 3, ix = irow & 7;
+  const int wsel = row >> 6, irow = row & 63, iy = row_iy(irow), ix = row_ix(irow);
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const uint32_t tS = K::TM_S + 64 * slot, tQ = K::TM_QKV + 64 * slot;
-  const int rsw = K::SWZ ? (row & 7) : 0;
   const float inv_c = 1.0f / (float)C_;
   const int ntiles = (geo.nwt + 1) / 2;
   uint32_t ph_q = 0, ph_s = 0, ph_o = 0, ph_p = 0;
@@ -222,7 +233,6 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
   uint64_t* bar_o_u = &bars[4 + slot_u];
   // coalesced mapping: warp w owns the 8-row group w (= one window row); lane -> (row, 16-byte chunk lane/8 + 4j)
   const int cr = warp * 8 + (lane & 7);
-  const int csw = K::SWZ ? (cr & 7) : 0;
 
   int dbg_n = 0;
   const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && row == 0 && part == 0;
@@ -240,107 +250,134 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     commit(bar_q_u);
   };
 
-  // coalesced-mapping state of the tile in flight and of the prefetched next tile
-  uint4 raw[K::NCH / 4];
-  int64_t tok;
-  int regv;
-  auto prefetch = [&](int tile, int nbuf) {
-    const int win = tile * 2 + (warp >> 3);
-    int region = 0; bool edge = false;
-    tok = -1;
-    if (tile < ntiles && win < geo.nwt) tok = win_token(geo, win, warp & 7, lane & 7, region, edge);
-    regv = edge ? region : -1;
-    if (K::ASYNC) {
-      // cp.async straight into the other raw-tile buffer: no staging registers, no scoreboard slots in flight
-      uint8_t* dst = smem + K::OFF_XT + nbuf * K::XT_BYTES + cr * K::PITCH;
+  // one thread: TMA loads of both windows of `tile` (4 boxes x NP panels each) into landing buffer `dst`; a window
+  // beyond the end (odd window count) is fetched from image index B, i.e. out of range -> zero fill
+  auto load_tile = [&](int tile, uint8_t* dst, uint64_t* bar) {
+    if (tile >= ntiles) return;
+    mbar_arrive_expect_tx(bar, K::XT_BYTES);
 #pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j) {
-        const int c = (lane >> 3) + 4 * j;
-        cp_async16(dst + ((c ^ csw) * 16), reinterpret_cast<const uint4*>(X + (tok >= 0 ? tok : 0) * ldx) + c, tok >= 0 ? 16u : 0u);
+    for (int w = 0; w < 2; ++w) {
+      const int win = tile * 2 + w;
+      const int b = win < geo.nwt ? win / geo.nw_img : geo.nwt / geo.nw_img;
+      const int wl = win < geo.nwt ? win - b * geo.nw_img : 0;
+      const int wy = wl / geo.nwx, wx = wl - wy * geo.nwx;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int hh = wy * 8 + 4 * (q >> 1) + geo.shift; if (hh >= geo.H) hh -= geo.H;   // shifted[h'] = x[(h'+s) mod H]  (:245)
+        int ww = wx * 8 + 4 * (q & 1) + geo.shift; if (ww >= geo.W) ww -= geo.W;
+#pragma unroll
+        for (int pnl = 0; pnl < K::NP; ++pnl)
+          tma::load_4d(dst + pnl * K::PANEL + (w * 64 + q * 16) * 128, &mapX, pnl * 64, ww, hh, b, bar);
       }
-      cp_async_commit();
-    } else {
-#pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j)
-        raw[j] = tok >= 0 ? __ldg(reinterpret_cast<const uint4*>(X + tok * ldx) + (lane >> 3) + 4 * j) : make_uint4(0, 0, 0, 0);
     }
   };
+  auto store_tile = [&](int tile, const uint8_t* src) {
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const int win = tile * 2 + w;
+      if (win >= geo.nwt) break;
+      const int b = win / geo.nw_img;
+      const int wl = win - b * geo.nw_img;
+      const int wy = wl / geo.nwx, wx = wl - wy * geo.nwx;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        int hh = wy * 8 + 4 * (q >> 1) + geo.shift; if (hh >= geo.H) hh -= geo.H;
+        int ww = wx * 8 + 4 * (q & 1) + geo.shift; if (ww >= geo.W) ww -= geo.W;
+#pragma unroll
+        for (int pnl = 0; pnl < K::NP; ++pnl)
+          tma::store_4d(&mapY, pnl * 64, ww, hh, b, src + pnl * K::PANEL + (w * 64 + q * 16) * 128);
+      }
+    }
+    bulk_commit();
+  };
+  uint8_t* const sLand = smem + K::OFF_KV;         // C=120 landing zone
   pdl_launch_dependents();       // the next kernel may start its own prologue as SMs free up
   pdl_wait();                    // everything above touched only weights; from here on we read the producer's output
-  prefetch(blockIdx.x, 0);
+  // All TMA traffic is issued by one elected lane of warp 8 (not an MMA issuer warp) under a warp-uniform branch:
+  // box coordinates and descriptors stay in uniform registers (a divergent `tid == 0` branch costs a waterfall loop per
+  // copy).  elect.sync picks the same lane every time, which the bulk-group waits rely on.
+  const bool tma_warp = warp_u == 8;
+  if (tma_warp) {
+    if (elect_one()) load_tile(blockIdx.x, K::DBUF ? smem + K::OFF_XT : sLand, &xbar[0]);
+    __syncwarp();
+  }
   int buf = 0;
+  uint32_t ph_x0 = 0, ph_x1 = 0;
 
-  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= (K::ASYNC ? 1 : 0)) {
+  for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= (K::DBUF ? 1 : 0)) {
     uint8_t* sXT = smem + K::OFF_XT + buf * K::XT_BYTES;
-    // ---------------- P1a: rows of two windows -> raw tile in smem + LayerNorm statistics (coalesced mapping) ---------
+    const uint8_t* sSrc = K::DBUF ? sXT : sLand;            // where this tile's raw rows landed
+    // ---------------- P1: thread = (token row, quarter of the channels): one pass over the landed rows ---------------
+    // partial sum / sum of squares -> exchange between the four threads of a row -> normalise from registers ->
+    // packed bf16 A operand of the qkv MMAs in TMEM.  (Pad channels are zero and add nothing to either sum.)
     RDST_TSTAMP();   // tile start
-    const int64_t tok_cur = tok;
-    const int reg_cur = regv;
-    if (K::ASYNC) {
-      cp_async_wait_all();           // this tile's rows have landed (issued one tile ago)
-      __syncthreads();
-      prefetch(tile + gridDim.x, buf ^ 1);    // the other buffer was drained by the previous tile's copy-out
-#pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j)
-        raw[j] = *reinterpret_cast<const uint4*>(sXT + cr * K::PITCH + ((((lane >> 3) + 4 * j) ^ csw) * 16));
-    }
+    if (buf == 0) { mbar_wait(&xbar[0], ph_x0 & 1); ph_x0++; } else { mbar_wait(&xbar[1], ph_x1 & 1); ph_x1++; }
+    RDST_TSTAMP();   // tile landed
+    constexpr int NCQ = K::NCH / 4;                           // 16-byte chunks per thread (2, 3 or 4)
+    uint4 rv[NCQ];
     {
-      if ((lane >> 3) == 0) sReg[cr] = reg_cur;
-      float s = 0.f;
 #pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j) {
-        const float2 f0 = up2(raw[j].x), f1 = up2(raw[j].y), f2 = up2(raw[j].z), f3 = up2(raw[j].w);
-        s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
-        if (!K::ASYNC) *reinterpret_cast<uint4*>(sXT + cr * K::PITCH + ((((lane >> 3) + 4 * j) ^ csw) * 16)) = raw[j];
+      for (int cc = 0; cc < NCQ; ++cc) rv[cc] = *reinterpret_cast<const uint4*>(sSrc + xt_off(row, g4 * NCQ + cc));
+      if (g4 == 0) {                 // region id of this thread's own row, for the shift mask
+        const int win = tile * 2 + wsel;
+        int reg = -1;
+        if (win < geo.nwt) {
+          const int wl = win % geo.nw_img;
+          reg = win_region(geo, wl / geo.nwx, wl % geo.nwx, iy, ix);
+        }
+        sReg[row] = reg;
       }
-      s += __shfl_xor_sync(0xffffffffu, s, 8);
-      s += __shfl_xor_sync(0xffffffffu, s, 16);
-      const float mean = s * inv_c;
-      float ss = 0.f;
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j) {
-        const uint32_t w4[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+      for (int cc = 0; cc < NCQ; ++cc) {
+        const uint32_t w4[4] = {rv[cc].x, rv[cc].y, rv[cc].z, rv[cc].w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float2 f = up2(w4[q]);
-          ss += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+          s0 += f.x; s1 += f.y;
+          q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
         }
       }
-      ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-      ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-      ss -= (float)(CP - C_) * mean * mean;
-      if ((lane >> 3) == 0) sStat[cr] = make_float2(mean, rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f));
+      sPart[g4 * 128 + row] = make_float2(s0 + s1, q0 + q1);
+      RDST_TSTAMP();   // stats written
     }
     __syncthreads();
     RDST_TSTAMP();   // P1a done
-    // ---------------- P1b: thread = (token row, quarter): normalise -> packed bf16 A operand in TMEM ----------------
     {
-      const float2 st = sStat[row];
-      constexpr int NC = K::NCH / 4;                          // 16-byte chunks per thread (2, 3 or 4)
-      uint32_t o[NC * 4];
+      const float2 p0 = sPart[row], p1 = sPart[128 + row], p2 = sPart[256 + row], p3 = sPart[384 + row];
+      const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * inv_c;
+      const float var = ((p0.y + p1.y) + (p2.y + p3.y)) * inv_c - mean * mean;
+      const float rstd = rsqrtf(fmaxf(var, 0.f) + 1e-5f);
+      const float nb = -mean * rstd;
+      uint32_t o[NCQ * 4];
 #pragma unroll
-      for (int cc = 0; cc < NC; ++cc) {
-        const uint4 v = *reinterpret_cast<const uint4*>(sXT + row * K::PITCH + (((g4 * NC + cc) ^ rsw) * 16));
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+      for (int cc = 0; cc < NCQ; ++cc) {
+        const uint32_t w4[4] = {rv[cc].x, rv[cc].y, rv[cc].z, rv[cc].w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float2 f = up2(w4[q]);
-          o[cc * 4 + q] = pk2((f.x - st.x) * st.y, (f.y - st.x) * st.y);
+          o[cc * 4 + q] = pk2(fmaf(f.x, rstd, nb), fmaf(f.y, rstd, nb));
         }
       }
-      const uint32_t dst = lane_addr + K::TM_XH + g4 * NC * 4;
+      RDST_TSTAMP();   // P1b loaded
+      const uint32_t dst = lane_addr + K::TM_XH + g4 * NCQ * 4;
 #pragma unroll
-      for (int c0 = 0; c0 + 8 <= NC * 4; c0 += 8) {
+      for (int c0 = 0; c0 + 8 <= NCQ * 4; c0 += 8) {
         uint32_t a[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) a[e] = o[c0 + e];
         tmem_st_x8(dst + c0, a);
       }
-      if ((NC * 4) % 8 != 0) {
-        uint32_t a4[4] = {o[NC * 4 - 4], o[NC * 4 - 3], o[NC * 4 - 2], o[NC * 4 - 1]};
-        tmem_st_x4(dst + NC * 4 - 4, a4);
+      if ((NCQ * 4) % 8 != 0) {
+        uint32_t a4[4] = {o[NCQ * 4 - 4], o[NCQ * 4 - 3], o[NCQ * 4 - 2], o[NCQ * 4 - 1]};
+        tmem_st_x4(dst + NCQ * 4 - 4, a4);
       }
       wait_st();
+      RDST_TSTAMP();   // P1b stored
+    }
+    if (!K::DBUF && tma_warp) {        // the previous tile's store has finished reading sXT (issued > P1a + P1b ago)
+      if (elect_one()) bulk_wait_read();
+      __syncwarp();
     }
     fence_before_sync();
     __syncthreads();
@@ -350,6 +387,21 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       fence_after_sync();
       if (elect_one()) issue_qkv(slot_u);
       __syncwarp();
+    }
+    if (K::DBUF) {
+      // next tile -> other buffer, under the first qkv MMAs (the previous tile's store out of that buffer is long done)
+      if (tma_warp) {
+        if (elect_one()) {
+          bulk_wait_read();
+          load_tile(tile + gridDim.x, smem + K::OFF_XT + (buf ^ 1) * K::XT_BYTES, &xbar[buf ^ 1]);
+        }
+        __syncwarp();
+      }
+    } else {
+      // C=120: the raw rows (still in registers) go to sXT under the first qkv MMAs: residual source and output
+      // staging.  Nobody reads the landing zone (= K/V image area) any more; the drain below may overwrite it.
+#pragma unroll
+      for (int cc = 0; cc < NCQ; ++cc) *reinterpret_cast<uint4*>(sXT + xt_off(row, g4 * NCQ + cc)) = rv[cc];
     }
     // shift mask of this thread's 32 keys: bit j set = key belongs to another region (edge windows only)
     const int myreg = sReg[row];
@@ -390,6 +442,11 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
 #pragma unroll
           for (int c8 = 0; c8 < (HD + 7) / 8; ++c8)
             *reinterpret_cast<uint4*>(sBk + c8 * 2048 + row * 16) = pack8<HD, HD, false>(f, bq, c8);
+          if (!K::DBUF && i == 0) {       // the raw tile landed here: re-zero the K-dim pad chunks of the image
+#pragma unroll
+            for (int c8 = (HD + 7) / 8; c8 < K::HDP / 8; ++c8)
+              *reinterpret_cast<uint4*>(sBk + c8 * 2048 + row * 16) = make_uint4(0, 0, 0, 0);
+          }
           wait_st();
         } else {
           // v (+ ones column) -> MN-major fp16 image; the v columns start at 2*HD: load an 8-aligned superset
@@ -401,6 +458,11 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
 #pragma unroll
           for (int c8 = 0; c8 < (HD + 8) / 8; ++c8)
             *reinterpret_cast<uint4*>(sBv + c8 * 2048 + row * 16) = pack8<2 * HD - C0, HD, true, true>(f, bq + C0, c8);
+          if (!K::DBUF && i == 0) {
+#pragma unroll
+            for (int c8 = (HD + 8) / 8; c8 < K::HDV / 8; ++c8)
+              *reinterpret_cast<uint4*>(sBv + c8 * 2048 + row * 16) = make_uint4(0, 0, 0, 0);
+          }
         }
       }
       fence_proxy_async();
@@ -437,7 +499,8 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
         __half2 hv[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) {
-          const uint32_t bp = tb[-(((2 * j) >> 3) * 24 + ((2 * j) & 7))];
+          // keys 2j, 2j+1 of this half (box order): jy = 4*part + ((2j>>2)&3), jx = 4*((2j>>4)&1) + (2j&3)
+          const uint32_t bp = tb[-((((2 * j) >> 2) & 3) * 24 + (((2 * j) >> 4) & 1) * 4 + ((2 * j) & 3))];
           hv[j] = __hadd2(__floats2half2_rn(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1])),
                           *reinterpret_cast<const __half2*>(&bp));
         }
@@ -494,6 +557,13 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
     mbar_wait(bar_o, (ph_o - 1) & 1);
     fence_after_sync();
     __syncthreads();                    // both slots are past their last qkv MMA: the normalised input is dead
+    if (!K::DBUF && tma_warp) {         // ... and past their last PV MMA: the K/V images are dead -> next tile lands there
+      if (elect_one()) {
+        fence_proxy_async();
+        load_tile(tile + gridDim.x, sLand, &xbar[0]);
+      }
+      __syncwarp();
+    }
     {
       // the three heads of a slot are split between its two warpgroups: part 0 takes two heads, part 1 one
       constexpr int NCO = (HD + 8) / 8 * 8;      // head_dim values + the row-sum column
@@ -542,11 +612,10 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
       }
       __syncwarp();
     }
-    // C=120 (no room for a second raw tile): prefetch the next tile's rows into registers under proj and the copy-out
-    if (!K::ASYNC) prefetch(tile + gridDim.x, 0);
     RDST_TSTAMP();   // O epilogue + proj issued
     mbar_wait(&bars[6], ph_p & 1); ph_p++;
     fence_after_sync();
+    RDST_TSTAMP();   // proj done
     // ---------------- proj epilogue in the row mapping: y = proj + bias + x, in place in the raw tile ----------------
     {
       constexpr int NC = CP / 4;                               // columns per thread (16, 24 or 32)
@@ -560,10 +629,11 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
         for (int e = 0; e < 8; ++e) acc[c0 + e] = t8[e];
       }
       wait_ld();
+      RDST_TSTAMP();   // proj loaded
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 8) {
         const uint32_t* v = acc + c0;
-        uint8_t* xp = sXT + row * K::PITCH + ((((cb + c0) >> 3) ^ rsw) * 16);
+        uint8_t* xp = sXT + xt_off(row, (cb + c0) >> 3);
         const uint4 xv = *reinterpret_cast<const uint4*>(xp);
         const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
         uint32_t o[4];
@@ -576,20 +646,22 @@ stl_attn_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16*
         *reinterpret_cast<uint4*>(xp) = make_uint4(o[0], o[1], o[2], o[3]);
       }
     }
+    RDST_TSTAMP();   // y written
+    fence_proxy_async();               // the finished rows are read by the TMA store (async proxy)
     fence_before_sync();
     __syncthreads();
     RDST_TSTAMP();   // y staged
-    if (tok_cur >= 0) {
-#pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j) {
-        const int c = (lane >> 3) + 4 * j;
-        *(reinterpret_cast<uint4*>(Y + tok_cur * ldy) + c) = *reinterpret_cast<const uint4*>(sXT + cr * K::PITCH + ((c ^ csw) * 16));
-      }
+    if (tma_warp) {
+      if (elect_one()) store_tile(tile, sXT);
+      __syncwarp();
     }
-    __syncthreads();
     RDST_TSTAMP();   // tile done
   }
 #undef RDST_TSTAMP
+  if (tma_warp) {
+    if (elect_one()) bulk_wait_read();
+    __syncwarp();
+  }
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
@@ -607,10 +679,13 @@ static int launch_attn(const void* x, int64_t ldx, void* y, int64_t ldy, const v
   g.nwt = B * g.nw_img;
   const int64_t ntiles = ((int64_t)g.nwt + 1) / 2;
   const int grid = (int)(ntiles < sms ? ntiles : sms);
+  const CUtensorMap* mx = get_act_tmap(x, ldx, B, H, W, K::CP, 4, 4);
+  const CUtensorMap* my = get_act_tmap(y, ldy, B, H, W, K::CP, 4, 4);
+  if (!mx || !my) return RDST_E_CUDA;
   auto k = stl_attn_kernel<C_>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) { set_error("rdst_stl_attn_fwd_bf16: smem attr (%d B): %s", K::SMEM, cudaGetErrorString(e)); return RDST_E_CUDA; }
-  e = launch_pdl(k, dim3(grid), dim3(ATTN_THREADS), (size_t)K::SMEM, st, (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy,
+  e = launch_pdl(k, dim3(grid), dim3(ATTN_THREADS), (size_t)K::SMEM, st, *mx, *my,
                  (const uint8_t*)wqkv, (const uint8_t*)wproj, bqkv, bproj, table, g, -100.0f * 1.4426950408889634f, g_attn_dbg);
   if (e != cudaSuccess) { set_error("rdst_stl_attn_fwd_bf16: launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   return RDST_OK;

@@ -28,10 +28,10 @@ _lib.call("rdst_debug_attn_timing", _lib.ptr(dbg))
 run(); torch.cuda.synchronize()
 _lib.call("rdst_debug_attn_timing", None)
 d = dbg.cpu().tolist()
-names = ["tile start", "P1a done", "P1b done"]
+names = ["tile start", "tile landed", "stats written", "P1a done", "P1b loaded", "P1b stored", "P1b done"]
 for i in range(3):
     names += [f"h{i} before qkv wait", f"h{i} drained", f"h{i} S ready", f"h{i} bias+max", f"h{i} softmax done"]
-names += ["heads issued", "O epi+proj issued", "y staged", "tile done"]
+names += ["heads issued", "O epi+proj issued", "proj done", "proj loaded", "y written", "y staged", "tile done"]
 for wg in range(2):
     t = d[wg * 64: wg * 64 + 64]
     print(f"--- warpgroup {wg} (C={c}, shift={shift}); first two tiles")
@@ -43,3 +43,9 @@ for wg in range(2):
             v = t[tile * n + k]
             print(f"  {nm:22s} +{v - prev:6d}  (t={v - base:6d})")
             prev = v
+if os.environ.get("RDST_TIMING_ABS"):
+    t0 = d[0]
+    print("--- absolute cycles (both stamping threads, relative to slot 0 tile 0 start)")
+    for tile in range(2):
+        for k, nm in enumerate(names):
+            print(f"  tile{tile} {nm:22s} slot0 {d[tile * n + k] - t0:7d}   slot1 {d[64 + tile * n + k] - t0:7d}")
