@@ -3,9 +3,10 @@
 // Replaces norm2 + Mlp + residual of SwinTransformerBlock.forward (reference swin_transformer_sr.py:272, :23-29).
 // One persistent CTA per SM keeps both weight matrices resident in shared memory as ready-made UMMA operand
 // images and walks over 128-token tiles:
-//   P1a coalesced load of the tile (8 rows x 64 B per warp instruction) into a swizzled raw tile in shared memory,
-//       LayerNorm statistics by 2 shuffles
-//   P1b thread = token row: normalise -> packed bf16 pairs -> tcgen05.st: the A operand of fc1 lives in TMEM, so
+//   P0  the 128 token rows of a tile arrive by TMA (one box per 64-channel panel, SWIZZLE_128B) into one of two raw
+//       tiles, a whole tile ahead; finished tiles leave the same way (TMA store), so no thread ever waits on HBM
+//   P1  thread = (token row, channel quarter): one pass over the landed rows -> partial LayerNorm sums -> exchange ->
+//       normalise from registers -> packed bf16 pairs -> tcgen05.st: the A operand of fc1 lives in TMEM, so
 //       the MMAs read only the weights from shared memory (SS-mode A reads were the bottleneck: 4 KB per k-step)
 //   P2  fc1 as two N-halves of tcgen05.mma (A from TMEM), each committed to its own mbarrier; issue is warp-uniform
 //       (elect.sync) so descriptors stay in uniform registers
@@ -16,6 +17,7 @@
 // Hidden activations never leave the SM.  LayerNorm gamma/beta are folded into fc1 by the host.
 #include "common.cuh"
 #include "umma.cuh"
+#include "tma.cuh"
 
 namespace rdst {
 using namespace umma;
@@ -59,14 +61,14 @@ struct MlpCfg {
   static constexpr int H1 = HP - H0;
   static constexpr int W1_BYTES = HP * CP * 2;
   static constexpr int W2_BYTES = CP * HP * 2;
-  static constexpr bool SWZ = (NCH == 8 || NCH == 16);    // raw tile rows: XOR-swizzled when NCH is a power of two
-  static constexpr int PITCH = SWZ ? CP * 2 : CP * 2 + 16;
-  static constexpr int XT_BYTES = 128 * PITCH;
+  static constexpr int NP = CP > 64 ? 2 : 1;              // raw tile: 64-channel panels [128 rows][128 B], SWIZZLE_128B
+  static constexpr int PANEL = 128 * 128;
+  static constexpr int XT_BYTES = NP * PANEL;
   static constexpr int WT_BYTES = 32 * CP * 2;
   static constexpr int OFF_W1 = 0;
   static constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
   static constexpr int OFF_XT = OFF_W2 + W2_BYTES;         // raw bf16 tile (residual source, later the output staging)
-  static constexpr int OFF_B1 = OFF_XT + 2 * XT_BYTES;     // two raw tiles: tile n+1 streams in (cp.async) while tile n computes
+  static constexpr int OFF_B1 = OFF_XT + 2 * XT_BYTES;     // two raw tiles: tile n+1 lands (TMA) while tile n computes
   static constexpr int OFF_B2 = OFF_B1 + HP * 4;
   static constexpr int OFF_STAT = OFF_B2 + CP * 4;         // [128] (mean, rstd)
   static constexpr int OFF_XCH = OFF_STAT + 128 * 8;       // [4][128] (sum, sumsq) exchange for the tail LayerNorm
@@ -81,7 +83,13 @@ struct MlpCfg {
   static constexpr int TM_HID = 384;                       // GELU(hidden) packed [384,384+HP/2)
   static_assert(HP % 16 == 0 && CP % 32 == 0 && H1 % 16 == 0 && H1 > 0, "tile shape");
   static_assert(HP <= 240 && CP <= 128 && TM_HID + HP / 2 <= 512, "TMEM budget");
+  static_assert(OFF_XT % 1024 == 0, "raw tiles must be 1024-byte aligned (SWIZZLE_128B)");
 };
+
+// byte offset of 16-byte chunk c (8 channels) of token row `row` inside a raw tile (TMA SWIZZLE_128B panels)
+__device__ __forceinline__ uint32_t mlp_xt_off(int row, int c) {
+  return (uint32_t)((c >> 3) * (128 * 128) + row * 128 + (((c & 7) ^ (row & 7)) << 4));
+}
 
 // store 8 packed columns held in a larger register array
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
@@ -103,23 +111,25 @@ constexpr int MLP_THREADS = 512;      // 16 warps: four threads (one per warpgro
 
 template <int CP, int HP, bool EXACT, bool TAIL>
 __global__ void __launch_bounds__(MLP_THREADS, 1)
-stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* __restrict__ Y, int64_t ldy,
+stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                const uint8_t* __restrict__ w1img, const uint8_t* __restrict__ w2img,
                const float* __restrict__ b1, const float* __restrict__ b2, int64_t T, int creal, TailArgs ta,
                unsigned long long* __restrict__ dbg) {
   using C = MlpCfg<CP, HP>;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bars[6];          // [0,1] fc1 halves, [2,3] fc2 halves, [4] tail, [5] weights landed
+  __shared__ uint64_t xbar[2];          // raw tile landed, one per buffer
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   float* sB1 = reinterpret_cast<float*>(smem + C::OFF_B1);
   float* sB2 = reinterpret_cast<float*>(smem + C::OFF_B2);
-  float2* sStat = reinterpret_cast<float2*>(smem + C::OFF_STAT);
   float2* sXch = reinterpret_cast<float2*>(smem + C::OFF_XCH);
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) {
     for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    mbar_init(&xbar[0], 1);
+    mbar_init(&xbar[1], 1);
     fence_mbar_init();
     // resident weights (ready-made operand images) arrive by bulk async copies that overlap the prologue and the
     // first tile's load + LayerNorm; the issuer waits on bars[5] once before its first tcgen05.mma
@@ -143,7 +153,6 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
 
   const int row = tid & 127, qtr = tid >> 7;             // token row (= TMEM lane) and column quarter of this thread
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
-  const int rsw = C::SWZ ? (row & 7) : 0;
   // warp-uniform values for the MMA issuer (warp 0): descriptors stay in uniform registers
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
@@ -151,97 +160,79 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
   const float inv_c = 1.0f / (float)creal;
   const int64_t ntiles = (T + 127) / 128;
   uint32_t parity = 0;
-  // coalesced mapping: warp w owns the 8-row group w; lane -> (row w*8 + lane%8, 16-byte chunk lane/8 + 4j)
-  const int cr = warp * 8 + (lane & 7);
-  const int csw = C::SWZ ? (cr & 7) : 0;
-
   int dbg_n = 0;
   const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && (tid & 127) == 0 && qtr < 2;
 #define RDST_TSTAMP()                                                         \
   do {                                                                        \
     if (dbg_on && dbg_n < 64) dbg[qtr * 64 + dbg_n++] = clock64();            \
   } while (0)
-  // The rows of the next tile stream into the other raw-tile buffer with cp.async (LDGSTS): no staging registers and no
-  // scoreboard slots are held while the loads are in flight (a register prefetch made the fc2 epilogue wait for the
-  // global loads, because LDG and tcgen05.ld share the long-scoreboard slots).
-  auto async_load = [&](int64_t tile, int b) {
-    uint8_t* dst = smem + C::OFF_XT + b * C::XT_BYTES + cr * C::PITCH;
-    const int64_t t = tile * 128 + cr;
-    const bool ok = tile < ntiles && t < T;
+  // All TMA traffic is issued by one elected lane of warp 4 under a warp-uniform branch (coordinates and descriptors
+  // stay in uniform registers; elect.sync picks the same lane every time, which the bulk-group waits rely on).
+  const bool tma_warp = warp_u == 4;
+  auto load_tile = [&](int64_t tile, int b) {           // rows beyond T are out of range -> zero fill
+    if (tile >= ntiles) return;
+    mbar_arrive_expect_tx(&xbar[b], C::XT_BYTES);
 #pragma unroll
-    for (int j = 0; j < C::NCH / 4; ++j) {
-      const int c = (lane >> 3) + 4 * j;
-      cp_async16(dst + ((c ^ csw) * 16), reinterpret_cast<const uint4*>(X + (ok ? t : 0) * ldx) + c, ok ? 16u : 0u);
-    }
-    cp_async_commit();
+    for (int pnl = 0; pnl < C::NP; ++pnl)
+      tma::load_4d(smem + C::OFF_XT + b * C::XT_BYTES + pnl * C::PANEL, &mapX, pnl * 64, (int)(tile * 128), 0, 0, &xbar[b]);
   };
   pdl_launch_dependents();
   pdl_wait();                    // prologue above touched only weights; the rows below come from the previous kernel
-  async_load(blockIdx.x, 0);
+  if (tma_warp) {
+    if (elect_one()) load_tile(blockIdx.x, 0);
+    __syncwarp();
+  }
   int buf = 0;
+  uint32_t ph_x0 = 0, ph_x1 = 0;
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1, buf ^= 1) {
     const int64_t t0 = tile * 128;
     uint8_t* sXT = smem + C::OFF_XT + buf * C::XT_BYTES;
-    cp_async_wait_all();           // this tile's rows have landed (issued one tile ago)
-    __syncthreads();
-    async_load(tile + gridDim.x, buf ^ 1);    // the other buffer was drained by the previous tile's copy-out
     RDST_TSTAMP();   // tile start
-    // ---------------- P1a: LayerNorm statistics of the landed raw tile (coalesced mapping, 2 shuffles) ----------------
+    if (buf == 0) { mbar_wait(&xbar[0], ph_x0 & 1); ph_x0++; } else { mbar_wait(&xbar[1], ph_x1 & 1); ph_x1++; }
+    // ---------------- P1: one pass over the landed rows: partial LayerNorm sums -> exchange -> A operand in TMEM ------
+    constexpr int NCQ = C::NCH / 4;                           // 16-byte chunks per thread (2, 3 or 4)
+    uint4 rv[NCQ];
     {
-      uint4 raw[C::NCH / 4];
 #pragma unroll
-      for (int j = 0; j < C::NCH / 4; ++j)
-        raw[j] = *reinterpret_cast<const uint4*>(sXT + cr * C::PITCH + ((((lane >> 3) + 4 * j) ^ csw) * 16));
-      float s = 0.f;
+      for (int cc = 0; cc < NCQ; ++cc) rv[cc] = *reinterpret_cast<const uint4*>(sXT + mlp_xt_off(row, qtr * NCQ + cc));
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-      for (int j = 0; j < C::NCH / 4; ++j) {
-        const float2 f0 = unpack_bf16x2(raw[j].x), f1 = unpack_bf16x2(raw[j].y), f2 = unpack_bf16x2(raw[j].z),
-                     f3 = unpack_bf16x2(raw[j].w);
-        s += (f0.x + f0.y) + (f1.x + f1.y) + (f2.x + f2.y) + (f3.x + f3.y);
-      }
-      s += __shfl_xor_sync(0xffffffffu, s, 8);
-      s += __shfl_xor_sync(0xffffffffu, s, 16);
-      const float mean = s * inv_c;
-      float ss = 0.f;
-#pragma unroll
-      for (int j = 0; j < C::NCH / 4; ++j) {
-        const uint32_t w4[4] = {raw[j].x, raw[j].y, raw[j].z, raw[j].w};
+      for (int cc = 0; cc < NCQ; ++cc) {
+        const uint32_t w4[4] = {rv[cc].x, rv[cc].y, rv[cc].z, rv[cc].w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float2 f = unpack_bf16x2(w4[q]);
-          ss += (f.x - mean) * (f.x - mean) + (f.y - mean) * (f.y - mean);
+          s0 += f.x; s1 += f.y;
+          q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
         }
       }
-      ss += __shfl_xor_sync(0xffffffffu, ss, 8);
-      ss += __shfl_xor_sync(0xffffffffu, ss, 16);
-      ss -= (float)(CP - creal) * mean * mean;                 // zero pads contributed mean^2 each
-      if ((lane >> 3) == 0) sStat[cr] = make_float2(mean, rsqrtf(fmaxf(ss, 0.f) * inv_c + 1e-5f));
+      sXch[qtr * 128 + row] = make_float2(s0 + s1, q0 + q1);   // zero pads add nothing to either sum
     }
     __syncthreads();
     RDST_TSTAMP();   // P1a done
-    // ---------------- P1b: thread = (token row, quarter): normalise -> packed bf16 A operand in TMEM ----------------
     {
-      const float2 st = sStat[row];
-      constexpr int NC = C::NCH / 4;                            // 16-byte chunks per thread (2, 3 or 4)
-      uint32_t o[NC * 4];
+      const float2 p0 = sXch[row], p1 = sXch[128 + row], p2 = sXch[256 + row], p3 = sXch[384 + row];
+      const float mean = ((p0.x + p1.x) + (p2.x + p3.x)) * inv_c;
+      const float var = ((p0.y + p1.y) + (p2.y + p3.y)) * inv_c - mean * mean;
+      const float rstd = rsqrtf(fmaxf(var, 0.f) + 1e-5f);
+      const float nb = -mean * rstd;
+      uint32_t o[NCQ * 4];
 #pragma unroll
-      for (int cc = 0; cc < NC; ++cc) {
-        const int c = qtr * NC + cc;
-        const uint4 v = *reinterpret_cast<const uint4*>(sXT + row * C::PITCH + ((c ^ rsw) * 16));
-        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+      for (int cc = 0; cc < NCQ; ++cc) {
+        const uint32_t w4[4] = {rv[cc].x, rv[cc].y, rv[cc].z, rv[cc].w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float2 f = unpack_bf16x2(w4[q]);
-          o[cc * 4 + q] = pack_bf16x2((f.x - st.x) * st.y, (f.y - st.x) * st.y);
+          o[cc * 4 + q] = pack_bf16x2(fmaf(f.x, rstd, nb), fmaf(f.y, rstd, nb));
         }
       }
-      const uint32_t dst = lane_addr + C::TM_XH + qtr * NC * 4;
+      const uint32_t dst = lane_addr + C::TM_XH + qtr * NCQ * 4;
 #pragma unroll
-      for (int c0 = 0; c0 + 8 <= NC * 4; c0 += 8) tmem_st8(dst + c0, o + c0);
-      if ((NC * 4) % 8 != 0) {
-        uint32_t a4[4] = {o[NC * 4 - 4], o[NC * 4 - 3], o[NC * 4 - 2], o[NC * 4 - 1]};
-        tmem_st_x4(dst + NC * 4 - 4, a4);
+      for (int c0 = 0; c0 + 8 <= NCQ * 4; c0 += 8) tmem_st8(dst + c0, o + c0);
+      if ((NCQ * 4) % 8 != 0) {
+        uint32_t a4[4] = {o[NCQ * 4 - 4], o[NCQ * 4 - 3], o[NCQ * 4 - 2], o[NCQ * 4 - 1]};
+        tmem_st_x4(dst + NCQ * 4 - 4, a4);
       }
       wait_st();
     }
@@ -264,6 +255,13 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
           mma_ts(tmem_u + C::TM_FC1 + C::H0, tmem_u + C::TM_XH + ks * 8,
                  make_smem_desc(aW1 + C::H0 * 16 + ks * 2 * (HP * 16), HP * 16, 128), id1, ks > 0);
         commit(&bars[1]);
+      }
+      __syncwarp();
+    }
+    if (tma_warp) {                // next tile -> other buffer, under fc1 (its last store has long been read out)
+      if (elect_one()) {
+        bulk_wait_read();
+        load_tile(tile + gridDim.x, buf ^ 1);
       }
       __syncwarp();
     }
@@ -343,7 +341,7 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 8) {
         const int ch = (cb + c0) / 8;
-        uint8_t* xp = sXT + row * C::PITCH + ((ch ^ rsw) * 16);
+        uint8_t* xp = sXT + mlp_xt_off(row, ch);
         const uint4 xv = *reinterpret_cast<const uint4*>(xp);
         const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
         uint32_t o[4];
@@ -382,6 +380,7 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
         wait_st();
       }
     }
+    if (!TAIL) fence_proxy_async();      // the finished rows are read by the TMA store (async proxy)
     fence_before_sync();
     __syncthreads();
     RDST_TSTAMP();   // P5 done
@@ -417,20 +416,22 @@ stl_mlp_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, __nv_bfloat16* 
       }
       fence_before_sync();
     } else {
-      // coalesced copy of the finished tile to global memory
-      const int64_t t = t0 + cr;
-      if (t < T) {
+      if (tma_warp) {              // rows beyond T are out of range and dropped
+        if (elect_one()) {
 #pragma unroll
-        for (int j = 0; j < C::NCH / 4; ++j) {
-          const int c = (lane >> 3) + 4 * j;
-          *(reinterpret_cast<uint4*>(Y + t * ldy) + c) = *reinterpret_cast<const uint4*>(sXT + cr * C::PITCH + ((c ^ csw) * 16));
+          for (int pnl = 0; pnl < C::NP; ++pnl) tma::store_4d(&mapY, pnl * 64, (int)t0, 0, 0, sXT + pnl * C::PANEL);
+          bulk_commit();
         }
+        __syncwarp();
       }
     }
-    __syncthreads();        // raw tile / TMEM are reused by the next tile
     RDST_TSTAMP();   // tile done
   }
 #undef RDST_TSTAMP
+  if (tma_warp) {
+    if (elect_one()) bulk_wait_read();
+    __syncwarp();
+  }
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<512>(tmem);
@@ -446,7 +447,11 @@ static int launch_mlp(const void* x, int64_t ldx, void* y, int64_t ldy, const vo
   const int grid = (int)(ntiles < sms ? ntiles : sms);
   TailArgs ta{};
   int smem = C::SMEM_PLAIN;
-  void (*k)(const __nv_bfloat16*, int64_t, __nv_bfloat16*, int64_t, const uint8_t*, const uint8_t*, const float*,
+  // activations as [T][CP] "images" of one row: box = 128 tokens x 64 channels
+  const CUtensorMap* mx = get_act_tmap(x, ldx, 1, 1, (int)T, CP, 128, 1);
+  const CUtensorMap* my = tail ? mx : get_act_tmap(y, ldy, 1, 1, (int)T, CP, 128, 1);
+  if (!mx || !my) return RDST_E_CUDA;
+  void (*k)(const CUtensorMap, const CUtensorMap, const uint8_t*, const uint8_t*, const float*,
             const float*, int64_t, int, TailArgs, unsigned long long*);
   if (tail) {
     ta = *tail;
@@ -457,7 +462,7 @@ static int launch_mlp(const void* x, int64_t ldx, void* y, int64_t ldy, const vo
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("rdst_stl_mlp_fwd_bf16: smem attr (%d B): %s", smem, cudaGetErrorString(e)); return RDST_E_CUDA; }
-  e = launch_pdl(k, dim3(grid), dim3(MLP_THREADS), (size_t)smem, st, (const __nv_bfloat16*)x, ldx, (__nv_bfloat16*)y, ldy,
+  e = launch_pdl(k, dim3(grid), dim3(MLP_THREADS), (size_t)smem, st, *mx, *my,
                  (const uint8_t*)w1, (const uint8_t*)w2, b1, b2, T, creal, ta, g_mlp_dbg);
   if (e != cudaSuccess) { set_error("rdst_stl_mlp_fwd_bf16: launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   return RDST_OK;
