@@ -199,6 +199,7 @@ int rdst_last_conv_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, flo
  * clock64() at its phase boundaries (64 stamps per warpgroup).  Pass NULL to switch it off (the default). */
 int rdst_debug_attn_timing(void* device_buffer_128_u64);
 int rdst_debug_mlp_timing(void* device_buffer_128_u64);     /* same for rdst_stl_mlp_*_fwd_bf16 */
+int rdst_debug_conv_timing(void* device_buffer_128_u64);    /* same for rdst_conv3x3_fwd_bf16_tc (128 stamps, CTA 0) */
 
 /* Self-test of the UMMA plumbing: D[M=128][N] = A[128][K] . B[N][K]^T with bf16 inputs, fp32 output.
  * b_mn_major != 0 feeds B from an MN-major shared-memory image.  Used by tests/ only. */

@@ -42,6 +42,7 @@ _SIGNATURES = {
     "rdst_stl_mlp_tail_fwd_bf16": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f, _i64, _i, _i, _vp]),
     "rdst_debug_attn_timing": (C.c_int, [_vp]),
     "rdst_debug_mlp_timing": (C.c_int, [_vp]),
+    "rdst_debug_conv_timing": (C.c_int, [_vp]),
     "rdst_umma_selftest": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rdst_tma_selftest": (C.c_int, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }

@@ -41,18 +41,20 @@ struct ConvCfg {
   static constexpr int OFF_A = W_BYTES;                  // two staging buffers: tile n+1 is staged while tile n's MMAs run
   static constexpr int OFF_BIAS = OFF_A + 2 * A_BYTES;
   static constexpr int SMEM = OFF_BIAS + NT * 4;
-  static constexpr int TMEM_COLS = NT <= 64 ? 64 : 128;
+  static constexpr int TMEM_COLS = NT <= 16 ? 32 : 2 * NT;   // two accumulators: tile n+1 runs under tile n's epilogue
   static_assert(NCH % 4 == 0 && (NT == 16 || NT == 32 || NT == 64 || NT == 128), "shape");
 };
 
+constexpr int CONV_THREADS = 288;     // warps 0..7 stage and run the epilogue, warp 8 only issues MMAs
+
 template <int CIN, int NT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(CONV_THREADS)
 conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_t* __restrict__ wimg,
                   const float* __restrict__ bias, const __nv_bfloat16* __restrict__ R, int64_t ldr,
-                  __nv_bfloat16* __restrict__ Y, int64_t ldy, ConvGeom g) {
+                  __nv_bfloat16* __restrict__ Y, int64_t ldy, ConvGeom g, unsigned long long* __restrict__ dbg) {
   using K = ConvCfg<CIN, NT>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar;
+  __shared__ uint64_t bar[2];           // accumulator b complete
   __shared__ uint64_t wbar;             // weights landed (bulk async copies)
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -63,7 +65,8 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
 
   if (warp == 0) tmem_alloc<K::TMEM_COLS>(&tmem_base_s);
   if (tid == 0) {
-    mbar_init(&bar, 1);
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
     mbar_init(&wbar, 1);
     fence_mbar_init();
     // the filter slice arrives by bulk async copies that overlap the staging of the first halo tile
@@ -72,8 +75,8 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
     for (int off = 0; off < K::W_BYTES; off += 32768) bulk_g2s(sW + off, src + off, min(32768, K::W_BYTES - off), &wbar);
   }
   {
-    for (int i = tid; i < 2 * K::A_BYTES / 16; i += 256) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
-    for (int i = tid; i < NT; i += 256) sBias[i] = (NT == 16) ? 0.f : bias[slice * NT + i];
+    for (int i = tid; i < 2 * K::A_BYTES / 16; i += CONV_THREADS) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+    for (int i = tid; i < NT; i += CONV_THREADS) sBias[i] = (NT == 16) ? 0.f : bias[slice * NT + i];
   }
   fence_proxy_async();
   fence_before_sync();
@@ -86,12 +89,14 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
   const int row = tid & 127, part = tid >> 7;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int64_t ntiles = (int64_t)g.B * g.nty * g.ntx;
-  uint32_t parity = 0;
   const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
 
-  // stage the halo tile of `tile` into staging buffer `buf` as a K-major image
+  // stage the halo tile of `tile` into staging buffer `buf` as a K-major image.  cp.async (LDGSTS) with zero fill for
+  // the padding ring: nothing waits on the loads until the tile's MMAs are about to be issued (a register-staged copy
+  // serialised three L2 round trips per warp, and the warp that also issued MMAs started its share last)
   auto stage = [&](int64_t tile, int buf) {
+    if (warp >= 8) return;
     const int b = (int)(tile / (g.nty * g.ntx));
     const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
     const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
@@ -99,60 +104,78 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
 #pragma unroll 1
     for (int pg = warp; pg * 8 < nps; pg += 8) {
       const int pos = pg * 8 + (lane & 7);
+      if (pos >= nps) continue;
       const int hy = pos / g.LW, hx = pos - hy * g.LW;
       const int y = y0 - 1 + hy, x = x0 - 1 + hx;
-      const bool ok = pos < nps && y >= 0 && y < g.H && x >= 0 && x < g.W;
-      const __nv_bfloat16* src = X + (((int64_t)b * g.H + y) * g.W + x) * ldx;
-      uint4 v[K::NCH / 4];
+      const bool ok = y >= 0 && y < g.H && x >= 0 && x < g.W;
+      const __nv_bfloat16* src = X + (ok ? (((int64_t)b * g.H + y) * g.W + x) * ldx : 0);
 #pragma unroll
       for (int j = 0; j < K::NCH / 4; ++j)
-        v[j] = ok ? __ldg(reinterpret_cast<const uint4*>(src) + (lane >> 3) + 4 * j) : make_uint4(0, 0, 0, 0);
-#pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j)
-        *reinterpret_cast<uint4*>(dst + (size_t)((lane >> 3) + 4 * j) * lboA + pos * 16) = v[j];
+        cp_async16(dst + (size_t)((lane >> 3) + 4 * j) * lboA + pos * 16, reinterpret_cast<const uint4*>(src) + (lane >> 3) + 4 * j,
+                   ok ? 16u : 0u);
     }
+    cp_async_commit();
   };
-  auto issue = [&](int buf) {        // warp 0, one elected lane
+  auto issue = [&](int buf) {        // warp 8, one elected lane: staging buffer `buf` -> accumulator `buf`
     constexpr uint32_t idesc = make_idesc_bf16(128, NT, false, false);
     const uint32_t ab = aA + buf * K::A_BYTES;
+    const uint32_t acc = tmem_u + buf * NT;
 #pragma unroll 1
     for (int tap = 0; tap < 9; ++tap) {
       const uint32_t a0 = ab + (uint32_t)((tap / 3) * g.LW + (tap % 3)) * 16;
       const uint32_t w0 = aW + tap * (CIN * NT * 2);
 #pragma unroll
       for (int ks = 0; ks < CIN / 16; ++ks)
-        mma_bf16_ss(tmem_u, make_smem_desc(a0 + ks * 2 * lboA, lboA, 128),
+        mma_bf16_ss(acc, make_smem_desc(a0 + ks * 2 * lboA, lboA, 128),
                     make_smem_desc(w0 + ks * 2 * (NT * 16), NT * 16, 128), idesc, (tap | ks) > 0);
     }
-    commit(&bar);
+    commit(&bar[buf]);
   };
 
+  int dbg_n = 0;
+  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 32;
+#define RDST_TSTAMP()                                                         \
+  do {                                                                        \
+    if (dbg_on && dbg_n < 128) dbg[dbg_n++] = clock64();                      \
+  } while (0)
   pdl_launch_dependents();
   pdl_wait();                    // only the filter slice was touched so far; activations come from the previous kernel
   int buf = 0;
+  uint32_t par0 = 0, par1 = 0;
   if ((int64_t)blockIdx.x < ntiles) {
     stage(blockIdx.x, 0);
+    cp_async_wait_all();
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();
-    if (warp_u == 0) {
+    if (warp_u == 8) {
       mbar_wait(&wbar, 0);             // filter slice has landed
       fence_after_sync();
       if (elect_one()) issue(0);
       __syncwarp();
     }
   }
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, parity ^= 1, buf ^= 1) {
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
     const int b = (int)(tile / (g.nty * g.ntx));
     const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
     const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
     const int64_t next = tile + gridDim.x;
-    if (next < ntiles) {               // overlaps with the MMAs of the current tile
-      stage(next, buf ^ 1);
-      fence_proxy_async();
-    }
-    mbar_wait(&bar, parity);
+    RDST_TSTAMP();   // tile start
+    if (next < ntiles) stage(next, buf ^ 1);       // in flight under the MMAs of the current tile
+    RDST_TSTAMP();   // next staged
+    if (buf == 0) { mbar_wait(&bar[0], par0); par0 ^= 1; } else { mbar_wait(&bar[1], par1); par1 ^= 1; }
+    RDST_TSTAMP();   // MMAs done
+    cp_async_wait_all();
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();          // next halo tile staged; every thread has drained the other accumulator (previous epilogue)
     fence_after_sync();
+    if (next < ntiles && warp_u == 8) {            // the next tile's MMAs run under this tile's epilogue
+      if (elect_one()) issue(buf ^ 1);
+      __syncwarp();
+    }
+    if (warp >= 8) continue;
+    const uint32_t acc_addr = lane_addr + buf * NT;
     // ---------------- epilogue ----------------
     if constexpr (NT == 16) {
       // last conv: one real output channel, fp32 image
@@ -160,7 +183,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
       const int y = y0 + oy, x = x0 + ox;
       const bool ok = part == 0 && ox < g.TW && oy < g.TH && y < g.H && x < g.W;
       uint32_t v[4];
-      tmem_ld_x4(lane_addr, v);
+      tmem_ld_x4(acc_addr, v);
       wait_ld();
       if (ok)
         reinterpret_cast<float*>(Y)[((int64_t)b * g.H + y) * g.W + x] = (__uint_as_float(v[0]) + sBias[0]) * g.out_scale + g.out_bias;
@@ -179,7 +202,7 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
 #pragma unroll
       for (int c0 = 0; c0 < NC; c0 += 16) {
         uint32_t v[16];
-        tmem_ld_x16(lane_addr + cb + c0, v);
+        tmem_ld_x16(acc_addr + cb + c0, v);
         wait_ld();
         if (ok) {
           float f[16];
@@ -198,18 +221,15 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
         }
       }
     }
-    fence_before_sync();
-    __syncthreads();          // accumulator drained, next halo tile staged
-    if (next < ntiles && warp_u == 0) {
-      fence_after_sync();
-      if (elect_one()) issue(buf ^ 1);
-      __syncwarp();
-    }
+    RDST_TSTAMP();   // epilogue done
   }
+#undef RDST_TSTAMP
   fence_before_sync();
   __syncthreads();
   if (warp == 0) tmem_dealloc<K::TMEM_COLS>(tmem);
 }
+
+static unsigned long long* g_conv_dbg = nullptr;
 
 template <int CIN, int NT>
 static int launch_conv(const void* x, int64_t ldx, const void* wimg, const float* bias, const void* r, int64_t ldr,
@@ -227,13 +247,18 @@ static int launch_conv(const void* x, int64_t ldx, const void* wimg, const float
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
   dim3 grid((unsigned)gx, (unsigned)nslices);
-  e = launch_pdl(k, grid, dim3(256), (size_t)K::SMEM, st, (const __nv_bfloat16*)x, ldx, (const uint8_t*)wimg, bias,
-                 (const __nv_bfloat16*)r, ldr, (__nv_bfloat16*)y, ldy, g);
+  e = launch_pdl(k, grid, dim3(CONV_THREADS), (size_t)K::SMEM, st, (const __nv_bfloat16*)x, ldx, (const uint8_t*)wimg, bias,
+                 (const __nv_bfloat16*)r, ldr, (__nv_bfloat16*)y, ldy, g, g_conv_dbg);
   if (e != cudaSuccess) { set_error("rdst_conv3x3_fwd_bf16_tc: launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   return RDST_OK;
 }
 
 }  // namespace rdst
+
+extern "C" int rdst_debug_conv_timing(void* device_buffer_128_u64) {
+  rdst::g_conv_dbg = (unsigned long long*)device_buffer_128_u64;
+  return RDST_OK;
+}
 
 extern "C" int rdst_last_conv_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, float bias, float out_scale,
                                           float out_bias, float* img, int B, int H, int W, void* stream) {
