@@ -92,6 +92,8 @@ int rdst_head_fwd(const float* img, float in_scale, float in_bias, const float* 
                   int B, int H, int W, int dtype, void* stream);
 
 /* Stand-alone LayerNorm over the first `creal` of `ld` stored channels with affine, times out_scale.
+ * Output channels >= creal are pads: the bf16 fast path (creal <= 64, 16-byte aligned rows) writes zeros to the pads
+ * that share the last 8-channel group with real channels, the generic path leaves all pads untouched.
  * Replaces RDSTSR.norm + *global_res_scale (rdst_variations.py:1337,1347). */
 int rdst_layernorm_fwd(const void* x, int64_t ldx, const float* gamma, const float* beta, void* y, int64_t ldy,
                        int64_t T, int creal, float out_scale, int dtype, void* stream);

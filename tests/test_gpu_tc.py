@@ -29,6 +29,36 @@ def test_umma_selftest(N, K, mn):
     assert (D - ref).abs().max().item() < 1e-3
 
 
+@pytest.mark.parametrize("C,ld,shift,hs0,ws0", [(64, 64, 0, 8, 16), (96, 160, 4, 32, 24), (128, 128, 4, 16, 24),
+                                                 (96, 96, 0, 0, 0), (128, 160, 4, 32, 0)])
+def test_tma_selftest(C, ld, shift, hs0, ws0):
+    """4x4-token TMA boxes of a (wrapped) shifted window: SWIZZLE_128B shared-memory image and the store round trip."""
+    L = _L()
+    B, H, W, b = 3, 40, 32, 1
+    x = _rand((B, H, W, ld), 21).to(torch.bfloat16).cuda()
+    y = torch.full((B, H, W, 128), 7.0, device="cuda", dtype=torch.bfloat16)
+    npan = (C + 63) // 64
+    dump = torch.zeros(npan * 4096, device="cuda", dtype=torch.bfloat16)
+    L.call("rdst_tma_selftest", L.ptr(x), ld, L.ptr(y), 128, B, H, W, C, shift, b, hs0, ws0, L.ptr(dump), L.stream_ptr())
+    torch.cuda.synchronize()
+    got = dump.cpu().view(npan, 64, 8, 8)
+    xc = x.cpu()
+    exp = torch.zeros(npan, 64, 8, 8, dtype=torch.bfloat16)
+    yy = torch.full((B, H, W, 128), 7.0, dtype=torch.bfloat16)
+    for iy in range(8):
+        for ix in range(8):
+            r = ((iy >> 2) * 2 + (ix >> 2)) * 16 + (iy & 3) * 4 + (ix & 3)      # box-major row order
+            h, w = (hs0 + iy + shift) % H, (ws0 + ix + shift) % W
+            v = torch.zeros(npan * 64, dtype=torch.bfloat16)
+            v[:C] = xc[b, h, w, :C]
+            for p in range(npan):
+                for c in range(8):
+                    exp[p, r, c ^ (r & 7)] = v[p * 64 + c * 8: p * 64 + c * 8 + 8]
+            yy[b, h, w, :C] = xc[b, h, w, :C]
+    assert (got == exp).all()
+    assert (y.cpu() == yy).all()
+
+
 def _padded_input(T, c, seed):
     from rdst_b200 import packing
     cp = packing.padded_width(c)
