@@ -158,7 +158,9 @@ constexpr int ATTN_THREADS = 512;     // 16 warps = 4 warpgroups: (head slot s i
 __device__ __forceinline__ void slot_barrier(int s) { asm volatile("bar.sync %0, 256;" ::"r"(1 + s) : "memory"); }
 __device__ __forceinline__ void pair_barrier(int id) { asm volatile("bar.sync %0, 64;" ::"r"(3 + id) : "memory"); }
 
-template <int C_>
+// DBG = true compiles the clock64() phase stamps in (rdst_debug_attn_timing); the production instantiation has none
+// (29 predicated stamps per tile were 5 % of all issued instructions of an issue-bound kernel).
+template <int C_, bool DBG>
 __global__ void __launch_bounds__(ATTN_THREADS, 1)
 stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                 const uint8_t* __restrict__ wqkv_img, const uint8_t* __restrict__ wproj_img,
@@ -235,10 +237,10 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   const int cr = warp * 8 + (lane & 7);
 
   int dbg_n = 0;
-  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && row == 0 && part == 0;
+  const bool dbg_on = DBG && dbg != nullptr && blockIdx.x == 0 && row == 0 && part == 0;
 #define RDST_TSTAMP()                                                         \
   do {                                                                        \
-    if (dbg_on && dbg_n < 64) dbg[slot * 64 + dbg_n++] = clock64();           \
+    if (DBG && dbg_on && dbg_n < 64) dbg[slot * 64 + dbg_n++] = clock64();    \
   } while (0)
 
   auto issue_qkv = [&](int h) {      // one elected lane of the slot's issuer warp; h is warp-uniform
@@ -682,7 +684,7 @@ static int launch_attn(const void* x, int64_t ldx, void* y, int64_t ldy, const v
   const CUtensorMap* mx = get_act_tmap(x, ldx, B, H, W, K::CP, 4, 4);
   const CUtensorMap* my = get_act_tmap(y, ldy, B, H, W, K::CP, 4, 4);
   if (!mx || !my) return RDST_E_CUDA;
-  auto k = stl_attn_kernel<C_>;
+  auto k = g_attn_dbg ? stl_attn_kernel<C_, true> : stl_attn_kernel<C_, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) { set_error("rdst_stl_attn_fwd_bf16: smem attr (%d B): %s", K::SMEM, cudaGetErrorString(e)); return RDST_E_CUDA; }
   e = launch_pdl(k, dim3(grid), dim3(ATTN_THREADS), (size_t)K::SMEM, st, *mx, *my,

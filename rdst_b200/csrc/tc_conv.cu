@@ -47,7 +47,7 @@ struct ConvCfg {
 
 constexpr int CONV_THREADS = 288;     // warps 0..7 stage and run the epilogue, warp 8 only issues MMAs
 
-template <int CIN, int NT>
+template <int CIN, int NT, bool DBG>       // DBG: clock64() phase stamps (rdst_debug_conv_timing)
 __global__ void __launch_bounds__(CONV_THREADS)
 conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_t* __restrict__ wimg,
                   const float* __restrict__ bias, const __nv_bfloat16* __restrict__ R, int64_t ldr,
@@ -133,10 +133,10 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
   };
 
   int dbg_n = 0;
-  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 32;
+  const bool dbg_on = DBG && dbg != nullptr && blockIdx.x == 0 && blockIdx.y == 0 && tid == 32;
 #define RDST_TSTAMP()                                                         \
   do {                                                                        \
-    if (dbg_on && dbg_n < 128) dbg[dbg_n++] = clock64();                      \
+    if (DBG && dbg_on && dbg_n < 128) dbg[dbg_n++] = clock64();               \
   } while (0)
   pdl_launch_dependents();
   pdl_wait();                    // only the filter slice was touched so far; activations come from the previous kernel
@@ -235,7 +235,7 @@ template <int CIN, int NT>
 static int launch_conv(const void* x, int64_t ldx, const void* wimg, const float* bias, const void* r, int64_t ldr,
                        void* y, int64_t ldy, ConvGeom g, int nslices, int sms, cudaStream_t st) {
   using K = ConvCfg<CIN, NT>;
-  auto k = conv3x3_tc_kernel<CIN, NT>;
+  auto k = g_conv_dbg ? conv3x3_tc_kernel<CIN, NT, true> : conv3x3_tc_kernel<CIN, NT, false>;
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
   if (e != cudaSuccess) { set_error("rdst_conv3x3_fwd_bf16_tc: smem attr (%d B): %s", K::SMEM, cudaGetErrorString(e)); return RDST_E_CUDA; }
   int occ = (int)(232448 / (K::SMEM + 2048));          // shared memory, TMEM columns and a cap of 4 CTAs per SM

@@ -109,7 +109,7 @@ struct TailArgs {
 
 constexpr int MLP_THREADS = 512;      // 16 warps: four threads (one per warpgroup) share a token row / TMEM lane
 
-template <int CP, int HP, bool EXACT, bool TAIL>
+template <int CP, int HP, bool EXACT, bool TAIL, bool DBG>      // DBG: clock64() phase stamps (rdst_debug_mlp_timing)
 __global__ void __launch_bounds__(MLP_THREADS, 1)
 stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
                const uint8_t* __restrict__ w1img, const uint8_t* __restrict__ w2img,
@@ -161,10 +161,10 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   const int64_t ntiles = (T + 127) / 128;
   uint32_t parity = 0;
   int dbg_n = 0;
-  const bool dbg_on = dbg != nullptr && blockIdx.x == 0 && (tid & 127) == 0 && qtr < 2;
+  const bool dbg_on = DBG && dbg != nullptr && blockIdx.x == 0 && (tid & 127) == 0 && qtr < 2;
 #define RDST_TSTAMP()                                                         \
   do {                                                                        \
-    if (dbg_on && dbg_n < 64) dbg[qtr * 64 + dbg_n++] = clock64();            \
+    if (DBG && dbg_on && dbg_n < 64) dbg[qtr * 64 + dbg_n++] = clock64();     \
   } while (0)
   // All TMA traffic is issued by one elected lane of warp 4 under a warp-uniform branch (coordinates and descriptors
   // stay in uniform registers; elect.sync picks the same lane every time, which the bulk-group waits rely on).
@@ -456,9 +456,11 @@ static int launch_mlp(const void* x, int64_t ldx, void* y, int64_t ldy, const vo
   if (tail) {
     ta = *tail;
     smem = C::SMEM_TAIL;
-    k = exact_gelu ? stl_mlp_kernel<CP, HP, true, true> : stl_mlp_kernel<CP, HP, false, true>;
+    k = exact_gelu ? stl_mlp_kernel<CP, HP, true, true, false> : stl_mlp_kernel<CP, HP, false, true, false>;
+    if (g_mlp_dbg && !exact_gelu) k = stl_mlp_kernel<CP, HP, false, true, true>;
   } else {
-    k = exact_gelu ? stl_mlp_kernel<CP, HP, true, false> : stl_mlp_kernel<CP, HP, false, false>;
+    k = exact_gelu ? stl_mlp_kernel<CP, HP, true, false, false> : stl_mlp_kernel<CP, HP, false, false, false>;
+    if (g_mlp_dbg && !exact_gelu) k = stl_mlp_kernel<CP, HP, false, false, true>;
   }
   cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   if (e != cudaSuccess) { set_error("rdst_stl_mlp_fwd_bf16: smem attr (%d B): %s", smem, cudaGetErrorString(e)); return RDST_E_CUDA; }
