@@ -137,17 +137,26 @@ __device__ __forceinline__ uint32_t ex2_h2(uint32_t x) {              // two fp1
   return y;
 }
 
-// 8 consecutive accumulator values (+bias) as four packed 16-bit pairs, zero beyond HD.  ONES: element HD is 1.0, so
+// A bias b rides inside the MMA: the A operand carries two ones in spare K slots and the matching rows of the weight
+// image hold b as a bf16 hi/lo pair (hi = bf16(b), lo = bf16(b - hi): |b - hi - lo| <= 2^-17 |b|), patched into the
+// shared-memory copy of the image once per CTA.  The CUDA cores never add a bias.
+__device__ __forceinline__ uint32_t bias_hi_lo(float b) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+  return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+}
+
+// 8 consecutive accumulator values as four packed 16-bit pairs, zero beyond HD.  ONES: element HD is 1.0, so
 // that column HD of O = P.V' accumulates the softmax row sum on the tensor core (exactly the fp16 P values that
 // enter the MMA) and the CUDA cores never add the probabilities up.
 template <int OFFSET, int HD, bool HALF, bool ONES = false>
-__device__ __forceinline__ uint4 pack8(const float* f, const float* bias, int c8) {
+__device__ __forceinline__ uint4 pack8(const float* f, int c8) {
   uint32_t o[4];
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const int d0 = c8 * 8 + 2 * q, d1 = d0 + 1;
-    const float a = d0 < HD ? f[OFFSET + d0] + bias[OFFSET + d0] : ((ONES && d0 == HD) ? 1.f : 0.f);
-    const float b = d1 < HD ? f[OFFSET + d1] + bias[OFFSET + d1] : ((ONES && d1 == HD) ? 1.f : 0.f);
+    const float a = d0 < HD ? f[OFFSET + d0] : ((ONES && d0 == HD) ? 1.f : 0.f);
+    const float b = d1 < HD ? f[OFFSET + d1] : ((ONES && d1 == HD) ? 1.f : 0.f);
     o[q] = HALF ? pk2h(a, b) : pk2(a, b);
   }
   return make_uint4(o[0], o[1], o[2], o[3]);
@@ -182,8 +191,6 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   uint8_t* sBv = sBk + K::BK_BYTES;
   const uint32_t* sTab2 = reinterpret_cast<const uint32_t*>(smem + K::OFF_TAB);    // packed fp16 pairs (t[idx], t[idx-1])
   uint32_t* sTabW = reinterpret_cast<uint32_t*>(smem + K::OFF_TAB);
-  float* sBqkv = reinterpret_cast<float*>(smem + K::OFF_BQKV);
-  float* sBproj = reinterpret_cast<float*>(smem + K::OFF_BPROJ);
   int* sReg = reinterpret_cast<int*>(smem + K::OFF_SREG);
   float2* sPart = reinterpret_cast<float2*>(smem + K::OFF_STAT);
 
@@ -205,8 +212,6 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   for (int i = tid; i < 2 * K::KV_BYTES / 16; i += ATTN_THREADS)
     *reinterpret_cast<uint4*>(smem + K::OFF_KV + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 6 * K::TBL; i += ATTN_THREADS) sTabW[i] = reinterpret_cast<const uint32_t*>(table)[i];
-  for (int i = tid; i < 6 * NH; i += ATTN_THREADS) sBqkv[i] = bqkv[i];
-  for (int i = tid; i < CP; i += ATTN_THREADS) sBproj[i] = bproj[i];
   fence_proxy_async();
   fence_before_sync();
   __syncthreads();
@@ -233,9 +238,6 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   uint64_t* bar_q_u = &bars[slot_u];
   uint64_t* bar_s_u = &bars[2 + slot_u];
   uint64_t* bar_o_u = &bars[4 + slot_u];
-  // coalesced mapping: warp w owns the 8-row group w (= one window row); lane -> (row, 16-byte chunk lane/8 + 4j)
-  const int cr = warp * 8 + (lane & 7);
-
   int dbg_n = 0;
   const bool dbg_on = DBG && dbg != nullptr && blockIdx.x == 0 && row == 0 && part == 0;
 #define RDST_TSTAMP()                                                         \
@@ -361,6 +363,8 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
           o[cc * 4 + q] = pk2(fmaf(f.x, rstd, nb), fmaf(f.y, rstd, nb));
         }
       }
+      // pad channels 60, 61 (zero weights in every real row) carry the ones of the folded qkv bias
+      if (g4 == 7 / NCQ) o[(7 % NCQ) * 4 + 2] = 0x3F803F80u;
       RDST_TSTAMP();   // P1b loaded
       const uint32_t dst = lane_addr + K::TM_XH + g4 * NCQ * 4;
 #pragma unroll
@@ -385,7 +389,28 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     __syncthreads();
     RDST_TSTAMP();   // P1b done
     if (issuer_warp) {
-      if (tile == (int)blockIdx.x) mbar_wait(&bars[7], 0);     // weights have landed (first tile only)
+      if (tile == (int)blockIdx.x) {
+        mbar_wait(&bars[7], 0);     // weights have landed (first tile only)
+        // fold the biases into the resident images: K rows 60/61 of this slot's qkv heads, spare K rows of proj
+#pragma unroll 1
+        for (int hh = slot_u; hh < 6; hh += 2)
+          for (int n = lane; n < NH; n += 32)
+            *reinterpret_cast<uint32_t*>(smem + K::OFF_WQKV + hh * (NH * CP * 2) + (7 * NH + n) * 16 + 8) = bias_hi_lo(bqkv[hh * NH + n]);
+        if (slot_u == 0) {
+          for (int n = lane; n < CP; n += 32) {
+            const uint32_t hl = bias_hi_lo(bproj[n]);
+            uint8_t* wp = smem + K::OFF_WPROJ;
+            if (C_ == 60) *reinterpret_cast<uint32_t*>(wp + (1 * CP + n) * 16 + 4) = hl;            // k = 10, 11
+            else if (C_ == 120) *reinterpret_cast<uint32_t*>(wp + (15 * CP + n) * 16) = hl;         // k = 120, 121
+            else {                                                                                   // k = 15, 31
+              *reinterpret_cast<uint16_t*>(wp + (1 * CP + n) * 16 + 14) = (uint16_t)(hl & 0xFFFFu);
+              *reinterpret_cast<uint16_t*>(wp + (3 * CP + n) * 16 + 14) = (uint16_t)(hl >> 16);
+            }
+          }
+        }
+        fence_proxy_async();
+        __syncwarp();
+      }
       fence_after_sync();
       if (elect_one()) issue_qkv(slot_u);
       __syncwarp();
@@ -422,7 +447,6 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
       mbar_wait(bar_q, ph_q & 1); ph_q++;
       fence_after_sync();
       {
-        const float* bq = sBqkv + h * NH;
         if (part == 0) {
           // q -> packed bf16 back into the consumed accumulator columns (A operand of S), k -> K-major image
           constexpr int NC = (2 * HD + 7) / 8 * 8;
@@ -432,7 +456,7 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 #pragma unroll
           for (int e = 0; e < K::HDP / 2; ++e) {
             const int d0 = 2 * e, d1 = d0 + 1;
-            qp[e] = pk2(d0 < HD ? f[d0] + bq[d0] : 0.f, d1 < HD ? f[d1] + bq[d1] : 0.f);
+            qp[e] = pk2(d0 < HD ? f[d0] : 0.f, d1 < HD ? f[d1] : 0.f);
           }
 #pragma unroll
           for (int c0 = 0; c0 < K::HDP / 2; c0 += 8) {
@@ -443,7 +467,7 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
           }
 #pragma unroll
           for (int c8 = 0; c8 < (HD + 7) / 8; ++c8)
-            *reinterpret_cast<uint4*>(sBk + c8 * 2048 + row * 16) = pack8<HD, HD, false>(f, bq, c8);
+            *reinterpret_cast<uint4*>(sBk + c8 * 2048 + row * 16) = pack8<HD, HD, false>(f, c8);
           if (!K::DBUF && i == 0) {       // the raw tile landed here: re-zero the K-dim pad chunks of the image
 #pragma unroll
             for (int c8 = (HD + 7) / 8; c8 < K::HDP / 8; ++c8)
@@ -459,7 +483,7 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
           if (i > 0) mbar_wait(bar_o, (ph_o - 1) & 1);        // PV of the previous head has finished reading V
 #pragma unroll
           for (int c8 = 0; c8 < (HD + 8) / 8; ++c8)
-            *reinterpret_cast<uint4*>(sBv + c8 * 2048 + row * 16) = pack8<2 * HD - C0, HD, true, true>(f, bq + C0, c8);
+            *reinterpret_cast<uint4*>(sBv + c8 * 2048 + row * 16) = pack8<2 * HD - C0, HD, true, true>(f, c8);
           if (!K::DBUF && i == 0) {
 #pragma unroll
             for (int c8 = (HD + 8) / 8; c8 < K::HDV / 8; ++c8)
@@ -584,6 +608,9 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
             const int d0 = 2 * e, d1 = d0 + 1;
             a[e] = pk2(d0 < HD ? f[d0] * inv : 0.f, d1 < HD ? f[d1] * inv : 0.f);
           }
+          // ones of the folded proj bias: C=60 k = 10, 11 (head 0); C=90 k = 15 and 31 (heads 0, 1)
+          if (C_ == 60 && h == 0) a[5] = 0x3F803F80u;
+          if (C_ == 90 && h < 2) a[7] = (a[7] & 0xFFFFu) | 0x3F800000u;
           tmem_st_x8(lane_addr + K::TM_XH + 8 * h, a);
         } else {   // HDO == 20: 10 columns per head
           uint32_t a[8], b[2];
@@ -596,7 +623,7 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
         }
       }
       if (K::HDO == 20 && g4 == 3) {      // K pad of proj (elements 120..127): must be finite; weights there are zero
-        uint32_t zz[4] = {0, 0, 0, 0};
+        uint32_t zz[4] = {0x3F803F80u, 0, 0, 0};            // k = 120, 121: ones of the folded proj bias
         tmem_st_x4(lane_addr + K::TM_XH + 60, zz);
       }
       wait_st();
@@ -642,8 +669,7 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
           const float2 xf = up2(xw[e]);
-          o[e] = pk2(__uint_as_float(v[2 * e]) + sBproj[cb + c0 + 2 * e] + xf.x,
-                     __uint_as_float(v[2 * e + 1]) + sBproj[cb + c0 + 2 * e + 1] + xf.y);
+          o[e] = pk2(__uint_as_float(v[2 * e]) + xf.x, __uint_as_float(v[2 * e + 1]) + xf.y);
         }
         *reinterpret_cast<uint4*>(xp) = make_uint4(o[0], o[1], o[2], o[3]);
       }

@@ -91,6 +91,14 @@ __device__ __forceinline__ uint32_t mlp_xt_off(int row, int c) {
   return (uint32_t)((c >> 3) * (128 * 128) + row * 128 + (((c & 7) ^ (row & 7)) << 4));
 }
 
+// b1 rides inside fc1: x-hat carries ones at pad channels 60/61 and rows 60/61 of the resident W1 image hold b1 as a
+// bf16 hi/lo pair (error <= 2^-17 |b1|), patched once per CTA
+__device__ __forceinline__ uint32_t mlp_bias_hi_lo(float b) {
+  const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+  return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+}
+
 // store 8 packed columns held in a larger register array
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* v) {
   uint32_t a[8];
@@ -121,7 +129,6 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   __shared__ uint64_t xbar[2];          // raw tile landed, one per buffer
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  float* sB1 = reinterpret_cast<float*>(smem + C::OFF_B1);
   float* sB2 = reinterpret_cast<float*>(smem + C::OFF_B2);
   float2* sXch = reinterpret_cast<float2*>(smem + C::OFF_XCH);
 
@@ -140,7 +147,6 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       bulk_g2s(smem + C::OFF_W2 + off, w2img + off, min(32768, C::W2_BYTES - off), &bars[5]);
     if (TAIL) bulk_g2s(smem + C::OFF_WT, ta.wtimg, C::WT_BYTES, &bars[5]);
   }
-  for (int i = tid; i < HP; i += MLP_THREADS) sB1[i] = b1[i];
   for (int i = tid; i < CP; i += MLP_THREADS) sB2[i] = b2[i];
   if (TAIL) {
     for (int i = tid; i < 32; i += MLP_THREADS) reinterpret_cast<float*>(smem + C::OFF_BT)[i] = ta.bt[i];
@@ -192,8 +198,9 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     if (buf == 0) { mbar_wait(&xbar[0], ph_x0 & 1); ph_x0++; } else { mbar_wait(&xbar[1], ph_x1 & 1); ph_x1++; }
     // ---------------- P1: one pass over the landed rows: partial LayerNorm sums -> exchange -> A operand in TMEM ------
     constexpr int NCQ = C::NCH / 4;                           // 16-byte chunks per thread (2, 3 or 4)
-    uint4 rv[NCQ];
+    float fv[NCQ * 8];
     {
+      uint4 rv[NCQ];
 #pragma unroll
       for (int cc = 0; cc < NCQ; ++cc) rv[cc] = *reinterpret_cast<const uint4*>(sXT + mlp_xt_off(row, qtr * NCQ + cc));
       float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
@@ -203,6 +210,7 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const float2 f = unpack_bf16x2(w4[q]);
+          fv[cc * 8 + 2 * q] = f.x; fv[cc * 8 + 2 * q + 1] = f.y;     // unpacked once, normalised from registers
           s0 += f.x; s1 += f.y;
           q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
         }
@@ -219,14 +227,8 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       const float nb = -mean * rstd;
       uint32_t o[NCQ * 4];
 #pragma unroll
-      for (int cc = 0; cc < NCQ; ++cc) {
-        const uint32_t w4[4] = {rv[cc].x, rv[cc].y, rv[cc].z, rv[cc].w};
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float2 f = unpack_bf16x2(w4[q]);
-          o[cc * 4 + q] = pack_bf16x2(fmaf(f.x, rstd, nb), fmaf(f.y, rstd, nb));
-        }
-      }
+      for (int e = 0; e < NCQ * 4; ++e) o[e] = pack_bf16x2(fmaf(fv[2 * e], rstd, nb), fmaf(fv[2 * e + 1], rstd, nb));
+      if (qtr == 7 / NCQ) o[(7 % NCQ) * 4 + 2] = 0x3F803F80u;      // ones at pad channels 60, 61 (folded fc1 bias)
       const uint32_t dst = lane_addr + C::TM_XH + qtr * NCQ * 4;
 #pragma unroll
       for (int c0 = 0; c0 + 8 <= NCQ * 4; c0 += 8) tmem_st8(dst + c0, o + c0);
@@ -241,7 +243,13 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     RDST_TSTAMP();   // P1b done
     // ---------------- P2: fc1 (two N-halves), A from TMEM ----------------
     if (warp_u == 0) {
-      if (tile == (int64_t)blockIdx.x) mbar_wait(&bars[5], 0);  // weights have landed (first tile only)
+      if (tile == (int64_t)blockIdx.x) {
+        mbar_wait(&bars[5], 0);  // weights have landed (first tile only)
+        for (int n = lane; n < HP; n += 32)
+          *reinterpret_cast<uint32_t*>(smem + C::OFF_W1 + (7 * HP + n) * 16 + 8) = mlp_bias_hi_lo(b1[n]);
+        fence_proxy_async();
+        __syncwarp();
+      }
       fence_after_sync();
       if (elect_one()) {
         constexpr uint32_t id0 = make_idesc_bf16(128, C::H0, false, false);
@@ -297,8 +305,7 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
             uint32_t o[4];
 #pragma unroll
             for (int j = 0; j < 4; ++j)
-              o[j] = gelu_pair<EXACT>(__uint_as_float(v[q * 8 + 2 * j]) + sB1[c0 + 2 * j],
-                                      __uint_as_float(v[q * 8 + 2 * j + 1]) + sB1[c0 + 2 * j + 1]);
+              o[j] = gelu_pair<EXACT>(__uint_as_float(v[q * 8 + 2 * j]), __uint_as_float(v[q * 8 + 2 * j + 1]));
             tmem_st_x4(lane_addr + C::TM_HID + c0 / 2, o);
           }
       }
