@@ -591,13 +591,11 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
       __syncwarp();
     }
     {
-      // the three heads of a slot are split between its two warpgroups: part 0 takes two heads, part 1 one
+      // The three heads of a slot are split evenly between its two warpgroups: part 0 takes head `slot`, part 1 head
+      // `slot+4`, and the columns of head `slot+2` are shared (part 0 the first 16 values, part 1 the rest).
       constexpr int NCO = (HD + 8) / 8 * 8;      // head_dim values + the row-sum column
-#pragma unroll
-      for (int ii = 0; ii < 2; ++ii) {
-        const int i = part == 0 ? ii : 2;
-        if (part == 1 && ii == 1) break;
-        const int h = slot + 2 * i;
+      {
+        const int h = slot + 4 * part;
         float f[NCO];
         tmem_load_cols<NCO>(lane_addr + K::TM_O + h * K::HDV, f);
         const float inv = 1.0f / f[HD];             // softmax row sum, accumulated by the PV MMA (ones column of V)
@@ -620,6 +618,49 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
           b[1] = pk2(f[18] * inv, f[19] * inv);
           tmem_st_x8(lane_addr + K::TM_XH + 10 * h, a);
           tmem_st_x2(lane_addr + K::TM_XH + 10 * h + 8, b);
+        }
+      }
+      {
+        const int h = slot + 2;
+        const uint32_t src = lane_addr + K::TM_O + h * K::HDV;
+        if (K::HDO == 16) {
+          // values 0..7 -> part 0, values 8..15 -> part 1; the row sum (column HD >= 8) sits in the second chunk
+          uint32_t lo[8], hi[8];
+          if (part == 0) tmem_ld_x8(src, lo);
+          tmem_ld_x8(src + 8, hi);
+          wait_ld();
+          const float inv = 1.0f / __uint_as_float(hi[HD - 8]);
+          uint32_t a[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const int d0 = 8 + 2 * e, d1 = d0 + 1;
+            const float v0 = part == 0 ? __uint_as_float(lo[2 * e]) : (d0 < HD ? __uint_as_float(hi[2 * e]) : 0.f);
+            const float v1 = part == 0 ? __uint_as_float(lo[2 * e + 1]) : (d1 < HD ? __uint_as_float(hi[2 * e + 1]) : 0.f);
+            a[e] = pk2(v0 * inv, v1 * inv);
+          }
+          tmem_st_x4(lane_addr + K::TM_XH + 8 * h + 4 * part, a);
+        } else {
+          // values 0..15 -> part 0 (8 packed columns), values 16..19 -> part 1 (2 packed columns); row sum at column 20
+          uint32_t t4[4];
+          tmem_ld_x4(src + 20, t4);
+          if (part == 0) {
+            uint32_t v[16];
+            tmem_ld_x16(src, v);
+            wait_ld();
+            const float inv = 1.0f / __uint_as_float(t4[0]);
+            uint32_t a[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) a[e] = pk2(__uint_as_float(v[2 * e]) * inv, __uint_as_float(v[2 * e + 1]) * inv);
+            tmem_st_x8(lane_addr + K::TM_XH + 10 * h, a);
+          } else {
+            uint32_t v[4];
+            tmem_ld_x4(src + 16, v);
+            wait_ld();
+            const float inv = 1.0f / __uint_as_float(t4[0]);
+            uint32_t b[2] = {pk2(__uint_as_float(v[0]) * inv, __uint_as_float(v[1]) * inv),
+                             pk2(__uint_as_float(v[2]) * inv, __uint_as_float(v[3]) * inv)};
+            tmem_st_x2(lane_addr + K::TM_XH + 10 * h + 8, b);
+          }
         }
       }
       if (K::HDO == 20 && g4 == 3) {      // K pad of proj (elements 120..127): must be finite; weights there are zero
