@@ -238,11 +238,19 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
   uint64_t* bar_q_u = &bars[slot_u];
   uint64_t* bar_s_u = &bars[2 + slot_u];
   uint64_t* bar_o_u = &bars[4 + slot_u];
+  // debug buffer pointer, low 3 bits = mode: 0 = every phase of the first two tiles of CTA 0; 1 = start / landed stamps
+  // of every tile of the middle CTA (whole-launch timeline)
+  const int dbg_mode = DBG ? (int)(reinterpret_cast<uintptr_t>(dbg) & 7) : 0;
+  dbg = reinterpret_cast<unsigned long long*>(reinterpret_cast<uintptr_t>(dbg) & ~(uintptr_t)7);
   int dbg_n = 0;
-  const bool dbg_on = DBG && dbg != nullptr && blockIdx.x == 0 && row == 0 && part == 0;
+  const bool dbg_on = DBG && dbg != nullptr && blockIdx.x == (dbg_mode ? gridDim.x / 2 : 0) && row == 0 && part == 0;
 #define RDST_TSTAMP()                                                         \
   do {                                                                        \
-    if (DBG && dbg_on && dbg_n < 64) dbg[slot * 64 + dbg_n++] = clock64();    \
+    if (DBG && dbg_on && dbg_mode == 0 && dbg_n < 64) dbg[slot * 64 + dbg_n++] = clock64();    \
+  } while (0)
+#define RDST_TSTAMP_TILE()                                                    \
+  do {                                                                        \
+    if (DBG && dbg_on && dbg_mode == 1 && dbg_n < 64) dbg[slot * 64 + dbg_n++] = clock64();    \
   } while (0)
 
   auto issue_qkv = [&](int h) {      // one elected lane of the slot's issuer warp; h is warp-uniform
@@ -315,8 +323,10 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     // partial sum / sum of squares -> exchange between the four threads of a row -> normalise from registers ->
     // packed bf16 A operand of the qkv MMAs in TMEM.  (Pad channels are zero and add nothing to either sum.)
     RDST_TSTAMP();   // tile start
+    RDST_TSTAMP_TILE();
     if (buf == 0) { mbar_wait(&xbar[0], ph_x0 & 1); ph_x0++; } else { mbar_wait(&xbar[1], ph_x1 & 1); ph_x1++; }
     RDST_TSTAMP();   // tile landed
+    RDST_TSTAMP_TILE();
     constexpr int NCQ = K::NCH / 4;                           // 16-byte chunks per thread (2, 3 or 4)
     uint4 rv[NCQ];
     {
@@ -726,7 +736,9 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     }
     RDST_TSTAMP();   // tile done
   }
+  RDST_TSTAMP_TILE();    // kernel end
 #undef RDST_TSTAMP
+#undef RDST_TSTAMP_TILE
   if (tma_warp) {
     if (elect_one()) bulk_wait_read();
     __syncwarp();
