@@ -192,7 +192,8 @@ int rdst_conv3x3_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, const
 
 /* Final reconstruction conv (64 stored channels -> 1) on tcgen05 (N padded to 16), fp32 NCHW image out,
  * add_mean folded: img = (conv + bias) * out_scale + out_bias.
- *   wimg : 9 taps of a K-major operand image [8][16][8] bf16, row 0 = the real filter, rows 1..15 zero.
+ *   wimg : one K-major operand image [8][16][8] bf16 whose rows are the 9 filter taps (row t = w[t][0:64], rows 9..15
+ *          zero): the kernel computes the per-position tap products on the tensor core and the 9-point sum on CUDA cores.
  * Same contract as rdst_last_conv_fwd with Cin = 64.  Replaces tail[-1] + add_mean (rdst_variations.py:1303,1358). */
 int rdst_last_conv_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, float bias, float out_scale,
                                float out_bias, float* img, int B, int H, int W, void* stream);

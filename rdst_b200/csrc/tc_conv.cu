@@ -229,6 +229,160 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
   if (warp == 0) tmem_dealloc<K::TMEM_COLS>(tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// Final 64 -> 1 convolution as a "tap GEMM": P[pos][tap] = sum_c x[pos][c] * w[tap][c] for every staged halo position
+// (one K = 64 GEMM with the 9 taps as N, padded to 16: 8 MMAs per tile instead of the 36 of the implicit-GEMM form,
+// which spent the tensor pipe on 15 zero output columns and was bound by its A reads), then the 9-point sum
+// out[y][x] = sum_tap P[(y+dy, x+dx)][tap] on the CUDA cores from shared memory.  HBM-bound: 128 B read per pixel.
+// ------------------------------------------------------------------------------------------------------------------
+struct LastCfg {
+  static constexpr int NCH = 8;
+  static constexpr int W_BYTES = 64 * 16 * 2;                        // [8][16 taps][8] bf16
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_A = W_BYTES;
+  static constexpr int NSTAGE = 3;                                   // halo tiles in flight (two tiles of loads outstanding)
+  // staging buffers and the tap-product array are sized by the actual number of staged positions NP (<= CONV_NP_MAX)
+  __host__ __device__ static constexpr int a_bytes(int np) { return NCH * np * 16; }
+  __host__ __device__ static constexpr int off_p(int np) { return OFF_A + NSTAGE * a_bytes(np); }     // [9][NP] fp32 tap products
+  __host__ __device__ static constexpr int smem(int np) { return off_p(np) + 9 * np * 4; }
+  static constexpr int TMEM_COLS = 64;                               // 2 accumulator sets x 2 position blocks x 16 taps
+};
+
+__global__ void __launch_bounds__(CONV_THREADS)
+last_conv_tap_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_t* __restrict__ wimg,
+                     float* __restrict__ img, ConvGeom g) {
+  using K = LastCfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar[2];
+  __shared__ uint64_t wbar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  uint8_t* sW = smem + K::OFF_W;
+  uint8_t* sA = smem + K::OFF_A;
+  const int a_bytes = K::a_bytes(g.NP);
+  float* sP = reinterpret_cast<float*>(smem + K::off_p(g.NP));
+
+  if (warp == 0) tmem_alloc<K::TMEM_COLS>(&tmem_base_s);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_init(&wbar, 1);
+    fence_mbar_init();
+    mbar_arrive_expect_tx(&wbar, K::W_BYTES);
+    bulk_g2s(sW, wimg, K::W_BYTES, &wbar);
+  }
+  for (int i = tid; i < K::NSTAGE * a_bytes / 16; i += CONV_THREADS) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
+  const uint32_t lboA = (uint32_t)g.NP * 16;
+  const int nps = (g.TH + 2) * g.LW;                       // staged halo positions (>= 128 for every tile shape)
+  const int blk1 = nps - 128;                              // second (overlapping) block of 128 positions
+  const int row = tid & 127, part = tid >> 7;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int64_t ntiles = (int64_t)g.B * g.nty * g.ntx;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+
+  auto stage = [&](int64_t tile, int buf) {      // always commits a (possibly empty) group: uniform group counting
+    if (warp >= 8 || tile >= ntiles) { cp_async_commit(); return; }
+    const int b = (int)(tile / (g.nty * g.ntx));
+    const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
+    const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
+    uint8_t* dst = sA + (size_t)buf * a_bytes;
+#pragma unroll 1
+    for (int pg = warp; pg * 8 < nps; pg += 8) {
+      const int pos = pg * 8 + (lane & 7);
+      if (pos >= nps) continue;
+      const int hy = pos / g.LW, hx = pos - hy * g.LW;
+      const int y = y0 - 1 + hy, x = x0 - 1 + hx;
+      const bool ok = y >= 0 && y < g.H && x >= 0 && x < g.W;
+      const __nv_bfloat16* src = X + (ok ? (((int64_t)b * g.H + y) * g.W + x) * ldx : 0);
+#pragma unroll
+      for (int j = 0; j < K::NCH / 4; ++j)
+        cp_async16(dst + (size_t)((lane >> 3) + 4 * j) * lboA + pos * 16, reinterpret_cast<const uint4*>(src) + (lane >> 3) + 4 * j,
+                   ok ? 16u : 0u);
+    }
+    cp_async_commit();
+  };
+  auto issue = [&](int sbuf, int buf) {        // warp 8, one elected lane: staging buffer sbuf -> accumulator set buf
+    constexpr uint32_t idesc = make_idesc_bf16(128, 16, false, false);
+    const uint32_t ab = aA + sbuf * a_bytes;
+#pragma unroll
+    for (int blk = 0; blk < 2; ++blk) {
+      const uint32_t a0 = ab + (uint32_t)(blk ? blk1 : 0) * 16;
+#pragma unroll
+      for (int ks = 0; ks < 4; ++ks)
+        mma_bf16_ss(tmem_u + buf * 32 + blk * 16, make_smem_desc(a0 + ks * 2 * lboA, lboA, 128),
+                    make_smem_desc(aW + ks * 2 * (16 * 16), 16 * 16, 128), idesc, ks > 0);
+    }
+    commit(&bar[buf]);
+  };
+
+  pdl_launch_dependents();
+  pdl_wait();
+  int buf = 0, sbuf = 0;
+  uint32_t par0 = 0, par1 = 0;
+  stage(blockIdx.x, 0);
+  stage((int64_t)blockIdx.x + gridDim.x, 1);
+  if ((int64_t)blockIdx.x < ntiles) {
+    cp_async_wait_group<1>();
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();
+    if (warp_u == 8) {
+      mbar_wait(&wbar, 0);
+      fence_after_sync();
+      if (elect_one()) issue(0, 0);
+      __syncwarp();
+    }
+  }
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1, sbuf = (sbuf + 1) % K::NSTAGE) {
+    const int b = (int)(tile / (g.nty * g.ntx));
+    const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
+    const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
+    const int64_t next = tile + gridDim.x;
+    stage(next + gridDim.x, (sbuf + 2) % K::NSTAGE);      // two tiles ahead; that buffer fed tile-1's MMAs (complete)
+    if (buf == 0) { mbar_wait(&bar[0], par0); par0 ^= 1; } else { mbar_wait(&bar[1], par1); par1 ^= 1; }
+    cp_async_wait_group<1>();                             // the next tile's halo has landed
+    fence_proxy_async();
+    fence_before_sync();
+    __syncthreads();          // next halo tile staged; previous tile's 9-point sums have read sP
+    fence_after_sync();
+    if (next < ntiles && warp_u == 8) {
+      if (elect_one()) issue((sbuf + 1) % K::NSTAGE, buf ^ 1);
+      __syncwarp();
+    }
+    if (warp < 8) {           // tap products of this thread's position -> shared memory, tap-major
+      uint32_t v[16];
+      tmem_ld_x16(lane_addr + buf * 32 + part * 16, v);
+      wait_ld();
+      const int pos = part ? blk1 + row : row;
+#pragma unroll
+      for (int t = 0; t < 9; ++t) sP[t * g.NP + pos] = __uint_as_float(v[t]);
+    }
+    fence_before_sync();
+    __syncthreads();
+    if (tid < 128) {
+      const int oy = row / g.LW, ox = row - oy * g.LW;
+      const int y = y0 + oy, x = x0 + ox;
+      if (ox < g.TW && oy < g.TH && y < g.H && x < g.W) {
+        float acc = 0.f;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) acc += sP[t * g.NP + row + (t / 3) * g.LW + (t % 3)];
+        img[((int64_t)b * g.H + y) * g.W + x] = acc * g.out_scale + g.out_bias;
+      }
+    }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<K::TMEM_COLS>(tmem);
+}
+
 static unsigned long long* g_conv_dbg = nullptr;
 
 template <int CIN, int NT>
@@ -283,8 +437,23 @@ extern "C" int rdst_last_conv_fwd_bf16_tc(const void* x, int64_t ldx, const void
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   g.out_bias = out_bias + bias * out_scale;      // scalar conv bias folded into the output affine (no device read)
-  int rc = launch_conv<64, 16>(x, ldx, wimg, nullptr, nullptr, 0, (void*)img, 0, g, 1, sms, (cudaStream_t)stream);
-  if (rc) return rc;
+  {
+    using K = LastCfg;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int smem_bytes = K::smem(g.NP);
+    cudaError_t e = cudaFuncSetAttribute(last_conv_tap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::smem(CONV_NP_MAX));
+    if (e != cudaSuccess) { set_error("rdst_last_conv_fwd_bf16_tc: smem attr: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
+    int occ = (int)(232448 / (smem_bytes + 2048));
+    if (occ > 512 / K::TMEM_COLS) occ = 512 / K::TMEM_COLS;
+    if (occ > 4) occ = 4;
+    if (occ < 1) occ = 1;
+    const int64_t ntiles = (int64_t)g.B * g.nty * g.ntx;
+    int64_t gx = (int64_t)occ * sms;
+    if (gx > ntiles) gx = ntiles;
+    e = launch_pdl(last_conv_tap_kernel, dim3((unsigned)gx), dim3(CONV_THREADS), (size_t)smem_bytes, st,
+                   (const __nv_bfloat16*)x, ldx, (const uint8_t*)wimg, img, g);
+    if (e != cudaSuccess) { set_error("rdst_last_conv_fwd_bf16_tc: launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
+  }
   RDST_CHECK_LAUNCH("rdst_last_conv_fwd_bf16_tc");
   return RDST_OK;
 }

@@ -172,6 +172,9 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uin
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+// all but the N most recently committed groups of this thread have landed
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Programmatic dependent launch: let the next kernel of the stream start its prologue early / wait for the producer
 __device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }

@@ -216,10 +216,8 @@ def conv_tc_image(w):
 
 
 def last_conv_tc_image(w9):
-    """[9][64] fp32 filter of the final 64->1 conv -> 9 taps x [8][16][8] bf16 (row 0 real, rows 1..15 zero)."""
-    parts = []
-    for tap in range(9):
-        m = w9.new_zeros(16, w9.shape[1])
-        m[0] = w9[tap]
-        parts.append(kmajor_image(m))
-    return torch.cat(parts).contiguous()
+    """[9][64] fp32 filter of the final 64->1 conv -> one K-major image [8][16][8] bf16 whose rows are the 9 taps
+    (rows 9..15 zero): B operand of the tap GEMM P[pos][tap] = x[pos] . w[tap] (tc_conv.cu, last_conv_tap_kernel)."""
+    m = w9.new_zeros(16, w9.shape[1])
+    m[:9] = w9
+    return kmajor_image(m).contiguous()
