@@ -383,6 +383,191 @@ last_conv_tap_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uin
   if (warp == 0) tmem_dealloc<K::TMEM_COLS>(tmem);
 }
 
+
+// ------------------------------------------------------------------------------------------------------------------
+// LFF (Cin = 160 -> 64) on CTA pairs.  The 9 x 160 x 64 filter (184 KB) does not fit one SM next to the halo tiles; the
+// single-CTA kernel therefore splits N over two CTAs and every CTA re-reads the whole A image for 32 output columns
+// (the MMAs are bound by the 4 KB/k-step A read).  Here two CTAs of a cluster run ONE tcgen05.mma.cta_group::2 per
+// k-step: M = 256 = the two CTAs' own 128-position tiles, N = 64 with each CTA holding 32 columns of B -- every A
+// byte is read once for all 64 output columns.  Leader (cluster rank 0) issues, completion is multicast to both.
+// ------------------------------------------------------------------------------------------------------------------
+struct PairCfg {
+  static constexpr int CIN = 160, NT = 32, NOUT = 64;
+  static constexpr int NCH = CIN / 8;
+  static constexpr int W_BYTES = 9 * CIN * NT * 2;               // this CTA's half of the filter
+  static constexpr int A_BYTES = NCH * CONV_NP_MAX * 16;
+  static constexpr int OFF_W = 0;
+  static constexpr int OFF_A = W_BYTES;
+  static constexpr int OFF_BIAS = OFF_A + 2 * A_BYTES;
+  static constexpr int SMEM = OFF_BIAS + NOUT * 4;
+  static constexpr int TMEM_COLS = 128;                           // two accumulators of 64 columns
+};
+
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS)
+conv3x3_pair_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_t* __restrict__ wimg,
+                    const float* __restrict__ bias, const __nv_bfloat16* __restrict__ R, int64_t ldr,
+                    __nv_bfloat16* __restrict__ Y, int64_t ldy, ConvGeom g) {
+  using K = PairCfg;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar[2];
+  __shared__ uint64_t wbar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int rank = (int)cluster_ctarank();
+  uint8_t* sW = smem + K::OFF_W;
+  uint8_t* sA = smem + K::OFF_A;
+  float* sBias = reinterpret_cast<float*>(smem + K::OFF_BIAS);
+
+  if (warp == 0) tmem_alloc_pair<K::TMEM_COLS>(&tmem_base_s);
+  if (tid == 0) {
+    mbar_init(&bar[0], 1);
+    mbar_init(&bar[1], 1);
+    mbar_init(&wbar, 1);
+    fence_mbar_init();
+    const uint8_t* src = wimg + (size_t)rank * K::W_BYTES;
+    mbar_arrive_expect_tx(&wbar, K::W_BYTES);
+    for (int off = 0; off < K::W_BYTES; off += 32768) bulk_g2s(sW + off, src + off, min(32768, K::W_BYTES - off), &wbar);
+  }
+  for (int i = tid; i < 2 * K::A_BYTES / 16; i += CONV_THREADS) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+  for (int i = tid; i < K::NOUT; i += CONV_THREADS) sBias[i] = bias[i];
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
+  const uint32_t lboA = (uint32_t)g.NP * 16;
+  const int nps = (g.TH + 2) * g.LW;
+  const int row = tid & 127, part = tid >> 7;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int64_t ntiles = (int64_t)g.B * g.nty * g.ntx;
+  const int64_t npairs = (ntiles + 1) / 2;
+  const int64_t cid = blockIdx.x >> 1, ncl = gridDim.x >> 1;
+  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
+  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+  const bool leader = rank == 0;
+
+  auto stage = [&](int64_t tile, int buf) {
+    if (warp >= 8 || tile >= ntiles) { cp_async_commit(); return; }
+    const int b = (int)(tile / (g.nty * g.ntx));
+    const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
+    const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
+    uint8_t* dst = sA + (size_t)buf * K::A_BYTES;
+#pragma unroll 1
+    for (int pg = warp; pg * 8 < nps; pg += 8) {
+      const int pos = pg * 8 + (lane & 7);
+      if (pos >= nps) continue;
+      const int hy = pos / g.LW, hx = pos - hy * g.LW;
+      const int y = y0 - 1 + hy, x = x0 - 1 + hx;
+      const bool ok = y >= 0 && y < g.H && x >= 0 && x < g.W;
+      const __nv_bfloat16* src = X + (ok ? (((int64_t)b * g.H + y) * g.W + x) * ldx : 0);
+#pragma unroll
+      for (int j = 0; j < K::NCH / 4; ++j)
+        cp_async16(dst + (size_t)((lane >> 3) + 4 * j) * lboA + pos * 16, reinterpret_cast<const uint4*>(src) + (lane >> 3) + 4 * j,
+                   ok ? 16u : 0u);
+    }
+    cp_async_commit();
+  };
+  auto issue = [&](int buf) {        // leader CTA, warp 8, one elected lane
+    constexpr uint32_t idesc = make_idesc_bf16(256, K::NOUT, false, false);
+    const uint32_t ab = aA + buf * K::A_BYTES;
+    const uint32_t acc = tmem_u + buf * K::NOUT;
+#pragma unroll 1
+    for (int tap = 0; tap < 9; ++tap) {
+      const uint32_t a0 = ab + (uint32_t)((tap / 3) * g.LW + (tap % 3)) * 16;
+      const uint32_t w0 = aW + tap * (K::CIN * K::NT * 2);
+#pragma unroll
+      for (int ks = 0; ks < K::CIN / 16; ++ks)
+        mma_bf16_ss_pair(acc, make_smem_desc(a0 + ks * 2 * lboA, lboA, 128),
+                         make_smem_desc(w0 + ks * 2 * (K::NT * 16), K::NT * 16, 128), idesc, (tap | ks) > 0);
+    }
+    commit_pair(&bar[buf]);
+  };
+
+  pdl_launch_dependents();
+  pdl_wait();
+  int buf = 0;
+  uint32_t par0 = 0, par1 = 0;
+  stage(2 * cid + rank, 0);
+  cp_async_wait_all();
+  if (warp_u == 8) mbar_wait(&wbar, 0);          // this CTA's half of the filter has landed
+  fence_proxy_async();
+  fence_before_sync();
+  cluster_sync();                                // both halo tiles staged, both filter halves resident
+  fence_after_sync();
+  if (cid < npairs && leader && warp_u == 8) {
+    if (elect_one()) issue(0);
+    __syncwarp();
+  }
+  for (int64_t pr = cid; pr < npairs; pr += ncl, buf ^= 1) {
+    const int64_t tile = 2 * pr + rank;
+    const bool have = tile < ntiles;
+    const int b = (int)(tile / (g.nty * g.ntx));
+    const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
+    const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
+    const int64_t npr = pr + ncl;
+    stage(2 * npr + rank, buf ^ 1);              // in flight under the MMAs of the current pair
+    if (buf == 0) { mbar_wait(&bar[0], par0); par0 ^= 1; } else { mbar_wait(&bar[1], par1); par1 ^= 1; }
+    cp_async_wait_all();
+    fence_proxy_async();
+    fence_before_sync();
+    cluster_sync();           // both CTAs: next halo tiles staged, other accumulator drained
+    fence_after_sync();
+    if (npr < npairs && leader && warp_u == 8) {
+      if (elect_one()) issue(buf ^ 1);
+      __syncwarp();
+    }
+    if (warp >= 8 || !have) continue;
+    const uint32_t acc_addr = lane_addr + buf * K::NOUT;
+    const int oy = row / g.LW, ox = row - oy * g.LW;
+    const int y = y0 + oy, x = x0 + ox;
+    const bool ok = ox < g.TW && oy < g.TH && y < g.H && x < g.W;
+    constexpr int NC = K::NOUT / 2;                        // columns per thread
+    const int cb = part * NC;
+    const int64_t tout = ((int64_t)b * g.H + y) * g.W + x;
+#pragma unroll
+    for (int c0 = 0; c0 < NC; c0 += 16) {
+      uint32_t v[16];
+      tmem_ld_x16(acc_addr + cb + c0, v);
+      wait_ld();
+      if (ok) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = (__uint_as_float(v[j]) + sBias[cb + c0 + j]) * g.out_scale;
+        if (R != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(R + tout * ldr + cb + c0);
+          const uint4 r0 = __ldg(rp), r1 = __ldg(rp + 1);
+          const uint32_t rw[8] = {r0.x, r0.y, r0.z, r0.w, r1.x, r1.y, r1.z, r1.w};
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float2 t = cup2(rw[j]); f[2 * j] += t.x; f[2 * j + 1] += t.y; }
+        }
+        uint4* yp = reinterpret_cast<uint4*>(Y + tout * ldy + cb + c0);
+        yp[0] = make_uint4(cpk2(f[0], f[1]), cpk2(f[2], f[3]), cpk2(f[4], f[5]), cpk2(f[6], f[7]));
+        yp[1] = make_uint4(cpk2(f[8], f[9]), cpk2(f[10], f[11]), cpk2(f[12], f[13]), cpk2(f[14], f[15]));
+      }
+    }
+  }
+  fence_before_sync();
+  cluster_sync();             // the peer's tensor core may still be reading this CTA's shared memory / TMEM
+  if (warp == 0) tmem_dealloc_pair<K::TMEM_COLS>(tmem);
+}
+
+static int launch_conv_pair(const void* x, int64_t ldx, const void* wimg, const float* bias, const void* r, int64_t ldr,
+                            void* y, int64_t ldy, ConvGeom g, int sms, cudaStream_t st) {
+  using K = PairCfg;
+  cudaError_t e = cudaFuncSetAttribute(conv3x3_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM);
+  if (e != cudaSuccess) { set_error("rdst_conv3x3_fwd_bf16_tc: smem attr (%d B): %s", K::SMEM, cudaGetErrorString(e)); return RDST_E_CUDA; }
+  const int64_t ntiles = (int64_t)g.B * g.nty * g.ntx;
+  const int64_t npairs = (ntiles + 1) / 2;
+  int64_t ncl = sms / 2;
+  if (ncl > npairs) ncl = npairs;
+  if (ncl < 1) ncl = 1;
+  e = launch_pdl(conv3x3_pair_kernel, dim3((unsigned)(2 * ncl)), dim3(CONV_THREADS), (size_t)K::SMEM, st,
+                 (const __nv_bfloat16*)x, ldx, (const uint8_t*)wimg, bias, (const __nv_bfloat16*)r, ldr, (__nv_bfloat16*)y, ldy, g);
+  if (e != cudaSuccess) { set_error("rdst_conv3x3_fwd_bf16_tc (pair): launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
+  return RDST_OK;
+}
+
 static unsigned long long* g_conv_dbg = nullptr;
 
 template <int CIN, int NT>
@@ -492,7 +677,8 @@ extern "C" int rdst_conv3x3_fwd_bf16_tc(const void* x, int64_t ldx, const void* 
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  if (Cin == 160) rc = launch_conv<160, 32>(x, ldx, wimg, bias, resid, ldr, y, ldy, g, 2, sms, st);
+  if (Cin == 160) rc = g_conv_dbg ? launch_conv<160, 32>(x, ldx, wimg, bias, resid, ldr, y, ldy, g, 2, sms, st)
+                                  : launch_conv_pair(x, ldx, wimg, bias, resid, ldr, y, ldy, g, sms, st);
   else if (N == 256) rc = launch_conv<64, 128>(x, ldx, wimg, bias, resid, ldr, y, ldy, g, 2, sms, st);
   else rc = launch_conv<64, 64>(x, ldx, wimg, bias, resid, ldr, y, ldy, g, 1, sms, st);
   if (rc) return rc;
