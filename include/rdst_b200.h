@@ -185,7 +185,9 @@ int rdst_stl_attn_fwd_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, con
  * shapes of the network: (Cin,N) = (160,64) LFF, (64,64) conv_after_body, (64,256)+shuffle=2 up-sampler.
  *   wimg : N/NT slices (NT = 32 when Cin == 160, 128 when N == 256, else 64), each 9 taps of a K-major operand image [Cin/8][NT][8] bf16
  *          built from the [N][9][Cin] weight of rdst_conv3x3_fwd (tap = ky*3+kx).
- * The halo tile is staged once in shared memory; the nine taps are descriptor offsets into that image. */
+ * The halo tile is staged once in shared memory; the nine taps are descriptor offsets into that image.
+ * (160,64) runs on CTA pairs (tcgen05.mma.cta_group::2, M = 256): the two 32-column slices of wimg are the two
+ * CTAs' halves of the B operand.  y must be 32-byte aligned with ldy a multiple of 16 elements (256-bit stores). */
 int rdst_conv3x3_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, const float* bias, const void* resid,
                              int64_t ldr, void* y, int64_t ldy, int B, int H, int W, int Cin, int N,
                              float out_scale, int shuffle, void* stream);

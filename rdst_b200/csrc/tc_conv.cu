@@ -18,6 +18,13 @@ __device__ __forceinline__ uint32_t cpk2(float a, float b) {
   __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
   return *reinterpret_cast<uint32_t*>(&v);
 }
+// 32 contiguous bytes (16 bf16 channels) in one 256-bit store: a full sector per lane
+__device__ __forceinline__ void st_global_256(void* p, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t a4,
+                                              uint32_t a5, uint32_t a6, uint32_t a7) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(p), "r"(a0), "r"(a1), "r"(a2), "r"(a3),
+               "r"(a4), "r"(a5), "r"(a6), "r"(a7)
+               : "memory");
+}
 __device__ __forceinline__ float2 cup2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
@@ -215,9 +222,8 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
 #pragma unroll
             for (int j = 0; j < 8; ++j) { const float2 t = cup2(rw[j]); f[2 * j] += t.x; f[2 * j + 1] += t.y; }
           }
-          uint4* yp = reinterpret_cast<uint4*>(Y + tout * ldy + ncol0 + c0);
-          yp[0] = make_uint4(cpk2(f[0], f[1]), cpk2(f[2], f[3]), cpk2(f[4], f[5]), cpk2(f[6], f[7]));
-          yp[1] = make_uint4(cpk2(f[8], f[9]), cpk2(f[10], f[11]), cpk2(f[12], f[13]), cpk2(f[14], f[15]));
+          st_global_256(Y + tout * ldy + ncol0 + c0, cpk2(f[0], f[1]), cpk2(f[2], f[3]), cpk2(f[4], f[5]), cpk2(f[6], f[7]),
+                        cpk2(f[8], f[9]), cpk2(f[10], f[11]), cpk2(f[12], f[13]), cpk2(f[14], f[15]));
         }
       }
     }
@@ -541,9 +547,8 @@ conv3x3_pair_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint
 #pragma unroll
           for (int j = 0; j < 8; ++j) { const float2 t = cup2(rw[j]); f[2 * j] += t.x; f[2 * j + 1] += t.y; }
         }
-        uint4* yp = reinterpret_cast<uint4*>(Y + tout * ldy + cb + c0);
-        yp[0] = make_uint4(cpk2(f[0], f[1]), cpk2(f[2], f[3]), cpk2(f[4], f[5]), cpk2(f[6], f[7]));
-        yp[1] = make_uint4(cpk2(f[8], f[9]), cpk2(f[10], f[11]), cpk2(f[12], f[13]), cpk2(f[14], f[15]));
+        st_global_256(Y + tout * ldy + cb + c0, cpk2(f[0], f[1]), cpk2(f[2], f[3]), cpk2(f[4], f[5]), cpk2(f[6], f[7]),
+                      cpk2(f[8], f[9]), cpk2(f[10], f[11]), cpk2(f[12], f[13]), cpk2(f[14], f[15]));
       }
     }
   }
@@ -658,6 +663,8 @@ extern "C" int rdst_conv3x3_fwd_bf16_tc(const void* x, int64_t ldx, const void* 
                    (resid == nullptr || (((uintptr_t)resid % 16 == 0) && ldr % 8 == 0)),
                "rdst_conv3x3_fwd_bf16_tc: pointers must be 16-byte aligned, strides multiples of 8 elements");
   RDST_REQUIRE(ldx >= Cin, "rdst_conv3x3_fwd_bf16_tc: ldx < Cin");
+  RDST_REQUIRE(((uintptr_t)y % 32 == 0) && ldy % 16 == 0,
+               "rdst_conv3x3_fwd_bf16_tc: y must be 32-byte aligned with a row stride multiple of 16 elements (256-bit stores)");
   if (B == 0) return RDST_OK;
   ConvGeom g{};
   g.B = B; g.H = H; g.W = W; g.shuffle = shuffle; g.out_scale = out_scale;
