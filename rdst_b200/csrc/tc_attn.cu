@@ -440,13 +440,15 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 #pragma unroll
       for (int cc = 0; cc < NCQ; ++cc) *reinterpret_cast<uint4*>(sXT + xt_off(row, g4 * NCQ + cc)) = rv[cc];
     }
-    // shift mask of this thread's 32 keys: bit j set = key belongs to another region (edge windows only)
+    // Shift mask (edge windows only).  The region borders of calculate_mask (:321-341) cut a window at row / column 4,
+    // i.e. exactly between the 4x4 TMA boxes that define the row order: the region id is constant inside a box, so the
+    // mask of this thread's 32 keys is two values, one per key box (keys 0..15 and 16..31 of its half).
     const int myreg = sReg[row];
-    uint32_t mbits = 0;
+    __half2 mk0 = __float2half2_rn(0.f), mk1 = mk0;
     if (myreg >= 0) {
       const int* rg = sReg + 64 * wsel + 32 * part;
-#pragma unroll
-      for (int j = 0; j < 32; ++j) mbits |= (rg[j] != myreg) ? (1u << j) : 0u;
+      if (rg[0] != myreg) mk0 = __float2half2_rn(mask_val);
+      if (rg[16] != myreg) mk1 = __float2half2_rn(mask_val);
     }
 
     // ---------------- heads of this slot ----------------
@@ -541,12 +543,8 @@ stl_attn_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
                           *reinterpret_cast<const __half2*>(&bp));
         }
         if (myreg >= 0) {
-          const __half hm = __float2half_rn(mask_val);
-          const __half hz = __float2half_rn(0.f);
 #pragma unroll
-          for (int j = 0; j < 16; ++j)
-            if ((mbits >> (2 * j)) & 3u)
-              hv[j] = __hadd2(hv[j], __halves2half2((mbits >> (2 * j)) & 1u ? hm : hz, (mbits >> (2 * j + 1)) & 1u ? hm : hz));
+          for (int j = 0; j < 16; ++j) hv[j] = __hadd2(hv[j], j < 8 ? mk0 : mk1);
         }
         __half2 m2[4] = {hv[0], hv[1], hv[2], hv[3]};
 #pragma unroll

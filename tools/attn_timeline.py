@@ -25,6 +25,10 @@ def run():
               _lib.ptr(pk["bqkv_tc"]), _lib.ptr(bp), _lib.ptr(pk["table_tc"]), B, H, W, c, shift, _lib.stream_ptr())
 for _ in range(3): run()
 torch.cuda.synchronize()
+flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device="cuda")
+if os.environ.get("RDST_COLD"):
+    flush.fill_(1)          # evict x / y / weights from L2: the launch below starts cold
+    torch.cuda.synchronize()
 import ctypes; _lib.call("rdst_debug_attn_timing", ctypes.c_void_p(dbg.data_ptr() + 1))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record(); run(); e1.record(); torch.cuda.synchronize()
@@ -40,4 +44,10 @@ print(f"  end {d[-1] - t0}")
 e0.record()
 for _ in range(20): run()
 e1.record(); torch.cuda.synchronize()
-print(f"production build: {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per launch")
+print(f"production build, back to back (warm L2): {e0.elapsed_time(e1) / 20 * 1e3:.1f} us per launch")
+tot = 0.0
+for _ in range(10):
+    flush.fill_(1)
+    e0.record(); run(); e1.record(); torch.cuda.synchronize()
+    tot += e0.elapsed_time(e1)
+print(f"production build, L2 flushed before each launch: {tot / 10 * 1e3:.1f} us per launch")
