@@ -57,8 +57,8 @@ __device__ __forceinline__ uint32_t gelu_pair(float a, float b) {
 template <int CP, int HP>
 struct MlpCfg {
   static constexpr int NCH = CP / 8;                      // 16-byte chunks per activation row
-  static constexpr int H0 = (HP / 2 + 15) / 16 * 16;      // fc1 N-half 0 (== fc2 K-half 0)
-  static constexpr int H1 = HP - H0;
+  static constexpr int NCHK = (HP + 63) / 64;             // fc1 N-chunks (== fc2 K-chunks) of 64 hidden units
+  static constexpr int LASTW = HP - 64 * (NCHK - 1);      // width of the last chunk (64 or 48)
   static constexpr int W1_BYTES = HP * CP * 2;
   static constexpr int W2_BYTES = CP * HP * 2;
   static constexpr int NP = CP > 64 ? 2 : 1;              // raw tile: 64-channel panels [128 rows][128 B], SWIZZLE_128B
@@ -81,7 +81,7 @@ struct MlpCfg {
   static constexpr int TM_FC2 = 256;                       // fc2 accumulator [256,256+CP)
   static constexpr int TM_XH = 256;                        // normalised input [256,256+CP/2): dead before fc2 starts (in-order MMAs)
   static constexpr int TM_HID = 384;                       // GELU(hidden) packed [384,384+HP/2)
-  static_assert(HP % 16 == 0 && CP % 32 == 0 && H1 % 16 == 0 && H1 > 0, "tile shape");
+  static_assert(HP % 16 == 0 && CP % 32 == 0 && LASTW % 16 == 0 && LASTW > 0 && NCHK <= 4, "tile shape");
   static_assert(HP <= 240 && CP <= 128 && TM_HID + HP / 2 <= 512, "TMEM budget");
   static_assert(OFF_XT % 1024 == 0, "raw tiles must be 1024-byte aligned (SWIZZLE_128B)");
 };
@@ -125,7 +125,7 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
                unsigned long long* __restrict__ dbg) {
   using C = MlpCfg<CP, HP>;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bars[6];          // [0,1] fc1 halves, [2,3] fc2 halves, [4] tail, [5] weights landed
+  __shared__ uint64_t bars[8];          // [0..3] fc1 chunks, [4] fc2, [5] tail, [6] weights landed
   __shared__ uint64_t xbar[2];          // raw tile landed, one per buffer
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -134,18 +134,18 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) {
-    for (int i = 0; i < 6; ++i) mbar_init(&bars[i], 1);
+    for (int i = 0; i < 8; ++i) mbar_init(&bars[i], 1);
     mbar_init(&xbar[0], 1);
     mbar_init(&xbar[1], 1);
     fence_mbar_init();
     // resident weights (ready-made operand images) arrive by bulk async copies that overlap the prologue and the
-    // first tile's load + LayerNorm; the issuer waits on bars[5] once before its first tcgen05.mma
-    mbar_arrive_expect_tx(&bars[5], C::W1_BYTES + C::W2_BYTES + (TAIL ? C::WT_BYTES : 0));
+    // first tile's load + LayerNorm; the issuer waits on bars[6] once before its first tcgen05.mma
+    mbar_arrive_expect_tx(&bars[6], C::W1_BYTES + C::W2_BYTES + (TAIL ? C::WT_BYTES : 0));
     for (int off = 0; off < C::W1_BYTES; off += 32768)
-      bulk_g2s(smem + C::OFF_W1 + off, w1img + off, min(32768, C::W1_BYTES - off), &bars[5]);
+      bulk_g2s(smem + C::OFF_W1 + off, w1img + off, min(32768, C::W1_BYTES - off), &bars[6]);
     for (int off = 0; off < C::W2_BYTES; off += 32768)
-      bulk_g2s(smem + C::OFF_W2 + off, w2img + off, min(32768, C::W2_BYTES - off), &bars[5]);
-    if (TAIL) bulk_g2s(smem + C::OFF_WT, ta.wtimg, C::WT_BYTES, &bars[5]);
+      bulk_g2s(smem + C::OFF_W2 + off, w2img + off, min(32768, C::W2_BYTES - off), &bars[6]);
+    if (TAIL) bulk_g2s(smem + C::OFF_WT, ta.wtimg, C::WT_BYTES, &bars[6]);
   }
   for (int i = tid; i < CP; i += MLP_THREADS) sB2[i] = b2[i];
   if (TAIL) {
@@ -181,6 +181,27 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 #pragma unroll
     for (int pnl = 0; pnl < C::NP; ++pnl)
       tma::load_4d(smem + C::OFF_XT + b * C::XT_BYTES + pnl * C::PANEL, &mapX, pnl * 64, (int)(tile * 128), 0, 0, &xbar[b]);
+  };
+  // fc1 runs in 64-column chunks (the last one may be 48 wide), each committed to its own mbarrier, so the GELU of
+  // chunk c starts while the tensor pipe works on chunk c+1; fc2 accumulates over the same chunks as K-slices.
+  // tcgen05.mma issue blocks while the tensor-pipe queue is full, so at most two chunks are queued ahead and the
+  // issuing warp rotates (an issuer that also owns token rows would otherwise be late for every barrier).
+  // All fc1 chunks are issued before the first fc2 chunk: the fc2 accumulator aliases the normalised input.
+  auto issue_fc1 = [&](int c) {
+    constexpr uint32_t idw = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idl = make_idesc_bf16(128, C::LASTW, false, false);
+#pragma unroll
+    for (int ks = 0; ks < CP / 16; ++ks)
+      mma_ts(tmem_u + C::TM_FC1 + 64 * c, tmem_u + C::TM_XH + ks * 8,
+             make_smem_desc(aW1 + 64 * c * 16 + ks * 2 * (HP * 16), HP * 16, 128), c == C::NCHK - 1 ? idl : idw, ks > 0);
+    commit(&bars[c]);
+  };
+  auto issue_fc2 = [&](int c) {
+    constexpr uint32_t id2 = make_idesc_f16(128, CP, false, false);       // hidden and W2 are fp16
+    const int ks0 = 4 * c, ks1 = c == C::NCHK - 1 ? HP / 16 : 4 * c + 4;
+    for (int ks = ks0; ks < ks1; ++ks)
+      mma_ts(tmem_u + C::TM_FC2, tmem_u + C::TM_HID + ks * 8, make_smem_desc(aW2 + ks * 2 * (CP * 16), CP * 16, 128), id2, ks > 0);
+    if (c == C::NCHK - 1) commit(&bars[4]);
   };
   pdl_launch_dependents();
   pdl_wait();                    // prologue above touched only weights; the rows below come from the previous kernel
@@ -244,7 +265,7 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
     // ---------------- P2: fc1 (two N-halves), A from TMEM ----------------
     if (warp_u == 0) {
       if (tile == (int64_t)blockIdx.x) {
-        mbar_wait(&bars[5], 0);  // weights have landed (first tile only)
+        mbar_wait(&bars[6], 0);  // weights have landed (first tile only)
         for (int n = lane; n < HP; n += 32)
           *reinterpret_cast<uint32_t*>(smem + C::OFF_W1 + (7 * HP + n) * 16 + 8) = mlp_bias_hi_lo(b1[n]);
         fence_proxy_async();
@@ -252,17 +273,8 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       }
       fence_after_sync();
       if (elect_one()) {
-        constexpr uint32_t id0 = make_idesc_bf16(128, C::H0, false, false);
-        constexpr uint32_t id1 = make_idesc_bf16(128, C::H1, false, false);
-#pragma unroll
-        for (int ks = 0; ks < CP / 16; ++ks)
-          mma_ts(tmem_u + C::TM_FC1, tmem_u + C::TM_XH + ks * 8, make_smem_desc(aW1 + ks * 2 * (HP * 16), HP * 16, 128), id0, ks > 0);
-        commit(&bars[0]);
-#pragma unroll
-        for (int ks = 0; ks < CP / 16; ++ks)
-          mma_ts(tmem_u + C::TM_FC1 + C::H0, tmem_u + C::TM_XH + ks * 8,
-                 make_smem_desc(aW1 + C::H0 * 16 + ks * 2 * (HP * 16), HP * 16, 128), id1, ks > 0);
-        commit(&bars[1]);
+        issue_fc1(0);
+        if (C::NCHK > 1) issue_fc1(1);
       }
       __syncwarp();
     }
@@ -273,11 +285,11 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       }
       __syncwarp();
     }
-    // ---------------- P3: GELU epilogue per half -> packed fp16 hidden in TMEM; fc2 K-half issued behind it ----------------
+    // ---------------- P3: GELU epilogue per chunk -> packed fp16 hidden in TMEM; fc2 K-chunk issued behind it ----------------
 #pragma unroll
-    for (int h = 0; h < 2; ++h) {
-      const int hbase = h == 0 ? 0 : C::H0;
-      const int hw = h == 0 ? C::H0 : C::H1;
+    for (int h = 0; h < C::NCHK; ++h) {
+      const int hbase = 64 * h;
+      const int hw = h == C::NCHK - 1 ? C::LASTW : 64;
       const int qw = (hw / 4 + 7) / 8 * 8;                     // columns per quarter (multiple of 8), last one may be short
       const int cbeg = hbase + min(qtr * qw, hw);
       const int cend = hbase + min((qtr + 1) * qw, hw);
@@ -287,7 +299,7 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       RDST_TSTAMP();   // fc1 half ready
       {
         // all accumulator columns of this thread are requested up front (one wait), then GELU -> packed hidden
-        constexpr int MAXC = 32;
+        constexpr int MAXC = 16;
         uint32_t v[MAXC];
 #pragma unroll
         for (int q = 0; q < MAXC / 8; ++q)
@@ -313,22 +325,25 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       RDST_TSTAMP();   // GELU half done
       fence_before_sync();
       __syncthreads();
-      if (warp_u == 0) {
+      if (warp_u == 1 + 4 * h) {            // rotating issuer: warps 1, 5, 9, 13
         fence_after_sync();
         if (elect_one()) {
-          constexpr uint32_t id2 = make_idesc_f16(128, CP, false, false);       // hidden and W2 are fp16
-          const int ks0 = hbase / 16, ks1 = (hbase + hw) / 16;
-          for (int ks = ks0; ks < ks1; ++ks)
-            mma_ts(tmem_u + C::TM_FC2, tmem_u + C::TM_HID + ks * 8, make_smem_desc(aW2 + ks * 2 * (CP * 16), CP * 16, 128), id2, ks > 0);
-          commit(&bars[2 + h]);
+          if (h + 2 < C::NCHK) issue_fc1(h + 2);
+          if (h >= C::NCHK - 3) {             // every fc1 chunk has been issued: fc2 K-slices of the finished chunks
+            if (h == C::NCHK - 3 || (C::NCHK < 3 && h == 0)) {
+#pragma unroll
+              for (int c2 = 0; c2 <= h; ++c2) issue_fc2(c2);
+            } else {
+              issue_fc2(h);
+            }
+          }
         }
         __syncwarp();
       }
     }
     // ---------------- P5: fc2 epilogue in the row mapping: y = acc + b2 + x (raw tile) ----------------
     RDST_TSTAMP();   // before fc2 wait
-    mbar_wait(&bars[2], parity);
-    mbar_wait(&bars[3], parity);
+    mbar_wait(&bars[4], parity);
     fence_after_sync();
     RDST_TSTAMP();   // fc2 ready
     {
@@ -399,11 +414,11 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
 #pragma unroll
           for (int ks = 0; ks < CP / 16; ++ks)
             mma_ts(tmem_u + C::TM_FC1, tmem_u + C::TM_XH + ks * 8, make_smem_desc(aWT + ks * 2 * (32 * 16), 32 * 16, 128), idt, ks > 0);
-          commit(&bars[4]);
+          commit(&bars[5]);
         }
         __syncwarp();
       }
-      mbar_wait(&bars[4], parity);
+      mbar_wait(&bars[5], parity);
       fence_after_sync();
       {
         // each quarter writes 8 of the 32 growth columns of its row (16 bytes)

@@ -19,8 +19,11 @@ run = lambda: _lib.call("rdst_stl_mlp_fwd_bf16", _lib.ptr(x), cp, _lib.ptr(y), c
                         _lib.ptr(d[3]), T, c, 0, _lib.stream_ptr())
 run(); torch.cuda.synchronize()
 _lib.call("rdst_debug_mlp_timing", _lib.ptr(dbg)); run(); torch.cuda.synchronize(); _lib.call("rdst_debug_mlp_timing", None)
-names = ["tile start", "P1a done", "P1b done", "before fc1[0] wait", "fc1[0] ready", "GELU[0] done", "before fc1[1] wait", "fc1[1] ready",
-         "GELU[1] done", "before fc2 wait", "fc2 ready", "P5 done", "tile done"]
+nchk = (hp + 63) // 64
+names = ["tile start", "P1a done", "P1b done"]
+for k in range(nchk):
+    names += [f"before fc1[{k}] wait", f"fc1[{k}] ready", f"GELU[{k}] done"]
+names += ["before fc2 wait", "fc2 ready", "P5 done", "tile done"]
 t = dbg.cpu().tolist()
 for half in range(2):
     print(f"--- warpgroup {half} (C={c})")
