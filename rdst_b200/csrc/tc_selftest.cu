@@ -91,7 +91,9 @@ __global__ void __launch_bounds__(128) umma_selftest_kernel(const __nv_bfloat16*
     }
     commit(&bar);
   } else if (tid == 0) {
-    const uint32_t idesc = make_idesc_bf16(m64 ? 64 : 128, N, false, b_mn_major != 0);
+    // m64 == 4: fp16 accumulators (c_format = F16): the raw TMEM columns are dumped, two fp16 values per column
+    const uint32_t idesc = m64 == 4 ? (make_idesc_f16(128, N, false, b_mn_major != 0) & ~(3u << 4))     // A/B are fp16 bit patterns
+                                    : make_idesc_bf16(m64 ? 64 : 128, N, false, b_mn_major != 0);
     for (int ks = 0; ks < K / 16; ++ks) {
       const uint64_t da = make_smem_desc(smem_u32(sA) + ks * 2 * 2048, 2048, 128);
       uint64_t db;
