@@ -1,8 +1,8 @@
 """Training path: forward with saved activations + hand-written backward over librdst_b200 kernels (fp32).
 
-The whole network is ONE torch.autograd.Function.  Its tensor inputs are the *packed* weights
-(rdst_b200/packing.py run in differentiable mode: LayerNorm folding, q scaling, padded scatter are ordinary torch ops
-on the 4.5 M parameters), so autograd carries the gradients of the packed tensors back to the reference-named
+The network is a chain of torch.autograd.Functions (head, one per RDSTB, tail).  Their tensor inputs are the *packed*
+weights (rdst_b200/packing.py run in differentiable mode: LayerNorm folding, q scaling, padded scatter are ordinary
+torch ops on the 4.5 M parameters), so autograd carries the gradients of the packed tensors back to the reference-named
 parameters; every activation-sized computation, forward and backward, is a kernel of the C ABI:
     data gradients     rdst_linear_fwd / rdst_conv3x3_fwd with transposed (and tap-flipped) weights
     weight gradients   rdst_gemm_tn_acc (token reduction, optional 3x3 gather) incl. bias column sums
@@ -65,42 +65,68 @@ def axpy(x, y, N, alpha=1.0):
     _call("rdst_axpy", _p(x), _ld(x), _p(y), _ld(y), x.shape[0], N, alpha, _lib.stream_ptr())
 
 
+def linear_t(dy, w, dx, K, N, scale=1.0):
+    """Data gradient of a Linear: dx[T][N] = scale * dy[T][K] . w[K][N]   (w is the forward weight [out=K][in=N])."""
+    linear(dy, w.t().contiguous(), torch.zeros(N, dtype=torch.float32, device=dy.device), dx, K, N, scale=scale)
+
+
 def conv_dgrad_weight(w):
     """[N][9][Cin] forward filter -> [Cin][9][N] filter of the data gradient (taps flipped)."""
     return w.flip(1).permute(2, 1, 0).contiguous()
 
 
 # ------------------------------------------------------------------------------------------------ packed weights
-def train_weights(m, device):
-    """Differentiable packed weights as a flat list + a spec to rebuild the nested structure."""
+def _adder(flat):
+    def add(t):
+        flat.append(t.contiguous())
+        return len(flat) - 1
+    return add
+
+
+def pack_block(m, blk, device):
+    """Differentiable packed weights of one RDSTB: flat tensor list + spec (indices into the list)."""
+    flat = []
+    add = _adder(flat)
     with packing.differentiable():
-        flat, spec = [], {"blocks": []}
+        bs = {"dstl": []}
+        c = packing.EMBED
+        for dstl in blk.body:
+            stls = []
+            for b in dstl.body.blocks:
+                p = packing.pack_stl(b, c)
+                stls.append({k: add(p[k]) for k in ("wqkv", "bqkv", "wproj", "bproj", "w1", "b1", "w2", "b2", "table")}
+                            | {"c": c, "cp": p["cp"], "hp": p["hp"], "shift": b.shift_size})
+            t = packing.pack_dstl_tail(dstl, c, m.dense_scale)
+            bs["dstl"].append({"c": c, "stl": stls, "tw": add(t["w"]), "tb": add(t["b"]), "scale": t["scale"]})
+            c += packing.GROWTH
+        pos = packing.channel_positions(c, device)
+        w, b = packing.pack_conv(blk.conv.weight, blk.conv.bias, pos, packing.DENSE_LD, 64)
+        bs["lff_w"], bs["lff_b"] = add(w), add(b)
+    bs["res_scale"] = float(m.rdb_residual_scale)
+    return flat, bs
 
-        def add(t):
-            flat.append(t.contiguous())
-            return len(flat) - 1
 
-        for blk in m.body:
-            bs = {"dstl": []}
-            c = packing.EMBED
-            for dstl in blk.body:
-                stls = []
-                for b in dstl.body.blocks:
-                    p = packing.pack_stl(b, c)
-                    stls.append({k: add(p[k]) for k in ("wqkv", "bqkv", "wproj", "bproj", "w1", "b1", "w2", "b2", "table")}
-                                | {"c": c, "cp": p["cp"], "hp": p["hp"], "shift": b.shift_size})
-                t = packing.pack_dstl_tail(dstl, c, m.dense_scale)
-                bs["dstl"].append({"c": c, "stl": stls, "tw": add(t["w"]), "tb": add(t["b"]), "scale": t["scale"]})
-                c += packing.GROWTH
-            pos = packing.channel_positions(c, device)
-            w, b = packing.pack_conv(blk.conv.weight, blk.conv.bias, pos, packing.DENSE_LD, 64)
-            bs["lff_w"], bs["lff_b"] = add(w), add(b)
-            spec["blocks"].append(bs)
-        id60 = torch.arange(60, device=device)
+def pack_head(m, device):
+    flat = []
+    add = _adder(flat)
+    with packing.differentiable():
         f = packing._f
-        spec["head_w"] = add(f(m.head.weight).reshape(60, 9))
-        spec["head_b"] = add(f(m.head.bias))
-        spec["pe_g"], spec["pe_b"] = add(f(m.patch_embed.norm.weight)), add(f(m.patch_embed.norm.bias))
+        hw = torch.zeros(64, 9, 16, device=device)
+        hw[:60, :, 0] = f(m.head.weight).reshape(60, 9)
+        hb = torch.zeros(64, device=device)
+        hb[:60] = f(m.head.bias)
+        spec = {"head_w": add(hw), "head_b": add(hb),
+                "pe_g": add(f(m.patch_embed.norm.weight)), "pe_b": add(f(m.patch_embed.norm.bias))}
+    return flat, spec
+
+
+def pack_tail(m, device):
+    flat = []
+    add = _adder(flat)
+    spec = {}
+    with packing.differentiable():
+        f = packing._f
+        id60 = torch.arange(60, device=device)
         spec["norm_g"], spec["norm_b"] = add(f(m.norm.weight)), add(f(m.norm.bias))
         w, b = packing.pack_conv(m.conv_after_body.weight, m.conv_after_body.bias, id60, 64, 64)
         spec["cab_w"], spec["cab_b"] = add(w), add(b)
@@ -113,97 +139,126 @@ def train_weights(m, device):
         lw = torch.zeros(1, 9, 64, device=device)
         lw[0, :, :60] = f(last.weight)[0].permute(1, 2, 0).reshape(9, 60)
         spec["last_w"], spec["last_b"] = add(lw), add(f(last.bias))
-    spec["scalars"] = dict(in_scale=float(m.sub_mean.weight.detach().reshape(-1)[0]),
-                           in_bias=float(m.sub_mean.bias.detach().reshape(-1)[0]),
-                           out_scale=float(m.add_mean.weight.detach().reshape(-1)[0]),
-                           out_bias=float(m.add_mean.bias.detach().reshape(-1)[0]),
-                           res_scale=float(m.rdb_residual_scale), grs=float(m.global_res_scale),
-                           flo=bool(m.feature_last_operation), sr=int(m.sr_scale))
     return flat, spec
 
 
-# ------------------------------------------------------------------------------------------------ the Function
-class RDSTFunction(torch.autograd.Function):
+def frozen_scalars(m):
+    """sub_mean / add_mean are frozen 1x1 convs (requires_grad False, reference common.py:151-167): their four numbers
+    are read once per buffer version (one host sync), never inside a step -> the step stays CUDA-graph capturable."""
+    key = tuple((t.data_ptr(), t._version) for t in (m.sub_mean.weight, m.sub_mean.bias, m.add_mean.weight, m.add_mean.bias))
+    cache = getattr(m, "_rdst_scalar_cache", None)
+    if cache is None or cache[0] != key:
+        vals = dict(in_scale=float(m.sub_mean.weight.detach().reshape(-1)[0]),
+                    in_bias=float(m.sub_mean.bias.detach().reshape(-1)[0]),
+                    out_scale=float(m.add_mean.weight.detach().reshape(-1)[0]),
+                    out_bias=float(m.add_mean.bias.detach().reshape(-1)[0]))
+        cache = (key, vals)
+        object.__setattr__(m, "_rdst_scalar_cache", cache)
+    return dict(cache[1], grs=float(m.global_res_scale), flo=bool(m.feature_last_operation), sr=int(m.sr_scale))
+
+
+# ------------------------------------------------------------------------------------------------ the Functions
+# The network is a chain of autograd.Functions -- head, one per RDSTB, tail -- and the (differentiable) weight
+# packing of each link is done right before the link runs.  In backward the autograd engine therefore finishes the
+# parameter gradients of RDSTB i (link backward, then its packing graph, then AccumulateGrad) before it starts
+# RDSTB i-1: gradient buckets become ready block by block and a data-parallel all-reduce (torch DDP, or
+# rdst_b200.ddp.BucketedAllReduce) overlaps with the rest of the backward pass.
+def _f32(dev):
+    return (lambda *s: torch.empty(*s, dtype=torch.float32, device=dev),
+            lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev))
+
+
+class HeadFunction(torch.autograd.Function):
+    """sub_mean -> head conv 1->60 -> patch_embed LayerNorm (rdst_variations.py:1344-1345, swin_transformer_sr.py:515-519).
+    Returns (F0 [T][64] head-conv output, X0 [T][64] normalised trunk)."""
+
     @staticmethod
-    def forward(ctx, spec, x, *W):
+    def forward(ctx, spec, sc, x, *W):
         dev = x.device
         B, _, H, Wd = x.shape
         T = B * H * Wd
-        sc = spec["scalars"]
-        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
-        saved = {"blocks": []}
+        e, z = _f32(dev)
         with torch.cuda.device(dev):
-            # head: conv 1->60 on a 16-channel padded image (generic conv kernel), then patch_embed LayerNorm
             img = z(T, 16)
             img[:, 0] = x.reshape(-1) * sc["in_scale"] + sc["in_bias"]
-            hw = z(64, 9, 16); hw[:60, :, 0] = W[spec["head_w"]]
-            hb = z(64); hb[:60] = W[spec["head_b"]]
             F0 = e(T, 64)
-            conv(img, hw, hb, F0, B, H, Wd, 16, 64)
-            D = z(T, 160)
-            _call("rdst_layernorm_fwd", _p(F0), 64, _p(W[spec["pe_g"]]), _p(W[spec["pe_b"]]), _p(D), 160, T, 60, 1.0, F32,
+            conv(img, W[spec["head_w"]], W[spec["head_b"]], F0, B, H, Wd, 16, 64)
+            X0 = z(T, 64)
+            _call("rdst_layernorm_fwd", _p(F0), 64, _p(W[spec["pe_g"]]), _p(W[spec["pe_b"]]), _p(X0), 64, T, 60, 1.0, F32,
                   _lib.stream_ptr())
-            saved["img"], saved["F0"] = img, F0
-            for bs in spec["blocks"]:
-                sb = {"D": D, "dstl": []}
-                for j, ds in enumerate(bs["dstl"]):
-                    c = ds["c"]
-                    src = D
-                    sl = []
-                    for st in ds["stl"]:
-                        cp, hp = st["cp"], st["hp"]
-                        qkv, o, x1, hid, act, y = e(T, 3 * c), e(T, c), e(T, cp), e(T, hp), e(T, hp), e(T, cp)
-                        linear(src, W[st["wqkv"]], W[st["bqkv"]], qkv, cp, 3 * c, ln_creal=c)
-                        _call("rdst_window_attention_fwd", _p(qkv), 3 * c, _p(W[st["table"]]), _p(o), c, B, H, Wd, c,
-                              packing.HEADS, st["shift"], F32, _lib.stream_ptr())
-                        linear(o, W[st["wproj"]], W[st["bproj"]], x1, c, cp, resid=src)
-                        linear(x1, W[st["w1"]], W[st["b1"]], hid, cp, hp, ln_creal=c)
-                        _call("rdst_gelu_fwd", _p(hid), hp, _p(act), hp, T, hp, _lib.stream_ptr())
-                        linear(act, W[st["w2"]], W[st["b2"]], y, hp, cp, resid=x1)
-                        sl.append(dict(x=src, qkv=qkv, o=o, x1=x1, hid=hid, y=y))
-                        del act
-                        src = y
-                    off = 64 + 32 * j
-                    linear(src, W[ds["tw"]], W[ds["tb"]], D[:, off:], ds["stl"][0]["cp"], 32, ln_creal=c, scale=ds["scale"])
-                    sb["dstl"].append(sl)
-                Dn = z(T, 160)
-                conv(D, W[bs["lff_w"]], W[bs["lff_b"]], Dn, B, H, Wd, 160, 64, scale=sc["res_scale"], resid=D)
-                saved["blocks"].append(sb)
-                D = Dn
-            saved["Dlast"] = D
-            FN = z(T, 64)
-            _call("rdst_layernorm_fwd", _p(D), 160, _p(W[spec["norm_g"]]), _p(W[spec["norm_b"]]), _p(FN), 64, T, 60,
-                  sc["grs"], F32, _lib.stream_ptr())
-            F1 = e(T, 64)
-            if sc["flo"]:
-                conv(FN, W[spec["cab_w"]], W[spec["cab_b"]], F1, B, H, Wd, 64, 64, resid=F0)
-            else:
-                F1.copy_(FN + F0)
-            saved["FN"] = FN
-            feats = [F1]
-            h, w_ = H, Wd
-            for wi, bi in spec["up"]:
-                up = e(B * 4 * h * w_, 64)
-                conv(feats[-1], W[wi], W[bi], up, B, h, w_, 64, 256, shuffle=2)
-                feats.append(up)
-                h, w_ = 2 * h, 2 * w_
-            saved["feats"] = feats
-            out = e(B * h * w_, 1)
-            conv(feats[-1], W[spec["last_w"]], W[spec["last_b"]], out, B, h, w_, 64, 1)
-            out = (out * sc["out_scale"] + sc["out_bias"]).reshape(B, 1, h, w_)
-        ctx.spec, ctx.saved, ctx.W, ctx.geom = spec, saved, W, (B, H, Wd)
-        return out
+        ctx.spec, ctx.W, ctx.geom, ctx.saved = spec, W, (B, H, Wd), (img, F0)
+        return F0, X0
 
     @staticmethod
-    def backward(ctx, dout):
-        spec, S, W = ctx.spec, ctx.saved, ctx.W
+    def backward(ctx, dF0, dX0):
+        spec, W = ctx.spec, ctx.W
         B, H, Wd = ctx.geom
         T = B * H * Wd
-        sc = spec["scalars"]
-        dev = dout.device
-        z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
-        e = lambda *s: torch.empty(*s, dtype=torch.float32, device=dev)
+        img, F0 = ctx.saved
+        dev = dX0.device
+        e, z = _f32(dev)
+        G = [None] * len(W)
+        with torch.cuda.device(dev):
+            dF = dF0.contiguous().clone()
+            dE = z(T, 64)
+            gg, gb = z(60), z(60)
+            _call("rdst_layernorm_bwd", _p(dX0.contiguous()), 64, _p(F0), 64, _p(W[spec["pe_g"]]), _p(dE), 64,
+                  _p(gg), _p(gb), T, 60, 1.0, _lib.stream_ptr())
+            G[spec["pe_g"]], G[spec["pe_b"]] = gg, gb
+            axpy(dE, dF, 60)
+            ghw, ghb = z(64, 9 * 16), z(64)
+            gemm_tn(dF, img, ghw, ghb, 64, 9 * 16, (B, H, Wd, 16))
+            G[spec["head_w"]], G[spec["head_b"]] = ghw.reshape(64, 9, 16), ghb
+        ctx.saved = None
+        return (None, None, None) + tuple(G)
+
+
+class BlockFunction(torch.autograd.Function):
+    """One RDSTB (rdst_variations.py:380-445): 3 DenseSTLayers on the [T][160] dense buffer, LFF conv + residual."""
+
+    @staticmethod
+    def forward(ctx, bs, geom, X, *W):
+        B, H, Wd = geom
+        T = B * H * Wd
+        dev = X.device
+        e, z = _f32(dev)
+        with torch.cuda.device(dev):
+            D = z(T, 160)
+            D[:, :64] = X
+            sb = []
+            for j, ds in enumerate(bs["dstl"]):
+                c = ds["c"]
+                src = D
+                sl = []
+                for st in ds["stl"]:
+                    cp, hp = st["cp"], st["hp"]
+                    qkv, o, x1, hid, act, y = e(T, 3 * c), e(T, c), e(T, cp), e(T, hp), e(T, hp), e(T, cp)
+                    linear(src, W[st["wqkv"]], W[st["bqkv"]], qkv, cp, 3 * c, ln_creal=c)
+                    _call("rdst_window_attention_fwd", _p(qkv), 3 * c, _p(W[st["table"]]), _p(o), c, B, H, Wd, c,
+                          packing.HEADS, st["shift"], F32, _lib.stream_ptr())
+                    linear(o, W[st["wproj"]], W[st["bproj"]], x1, c, cp, resid=src)
+                    linear(x1, W[st["w1"]], W[st["b1"]], hid, cp, hp, ln_creal=c)
+                    _call("rdst_gelu_fwd", _p(hid), hp, _p(act), hp, T, hp, _lib.stream_ptr())
+                    linear(act, W[st["w2"]], W[st["b2"]], y, hp, cp, resid=x1)
+                    sl.append(dict(x=src, qkv=qkv, o=o, x1=x1, hid=hid, y=y))
+                    del act
+                    src = y
+                off = 64 + 32 * j
+                linear(src, W[ds["tw"]], W[ds["tb"]], D[:, off:], ds["stl"][0]["cp"], 32, ln_creal=c, scale=ds["scale"])
+                sb.append(sl)
+            Xn = e(T, 64)
+            conv(D, W[bs["lff_w"]], W[bs["lff_b"]], Xn, B, H, Wd, 160, 64, scale=bs["res_scale"], resid=D)
+        ctx.bs, ctx.geom, ctx.W, ctx.saved = bs, geom, W, (D, sb)
+        return Xn
+
+    @staticmethod
+    def backward(ctx, dXn):
+        bs, W = ctx.bs, ctx.W
+        B, H, Wd = ctx.geom
+        T = B * H * Wd
+        D, sb = ctx.saved
+        dev = dXn.device
+        e, z = _f32(dev)
         G = [None] * len(W)
 
         def gz(i):
@@ -212,7 +267,87 @@ class RDSTFunction(torch.autograd.Function):
             return G[i]
 
         with torch.cuda.device(dev):
-            feats = S["feats"]
+            dX = dXn.contiguous()
+            dys = dX if bs["res_scale"] == 1.0 else dX * bs["res_scale"]
+            gemm_tn(dys, D, gz(bs["lff_w"]), gz(bs["lff_b"]), 64, 9 * 160, (B, H, Wd, 160))
+            dD = e(T, 160)
+            conv(dX, conv_dgrad_weight(W[bs["lff_w"]]), z(160), dD, B, H, Wd, 64, 160, scale=bs["res_scale"])
+            axpy(dX, dD, 64)                          # residual: block output = LFF(D) + D[:, :64]
+            for j in range(len(bs["dstl"]) - 1, -1, -1):
+                ds, sl = bs["dstl"][j], sb[j]
+                c = ds["c"]
+                cp = ds["stl"][0]["cp"]
+                off = 64 + 32 * j
+                dg = dD[:, off:off + 32]
+                y1 = sl[-1]["y"]
+                xh = e(T, cp)
+                lnhat(y1, xh, cp, c)
+                gw, gb = gz(ds["tw"]), gz(ds["tb"])
+                gemm_tn(dg, xh, gw, gb, 32, cp)
+                if ds["scale"] != 1.0:
+                    gw.mul_(ds["scale"]); gb.mul_(ds["scale"])
+                dxh = e(T, cp)
+                linear_t(dg, W[ds["tw"]], dxh, 32, cp, scale=ds["scale"])
+                dy_cur = e(T, cp)
+                lnhat_bwd(dxh, y1, dy_cur, cp, c)
+                del xh, dxh
+                for k in range(len(ds["stl"]) - 1, -1, -1):
+                    first = k == 0
+                    dy_cur = _stl_backward(ds["stl"][k], sl[k], W, gz, dy_cur, B, H, Wd,
+                                           accumulate_into=dD if first else None)
+            dXin = dD[:, :64].contiguous()
+        ctx.saved = None
+        return (None, None, dXin) + tuple(G)
+
+
+class TailFunction(torch.autograd.Function):
+    """final norm * global_res_scale -> conv_after_body + head skip -> UpSampler -> last conv -> add_mean
+    (rdst_variations.py:1337-1358)."""
+
+    @staticmethod
+    def forward(ctx, spec, sc, geom, X, F0, *W):
+        B, H, Wd = geom
+        T = B * H * Wd
+        dev = X.device
+        e, z = _f32(dev)
+        with torch.cuda.device(dev):
+            FN = z(T, 64)
+            _call("rdst_layernorm_fwd", _p(X), 64, _p(W[spec["norm_g"]]), _p(W[spec["norm_b"]]), _p(FN), 64, T, 60,
+                  sc["grs"], F32, _lib.stream_ptr())
+            F1 = e(T, 64)
+            if sc["flo"]:
+                conv(FN, W[spec["cab_w"]], W[spec["cab_b"]], F1, B, H, Wd, 64, 64, resid=F0)
+            else:
+                torch.add(FN, F0, out=F1)
+            feats = [F1]
+            h, w_ = H, Wd
+            for wi, bi in spec["up"]:
+                up = e(B * 4 * h * w_, 64)
+                conv(feats[-1], W[wi], W[bi], up, B, h, w_, 64, 256, shuffle=2)
+                feats.append(up)
+                h, w_ = 2 * h, 2 * w_
+            out = e(B * h * w_, 1)
+            conv(feats[-1], W[spec["last_w"]], W[spec["last_b"]], out, B, h, w_, 64, 1)
+            out = (out * sc["out_scale"] + sc["out_bias"]).reshape(B, 1, h, w_)
+        ctx.spec, ctx.sc, ctx.geom, ctx.W, ctx.saved = spec, sc, geom, W, (X, FN, feats)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        spec, sc, W = ctx.spec, ctx.sc, ctx.W
+        B, H, Wd = ctx.geom
+        T = B * H * Wd
+        X, FN, feats = ctx.saved
+        dev = dout.device
+        e, z = _f32(dev)
+        G = [None] * len(W)
+
+        def gz(i):
+            if G[i] is None:
+                G[i] = torch.zeros_like(W[i])
+            return G[i]
+
+        with torch.cuda.device(dev):
             n_up = len(spec["up"])
             h, w_ = H * (2 ** n_up), Wd * (2 ** n_up)
             # ---- last conv (64 -> 1) + add_mean ----
@@ -236,57 +371,15 @@ class RDSTFunction(torch.autograd.Function):
             dF0 = dF1.clone()
             dFN = e(T, 64)
             if sc["flo"]:
-                gemm_tn(dF1, S["FN"], gz(spec["cab_w"]), gz(spec["cab_b"]), 64, 9 * 64, (B, H, Wd, 64))
+                gemm_tn(dF1, FN, gz(spec["cab_w"]), gz(spec["cab_b"]), 64, 9 * 64, (B, H, Wd, 64))
                 conv(dF1, conv_dgrad_weight(W[spec["cab_w"]]), z(64), dFN, B, H, Wd, 64, 64)
             else:
                 dFN.copy_(dF1)
-            # ---- final norm ----
-            dX = z(T, 64)                                 # grad wrt the trunk (block output), pads zero
-            _call("rdst_layernorm_bwd", _p(dFN), 64, _p(S["Dlast"]), 160, _p(W[spec["norm_g"]]), _p(dX), 64,
+            dX = z(T, 64)                                 # grad wrt the trunk (last block output), pads zero
+            _call("rdst_layernorm_bwd", _p(dFN), 64, _p(X), 64, _p(W[spec["norm_g"]]), _p(dX), 64,
                   _p(gz(spec["norm_g"])), _p(gz(spec["norm_b"])), T, 60, sc["grs"], _lib.stream_ptr())
-            # ---- RDSTBs in reverse ----
-            for bs, sb in zip(reversed(spec["blocks"]), reversed(S["blocks"])):
-                D = sb["D"]
-                dys = dX if sc["res_scale"] == 1.0 else dX * sc["res_scale"]
-                gemm_tn(dys, D, gz(bs["lff_w"]), gz(bs["lff_b"]), 64, 9 * 160, (B, H, Wd, 160))
-                dD = e(T, 160)
-                conv(dX, conv_dgrad_weight(W[bs["lff_w"]]), z(160), dD, B, H, Wd, 64, 160, scale=sc["res_scale"])
-                axpy(dX, dD, 64)                          # residual: block output = LFF(D) + D[:, :64]
-                for j in range(len(bs["dstl"]) - 1, -1, -1):
-                    ds, sl = bs["dstl"][j], sb["dstl"][j]
-                    c = ds["c"]
-                    cp = ds["stl"][0]["cp"]
-                    off = 64 + 32 * j
-                    dg = dD[:, off:off + 32]
-                    y1 = sl[-1]["y"]
-                    xh = e(T, cp)
-                    lnhat(y1, xh, cp, c)
-                    gw, gb = z(32, cp), z(32)
-                    gemm_tn(dg, xh, gw, gb, 32, cp)
-                    gz(ds["tw"]).add_(gw, alpha=ds["scale"]); gz(ds["tb"]).add_(gb, alpha=ds["scale"])
-                    dxh = e(T, cp)
-                    linear(dg, W[ds["tw"]].t().contiguous(), z(cp), dxh, 32, cp, scale=ds["scale"])
-                    dy_cur = e(T, cp)
-                    lnhat_bwd(dxh, y1, dy_cur, cp, c)
-                    del xh, dxh
-                    for k in range(len(ds["stl"]) - 1, -1, -1):
-                        first = k == 0
-                        dy_cur = _stl_backward(ds["stl"][k], sl[k], W, gz, dy_cur, B, H, Wd,
-                                               accumulate_into=dD if first else None)
-                dX = dD[:, :64].contiguous()
-                del dD
-            # ---- patch_embed norm + head conv ----
-            dE = e(T, 64)
-            dE.zero_()
-            _call("rdst_layernorm_bwd", _p(dX), 64, _p(S["F0"]), 64, _p(W[spec["pe_g"]]), _p(dE), 64,
-                  _p(gz(spec["pe_g"])), _p(gz(spec["pe_b"])), T, 60, 1.0, _lib.stream_ptr())
-            axpy(dE, dF0, 60)
-            ghw, ghb = z(64, 9 * 16), z(64)
-            gemm_tn(dF0, S["img"], ghw, ghb, 64, 9 * 16, (B, H, Wd, 16))
-            gz(spec["head_w"]).add_(ghw.reshape(64, 9, 16)[:60, :, 0])
-            gz(spec["head_b"]).add_(ghb[:60])
         ctx.saved = None
-        return (None, None) + tuple(G)
+        return (None, None, None, dX, dF0) + tuple(G)
 
 
 def _stl_backward(st, sv, W, gz, dY, B, H, Wd, accumulate_into=None):
@@ -303,27 +396,27 @@ def _stl_backward(st, sv, W, gz, dY, B, H, Wd, accumulate_into=None):
     _call("rdst_gelu_fwd", _p(hid), hp, _p(act), hp, T, hp, _lib.stream_ptr())
     gemm_tn(dY, act, gz(st["w2"]), gz(st["b2"]), cp, hp)
     dact = act                                                      # reuse the buffer
-    linear(dY, W[st["w2"]].t().contiguous(), z(hp), dact, cp, hp)
+    linear_t(dY, W[st["w2"]], dact, cp, hp)
     dhid = e(T, hp)
     _call("rdst_gelu_bwd", _p(hid), hp, _p(dact), hp, _p(dhid), hp, T, hp, _lib.stream_ptr())
     xh = e(T, cp)
     lnhat(x1, xh, cp, c)
     gemm_tn(dhid, xh, gz(st["w1"]), gz(st["b1"]), hp, cp)
     dxh = e(T, cp)
-    linear(dhid, W[st["w1"]].t().contiguous(), z(cp), dxh, hp, cp)
+    linear_t(dhid, W[st["w1"]], dxh, hp, cp)
     dX1 = e(T, cp)
     lnhat_bwd(dxh, x1, dX1, cp, c, resid=dY)
     del act, dhid
     # ---- x1 = x + proj(attn(lnhat(x))) ----
     gemm_tn(dX1, o, gz(st["wproj"]), gz(st["bproj"]), cp, c)
     dO = e(T, c)
-    linear(dX1, W[st["wproj"]].t().contiguous(), z(c), dO, cp, c)
+    linear_t(dX1, W[st["wproj"]], dO, cp, c)
     dqkv = e(T, 3 * c)
     _call("rdst_window_attention_bwd", _p(qkv), 3 * c, _p(W[st["table"]]), _p(dO), c, _p(dqkv), 3 * c,
           _p(gz(st["table"])), B, H, Wd, c, packing.HEADS, st["shift"], _lib.stream_ptr())
     lnhat(x, xh, cp, c)
     gemm_tn(dqkv, xh, gz(st["wqkv"]), gz(st["bqkv"]), 3 * c, cp)
-    linear(dqkv, W[st["wqkv"]].t().contiguous(), z(cp), dxh, 3 * c, cp)
+    linear_t(dqkv, W[st["wqkv"]], dxh, 3 * c, cp)
     if accumulate_into is None:
         dX = e(T, cp)
         lnhat_bwd(dxh, x, dX, cp, c, resid=dX1)
@@ -339,5 +432,14 @@ def forward_with_grad(executor, x):
                                   "call model.set_precision('fp32') for training, bf16 is inference-only for now")
     if x.requires_grad:
         raise NotImplementedError("rdst_b200: gradients with respect to the input image are not implemented")
-    flat, spec = train_weights(m, x.device)
-    return RDSTFunction.apply(spec, x.detach().to(torch.float32).contiguous(), *flat)
+    dev = x.device
+    B, _, H, Wd = x.shape
+    geom = (B, H, Wd)
+    sc = frozen_scalars(m)
+    flat, spec = pack_head(m, dev)
+    F0, X = HeadFunction.apply(spec, sc, x.detach().to(torch.float32).contiguous(), *flat)
+    for blk in m.body:
+        flat, bs = pack_block(m, blk, dev)
+        X = BlockFunction.apply(bs, geom, X, *flat)
+    flat, spec = pack_tail(m, dev)
+    return TailFunction.apply(spec, sc, geom, X, F0, *flat)

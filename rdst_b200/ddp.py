@@ -1,0 +1,100 @@
+"""Data-parallel gradient exchange for RDST training (BASELINE cfg4): one bucket per link of the network, all-reduced
+over NCCL (NVLink 5 / NVSwitch) as soon as the bucket's last gradient has been accumulated, i.e. while the backward
+kernels of the earlier RDSTBs are still running.
+
+The training path (rdst_b200/autograd.py) is a chain of autograd.Functions (head, RDSTB 0..n-1, tail) with the weight
+packing of each link interleaved, so the engine finishes the parameter gradients link by link in reverse order.
+`BucketedAllReduce` keeps every bucket's gradients in ONE flat fp32 buffer (`p.grad` are views into it, so autograd
+accumulates in place and the collective needs no copy), counts accumulations with post-accumulate-grad hooks and
+launches `all_reduce(AVG)` asynchronously: ProcessGroupNCCL runs it on its own stream after an event on the compute
+stream, and `finish()` makes the compute stream wait for all of them before the optimizer reads the gradients.
+Everything here is stream-ordered (no host sync), so a whole step -- forward, backward, the all-reduces and the
+optimizer -- can be captured into one CUDA graph (rdst_b200/train.py).
+
+torch's DistributedDataParallel also works on the module (it sees the same link-by-link readiness); this class is
+the graph-capturable, copy-free alternative.  The reference trains on a single GPU (models/trans_sr_trainer.py), so
+there is no reference interface to mirror here.
+"""
+import torch
+import torch.distributed as dist
+
+
+def rdst_link_of(name):
+    """Bucket key of a parameter name of RDSTSR: 'head' | 'body.<i>' | 'tail' (state_dict layout)."""
+    parts = name.split(".")
+    if parts[0] == "body":
+        return "body." + parts[1]
+    if parts[0] in ("head", "patch_embed"):
+        return "head"
+    return "tail"
+
+
+class BucketedAllReduce:
+    def __init__(self, model, process_group=None, bucket_of=rdst_link_of, average=True):
+        self.group = process_group
+        self.average = average
+        self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
+        groups = {}
+        for name, p in model.named_parameters():
+            if p.requires_grad:
+                groups.setdefault(bucket_of(name), []).append(p)
+        self.buckets = []
+        self._hooks = []
+        for key, params in groups.items():
+            n = sum(p.numel() for p in params)
+            flat = torch.zeros(n, dtype=params[0].dtype, device=params[0].device)
+            views, off = [], 0
+            for p in params:
+                views.append(flat[off:off + p.numel()].view_as(p))
+                off += p.numel()
+            b = dict(key=key, params=params, flat=flat, views=views, pending=len(params), fired=False)
+            self.buckets.append(b)
+            for p in params:
+                self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(b)))
+        self._works = []
+        self.launch_order = []          # bucket keys in the order their all-reduce was launched (last step)
+        self.begin_step()
+
+    def _make_hook(self, b):
+        def hook(_param):
+            b["pending"] -= 1
+            if b["pending"] == 0:
+                self._launch(b)
+        return hook
+
+    def _launch(self, b):
+        b["fired"] = True
+        self.launch_order.append(b["key"])
+        if self.world == 1:
+            return
+        if self.average and dist.get_backend(self.group) == "nccl":
+            self._works.append(dist.all_reduce(b["flat"], op=dist.ReduceOp.AVG, group=self.group, async_op=True))
+        else:
+            if self.average:
+                b["flat"].div_(self.world)
+            self._works.append(dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
+
+    def begin_step(self):
+        """Replaces optimizer.zero_grad(): zero the flat buffers and (re)attach the gradient views."""
+        self._works, self.launch_order = [], []
+        for b in self.buckets:
+            b["flat"].zero_()
+            b["pending"], b["fired"] = len(b["params"]), False
+            for p, v in zip(b["params"], b["views"]):
+                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                    p.grad = v
+
+    def finish(self):
+        """Call after backward(): the current stream waits for every bucket's all-reduce."""
+        missing = [b["key"] for b in self.buckets if not b["fired"]]
+        if missing:
+            raise RuntimeError(f"rdst_b200.ddp: buckets {missing} received no gradient in this backward pass "
+                               "(unused parameters are not supported)")
+        for w in self._works:
+            w.wait()
+        self._works = []
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []

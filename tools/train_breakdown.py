@@ -1,0 +1,85 @@
+"""Where a training step's time goes (cfg4 shape 32x1x24x24, 1 GPU): wall time of forward / backward / optimizer,
+and the per-ABI-call device time (CUDA events around every launch) summed over one step."""
+import collections
+import os
+import sys
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
+    sys.path.insert(0, p)
+import helpers  # noqa: E402
+from rdst_b200 import _lib  # noqa: E402
+
+prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
+torch.manual_seed(0)
+m = helpers.make_module(8, 4, prec).cuda().train()
+opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.99), eps=1e-8)
+x = torch.rand(32, 1, 24, 24, device="cuda")
+y = torch.rand(32, 1, 96, 96, device="cuda")
+
+
+def step(t=None):
+    def mark(k):
+        if t is not None:
+            torch.cuda.synchronize()
+            t[k] = time.perf_counter()
+    mark("t0")
+    opt.zero_grad(set_to_none=True)
+    out = m(x)
+    loss = torch.nn.functional.l1_loss(out, y)
+    mark("fwd")
+    loss.backward()
+    mark("bwd")
+    opt.step()
+    mark("opt")
+
+
+for _ in range(3):
+    step()
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+for _ in range(5):
+    step()
+torch.cuda.synchronize()
+print(f"step (no instrumentation): {(time.perf_counter() - t0) / 5 * 1e3:.2f} ms")
+t = {}
+step(t)
+print(f"forward {1e3 * (t['fwd'] - t['t0']):.2f} ms, backward {1e3 * (t['bwd'] - t['fwd']):.2f} ms, "
+      f"optimizer {1e3 * (t['opt'] - t['bwd']):.2f} ms (each followed by a sync)")
+
+orig = _lib.call
+evs = []
+
+
+def timed(name, *a):
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    orig(name, *a)
+    e1.record()
+    evs.append((name, e0, e1))
+
+
+_lib.call = timed
+step()
+torch.cuda.synchronize()
+_lib.call = orig
+agg = collections.defaultdict(lambda: [0, 0.0])
+for k, a, b in evs:
+    agg[k][0] += 1
+    agg[k][1] += a.elapsed_time(b)
+tot = sum(v for _, v in agg.values())
+print(f"{'call':40s} {'n/step':>7s} {'us/call':>9s} {'ms/step':>8s} {'share':>6s}")
+for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
+    print(f"{k:40s} {n:7d} {v / n * 1e3:9.1f} {v:8.3f} {100 * v / tot:5.1f}%")
+print(f"{'TOTAL device time in ABI calls':40s} {len(evs):7d} {'':9s} {tot:8.3f}")
+
+# host-only cost: time to enqueue (no sync) one step
+torch.cuda.synchronize()
+t0 = time.perf_counter()
+step()
+t1 = time.perf_counter()
+torch.cuda.synchronize()
+print(f"host enqueue time of one step: {1e3 * (t1 - t0):.2f} ms")
