@@ -10,8 +10,10 @@ parameters; every activation-sized computation, forward and backward, is a kerne
     attention          rdst_window_attention_bwd (recomputes the probabilities; relative-position table gradient)
     GELU, residual joins, PixelShuffle  rdst_gelu_fwd/_bwd, rdst_axpy, rdst_pixel_unshuffle2
 Gradient of: RDSTSR.forward (rdst_variations.py:1342-1360) and everything it calls; checked against torch.autograd
-through the CPU oracle in tests/test_gpu_backward.py.  Training runs in precision='fp32' (this round).
+through the CPU oracle in tests/test_gpu_backward.py (fp32) and tests/test_gpu_train_tc.py (bf16 tensor-core GEMMs).
 """
+import threading
+
 import torch
 
 from . import _lib, packing
@@ -32,24 +34,64 @@ def _ld(t):
 
 
 # ------------------------------------------------------------------------------------------------ kernel wrappers
+# precision 'fp32': every GEMM is a CUDA-core FFMA kernel (the <=1e-4 parity path).  precision 'bf16': the GEMMs --
+# Linear / conv forward, data gradients, weight gradients -- run on tcgen05 with operands rounded to bf16 while they
+# are staged (csrc/tc_train.cu); storage, LayerNorm / softmax / GELU and all reductions stay fp32.  Each Function sets
+# the mode of the calling thread on entry (backward runs on autograd's device thread).
+_MODE = threading.local()
+
+
+def _tc():
+    return getattr(_MODE, "tc", False)
+
+
+def _aligned(*ts):
+    return all(t is None or (t.data_ptr() % 16 == 0 and (t.dim() < 2 or t.stride(0) % 4 == 0)) for t in ts)
+
+
 def linear(x, w, b, y, K, N, ln_creal=0, act=0, scale=1.0, resid=None):
     T = x.shape[0]
+    if _tc() and act == 0 and _aligned(x, y, resid):
+        _call("rdst_gemm_tc", _p(x), _ld(x), _p(w), _ld(w), 0, _p(b), _p(resid), 0 if resid is None else _ld(resid),
+              _p(y), _ld(y), T, K, N, ln_creal, scale, 0, 0, 0, 0, 0, 0, _lib.stream_ptr())
+        return
+    assert w.is_contiguous() and w.shape[-1] == K
     _call("rdst_linear_fwd", _p(x), _ld(x), _p(w), _p(b), _p(resid), 0 if resid is None else _ld(resid), _p(y), _ld(y),
           T, K, N, ln_creal, act, scale, F32, _lib.stream_ptr())
 
 
+def linear_t(dy, w, dx, K, N, scale=1.0):
+    """Data gradient of a Linear: dx[T][N] = scale * dy[T][K] . w[K][N]   (w is the forward weight [out=K][in=N])."""
+    if _tc() and _aligned(dy, dx):
+        _call("rdst_gemm_tc", _p(dy), _ld(dy), _p(w), _ld(w), 1, None, None, 0, _p(dx), _ld(dx), dy.shape[0], K, N, 0,
+              scale, 0, 0, 0, 0, 0, 0, _lib.stream_ptr())
+        return
+    linear(dy, w.t().contiguous(), torch.zeros(N, dtype=torch.float32, device=dy.device), dx, K, N, scale=scale)
+
+
 def conv(x, w, b, y, B, H, W, cin, n, scale=1.0, shuffle=0, resid=None):
+    if _tc() and cin % 16 == 0 and _aligned(x, y, resid):
+        _call("rdst_gemm_tc", _p(x), _ld(x), _p(w), 9 * cin, 0, _p(b), _p(resid), 0 if resid is None else _ld(resid),
+              _p(y), _ld(y), B * H * W, 9 * cin, n, 0, scale, 1, B, H, W, cin, shuffle, _lib.stream_ptr())
+        return
     _call("rdst_conv3x3_fwd", _p(x), _ld(x), _p(w), _p(b), _p(resid), 0 if resid is None else _ld(resid), _p(y), _ld(y),
           B, H, W, cin, n, scale, shuffle, F32, _lib.stream_ptr())
 
 
 def gemm_tn(dy, x, dw, db, N, K, conv_geom=None):
     T = dy.shape[0]
+    name = "rdst_gemm_tn_acc"
+    if _tc() and _aligned(dy, x) and dw.data_ptr() % 16 == 0 and (conv_geom is None or conv_geom[3] % 16 == 0):
+        name = "rdst_gemm_tn_tc"
     if conv_geom is None:
-        _call("rdst_gemm_tn_acc", _p(dy), _ld(dy), _p(x), _ld(x), _p(dw), _p(db), T, N, K, 0, 0, 0, 0, 0, _lib.stream_ptr())
+        _call(name, _p(dy), _ld(dy), _p(x), _ld(x), _p(dw), _p(db), T, N, K, 0, 0, 0, 0, 0, _lib.stream_ptr())
     else:
         B, H, W, cin = conv_geom
-        _call("rdst_gemm_tn_acc", _p(dy), _ld(dy), _p(x), _ld(x), _p(dw), _p(db), T, N, K, 1, B, H, W, cin, _lib.stream_ptr())
+        _call(name, _p(dy), _ld(dy), _p(x), _ld(x), _p(dw), _p(db), T, N, K, 1, B, H, W, cin, _lib.stream_ptr())
+
+
+def _pad8(n):
+    return (n + 7) // 8 * 8
 
 
 def lnhat(x, y, K, creal):
@@ -63,11 +105,6 @@ def lnhat_bwd(dxh, x, dx, K, creal, resid=None, resid2=None):
 
 def axpy(x, y, N, alpha=1.0):
     _call("rdst_axpy", _p(x), _ld(x), _p(y), _ld(y), x.shape[0], N, alpha, _lib.stream_ptr())
-
-
-def linear_t(dy, w, dx, K, N, scale=1.0):
-    """Data gradient of a Linear: dx[T][N] = scale * dy[T][K] . w[K][N]   (w is the forward weight [out=K][in=N])."""
-    linear(dy, w.t().contiguous(), torch.zeros(N, dtype=torch.float32, device=dy.device), dx, K, N, scale=scale)
 
 
 def conv_dgrad_weight(w):
@@ -178,6 +215,7 @@ class HeadFunction(torch.autograd.Function):
         B, _, H, Wd = x.shape
         T = B * H * Wd
         e, z = _f32(dev)
+        _MODE.tc = sc["tc"]
         with torch.cuda.device(dev):
             img = z(T, 16)
             img[:, 0] = x.reshape(-1) * sc["in_scale"] + sc["in_bias"]
@@ -186,7 +224,7 @@ class HeadFunction(torch.autograd.Function):
             X0 = z(T, 64)
             _call("rdst_layernorm_fwd", _p(F0), 64, _p(W[spec["pe_g"]]), _p(W[spec["pe_b"]]), _p(X0), 64, T, 60, 1.0, F32,
                   _lib.stream_ptr())
-        ctx.spec, ctx.W, ctx.geom, ctx.saved = spec, W, (B, H, Wd), (img, F0)
+        ctx.spec, ctx.W, ctx.geom, ctx.saved, ctx.tc = spec, W, (B, H, Wd), (img, F0), sc["tc"]
         return F0, X0
 
     @staticmethod
@@ -198,6 +236,7 @@ class HeadFunction(torch.autograd.Function):
         dev = dX0.device
         e, z = _f32(dev)
         G = [None] * len(W)
+        _MODE.tc = ctx.tc
         with torch.cuda.device(dev):
             dF = dF0.contiguous().clone()
             dE = z(T, 64)
@@ -222,6 +261,7 @@ class BlockFunction(torch.autograd.Function):
         T = B * H * Wd
         dev = X.device
         e, z = _f32(dev)
+        _MODE.tc = tc = bs["tc"]
         with torch.cuda.device(dev):
             D = z(T, 160)
             D[:, :64] = X
@@ -232,9 +272,11 @@ class BlockFunction(torch.autograd.Function):
                 sl = []
                 for st in ds["stl"]:
                     cp, hp = st["cp"], st["hp"]
-                    qkv, o, x1, hid, act, y = e(T, 3 * c), e(T, c), e(T, cp), e(T, hp), e(T, hp), e(T, cp)
+                    # tensor-core mode keeps every row 16-byte aligned: q|k|v rows padded to a multiple of 8 floats
+                    qkv, o = e(T, _pad8(3 * c) if tc else 3 * c), e(T, cp if tc else c)
+                    x1, hid, act, y = e(T, cp), e(T, hp), e(T, hp), e(T, cp)
                     linear(src, W[st["wqkv"]], W[st["bqkv"]], qkv, cp, 3 * c, ln_creal=c)
-                    _call("rdst_window_attention_fwd", _p(qkv), 3 * c, _p(W[st["table"]]), _p(o), c, B, H, Wd, c,
+                    _call("rdst_window_attention_fwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(o), _ld(o), B, H, Wd, c,
                           packing.HEADS, st["shift"], F32, _lib.stream_ptr())
                     linear(o, W[st["wproj"]], W[st["bproj"]], x1, c, cp, resid=src)
                     linear(x1, W[st["w1"]], W[st["b1"]], hid, cp, hp, ln_creal=c)
@@ -266,6 +308,7 @@ class BlockFunction(torch.autograd.Function):
                 G[i] = torch.zeros_like(W[i])
             return G[i]
 
+        _MODE.tc = bs["tc"]
         with torch.cuda.device(dev):
             dX = dXn.contiguous()
             dys = dX if bs["res_scale"] == 1.0 else dX * bs["res_scale"]
@@ -310,6 +353,7 @@ class TailFunction(torch.autograd.Function):
         T = B * H * Wd
         dev = X.device
         e, z = _f32(dev)
+        _MODE.tc = sc["tc"]
         with torch.cuda.device(dev):
             FN = z(T, 64)
             _call("rdst_layernorm_fwd", _p(X), 64, _p(W[spec["norm_g"]]), _p(W[spec["norm_b"]]), _p(FN), 64, T, 60,
@@ -347,6 +391,7 @@ class TailFunction(torch.autograd.Function):
                 G[i] = torch.zeros_like(W[i])
             return G[i]
 
+        _MODE.tc = sc["tc"]
         with torch.cuda.device(dev):
             n_up = len(spec["up"])
             h, w_ = H * (2 ** n_up), Wd * (2 ** n_up)
@@ -409,10 +454,10 @@ def _stl_backward(st, sv, W, gz, dY, B, H, Wd, accumulate_into=None):
     del act, dhid
     # ---- x1 = x + proj(attn(lnhat(x))) ----
     gemm_tn(dX1, o, gz(st["wproj"]), gz(st["bproj"]), cp, c)
-    dO = e(T, c)
+    dO = torch.empty_like(o)
     linear_t(dX1, W[st["wproj"]], dO, cp, c)
-    dqkv = e(T, 3 * c)
-    _call("rdst_window_attention_bwd", _p(qkv), 3 * c, _p(W[st["table"]]), _p(dO), c, _p(dqkv), 3 * c,
+    dqkv = torch.empty_like(qkv)
+    _call("rdst_window_attention_bwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(dO), _ld(dO), _p(dqkv), _ld(dqkv),
           _p(gz(st["table"])), B, H, Wd, c, packing.HEADS, st["shift"], _lib.stream_ptr())
     lnhat(x, xh, cp, c)
     gemm_tn(dqkv, xh, gz(st["wqkv"]), gz(st["bqkv"]), 3 * c, cp)
@@ -427,19 +472,20 @@ def _stl_backward(st, sv, W, gz, dY, B, H, Wd, accumulate_into=None):
 
 def forward_with_grad(executor, x):
     m = executor._module()
-    if m.precision != "fp32":
-        raise NotImplementedError("rdst_b200: training (autograd) is implemented for precision='fp32' in this round; "
-                                  "call model.set_precision('fp32') for training, bf16 is inference-only for now")
+    tc = m.precision == "bf16"
+    if tc and not _lib.load().rdst_has_tcgen05():
+        raise RuntimeError("rdst_b200: precision='bf16' training needs the tcgen05 kernels (sm_100a device)")
     if x.requires_grad:
         raise NotImplementedError("rdst_b200: gradients with respect to the input image are not implemented")
     dev = x.device
     B, _, H, Wd = x.shape
     geom = (B, H, Wd)
-    sc = frozen_scalars(m)
+    sc = dict(frozen_scalars(m), tc=tc)
     flat, spec = pack_head(m, dev)
     F0, X = HeadFunction.apply(spec, sc, x.detach().to(torch.float32).contiguous(), *flat)
     for blk in m.body:
         flat, bs = pack_block(m, blk, dev)
+        bs["tc"] = tc
         X = BlockFunction.apply(bs, geom, X, *flat)
     flat, spec = pack_tail(m, dev)
     return TailFunction.apply(spec, sc, geom, X, F0, *flat)

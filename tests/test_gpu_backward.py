@@ -69,9 +69,3 @@ def test_training_step_reduces_loss():
     with torch.no_grad():
         m.eval()
         assert torch.isfinite(m(x)).all()
-
-
-def test_bf16_training_is_rejected_loudly():
-    m = helpers.make_module(1, 4, "bf16").cuda().train()
-    with pytest.raises(NotImplementedError, match="fp32"):
-        m(torch.rand(1, 1, 8, 8, device="cuda"))

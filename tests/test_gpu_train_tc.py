@@ -1,0 +1,210 @@
+"""Tensor-core GEMMs of the bf16 training path (csrc/tc_train.cu) against torch on the SAME bf16-rounded operands
+(fp64 accumulation), over every shape class the network uses: Linear forward with the LayerNorm prologue, Linear data
+gradient (transposed weight = MN-major B operand), 3x3 conv forward / data gradient incl. PixelShuffle store, and the
+weight / bias gradients (token-reduction GEMM with MN-major A and B, ones-column bias, split-T fp32 reductions).
+Then the whole training step in precision='bf16' against torch.autograd through the fp32 oracle."""
+import pytest
+import torch
+import torch.nn.functional as F
+
+import helpers
+import rdst_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from rdst_b200 import _lib as L
+    return L
+
+
+def bf(t):
+    return t.to(torch.bfloat16).double()
+
+
+def lnhat(x, creal):
+    mean = x.sum(1, keepdim=True) / creal
+    var = (x * x).sum(1, keepdim=True) / creal - mean * mean
+    return (x - mean) * torch.rsqrt(var.clamp_min(0) + 1e-5)
+
+
+def _close(got, ref, tol=2e-3):
+    err = (got.double() - ref).abs().max().item()
+    scale = ref.abs().max().item() + 1e-12
+    assert err / scale < tol, (err, scale)
+
+
+@pytest.mark.parametrize("T,K,ldx,N,ldy,ln,w_mn,resid", [
+    (300, 128, 128, 360, 360, 120, 0, False),      # qkv forward, C=120
+    (300, 96, 96, 270, 272, 90, 0, False),         # qkv forward, C=90 (q|k|v rows padded to 272)
+    (1000, 120, 128, 128, 128, 0, 0, True),        # proj forward + residual, K = C real columns of a padded row
+    (257, 90, 96, 96, 96, 0, 0, True),             # proj, C=90: weight rows of 90 floats (unaligned -> scalar staging)
+    (300, 240, 240, 128, 128, 0, 0, True),         # fc2
+    (300, 64, 160, 32, 160, 60, 0, False),         # DSTL tail into a 32-wide slice of the dense buffer
+    (300, 360, 360, 128, 128, 0, 1, False),        # qkv data gradient: K = 360 -> padded to 368
+    (300, 270, 272, 96, 96, 0, 1, False),
+    (300, 96, 96, 90, 96, 0, 1, False),            # proj data gradient, N = 90 (ragged epilogue)
+    (20000, 128, 128, 240, 240, 120, 0, False),    # more tiles than SMs (persistent loop, weights staged once)
+])
+def test_gemm_tc_linear(T, K, ldx, N, ldy, ln, w_mn, resid):
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(T + K + N)
+    x = torch.randn(T, ldx, device="cuda", generator=g)
+    if ln:
+        x[:, ln:] = 0
+        x += 0.5
+        x[:, ln:] = 0
+    w = torch.randn((K, N) if w_mn else (N, K), device="cuda", generator=g) * 0.1
+    b = None if w_mn else torch.randn(N, device="cuda", generator=g)
+    r = torch.randn(T, ldy, device="cuda", generator=g) if resid else None
+    y = torch.full((T, ldy), 7.0, device="cuda")
+    scale = 0.75
+    L.call("rdst_gemm_tc", L.ptr(x), ldx, L.ptr(w), w.stride(0), w_mn, L.ptr(b), L.ptr(r), ldy if resid else 0, L.ptr(y), ldy,
+           T, K, N, ln, scale, 0, 0, 0, 0, 0, 0, L.stream_ptr())
+    torch.cuda.synchronize()
+    a = x[:, :K]
+    if ln:
+        a = lnhat(a, ln)
+    wk = w.t() if w_mn else w
+    ref = bf(a) @ bf(wk).t()
+    if b is not None:
+        ref = ref + b.double()
+    ref = ref * scale
+    if resid:
+        ref = ref + r[:, :N].double()
+    _close(y[:, :N], ref)
+    assert (y[:, N:] == 7.0).all()                 # nothing written beyond N
+
+
+@pytest.mark.parametrize("B,H,W,cin,ldx,n,shuffle,resid", [
+    (2, 16, 24, 64, 64, 64, 0, True),
+    (2, 16, 24, 160, 160, 64, 0, True),
+    (2, 16, 24, 64, 64, 160, 0, False),
+    (1, 24, 24, 64, 64, 256, 2, False),
+    (3, 8, 8, 256, 256, 64, 0, False),
+    (2, 16, 24, 16, 16, 64, 0, False),
+])
+def test_gemm_tc_conv(B, H, W, cin, ldx, n, shuffle, resid):
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(cin + n)
+    T = B * H * W
+    x = torch.randn(T, ldx, device="cuda", generator=g)
+    w = torch.randn(n, 9, cin, device="cuda", generator=g) * 0.05
+    b = torch.randn(n, device="cuda", generator=g)
+    ldy = 64 if shuffle else (160 if n == 160 else 64)
+    r = torch.randn(T, 160, device="cuda", generator=g) if resid else None
+    Ty = T * 4 if shuffle else T
+    y = torch.zeros(Ty, ldy, device="cuda")
+    L.call("rdst_gemm_tc", L.ptr(x), ldx, L.ptr(w), 9 * cin, 0, L.ptr(b), L.ptr(r), 160 if resid else 0, L.ptr(y), ldy,
+           T, 9 * cin, n, 0, 0.5, 1, B, H, W, cin, shuffle, L.stream_ptr())
+    torch.cuda.synchronize()
+    xi = bf(x[:, :cin]).reshape(B, H, W, cin).permute(0, 3, 1, 2)
+    wt = bf(w).reshape(n, 3, 3, cin).permute(0, 3, 1, 2)
+    v = (F.conv2d(xi, wt, None, padding=1) + b.double()[None, :, None, None]) * 0.5
+    if shuffle:
+        G = n // 4
+        ref = v.reshape(B, 2, 2, G, H, W).permute(0, 4, 1, 5, 2, 3).reshape(B * 2 * H * 2 * W, G)
+    else:
+        ref = v.permute(0, 2, 3, 1).reshape(T, n)
+        if resid:
+            ref = ref + r[:, :n].double()
+    _close(y[:, :ref.shape[1]], ref)
+
+
+@pytest.mark.parametrize("T,N,ldy,K,ldx,bias", [
+    (1000, 360, 360, 128, 128, True),
+    (18432, 270, 272, 96, 96, True),
+    (300, 96, 96, 90, 96, True),                   # wproj gradient, K = 90 (scalar reductions)
+    (300, 32, 160, 128, 128, True),                # tail: dY is a slice of the dense-buffer gradient
+    (5000, 240, 240, 128, 128, False),
+    (129, 128, 128, 240, 240, True),
+])
+def test_gemm_tn_tc_linear(T, N, ldy, K, ldx, bias):
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(T + N + K)
+    dy = torch.randn(T, ldy, device="cuda", generator=g)
+    x = torch.randn(T, ldx, device="cuda", generator=g)
+    dw = torch.ones(N, K, device="cuda")
+    db = torch.ones(N, device="cuda") if bias else None
+    L.call("rdst_gemm_tn_tc", L.ptr(dy), ldy, L.ptr(x), ldx, L.ptr(dw), L.ptr(db), T, N, K, 0, 0, 0, 0, 0, L.stream_ptr())
+    torch.cuda.synchronize()
+    ref = bf(dy[:, :N]).t() @ bf(x[:, :K]) + 1.0
+    _close(dw, ref)
+    if bias:
+        _close(db, bf(dy[:, :N]).sum(0) + 1.0)
+
+
+@pytest.mark.parametrize("B,H,W,N,cin", [(2, 16, 24, 64, 160), (1, 24, 24, 256, 64), (2, 8, 16, 64, 16), (32, 24, 24, 64, 64)])
+def test_gemm_tn_tc_conv(B, H, W, N, cin):
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(N + cin)
+    T = B * H * W
+    dy = torch.randn(T, N, device="cuda", generator=g)
+    x = torch.randn(T, cin, device="cuda", generator=g)
+    dw = torch.zeros(N, 9 * cin, device="cuda")
+    db = torch.zeros(N, device="cuda")
+    L.call("rdst_gemm_tn_tc", L.ptr(dy), N, L.ptr(x), cin, L.ptr(dw), L.ptr(db), T, N, 9 * cin, 1, B, H, W, cin, L.stream_ptr())
+    torch.cuda.synchronize()
+    xi = bf(x).reshape(B, H, W, cin).permute(0, 3, 1, 2)
+    cols = F.unfold(xi, 3, padding=1).reshape(B, cin, 9, H * W).permute(0, 3, 2, 1).reshape(T, 9 * cin)   # [t][tap][ci]
+    ref = bf(dy).t() @ cols
+    _close(dw, ref)
+    _close(db, bf(dy).sum(0))
+
+
+def _oracle_grads(sd, x, target, scale):
+    p = {k: (v.clone().double().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
+    out = O.forward(p, x.double(), scale)
+    loss = (out - target.double()).abs().mean()
+    names = [k for k, v in p.items() if v.is_floating_point() and "mean." not in k and "attn_mask" not in k]
+    grads = torch.autograd.grad(loss, [p[k] for k in names], allow_unused=True)
+    return loss.item(), dict(zip(names, grads)), out.detach()
+
+
+@pytest.mark.parametrize("blocks,shape,scale", [(1, (2, 1, 16, 24), 4), (2, (1, 1, 24, 24), 2)])
+def test_bf16_training_gradients_close_to_fp32_autograd(blocks, shape, scale):
+    """precision='bf16' training: GEMM operands are rounded to bf16, so gradients agree with the exact fp32 autograd of
+    the oracle to bf16 accuracy: per-tensor relative L2 error <= 3e-2 (<= 1e-1 for the tiny relative-position tables), output within the bf16 inference bar (1e-2)."""
+    from synth_weights import fill_state_dict
+    sd = fill_state_dict(helpers.skeleton_state_dict(blocks, scale), 11, True)
+    x = torch.rand(*shape, generator=torch.Generator().manual_seed(4))
+    target = torch.rand(shape[0], 1, shape[2] * scale, shape[3] * scale, generator=torch.Generator().manual_seed(5))
+    loss_ref, g_ref, out_ref = _oracle_grads(sd, x, target, scale)
+    m = helpers.make_module(blocks, scale, "bf16").cuda().train()
+    m.load_state_dict(sd, strict=True)
+    out = m(x.cuda())
+    loss = F.l1_loss(out, target.cuda())
+    loss.backward()
+    assert (out.detach().cpu().double() - out_ref).abs().max().item() < 1e-2
+    assert abs(loss.item() - loss_ref) < 1e-3
+    params = dict(m.named_parameters())
+    worst, worst_tab = ("", 0.0), ("", 0.0)
+    for k, gr in g_ref.items():
+        if gr is None:
+            continue
+        gp = params[k].grad
+        assert gp is not None, k
+        rel = ((gp.detach().cpu().double() - gr).norm() / (gr.norm() + 1e-12)).item()
+        if "relative_position_bias_table" in k:      # 225x6 sums of signed score gradients: cancellation amplifies rounding
+            worst_tab = max(worst_tab, (k, rel), key=lambda kv: kv[1])
+        else:
+            worst = max(worst, (k, rel), key=lambda kv: kv[1])
+    print("worst relative L2 gradient error (bf16 GEMMs):", worst, worst_tab)
+    assert worst[1] < 3e-2, worst
+    assert worst_tab[1] < 1e-1, worst_tab
+
+
+def test_bf16_training_step_reduces_loss():
+    torch.manual_seed(0)
+    m = helpers.make_module(1, 4, "bf16").cuda().train()
+    opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-3, betas=(0.9, 0.99), eps=1e-8)
+    x = torch.rand(4, 1, 24, 24, device="cuda")
+    y = F.interpolate(x, scale_factor=4, mode="bilinear")
+    losses = []
+    for _ in range(6):
+        opt.zero_grad()
+        loss = F.l1_loss(m(x), y)
+        loss.backward()
+        opt.step()
+        losses.append(float(loss))
+    assert losses[-1] < losses[0] * 0.9, losses

@@ -59,6 +59,10 @@ def timed(name, *a):
     e0.record()
     orig(name, *a)
     e1.record()
+    if name == "rdst_gemm_tc":          # (x, ldx, w, ldw, w_mn, bias, resid, ldr, y, ldy, T, K, N, ln, scale, conv, ...)
+        name += f" T={a[10]} K={a[11]} N={a[12]}" + (" wT" if a[4] else "") + (" ln" if a[13] else "") + (" conv" if a[15] else "")
+    elif name in ("rdst_gemm_tn_tc", "rdst_gemm_tn_acc"):   # (dy, ldy, x, ldx, dw, db, T, N, K, conv, ...)
+        name += f" T={a[6]} N={a[7]} K={a[8]}" + (" conv" if a[9] else "")
     evs.append((name, e0, e1))
 
 
@@ -71,10 +75,10 @@ for k, a, b in evs:
     agg[k][0] += 1
     agg[k][1] += a.elapsed_time(b)
 tot = sum(v for _, v in agg.values())
-print(f"{'call':40s} {'n/step':>7s} {'us/call':>9s} {'ms/step':>8s} {'share':>6s}")
+print(f"{'call':48s} {'n/step':>7s} {'us/call':>9s} {'ms/step':>8s} {'share':>6s}")
 for k, (n, v) in sorted(agg.items(), key=lambda kv: -kv[1][1]):
-    print(f"{k:40s} {n:7d} {v / n * 1e3:9.1f} {v:8.3f} {100 * v / tot:5.1f}%")
-print(f"{'TOTAL device time in ABI calls':40s} {len(evs):7d} {'':9s} {tot:8.3f}")
+    print(f"{k:48s} {n:7d} {v / n * 1e3:9.1f} {v:8.3f} {100 * v / tot:5.1f}%")
+print(f"{'TOTAL device time in ABI calls':48s} {len(evs):7d} {'':9s} {tot:8.3f}")
 
 # host-only cost: time to enqueue (no sync) one step
 torch.cuda.synchronize()
