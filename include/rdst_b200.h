@@ -147,19 +147,26 @@ int rdst_window_attention_bwd(const float* qkv, int64_t ldq, const float* table,
 /* ---- tensor-core GEMMs of the training path (precision 'bf16'): fp32 storage, operands rounded to bf16 while they
  *      are staged into shared memory, tcgen05.mma with fp32 accumulation in TMEM (rdst_b200/csrc/tc_train.cu) ------ */
 
-/* Y[t][n] = out_scale * ( LNhat(X[t][0:K]) . Wop + bias[n] ) + R[t][n]          (all fp32 in memory)
+/* Y[t][n] = out_scale * ( op(X[t][0:K]) . Wop + bias[n] ) * G[t][n] + R[t][n]          (all fp32 in memory)
+ *   a_op: 0 none; 1 LNhat over ln_creal real channels (as rdst_linear_fwd); 2 exact-erf GELU (fc2 reads the saved
+ *         pre-activation of fc1, the activated tensor is never stored).
+ *   G = gelu'(gelu_aux[t][n]) if gelu_aux != NULL (GELU backward fused into the fc2 data gradient), else 1.
  *   w_mn_major == 0: W is [N][ldw], K contiguous   (forward nn.Linear weight; conv filter [N][9][Cin])
  *   w_mn_major == 1: W is [K][ldw], N contiguous   (the forward weight of a Linear used for its data gradient dX = dY.W)
  *   conv != 0: X is a [B*H*W][ldx] map, K = 9*Cin, the A rows are 3x3 neighbourhoods (zero padding); shuffle == 2 folds
  *   PixelShuffle(2) into the store (N == 256 = 4 sub-pixels x 64 channels, Y is the [B*2H*2W][ldy] map).
- *   LNhat as in rdst_linear_fwd.  Rows must be 16-byte aligned.  Same layers as rdst_linear_fwd / rdst_conv3x3_fwd. */
+ *   Activation rows must be 16-byte aligned and readable up to the next multiple of 8 columns (pads may hold anything).
+ *   Same layers as rdst_linear_fwd / rdst_conv3x3_fwd / rdst_gelu_fwd / rdst_gelu_bwd. */
 int rdst_gemm_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, int w_mn_major, const float* bias,
-                 const float* resid, int64_t ldr, float* y, int64_t ldy, int64_t T, int K, int N, int ln_creal,
-                 float out_scale, int conv, int B, int H, int W, int Cin, int shuffle, void* stream);
+                 const float* resid, int64_t ldr, const float* gelu_aux, int64_t lda, float* y, int64_t ldy,
+                 int64_t T, int K, int N, int a_op, int ln_creal, float out_scale, int conv, int B, int H, int W,
+                 int Cin, int shuffle, void* stream);
 
-/* Tensor-core version of rdst_gemm_tn_acc (same arguments and meaning; Cin % 16 == 0 in conv mode, 16-byte aligned rows). */
+/* Tensor-core version of rdst_gemm_tn_acc: dW[n][k] += sum_t dY[t][n] * op(X)[t][k], db[n] += sum_t dY[t][n].
+ * x_op: 0 none, 1 LNhat over x_creal real channels (K <= 240), 2 exact-erf GELU -- the normalised / activated operand of
+ * the weight gradient is recomputed while staging instead of being stored.  Cin % 16 == 0 in conv mode. */
 int rdst_gemm_tn_tc(const float* dy, int64_t ldy, const float* x, int64_t ldx, float* dw, float* db, int64_t T,
-                    int N, int K, int conv, int B, int H, int W, int Cin, void* stream);
+                    int N, int K, int conv, int B, int H, int W, int Cin, int x_op, int x_creal, void* stream);
 
 /* ---- tcgen05 / TMEM kernels (bf16 operands, fp32 accumulate), sm_100a only ---------------------------- */
 

@@ -35,8 +35,9 @@ _SIGNATURES = {
     "rdst_gelu_fwd": (C.c_int, [_vp, _i64, _vp, _i64, _i64, _i, _vp]),
     "rdst_gelu_bwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _vp]),
     "rdst_window_attention_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp]),
-    "rdst_gemm_tc": (C.c_int, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _f, _i, _i, _i, _i, _i, _i, _vp]),
-    "rdst_gemm_tn_tc": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
+    "rdst_gemm_tc": (C.c_int, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _f,
+                               _i, _i, _i, _i, _i, _i, _vp]),
+    "rdst_gemm_tn_tc": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rdst_stl_mlp_fwd_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "rdst_stl_attn_fwd_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
     "rdst_conv3x3_fwd_bf16_tc": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _i, _vp]),

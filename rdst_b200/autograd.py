@@ -49,45 +49,67 @@ def _aligned(*ts):
     return all(t is None or (t.data_ptr() % 16 == 0 and (t.dim() < 2 or t.stride(0) % 4 == 0)) for t in ts)
 
 
-def linear(x, w, b, y, K, N, ln_creal=0, act=0, scale=1.0, resid=None):
+def linear(x, w, b, y, K, N, ln_creal=0, scale=1.0, resid=None, gelu_in=False):
+    """y = scale * (op(x) . w^T + b) + resid;  op = LayerNorm-hat (ln_creal > 0), exact-erf GELU (gelu_in) or identity."""
     T = x.shape[0]
-    if _tc() and act == 0 and _aligned(x, y, resid):
-        _call("rdst_gemm_tc", _p(x), _ld(x), _p(w), _ld(w), 0, _p(b), _p(resid), 0 if resid is None else _ld(resid),
-              _p(y), _ld(y), T, K, N, ln_creal, scale, 0, 0, 0, 0, 0, 0, _lib.stream_ptr())
+    if _tc() and _aligned(x, y, resid):
+        _call("rdst_gemm_tc", _p(x), _ld(x), _p(w), _ld(w), 0, _p(b), _p(resid), 0 if resid is None else _ld(resid), None, 0,
+              _p(y), _ld(y), T, K, N, 1 if ln_creal else (2 if gelu_in else 0), ln_creal, scale, 0, 0, 0, 0, 0, 0,
+              _lib.stream_ptr())
         return
     assert w.is_contiguous() and w.shape[-1] == K
+    if gelu_in:
+        act = torch.empty(T, K, dtype=torch.float32, device=x.device)
+        _call("rdst_gelu_fwd", _p(x), _ld(x), _p(act), K, T, K, _lib.stream_ptr())
+        x = act
     _call("rdst_linear_fwd", _p(x), _ld(x), _p(w), _p(b), _p(resid), 0 if resid is None else _ld(resid), _p(y), _ld(y),
-          T, K, N, ln_creal, act, scale, F32, _lib.stream_ptr())
+          T, K, N, ln_creal, 0, scale, F32, _lib.stream_ptr())
 
 
-def linear_t(dy, w, dx, K, N, scale=1.0):
-    """Data gradient of a Linear: dx[T][N] = scale * dy[T][K] . w[K][N]   (w is the forward weight [out=K][in=N])."""
-    if _tc() and _aligned(dy, dx):
-        _call("rdst_gemm_tc", _p(dy), _ld(dy), _p(w), _ld(w), 1, None, None, 0, _p(dx), _ld(dx), dy.shape[0], K, N, 0,
-              scale, 0, 0, 0, 0, 0, 0, _lib.stream_ptr())
+def linear_t(dy, w, dx, K, N, scale=1.0, gelu_aux=None):
+    """Data gradient of a Linear: dx[T][N] = scale * dy[T][K] . w[K][N]   (w is the forward weight [out=K][in=N]),
+    optionally times gelu'(gelu_aux) -- the gradient through the GELU that fed the Linear."""
+    T = dy.shape[0]
+    if _tc() and _aligned(dy, dx, gelu_aux):
+        _call("rdst_gemm_tc", _p(dy), _ld(dy), _p(w), _ld(w), 1, None, None, 0, _p(gelu_aux),
+              0 if gelu_aux is None else _ld(gelu_aux), _p(dx), _ld(dx), T, K, N, 0, 0, scale, 0, 0, 0, 0, 0, 0,
+              _lib.stream_ptr())
         return
-    linear(dy, w.t().contiguous(), torch.zeros(N, dtype=torch.float32, device=dy.device), dx, K, N, scale=scale)
+    wt = w.t().contiguous()
+    zb = torch.zeros(N, dtype=torch.float32, device=dy.device)
+    if gelu_aux is None:
+        linear(dy, wt, zb, dx, K, N, scale=scale)
+    else:
+        tmp = torch.empty(T, N, dtype=torch.float32, device=dy.device)
+        linear(dy, wt, zb, tmp, K, N, scale=scale)
+        _call("rdst_gelu_bwd", _p(gelu_aux), _ld(gelu_aux), _p(tmp), N, _p(dx), _ld(dx), T, N, _lib.stream_ptr())
 
 
 def conv(x, w, b, y, B, H, W, cin, n, scale=1.0, shuffle=0, resid=None):
     if _tc() and cin % 16 == 0 and _aligned(x, y, resid):
-        _call("rdst_gemm_tc", _p(x), _ld(x), _p(w), 9 * cin, 0, _p(b), _p(resid), 0 if resid is None else _ld(resid),
-              _p(y), _ld(y), B * H * W, 9 * cin, n, 0, scale, 1, B, H, W, cin, shuffle, _lib.stream_ptr())
+        _call("rdst_gemm_tc", _p(x), _ld(x), _p(w), 9 * cin, 0, _p(b), _p(resid), 0 if resid is None else _ld(resid), None, 0,
+              _p(y), _ld(y), B * H * W, 9 * cin, n, 0, 0, scale, 1, B, H, W, cin, shuffle, _lib.stream_ptr())
         return
     _call("rdst_conv3x3_fwd", _p(x), _ld(x), _p(w), _p(b), _p(resid), 0 if resid is None else _ld(resid), _p(y), _ld(y),
           B, H, W, cin, n, scale, shuffle, F32, _lib.stream_ptr())
 
 
-def gemm_tn(dy, x, dw, db, N, K, conv_geom=None):
+def gemm_tn(dy, x, dw, db, N, K, conv_geom=None, x_op=0, creal=0):
+    """dw[N][K] += dy^T . op(x), db += column sums of dy;  op: 0 identity, 1 LayerNorm-hat (creal), 2 exact-erf GELU."""
     T = dy.shape[0]
-    name = "rdst_gemm_tn_acc"
+    geom = (0, 0, 0, 0, 0) if conv_geom is None else (1,) + tuple(conv_geom)
     if _tc() and _aligned(dy, x) and dw.data_ptr() % 16 == 0 and (conv_geom is None or conv_geom[3] % 16 == 0):
-        name = "rdst_gemm_tn_tc"
-    if conv_geom is None:
-        _call(name, _p(dy), _ld(dy), _p(x), _ld(x), _p(dw), _p(db), T, N, K, 0, 0, 0, 0, 0, _lib.stream_ptr())
-    else:
-        B, H, W, cin = conv_geom
-        _call(name, _p(dy), _ld(dy), _p(x), _ld(x), _p(dw), _p(db), T, N, K, 1, B, H, W, cin, _lib.stream_ptr())
+        _call("rdst_gemm_tn_tc", _p(dy), _ld(dy), _p(x), _ld(x), _p(dw), _p(db), T, N, K, *geom, x_op, creal,
+              _lib.stream_ptr())
+        return
+    if x_op:
+        tmp = torch.empty(T, K, dtype=torch.float32, device=x.device)
+        if x_op == 1:
+            lnhat(x, tmp, K, creal)
+        else:
+            _call("rdst_gelu_fwd", _p(x), _ld(x), _p(tmp), K, T, K, _lib.stream_ptr())
+        x = tmp
+    _call("rdst_gemm_tn_acc", _p(dy), _ld(dy), _p(x), _ld(x), _p(dw), _p(db), T, N, K, *geom, _lib.stream_ptr())
 
 
 def _pad8(n):
@@ -274,16 +296,14 @@ class BlockFunction(torch.autograd.Function):
                     cp, hp = st["cp"], st["hp"]
                     # tensor-core mode keeps every row 16-byte aligned: q|k|v rows padded to a multiple of 8 floats
                     qkv, o = e(T, _pad8(3 * c) if tc else 3 * c), e(T, cp if tc else c)
-                    x1, hid, act, y = e(T, cp), e(T, hp), e(T, hp), e(T, cp)
+                    x1, hid, y = e(T, cp), e(T, hp), e(T, cp)
                     linear(src, W[st["wqkv"]], W[st["bqkv"]], qkv, cp, 3 * c, ln_creal=c)
                     _call("rdst_window_attention_fwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(o), _ld(o), B, H, Wd, c,
                           packing.HEADS, st["shift"], F32, _lib.stream_ptr())
                     linear(o, W[st["wproj"]], W[st["bproj"]], x1, c, cp, resid=src)
                     linear(x1, W[st["w1"]], W[st["b1"]], hid, cp, hp, ln_creal=c)
-                    _call("rdst_gelu_fwd", _p(hid), hp, _p(act), hp, T, hp, _lib.stream_ptr())
-                    linear(act, W[st["w2"]], W[st["b2"]], y, hp, cp, resid=x1)
+                    linear(hid, W[st["w2"]], W[st["b2"]], y, hp, cp, resid=x1, gelu_in=True)   # act = GELU(hid) not stored
                     sl.append(dict(x=src, qkv=qkv, o=o, x1=x1, hid=hid, y=y))
-                    del act
                     src = y
                 off = 64 + 32 * j
                 linear(src, W[ds["tw"]], W[ds["tb"]], D[:, off:], ds["stl"][0]["cp"], 32, ln_creal=c, scale=ds["scale"])
@@ -323,17 +343,15 @@ class BlockFunction(torch.autograd.Function):
                 off = 64 + 32 * j
                 dg = dD[:, off:off + 32]
                 y1 = sl[-1]["y"]
-                xh = e(T, cp)
-                lnhat(y1, xh, cp, c)
                 gw, gb = gz(ds["tw"]), gz(ds["tb"])
-                gemm_tn(dg, xh, gw, gb, 32, cp)
+                gemm_tn(dg, y1, gw, gb, 32, cp, x_op=1, creal=c)
                 if ds["scale"] != 1.0:
                     gw.mul_(ds["scale"]); gb.mul_(ds["scale"])
                 dxh = e(T, cp)
                 linear_t(dg, W[ds["tw"]], dxh, 32, cp, scale=ds["scale"])
                 dy_cur = e(T, cp)
                 lnhat_bwd(dxh, y1, dy_cur, cp, c)
-                del xh, dxh
+                del dxh
                 for k in range(len(ds["stl"]) - 1, -1, -1):
                     first = k == 0
                     dy_cur = _stl_backward(ds["stl"][k], sl[k], W, gz, dy_cur, B, H, Wd,
@@ -370,9 +388,9 @@ class TailFunction(torch.autograd.Function):
                 conv(feats[-1], W[wi], W[bi], up, B, h, w_, 64, 256, shuffle=2)
                 feats.append(up)
                 h, w_ = 2 * h, 2 * w_
-            out = e(B * h * w_, 1)
-            conv(feats[-1], W[spec["last_w"]], W[spec["last_b"]], out, B, h, w_, 64, 1)
-            out = (out * sc["out_scale"] + sc["out_bias"]).reshape(B, 1, h, w_)
+            out4 = e(B * h * w_, 4)                         # one output channel in a 16-byte row (aligned for the GEMM kernels)
+            conv(feats[-1], W[spec["last_w"]], W[spec["last_b"]], out4, B, h, w_, 64, 1)
+            out = (out4[:, 0] * sc["out_scale"] + sc["out_bias"]).reshape(B, 1, h, w_)
         ctx.spec, ctx.sc, ctx.geom, ctx.W, ctx.saved = spec, sc, geom, W, (X, FN, feats)
         return out
 
@@ -396,11 +414,13 @@ class TailFunction(torch.autograd.Function):
             n_up = len(spec["up"])
             h, w_ = H * (2 ** n_up), Wd * (2 ** n_up)
             # ---- last conv (64 -> 1) + add_mean ----
-            dy = (dout.to(torch.float32) * sc["out_scale"]).reshape(-1, 1).contiguous()
-            gemm_tn(dy, feats[-1], gz(spec["last_w"]), gz(spec["last_b"]), 1, 9 * 64, (B, h, w_, 64))
-            dy16 = z(dy.shape[0], 16); dy16[:, 0] = dy[:, 0]
+            dy16 = z(dout.numel(), 16)                      # the single output channel as column 0 of a 16-wide map
+            dy16[:, 0] = dout.to(torch.float32).reshape(-1) * sc["out_scale"]
+            gw16, gb16 = z(16, 9 * 64), z(16)
+            gemm_tn(dy16, feats[-1], gw16, gb16, 16, 9 * 64, (B, h, w_, 64))
+            G[spec["last_w"]], G[spec["last_b"]] = gw16[:1].reshape(1, 9, 64), gb16[:1]
             wT = z(64, 9, 16); wT[:, :, 0] = conv_dgrad_weight(W[spec["last_w"]])[:, :, 0]
-            dfeat = e(dy.shape[0], 64)
+            dfeat = e(dy16.shape[0], 64)
             conv(dy16, wT, z(64), dfeat, B, h, w_, 16, 64)
             # ---- up-sampling convs + PixelShuffle ----
             for k in range(n_up - 1, -1, -1):
@@ -437,21 +457,15 @@ def _stl_backward(st, sv, W, gz, dY, B, H, Wd, accumulate_into=None):
     z = lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev)
     x, qkv, o, x1, hid = sv["x"], sv["qkv"], sv["o"], sv["x1"], sv["hid"]
     # ---- y = x1 + fc2(gelu(fc1(lnhat(x1)))) ----
-    act = e(T, hp)
-    _call("rdst_gelu_fwd", _p(hid), hp, _p(act), hp, T, hp, _lib.stream_ptr())
-    gemm_tn(dY, act, gz(st["w2"]), gz(st["b2"]), cp, hp)
-    dact = act                                                      # reuse the buffer
-    linear_t(dY, W[st["w2"]], dact, cp, hp)
+    gemm_tn(dY, hid, gz(st["w2"]), gz(st["b2"]), cp, hp, x_op=2)                     # operand GELU(hid) recomputed
     dhid = e(T, hp)
-    _call("rdst_gelu_bwd", _p(hid), hp, _p(dact), hp, _p(dhid), hp, T, hp, _lib.stream_ptr())
-    xh = e(T, cp)
-    lnhat(x1, xh, cp, c)
-    gemm_tn(dhid, xh, gz(st["w1"]), gz(st["b1"]), hp, cp)
+    linear_t(dY, W[st["w2"]], dhid, cp, hp, gelu_aux=hid)                            # (dY . W2) * gelu'(hid)
+    gemm_tn(dhid, x1, gz(st["w1"]), gz(st["b1"]), hp, cp, x_op=1, creal=c)           # operand lnhat(x1) recomputed
     dxh = e(T, cp)
     linear_t(dhid, W[st["w1"]], dxh, hp, cp)
     dX1 = e(T, cp)
     lnhat_bwd(dxh, x1, dX1, cp, c, resid=dY)
-    del act, dhid
+    del dhid
     # ---- x1 = x + proj(attn(lnhat(x))) ----
     gemm_tn(dX1, o, gz(st["wproj"]), gz(st["bproj"]), cp, c)
     dO = torch.empty_like(o)
@@ -459,8 +473,7 @@ def _stl_backward(st, sv, W, gz, dY, B, H, Wd, accumulate_into=None):
     dqkv = torch.empty_like(qkv)
     _call("rdst_window_attention_bwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(dO), _ld(dO), _p(dqkv), _ld(dqkv),
           _p(gz(st["table"])), B, H, Wd, c, packing.HEADS, st["shift"], _lib.stream_ptr())
-    lnhat(x, xh, cp, c)
-    gemm_tn(dqkv, xh, gz(st["wqkv"]), gz(st["bqkv"]), 3 * c, cp)
+    gemm_tn(dqkv, x, gz(st["wqkv"]), gz(st["bqkv"]), 3 * c, cp, x_op=1, creal=c)
     linear_t(dqkv, W[st["wqkv"]], dxh, 3 * c, cp)
     if accumulate_into is None:
         dX = e(T, cp)

@@ -30,12 +30,14 @@ constexpr int NTHREADS = 256;
 
 struct GemmArgs {
   const float* x; int64_t ldx;
-  const float* w; int64_t ldw; int w_mn;
+  const float* w; int64_t ldw; int w_mn, w_vec;
   const float* bias; const float* resid; int64_t ldr;
+  const float* aux; int64_t lda;   // epilogue: acc *= gelu'(aux[t][n])  (GELU backward fused into the data-gradient GEMM)
   float* y; int64_t ldy;
   int64_t T; int K, N, Np;       // Np = N rounded up to 16
   int KC, nkc;                   // K-chunk (multiple of 16, <= 256 or the whole padded K) and number of chunks
-  int ln_creal; float out_scale;
+  int a_op, ln_creal;            // A prologue: 0 none, 1 LayerNorm-hat over ln_creal real channels, 2 exact-erf GELU
+  float out_scale;
   int conv, B, H, W, Cin, shuffle;
 };
 
@@ -48,15 +50,29 @@ __device__ __forceinline__ uint4 pack8(const float4& a, const float4& b) {
   return r;
 }
 
-// 8 consecutive floats starting at p, of which the first `valid` (0..8) are real; the rest read as 0.  Activation rows are
-// always 16-byte aligned (checked on the host); weight rows of odd width (C = 90) take the scalar path.
-__device__ __forceinline__ void load8(const float* p, int valid, float4& a, float4& b) {
-  a = make_float4(0.f, 0.f, 0.f, 0.f);
-  b = a;
-  if (valid >= 8 && ((uintptr_t)p & 15) == 0) {
+__device__ __forceinline__ float4 zero4() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+
+// Activation rows are 16-byte aligned and readable up to the next multiple of 8 columns (checked on the host), so a chunk
+// is always two vector loads; columns >= valid are zeroed afterwards (pads may hold anything, 0 * NaN must not reach the MMA)
+__device__ __forceinline__ void mask8(int valid, float4& a, float4& b) {
+  if (valid < 8) {
+    if (valid < 1) a.x = 0.f;
+    if (valid < 2) a.y = 0.f;
+    if (valid < 3) a.z = 0.f;
+    if (valid < 4) a.w = 0.f;
+    if (valid < 5) b.x = 0.f;
+    if (valid < 6) b.y = 0.f;
+    if (valid < 7) b.z = 0.f;
+    b.w = 0.f;
+  }
+}
+
+// weight rows: vector loads when every row is 16-byte aligned (vec), else scalar (rows of 90 floats, C = 90)
+__device__ __forceinline__ void load_w8(const float* p, int valid, bool vec, float4& a, float4& b) {
+  if (vec && valid >= 8) {
     a = __ldg(reinterpret_cast<const float4*>(p));
     b = __ldg(reinterpret_cast<const float4*>(p) + 1);
-  } else if (valid > 0) {
+  } else {
     float t[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) t[j] = j < valid ? __ldg(p + j) : 0.f;
@@ -65,18 +81,87 @@ __device__ __forceinline__ void load8(const float* p, int valid, float4& a, floa
   }
 }
 
+// address of the 8-column chunk starting at column k of token t's GEMM row (3x3 gather in conv mode); nullptr = zeros
+__device__ __forceinline__ const float* act_chunk(const float* x, int64_t ldx, int64_t t, int64_t T, int k, int K, int conv,
+                                                  int Cin, int H, int W, int HW) {
+  if (t >= T || k >= K) return nullptr;
+  if (!conv) return x + t * ldx + k;
+  const int tap = k / Cin, ci = k - tap * Cin;
+  const int b = (int)(t / HW), rem = (int)(t - (int64_t)b * HW);
+  const int yy = rem / W;
+  const int py = yy + tap / 3 - 1, px = rem - yy * W + tap % 3 - 1;
+  if (py < 0 || py >= H || px < 0 || px >= W) return nullptr;
+  return x + ((int64_t)b * HW + (int64_t)py * W + px) * ldx + ci;
+}
+
+__device__ __forceinline__ float gelu_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752440f)) + x * 0.39894228040143267794f * __expf(-0.5f * x * x);
+}
+
+__device__ __forceinline__ void apply_op(int op, float m, float rs, float4& a, float4& b) {
+  if (op == 1) {
+    a = make_float4((a.x - m) * rs, (a.y - m) * rs, (a.z - m) * rs, (a.w - m) * rs);
+    b = make_float4((b.x - m) * rs, (b.y - m) * rs, (b.z - m) * rs, (b.w - m) * rs);
+  } else if (op == 2) {
+    a = make_float4(gelu_erf(a.x), gelu_erf(a.y), gelu_erf(a.z), gelu_erf(a.w));
+    b = make_float4(gelu_erf(b.x), gelu_erf(b.y), gelu_erf(b.z), gelu_erf(b.w));
+  }
+}
+
 __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// LayerNorm statistics of 128 consecutive rows (one warp per row, four rows in flight): mean / rstd over the K stored
+// values divided by creal real channels (pads are zero), as rdst_linear_fwd.
+__device__ __forceinline__ void row_stats(const float* x, int64_t ldx, int64_t t0, int64_t T, int K, int creal, float* s_mean,
+                                          float* s_rstd, int warp, int lane) {
+  const float inv = 1.f / (float)creal;
+  for (int r0 = warp * 4; r0 < TM; r0 += (NTHREADS / 32) * 4) {
+    float s[4], ss[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      s[u] = ss[u] = 0.f;
+      const int64_t t = t0 + r0 + u;
+      if (t < T) {
+        const float* row = x + t * ldx;
+        for (int k = lane * 4; k < K; k += 128) {
+          const float4 v = __ldg(reinterpret_cast<const float4*>(row + k));
+          s[u] += v.x + v.y + v.z + v.w;
+          ss[u] += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        s[u] += __shfl_xor_sync(0xffffffffu, s[u], o);
+        ss[u] += __shfl_xor_sync(0xffffffffu, ss[u], o);
+      }
+    }
+    if (lane < 4) {                            // lane u publishes row r0+u (all lanes hold all four sums)
+      const float sv = lane == 0 ? s[0] : lane == 1 ? s[1] : lane == 2 ? s[2] : s[3];
+      const float qv = lane == 0 ? ss[0] : lane == 1 ? ss[1] : lane == 2 ? ss[2] : ss[3];
+      const float mean = sv * inv;
+      const float var = fmaxf(qv * inv - mean * mean, 0.f);
+      s_mean[r0 + lane] = mean;
+      s_rstd[r0 + lane] = rsqrtf(var + 1e-5f);
+    }
+  }
+}
+
+constexpr int U = 4;                      // independent chunk loads in flight per thread while staging
+
 // ------------------------------------------------------------------------------------------------------------------
-// Y = scale * (LNhat(X) . Wop + bias) + R
+// Y = scale * (op(X) . Wop + bias) [* gelu'(aux)] + R
 // ------------------------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_mean[TM], s_rstd[TM];
+  __shared__ float s_bias[512];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KC = a.KC, Np = a.Np;
   uint8_t* sA = smem;                               // K-major [KC/8][128][8] bf16
@@ -84,6 +169,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) 
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  for (int n = tid; n < Np; n += NTHREADS) s_bias[n] = (a.bias && n < a.N) ? __ldg(a.bias + n) : 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -95,35 +181,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) 
   const int chg = (nch + 3) >> 2;                   // chunk groups of 4
   const int64_t ntiles = (a.T + TM - 1) / TM;
   const int HW = a.H * a.W;
+  constexpr int NW = NTHREADS / 32;
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t t0 = tile * TM;
-    // ---- LayerNorm statistics of the tile's rows (one warp per row, coalesced) ----
-    if (a.ln_creal > 0) {
-      for (int r = warp; r < TM; r += NTHREADS / 32) {
-        const int64_t t = t0 + r;
-        float s = 0.f, ss = 0.f;
-        if (t < a.T) {
-          const float* row = a.x + t * a.ldx;
-          for (int k = lane * 4; k < a.K; k += 128) {
-            const float4 v = __ldg(reinterpret_cast<const float4*>(row + k));
-            s += v.x + v.y + v.z + v.w;
-            ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
-          }
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) {
-          s += __shfl_xor_sync(0xffffffffu, s, o);
-          ss += __shfl_xor_sync(0xffffffffu, ss, o);
-        }
-        if (lane == 0) {
-          const float inv = 1.f / (float)a.ln_creal;
-          const float mean = s * inv;
-          const float var = fmaxf(ss * inv - mean * mean, 0.f);
-          s_mean[r] = mean;
-          s_rstd[r] = rsqrtf(var + 1e-5f);
-        }
-      }
+    if (a.a_op == 1) {
+      row_stats(a.x, a.ldx, t0, a.T, a.K, a.ln_creal, s_mean, s_rstd, warp, lane);
       __syncthreads();
     }
     for (int kc = 0; kc < a.nkc; ++kc) {
@@ -133,62 +196,85 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) 
         phase ^= 1;
         fence_after_sync();
       }
-      // ---- stage A: rows = tokens, K-major image ----
-      for (int blk = warp; blk < 16 * chg; blk += NTHREADS / 32) {
-        const int r = (blk % 16) * 8 + r8;
-        const int ch = (blk / 16) * 4 + c4;
-        if (ch >= nch) continue;
-        const int k = k0 + ch * 8;                   // first of 8 columns
-        const int64_t t = t0 + r;
-        float4 v0, v1;
-        if (t >= a.T || k >= a.K) {
-          v0 = make_float4(0.f, 0.f, 0.f, 0.f);
-          v1 = v0;
-        } else if (!a.conv) {
-          load8(a.x + t * a.ldx + k, a.K - k, v0, v1);
-          if (a.ln_creal > 0) {
-            const float m = s_mean[r], rs = s_rstd[r];
-            v0 = make_float4((v0.x - m) * rs, (v0.y - m) * rs, (v0.z - m) * rs, (v0.w - m) * rs);
-            v1 = make_float4((v1.x - m) * rs, (v1.y - m) * rs, (v1.z - m) * rs, (v1.w - m) * rs);
-          }
-        } else {
-          const int tap = k / a.Cin, ci = k - tap * a.Cin;
-          const int b = (int)(t / HW), rem = (int)(t - (int64_t)b * HW);
-          const int py = rem / a.W + tap / 3 - 1, px = rem % a.W + tap % 3 - 1;
-          if (py < 0 || py >= a.H || px < 0 || px >= a.W) {
-            v0 = make_float4(0.f, 0.f, 0.f, 0.f);
-            v1 = v0;
+      // ---- stage A: rows = tokens, K-major image; U chunk loads in flight per thread ----
+      for (int b0 = warp; b0 < 16 * chg; b0 += NW * U) {
+        float4 v0[U], v1[U];
+        int valid[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int blk = b0 + u * NW;
+          const int r = (blk & 15) * 8 + r8, ch = (blk >> 4) * 4 + c4;
+          const int k = k0 + ch * 8;
+          const float* p = (blk < 16 * chg && ch < nch)
+                               ? act_chunk(a.x, a.ldx, t0 + r, a.T, k, a.K, a.conv, a.Cin, a.H, a.W, HW) : nullptr;
+          valid[u] = p ? min(8, a.K - k) : 0;
+          if (p) {
+            v0[u] = __ldg(reinterpret_cast<const float4*>(p));
+            v1[u] = __ldg(reinterpret_cast<const float4*>(p) + 1);
           } else {
-            load8(a.x + ((int64_t)b * HW + (int64_t)py * a.W + px) * a.ldx + ci, 8, v0, v1);
+            v0[u] = zero4();
+            v1[u] = zero4();
           }
         }
-        *reinterpret_cast<uint4*>(sA + (size_t)ch * (TM * 16) + r * 16) = pack8(v0, v1);
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int blk = b0 + u * NW;
+          const int r = (blk & 15) * 8 + r8, ch = (blk >> 4) * 4 + c4;
+          if (blk < 16 * chg && ch < nch) {
+            if (valid[u] > 0) {
+              mask8(valid[u], v0[u], v1[u]);
+              apply_op(a.a_op, s_mean[r], s_rstd[r], v0[u], v1[u]);
+            }
+            *reinterpret_cast<uint4*>(sA + (size_t)ch * (TM * 16) + r * 16) = pack8(v0[u], v1[u]);
+          }
+        }
       }
       // ---- stage B (weights): once per CTA when there is a single K-chunk ----
       if (a.nkc > 1 || tile == blockIdx.x) {
+        const bool vec = a.w_vec != 0;
         if (!a.w_mn) {
           // W [N][ldw] (K contiguous) -> K-major image: (k/8)*(Np*16) + n*16
           const int ng = Np >> 3;
-          for (int blk = warp; blk < ng * chg; blk += NTHREADS / 32) {
-            const int n = (blk % ng) * 8 + r8;
-            const int ch = (blk / ng) * 4 + c4;
-            if (ch >= nch) continue;
-            const int k = k0 + ch * 8;
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            if (n < a.N && k < a.K) load8(a.w + (int64_t)n * a.ldw + k, a.K - k, v0, v1);
-            *reinterpret_cast<uint4*>(sB + (size_t)ch * (Np * 16) + n * 16) = pack8(v0, v1);
+          for (int b0 = warp; b0 < ng * chg; b0 += NW * U) {
+            float4 v0[U], v1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int blk = b0 + u * NW;
+              const int n = (blk % ng) * 8 + r8, ch = (blk / ng) * 4 + c4;
+              const int k = k0 + ch * 8;
+              v0[u] = zero4();
+              v1[u] = zero4();
+              if (blk < ng * chg && ch < nch && n < a.N && k < a.K) load_w8(a.w + (int64_t)n * a.ldw + k, a.K - k, vec, v0[u], v1[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int blk = b0 + u * NW;
+              const int n = (blk % ng) * 8 + r8, ch = (blk / ng) * 4 + c4;
+              if (blk < ng * chg && ch < nch) *reinterpret_cast<uint4*>(sB + (size_t)ch * (Np * 16) + n * 16) = pack8(v0[u], v1[u]);
+            }
           }
         } else {
           // W [K][ldw] (N contiguous) -> MN-major image: (k/8)*128 + (n/8)*(nch*128) + (k%8)*16
           const int ncg = ((Np >> 3) + 3) >> 2;
-          for (int blk = warp; blk < nch * ncg; blk += NTHREADS / 32) {
-            const int kk = (blk % nch) * 8 + r8;         // k within the chunk
-            const int n8 = (blk / nch) * 4 + c4;
-            if (n8 >= (Np >> 3)) continue;
-            const int k = k0 + kk, n = n8 * 8;
-            float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-            if (k < a.K && n < a.N) load8(a.w + (int64_t)k * a.ldw + n, a.N - n, v0, v1);
-            *reinterpret_cast<uint4*>(sB + (size_t)(kk >> 3) * 128 + (size_t)n8 * (nch * 128) + (kk & 7) * 16) = pack8(v0, v1);
+          for (int b0 = warp; b0 < nch * ncg; b0 += NW * U) {
+            float4 v0[U], v1[U];
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int blk = b0 + u * NW;
+              const int kk = (blk % nch) * 8 + r8, n8 = (blk / nch) * 4 + c4;
+              const int k = k0 + kk, n = n8 * 8;
+              v0[u] = zero4();
+              v1[u] = zero4();
+              if (blk < nch * ncg && n8 < (Np >> 3) && k < a.K && n < a.N)
+                load_w8(a.w + (int64_t)k * a.ldw + n, a.N - n, vec, v0[u], v1[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < U; ++u) {
+              const int blk = b0 + u * NW;
+              const int kk = (blk % nch) * 8 + r8, n8 = (blk / nch) * 4 + c4;
+              if (blk < nch * ncg && n8 < (Np >> 3))
+                *reinterpret_cast<uint4*>(sB + (size_t)(kk >> 3) * 128 + (size_t)n8 * (nch * 128) + (kk & 7) * 16) = pack8(v0[u], v1[u]);
+            }
           }
         }
       }
@@ -246,14 +332,18 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) 
         }
         float* yp = a.y + yrow * a.ldy + ncol;
         const float* rp = a.resid ? a.resid + t * a.ldr + n0 : nullptr;
+        const float* ap = a.aux ? a.aux + t * a.lda + n0 : nullptr;
         float o[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) {
-          float acc = __uint_as_float(v[j]);
-          if (a.bias && n0 + j < a.N) acc += __ldg(a.bias + n0 + j);
-          o[j] = acc * a.out_scale;
-        }
+        for (int j = 0; j < 16; ++j) o[j] = (__uint_as_float(v[j]) + s_bias[n0 + j]) * a.out_scale;
         if (n0 + 16 <= a.N) {
+          if (ap) {
+#pragma unroll
+            for (int j = 0; j < 16; j += 4) {
+              const float4 h = __ldg(reinterpret_cast<const float4*>(ap + j));
+              o[j] *= gelu_grad(h.x); o[j + 1] *= gelu_grad(h.y); o[j + 2] *= gelu_grad(h.z); o[j + 3] *= gelu_grad(h.w);
+            }
+          }
           if (rp) {
 #pragma unroll
             for (int j = 0; j < 16; j += 4) {
@@ -266,7 +356,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) 
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
-            if (n0 + j < a.N) yp[j] = o[j] + (rp ? rp[j] : 0.f);
+            if (n0 + j < a.N) yp[j] = o[j] * (ap ? gelu_grad(ap[j]) : 1.f) + (rp ? rp[j] : 0.f);
         }
       }
     }
@@ -278,7 +368,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) 
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// dW[N][K] += dY^T X   (+ db)
+// dW[N][K] += dY^T op(X)   (+ db)
 // ------------------------------------------------------------------------------------------------------------------
 struct TnArgs {
   const float* dy; int64_t ldy; const float* x; int64_t ldx; float* dw; float* db;
@@ -286,12 +376,14 @@ struct TnArgs {
   int KCW;                      // columns of X (k) per CTA, multiple of 16, <= 240
   int64_t t_per_split;          // multiple of 128
   int conv, B, H, W, Cin;
+  int x_op, x_creal;            // prologue on X: 0 none, 1 LayerNorm-hat (x_creal real channels), 2 exact-erf GELU
 };
 
 __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const TnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
+  __shared__ float s_mean[TM], s_rstd[TM];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * TM;                   // first output row (n) of this CTA
   const int k0 = blockIdx.y * a.KCW;                // first output column (k)
@@ -314,6 +406,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const TnArgs a)
   const int64_t te = min(a.T, ts + a.t_per_split);
   const int HW = a.H * a.W;
   const int nbc = NB >> 3;                          // 8-column chunks of the B image
+  const int nbg = (nbc + 3) >> 2;
+  constexpr int NW = NTHREADS / 32;
   bool first = true;
   for (int64_t t0 = ts; t0 < te; t0 += TM) {
     if (!first) {
@@ -321,40 +415,69 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const TnArgs a)
       phase ^= 1;
       fence_after_sync();
     }
-    // ---- A image: dY[t][m0 .. m0+128) ----
-    for (int blk = warp; blk < 16 * 4; blk += NTHREADS / 32) {
-      const int tt = (blk % 16) * 8 + r8;
-      const int ch = (blk / 16) * 4 + c4;           // 16 chunks of 8 n
-      const int64_t t = t0 + tt;
-      const int n = m0 + ch * 8;
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-      if (t < te && n < a.N) load8(a.dy + t * a.ldy + n, a.N - n, v0, v1);
-      *reinterpret_cast<uint4*>(sA + (size_t)(tt >> 3) * 128 + (size_t)ch * 2048 + (tt & 7) * 16) = pack8(v0, v1);
+    if (a.x_op == 1) {
+      row_stats(a.x, a.ldx, t0, te, a.K, a.x_creal, s_mean, s_rstd, warp, lane);
+      __syncthreads();
     }
-    // ---- B image: X[t][k0 .. k0+KCW) (3x3 gather in conv mode) + ones column ----
-    for (int blk = warp; blk < 16 * ((nbc + 3) >> 2); blk += NTHREADS / 32) {
-      const int tt = (blk % 16) * 8 + r8;
-      const int ch = (blk / 16) * 4 + c4;
-      if (ch >= nbc) continue;
-      const int64_t t = t0 + tt;
-      float4 v0 = make_float4(0.f, 0.f, 0.f, 0.f), v1 = v0;
-      if (ch * 8 >= a.KCW) {
-        if (ch * 8 == a.KCW && t < te) v0.x = 1.f;  // the ones column: accumulates db[n] = sum_t dY[t][n]
-      } else {
-        const int k = k0 + ch * 8;
-        if (t < te && k < a.K) {
-          if (!a.conv) {
-            load8(a.x + t * a.ldx + k, a.K - k, v0, v1);
-          } else {
-            const int tap = k / a.Cin, ci = k - tap * a.Cin;
-            const int b = (int)(t / HW), rem = (int)(t - (int64_t)b * HW);
-            const int py = rem / a.W + tap / 3 - 1, px = rem % a.W + tap % 3 - 1;
-            if (py >= 0 && py < a.H && px >= 0 && px < a.W)
-              load8(a.x + ((int64_t)b * HW + (int64_t)py * a.W + px) * a.ldx + ci, 8, v0, v1);
-          }
+    // ---- A image: dY[t][m0 .. m0+128) ----
+    for (int b0 = warp; b0 < 16 * 4; b0 += NW * U) {
+      float4 v0[U], v1[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int blk = b0 + u * NW;
+        const int tt = (blk & 15) * 8 + r8, ch = (blk >> 4) * 4 + c4;       // 16 chunks of 8 n
+        const int64_t t = t0 + tt;
+        const int n = m0 + ch * 8;
+        v0[u] = zero4();
+        v1[u] = zero4();
+        if (t < te && n < a.N) {
+          const float* p = a.dy + t * a.ldy + n;
+          v0[u] = __ldg(reinterpret_cast<const float4*>(p));
+          v1[u] = __ldg(reinterpret_cast<const float4*>(p) + 1);
+          mask8(a.N - n, v0[u], v1[u]);
         }
       }
-      *reinterpret_cast<uint4*>(sB + (size_t)(tt >> 3) * 128 + (size_t)ch * 2048 + (tt & 7) * 16) = pack8(v0, v1);
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int blk = b0 + u * NW;
+        const int tt = (blk & 15) * 8 + r8, ch = (blk >> 4) * 4 + c4;
+        *reinterpret_cast<uint4*>(sA + (size_t)(tt >> 3) * 128 + (size_t)ch * 2048 + (tt & 7) * 16) = pack8(v0[u], v1[u]);
+      }
+    }
+    // ---- B image: op(X)[t][k0 .. k0+KCW) (3x3 gather in conv mode) + ones column ----
+    for (int b0 = warp; b0 < 16 * nbg; b0 += NW * U) {
+      float4 v0[U], v1[U];
+      int valid[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int blk = b0 + u * NW;
+        const int tt = (blk & 15) * 8 + r8, ch = (blk >> 4) * 4 + c4;
+        const int k = k0 + ch * 8;
+        const float* p = (blk < 16 * nbg && ch * 8 < a.KCW)
+                             ? act_chunk(a.x, a.ldx, t0 + tt, te, k, a.K, a.conv, a.Cin, a.H, a.W, HW) : nullptr;
+        valid[u] = p ? min(8, a.K - k) : 0;
+        if (p) {
+          v0[u] = __ldg(reinterpret_cast<const float4*>(p));
+          v1[u] = __ldg(reinterpret_cast<const float4*>(p) + 1);
+        } else {
+          v0[u] = zero4();
+          v1[u] = zero4();
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int blk = b0 + u * NW;
+        const int tt = (blk & 15) * 8 + r8, ch = (blk >> 4) * 4 + c4;
+        if (blk < 16 * nbg && ch < nbc) {
+          if (valid[u] > 0) {
+            mask8(valid[u], v0[u], v1[u]);
+            apply_op(a.x_op, s_mean[tt], s_rstd[tt], v0[u], v1[u]);
+            if (a.x_op == 1) mask8(valid[u], v0[u], v1[u]);
+          }
+          if (ch * 8 == a.KCW && t0 + tt < te) v0[u].x = 1.f;   // the ones column: accumulates db[n] = sum_t dY[t][n]
+          *reinterpret_cast<uint4*>(sB + (size_t)(tt >> 3) * 128 + (size_t)ch * 2048 + (tt & 7) * 16) = pack8(v0[u], v1[u]);
+        }
+      }
     }
     fence_proxy_async();
     fence_before_sync();
@@ -432,8 +555,9 @@ int sm_count() {
 }  // namespace rdst
 
 extern "C" int rdst_gemm_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, int w_mn_major, const float* bias,
-                            const float* resid, int64_t ldr, float* y, int64_t ldy, int64_t T, int K, int N, int ln_creal,
-                            float out_scale, int conv, int B, int H, int W, int Cin, int shuffle, void* stream) {
+                            const float* resid, int64_t ldr, const float* gelu_aux, int64_t lda, float* y, int64_t ldy,
+                            int64_t T, int K, int N, int a_op, int ln_creal, float out_scale, int conv, int B, int H, int W,
+                            int Cin, int shuffle, void* stream) {
   using namespace rdst;
   RDST_REQUIRE(x && w && y, "rdst_gemm_tc: null pointer");
   RDST_REQUIRE(T >= 0 && K > 0 && N > 0 && N <= 512, "rdst_gemm_tc: bad shape (T=%lld K=%d N=%d; N <= 512)", (long long)T, K, N);
@@ -441,13 +565,17 @@ extern "C" int rdst_gemm_tc(const float* x, int64_t ldx, const float* w, int64_t
                    ((uintptr_t)x & 15) == 0 && ((uintptr_t)y & 15) == 0 &&
                    (!resid || ((uintptr_t)resid & 15) == 0),
                "rdst_gemm_tc: activation rows must be 16-byte aligned (pointers and leading dimensions multiples of 4 floats)");
-  RDST_REQUIRE(!conv || (Cin > 0 && Cin % 16 == 0 && K == 9 * Cin && T == (int64_t)B * H * W && !w_mn_major && !ln_creal),
-               "rdst_gemm_tc: conv mode needs Cin %% 16 == 0, K == 9*Cin, T == B*H*W, K-major weights, no LayerNorm");
+  RDST_REQUIRE(!conv || (Cin > 0 && Cin % 16 == 0 && K == 9 * Cin && T == (int64_t)B * H * W && !w_mn_major && !a_op && ldx >= Cin),
+               "rdst_gemm_tc: conv mode needs Cin %% 16 == 0, K == 9*Cin, T == B*H*W, K-major weights, no prologue");
+  RDST_REQUIRE(conv || ldx >= (K + 7) / 8 * 8, "rdst_gemm_tc: rows of X must be readable up to the next multiple of 8 columns");
+  RDST_REQUIRE(a_op >= 0 && a_op <= 2 && (!gelu_aux || ((lda & 3) == 0 && ((uintptr_t)gelu_aux & 15) == 0)), "rdst_gemm_tc: bad a_op / aux");
   RDST_REQUIRE(!shuffle || (conv && shuffle == 2 && N == 256 && !resid), "rdst_gemm_tc: shuffle=2 needs conv mode, N == 256, no residual");
-  RDST_REQUIRE(!ln_creal || (ln_creal <= K && K <= 512 && !conv), "rdst_gemm_tc: bad LayerNorm width");
+  RDST_REQUIRE(a_op != 1 || (ln_creal > 0 && ln_creal <= K && (K & 3) == 0), "rdst_gemm_tc: bad LayerNorm width");
   if (T == 0) return RDST_OK;
   GemmArgs a{};
   a.x = x; a.ldx = ldx; a.w = w; a.ldw = ldw; a.w_mn = w_mn_major; a.bias = bias; a.resid = resid; a.ldr = ldr;
+  a.w_vec = ((ldw & 3) == 0 && ((uintptr_t)w & 15) == 0) ? 1 : 0;
+  a.aux = gelu_aux; a.lda = lda; a.a_op = a_op;
   a.y = y; a.ldy = ldy; a.T = T; a.K = K; a.N = N; a.Np = (N + 15) / 16 * 16;
   a.ln_creal = ln_creal; a.out_scale = out_scale;
   a.conv = conv; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.shuffle = shuffle;
@@ -471,19 +599,23 @@ extern "C" int rdst_gemm_tc(const float* x, int64_t ldx, const float* w, int64_t
 }
 
 extern "C" int rdst_gemm_tn_tc(const float* dy, int64_t ldy, const float* x, int64_t ldx, float* dw, float* db, int64_t T,
-                               int N, int K, int conv, int B, int H, int W, int Cin, void* stream) {
+                               int N, int K, int conv, int B, int H, int W, int Cin, int x_op, int x_creal, void* stream) {
   using namespace rdst;
   RDST_REQUIRE(dy && x && dw, "rdst_gemm_tn_tc: null pointer");
   RDST_REQUIRE(T >= 0 && N > 0 && K > 0, "rdst_gemm_tn_tc: bad shape");
   RDST_REQUIRE((ldx & 3) == 0 && (ldy & 3) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dy & 15) == 0 &&
                    ((uintptr_t)dw & 15) == 0,
                "rdst_gemm_tn_tc: rows must be 16-byte aligned (pointers and leading dimensions multiples of 4 floats)");
-  RDST_REQUIRE(!conv || (Cin > 0 && Cin % 16 == 0 && K == 9 * Cin && T == (int64_t)B * H * W),
-               "rdst_gemm_tn_tc: conv mode needs Cin %% 16 == 0, K == 9*Cin and T == B*H*W");
+  RDST_REQUIRE(!conv || (Cin > 0 && Cin % 16 == 0 && K == 9 * Cin && T == (int64_t)B * H * W && ldx >= Cin && !x_op),
+               "rdst_gemm_tn_tc: conv mode needs Cin %% 16 == 0, K == 9*Cin, T == B*H*W and no prologue");
+  RDST_REQUIRE(ldy >= (N + 7) / 8 * 8 && (conv || ldx >= (K + 7) / 8 * 8),
+               "rdst_gemm_tn_tc: rows of dY / X must be readable up to the next multiple of 8 columns");
+  RDST_REQUIRE(x_op >= 0 && x_op <= 2 && (x_op != 1 || (x_creal > 0 && x_creal <= K && K <= 240 && (K & 3) == 0)),
+               "rdst_gemm_tn_tc: bad prologue (LayerNorm needs the whole row in one column chunk: K <= 240)");
   if (T == 0) return RDST_OK;
   TnArgs a{};
   a.dy = dy; a.ldy = ldy; a.x = x; a.ldx = ldx; a.dw = dw; a.db = db; a.T = T; a.N = N; a.K = K;
-  a.conv = conv; a.B = B; a.H = H; a.W = W; a.Cin = Cin;
+  a.conv = conv; a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.x_op = x_op; a.x_creal = x_creal;
   const int Kp = (K + 15) / 16 * 16;
   const int kchunks = (Kp + 239) / 240;
   a.KCW = ((Kp + kchunks - 1) / kchunks + 15) / 16 * 16;

@@ -59,8 +59,8 @@ def test_gemm_tc_linear(T, K, ldx, N, ldy, ln, w_mn, resid):
     r = torch.randn(T, ldy, device="cuda", generator=g) if resid else None
     y = torch.full((T, ldy), 7.0, device="cuda")
     scale = 0.75
-    L.call("rdst_gemm_tc", L.ptr(x), ldx, L.ptr(w), w.stride(0), w_mn, L.ptr(b), L.ptr(r), ldy if resid else 0, L.ptr(y), ldy,
-           T, K, N, ln, scale, 0, 0, 0, 0, 0, 0, L.stream_ptr())
+    L.call("rdst_gemm_tc", L.ptr(x), ldx, L.ptr(w), w.stride(0), w_mn, L.ptr(b), L.ptr(r), ldy if resid else 0, None, 0, L.ptr(y), ldy,
+           T, K, N, 1 if ln else 0, ln, scale, 0, 0, 0, 0, 0, 0, L.stream_ptr())
     torch.cuda.synchronize()
     a = x[:, :K]
     if ln:
@@ -95,8 +95,8 @@ def test_gemm_tc_conv(B, H, W, cin, ldx, n, shuffle, resid):
     r = torch.randn(T, 160, device="cuda", generator=g) if resid else None
     Ty = T * 4 if shuffle else T
     y = torch.zeros(Ty, ldy, device="cuda")
-    L.call("rdst_gemm_tc", L.ptr(x), ldx, L.ptr(w), 9 * cin, 0, L.ptr(b), L.ptr(r), 160 if resid else 0, L.ptr(y), ldy,
-           T, 9 * cin, n, 0, 0.5, 1, B, H, W, cin, shuffle, L.stream_ptr())
+    L.call("rdst_gemm_tc", L.ptr(x), ldx, L.ptr(w), 9 * cin, 0, L.ptr(b), L.ptr(r), 160 if resid else 0, None, 0, L.ptr(y), ldy,
+           T, 9 * cin, n, 0, 0, 0.5, 1, B, H, W, cin, shuffle, L.stream_ptr())
     torch.cuda.synchronize()
     xi = bf(x[:, :cin]).reshape(B, H, W, cin).permute(0, 3, 1, 2)
     wt = bf(w).reshape(n, 3, 3, cin).permute(0, 3, 1, 2)
@@ -126,7 +126,7 @@ def test_gemm_tn_tc_linear(T, N, ldy, K, ldx, bias):
     x = torch.randn(T, ldx, device="cuda", generator=g)
     dw = torch.ones(N, K, device="cuda")
     db = torch.ones(N, device="cuda") if bias else None
-    L.call("rdst_gemm_tn_tc", L.ptr(dy), ldy, L.ptr(x), ldx, L.ptr(dw), L.ptr(db), T, N, K, 0, 0, 0, 0, 0, L.stream_ptr())
+    L.call("rdst_gemm_tn_tc", L.ptr(dy), ldy, L.ptr(x), ldx, L.ptr(dw), L.ptr(db), T, N, K, 0, 0, 0, 0, 0, 0, 0, L.stream_ptr())
     torch.cuda.synchronize()
     ref = bf(dy[:, :N]).t() @ bf(x[:, :K]) + 1.0
     _close(dw, ref)
@@ -143,13 +143,47 @@ def test_gemm_tn_tc_conv(B, H, W, N, cin):
     x = torch.randn(T, cin, device="cuda", generator=g)
     dw = torch.zeros(N, 9 * cin, device="cuda")
     db = torch.zeros(N, device="cuda")
-    L.call("rdst_gemm_tn_tc", L.ptr(dy), N, L.ptr(x), cin, L.ptr(dw), L.ptr(db), T, N, 9 * cin, 1, B, H, W, cin, L.stream_ptr())
+    L.call("rdst_gemm_tn_tc", L.ptr(dy), N, L.ptr(x), cin, L.ptr(dw), L.ptr(db), T, N, 9 * cin, 1, B, H, W, cin, 0, 0, L.stream_ptr())
     torch.cuda.synchronize()
     xi = bf(x).reshape(B, H, W, cin).permute(0, 3, 1, 2)
     cols = F.unfold(xi, 3, padding=1).reshape(B, cin, 9, H * W).permute(0, 3, 2, 1).reshape(T, 9 * cin)   # [t][tap][ci]
     ref = bf(dy).t() @ cols
     _close(dw, ref)
     _close(db, bf(dy).sum(0))
+
+
+def test_gemm_tc_fused_gelu_and_lnhat_operands():
+    """fc2 reads GELU(hid) (a_op 2), the fc2 data gradient is multiplied by gelu'(hid), and the weight gradients
+    recompute their GELU / LayerNorm-hat operand while staging (x_op 2 / 1)."""
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(7)
+    T, hp, cp, c = 1000, 240, 128, 120
+    hid = torch.randn(T, hp, device="cuda", generator=g)
+    w2 = torch.randn(cp, hp, device="cuda", generator=g) * 0.1
+    b2 = torch.randn(cp, device="cuda", generator=g)
+    y = torch.zeros(T, cp, device="cuda")
+    L.call("rdst_gemm_tc", L.ptr(hid), hp, L.ptr(w2), hp, 0, L.ptr(b2), None, 0, None, 0, L.ptr(y), cp,
+           T, hp, cp, 2, 0, 1.0, 0, 0, 0, 0, 0, 0, L.stream_ptr())
+    act = F.gelu(hid.double())
+    _close(y, bf(act) @ bf(w2).t() + b2.double())
+    dy = torch.randn(T, cp, device="cuda", generator=g)
+    dhid = torch.zeros(T, hp, device="cuda")
+    L.call("rdst_gemm_tc", L.ptr(dy), cp, L.ptr(w2), hp, 1, None, None, 0, L.ptr(hid), hp, L.ptr(dhid), hp,
+           T, cp, hp, 0, 0, 1.0, 0, 0, 0, 0, 0, 0, L.stream_ptr())
+    h64 = hid.double().requires_grad_(True)
+    gp, = torch.autograd.grad(F.gelu(h64).sum(), h64)
+    _close(dhid, (bf(dy) @ bf(w2)) * gp)
+    dw = torch.zeros(cp, hp, device="cuda")
+    db = torch.zeros(cp, device="cuda")
+    L.call("rdst_gemm_tn_tc", L.ptr(dy), cp, L.ptr(hid), hp, L.ptr(dw), L.ptr(db), T, cp, hp, 0, 0, 0, 0, 0, 2, 0, L.stream_ptr())
+    _close(dw, bf(dy).t() @ bf(act))
+    x = torch.randn(T, cp, device="cuda", generator=g) + 0.3
+    x[:, c:] = 0
+    dq = torch.randn(T, 360, device="cuda", generator=g)
+    dwq = torch.zeros(360, cp, device="cuda")
+    L.call("rdst_gemm_tn_tc", L.ptr(dq), 360, L.ptr(x), cp, L.ptr(dwq), None, T, 360, cp, 0, 0, 0, 0, 0, 1, c, L.stream_ptr())
+    torch.cuda.synchronize()
+    _close(dwq[:, :c], bf(dq).t() @ bf(lnhat(x, c))[:, :c])
 
 
 def _oracle_grads(sd, x, target, scale):

@@ -59,10 +59,11 @@ def timed(name, *a):
     e0.record()
     orig(name, *a)
     e1.record()
-    if name == "rdst_gemm_tc":          # (x, ldx, w, ldw, w_mn, bias, resid, ldr, y, ldy, T, K, N, ln, scale, conv, ...)
-        name += f" T={a[10]} K={a[11]} N={a[12]}" + (" wT" if a[4] else "") + (" ln" if a[13] else "") + (" conv" if a[15] else "")
-    elif name in ("rdst_gemm_tn_tc", "rdst_gemm_tn_acc"):   # (dy, ldy, x, ldx, dw, db, T, N, K, conv, ...)
-        name += f" T={a[6]} N={a[7]} K={a[8]}" + (" conv" if a[9] else "")
+    if name == "rdst_gemm_tc":   # (x, ldx, w, ldw, w_mn, bias, resid, ldr, aux, lda, y, ldy, T, K, N, a_op, ln, scale, conv, ...)
+        name += (f" T={a[12]} K={a[13]} N={a[14]}" + (" wT" if a[4] else "") + ("", " ln", " gelu")[a[15]] +
+                 (" *gelu'" if a[8] is not None else "") + (" conv" if a[18] else ""))
+    elif name in ("rdst_gemm_tn_tc", "rdst_gemm_tn_acc"):   # (dy, ldy, x, ldx, dw, db, T, N, K, conv, B, H, W, Cin[, x_op, creal])
+        name += f" T={a[6]} N={a[7]} K={a[8]}" + (" conv" if a[9] else "") + (("", " ln", " gelu")[a[14]] if len(a) > 16 else "")
     evs.append((name, e0, e1))
 
 
