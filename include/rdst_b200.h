@@ -144,6 +144,19 @@ int rdst_window_attention_bwd(const float* qkv, int64_t ldq, const float* table,
                               float* dqkv, int64_t ldg, float* dtable, int B, int H, int W, int C, int heads, int shift,
                               void* stream);
 
+/* ---- weight packing of the training path, forward and backward (rdst_b200/csrc/pack.cu) ------------------------------ */
+/* Wp[pn(n)][pk(k)] = rs(n) * W[n][k] * gamma[k],  bp[pn(n)] = rs(n) * (b[n] + sum_k W[n][k]*beta[k])   (fp32)
+ *   W [N][K], Wp [.][ldp] and bp pre-zeroed by the caller; gamma/beta = the LayerNorm in front of the Linear or NULL;
+ *   rs(n) = q_scale for n < q_rows (attention scale on the q rows, swin_transformer_sr.py:120), else 1;
+ *   pn / pk = stored position of a real channel in the padded dense-block layout if scatter_rows / scatter_cols, else
+ *   identity.  Same arithmetic as rdst_b200/packing.py:pack_stl / pack_dstl_tail. */
+int rdst_pack_linear_fwd(const float* W, const float* b, const float* gamma, const float* beta, float* Wp, float* bp,
+                         int N, int K, int ldp, int scatter_rows, int scatter_cols, int q_rows, float q_scale, void* stream);
+/* Gradients of the parameters from the gradients of the packed tensors (dW, db, dgamma, dbeta are overwritten). */
+int rdst_pack_linear_bwd(const float* W, const float* gamma, const float* beta, const float* dWp, const float* dbp,
+                         float* dW, float* db, float* dgamma, float* dbeta, int N, int K, int ldp, int scatter_rows,
+                         int scatter_cols, int q_rows, float q_scale, void* stream);
+
 /* ---- tensor-core GEMMs of the training path (precision 'bf16'): fp32 storage, operands rounded to bf16 while they
  *      are staged into shared memory, tcgen05.mma with fp32 accumulation in TMEM (rdst_b200/csrc/tc_train.cu) ------ */
 

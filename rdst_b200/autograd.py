@@ -142,27 +142,84 @@ def _adder(flat):
     return add
 
 
-def pack_block(m, blk, device):
-    """Differentiable packed weights of one RDSTB: flat tensor list + spec (indices into the list)."""
-    flat = []
-    add = _adder(flat)
-    with packing.differentiable():
-        bs = {"dstl": []}
-        c = packing.EMBED
-        for dstl in blk.body:
-            stls = []
-            for b in dstl.body.blocks:
-                p = packing.pack_stl(b, c)
-                stls.append({k: add(p[k]) for k in ("wqkv", "bqkv", "wproj", "bproj", "w1", "b1", "w2", "b2", "table")}
-                            | {"c": c, "cp": p["cp"], "hp": p["hp"], "shift": b.shift_size})
-            t = packing.pack_dstl_tail(dstl, c, m.dense_scale)
-            bs["dstl"].append({"c": c, "stl": stls, "tw": add(t["w"]), "tb": add(t["b"]), "scale": t["scale"]})
-            c += packing.GROWTH
-        pos = packing.channel_positions(c, device)
-        w, b = packing.pack_conv(blk.conv.weight, blk.conv.bias, pos, packing.DENSE_LD, 64)
-        bs["lff_w"], bs["lff_b"] = add(w), add(b)
+def block_params(blk):
+    """Reference-named parameters of one RDSTB's Swin blocks and DenseSTLayer tails, in the fixed order the BlockFunction
+    takes them (the LFF conv goes through packing.pack_conv under autograd: a handful of torch ops)."""
+    ps = []
+    for dstl in blk.body:
+        for b in dstl.body.blocks:
+            ps += [b.norm1.weight, b.norm1.bias, b.attn.qkv.weight, b.attn.qkv.bias, b.attn.relative_position_bias_table,
+                   b.attn.proj.weight, b.attn.proj.bias, b.norm2.weight, b.norm2.bias,
+                   b.mlp.fc1.weight, b.mlp.fc1.bias, b.mlp.fc2.weight, b.mlp.fc2.bias]
+        ps += [dstl.tail[0].weight, dstl.tail[0].bias, dstl.tail[1].weight, dstl.tail[1].bias]
+    return ps
+
+
+def block_layout(m, blk):
+    """Static description of one RDSTB: where every packed tensor lives in the block's flat packed buffer and which
+    rdst_pack_linear call produces it.  Slot numbers index the list of packed tensors (`W` in the Functions)."""
+    lins, slots, off, nslot, pi = [], [], 0, 0, 0
+
+    def slot(shape):
+        nonlocal off, nslot
+        n = 1
+        for d in shape:
+            n *= d
+        slots.append((off, tuple(shape)))
+        off += (n + 3) // 4 * 4                       # keep every packed tensor 16-byte aligned
+        nslot += 1
+        return nslot - 1
+
+    def lin(w, b, g, be, N, K, rows_p, ldp, srows, scols, q_rows=0, q_scale=1.0):
+        sw, sb = slot((rows_p, ldp)), slot((rows_p,))
+        lins.append(dict(w=w, b=b, g=g, be=be, N=N, K=K, ldp=ldp, srows=srows, scols=scols, q_rows=q_rows,
+                         q_scale=float(q_scale), sw=sw, sb=sb))
+        return sw, sb
+
+    bs = {"dstl": [], "tables": []}
+    c = packing.EMBED
+    for dstl in blk.body:
+        cp, hid = packing.padded_width(c), None
+        stls = []
+        for b in dstl.body.blocks:
+            hid = b.mlp.fc1.weight.shape[0]
+            hp = packing.hidden_width(hid)
+            n1g, n1b, qw, qb, tab, pw, pb, n2g, n2b, f1w, f1b, f2w, f2b = range(pi, pi + 13)
+            pi += 13
+            st = {"c": c, "cp": cp, "hp": hp, "shift": b.shift_size}
+            st["wqkv"], st["bqkv"] = lin(qw, qb, n1g, n1b, 3 * c, c, 3 * c, cp, 0, 1, c, b.attn.scale)
+            st["wproj"], st["bproj"] = lin(pw, pb, None, None, c, c, cp, c, 1, 0)
+            st["w1"], st["b1"] = lin(f1w, f1b, n2g, n2b, hid, c, hp, cp, 0, 1)
+            st["w2"], st["b2"] = lin(f2w, f2b, None, None, c, hid, cp, hp, 1, 0)
+            st["table"] = -1 - len(bs["tables"])          # raw parameter, used as is: W[-1-i] is appended behind the slots
+            bs["tables"].append(tab)
+            stls.append(st)
+        tg, tb_, tw, tbias = range(pi, pi + 4)
+        pi += 4
+        sw, sb = lin(tw, tbias, tg, tb_, packing.GROWTH, c, 32, cp, 0, 1)
+        bs["dstl"].append({"c": c, "stl": stls, "tw": sw, "tb": sb, "scale": float(m.dense_scale)})
+        c += packing.GROWTH
+    bs["lins"], bs["slots"], bs["packed_floats"], bs["n_params"] = lins, slots, off, pi
+    bs["lff_w"], bs["lff_b"] = nslot, nslot + 1
     bs["res_scale"] = float(m.rdb_residual_scale)
-    return flat, bs
+    return bs
+
+
+def _views(buf, slots):
+    return [buf[o:o + _numel(s)].view(s) for o, s in slots]
+
+
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return n
+
+
+def pack_lff(blk, device):
+    with packing.differentiable():
+        pos = packing.channel_positions(packing.EMBED + 3 * packing.GROWTH, device)
+        return packing.pack_conv(blk.conv.weight, blk.conv.bias, pos, packing.DENSE_LD, 64)
 
 
 def pack_head(m, device):
@@ -278,13 +335,23 @@ class BlockFunction(torch.autograd.Function):
     """One RDSTB (rdst_variations.py:380-445): 3 DenseSTLayers on the [T][160] dense buffer, LFF conv + residual."""
 
     @staticmethod
-    def forward(ctx, bs, geom, X, *W):
+    def forward(ctx, bs, geom, X, lff_w, lff_b, *P):
         B, H, Wd = geom
         T = B * H * Wd
         dev = X.device
         e, z = _f32(dev)
         _MODE.tc = tc = bs["tc"]
         with torch.cuda.device(dev):
+            # packed weights of the block: one zeroed buffer, one rdst_pack_linear_fwd per Linear (csrc/pack.cu)
+            W = _views(z(bs["packed_floats"]), bs["slots"])
+            st_ = _lib.stream_ptr()
+            for l in bs["lins"]:
+                _call("rdst_pack_linear_fwd", _p(P[l["w"]]), _p(P[l["b"]]), _p(None if l["g"] is None else P[l["g"]]),
+                      _p(None if l["be"] is None else P[l["be"]]), _p(W[l["sw"]]), _p(W[l["sb"]]), l["N"], l["K"], l["ldp"],
+                      l["srows"], l["scols"], l["q_rows"], l["q_scale"], st_)
+            # slots | LFF filter, bias (packed by torch ops under autograd) | relative-position tables, reversed, used as
+            # stored: W[-1-i] is table i
+            W = W + [lff_w, lff_b] + [P[i] for i in reversed(bs["tables"])]
             D = z(T, 160)
             D[:, :64] = X
             sb = []
@@ -310,22 +377,22 @@ class BlockFunction(torch.autograd.Function):
                 sb.append(sl)
             Xn = e(T, 64)
             conv(D, W[bs["lff_w"]], W[bs["lff_b"]], Xn, B, H, Wd, 160, 64, scale=bs["res_scale"], resid=D)
-        ctx.bs, ctx.geom, ctx.W, ctx.saved = bs, geom, W, (D, sb)
+        ctx.bs, ctx.geom, ctx.W, ctx.P, ctx.saved = bs, geom, W, P, (D, sb)
         return Xn
 
     @staticmethod
     def backward(ctx, dXn):
-        bs, W = ctx.bs, ctx.W
+        bs, W, P = ctx.bs, ctx.W, ctx.P
         B, H, Wd = ctx.geom
         T = B * H * Wd
         D, sb = ctx.saved
         dev = dXn.device
         e, z = _f32(dev)
-        G = [None] * len(W)
+        # gradients of the packed tensors accumulate in one zeroed buffer laid out like the packed weights
+        G = _views(z(bs["packed_floats"]), bs["slots"]) + [torch.zeros_like(W[bs["lff_w"]]), torch.zeros_like(W[bs["lff_b"]])] + \
+            [torch.zeros_like(P[i]) for i in reversed(bs["tables"])]
 
         def gz(i):
-            if G[i] is None:
-                G[i] = torch.zeros_like(W[i])
             return G[i]
 
         _MODE.tc = bs["tc"]
@@ -357,8 +424,22 @@ class BlockFunction(torch.autograd.Function):
                     dy_cur = _stl_backward(ds["stl"][k], sl[k], W, gz, dy_cur, B, H, Wd,
                                            accumulate_into=dD if first else None)
             dXin = dD[:, :64].contiguous()
+            # packed-weight gradients -> gradients of the reference-named parameters
+            GP = [None] * len(P)
+            st_ = _lib.stream_ptr()
+            for l in bs["lins"]:
+                ln = l["g"] is not None
+                GP[l["w"]], GP[l["b"]] = torch.empty_like(P[l["w"]]), torch.empty_like(P[l["b"]])
+                if ln:
+                    GP[l["g"]], GP[l["be"]] = torch.empty_like(P[l["g"]]), torch.empty_like(P[l["be"]])
+                _call("rdst_pack_linear_bwd", _p(P[l["w"]]), _p(P[l["g"]] if ln else None), _p(P[l["be"]] if ln else None),
+                      _p(G[l["sw"]]), _p(G[l["sb"]]), _p(GP[l["w"]]), _p(GP[l["b"]]), _p(GP[l["g"]] if ln else None),
+                      _p(GP[l["be"]] if ln else None), l["N"], l["K"], l["ldp"], l["srows"], l["scols"], l["q_rows"],
+                      l["q_scale"], st_)
+            for i, pi in enumerate(bs["tables"]):
+                GP[pi] = G[-1 - i]
         ctx.saved = None
-        return (None, None, dXin) + tuple(G)
+        return (None, None, dXin, G[bs["lff_w"]], G[bs["lff_b"]]) + tuple(GP)
 
 
 class TailFunction(torch.autograd.Function):
@@ -497,8 +578,8 @@ def forward_with_grad(executor, x):
     flat, spec = pack_head(m, dev)
     F0, X = HeadFunction.apply(spec, sc, x.detach().to(torch.float32).contiguous(), *flat)
     for blk in m.body:
-        flat, bs = pack_block(m, blk, dev)
-        bs["tc"] = tc
-        X = BlockFunction.apply(bs, geom, X, *flat)
+        bs = dict(block_layout(m, blk), tc=tc)
+        lff_w, lff_b = pack_lff(blk, dev)
+        X = BlockFunction.apply(bs, geom, X, lff_w, lff_b, *block_params(blk))
     flat, spec = pack_tail(m, dev)
     return TailFunction.apply(spec, sc, geom, X, F0, *flat)

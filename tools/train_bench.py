@@ -53,8 +53,9 @@ def main():
     y = torch.rand(a.batch, 1, 96, 96, device="cuda", generator=g)
 
     def make_opt(model, capturable):
+        # the reference's optimiser (utils/optim.py: Adam, ini :130-135); fused=True = one multi-tensor kernel
         return torch.optim.Adam([p for p in model.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.99),
-                                eps=1e-8, capturable=capturable)
+                                eps=1e-8, capturable=capturable, fused=True)
 
     def run(model, mode, steps, timed):
         opt = make_opt(model, mode == "graph")

@@ -16,7 +16,7 @@ from rdst_b200 import _lib  # noqa: E402
 prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
 torch.manual_seed(0)
 m = helpers.make_module(8, 4, prec).cuda().train()
-opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.99), eps=1e-8)
+opt = torch.optim.Adam([p for p in m.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.99), eps=1e-8, fused=True)
 x = torch.rand(32, 1, 24, 24, device="cuda")
 y = torch.rand(32, 1, 96, 96, device="cuda")
 
@@ -88,3 +88,18 @@ step()
 t1 = time.perf_counter()
 torch.cuda.synchronize()
 print(f"host enqueue time of one step: {1e3 * (t1 - t0):.2f} ms")
+
+# every CUDA kernel of one step (torch ops included), from the profiler: who owns the rest of the device time?
+from torch.profiler import profile, ProfilerActivity  # noqa: E402
+with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
+    step()
+    torch.cuda.synchronize()
+rows = [(e.key, e.count, e.device_time_total) for e in prof.key_averages() if e.device_time_total > 0 and e.device_type.name == "CUDA"]
+rows.sort(key=lambda r: -r[2])
+tot_n, tot_t = sum(r[1] for r in rows), sum(r[2] for r in rows)
+ours = [r for r in rows if "rdst" in r[0]]
+print(f"profiler: {tot_n} kernels, {tot_t / 1e3:.2f} ms device time; librdst kernels: {sum(r[1] for r in ours)} launches, "
+      f"{sum(r[2] for r in ours) / 1e3:.2f} ms; torch kernels: {tot_n - sum(r[1] for r in ours)} launches, "
+      f"{(tot_t - sum(r[2] for r in ours)) / 1e3:.2f} ms")
+for k, n, t in rows[:14]:
+    print(f"  {k[:90]:90s} {n:6d} {t / 1e3:8.3f} ms")
