@@ -152,7 +152,8 @@ int rdst_window_attention_bwd(const float* qkv, int64_t ldq, const float* table,
  *   identity.  Same arithmetic as rdst_b200/packing.py:pack_stl / pack_dstl_tail. */
 int rdst_pack_linear_fwd(const float* W, const float* b, const float* gamma, const float* beta, float* Wp, float* bp,
                          int N, int K, int ldp, int scatter_rows, int scatter_cols, int q_rows, float q_scale, void* stream);
-/* Gradients of the parameters from the gradients of the packed tensors (dW, db, dgamma, dbeta are overwritten). */
+/* Gradients of the parameters from the gradients of the packed tensors: dW, db are overwritten, dgamma / dbeta are
+ * accumulated (pass them zeroed). */
 int rdst_pack_linear_bwd(const float* W, const float* gamma, const float* beta, const float* dWp, const float* dbp,
                          float* dW, float* db, float* dgamma, float* dbeta, int N, int K, int ldp, int scatter_rows,
                          int scatter_cols, int q_rows, float q_scale, void* stream);

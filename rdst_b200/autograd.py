@@ -431,7 +431,7 @@ class BlockFunction(torch.autograd.Function):
                 ln = l["g"] is not None
                 GP[l["w"]], GP[l["b"]] = torch.empty_like(P[l["w"]]), torch.empty_like(P[l["b"]])
                 if ln:
-                    GP[l["g"]], GP[l["be"]] = torch.empty_like(P[l["g"]]), torch.empty_like(P[l["be"]])
+                    GP[l["g"]], GP[l["be"]] = torch.zeros_like(P[l["g"]]), torch.zeros_like(P[l["be"]])
                 _call("rdst_pack_linear_bwd", _p(P[l["w"]]), _p(P[l["g"]] if ln else None), _p(P[l["be"]] if ln else None),
                       _p(G[l["sw"]]), _p(G[l["sb"]]), _p(GP[l["w"]]), _p(GP[l["b"]]), _p(GP[l["g"]] if ln else None),
                       _p(GP[l["be"]] if ln else None), l["N"], l["K"], l["ldp"], l["srows"], l["scols"], l["q_rows"],

@@ -5,7 +5,7 @@
 // swin_transformer_sr.py:120), and rows / columns moved to their stored channel positions in the padded dense-block
 // layout (include/rdst_b200.h: 60 trunk channels at [0,60), growth group g at [64+32g, +30)).  The backward kernel turns the
 // gradients of the packed tensors into the gradients of the reference-named parameters:
-//   dW = rs * (gamma * dWp + dbp (x) beta),  db = rs * dbp,  dgamma[k] = sum_n rs W dWp,  dbeta[k] = sum_n rs W dbp.
+//   dW = rs * (gamma * dWp + dbp (x) beta),  db = rs * dbp,  dgamma[k] += sum_n rs W dWp,  dbeta[k] += sum_n rs W dbp.
 // Same arithmetic as rdst_b200/packing.py (pack_stl / pack_dstl_tail), which stays the inference-time packer.
 #include "common.cuh"
 
@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256) pack_linear_bwd_kernel(const float* __res
   if (k < K) {
     const int pk = chan_pos(k, scols);
     const float g = gamma ? gamma[k] : 1.f, be = beta ? beta[k] : 0.f;
-    for (int n = ry; n < N; n += 8) {
+    for (int n = blockIdx.y * 8 + ry; n < N; n += 8 * gridDim.y) {
       const float rs = n < q_rows ? q_scale : 1.f;
       const int pn = chan_pos(n, srows);
       const float gw = dWp[(size_t)pn * ldp + pk], gb = dbp[pn];
@@ -71,8 +71,8 @@ __global__ void __launch_bounds__(256) pack_linear_bwd_kernel(const float* __res
     float tg = 0.f, tb = 0.f;
 #pragma unroll
     for (int j = 0; j < 8; ++j) { tg += sg[j][kx]; tb += sb[j][kx]; }
-    dgamma[k] = tg;
-    dbeta[k] = tb;
+    atomicAdd(dgamma + k, tg);          // row groups are split over blockIdx.y; dgamma / dbeta arrive zeroed
+    atomicAdd(dbeta + k, tb);
   }
 }
 
@@ -99,7 +99,8 @@ extern "C" int rdst_pack_linear_bwd(const float* W, const float* gamma, const fl
   RDST_REQUIRE(N > 0 && K > 0 && ldp >= K && (gamma != nullptr) == (beta != nullptr) && (gamma != nullptr) == (dgamma != nullptr) &&
                    (dgamma != nullptr) == (dbeta != nullptr),
                "rdst_pack_linear_bwd: bad argument");
-  pack_linear_bwd_kernel<<<(K + 31) / 32, 256, 0, (cudaStream_t)stream>>>(W, gamma, beta, dWp, dbp, dW, db, dgamma, dbeta, N, K,
+  const dim3 grid((unsigned)((K + 31) / 32), (unsigned)((N + 63) / 64));
+  pack_linear_bwd_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(W, gamma, beta, dWp, dbp, dW, db, dgamma, dbeta, N, K,
                                                                          ldp, scatter_rows, scatter_cols, q_rows, q_scale);
   RDST_CHECK_LAUNCH("rdst_pack_linear_bwd");
   return RDST_OK;

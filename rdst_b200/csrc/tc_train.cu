@@ -26,7 +26,8 @@ using namespace umma;
 namespace {
 
 constexpr int TM = 128;          // token rows per tile (= TMEM lanes)
-constexpr int NTHREADS = 256;
+constexpr int NT_GEMM = 512;         // one tile per SM at the training batch: threads buy memory-level parallelism
+constexpr int NT_TN = 256;           // weight-gradient CTAs are smaller and run two per SM
 
 struct GemmArgs {
   const float* x; int64_t ldx;
@@ -114,6 +115,7 @@ __device__ __forceinline__ void red_add_v4(float* p, float a, float b, float c, 
 
 // LayerNorm statistics of 128 consecutive rows (one warp per row, four rows in flight): mean / rstd over the K stored
 // values divided by creal real channels (pads are zero), as rdst_linear_fwd.
+template <int NTHREADS>
 __device__ __forceinline__ void row_stats(const float* x, int64_t ldx, int64_t t0, int64_t T, int K, int creal, float* s_mean,
                                           float* s_rstd, int warp, int lane) {
   const float inv = 1.f / (float)creal;
@@ -156,7 +158,7 @@ constexpr int U = 4;                      // independent chunk loads in flight p
 // ------------------------------------------------------------------------------------------------------------------
 // Y = scale * (op(X) . Wop + bias) [* gelu'(aux)] + R
 // ------------------------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) {
+__global__ void __launch_bounds__(NT_GEMM, 1) gemm_tc_kernel(const GemmArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) 
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
-  for (int n = tid; n < Np; n += NTHREADS) s_bias[n] = (a.bias && n < a.N) ? __ldg(a.bias + n) : 0.f;
+  for (int n = tid; n < Np; n += NT_GEMM) s_bias[n] = (a.bias && n < a.N) ? __ldg(a.bias + n) : 0.f;
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
@@ -181,12 +183,12 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) 
   const int chg = (nch + 3) >> 2;                   // chunk groups of 4
   const int64_t ntiles = (a.T + TM - 1) / TM;
   const int HW = a.H * a.W;
-  constexpr int NW = NTHREADS / 32;
+  constexpr int NW = NT_GEMM / 32;
 
   for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
     const int64_t t0 = tile * TM;
     if (a.a_op == 1) {
-      row_stats(a.x, a.ldx, t0, a.T, a.K, a.ln_creal, s_mean, s_rstd, warp, lane);
+      row_stats<NT_GEMM>(a.x, a.ldx, t0, a.T, a.K, a.ln_creal, s_mean, s_rstd, warp, lane);
       __syncthreads();
     }
     for (int kc = 0; kc < a.nkc; ++kc) {
@@ -304,9 +306,9 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) 
     mbar_wait(&bar, phase);
     phase ^= 1;
     fence_after_sync();
-    // ---- epilogue: thread = token row (TMEM lane), the two thread halves alternate over 16-column groups ----
+    // ---- epilogue: thread = token row (TMEM lane), the four thread quarters alternate over 16-column groups ----
     {
-      const int r = tid & 127, half = tid >> 7;
+      const int r = tid & 127, quarter = tid >> 7;
       const int64_t t = t0 + r;
       const bool live = t < a.T;
       int64_t yrow = t;
@@ -317,8 +319,19 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) 
         py = rem / a.W;
         px = rem % a.W;
       }
-      for (int g = half; g * 16 < a.N; g += 2) {
+      for (int g = quarter; g * 16 < a.N; g += NT_GEMM / 128) {
         const int n0 = g * 16;
+        const bool full = n0 + 16 <= a.N;
+        const float* rp = (a.resid && live) ? a.resid + t * a.ldr + n0 : nullptr;
+        const float* ap = (a.aux && live) ? a.aux + t * a.lda + n0 : nullptr;
+        float4 rv[4], hv[4];                              // residual / GELU operand: in flight while TMEM is read
+        if (full) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            rv[j] = rp ? __ldg(reinterpret_cast<const float4*>(rp) + j) : zero4();
+            if (ap) hv[j] = __ldg(reinterpret_cast<const float4*>(ap) + j);
+          }
+        }
         uint32_t v[16];
         __syncwarp();
         tmem_ld_x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + n0, v);
@@ -331,28 +344,21 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tc_kernel(const GemmArgs a) 
           ncol = n0 & 63;
         }
         float* yp = a.y + yrow * a.ldy + ncol;
-        const float* rp = a.resid ? a.resid + t * a.ldr + n0 : nullptr;
-        const float* ap = a.aux ? a.aux + t * a.lda + n0 : nullptr;
         float o[16];
 #pragma unroll
         for (int j = 0; j < 16; ++j) o[j] = (__uint_as_float(v[j]) + s_bias[n0 + j]) * a.out_scale;
-        if (n0 + 16 <= a.N) {
+        if (full) {
           if (ap) {
 #pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 h = __ldg(reinterpret_cast<const float4*>(ap + j));
-              o[j] *= gelu_grad(h.x); o[j + 1] *= gelu_grad(h.y); o[j + 2] *= gelu_grad(h.z); o[j + 3] *= gelu_grad(h.w);
-            }
-          }
-          if (rp) {
-#pragma unroll
-            for (int j = 0; j < 16; j += 4) {
-              const float4 rv = *reinterpret_cast<const float4*>(rp + j);
-              o[j] += rv.x; o[j + 1] += rv.y; o[j + 2] += rv.z; o[j + 3] += rv.w;
+            for (int j = 0; j < 4; ++j) {
+              o[4 * j] *= gelu_grad(hv[j].x); o[4 * j + 1] *= gelu_grad(hv[j].y);
+              o[4 * j + 2] *= gelu_grad(hv[j].z); o[4 * j + 3] *= gelu_grad(hv[j].w);
             }
           }
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(yp + j) = make_float4(o[j], o[j + 1], o[j + 2], o[j + 3]);
+          for (int j = 0; j < 4; ++j)
+            *reinterpret_cast<float4*>(yp + 4 * j) =
+                make_float4(o[4 * j] + rv[j].x, o[4 * j + 1] + rv[j].y, o[4 * j + 2] + rv[j].z, o[4 * j + 3] + rv[j].w);
         } else {
 #pragma unroll
           for (int j = 0; j < 16; ++j)
@@ -379,7 +385,7 @@ struct TnArgs {
   int x_op, x_creal;            // prologue on X: 0 none, 1 LayerNorm-hat (x_creal real channels), 2 exact-erf GELU
 };
 
-__global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const TnArgs a) {
+__global__ void __launch_bounds__(NT_TN, 1) gemm_tn_tc_kernel(const TnArgs a) {
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar;
   __shared__ uint32_t tmem_base_s;
@@ -407,7 +413,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const TnArgs a)
   const int HW = a.H * a.W;
   const int nbc = NB >> 3;                          // 8-column chunks of the B image
   const int nbg = (nbc + 3) >> 2;
-  constexpr int NW = NTHREADS / 32;
+  constexpr int NW = NT_TN / 32;
   bool first = true;
   for (int64_t t0 = ts; t0 < te; t0 += TM) {
     if (!first) {
@@ -416,7 +422,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const TnArgs a)
       fence_after_sync();
     }
     if (a.x_op == 1) {
-      row_stats(a.x, a.ldx, t0, te, a.K, a.x_creal, s_mean, s_rstd, warp, lane);
+      row_stats<NT_TN>(a.x, a.ldx, t0, te, a.K, a.x_creal, s_mean, s_rstd, warp, lane);
       __syncthreads();
     }
     // ---- A image: dY[t][m0 .. m0+128) ----
@@ -507,10 +513,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) gemm_tn_tc_kernel(const TnArgs a)
   fence_after_sync();
   // ---- epilogue: thread = output row n, fp32 reductions into dW / db ----
   {
-    const int r = tid & 127, half = tid >> 7;
+    const int r = tid & 127, quarter = tid >> 7;
     const int n = m0 + r;
     const bool vec = (a.K & 3) == 0;
-    for (int g = half; g * 16 < NB; g += 2) {
+    for (int g = quarter; g * 16 < NB; g += NT_TN / 128) {
       const int c0 = g * 16;
       uint32_t v[16];
       __syncwarp();
@@ -593,7 +599,7 @@ extern "C" int rdst_gemm_tc(const float* x, int64_t ldx, const float* w, int64_t
   if (e != cudaSuccess) { set_error("rdst_gemm_tc: smem attr: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   const int64_t tiles = (T + TM - 1) / TM;
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
-  gemm_tc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+  gemm_tc_kernel<<<grid, NT_GEMM, smem, (cudaStream_t)stream>>>(a);
   RDST_CHECK_LAUNCH("rdst_gemm_tc");
   return RDST_OK;
 }
@@ -631,7 +637,7 @@ extern "C" int rdst_gemm_tn_tc(const float* dy, int64_t ldy, const float* x, int
   cudaError_t e = cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
   if (e != cudaSuccess) { set_error("rdst_gemm_tn_tc: smem attr: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   dim3 grid((unsigned)mt, (unsigned)kc, (unsigned)splits);
-  gemm_tn_tc_kernel<<<grid, NTHREADS, smem, (cudaStream_t)stream>>>(a);
+  gemm_tn_tc_kernel<<<grid, NT_TN, smem, (cudaStream_t)stream>>>(a);
   RDST_CHECK_LAUNCH("rdst_gemm_tn_tc");
   return RDST_OK;
 }
