@@ -27,7 +27,7 @@ namespace {
 
 constexpr int TM = 128;          // token rows per tile (= TMEM lanes)
 constexpr int NT_GEMM = 512;         // one tile per SM at the training batch: threads buy memory-level parallelism
-constexpr int NT_TN = 256;           // weight-gradient CTAs are smaller and run two per SM
+constexpr int NT_TN = 512;
 
 struct GemmArgs {
   const float* x; int64_t ldx;
@@ -380,6 +380,7 @@ struct TnArgs {
   const float* dy; int64_t ldy; const float* x; int64_t ldx; float* dw; float* db;
   int64_t T; int N, K;
   int KCW;                      // columns of X (k) per CTA, multiple of 16, <= 240
+  int MT;                       // 128-row tiles of dW (n) per CTA: X is staged once for all of them (MT * (KCW+16) <= 512)
   int64_t t_per_split;          // multiple of 128
   int conv, B, H, W, Cin;
   int x_op, x_creal;            // prologue on X: 0 none, 1 LayerNorm-hat (x_creal real channels), 2 exact-erf GELU
@@ -391,15 +392,16 @@ __global__ void __launch_bounds__(NT_TN, 1) gemm_tn_tc_kernel(const TnArgs a) {
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_mean[TM], s_rstd[TM];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  const int m0 = blockIdx.x * TM;                   // first output row (n) of this CTA
+  const int MT = a.MT;
+  const int m0 = blockIdx.x * MT * TM;              // first output row (n) of this CTA
   const int k0 = blockIdx.y * a.KCW;                // first output column (k)
   const bool with_bias = a.db != nullptr && blockIdx.y == 0;
   const int NB = a.KCW + (with_bias ? 16 : 0);      // MMA N: k columns (+ the ones column group)
   // MN-major images, token = MMA K dimension: element (t, c) at (t/8)*128 + (c/8)*2048 + (t%8)*16 + (c%8)*2
-  uint8_t* sA = smem;                               // dY: 128 tokens x 128 n
-  uint8_t* sB = smem + (size_t)TM * 128 * 2;        // X : 128 tokens x NB k
+  uint8_t* sA = smem;                               // dY: MT images of 128 tokens x 128 n
+  uint8_t* sB = smem + (size_t)MT * TM * 128 * 2;   // X : 128 tokens x NB k
 
-  if (warp == 0) tmem_alloc<256>(&tmem_base_s);
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
   fence_before_sync();
   __syncthreads();
@@ -421,22 +423,18 @@ __global__ void __launch_bounds__(NT_TN, 1) gemm_tn_tc_kernel(const TnArgs a) {
       phase ^= 1;
       fence_after_sync();
     }
-    if (a.x_op == 1) {
-      row_stats<NT_TN>(a.x, a.ldx, t0, te, a.K, a.x_creal, s_mean, s_rstd, warp, lane);
-      __syncthreads();
-    }
-    // ---- A image: dY[t][m0 .. m0+128) ----
-    for (int b0 = warp; b0 < 16 * 4; b0 += NW * U) {
+    // ---- A images: dY[t][m0 .. m0 + MT*128) ----
+    for (int b0 = warp; b0 < MT * 64; b0 += NW * U) {
       float4 v0[U], v1[U];
 #pragma unroll
       for (int u = 0; u < U; ++u) {
         const int blk = b0 + u * NW;
-        const int tt = (blk & 15) * 8 + r8, ch = (blk >> 4) * 4 + c4;       // 16 chunks of 8 n
+        const int tt = (blk & 15) * 8 + r8, ch = (blk >> 4) * 4 + c4;       // MT*16 chunks of 8 n
         const int64_t t = t0 + tt;
         const int n = m0 + ch * 8;
         v0[u] = zero4();
         v1[u] = zero4();
-        if (t < te && n < a.N) {
+        if (blk < MT * 64 && t < te && n < a.N) {
           const float* p = a.dy + t * a.ldy + n;
           v0[u] = __ldg(reinterpret_cast<const float4*>(p));
           v1[u] = __ldg(reinterpret_cast<const float4*>(p) + 1);
@@ -447,8 +445,13 @@ __global__ void __launch_bounds__(NT_TN, 1) gemm_tn_tc_kernel(const TnArgs a) {
       for (int u = 0; u < U; ++u) {
         const int blk = b0 + u * NW;
         const int tt = (blk & 15) * 8 + r8, ch = (blk >> 4) * 4 + c4;
-        *reinterpret_cast<uint4*>(sA + (size_t)(tt >> 3) * 128 + (size_t)ch * 2048 + (tt & 7) * 16) = pack8(v0[u], v1[u]);
+        if (blk < MT * 64)
+          *reinterpret_cast<uint4*>(sA + (size_t)(tt >> 3) * 128 + (size_t)ch * 2048 + (tt & 7) * 16) = pack8(v0[u], v1[u]);
       }
+    }
+    if (a.x_op == 1) {
+      row_stats<NT_TN>(a.x, a.ldx, t0, te, a.K, a.x_creal, s_mean, s_rstd, warp, lane);
+      __syncthreads();
     }
     // ---- B image: op(X)[t][k0 .. k0+KCW) (3x3 gather in conv mode) + ones column ----
     for (int b0 = warp; b0 < 16 * nbg; b0 += NW * U) {
@@ -492,11 +495,12 @@ __global__ void __launch_bounds__(NT_TN, 1) gemm_tn_tc_kernel(const TnArgs a) {
     if (warp == 0) {
       if (elect_one()) {
         const uint32_t idesc = make_idesc_bf16(TM, NB, true, true);
-        for (int ks = 0; ks < TM / 16; ++ks) {
-          const uint64_t da = make_smem_desc(smem_u32(sA) + ks * 2 * 128, 128, 2048);
-          const uint64_t db = make_smem_desc(smem_u32(sB) + ks * 2 * 128, 128, 2048);
-          mma_bf16_ss(tmem, da, db, idesc, (!first || ks > 0) ? 1u : 0u);
-        }
+        for (int m = 0; m < MT; ++m)
+          for (int ks = 0; ks < TM / 16; ++ks) {
+            const uint64_t da = make_smem_desc(smem_u32(sA) + m * (TM * 128 * 2) + ks * 2 * 128, 128, 2048);
+            const uint64_t db = make_smem_desc(smem_u32(sB) + ks * 2 * 128, 128, 2048);
+            mma_bf16_ss(tmem + m * NB, da, db, idesc, (!first || ks > 0) ? 1u : 0u);
+          }
         commit(&bar);
       }
       __syncwarp();
@@ -506,21 +510,22 @@ __global__ void __launch_bounds__(NT_TN, 1) gemm_tn_tc_kernel(const TnArgs a) {
   if (first) {                                       // empty token range: nothing to add
     fence_before_sync();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tmem);
+    if (warp == 0) tmem_dealloc<512>(tmem);
     return;
   }
   mbar_wait(&bar, phase);
   fence_after_sync();
-  // ---- epilogue: thread = output row n, fp32 reductions into dW / db ----
+  // ---- epilogue: thread = output row n of tile m, fp32 reductions into dW / db ----
   {
     const int r = tid & 127, quarter = tid >> 7;
-    const int n = m0 + r;
     const bool vec = (a.K & 3) == 0;
-    for (int g = quarter; g * 16 < NB; g += NT_TN / 128) {
-      const int c0 = g * 16;
+    const int ng = NB >> 4;
+    for (int gi = quarter; gi < MT * ng; gi += NT_TN / 128) {
+      const int m = gi / ng, c0 = (gi - m * ng) * 16;
+      const int n = m0 + m * TM + r;
       uint32_t v[16];
       __syncwarp();
-      tmem_ld_x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + c0, v);
+      tmem_ld_x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + m * NB + c0, v);
       wait_ld();
       if (n >= a.N) continue;
       if (c0 >= a.KCW) {                             // ones column group
@@ -544,7 +549,7 @@ __global__ void __launch_bounds__(NT_TN, 1) gemm_tn_tc_kernel(const TnArgs a) {
   }
   fence_before_sync();
   __syncthreads();
-  if (warp == 0) tmem_dealloc<256>(tmem);
+  if (warp == 0) tmem_dealloc<512>(tmem);
 }
 
 int sm_count() {
@@ -626,15 +631,18 @@ extern "C" int rdst_gemm_tn_tc(const float* dy, int64_t ldy, const float* x, int
   const int kchunks = (Kp + 239) / 240;
   a.KCW = ((Kp + kchunks - 1) / kchunks + 15) / 16 * 16;
   const int kc = (Kp + a.KCW - 1) / a.KCW;
-  const int mt = (N + TM - 1) / TM;
-  int64_t splits = (2 * sm_count() + mt * kc - 1) / (mt * kc);          // about two CTAs' worth of work per SM in flight
+  const int mt_all = (N + TM - 1) / TM;
+  a.MT = mt_all;                                                        // all row tiles of dW in one CTA when TMEM holds them
+  while (a.MT > 1 && (a.MT * (a.KCW + 16) > 512 || a.MT > 3)) --a.MT;
+  const int mt = (mt_all + a.MT - 1) / a.MT;
+  int64_t splits = (sm_count() + mt * kc - 1) / (mt * kc);              // one CTA per SM
   const int64_t max_splits = (T + TM - 1) / TM;                         // at least one 128-token stage per CTA
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
   a.t_per_split = ((T + splits - 1) / splits + TM - 1) / TM * TM;
   splits = (T + a.t_per_split - 1) / a.t_per_split;
-  const size_t smem = (size_t)TM * 128 * 2 + (size_t)TM * (a.KCW + 16) * 2;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024);
+  const size_t smem = (size_t)a.MT * TM * 128 * 2 + (size_t)TM * (a.KCW + 16) * 2;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tn_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 170 * 1024);
   if (e != cudaSuccess) { set_error("rdst_gemm_tn_tc: smem attr: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   dim3 grid((unsigned)mt, (unsigned)kc, (unsigned)splits);
   gemm_tn_tc_kernel<<<grid, NT_TN, smem, (cudaStream_t)stream>>>(a);
