@@ -236,14 +236,17 @@ __global__ void __launch_bounds__(64) window_attention_bwd_kernel(const float* _
                                                                   int64_t ldo, float* __restrict__ dqkv, int64_t ldg,
                                                                   float* __restrict__ dtable, int H, int W, int C, int heads,
                                                                   int shift) {
-  extern __shared__ float smf[];
-  float (*sq)[HD + 1] = reinterpret_cast<float (*)[HD + 1]>(smf);
-  float (*sk)[HD + 1] = sq + 64;
-  float (*sv)[HD + 1] = sk + 64;
-  float (*sgo)[HD + 1] = sv + 64;
-  float (*sP)[65] = reinterpret_cast<float (*)[65]>(smf + 4 * 64 * (HD + 1));
+  // q / k / v / dO rows padded to a multiple of 4 floats (pads zero): the row a loop iteration needs is the same for all
+  // threads (broadcast), so one 16-byte shared-memory load feeds four FMAs
+  constexpr int HP = (HD + 3) / 4 * 4;
+  extern __shared__ __align__(16) float smf[];
+  float (*sq)[HP] = reinterpret_cast<float (*)[HP]>(smf);
+  float (*sk)[HP] = sq + 64;
+  float (*sv)[HP] = sk + 64;
+  float (*sgo)[HP] = sv + 64;
+  float (*sP)[65] = reinterpret_cast<float (*)[65]>(smf + 4 * 64 * HP);
   float (*sdS)[65] = sP + 64;
-  float* stab = smf + 4 * 64 * (HD + 1) + 2 * 64 * 65;
+  float* stab = smf + 4 * 64 * HP + 2 * 64 * 65;
   float* sdtab = stab + 225;
   int* sreg = reinterpret_cast<int*>(sdtab + 225);
   const int wi = blockIdx.x, h = blockIdx.y, i = threadIdx.x;
@@ -265,23 +268,26 @@ __global__ void __launch_bounds__(64) window_attention_bwd_kernel(const float* _
   sreg[i] = reg;
   const float* row = qkv + t * ldq + h * HD;
 #pragma unroll
-  for (int d = 0; d < HD; ++d) {
-    sq[i][d] = row[d];
-    sk[i][d] = row[C + d];
-    sv[i][d] = row[2 * C + d];
-    sgo[i][d] = dout[t * ldo + h * HD + d];
+  for (int d = 0; d < HP; ++d) {
+    sq[i][d] = d < HD ? row[d] : 0.f;
+    sk[i][d] = d < HD ? row[C + d] : 0.f;
+    sv[i][d] = d < HD ? row[2 * C + d] : 0.f;
+    sgo[i][d] = d < HD ? dout[t * ldo + h * HD + d] : 0.f;
   }
   __syncthreads();
   // phase 1 (thread = query i): probabilities P_i., dP_i. = dO_i . v_j, dS_i. = P (dP - sum_k P_k dP_k), dq_i
   {
-    float q[HD], go[HD];
+    float q[HP], go[HP];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) { q[d] = sq[i][d]; go[d] = sgo[i][d]; }
+    for (int d = 0; d < HP; ++d) { q[d] = sq[i][d]; go[d] = sgo[i][d]; }
     float mx = -INFINITY;
     for (int j = 0; j < 64; ++j) {
       float acc = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc = fmaf(q[d], sk[j][d], acc);
+      for (int d = 0; d < HP; d += 4) {
+        const float4 kv = *reinterpret_cast<const float4*>(&sk[j][d]);
+        acc = fmaf(q[d], kv.x, acc); acc = fmaf(q[d + 1], kv.y, acc); acc = fmaf(q[d + 2], kv.z, acc); acc = fmaf(q[d + 3], kv.w, acc);
+      }
       acc += stab[(iy - (j >> 3) + 7) * 15 + (ix - (j & 7) + 7)];
       if (shift > 0 && sreg[j] != reg) acc += -100.0f;
       sP[i][j] = acc;
@@ -295,19 +301,25 @@ __global__ void __launch_bounds__(64) window_attention_bwd_kernel(const float* _
       const float pj = sP[i][j] * inv;
       float acc = 0.f;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) acc = fmaf(go[d], sv[j][d], acc);
+      for (int d = 0; d < HP; d += 4) {
+        const float4 vv = *reinterpret_cast<const float4*>(&sv[j][d]);
+        acc = fmaf(go[d], vv.x, acc); acc = fmaf(go[d + 1], vv.y, acc); acc = fmaf(go[d + 2], vv.z, acc); acc = fmaf(go[d + 3], vv.w, acc);
+      }
       sP[i][j] = pj;
       sdS[i][j] = acc;
       dotsum = fmaf(pj, acc, dotsum);
     }
-    float dq[HD];
+    float dq[HP];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) dq[d] = 0.f;
+    for (int d = 0; d < HP; ++d) dq[d] = 0.f;
     for (int j = 0; j < 64; ++j) {
       const float ds = sP[i][j] * (sdS[i][j] - dotsum);
       sdS[i][j] = ds;
 #pragma unroll
-      for (int d = 0; d < HD; ++d) dq[d] = fmaf(ds, sk[j][d], dq[d]);
+      for (int d = 0; d < HP; d += 4) {
+        const float4 kv = *reinterpret_cast<const float4*>(&sk[j][d]);
+        dq[d] = fmaf(ds, kv.x, dq[d]); dq[d + 1] = fmaf(ds, kv.y, dq[d + 1]); dq[d + 2] = fmaf(ds, kv.z, dq[d + 2]); dq[d + 3] = fmaf(ds, kv.w, dq[d + 3]);
+      }
       atomicAdd(&sdtab[(iy - (j >> 3) + 7) * 15 + (ix - (j & 7) + 7)], ds);
     }
     float* grow = dqkv + t * ldg + h * HD;
@@ -317,13 +329,18 @@ __global__ void __launch_bounds__(64) window_attention_bwd_kernel(const float* _
   __syncthreads();
   // phase 2 (thread = key j = i): dk_j = sum_i dS_ij q_i ; dv_j = sum_i P_ij dO_i
   {
-    float dk[HD], dv[HD];
+    float dk[HP], dv[HP];
 #pragma unroll
-    for (int d = 0; d < HD; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
+    for (int d = 0; d < HP; ++d) { dk[d] = 0.f; dv[d] = 0.f; }
     for (int r = 0; r < 64; ++r) {
       const float ds = sdS[r][i], pr = sP[r][i];
 #pragma unroll
-      for (int d = 0; d < HD; ++d) { dk[d] = fmaf(ds, sq[r][d], dk[d]); dv[d] = fmaf(pr, sgo[r][d], dv[d]); }
+      for (int d = 0; d < HP; d += 4) {
+        const float4 qv = *reinterpret_cast<const float4*>(&sq[r][d]);
+        const float4 gv = *reinterpret_cast<const float4*>(&sgo[r][d]);
+        dk[d] = fmaf(ds, qv.x, dk[d]); dk[d + 1] = fmaf(ds, qv.y, dk[d + 1]); dk[d + 2] = fmaf(ds, qv.z, dk[d + 2]); dk[d + 3] = fmaf(ds, qv.w, dk[d + 3]);
+        dv[d] = fmaf(pr, gv.x, dv[d]); dv[d + 1] = fmaf(pr, gv.y, dv[d + 1]); dv[d + 2] = fmaf(pr, gv.z, dv[d + 2]); dv[d + 3] = fmaf(pr, gv.w, dv[d + 3]);
+      }
     }
     float* grow = dqkv + t * ldg + h * HD;
 #pragma unroll
@@ -336,7 +353,7 @@ __global__ void __launch_bounds__(64) window_attention_bwd_kernel(const float* _
 template <int HD>
 static void launch_wattn_bwd(dim3 grid, cudaStream_t st, const float* qkv, int64_t ldq, const float* table, const float* dout,
                              int64_t ldo, float* dqkv, int64_t ldg, float* dtable, int H, int W, int C, int heads, int shift) {
-  const size_t smem = (size_t)(4 * 64 * (HD + 1) + 2 * 64 * 65 + 2 * 225 + 64) * sizeof(float);
+  const size_t smem = (size_t)(4 * 64 * ((HD + 3) / 4 * 4) + 2 * 64 * 65 + 2 * 225 + 64) * sizeof(float);
   cudaFuncSetAttribute(window_attention_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   window_attention_bwd_kernel<HD><<<grid, 64, smem, st>>>(qkv, ldq, table, dout, ldo, dqkv, ldg, dtable, H, W, C, heads, shift);
 }

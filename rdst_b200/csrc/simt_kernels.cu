@@ -174,8 +174,11 @@ template <typename TA, int HD>
 __global__ void __launch_bounds__(64) window_attention_simt_kernel(
     const TA* __restrict__ qkv, int64_t ldq, const float* __restrict__ table, TA* __restrict__ out, int64_t ldo,
     int H, int W, int C, int heads, int shift) {
-  __shared__ float sk[64][HD + 1];
-  __shared__ float sv[64][HD + 1];
+  // K / V rows padded to a multiple of 4 floats (pads zero): every thread reads the same row (broadcast), so one
+  // 16-byte shared-memory load feeds four FMAs instead of one
+  constexpr int HP = (HD + 3) / 4 * 4;
+  __shared__ __align__(16) float sk[64][HP];
+  __shared__ __align__(16) float sv[64][HP];
   __shared__ float stab[225];
   __shared__ int sreg[64];
 
@@ -199,12 +202,12 @@ __global__ void __launch_bounds__(64) window_attention_simt_kernel(
   sreg[i] = reg;
 
   const TA* row = qkv + t * ldq + h * HD;
-  float q[HD];
+  float q[HP];
 #pragma unroll
-  for (int d = 0; d < HD; ++d) {
-    q[d] = ld_act(row + d);
-    sk[i][d] = ld_act(row + C + d);
-    sv[i][d] = ld_act(row + 2 * C + d);
+  for (int d = 0; d < HP; ++d) {
+    q[d] = d < HD ? ld_act(row + d) : 0.f;
+    sk[i][d] = d < HD ? ld_act(row + C + d) : 0.f;
+    sv[i][d] = d < HD ? ld_act(row + 2 * C + d) : 0.f;
   }
   __syncthreads();
 
@@ -214,7 +217,10 @@ __global__ void __launch_bounds__(64) window_attention_simt_kernel(
   for (int j = 0; j < 64; ++j) {
     float acc = 0.f;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) acc = fmaf(q[d], sk[j][d], acc);
+    for (int d = 0; d < HP; d += 4) {
+      const float4 kv = *reinterpret_cast<const float4*>(&sk[j][d]);
+      acc = fmaf(q[d], kv.x, acc); acc = fmaf(q[d + 1], kv.y, acc); acc = fmaf(q[d + 2], kv.z, acc); acc = fmaf(q[d + 3], kv.w, acc);
+    }
     const int jy = j >> 3, jx = j & 7;
     acc += stab[(iy - jy + 7) * 15 + (ix - jx + 7)];
     if (shift > 0 && sreg[j] != reg) acc += -100.0f;
@@ -225,14 +231,17 @@ __global__ void __launch_bounds__(64) window_attention_simt_kernel(
 #pragma unroll
   for (int j = 0; j < 64; ++j) { s[j] = expf(s[j] - mx); sum += s[j]; }
   const float inv = 1.0f / sum;
-  float o[HD];
+  float o[HP];
 #pragma unroll
-  for (int d = 0; d < HD; ++d) o[d] = 0.f;
+  for (int d = 0; d < HP; ++d) o[d] = 0.f;
 #pragma unroll
   for (int j = 0; j < 64; ++j) {
     const float p = s[j] * inv;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = fmaf(p, sv[j][d], o[d]);
+    for (int d = 0; d < HP; d += 4) {
+      const float4 vv = *reinterpret_cast<const float4*>(&sv[j][d]);
+      o[d] = fmaf(p, vv.x, o[d]); o[d + 1] = fmaf(p, vv.y, o[d + 1]); o[d + 2] = fmaf(p, vv.z, o[d + 2]); o[d + 3] = fmaf(p, vv.w, o[d + 3]);
+    }
   }
   TA* orow = out + t * ldo + h * HD;
 #pragma unroll
