@@ -1,0 +1,124 @@
+"""world_size-2 gloo test (CPU) of the data-parallel gradient exchange (rdst_b200/ddp.py): buckets follow the links of the
+network, every bucket's all-reduce is launched as soon as its last gradient has been accumulated (reverse link order =
+overlap with the rest of backward), `p.grad` are views of the flat bucket buffers, and the averaged gradients equal the
+mean of the per-rank gradients computed in one process."""
+import os
+import socket
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+import helpers
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+class _Link(torch.nn.Module):
+    def __init__(self, d):
+        super().__init__()
+        self.fc = torch.nn.Linear(d, d)
+        self.norm = torch.nn.LayerNorm(d)
+
+    def forward(self, x):
+        return x + self.fc(self.norm(x))
+
+
+class _Net(torch.nn.Module):
+    """Same top-level names as RDSTSR (head / patch_embed / body.i / norm / tail) so rdst_link_of() applies."""
+
+    def __init__(self, d=8, n=3):
+        super().__init__()
+        self.head = torch.nn.Linear(d, d)
+        self.patch_embed = torch.nn.LayerNorm(d)
+        self.body = torch.nn.ModuleList([_Link(d) for _ in range(n)])
+        self.norm = torch.nn.LayerNorm(d)
+        self.tail = torch.nn.Linear(d, 1)
+        self.frozen = torch.nn.Parameter(torch.ones(1), requires_grad=False)
+
+    def forward(self, x):
+        x = self.patch_embed(self.head(x))
+        for b in self.body:
+            x = b(x)
+        return self.tail(self.norm(x))
+
+
+def _data(rank):
+    g = torch.Generator().manual_seed(10 + rank)
+    return torch.randn(16, 8, generator=g), torch.randn(16, 1, generator=g)
+
+
+def _worker(rank, world, port, ret):
+    import sys
+    if helpers.ROOT not in sys.path:
+        sys.path.insert(0, helpers.ROOT)
+    from rdst_b200 import ddp
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    torch.set_num_threads(1)
+    torch.manual_seed(0)
+    net = _Net()
+    red = ddp.BucketedAllReduce(net)
+    x, y = _data(rank)
+    ok = True
+    for step in range(2):                                   # second step: buffers re-zeroed, views still attached
+        red.begin_step()
+        torch.nn.functional.l1_loss(net(x), y).backward()
+        order = list(red.launch_order)
+        red.finish()
+        ok &= order == ["tail", "body.2", "body.1", "body.0", "head"]
+        ok &= all(p.grad.data_ptr() == v.data_ptr() for b in red.buckets for p, v in zip(b["params"], b["views"]))
+    # reference: mean over ranks of the single-process gradients
+    torch.manual_seed(0)
+    ref = _Net()
+    acc = [torch.zeros_like(p) for p in ref.parameters() if p.requires_grad]
+    for r in range(world):
+        ref.zero_grad()
+        xr, yr = _data(r)
+        torch.nn.functional.l1_loss(ref(xr), yr).backward()
+        for a, p in zip(acc, [p for p in ref.parameters() if p.requires_grad]):
+            a += p.grad / world
+    got = [p.grad for p in net.parameters() if p.requires_grad]
+    err = max((g - a).abs().max().item() for g, a in zip(got, acc))
+    # a backward pass that leaves a bucket without gradients must be reported, not silently skipped
+    red.begin_step()
+    net.body[0](x).sum().backward()
+    try:
+        red.finish()
+        raised = False
+    except RuntimeError as e:
+        raised = "received no gradient" in str(e)
+    for w in red._works:
+        w.wait()
+    if rank == 0:
+        ret.update(ok=bool(ok), err=err, raised=raised, frozen_grad=net.frozen.grad is None,
+                   keys=[b["key"] for b in red.buckets])
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_two_ranks():
+    port = _free_port()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
+    assert ret["ok"], "launch order / gradient views"
+    assert ret["err"] < 1e-6, ret["err"]
+    assert ret["raised"] and ret["frozen_grad"]
+    assert sorted(ret["keys"]) == ["body.0", "body.1", "body.2", "head", "tail"]
+
+
+def test_rdst_link_of_maps_state_dict_names():
+    from rdst_b200 import ddp
+    assert ddp.rdst_link_of("body.3.body.1.body.blocks.0.attn.qkv.weight") == "body.3"
+    assert ddp.rdst_link_of("body.0.conv.bias") == "body.0"
+    assert ddp.rdst_link_of("head.weight") == "head" and ddp.rdst_link_of("patch_embed.norm.bias") == "head"
+    for n in ("norm.weight", "conv_after_body.bias", "tail.0.0.weight", "tail.1.bias"):
+        assert ddp.rdst_link_of(n) == "tail"
