@@ -182,6 +182,18 @@ int rdst_gemm_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, int w
 int rdst_gemm_tn_tc(const float* dy, int64_t ldy, const float* x, int64_t ldx, float* dw, float* db, int64_t T,
                     int N, int K, int conv, int B, int H, int W, int Cin, int x_op, int x_creal, void* stream);
 
+/* Window attention of the training path on tcgen05 (rdst_b200/csrc/tc_attn_train.cu): same contract as
+ * rdst_window_attention_fwd / _bwd in fp32 storage (qkv [T][ldq] = q|k|v with q pre-scaled, table (225, 6), heads = 6,
+ * C in {60, 90, 120}), operands rounded to bf16 while staged.  The forward also writes the row log-sum-exp
+ * lse [T][6] (may be NULL), which the backward reads instead of recomputing the softmax reduction.
+ * Replaces WindowAttention.forward (swin_transformer_sr.py:110-141) + roll / window_partition / window_reverse / mask
+ * (:32-59, :211-232, :239-271) and their autograd. */
+int rdst_window_attention_tc_fwd(const float* qkv, int64_t ldq, const float* table, float* out, int64_t ldo, float* lse,
+                                 int B, int H, int W, int C, int shift, void* stream);
+int rdst_window_attention_tc_bwd(const float* qkv, int64_t ldq, const float* table, const float* lse, const float* dout,
+                                 int64_t ldo, float* dqkv, int64_t ldg, float* dtable, int B, int H, int W, int C, int shift,
+                                 void* stream);
+
 /* ---- tcgen05 / TMEM kernels (bf16 operands, fp32 accumulate), sm_100a only ---------------------------- */
 
 /* Fused Swin MLP:  Y[t] = X[t] + fc2( GELU( fc1( LNhat(X[t]) ) ) ),  bf16 storage, T tokens, C in {60,90,120}

@@ -37,6 +37,8 @@ _SIGNATURES = {
     "rdst_window_attention_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _i, _vp]),
     "rdst_pack_linear_fwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "rdst_pack_linear_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
+    "rdst_window_attention_tc_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rdst_window_attention_tc_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp]),
     "rdst_gemm_tc": (C.c_int, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _f,
                                _i, _i, _i, _i, _i, _i, _vp]),
     "rdst_gemm_tn_tc": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

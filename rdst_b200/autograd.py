@@ -365,12 +365,18 @@ class BlockFunction(torch.autograd.Function):
                     qkv, o = e(T, _pad8(3 * c) if tc else 3 * c), e(T, cp if tc else c)
                     x1, hid, y = e(T, cp), e(T, hp), e(T, cp)
                     linear(src, W[st["wqkv"]], W[st["bqkv"]], qkv, cp, 3 * c, ln_creal=c)
-                    _call("rdst_window_attention_fwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(o), _ld(o), B, H, Wd, c,
-                          packing.HEADS, st["shift"], F32, _lib.stream_ptr())
+                    lse = None
+                    if tc:      # tcgen05 attention; keeps the row log-sum-exp for the backward kernel
+                        lse = e(T, packing.HEADS)
+                        _call("rdst_window_attention_tc_fwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(o), _ld(o), _p(lse),
+                              B, H, Wd, c, st["shift"], _lib.stream_ptr())
+                    else:
+                        _call("rdst_window_attention_fwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(o), _ld(o), B, H, Wd, c,
+                              packing.HEADS, st["shift"], F32, _lib.stream_ptr())
                     linear(o, W[st["wproj"]], W[st["bproj"]], x1, c, cp, resid=src)
                     linear(x1, W[st["w1"]], W[st["b1"]], hid, cp, hp, ln_creal=c)
                     linear(hid, W[st["w2"]], W[st["b2"]], y, hp, cp, resid=x1, gelu_in=True)   # act = GELU(hid) not stored
-                    sl.append(dict(x=src, qkv=qkv, o=o, x1=x1, hid=hid, y=y))
+                    sl.append(dict(x=src, qkv=qkv, o=o, x1=x1, hid=hid, y=y, lse=lse))
                     src = y
                 off = 64 + 32 * j
                 linear(src, W[ds["tw"]], W[ds["tb"]], D[:, off:], ds["stl"][0]["cp"], 32, ln_creal=c, scale=ds["scale"])
@@ -552,8 +558,12 @@ def _stl_backward(st, sv, W, gz, dY, B, H, Wd, accumulate_into=None):
     dO = torch.empty_like(o)
     linear_t(dX1, W[st["wproj"]], dO, cp, c)
     dqkv = torch.empty_like(qkv)
-    _call("rdst_window_attention_bwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(dO), _ld(dO), _p(dqkv), _ld(dqkv),
-          _p(gz(st["table"])), B, H, Wd, c, packing.HEADS, st["shift"], _lib.stream_ptr())
+    if sv["lse"] is not None:
+        _call("rdst_window_attention_tc_bwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(sv["lse"]), _p(dO), _ld(dO),
+              _p(dqkv), _ld(dqkv), _p(gz(st["table"])), B, H, Wd, c, st["shift"], _lib.stream_ptr())
+    else:
+        _call("rdst_window_attention_bwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(dO), _ld(dO), _p(dqkv), _ld(dqkv),
+              _p(gz(st["table"])), B, H, Wd, c, packing.HEADS, st["shift"], _lib.stream_ptr())
     gemm_tn(dqkv, x, gz(st["wqkv"]), gz(st["bqkv"]), 3 * c, cp, x_op=1, creal=c)
     linear_t(dqkv, W[st["wqkv"]], dxh, 3 * c, cp)
     if accumulate_into is None:

@@ -186,6 +186,41 @@ def test_gemm_tc_fused_gelu_and_lnhat_operands():
     _close(dwq[:, :c], bf(dq).t() @ bf(lnhat(x, c))[:, :c])
 
 
+@pytest.mark.parametrize("B,H,W,C,shift", [(2, 16, 24, 60, 0), (2, 16, 24, 60, 4), (1, 8, 8, 90, 4), (1, 40, 32, 120, 4),
+                                            (3, 24, 24, 120, 0), (3, 8, 8, 90, 0), (32, 24, 24, 120, 4)])
+def test_window_attention_tc_fwd_bwd(B, H, W, C, shift):
+    """tcgen05 window attention of the training path against the fp32 CUDA-core kernels (which tests/test_gpu_kernels.py
+    and test_gpu_backward.py pin to the reference): forward output, log-sum-exp, and all three gradients + table gradient."""
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(B * H + C + shift)
+    T = B * H * W
+    ldq, ldo = (3 * C + 7) // 8 * 8, {60: 64, 90: 96, 120: 128}[C]
+    qkv = torch.randn(T, ldq, device="cuda", generator=g) * 0.7
+    table = torch.randn(225, 6, device="cuda", generator=g) * 0.5
+    o_ref = torch.zeros(T, ldo, device="cuda")
+    L.call("rdst_window_attention_fwd", L.ptr(qkv), ldq, L.ptr(table), L.ptr(o_ref), ldo, B, H, W, C, 6, shift, 0, L.stream_ptr())
+    o = torch.zeros(T, ldo, device="cuda")
+    lse = torch.zeros(T, 6, device="cuda")
+    L.call("rdst_window_attention_tc_fwd", L.ptr(qkv), ldq, L.ptr(table), L.ptr(o), ldo, L.ptr(lse), B, H, W, C, shift,
+           L.stream_ptr())
+    torch.cuda.synchronize()
+    assert torch.isfinite(lse).all()
+    assert (o[:, :C] - o_ref[:, :C]).abs().max().item() < 3e-2 * o_ref.abs().max().item()
+    do = torch.randn(T, ldo, device="cuda", generator=g)
+    dq_ref, dt_ref = torch.zeros(T, ldq, device="cuda"), torch.zeros(225, 6, device="cuda")
+    L.call("rdst_window_attention_bwd", L.ptr(qkv), ldq, L.ptr(table), L.ptr(do), ldo, L.ptr(dq_ref), ldq, L.ptr(dt_ref),
+           B, H, W, C, 6, shift, L.stream_ptr())
+    dq, dt = torch.zeros(T, ldq, device="cuda"), torch.zeros(225, 6, device="cuda")
+    L.call("rdst_window_attention_tc_bwd", L.ptr(qkv), ldq, L.ptr(table), L.ptr(lse), L.ptr(do), ldo, L.ptr(dq), ldq,
+           L.ptr(dt), B, H, W, C, shift, L.stream_ptr())
+    torch.cuda.synchronize()
+    for name, lo in (("dq", 0), ("dk", C), ("dv", 2 * C)):
+        a, b = dq[:, lo:lo + C], dq_ref[:, lo:lo + C]
+        rel = ((a - b).norm() / b.norm()).item()
+        assert rel < 2e-2, (name, rel)
+    assert ((dt - dt_ref).norm() / dt_ref.norm()).item() < 2e-2
+
+
 def _oracle_grads(sd, x, target, scale):
     p = {k: (v.clone().double().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
     out = O.forward(p, x.double(), scale)
