@@ -2,6 +2,7 @@
 import csv, subprocess, sys, io
 rep = sys.argv[1]
 top_n = int(sys.argv[2]) if len(sys.argv) > 2 else 30
+kidx = int(sys.argv[3]) if len(sys.argv) > 3 else 0          # which captured launch the source page is read for
 raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(raw)))
 hdr, units = rows[0], rows[1]
@@ -17,7 +18,8 @@ for i, h in enumerate(hdr):
 src = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(src)))
 idx = [i for i, r in enumerate(rows) if r and r[0] == "Address"]
-start = idx[0]; end = idx[1] - 1 if len(idx) > 1 else len(rows)
+start = idx[kidx]; end = idx[kidx + 1] - 1 if len(idx) > kidx + 1 else len(rows)
+print(f"source-level samples of captured launch #{kidx}")
 hdr = rows[start]; data = [r for r in rows[start + 1:end] if len(r) >= len(hdr)]
 ci = {h: i for i, h in enumerate(hdr)}
 tot = sum(int(r[ci["# Samples"]]) for r in data)
