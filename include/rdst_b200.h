@@ -158,6 +158,21 @@ int rdst_pack_linear_bwd(const float* W, const float* gamma, const float* beta, 
                          float* dW, float* db, float* dgamma, float* dbeta, int N, int K, int ldp, int scatter_rows,
                          int scatter_cols, int q_rows, float q_scale, void* stream);
 
+/* Batched form of the two entry points above: all Linears of one RDSTB (<= RDST_PACK_MAX) in ONE launch; the descriptors
+ * are copied into the kernel's parameter space, nothing is read from `descs` after the call returns.
+ * backward == 0: fields W, b, gamma, beta, Wp, bp are used; backward != 0: W, gamma, beta, dWp, dbp, dW, db, dgamma, dbeta. */
+#define RDST_PACK_MAX 32
+typedef struct RdstPackDesc {
+  const float* W; const float* b; const float* gamma; const float* beta;
+  float* Wp; float* bp;
+  const float* dWp; const float* dbp;
+  float* dW; float* db; float* dgamma; float* dbeta;
+  int N, K, ldp, scatter_rows, scatter_cols, q_rows;
+  float q_scale;
+  int _pad;
+} RdstPackDesc;
+int rdst_pack_linear_batch(const RdstPackDesc* descs, int n, int backward, void* stream);
+
 /* ---- tensor-core GEMMs of the training path (precision 'bf16'): fp32 storage, operands rounded to bf16 while they
  *      are staged into shared memory, tcgen05.mma with fp32 accumulation in TMEM (rdst_b200/csrc/tc_train.cu) ------ */
 

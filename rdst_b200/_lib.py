@@ -16,6 +16,13 @@ ABI_VERSION = 1
 
 _vp, _i64, _i, _f = C.c_void_p, C.c_int64, C.c_int, C.c_float
 
+class PackDesc(C.Structure):
+    """RdstPackDesc of include/rdst_b200.h."""
+    _fields_ = [(n, C.c_void_p) for n in ("W", "b", "gamma", "beta", "Wp", "bp", "dWp", "dbp", "dW", "db", "dgamma", "dbeta")] + \
+               [(n, C.c_int) for n in ("N", "K", "ldp", "scatter_rows", "scatter_cols", "q_rows")] + \
+               [("q_scale", C.c_float), ("_pad", C.c_int)]
+
+
 _SIGNATURES = {
     "rdst_abi_version": (C.c_int, []),
     "rdst_last_error": (C.c_char_p, []),
@@ -39,6 +46,7 @@ _SIGNATURES = {
     "rdst_pack_linear_bwd": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _i, _f, _vp]),
     "rdst_window_attention_tc_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp]),
     "rdst_window_attention_tc_bwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rdst_pack_linear_batch": (C.c_int, [_vp, _i, _i, _vp]),
     "rdst_gemm_tc": (C.c_int, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _f,
                                _i, _i, _i, _i, _i, _i, _vp]),
     "rdst_gemm_tn_tc": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),

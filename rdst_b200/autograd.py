@@ -205,6 +205,24 @@ def block_layout(m, blk):
     return bs
 
 
+def _pack_batch(lins, P, W, G, GP, backward):
+    """All Linears of one RDSTB in one rdst_pack_linear_batch launch (forward: P -> W; backward: G -> GP)."""
+    arr = (_lib.PackDesc * len(lins))()
+    dp = lambda t: None if t is None else t.data_ptr()
+    for d, l in zip(arr, lins):
+        ln = l["g"] is not None
+        d.W, d.b = dp(P[l["w"]]), dp(P[l["b"]])
+        d.gamma, d.beta = (dp(P[l["g"]]), dp(P[l["be"]])) if ln else (None, None)
+        if backward:
+            d.dWp, d.dbp, d.dW, d.db = dp(G[l["sw"]]), dp(G[l["sb"]]), dp(GP[l["w"]]), dp(GP[l["b"]])
+            d.dgamma, d.dbeta = (dp(GP[l["g"]]), dp(GP[l["be"]])) if ln else (None, None)
+        else:
+            d.Wp, d.bp = dp(W[l["sw"]]), dp(W[l["sb"]])
+        d.N, d.K, d.ldp, d.scatter_rows, d.scatter_cols = l["N"], l["K"], l["ldp"], l["srows"], l["scols"]
+        d.q_rows, d.q_scale = l["q_rows"], l["q_scale"]
+    _call("rdst_pack_linear_batch", arr, len(lins), 1 if backward else 0, _lib.stream_ptr())
+
+
 def _views(buf, slots):
     return [buf[o:o + _numel(s)].view(s) for o, s in slots]
 
@@ -344,11 +362,7 @@ class BlockFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             # packed weights of the block: one zeroed buffer, one rdst_pack_linear_fwd per Linear (csrc/pack.cu)
             W = _views(z(bs["packed_floats"]), bs["slots"])
-            st_ = _lib.stream_ptr()
-            for l in bs["lins"]:
-                _call("rdst_pack_linear_fwd", _p(P[l["w"]]), _p(P[l["b"]]), _p(None if l["g"] is None else P[l["g"]]),
-                      _p(None if l["be"] is None else P[l["be"]]), _p(W[l["sw"]]), _p(W[l["sb"]]), l["N"], l["K"], l["ldp"],
-                      l["srows"], l["scols"], l["q_rows"], l["q_scale"], st_)
+            _pack_batch(bs["lins"], P, W, None, None, backward=False)
             # slots | LFF filter, bias (packed by torch ops under autograd) | relative-position tables, reversed, used as
             # stored: W[-1-i] is table i
             W = W + [lff_w, lff_b] + [P[i] for i in reversed(bs["tables"])]
@@ -432,16 +446,15 @@ class BlockFunction(torch.autograd.Function):
             dXin = dD[:, :64].contiguous()
             # packed-weight gradients -> gradients of the reference-named parameters
             GP = [None] * len(P)
-            st_ = _lib.stream_ptr()
+            ln_idx = [i for l in bs["lins"] if l["g"] is not None for i in (l["g"], l["be"])]
+            lnbuf = z(sum(P[i].numel() for i in ln_idx))        # dgamma / dbeta are accumulated: one zero fill for all
+            off = 0
+            for i in ln_idx:
+                GP[i] = lnbuf[off:off + P[i].numel()].view_as(P[i])
+                off += P[i].numel()
             for l in bs["lins"]:
-                ln = l["g"] is not None
                 GP[l["w"]], GP[l["b"]] = torch.empty_like(P[l["w"]]), torch.empty_like(P[l["b"]])
-                if ln:
-                    GP[l["g"]], GP[l["be"]] = torch.zeros_like(P[l["g"]]), torch.zeros_like(P[l["be"]])
-                _call("rdst_pack_linear_bwd", _p(P[l["w"]]), _p(P[l["g"]] if ln else None), _p(P[l["be"]] if ln else None),
-                      _p(G[l["sw"]]), _p(G[l["sb"]]), _p(GP[l["w"]]), _p(GP[l["b"]]), _p(GP[l["g"]] if ln else None),
-                      _p(GP[l["be"]] if ln else None), l["N"], l["K"], l["ldp"], l["srows"], l["scols"], l["q_rows"],
-                      l["q_scale"], st_)
+            _pack_batch(bs["lins"], P, None, G, GP, backward=True)
             for i, pi in enumerate(bs["tables"]):
                 GP[pi] = G[-1 - i]
         ctx.saved = None
