@@ -191,6 +191,15 @@ int rdst_gemm_tc(const float* x, int64_t ldx, const float* w, int64_t ldw, int w
                  int64_t T, int K, int N, int a_op, int ln_creal, float out_scale, int conv, int B, int H, int W,
                  int Cin, int shuffle, void* stream);
 
+/* Data gradient of LayerNorm-hat -> Linear in one kernel:  dxh = scale * dY[T][K] . W[K][N]  (W = forward weight, [out=K][in=N]),
+ * then, in the epilogue, the LayerNorm-hat backward of every row with respect to X[t][0:N] over `creal` real channels
+ * (pads of the dense-block layout excluded, pad outputs 0) plus up to two residual rows:
+ *   dX = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)) + R + R2.      N <= 128, N % 16 == 0; dX may alias R2.
+ * = rdst_gemm_tc(w_mn_major = 1) followed by rdst_lnhat_bwd(dense_layout = 1), without storing dxh. */
+int rdst_gemm_tc_lnbwd(const float* dy, int64_t ldy, const float* w, int64_t ldw, const float* x, int64_t ldx,
+                       const float* resid, int64_t ldr, const float* resid2, int64_t ldr2, float* dx, int64_t ldo,
+                       int64_t T, int K, int N, int creal, float scale, void* stream);
+
 /* Tensor-core version of rdst_gemm_tn_acc: dW[n][k] += sum_t dY[t][n] * op(X)[t][k], db[n] += sum_t dY[t][n].
  * x_op: 0 none, 1 LNhat over x_creal real channels (K <= 240), 2 exact-erf GELU -- the normalised / activated operand of
  * the weight gradient is recomputed while staging instead of being stored.  Cin % 16 == 0 in conv mode. */

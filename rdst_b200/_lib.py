@@ -49,6 +49,7 @@ _SIGNATURES = {
     "rdst_pack_linear_batch": (C.c_int, [_vp, _i, _i, _vp]),
     "rdst_gemm_tc": (C.c_int, [_vp, _i64, _vp, _i64, _i, _vp, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _f,
                                _i, _i, _i, _i, _i, _i, _vp]),
+    "rdst_gemm_tc_lnbwd": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _f, _vp]),
     "rdst_gemm_tn_tc": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rdst_stl_mlp_fwd_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _i64, _i, _i, _vp]),
     "rdst_stl_attn_fwd_bf16": (C.c_int, [_vp, _i64, _vp, _i64, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),

@@ -85,6 +85,19 @@ def linear_t(dy, w, dx, K, N, scale=1.0, gelu_aux=None):
         _call("rdst_gelu_bwd", _p(gelu_aux), _ld(gelu_aux), _p(tmp), N, _p(dx), _ld(dx), T, N, _lib.stream_ptr())
 
 
+def linear_t_lnbwd(dy, w, x, dx, K, N, creal, scale=1.0, resid=None, resid2=None):
+    """dx = lnhat_bwd(scale * dy . w, x) + resid + resid2: data gradient through LayerNorm-hat -> Linear (w = forward weight
+    [out=K][in=N]).  One tensor-core kernel in bf16 mode (the LayerNorm backward is the GEMM's epilogue)."""
+    if _tc() and N <= 128 and N % 16 == 0 and _aligned(dy, x, dx, resid, resid2):
+        _call("rdst_gemm_tc_lnbwd", _p(dy), _ld(dy), _p(w), _ld(w), _p(x), _ld(x), _p(resid), 0 if resid is None else _ld(resid),
+              _p(resid2), 0 if resid2 is None else _ld(resid2), _p(dx), _ld(dx), dy.shape[0], K, N, creal, scale,
+              _lib.stream_ptr())
+        return
+    dxh = torch.empty(dy.shape[0], N, dtype=torch.float32, device=dy.device)
+    linear_t(dy, w, dxh, K, N, scale=scale)
+    lnhat_bwd(dxh, x, dx, N, creal, resid=resid, resid2=resid2)
+
+
 def conv(x, w, b, y, B, H, W, cin, n, scale=1.0, shuffle=0, resid=None):
     if _tc() and cin % 16 == 0 and _aligned(x, y, resid):
         _call("rdst_gemm_tc", _p(x), _ld(x), _p(w), 9 * cin, 0, _p(b), _p(resid), 0 if resid is None else _ld(resid), None, 0,
@@ -434,11 +447,8 @@ class BlockFunction(torch.autograd.Function):
                 gemm_tn(dg, y1, gw, gb, 32, cp, x_op=1, creal=c)
                 if ds["scale"] != 1.0:
                     gw.mul_(ds["scale"]); gb.mul_(ds["scale"])
-                dxh = e(T, cp)
-                linear_t(dg, W[ds["tw"]], dxh, 32, cp, scale=ds["scale"])
                 dy_cur = e(T, cp)
-                lnhat_bwd(dxh, y1, dy_cur, cp, c)
-                del dxh
+                linear_t_lnbwd(dg, W[ds["tw"]], y1, dy_cur, 32, cp, c, scale=ds["scale"])
                 for k in range(len(ds["stl"]) - 1, -1, -1):
                     first = k == 0
                     dy_cur = _stl_backward(ds["stl"][k], sl[k], W, gz, dy_cur, B, H, Wd,
@@ -561,10 +571,8 @@ def _stl_backward(st, sv, W, gz, dY, B, H, Wd, accumulate_into=None):
     dhid = e(T, hp)
     linear_t(dY, W[st["w2"]], dhid, cp, hp, gelu_aux=hid)                            # (dY . W2) * gelu'(hid)
     gemm_tn(dhid, x1, gz(st["w1"]), gz(st["b1"]), hp, cp, x_op=1, creal=c)           # operand lnhat(x1) recomputed
-    dxh = e(T, cp)
-    linear_t(dhid, W[st["w1"]], dxh, hp, cp)
     dX1 = e(T, cp)
-    lnhat_bwd(dxh, x1, dX1, cp, c, resid=dY)
+    linear_t_lnbwd(dhid, W[st["w1"]], x1, dX1, hp, cp, c, resid=dY)
     del dhid
     # ---- x1 = x + proj(attn(lnhat(x))) ----
     gemm_tn(dX1, o, gz(st["wproj"]), gz(st["bproj"]), cp, c)
@@ -578,12 +586,11 @@ def _stl_backward(st, sv, W, gz, dY, B, H, Wd, accumulate_into=None):
         _call("rdst_window_attention_bwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(dO), _ld(dO), _p(dqkv), _ld(dqkv),
               _p(gz(st["table"])), B, H, Wd, c, packing.HEADS, st["shift"], _lib.stream_ptr())
     gemm_tn(dqkv, x, gz(st["wqkv"]), gz(st["bqkv"]), 3 * c, cp, x_op=1, creal=c)
-    linear_t(dqkv, W[st["wqkv"]], dxh, 3 * c, cp)
     if accumulate_into is None:
         dX = e(T, cp)
-        lnhat_bwd(dxh, x, dX, cp, c, resid=dX1)
+        linear_t_lnbwd(dqkv, W[st["wqkv"]], x, dX, 3 * c, cp, c, resid=dX1)
         return dX
-    lnhat_bwd(dxh, x, accumulate_into, cp, c, resid=dX1, resid2=accumulate_into)
+    linear_t_lnbwd(dqkv, W[st["wqkv"]], x, accumulate_into, 3 * c, cp, c, resid=dX1, resid2=accumulate_into)
     return None
 
 

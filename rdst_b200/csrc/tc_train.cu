@@ -34,6 +34,8 @@ struct GemmArgs {
   const float* w; int64_t ldw; int w_mn, w_vec;
   const float* bias; const float* resid; int64_t ldr;
   const float* aux; int64_t lda;   // epilogue: acc *= gelu'(aux[t][n])  (GELU backward fused into the data-gradient GEMM)
+  const float* lnx; int64_t ldlx; int lnb_creal;   // epilogue: LayerNorm-hat backward of the row w.r.t. lnx (N <= 128)
+  const float* resid2; int64_t ldr2;
   float* y; int64_t ldy;
   int64_t T; int K, N, Np;       // Np = N rounded up to 16
   int KC, nkc;                   // K-chunk (multiple of 16, <= 256 or the whole padded K) and number of chunks
@@ -164,6 +166,7 @@ __global__ void __launch_bounds__(NT_GEMM, 1) gemm_tc_kernel(const GemmArgs a) {
   __shared__ uint32_t tmem_base_s;
   __shared__ float s_mean[TM], s_rstd[TM];
   __shared__ float s_bias[512];
+  __shared__ float2 s_red[2][NT_GEMM / 128][TM];
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int KC = a.KC, Np = a.Np;
   uint8_t* sA = smem;                               // K-major [KC/8][128][8] bf16
@@ -306,7 +309,93 @@ __global__ void __launch_bounds__(NT_GEMM, 1) gemm_tc_kernel(const GemmArgs a) {
     mbar_wait(&bar, phase);
     phase ^= 1;
     fence_after_sync();
-    // ---- epilogue: thread = token row (TMEM lane), the four thread quarters alternate over 16-column groups ----
+    // ---- epilogue A: the accumulator row is d(xhat); LayerNorm-hat backward w.r.t. the row of lnx, + residual(s):
+    //      dx = rstd * (dxh - mean(dxh) - xhat * mean(dxh * xhat)) over the real channels, pads 0   (rdst_lnhat_bwd) ----
+    if (a.lnx) {
+      const int r = tid & 127, quarter = tid >> 7;
+      const int64_t t = t0 + r;
+      const bool live = t < a.T;
+      float av[2][16], xv[2][16];
+      float s = 0.f, ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int n0 = (quarter + 4 * i) * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) { av[i][j] = 0.f; xv[i][j] = 0.f; }
+        if (n0 < a.N) {                                   // warp-uniform
+          uint32_t v[16];
+          __syncwarp();
+          tmem_ld_x16(tmem + ((uint32_t)((warp & 3) * 32) << 16) + n0, v);
+          wait_ld();
+          if (live) {
+            const float4* xp = reinterpret_cast<const float4*>(a.lnx + t * a.ldlx + n0);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float4 x4 = __ldg(xp + j);
+              xv[i][4 * j] = x4.x; xv[i][4 * j + 1] = x4.y; xv[i][4 * j + 2] = x4.z; xv[i][4 * j + 3] = x4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              av[i][j] = __uint_as_float(v[j]) * a.out_scale;
+              s += xv[i][j];
+              ss += xv[i][j] * xv[i][j];
+            }
+          }
+        }
+      }
+      s_red[0][quarter][r] = make_float2(s, ss);
+      __syncthreads();
+      const float inv = 1.f / (float)a.lnb_creal;
+      float S = 0.f, SS = 0.f;
+#pragma unroll
+      for (int q = 0; q < NT_GEMM / 128; ++q) { const float2 p = s_red[0][q][r]; S += p.x; SS += p.y; }
+      const float mean = S * inv;
+      const float rstd = rsqrtf(fmaxf(SS * inv - mean * mean, 0.f) + 1e-5f);
+      float m1 = 0.f, m2 = 0.f;
+#pragma unroll
+      for (int i = 0; i < 2; ++i) {
+        const int n0 = (quarter + 4 * i) * 16;
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+          const int n = n0 + j;
+          const bool real = n < 60 || (n >= 64 && ((n - 64) & 31) < 30);
+          xv[i][j] = (xv[i][j] - mean) * rstd;            // xhat
+          if (real && n < a.N) { m1 += av[i][j]; m2 = fmaf(av[i][j], xv[i][j], m2); }
+        }
+      }
+      s_red[1][quarter][r] = make_float2(m1, m2);
+      __syncthreads();
+      float M1 = 0.f, M2 = 0.f;
+#pragma unroll
+      for (int q = 0; q < NT_GEMM / 128; ++q) { const float2 p = s_red[1][q][r]; M1 += p.x; M2 += p.y; }
+      M1 *= inv;
+      M2 *= inv;
+      if (live) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+          const int n0 = (quarter + 4 * i) * 16;
+          if (n0 < a.N) {
+            float* yp = a.y + t * a.ldy + n0;
+            const float4* rp = a.resid ? reinterpret_cast<const float4*>(a.resid + t * a.ldr + n0) : nullptr;
+            const float4* rp2 = a.resid2 ? reinterpret_cast<const float4*>(a.resid2 + t * a.ldr2 + n0) : nullptr;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              float o[4];
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const int n = n0 + 4 * j + e;
+                const bool real = n < 60 || (n >= 64 && ((n - 64) & 31) < 30);
+                o[e] = real ? rstd * (av[i][4 * j + e] - M1 - xv[i][4 * j + e] * M2) : 0.f;
+              }
+              if (rp) { const float4 q4 = rp[j]; o[0] += q4.x; o[1] += q4.y; o[2] += q4.z; o[3] += q4.w; }
+              if (rp2) { const float4 q4 = rp2[j]; o[0] += q4.x; o[1] += q4.y; o[2] += q4.z; o[3] += q4.w; }
+              *reinterpret_cast<float4*>(yp + 4 * j) = make_float4(o[0], o[1], o[2], o[3]);
+            }
+          }
+        }
+      }
+    } else
+    // ---- epilogue B: thread = token row (TMEM lane), the four thread quarters alternate over 16-column groups ----
     {
       const int r = tid & 127, quarter = tid >> 7;
       const int64_t t = t0 + r;
@@ -599,13 +688,42 @@ extern "C" int rdst_gemm_tc(const float* x, int64_t ldx, const float* w, int64_t
   }
   a.nkc = (Kp + a.KC - 1) / a.KC;
   const size_t smem = (size_t)TM * a.KC * 2 + (size_t)a.Np * a.KC * 2;
-  RDST_REQUIRE(smem <= 220 * 1024, "rdst_gemm_tc: operand images need %zu bytes of shared memory (K=%d N=%d)", smem, K, N);
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024);
+  RDST_REQUIRE(smem <= 212 * 1024, "rdst_gemm_tc: operand images need %zu bytes of shared memory (K=%d N=%d)", smem, K, N);
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
   if (e != cudaSuccess) { set_error("rdst_gemm_tc: smem attr: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   const int64_t tiles = (T + TM - 1) / TM;
   const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
   gemm_tc_kernel<<<grid, NT_GEMM, smem, (cudaStream_t)stream>>>(a);
   RDST_CHECK_LAUNCH("rdst_gemm_tc");
+  return RDST_OK;
+}
+
+extern "C" int rdst_gemm_tc_lnbwd(const float* dy, int64_t ldy, const float* w, int64_t ldw, const float* x, int64_t ldx,
+                                  const float* resid, int64_t ldr, const float* resid2, int64_t ldr2, float* dx, int64_t ldo,
+                                  int64_t T, int K, int N, int creal, float scale, void* stream) {
+  using namespace rdst;
+  RDST_REQUIRE(dy && w && x && dx, "rdst_gemm_tc_lnbwd: null pointer");
+  RDST_REQUIRE(T >= 0 && K > 0 && K <= 384 && N > 0 && N <= 128 && (N & 15) == 0 && creal > 0 && creal <= N,
+               "rdst_gemm_tc_lnbwd: bad shape (T=%lld K=%d N=%d creal=%d; K <= 384, N <= 128, N %% 16 == 0)", (long long)T, K, N, creal);
+  RDST_REQUIRE((ldy & 3) == 0 && (ldx & 3) == 0 && (ldo & 3) == 0 && (!resid || (ldr & 3) == 0) && (!resid2 || (ldr2 & 3) == 0) &&
+                   ((uintptr_t)dy & 15) == 0 && ((uintptr_t)x & 15) == 0 && ((uintptr_t)dx & 15) == 0 &&
+                   (!resid || ((uintptr_t)resid & 15) == 0) && (!resid2 || ((uintptr_t)resid2 & 15) == 0) &&
+                   ldy >= (K + 7) / 8 * 8 && ldx >= N && ldo >= N,
+               "rdst_gemm_tc_lnbwd: rows must be 16-byte aligned and wide enough");
+  if (T == 0) return RDST_OK;
+  GemmArgs a{};
+  a.x = dy; a.ldx = ldy; a.w = w; a.ldw = ldw; a.w_mn = 1; a.w_vec = ((ldw & 3) == 0 && ((uintptr_t)w & 15) == 0) ? 1 : 0;
+  a.resid = resid; a.ldr = ldr; a.resid2 = resid2; a.ldr2 = ldr2; a.lnx = x; a.ldlx = ldx; a.lnb_creal = creal;
+  a.y = dx; a.ldy = ldo; a.T = T; a.K = K; a.N = N; a.Np = N; a.out_scale = scale;
+  a.KC = (K + 15) / 16 * 16;
+  a.nkc = 1;
+  const size_t smem = (size_t)TM * a.KC * 2 + (size_t)a.Np * a.KC * 2;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 212 * 1024);
+  if (e != cudaSuccess) { set_error("rdst_gemm_tc_lnbwd: smem attr: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
+  const int64_t tiles = (T + TM - 1) / TM;
+  const unsigned grid = (unsigned)(tiles < sm_count() ? tiles : sm_count());
+  gemm_tc_kernel<<<grid, NT_GEMM, smem, (cudaStream_t)stream>>>(a);
+  RDST_CHECK_LAUNCH("rdst_gemm_tc_lnbwd");
   return RDST_OK;
 }
 

@@ -221,6 +221,32 @@ def test_window_attention_tc_fwd_bwd(B, H, W, C, shift):
     assert ((dt - dt_ref).norm() / dt_ref.norm()).item() < 2e-2
 
 
+@pytest.mark.parametrize("T,K,ldy,N,ldo,creal,two", [(1000, 360, 360, 128, 128, 120, False), (300, 240, 240, 128, 160, 120, True),
+                                                      (257, 270, 272, 96, 96, 90, False), (300, 32, 160, 64, 64, 60, False)])
+def test_gemm_tc_lnbwd(T, K, ldy, N, ldo, creal, two):
+    """Data-gradient GEMM with the LayerNorm-hat backward as its epilogue == rdst_gemm_tc + rdst_lnhat_bwd (fp32 kernel)."""
+    L = _lib()
+    g = torch.Generator(device="cuda").manual_seed(T + K)
+    dy = torch.randn(T, ldy, device="cuda", generator=g)
+    w = torch.randn(K, N, device="cuda", generator=g) * 0.1
+    real = torch.tensor([n < 60 or (n >= 64 and (n - 64) % 32 < 30) for n in range(N)], device="cuda")
+    x = (torch.randn(T, N, device="cuda", generator=g) + 0.4) * real
+    r = torch.randn(T, N, device="cuda", generator=g)
+    out = torch.randn(T, ldo, device="cuda", generator=g)
+    out0 = out.clone()
+    L.call("rdst_gemm_tc_lnbwd", L.ptr(dy), ldy, L.ptr(w), N, L.ptr(x), N, L.ptr(r), N, L.ptr(out) if two else None,
+           ldo if two else 0, L.ptr(out), ldo, T, K, N, creal, 0.5, L.stream_ptr())
+    dxh = torch.zeros(T, N, device="cuda")
+    L.call("rdst_gemm_tc", L.ptr(dy), ldy, L.ptr(w), N, 1, None, None, 0, None, 0, L.ptr(dxh), N, T, K, N, 0, 0, 0.5,
+           0, 0, 0, 0, 0, 0, L.stream_ptr())
+    ref = out0.clone()
+    L.call("rdst_lnhat_bwd", L.ptr(dxh), N, L.ptr(x), N, L.ptr(r), N, L.ptr(out0) if two else None, ldo if two else 0,
+           L.ptr(ref), ldo, T, N, creal, 1, L.stream_ptr())
+    torch.cuda.synchronize()
+    _close(out[:, :N], ref[:, :N].double(), tol=1e-4)
+    assert torch.equal(out[:, N:], ref[:, N:])
+
+
 def _oracle_grads(sd, x, target, scale):
     p = {k: (v.clone().double().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
     out = O.forward(p, x.double(), scale)
