@@ -10,6 +10,7 @@ import importlib
 import sys
 
 from .network import RDSTSR, make_RDSTSR
+from .swinir import SwinIR, swinir_make_model
 
 _TARGETS = ("networks.swinIR_variations", "networks.rdst_variations")
 _CALLERS = ("models.trans_sr_trainer", "models.trans_sr_tester")
@@ -30,9 +31,25 @@ def install(strict=False):
         mod.make_RDSTSR = make_RDSTSR
         mod.RDSTSR = RDSTSR
         patched.append(name)
+    # vanilla SwinIR (feature_generator = 'swinir'): `from networks.swin_transformer_sr import swinir_make_model`
+    # (models/trans_sr_trainer.py:2, models/trans_sr_tester.py:2)
+    mod = sys.modules.get("networks.swin_transformer_sr")
+    if mod is None:
+        try:
+            mod = importlib.import_module("networks.swin_transformer_sr")
+        except Exception:
+            if strict:
+                raise
+            mod = None
+    if mod is not None:
+        mod.swinir_make_model = swinir_make_model
+        mod.SwinIR = SwinIR
+        patched.append("networks.swin_transformer_sr")
     for name in _CALLERS:
         mod = sys.modules.get(name)
         if mod is not None and hasattr(mod, "make_RDSTSR"):
             mod.make_RDSTSR = make_RDSTSR
+            if hasattr(mod, "swinir_make_model"):
+                mod.swinir_make_model = swinir_make_model
             patched.append(name)
     return patched

@@ -53,3 +53,38 @@ def make_module(blocks=8, scale=4, precision="fp32", img_size=24):
     return rdst_b200.RDSTSR(img_size=img_size, sr_scale=scale, dense_layer_depths=[2] * blocks,
                             num_heads=[6] * blocks, window_size=[8] * blocks, rdb_depths=[3] * blocks,
                             mlp_ratio=2., pre_norm=True, feature_last_operation=True, precision=precision)
+
+
+# ---- vanilla SwinIR: fixtures from oracle/gen_golden_swinir.py ----
+SWINIR_CASES = ["swinir_ini_x4_40x32", "swinir_x2_16x24_b2", "swinir_x3_8x8"]
+
+
+def swinir_manifest(name):
+    rows = []
+    with open(os.path.join(GOLDEN, name + "_manifest.txt")) as f:
+        for line in f:
+            k, shape, dt = line.rstrip("\n").split("\t")
+            rows.append((k, eval(shape), getattr(torch, dt)))
+    return rows
+
+
+def load_swinir_case(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    img = int(g["meta_img_size"])
+    sd = {}
+    for k, shape, dt in swinir_manifest(name):
+        sd[k] = torch.zeros(shape, dtype=dt)
+        if k.endswith("relative_position_index"):
+            sd[k] = O.rel_pos_index()
+        if k.endswith("attn_mask"):
+            sd[k] = O.shift_mask(img, img)
+    sd = fill_state_dict(sd, int(g["meta_wseed"]), True)
+    x = synth_input(tuple(int(v) for v in g["shape"]), int(g["meta_xseed"]))
+    return dict(g=g, sd=sd, x=x, img_size=img, upscale=int(g["meta_upscale"]), depths=[int(d) for d in g["depths"]])
+
+
+def make_swinir(c, precision="fp32"):
+    from rdst_b200 import swinir
+    return swinir.SwinIR(img_size=c["img_size"], patch_size=1, in_chans=1, embed_dim=60, depths=c["depths"],
+                         num_heads=[6] * len(c["depths"]), window_size=8, mlp_ratio=2., upscale=c["upscale"], img_range=1.,
+                         upsampler="pixelshuffledirect", resi_connection="1conv", precision=precision)
