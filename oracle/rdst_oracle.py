@@ -175,14 +175,24 @@ def forward(sd, x, sr_scale=4, rnd=None, taps=None, global_res_scale=1.0, featur
     if taps is not None:
         taps["head"] = x0.clone()
         taps["embed"] = t.clone()
+    feats = []
     for i in range(count_blocks(sd)):
         t = rdstb(t, H, W, sd, f"body.{i}.", rnd=rnd)
+        feats.append(t)
         if taps is not None:
             taps[f"rdstb{i}"] = t.clone()
-    t = F.layer_norm(t, (t.shape[-1],), sd["norm.weight"], sd["norm.bias"], 1e-5)
-    res = tokens_to_map(t, H, W) * global_res_scale
-    if feature_last_operation:
-        res = conv3x3(res, sd, "conv_after_body.")
+    if "bottleneck.0.weight" in sd:
+        # RDSTSR_N, global bottleneck 'mlp' [rdst_variations.py:1071-1079,1092-1093]: cat of all RDSTB outputs -> two Linears;
+        # `norm` and `conv_after_body` exist in the state_dict but are not used by that forward
+        t = torch.cat(feats, 2)
+        t = F.linear(t, sd["bottleneck.0.weight"], sd["bottleneck.0.bias"])
+        t = F.linear(t, sd["bottleneck.1.weight"], sd["bottleneck.1.bias"])
+        res = tokens_to_map(t, H, W) * global_res_scale
+    else:
+        t = F.layer_norm(t, (t.shape[-1],), sd["norm.weight"], sd["norm.bias"], 1e-5)
+        res = tokens_to_map(t, H, W) * global_res_scale
+        if feature_last_operation:
+            res = conv3x3(res, sd, "conv_after_body.")
     res = res + x0
     if rnd is not None:
         res = rnd(res, "feat")

@@ -148,7 +148,7 @@ class Executor:
         cur = 0
         call("rdst_head_fwd", ptr(xin), P["in_scale"], P["in_bias"], ptr(P["head_w"]), ptr(P["head_b"]),
              ptr(P["pe_g"]), ptr(P["pe_b"]), ptr(ws["F0"]), 64, ptr(D[cur]), 160, B, H, W, dt, st)
-        for blk in P["blocks"]:
+        for bi, blk in enumerate(P["blocks"]):
             for j, ds in enumerate(blk["dstl"]):
                 src, lds = D[cur], 160
                 t = ds["tail"]
@@ -167,15 +167,8 @@ class Executor:
             self._conv(D[cur], 160, blk["lff_w"], blk["lff_img"], blk["lff_b"], D[cur], 160, D[1 - cur], 160,
                        B, H, W, 160, 64, float(m.rdb_residual_scale), 0, dt, st)
             cur = 1 - cur
-        call("rdst_layernorm_fwd", ptr(D[cur]), 160, ptr(P["norm_g"]), ptr(P["norm_b"]), ptr(ws["FN"]), 64,
-             T, 60, float(m.global_res_scale), dt, st)
-        if m.feature_last_operation:
-            self._conv(ws["FN"], 64, P["cab_w"], P["cab_img"], P["cab_b"], ws["F0"], 64, ws["F1"], 64,
-                       B, H, W, 64, 64, 1.0, 0, dt, st)
-            feat = ws["F1"]
-        else:
-            feat = ws["F1"]
-            torch.add(ws["FN"], ws["F0"], out=feat)
+            self._block_done(bi, D[cur], T)
+        feat = self._deep_features(D[cur], P, ws, B, H, W, T, dt, st)
         h, w_ = H, W
         for (uw, ub), uimg, buf in zip(P["up"], P["up_img"], ws["UP"]):
             self._conv(feat, 64, uw, uimg, ub, None, 0, buf, 64, B, h, w_, 64, 256, 1.0, 2, dt, st)
@@ -188,6 +181,22 @@ class Executor:
             call("rdst_last_conv_fwd", ptr(feat), 64, ptr(P["last_w"]), P["last_b"], P["out_scale"], P["out_bias"],
                  ptr(out), B, h, w_, 64, dt, st)
         return out if x.dtype == torch.float32 else out.to(x.dtype)
+
+    def _block_done(self, index, trunk, T):
+        """Hook after RDSTB `index` (trunk = dense buffer whose first 64 columns hold the block output)."""
+
+    def _deep_features(self, trunk, P, ws, B, H, W, T, dt, st):
+        """norm * global_res_scale -> conv_after_body -> + head output  (rdst_variations.py:1337-1350); returns the map
+        that feeds the up-sampler."""
+        m = self._module()
+        call("rdst_layernorm_fwd", ptr(trunk), 160, ptr(P["norm_g"]), ptr(P["norm_b"]), ptr(ws["FN"]), 64,
+             T, 60, float(m.global_res_scale), dt, st)
+        if m.feature_last_operation:
+            self._conv(ws["FN"], 64, P["cab_w"], P["cab_img"], P["cab_b"], ws["F0"], 64, ws["F1"], 64,
+                       B, H, W, 64, 64, 1.0, 0, dt, st)
+        else:
+            torch.add(ws["FN"], ws["F0"], out=ws["F1"])
+        return ws["F1"]
 
     def _conv(self, x, ldx, w, wimg, b, r, ldr, y, ldy, B, H, W, cin, n, scale, shuffle, dt, st):
         if dt == _lib.BF16 and self.use_tc:
@@ -224,3 +233,52 @@ class Executor:
              T, cp, hp, c, 1, 1.0, dt, st)
         call("rdst_linear_fwd", ptr(hid), hp, ptr(w["w2"]), ptr(w["b2"]), ptr(x1), cp, ptr(dst), cp,
              T, hp, cp, 0, 0, 1.0, dt, st)
+
+
+class ExecutorN(Executor):
+    """RDSTSR_N (rdst_variations.py:824-1112) with the global bottleneck in 'mlp' mode: the outputs of all RDSTBs are
+    concatenated channel-wise and reduced by two Linears (:1071-1079); `norm` / `conv_after_body` are not on its path."""
+
+    def _weights(self, device):
+        fresh = self._packed is None
+        P = super()._weights(device)
+        if fresh or "bn_w1" not in P:
+            m = self._module()
+            n = len(m.body)
+            with torch.no_grad():
+                f = lambda t: t.detach().float()
+                pos = torch.cat([torch.arange(60, device=device) + 64 * i for i in range(n)])     # real channel -> cat column
+                w1 = torch.zeros(64, 64 * n, device=device)
+                w1[:60, pos] = f(m.bottleneck[0].weight)
+                b1 = torch.zeros(64, device=device)
+                b1[:60] = f(m.bottleneck[0].bias)
+                w2 = torch.zeros(64, 64, device=device)
+                w2[:60, :60] = f(m.bottleneck[1].weight)
+                b2 = torch.zeros(64, device=device)
+                b2[:60] = f(m.bottleneck[1].bias)
+                P["bn_w1"], P["bn_b1"], P["bn_w2"], P["bn_b2"] = w1.contiguous(), b1, w2.contiguous(), b2
+        return P
+
+    def forward(self, x):
+        m = self._module()
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in m.parameters())):
+            raise NotImplementedError("rdst_b200.RDSTSR_N: training (autograd) is not implemented in this round; "
+                                      "wrap inference in torch.no_grad()")
+        return super().forward(x)
+
+    def _block_done(self, index, trunk, T):
+        n = len(self._module().body)
+        cat = getattr(self, "_cat", None)
+        if cat is None or cat.shape != (T, 64 * n) or cat.dtype != trunk.dtype or cat.device != trunk.device:
+            cat = self._cat = torch.empty(T, 64 * n, dtype=trunk.dtype, device=trunk.device)
+        cat[:, 64 * index:64 * index + 64].copy_(trunk[:, :64])       # the reference's torch.cat of the RDSTB outputs
+
+    def _deep_features(self, trunk, P, ws, B, H, W, T, dt, st):
+        m = self._module()
+        n = len(m.body)
+        tmp = ws["FN"]
+        call("rdst_linear_fwd", ptr(self._cat), 64 * n, ptr(P["bn_w1"]), ptr(P["bn_b1"]), None, 0, ptr(tmp), 64,
+             T, 64 * n, 64, 0, 0, 1.0, dt, st)
+        call("rdst_linear_fwd", ptr(tmp), 64, ptr(P["bn_w2"]), ptr(P["bn_b2"]), ptr(ws["F0"]), 64, ptr(ws["F1"]), 64,
+             T, 64, 64, 0, 0, float(m.global_res_scale), dt, st)
+        return ws["F1"]

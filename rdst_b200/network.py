@@ -249,11 +249,82 @@ class RDSTSR(nn.Module):
         return None
 
 
+class RDSTSR_N(RDSTSR):
+    """Same constructor signature as the reference RDSTSR_N (rdst_variations.py:850-867).  Supported: the E1 envelope of
+    RDSTSR plus global_bottleneck=True, global_bottleneck_ratio=1, global_bottleneck_mode='mlp' (cat of all RDSTB outputs
+    -> Linear(60n, 60) -> Linear(60, 60), :995-1002, :1071-1079).  As in the reference, `norm` and `conv_after_body` are
+    registered (they are in the state_dict) but not used by the forward.  Inference only in this round."""
+
+    def __init__(self, img_size=48, patch_size=1, in_chans=1, sr_scale=2, embed_dim=60,
+                 dense_layer_depths=[2, 2, 2, 2], num_heads=[6, 6, 6, 6],
+                 window_size=[4, 4, 4, 4], rdb_depths=[3, 3, 3, 3],
+                 mlp_ratio=4., qkv_bias=True, qk_scale=None,
+                 drop_rate=0., attn_drop=0., drop_path_rate=0.,
+                 norm_layer=nn.LayerNorm, ape=False, patch_norm=True,
+                 use_checkpoint=False, resi_connection='1conv',
+                 growth_rate=30, dense_scale=1., dim_modify_mode='tail',
+                 rdb_residual_scale=1., global_res_scale=1.,
+                 mean=None, std=None,
+                 act_in_conv='leaky_relu', bn_in_conv=None,
+                 scale_free=False, scale_embedding=False,
+                 pre_norm=False,
+                 global_bottleneck=True, global_bottleneck_ratio=1., global_bottleneck_mode='mlp',
+                 precision=None):
+        super().__init__(img_size=img_size, patch_size=patch_size, in_chans=in_chans, sr_scale=sr_scale, embed_dim=embed_dim,
+                         dense_layer_depths=dense_layer_depths, num_heads=num_heads, window_size=window_size,
+                         rdb_depths=rdb_depths, mlp_ratio=mlp_ratio, qkv_bias=qkv_bias, qk_scale=qk_scale,
+                         drop_rate=drop_rate, attn_drop=attn_drop, drop_path_rate=drop_path_rate, norm_layer=norm_layer,
+                         ape=ape, patch_norm=patch_norm, use_checkpoint=use_checkpoint, resi_connection=resi_connection,
+                         growth_rate=growth_rate, dense_scale=dense_scale, dim_modify_mode=dim_modify_mode,
+                         rdb_residual_scale=rdb_residual_scale, global_res_scale=global_res_scale, mean=mean, std=std,
+                         act_in_conv=act_in_conv, bn_in_conv=bn_in_conv, scale_free=scale_free,
+                         scale_embedding=scale_embedding, pre_norm=pre_norm, feature_last_operation=False,
+                         precision=precision)
+        if not global_bottleneck: _unsupported("RDSTSR_N with global_bottleneck=False")
+        if float(global_bottleneck_ratio) != 1.0: _unsupported(f"global_bottleneck_ratio={global_bottleneck_ratio}")
+        if global_bottleneck_mode != 'mlp': _unsupported(f"global_bottleneck_mode={global_bottleneck_mode!r}")
+        self.global_bottleneck_mode, self.do_global_bottleneck = global_bottleneck_mode, True
+        del self.feature_last_operation                       # not an attribute of the reference RDSTSR_N
+        self.bottleneck = nn.Sequential(nn.Linear(embed_dim * self.num_blocks, embed_dim), nn.Linear(embed_dim, embed_dim))
+        self.bottleneck.apply(self._init_weights)
+        # registration order of the reference: ... body, norm, bottleneck, conv_after_body, tail
+        order = list(self._modules)
+        order.remove("bottleneck")
+        order.insert(order.index("norm") + 1, "bottleneck")
+        mods = dict(self._modules)
+        self._modules.clear()
+        for k in order:
+            self._modules[k] = mods[k]
+        self._exec = executor.ExecutorN(self)
+
+    def forward(self, x, sr_scale=None):
+        if not self._exec.bound_to(self):
+            self._exec = executor.ExecutorN(self)
+        return self._exec.forward(x)
+
+
 def make_RDSTSR(paras, mean=None, std=None):
     """Same contract as the reference factory (rdst_variations.py:1369-1457): reads the same `paras.*` names."""
-    if paras.rdst_global_bottleneck:
-        _unsupported("rdst_global_bottleneck=True (RDSTSR_N)")
     norm_layer = nn.LayerNorm if paras.rdst_layer_norm else nn.Identity
+    if paras.rdst_global_bottleneck:
+        return RDSTSR_N(
+            img_size=paras.patch_size, patch_size=paras.swin_patch_size, in_chans=paras.input_channel,
+            sr_scale=int(paras.sr_scale), embed_dim=paras.rdst_embed_dim,
+            dense_layer_depths=paras.rdst_dense_layer_depths, num_heads=paras.rdst_num_heads,
+            window_size=paras.rdst_window_size, rdb_depths=paras.rdst_rdb_depths,
+            mlp_ratio=paras.swin_hidden_ratio, qkv_bias=paras.swin_qkv_bias, qk_scale=paras.swin_qk_scale,
+            drop_rate=paras.swin_drop_rate, attn_drop=paras.swin_attn_drop_rate,
+            drop_path_rate=paras.swin_drop_path_rate,
+            norm_layer=norm_layer, ape=paras.rdst_ape, patch_norm=paras.rdst_patch_norm,
+            use_checkpoint=paras.rdst_use_checkpoint, resi_connection=paras.rdst_res_connection,
+            growth_rate=paras.rdst_growth_rate, dense_scale=paras.rdst_dense_scale,
+            dim_modify_mode=paras.rdst_dim_modify_mode,
+            rdb_residual_scale=paras.rdst_rdb_residual_scale, global_res_scale=paras.rdst_global_res_scale,
+            mean=mean, std=std, act_in_conv=paras.rdst_act_in_conv, bn_in_conv=paras.rdst_bn_in_conv,
+            scale_free=paras.scale_free, pre_norm=paras.rdst_pre_norm,
+            global_bottleneck=True, global_bottleneck_ratio=paras.rdst_global_bottleneck_ratio,
+            global_bottleneck_mode=paras.rdst_global_bottleneck_mode,
+            precision=getattr(paras, "rdst_b200_precision", None))
     _ = paras.rdst_global_bottleneck_ratio            # read for interface parity; unused on this branch
     return RDSTSR(
         img_size=paras.patch_size, patch_size=paras.swin_patch_size, in_chans=paras.input_channel,

@@ -88,3 +88,31 @@ def make_swinir(c, precision="fp32"):
     return swinir.SwinIR(img_size=c["img_size"], patch_size=1, in_chans=1, embed_dim=60, depths=c["depths"],
                          num_heads=[6] * len(c["depths"]), window_size=8, mlp_ratio=2., upscale=c["upscale"], img_range=1.,
                          upsampler="pixelshuffledirect", resi_connection="1conv", precision=precision)
+
+
+# ---- RDSTSR_N (global bottleneck): fixtures from oracle/gen_golden_rdstn.py ----
+RDSTN_CASES = ["rdstn_e1_x4_40x32", "rdstn_2blk_x2_16x24_b2"]
+
+
+def load_rdstn_case(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    blocks, scale = int(g["meta_blocks"]), int(g["meta_scale"])
+    sd = {}
+    for k, shape, dt in swinir_manifest(name):
+        sd[k] = torch.zeros(shape, dtype=dt)
+        if k.endswith("relative_position_index"):
+            sd[k] = O.rel_pos_index()
+        if k.endswith("attn_mask"):
+            sd[k] = O.shift_mask(24, 24)
+    sd["sub_mean.weight"][:] = 1
+    sd["add_mean.weight"][:] = 1
+    sd = fill_state_dict(sd, int(g["meta_wseed"]), True)
+    x = synth_input(tuple(int(v) for v in g["shape"]), int(g["meta_xseed"]))
+    return dict(g=g, sd=sd, x=x, blocks=blocks, scale=scale)
+
+
+def make_rdstn(c, precision="fp32"):
+    from rdst_b200 import network
+    b = c["blocks"]
+    return network.RDSTSR_N(img_size=24, sr_scale=c["scale"], dense_layer_depths=[2] * b, num_heads=[6] * b,
+                            window_size=[8] * b, rdb_depths=[3] * b, mlp_ratio=2., pre_norm=True, precision=precision)
