@@ -187,7 +187,8 @@ def test_gemm_tc_fused_gelu_and_lnhat_operands():
 
 
 @pytest.mark.parametrize("B,H,W,C,shift", [(2, 16, 24, 60, 0), (2, 16, 24, 60, 4), (1, 8, 8, 90, 4), (1, 40, 32, 120, 4),
-                                            (3, 24, 24, 120, 0), (3, 8, 8, 90, 0), (32, 24, 24, 120, 4)])
+                                            (3, 24, 24, 120, 0), (3, 8, 8, 90, 0), (32, 24, 24, 120, 4),
+                                            (70, 24, 24, 60, 4), (5, 40, 32, 90, 4)])     # > 148 tiles: persistent loop
 def test_window_attention_tc_fwd_bwd(B, H, W, C, shift):
     """tcgen05 window attention of the training path against the fp32 CUDA-core kernels (which tests/test_gpu_kernels.py
     and test_gpu_backward.py pin to the reference): forward output, log-sum-exp, and all three gradients + table gradient."""
@@ -256,7 +257,8 @@ def _oracle_grads(sd, x, target, scale):
     return loss.item(), dict(zip(names, grads)), out.detach()
 
 
-@pytest.mark.parametrize("blocks,shape,scale", [(1, (2, 1, 16, 24), 4), (2, (1, 1, 24, 24), 2)])
+@pytest.mark.parametrize("blocks,shape,scale", [(1, (2, 1, 16, 24), 4), (2, (1, 1, 24, 24), 2), (1, (3, 1, 40, 32), 4),
+                                                (1, (1, 1, 8, 8), 2)])
 def test_bf16_training_gradients_close_to_fp32_autograd(blocks, shape, scale):
     """precision='bf16' training: GEMM operands are rounded to bf16, so gradients agree with the exact fp32 autograd of
     the oracle to bf16 accuracy: per-tensor relative L2 error <= 3e-2 (<= 1e-1 for the tiny relative-position tables), output within the bf16 inference bar (1e-2)."""
