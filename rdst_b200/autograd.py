@@ -161,61 +161,112 @@ def block_params(blk):
     ps = []
     for dstl in blk.body:
         for b in dstl.body.blocks:
-            ps += [b.norm1.weight, b.norm1.bias, b.attn.qkv.weight, b.attn.qkv.bias, b.attn.relative_position_bias_table,
-                   b.attn.proj.weight, b.attn.proj.bias, b.norm2.weight, b.norm2.bias,
-                   b.mlp.fc1.weight, b.mlp.fc1.bias, b.mlp.fc2.weight, b.mlp.fc2.bias]
+            ps += stl_params(b)
         ps += [dstl.tail[0].weight, dstl.tail[0].bias, dstl.tail[1].weight, dstl.tail[1].bias]
     return ps
 
 
-def block_layout(m, blk):
-    """Static description of one RDSTB: where every packed tensor lives in the block's flat packed buffer and which
-    rdst_pack_linear call produces it.  Slot numbers index the list of packed tensors (`W` in the Functions)."""
-    lins, slots, off, nslot, pi = [], [], 0, 0, 0
+_STL_PARAMS = 13     # norm1.{w,b}, qkv.{w,b}, table, proj.{w,b}, norm2.{w,b}, fc1.{w,b}, fc2.{w,b}
 
-    def slot(shape):
-        nonlocal off, nslot
-        n = 1
-        for d in shape:
-            n *= d
-        slots.append((off, tuple(shape)))
-        off += (n + 3) // 4 * 4                       # keep every packed tensor 16-byte aligned
-        nslot += 1
-        return nslot - 1
 
-    def lin(w, b, g, be, N, K, rows_p, ldp, srows, scols, q_rows=0, q_scale=1.0):
-        sw, sb = slot((rows_p, ldp)), slot((rows_p,))
-        lins.append(dict(w=w, b=b, g=g, be=be, N=N, K=K, ldp=ldp, srows=srows, scols=scols, q_rows=q_rows,
-                         q_scale=float(q_scale), sw=sw, sb=sb))
+def stl_params(b):
+    return [b.norm1.weight, b.norm1.bias, b.attn.qkv.weight, b.attn.qkv.bias, b.attn.relative_position_bias_table,
+            b.attn.proj.weight, b.attn.proj.bias, b.norm2.weight, b.norm2.bias,
+            b.mlp.fc1.weight, b.mlp.fc1.bias, b.mlp.fc2.weight, b.mlp.fc2.bias]
+
+
+class _Layout:
+    """Where every packed tensor of one link lives in its flat packed buffer and which rdst_pack_linear descriptor produces
+    it.  Slot numbers index the list of packed tensors (`W` in the Functions); parameter numbers index the link's
+    parameter list."""
+
+    def __init__(self):
+        self.lins, self.slots, self.tables, self.off, self.pi = [], [], [], 0, 0
+
+    def slot(self, shape):
+        self.slots.append((self.off, tuple(shape)))
+        self.off += (_numel(shape) + 3) // 4 * 4              # keep every packed tensor 16-byte aligned
+        return len(self.slots) - 1
+
+    def lin(self, w, b, g, be, N, K, rows_p, ldp, srows, scols, q_rows=0, q_scale=1.0):
+        sw, sb = self.slot((rows_p, ldp)), self.slot((rows_p,))
+        self.lins.append(dict(w=w, b=b, g=g, be=be, N=N, K=K, ldp=ldp, srows=srows, scols=scols, q_rows=q_rows,
+                              q_scale=float(q_scale), sw=sw, sb=sb))
         return sw, sb
 
-    bs = {"dstl": [], "tables": []}
+    def take(self, n):
+        r = range(self.pi, self.pi + n)
+        self.pi += n
+        return r
+
+    def stl(self, b, c):
+        """One Swin block of width c (its 13 parameters are next in the link's parameter list)."""
+        cp = packing.padded_width(c)
+        hid = b.mlp.fc1.weight.shape[0]
+        hp = packing.hidden_width(hid)
+        n1g, n1b, qw, qb, tab, pw, pb, n2g, n2b, f1w, f1b, f2w, f2b = self.take(_STL_PARAMS)
+        st = {"c": c, "cp": cp, "hp": hp, "shift": b.shift_size}
+        st["wqkv"], st["bqkv"] = self.lin(qw, qb, n1g, n1b, 3 * c, c, 3 * c, cp, 0, 1, c, b.attn.scale)
+        st["wproj"], st["bproj"] = self.lin(pw, pb, None, None, c, c, cp, c, 1, 0)
+        st["w1"], st["b1"] = self.lin(f1w, f1b, n2g, n2b, hid, c, hp, cp, 0, 1)
+        st["w2"], st["b2"] = self.lin(f2w, f2b, None, None, c, hid, cp, hp, 1, 0)
+        st["table"] = -1 - len(self.tables)               # raw parameter, used as is: W[-1-i] is appended behind the slots
+        self.tables.append(tab)
+        return st
+
+    def finish(self, bs):
+        n = len(self.slots)
+        bs.update(lins=self.lins, slots=self.slots, tables=self.tables, packed_floats=self.off, n_params=self.pi,
+                  lff_w=n, lff_b=n + 1)                   # the link's conv filter / bias follow the slots in `W`
+        return bs
+
+
+def block_layout(m, blk):
+    """Static description of one RDSTB (3 DenseSTLayers: 2 Swin blocks + LN/Linear tail each)."""
+    L = _Layout()
+    bs = {"dstl": []}
     c = packing.EMBED
     for dstl in blk.body:
-        cp, hid = packing.padded_width(c), None
-        stls = []
-        for b in dstl.body.blocks:
-            hid = b.mlp.fc1.weight.shape[0]
-            hp = packing.hidden_width(hid)
-            n1g, n1b, qw, qb, tab, pw, pb, n2g, n2b, f1w, f1b, f2w, f2b = range(pi, pi + 13)
-            pi += 13
-            st = {"c": c, "cp": cp, "hp": hp, "shift": b.shift_size}
-            st["wqkv"], st["bqkv"] = lin(qw, qb, n1g, n1b, 3 * c, c, 3 * c, cp, 0, 1, c, b.attn.scale)
-            st["wproj"], st["bproj"] = lin(pw, pb, None, None, c, c, cp, c, 1, 0)
-            st["w1"], st["b1"] = lin(f1w, f1b, n2g, n2b, hid, c, hp, cp, 0, 1)
-            st["w2"], st["b2"] = lin(f2w, f2b, None, None, c, hid, cp, hp, 1, 0)
-            st["table"] = -1 - len(bs["tables"])          # raw parameter, used as is: W[-1-i] is appended behind the slots
-            bs["tables"].append(tab)
-            stls.append(st)
-        tg, tb_, tw, tbias = range(pi, pi + 4)
-        pi += 4
-        sw, sb = lin(tw, tbias, tg, tb_, packing.GROWTH, c, 32, cp, 0, 1)
+        stls = [L.stl(b, c) for b in dstl.body.blocks]
+        tg, tb_, tw, tbias = L.take(4)
+        sw, sb = L.lin(tw, tbias, tg, tb_, packing.GROWTH, c, 32, packing.padded_width(c), 0, 1)
         bs["dstl"].append({"c": c, "stl": stls, "tw": sw, "tb": sb, "scale": float(m.dense_scale)})
         c += packing.GROWTH
-    bs["lins"], bs["slots"], bs["packed_floats"], bs["n_params"] = lins, slots, off, pi
-    bs["lff_w"], bs["lff_b"] = nslot, nslot + 1
     bs["res_scale"] = float(m.rdb_residual_scale)
-    return bs
+    return L.finish(bs)
+
+
+def rstb_layout(layer):
+    """Static description of one RSTB of the vanilla SwinIR: depth Swin blocks at C = 60 (+ the 3x3 conv, packed by torch)."""
+    L = _Layout()
+    return L.finish({"stl": [L.stl(b, packing.EMBED) for b in layer.residual_group.blocks]})
+
+
+def rstb_params(layer):
+    return [p for b in layer.residual_group.blocks for p in stl_params(b)]
+
+
+def _views(buf, slots):
+    return [buf[o:o + _numel(s)].view(s) for o, s in slots]
+
+
+def _numel(shape):
+    n = 1
+    for d in shape:
+        n *= d
+    return n
+
+
+def pack_lff(blk, device):
+    with packing.differentiable():
+        pos = packing.channel_positions(packing.EMBED + 3 * packing.GROWTH, device)
+        return packing.pack_conv(blk.conv.weight, blk.conv.bias, pos, packing.DENSE_LD, 64)
+
+
+def pack_conv64(conv, device, n_pad=64):
+    """Differentiable packing of a 60 -> n conv on a [T][64] map: [n_pad][9][64], [n_pad]."""
+    with packing.differentiable():
+        return packing.pack_conv(conv.weight, conv.bias, torch.arange(60, device=device), 64, n_pad)
 
 
 def _pack_batch(lins, P, W, G, GP, backward):
@@ -234,23 +285,6 @@ def _pack_batch(lins, P, W, G, GP, backward):
         d.N, d.K, d.ldp, d.scatter_rows, d.scatter_cols = l["N"], l["K"], l["ldp"], l["srows"], l["scols"]
         d.q_rows, d.q_scale = l["q_rows"], l["q_scale"]
     _call("rdst_pack_linear_batch", arr, len(lins), 1 if backward else 0, _lib.stream_ptr())
-
-
-def _views(buf, slots):
-    return [buf[o:o + _numel(s)].view(s) for o, s in slots]
-
-
-def _numel(shape):
-    n = 1
-    for d in shape:
-        n *= d
-    return n
-
-
-def pack_lff(blk, device):
-    with packing.differentiable():
-        pos = packing.channel_positions(packing.EMBED + 3 * packing.GROWTH, device)
-        return packing.pack_conv(blk.conv.weight, blk.conv.bias, pos, packing.DENSE_LD, 64)
 
 
 def pack_head(m, device):
@@ -387,23 +421,9 @@ class BlockFunction(torch.autograd.Function):
                 src = D
                 sl = []
                 for st in ds["stl"]:
-                    cp, hp = st["cp"], st["hp"]
-                    # tensor-core mode keeps every row 16-byte aligned: q|k|v rows padded to a multiple of 8 floats
-                    qkv, o = e(T, _pad8(3 * c) if tc else 3 * c), e(T, cp if tc else c)
-                    x1, hid, y = e(T, cp), e(T, hp), e(T, cp)
-                    linear(src, W[st["wqkv"]], W[st["bqkv"]], qkv, cp, 3 * c, ln_creal=c)
-                    lse = None
-                    if tc:      # tcgen05 attention; keeps the row log-sum-exp for the backward kernel
-                        lse = e(T, packing.HEADS)
-                        _call("rdst_window_attention_tc_fwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(o), _ld(o), _p(lse),
-                              B, H, Wd, c, st["shift"], _lib.stream_ptr())
-                    else:
-                        _call("rdst_window_attention_fwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(o), _ld(o), B, H, Wd, c,
-                              packing.HEADS, st["shift"], F32, _lib.stream_ptr())
-                    linear(o, W[st["wproj"]], W[st["bproj"]], x1, c, cp, resid=src)
-                    linear(x1, W[st["w1"]], W[st["b1"]], hid, cp, hp, ln_creal=c)
-                    linear(hid, W[st["w2"]], W[st["b2"]], y, hp, cp, resid=x1, gelu_in=True)   # act = GELU(hid) not stored
-                    sl.append(dict(x=src, qkv=qkv, o=o, x1=x1, hid=hid, y=y, lse=lse))
+                    sv = _stl_forward(st, W, src, B, H, Wd, tc)
+                    sl.append(sv)
+                    y = sv["y"]
                     src = y
                 off = 64 + 32 * j
                 linear(src, W[ds["tw"]], W[ds["tb"]], D[:, off:], ds["stl"][0]["cp"], 32, ln_creal=c, scale=ds["scale"])
@@ -555,6 +575,30 @@ class TailFunction(torch.autograd.Function):
                   _p(gz(spec["norm_g"])), _p(gz(spec["norm_b"])), T, 60, sc["grs"], _lib.stream_ptr())
         ctx.saved = None
         return (None, None, None, dX, dF0) + tuple(G)
+
+
+def _stl_forward(st, W, src, B, H, Wd, tc):
+    """One Swin block forward on the training path: x1 = src + proj(attn(lnhat(src))), y = x1 + fc2(gelu(fc1(lnhat(x1)))).
+    Returns the tensors the backward needs (reference SwinTransformerBlock.forward, swin_transformer_sr.py:234-274)."""
+    T = src.shape[0]
+    c, cp, hp = st["c"], st["cp"], st["hp"]
+    e, _ = _f32(src.device)
+    # tensor-core mode keeps every row 16-byte aligned: q|k|v rows padded to a multiple of 8 floats
+    qkv, o = e(T, _pad8(3 * c) if tc else 3 * c), e(T, cp if tc else c)
+    x1, hid, y = e(T, cp), e(T, hp), e(T, cp)
+    linear(src, W[st["wqkv"]], W[st["bqkv"]], qkv, cp, 3 * c, ln_creal=c)
+    lse = None
+    if tc:      # tcgen05 attention; keeps the row log-sum-exp for the backward kernel
+        lse = e(T, packing.HEADS)
+        _call("rdst_window_attention_tc_fwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(o), _ld(o), _p(lse),
+              B, H, Wd, c, st["shift"], _lib.stream_ptr())
+    else:
+        _call("rdst_window_attention_fwd", _p(qkv), _ld(qkv), _p(W[st["table"]]), _p(o), _ld(o), B, H, Wd, c,
+              packing.HEADS, st["shift"], F32, _lib.stream_ptr())
+    linear(o, W[st["wproj"]], W[st["bproj"]], x1, c, cp, resid=src)
+    linear(x1, W[st["w1"]], W[st["b1"]], hid, cp, hp, ln_creal=c)
+    linear(hid, W[st["w2"]], W[st["b2"]], y, hp, cp, resid=x1, gelu_in=True)   # act = GELU(hid) not stored
+    return dict(x=src, qkv=qkv, o=o, x1=x1, hid=hid, y=y, lse=lse)
 
 
 def _stl_backward(st, sv, W, gz, dY, B, H, Wd, accumulate_into=None):
