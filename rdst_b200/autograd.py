@@ -335,7 +335,8 @@ def frozen_scalars(m):
                     out_bias=float(m.add_mean.bias.detach().reshape(-1)[0]))
         cache = (key, vals)
         object.__setattr__(m, "_rdst_scalar_cache", cache)
-    return dict(cache[1], grs=float(m.global_res_scale), flo=bool(m.feature_last_operation), sr=int(m.sr_scale))
+    return dict(cache[1], grs=float(m.global_res_scale), flo=bool(getattr(m, "feature_last_operation", False)),
+                sr=int(m.sr_scale))
 
 
 # ------------------------------------------------------------------------------------------------ the Functions
@@ -503,14 +504,17 @@ class TailFunction(torch.autograd.Function):
         e, z = _f32(dev)
         _MODE.tc = sc["tc"]
         with torch.cuda.device(dev):
-            FN = z(T, 64)
-            _call("rdst_layernorm_fwd", _p(X), 64, _p(W[spec["norm_g"]]), _p(W[spec["norm_b"]]), _p(FN), 64, T, 60,
-                  sc["grs"], F32, _lib.stream_ptr())
-            F1 = e(T, 64)
-            if sc["flo"]:
-                conv(FN, W[spec["cab_w"]], W[spec["cab_b"]], F1, B, H, Wd, 64, 64, resid=F0)
+            if sc.get("tail_only"):                          # RDSTSR_N: X already is the map that feeds the up-sampler
+                FN, F1 = None, X.contiguous()
             else:
-                torch.add(FN, F0, out=F1)
+                FN = z(T, 64)
+                _call("rdst_layernorm_fwd", _p(X), 64, _p(W[spec["norm_g"]]), _p(W[spec["norm_b"]]), _p(FN), 64, T, 60,
+                      sc["grs"], F32, _lib.stream_ptr())
+                F1 = e(T, 64)
+                if sc["flo"]:
+                    conv(FN, W[spec["cab_w"]], W[spec["cab_b"]], F1, B, H, Wd, 64, 64, resid=F0)
+                else:
+                    torch.add(FN, F0, out=F1)
             feats = [F1]
             h, w_ = H, Wd
             for wi, bi in spec["up"]:
@@ -563,6 +567,9 @@ class TailFunction(torch.autograd.Function):
                 dfeat = e(tz, 64)
                 conv(dz, conv_dgrad_weight(W[wi]), z(64), dfeat, B, h, w_, 256, 64)
             dF1 = dfeat                                   # grad wrt F1 = cab(FN) + F0
+            if sc.get("tail_only"):
+                ctx.saved = None
+                return (None, None, None, dF1, None) + tuple(G)
             dF0 = dF1.clone()
             dFN = e(T, 64)
             if sc["flo"]:
@@ -638,6 +645,198 @@ def _stl_backward(st, sv, W, gz, dY, B, H, Wd, accumulate_into=None):
     return None
 
 
+# ------------------------------------------------------------------------------------------------ widened variants
+def _link_packed(bs, P, conv_w, conv_b):
+    """Packed tensors of a link: slots | conv filter, bias (packed by torch ops under autograd) | tables reversed."""
+    dev = P[0].device
+    W = _views(torch.zeros(bs["packed_floats"], dtype=torch.float32, device=dev), bs["slots"])
+    _pack_batch(bs["lins"], P, W, None, None, backward=False)
+    return W + [conv_w, conv_b] + [P[i] for i in reversed(bs["tables"])]
+
+
+def _link_grad_buffers(bs, W, P):
+    dev = P[0].device
+    return _views(torch.zeros(bs["packed_floats"], dtype=torch.float32, device=dev), bs["slots"]) + \
+        [torch.zeros_like(W[bs["lff_w"]]), torch.zeros_like(W[bs["lff_b"]])] + [torch.zeros_like(P[i]) for i in reversed(bs["tables"])]
+
+
+def _link_param_grads(bs, P, G):
+    """Packed-weight gradients -> gradients of the reference-named parameters (one rdst_pack_linear_batch launch)."""
+    dev = P[0].device
+    GP = [None] * len(P)
+    ln_idx = [i for l in bs["lins"] if l["g"] is not None for i in (l["g"], l["be"])]
+    lnbuf = torch.zeros(sum(P[i].numel() for i in ln_idx), dtype=torch.float32, device=dev)
+    off = 0
+    for i in ln_idx:
+        GP[i] = lnbuf[off:off + P[i].numel()].view_as(P[i])
+        off += P[i].numel()
+    for l in bs["lins"]:
+        GP[l["w"]], GP[l["b"]] = torch.empty_like(P[l["w"]]), torch.empty_like(P[l["b"]])
+    _pack_batch(bs["lins"], P, None, G, GP, backward=True)
+    for i, pi in enumerate(bs["tables"]):
+        GP[pi] = G[-1 - i]
+    return GP
+
+
+class RSTBFunction(torch.autograd.Function):
+    """One RSTB of the vanilla SwinIR (swin_transformer_sr.py:471-472): depth Swin blocks at C = 60 -> 3x3 conv -> + input."""
+
+    @staticmethod
+    def forward(ctx, bs, geom, X, conv_w, conv_b, *P):
+        B, H, Wd = geom
+        T = B * H * Wd
+        e, z = _f32(X.device)
+        _MODE.tc = tc = bs["tc"]
+        with torch.cuda.device(X.device):
+            W = _link_packed(bs, P, conv_w, conv_b)
+            src, saved = X.contiguous(), []
+            for st in bs["stl"]:
+                sv = _stl_forward(st, W, src, B, H, Wd, tc)
+                saved.append(sv)
+                src = sv["y"]
+            Xn = e(T, 64)
+            conv(src, W[bs["lff_w"]], W[bs["lff_b"]], Xn, B, H, Wd, 64, 64, resid=saved[0]["x"])
+        ctx.bs, ctx.geom, ctx.W, ctx.P, ctx.saved = bs, geom, W, P, saved
+        return Xn
+
+    @staticmethod
+    def backward(ctx, dXn):
+        bs, W, P, saved = ctx.bs, ctx.W, ctx.P, ctx.saved
+        B, H, Wd = ctx.geom
+        T = B * H * Wd
+        e, z = _f32(dXn.device)
+        _MODE.tc = bs["tc"]
+        with torch.cuda.device(dXn.device):
+            G = _link_grad_buffers(bs, W, P)
+            gz = lambda i: G[i]
+            dX = dXn.contiguous()
+            gemm_tn(dX, saved[-1]["y"], gz(bs["lff_w"]), gz(bs["lff_b"]), 64, 9 * 64, (B, H, Wd, 64))
+            dY = e(T, 64)
+            conv(dX, conv_dgrad_weight(W[bs["lff_w"]]), z(64), dY, B, H, Wd, 64, 64)
+            for k in range(len(bs["stl"]) - 1, -1, -1):
+                dY = _stl_backward(bs["stl"][k], saved[k], W, gz, dY, B, H, Wd)
+            axpy(dX, dY, 64)                                     # the RSTB residual
+            GP = _link_param_grads(bs, P, G)
+        ctx.saved = None
+        return (None, None, dY, G[bs["lff_w"]], G[bs["lff_b"]]) + tuple(GP)
+
+
+class SwinIRTailFunction(torch.autograd.Function):
+    """norm -> conv_after_body + conv_first skip -> UpsampleOneStep conv (60 -> s^2) (swin_transformer_sr.py:781-799).
+    Returns the [T][16] map of sub-pixel channels; PixelShuffle / img_range / mean are views and scalars outside."""
+
+    @staticmethod
+    def forward(ctx, tc, geom, X, F0, norm_g, norm_b, cab_w, cab_b, up_w, up_b):
+        B, H, Wd = geom
+        T = B * H * Wd
+        e, z = _f32(X.device)
+        _MODE.tc = tc
+        with torch.cuda.device(X.device):
+            X = X.contiguous()
+            FN = z(T, 64)
+            _call("rdst_layernorm_fwd", _p(X), 64, _p(norm_g), _p(norm_b), _p(FN), 64, T, 60, 1.0, F32, _lib.stream_ptr())
+            F1 = e(T, 64)
+            conv(FN, cab_w, cab_b, F1, B, H, Wd, 64, 64, resid=F0)
+            up = e(T, 16)
+            conv(F1, up_w, up_b, up, B, H, Wd, 64, 16)
+        ctx.tc, ctx.geom, ctx.saved = tc, geom, (X, FN, F1, norm_g, cab_w, up_w)
+        return up
+
+    @staticmethod
+    def backward(ctx, dup):
+        B, H, Wd = ctx.geom
+        T = B * H * Wd
+        X, FN, F1, norm_g, cab_w, up_w = ctx.saved
+        e, z = _f32(dup.device)
+        _MODE.tc = ctx.tc
+        with torch.cuda.device(dup.device):
+            dup = dup.contiguous()
+            g_upw, g_upb = z(16, 9, 64), z(16)
+            gemm_tn(dup, F1, g_upw, g_upb, 16, 9 * 64, (B, H, Wd, 64))
+            dF1 = e(T, 64)
+            conv(dup, conv_dgrad_weight(up_w), z(64), dF1, B, H, Wd, 16, 64)
+            g_cabw, g_cabb = z(64, 9, 64), z(64)
+            gemm_tn(dF1, FN, g_cabw, g_cabb, 64, 9 * 64, (B, H, Wd, 64))
+            dFN = e(T, 64)
+            conv(dF1, conv_dgrad_weight(cab_w), z(64), dFN, B, H, Wd, 64, 64)
+            dX, gg, gb = z(T, 64), z(60), z(60)
+            _call("rdst_layernorm_bwd", _p(dFN), 64, _p(X), 64, _p(norm_g), _p(dX), 64, _p(gg), _p(gb), T, 60, 1.0,
+                  _lib.stream_ptr())
+        ctx.saved = None
+        return None, None, dX, dF1, gg, gb, g_cabw, g_cabb, g_upw, g_upb
+
+
+def forward_with_grad_swinir(executor, x):
+    """Training forward of rdst_b200.SwinIR: head -> RSTB chain -> tail, same machinery as forward_with_grad."""
+    m = executor._module()
+    tc = m.precision == "bf16"
+    if tc and not _lib.load().rdst_has_tcgen05():
+        raise RuntimeError("rdst_b200: precision='bf16' training needs the tcgen05 kernels (sm_100a device)")
+    if x.requires_grad:
+        raise NotImplementedError("rdst_b200: gradients with respect to the input image are not implemented")
+    dev = x.device
+    B, _, H, Wd = x.shape
+    geom = (B, H, Wd)
+    rng, mean, s = float(m.img_range), float(m.mean.reshape(-1)[0]), m.upscale
+    sc = dict(in_scale=rng, in_bias=-mean * rng, tc=tc)
+    with packing.differentiable():
+        f = packing._f
+        hw = torch.zeros(64, 9, 16, device=dev)
+        hw[:60, :, 0] = f(m.conv_first.weight).reshape(60, 9)
+        hb = torch.zeros(64, device=dev)
+        hb[:60] = f(m.conv_first.bias)
+        head = [hw, hb, f(m.patch_embed.norm.weight).contiguous(), f(m.patch_embed.norm.bias).contiguous()]
+    F0, X = HeadFunction.apply(dict(head_w=0, head_b=1, pe_g=2, pe_b=3), sc, x.detach().to(torch.float32).contiguous(), *head)
+    for layer in m.layers:
+        bs = dict(rstb_layout(layer), tc=tc)
+        cw, cb = pack_conv64(layer.conv, dev)
+        X = RSTBFunction.apply(bs, geom, X, cw, cb, *rstb_params(layer))
+    cabw, cabb = pack_conv64(m.conv_after_body, dev)
+    upw, upb = pack_conv64(m.upsample[0], dev, 16)
+    with packing.differentiable():
+        ng, nb = packing._f(m.norm.weight).contiguous(), packing._f(m.norm.bias).contiguous()
+    up = SwinIRTailFunction.apply(tc, geom, X, F0, ng, nb, cabw, cabb, upw, upb)
+    out = up[:, :s * s].reshape(B, H, Wd, s, s).permute(0, 1, 3, 2, 4).reshape(B, 1, H * s, Wd * s)
+    return out / rng + mean
+
+
+class BottleneckFunction(torch.autograd.Function):
+    """Global bottleneck 'mlp' of RDSTSR_N (rdst_variations.py:1071-1079, 1092-1093) on the [T][64n] concatenation of the RDSTB
+    outputs:  F1 = grs * Linear2(Linear1(cat)) + F0."""
+
+    @staticmethod
+    def forward(ctx, tc, grs, cat, F0, w1, b1, w2, b2):
+        T, K = cat.shape
+        e, _ = _f32(cat.device)
+        _MODE.tc = tc
+        with torch.cuda.device(cat.device):
+            cat = cat.contiguous()
+            tmp, F1 = e(T, 64), e(T, 64)
+            linear(cat, w1, b1, tmp, K, 64)
+            linear(tmp, w2, b2, F1, 64, 64, scale=grs, resid=F0)
+        ctx.tc, ctx.grs, ctx.saved = tc, grs, (cat, tmp, w1, w2)
+        return F1
+
+    @staticmethod
+    def backward(ctx, dF1):
+        cat, tmp, w1, w2 = ctx.saved
+        T, K = cat.shape
+        e, z = _f32(dF1.device)
+        _MODE.tc = ctx.tc
+        with torch.cuda.device(dF1.device):
+            dF1 = dF1.contiguous()
+            dy = dF1 if ctx.grs == 1.0 else dF1 * ctx.grs
+            gw2, gb2, gw1, gb1 = z(64, 64), z(64), z(64, K), z(64)
+            gemm_tn(dy, tmp, gw2, gb2, 64, 64)
+            dtmp = e(T, 64)
+            linear_t(dy, w2, dtmp, 64, 64)
+            gemm_tn(dtmp, cat, gw1, gb1, 64, K)
+            dcat = e(T, K)
+            linear_t(dtmp, w1, dcat, 64, K)
+        ctx.saved = None
+        return None, None, dcat, dF1, gw1, gb1, gw2, gb2
+
+
 def forward_with_grad(executor, x):
     m = executor._module()
     tc = m.precision == "bf16"
@@ -651,9 +850,26 @@ def forward_with_grad(executor, x):
     sc = dict(frozen_scalars(m), tc=tc)
     flat, spec = pack_head(m, dev)
     F0, X = HeadFunction.apply(spec, sc, x.detach().to(torch.float32).contiguous(), *flat)
+    feats = []
     for blk in m.body:
         bs = dict(block_layout(m, blk), tc=tc)
         lff_w, lff_b = pack_lff(blk, dev)
         X = BlockFunction.apply(bs, geom, X, lff_w, lff_b, *block_params(blk))
+        feats.append(X)
     flat, spec = pack_tail(m, dev)
+    if getattr(m, "do_global_bottleneck", False):            # RDSTSR_N: cat -> two Linears; norm / conv_after_body unused
+        n = len(feats)
+        with packing.differentiable():
+            f = packing._f
+            pos = torch.cat([torch.arange(60, device=dev) + 64 * i for i in range(n)])
+            w1 = torch.zeros(64, 64 * n, device=dev)
+            w1[:60, pos] = f(m.bottleneck[0].weight)
+            b1 = torch.zeros(64, device=dev)
+            b1[:60] = f(m.bottleneck[0].bias)
+            w2 = torch.zeros(64, 64, device=dev)
+            w2[:60, :60] = f(m.bottleneck[1].weight)
+            b2 = torch.zeros(64, device=dev)
+            b2[:60] = f(m.bottleneck[1].bias)
+        F1 = BottleneckFunction.apply(tc, float(m.global_res_scale), torch.cat(feats, 1), F0, w1, b1, w2, b2)
+        return TailFunction.apply(spec, dict(sc, tail_only=True), geom, F1, F0, *flat)
     return TailFunction.apply(spec, sc, geom, X, F0, *flat)

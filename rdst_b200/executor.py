@@ -259,13 +259,6 @@ class ExecutorN(Executor):
                 P["bn_w1"], P["bn_b1"], P["bn_w2"], P["bn_b2"] = w1.contiguous(), b1, w2.contiguous(), b2
         return P
 
-    def forward(self, x):
-        m = self._module()
-        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in m.parameters())):
-            raise NotImplementedError("rdst_b200.RDSTSR_N: training (autograd) is not implemented in this round; "
-                                      "wrap inference in torch.no_grad()")
-        return super().forward(x)
-
     def _block_done(self, index, trunk, T):
         n = len(self._module().body)
         cat = getattr(self, "_cat", None)

@@ -253,7 +253,7 @@ class RDSTSR_N(RDSTSR):
     """Same constructor signature as the reference RDSTSR_N (rdst_variations.py:850-867).  Supported: the E1 envelope of
     RDSTSR plus global_bottleneck=True, global_bottleneck_ratio=1, global_bottleneck_mode='mlp' (cat of all RDSTB outputs
     -> Linear(60n, 60) -> Linear(60, 60), :995-1002, :1071-1079).  As in the reference, `norm` and `conv_after_body` are
-    registered (they are in the state_dict) but not used by the forward.  Inference only in this round."""
+    registered (they are in the state_dict) but not used by the forward, so they receive no gradient."""
 
     def __init__(self, img_size=48, patch_size=1, in_chans=1, sr_scale=2, embed_dim=60,
                  dense_layer_depths=[2, 2, 2, 2], num_heads=[6, 6, 6, 6],

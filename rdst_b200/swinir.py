@@ -12,7 +12,7 @@ sequence over the same librdst_b200 kernels:
 Same constructor arguments, `forward(x)` and `state_dict` keys as the reference (manifest:
 tests/golden/swinir_state_dict_manifest.txt).  Supported envelope: embed_dim 60, 6 heads, window 8, mlp_ratio 2,
 in_chans 1, patch_size 1, LayerNorm, no ape, '1conv', upsampler 'pixelshuffledirect', upscale 2/3/4; anything else
-raises NotImplementedError.  Inference only in this round (autograd raises).
+raises NotImplementedError.  Training runs through rdst_b200/autograd.py (RSTBFunction chain), fp32 or bf16 GEMMs.
 """
 import os
 
@@ -171,8 +171,8 @@ class SwinIRExecutor(executor.Executor):
             raise RuntimeError(f"rdst_b200: H={H}, W={W} must be multiples of the window size 8 "
                                "(the reference fails in window_partition's view for such inputs)")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in m.parameters())):
-            raise NotImplementedError("rdst_b200.SwinIR: training (autograd) is not implemented in this round; "
-                                      "wrap inference in torch.no_grad()")
+            from . import autograd
+            return autograd.forward_with_grad_swinir(self, x)
         with torch.no_grad(), torch.cuda.device(x.device):
             return self._forward_swinir(x)
 

@@ -69,5 +69,20 @@ def test_gpu_matches_reference_golden(name, precision, tol):
     if precision == "bf16":
         target = torch.rand(ref.shape, generator=torch.Generator().manual_seed(123))
         assert abs(O.psnr(y, target) - O.psnr(ref, target)) < 0.01
-    with pytest.raises(NotImplementedError, match="training"):
-        m.train()(c["x"].cuda())
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_gpu_training_gradients_match_oracle_autograd(precision):
+    """Gradients through the bottleneck branch; `norm` / `conv_after_body` are unused by this forward and get none."""
+    from test_swinir import _grad_check
+    c = helpers.load_rdstn_case("rdstn_2blk_x2_16x24_b2")
+    x, s = c["x"], c["scale"]
+    target = torch.rand(x.shape[0], 1, x.shape[2] * s, x.shape[3] * s, generator=torch.Generator().manual_seed(5))
+    p = {k: (v.clone().double().requires_grad_(True) if v.is_floating_point() else v) for k, v in c["sd"].items()}
+    names = [k for k, v in p.items() if v.is_floating_point() and "mean." not in k and "attn_mask" not in k]
+    loss_ref = (O.forward(p, x.double(), s) - target.double()).abs().mean()
+    g_ref = dict(zip(names, torch.autograd.grad(loss_ref, [p[k] for k in names], allow_unused=True)))
+    assert g_ref["norm.weight"] is None and g_ref["conv_after_body.weight"] is None
+    m = helpers.make_rdstn(c, precision).cuda().train()
+    _grad_check(m, c["sd"], x, target, loss_ref.item(), g_ref, precision == "fp32")

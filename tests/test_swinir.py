@@ -85,5 +85,39 @@ def test_gpu_volume_batch_and_training_rejected():
     ref = SO.forward(c["sd"], x[:2].cpu(), 4)
     # 1e-2 is the bar on [0,1]-normalised images; with the perturbed synthetic weights the output spans about +-1.2
     assert (y[:2].cpu() - ref).abs().max().item() < 1e-2 * max(1.0, ref.abs().max().item())
-    with pytest.raises(NotImplementedError, match="training"):
-        m.train()(x[:1])
+
+
+def _grad_check(m, sd, x, target, loss_ref, g_ref, tight):
+    m.load_state_dict(sd, strict=True)
+    loss = torch.nn.functional.l1_loss(m(x.cuda()), target.cuda())
+    loss.backward()
+    assert abs(loss.item() - loss_ref) < (1e-5 if tight else 2e-3)
+    params = dict(m.named_parameters())
+    worst = ("", 0.0)
+    for k, gr in g_ref.items():
+        if gr is None:
+            assert params[k].grad is None or float(params[k].grad.abs().max()) == 0.0, k
+            continue
+        assert params[k].grad is not None, k
+        rel = ((params[k].grad.detach().cpu().double() - gr).norm() / (gr.norm() + 1e-12)).item()
+        tol = 1e-3 if tight else (1e-1 if "relative_position_bias_table" in k else 3e-2)
+        assert rel < tol, (k, rel)
+        worst = max(worst, (k, rel), key=lambda kv: kv[1])
+    print("worst relative L2 gradient error:", worst)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["swinir_x2_16x24_b2", "swinir_x3_8x8"])
+def test_gpu_training_gradients_match_oracle_autograd(name, precision):
+    """loss.backward() through the RSTB Function chain against torch.autograd through the fp64 oracle (L1 loss)."""
+    c = helpers.load_swinir_case(name)
+    s = c["upscale"]
+    x = c["x"]
+    target = torch.rand(x.shape[0], 1, x.shape[2] * s, x.shape[3] * s, generator=torch.Generator().manual_seed(5))
+    p = {k: (v.clone().double().requires_grad_(True) if v.is_floating_point() else v) for k, v in c["sd"].items()}
+    names = [k for k, v in p.items() if v.is_floating_point() and "attn_mask" not in k]
+    loss_ref = (SO.forward(p, x.double(), s) - target.double()).abs().mean()
+    g_ref = dict(zip(names, torch.autograd.grad(loss_ref, [p[k] for k in names], allow_unused=True)))
+    m = helpers.make_swinir(c, precision).cuda().train()
+    _grad_check(m, c["sd"], x, target, loss_ref.item(), g_ref, precision == "fp32")
