@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--ddp", default="auto", choices=["auto", "torch", "bucket"])
     ap.add_argument("--precision", default="fp32", choices=["fp32", "bf16"])
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--model", default="rdst", choices=["rdst", "rdstn", "swinir"])
     ap.add_argument("--check", action="store_true")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -46,7 +47,14 @@ def main():
     from rdst_b200 import ddp as rddp, train as rtrain
 
     torch.manual_seed(0)
-    m = helpers.make_module(a.blocks, 4, a.precision).cuda().train()
+    def build():
+        if a.model == "swinir":      # the ini's [SwinIR] section: 4 RSTBs x 6 blocks, constructor resolution 8 (no shifted blocks)
+            return helpers.make_swinir(dict(img_size=8, depths=[6] * 4, upscale=4), a.precision)
+        if a.model == "rdstn":
+            return helpers.make_rdstn(dict(blocks=a.blocks, scale=4), a.precision)
+        return helpers.make_module(a.blocks, 4, a.precision)
+
+    m = build().cuda().train()
     m0 = copy.deepcopy(m.state_dict())
     g = torch.Generator(device="cuda").manual_seed(100 + rank)
     x = torch.rand(a.batch, 1, 24, 24, device="cuda", generator=g)
@@ -109,13 +117,14 @@ def main():
         dist.all_reduce(lo, op=dist.ReduceOp.MIN)
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
         same = bool(lo == hi)
-    line = {"what": "RDST-E1 x4 training step (L1, Adam)", "world": world, "blocks": a.blocks, "mode": a.mode,
+    line = {"what": {"rdst": "RDST-E1", "rdstn": "RDSTSR_N", "swinir": "SwinIR-lite"}[a.model] + " x4 training step (L1, Adam)",
+            "world": world, "blocks": a.blocks, "mode": a.mode,
             "ddp": ddp if world > 1 else None, "precision": a.precision, "batch_per_gpu": a.batch,
             "ms_per_step": round(ms, 3), "hr_mpix_per_s": round(world * a.batch * 96 * 96 / ms / 1e3, 3),
             "loss_first": round(losses[0], 5), "loss_last": round(losses[-1], 5), "replicas_identical": same,
             "bucket_launch_order": order}
     if a.check:
-        m2 = helpers.make_module(a.blocks, 4, a.precision).cuda().train()
+        m2 = build().cuda().train()
         m2.load_state_dict(m0)
         _, losses2, _ = run(m2, "eager", a.steps + 2, False)
         diff = max((p.detach() - q.detach()).abs().max().item() for p, q in zip(m.parameters(), m2.parameters()))
