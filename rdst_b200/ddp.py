@@ -20,19 +20,22 @@ import torch.distributed as dist
 
 
 def rdst_link_of(name):
-    """Bucket key of a parameter name of RDSTSR: 'head' | 'body.<i>' | 'tail' (state_dict layout)."""
+    """Bucket key of a parameter name of RDSTSR / RDSTSR_N ('head' | 'body.<i>' | 'tail'; state_dict layout) or
+    of SwinIR ('head' | 'layers.<i>' | 'tail'): one bucket per link of the autograd chain."""
     parts = name.split(".")
-    if parts[0] == "body":
-        return "body." + parts[1]
-    if parts[0] in ("head", "patch_embed"):
+    if parts[0] in ("body", "layers"):
+        return parts[0] + "." + parts[1]
+    if parts[0] in ("head", "conv_first", "patch_embed"):
         return "head"
     return "tail"
 
 
 class BucketedAllReduce:
-    def __init__(self, model, process_group=None, bucket_of=rdst_link_of, average=True):
+    def __init__(self, model, process_group=None, bucket_of=rdst_link_of, average=True, allow_unused=False):
         self.group = process_group
         self.average = average
+        self.allow_unused = allow_unused    # parameters the forward never uses (RDSTSR_N's norm / conv_after_body): their
+                                            # bucket is reduced at finish() with zeros in the unused slots
         self.world = dist.get_world_size(process_group) if dist.is_available() and dist.is_initialized() else 1
         groups = {}
         for name, p in model.named_parameters():
@@ -86,10 +89,12 @@ class BucketedAllReduce:
 
     def finish(self):
         """Call after backward(): the current stream waits for every bucket's all-reduce."""
-        missing = [b["key"] for b in self.buckets if not b["fired"]]
-        if missing:
-            raise RuntimeError(f"rdst_b200.ddp: buckets {missing} received no gradient in this backward pass "
-                               "(unused parameters are not supported)")
+        missing = [b for b in self.buckets if not b["fired"]]
+        if missing and not self.allow_unused:
+            raise RuntimeError(f"rdst_b200.ddp: buckets {[b['key'] for b in missing]} received no gradient in this backward "
+                               "pass (pass allow_unused=True if the model has parameters its forward never uses)")
+        for b in missing:                   # same set on every rank: the collective stays matched
+            self._launch(b)
         for w in self._works:
             w.wait()
         self._works = []

@@ -97,8 +97,16 @@ def _worker(rank, world, port, ret):
         raised = "received no gradient" in str(e)
     for w in red._works:
         w.wait()
+    red.remove()
+    # allow_unused: the bucket of the unused link is reduced at finish() (zeros), the used ones as usual
+    red2 = ddp.BucketedAllReduce(net, allow_unused=True)
+    red2.begin_step()
+    net.body[0](x).sum().backward()
+    red2.finish()
+    unused_ok = red2.launch_order[0] == "body.0" and set(red2.launch_order) == {"body.0", "body.1", "body.2", "head", "tail"} \
+        and float(net.tail.weight.grad.abs().max()) == 0.0
     if rank == 0:
-        ret.update(ok=bool(ok), err=err, raised=raised, frozen_grad=net.frozen.grad is None,
+        ret.update(ok=bool(ok), err=err, raised=raised, frozen_grad=net.frozen.grad is None, unused_ok=bool(unused_ok),
                    keys=[b["key"] for b in red.buckets])
     dist.barrier()
     dist.destroy_process_group()
@@ -111,7 +119,7 @@ def test_bucketed_allreduce_two_ranks():
     mp.spawn(_worker, args=(2, port, ret), nprocs=2, join=True)
     assert ret["ok"], "launch order / gradient views"
     assert ret["err"] < 1e-6, ret["err"]
-    assert ret["raised"] and ret["frozen_grad"]
+    assert ret["raised"] and ret["frozen_grad"] and ret["unused_ok"]
     assert sorted(ret["keys"]) == ["body.0", "body.1", "body.2", "head", "tail"]
 
 
@@ -120,5 +128,7 @@ def test_rdst_link_of_maps_state_dict_names():
     assert ddp.rdst_link_of("body.3.body.1.body.blocks.0.attn.qkv.weight") == "body.3"
     assert ddp.rdst_link_of("body.0.conv.bias") == "body.0"
     assert ddp.rdst_link_of("head.weight") == "head" and ddp.rdst_link_of("patch_embed.norm.bias") == "head"
-    for n in ("norm.weight", "conv_after_body.bias", "tail.0.0.weight", "tail.1.bias"):
+    for n in ("norm.weight", "conv_after_body.bias", "tail.0.0.weight", "tail.1.bias", "bottleneck.0.weight", "upsample.0.bias"):
         assert ddp.rdst_link_of(n) == "tail"
+    assert ddp.rdst_link_of("layers.2.residual_group.blocks.5.mlp.fc1.weight") == "layers.2"      # SwinIR
+    assert ddp.rdst_link_of("layers.0.conv.weight") == "layers.0" and ddp.rdst_link_of("conv_first.bias") == "head"
