@@ -117,7 +117,10 @@ class Executor:
         return ws
 
     # ------------------------------------------------------------------ forward
-    def forward(self, x):
+    def forward(self, x, out=None):
+        """out: optional fp32 (B,1,sH,sW) tensor the reconstruction kernel writes into -- a device tensor, or PINNED HOST
+        memory (mapped into the device address space): the HR image then crosses PCIe as it is produced instead of in a
+        separate device->host copy.  Inference only."""
         m = self._module()
         if not x.is_cuda:
             raise RuntimeError("rdst_b200: input must be a CUDA tensor; this package has no CPU path")
@@ -128,12 +131,21 @@ class Executor:
             raise RuntimeError(f"rdst_b200: H={H}, W={W} must be multiples of the window size 8 "
                                "(the reference fails in window_partition's view for such inputs)")
         if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in m.parameters())):
+            if out is not None:
+                raise ValueError("rdst_b200: out= is an inference option (call under torch.no_grad())")
             from . import autograd
             return autograd.forward_with_grad(self, x)
+        if out is not None:
+            s = m.sr_scale
+            ok = (out.dtype == torch.float32 and out.is_contiguous() and tuple(out.shape) == (B, 1, H * s, W * s) and
+                  (out.is_cuda and out.device == x.device or (not out.is_cuda and out.is_pinned())))
+            if not ok:
+                raise ValueError("rdst_b200: out= must be a contiguous fp32 (B,1,sH,sW) tensor on the input's device or in "
+                                 "pinned host memory")
         with torch.no_grad(), torch.cuda.device(x.device):
-            return self._forward_impl(x)
+            return self._forward_impl(x, out)
 
-    def _forward_impl(self, x):
+    def _forward_impl(self, x, out=None):
         m = self._module()
         dev = x.device
         adt = torch.float32 if m.precision == "fp32" else torch.bfloat16
@@ -173,14 +185,16 @@ class Executor:
         for (uw, ub), uimg, buf in zip(P["up"], P["up_img"], ws["UP"]):
             self._conv(feat, 64, uw, uimg, ub, None, 0, buf, 64, B, h, w_, 64, 256, 1.0, 2, dt, st)
             feat, h, w_ = buf, 2 * h, 2 * w_
-        out = torch.empty(B, 1, h, w_, dtype=torch.float32, device=dev)
+        given = out is not None
+        if not given:
+            out = torch.empty(B, 1, h, w_, dtype=torch.float32, device=dev)
         if dt == _lib.BF16 and self.use_tc:
             call("rdst_last_conv_fwd_bf16_tc", ptr(feat), 64, ptr(P["last_img"]), P["last_b"], P["out_scale"],
                  P["out_bias"], ptr(out), B, h, w_, st)
         else:
             call("rdst_last_conv_fwd", ptr(feat), 64, ptr(P["last_w"]), P["last_b"], P["out_scale"], P["out_bias"],
                  ptr(out), B, h, w_, 64, dt, st)
-        return out if x.dtype == torch.float32 else out.to(x.dtype)
+        return out if (given or x.dtype == torch.float32) else out.to(x.dtype)
 
     def _block_done(self, index, trunk, T):
         """Hook after RDSTB `index` (trunk = dense buffer whose first 64 columns hold the block output)."""

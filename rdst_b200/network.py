@@ -237,10 +237,12 @@ class RDSTSR(nn.Module):
         self.precision = precision
         return self
 
-    def forward(self, x, sr_scale=None):
+    def forward(self, x, sr_scale=None, out=None):
+        """Reference signature forward(x, sr_scale=None) (rdst_variations.py:1342); `out` is an optional extension: an fp32
+        result tensor on the device or in pinned host memory that the last kernel writes directly (inference only)."""
         if not self._exec.bound_to(self):            # e.g. after copy.deepcopy
             self._exec = executor.Executor(self)
-        return self._exec.forward(x)
+        return self._exec.forward(x, out)
 
     def extra_repr(self):
         return f"precision={self.precision}, sr_scale={self.sr_scale}, backend=librdst_b200 (sm_100a)"
@@ -297,10 +299,10 @@ class RDSTSR_N(RDSTSR):
             self._modules[k] = mods[k]
         self._exec = executor.ExecutorN(self)
 
-    def forward(self, x, sr_scale=None):
+    def forward(self, x, sr_scale=None, out=None):
         if not self._exec.bound_to(self):
             self._exec = executor.ExecutorN(self)
-        return self._exec.forward(x)
+        return self._exec.forward(x, out)
 
 
 def make_RDSTSR(paras, mean=None, std=None):

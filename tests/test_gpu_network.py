@@ -112,3 +112,29 @@ def test_graphed_inference_driver_matches_eager():
     with torch.no_grad():
         ref = m(vol.cuda()).cpu()
     assert out.shape == (10, 1, 160, 128) and torch.equal(out, ref)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_out_argument_device_and_pinned_host(precision):
+    """forward(x, out=...) writes the HR image into the given tensor -- device memory or pinned host memory -- with the
+    same bits as the default path; bad `out` tensors are rejected."""
+    c = helpers.load_case("e2blk_x4_8x8")
+    m = helpers.make_module(c["blocks"], c["scale"], precision).cuda().eval()
+    m.load_state_dict(c["sd"])
+    x = torch.rand(5, 1, 16, 24, generator=torch.Generator().manual_seed(2)).cuda()
+    with torch.no_grad():
+        ref = m(x)
+        dev_out = torch.zeros_like(ref)
+        assert m(x, out=dev_out) is dev_out and torch.equal(dev_out, ref)
+        host_out = torch.zeros(ref.shape).pin_memory()
+        m(x, out=host_out)
+        torch.cuda.synchronize()
+        assert torch.equal(host_out, ref.cpu())
+        with pytest.raises(ValueError, match="out="):
+            m(x, out=torch.zeros(ref.shape))                      # pageable host memory
+        with pytest.raises(ValueError, match="out="):
+            m(x, out=torch.zeros(5, 1, 8, 8, device="cuda"))
+    from rdst_b200 import infer
+    vol = x.cpu().pin_memory()
+    y = infer.super_resolve_slices(m, vol, batch_size=2)
+    assert y.is_pinned() and torch.equal(y, ref.cpu())
