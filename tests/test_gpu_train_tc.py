@@ -248,6 +248,49 @@ def test_gemm_tc_lnbwd(T, K, ldy, N, ldo, creal, two):
     assert torch.equal(out[:, N:], ref[:, N:])
 
 
+@pytest.mark.parametrize("c", [60, 90, 120])
+def test_pack_kernels_match_packing_py(c):
+    """rdst_pack_linear_batch (forward and backward) against rdst_b200/packing.py -- the inference-time packer -- and its
+    torch autograd: packed weights of a Swin block + DenseSTLayer tail, and parameter gradients from packed gradients."""
+    from rdst_b200 import autograd as A, network, packing
+    torch.manual_seed(c)
+    blk = network.SwinTransformerBlock(c, (24, 24), 6, 4, 2.0, True, None).cuda()
+    tail = torch.nn.Sequential(torch.nn.LayerNorm(c), torch.nn.Linear(c, 30)).cuda()
+    for p in list(blk.parameters()) + list(tail.parameters()):
+        torch.nn.init.normal_(p, std=0.3)
+    L = A._Layout()
+    st = L.stl(blk, c)
+    tg, tb_, tw, tbias = L.take(4)
+    sw, sb = L.lin(tw, tbias, tg, tb_, 30, c, 32, packing.padded_width(c), 0, 1)
+    bs = L.finish({})
+    P = A.stl_params(blk) + [tail[0].weight, tail[0].bias, tail[1].weight, tail[1].bias]
+    W = A._views(torch.zeros(bs["packed_floats"], device="cuda"), bs["slots"])
+    A._pack_batch(bs["lins"], P, W, None, None, backward=False)
+    with packing.differentiable():
+        ref = packing.pack_stl(blk, c)
+        dstl = type("D", (), {"tail": tail})()
+        rt = packing.pack_dstl_tail(dstl, c, 1.0)
+    pairs = [(W[st[k]], ref[k]) for k in ("wqkv", "bqkv", "wproj", "bproj", "w1", "b1", "w2", "b2")] + [(W[sw], rt["w"]), (W[sb], rt["b"])]
+    for got, want in pairs:
+        assert got.shape == want.shape and (got - want).abs().max().item() <= 1e-6 * max(1.0, want.abs().max().item())
+    # backward: random packed gradients -> parameter gradients, vs autograd through packing.py
+    G = [torch.randn_like(w) for w in W]
+    loss = sum((g * want).sum() for g, (_, want) in zip([G[st[k]] for k in ("wqkv", "bqkv", "wproj", "bproj", "w1", "b1", "w2", "b2")] + [G[sw], G[sb]], pairs))
+    g_ref = torch.autograd.grad(loss, P, allow_unused=True)
+    GP = [None] * len(P)
+    for l in bs["lins"]:
+        GP[l["w"]], GP[l["b"]] = torch.empty_like(P[l["w"]]), torch.empty_like(P[l["b"]])
+        if l["g"] is not None:
+            GP[l["g"]], GP[l["be"]] = torch.zeros_like(P[l["g"]]), torch.zeros_like(P[l["be"]])
+    A._pack_batch(bs["lins"], P, None, G, GP, backward=True)
+    torch.cuda.synchronize()
+    for i, (got, want) in enumerate(zip(GP, g_ref)):
+        if got is None:                        # the relative-position table is used as stored (not packed)
+            assert i == 4
+            continue
+        assert (got - want).abs().max().item() <= 2e-5 * max(1.0, want.abs().max().item()), i
+
+
 def _oracle_grads(sd, x, target, scale):
     p = {k: (v.clone().double().requires_grad_(True) if v.is_floating_point() else v) for k, v in sd.items()}
     out = O.forward(p, x.double(), scale)
