@@ -263,6 +263,7 @@ __global__ void __launch_bounds__(NT, 1) attn_train_bwd_kernel(const AttnArgs a)
   __shared__ uint32_t tmem_base_s;
   __shared__ float stab[HEADS][225];
   __shared__ float sdtab[HEADS][225];
+  __shared__ float swtab[NT / 32][232];              // per-warp private copy of the table gradient of the head in flight
   __shared__ int sreg[128];
   const int tid = threadIdx.x, warp = tid >> 5;
   const int row = tid & 127, g = tid >> 7;
@@ -301,6 +302,7 @@ __global__ void __launch_bounds__(NT, 1) attn_train_bwd_kernel(const AttnArgs a)
       stage_row<HD, HDP>(sV, row, qrow ? qrow + 2 * a.C + h * HD : nullptr);
       stage_row<HD, HDP>(sG, row, grow ? grow + h * HD : nullptr);
       const float lse = t >= 0 ? __ldg(a.lse + t * HEADS + h) : 0.f;
+      for (int e = tid & 31; e < 225; e += 32) swtab[warp][e] = 0.f;
       fence_proxy_async();
       fence_before_sync();
       __syncthreads();
@@ -353,7 +355,11 @@ __global__ void __launch_bounds__(NT, 1) attn_train_bwd_kernel(const AttnArgs a)
             const int j = half * 32 + jj;
             const float ds = p[j] * (__uint_as_float(v[jj]) - delta);
             p[j] = ds;
-            if (t >= 0) atomicAdd(&sdtab[h][(iy - (j >> 3) + 7) * 15 + (ix - (j & 7) + 7)], ds);
+            // relative-position-table gradient: for one key j the 32 rows of a warp hit 32 different bins, so a plain
+            // read-modify-write on the warp's private table needs no atomics (shared fp32 atomics are CAS loops)
+            float* bin = &swtab[warp][(iy - (j >> 3) + 7) * 15 + (ix - (j & 7) + 7)];
+            if (t >= 0) *bin += ds;
+            __syncwarp();
           }
         }
         store_row64(sD, row, p);
@@ -362,6 +368,8 @@ __global__ void __launch_bounds__(NT, 1) attn_train_bwd_kernel(const AttnArgs a)
       fence_before_sync();
       __syncthreads();
       fence_after_sync();
+      for (int e = row; e < 225; e += 128)
+        sdtab[h][e] += (swtab[4 * g][e] + swtab[4 * g + 1][e]) + (swtab[4 * g + 2][e] + swtab[4 * g + 3][e]);
       // ---- dQ = dS k, dK = dS^T q, dV = P^T dO (contraction over the 64 tokens of the window) ----
       if (warp == 0) {
         if (elect_one()) {
