@@ -247,8 +247,8 @@ __global__ void __launch_bounds__(64) window_attention_bwd_kernel(const float* _
   float (*sP)[65] = reinterpret_cast<float (*)[65]>(smf + 4 * 64 * HP);
   float (*sdS)[65] = sP + 64;
   float* stab = smf + 4 * 64 * HP + 2 * 64 * 65;
-  float* sdtab = stab + 225;
-  int* sreg = reinterpret_cast<int*>(sdtab + 225);
+  float* sdtab = stab + 225;                        // two private copies (one per warp): plain read-modify-write, no atomics
+  int* sreg = reinterpret_cast<int*>(sdtab + 2 * 225);
   const int wi = blockIdx.x, h = blockIdx.y, i = threadIdx.x;
   const int nwx = W >> 3, nw_img = (H >> 3) * nwx;
   const int b = wi / nw_img, wl = wi - b * nw_img;
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(64) window_attention_bwd_kernel(const float* _
   int hh = hs + shift; if (hh >= H) hh -= H;
   int ww = ws + shift; if (ww >= W) ww -= W;
   const int64_t t = ((int64_t)b * H + hh) * W + ww;
-  for (int e = i; e < 225; e += 64) { stab[e] = table[e * heads + h]; sdtab[e] = 0.f; }
+  for (int e = i; e < 225; e += 64) { stab[e] = table[e * heads + h]; sdtab[e] = 0.f; sdtab[225 + e] = 0.f; }
   int reg = 0;
   if (shift > 0) {
     const int rh = hs < H - 8 ? 0 : (hs < H - shift ? 1 : 2);
@@ -320,7 +320,9 @@ __global__ void __launch_bounds__(64) window_attention_bwd_kernel(const float* _
         const float4 kv = *reinterpret_cast<const float4*>(&sk[j][d]);
         dq[d] = fmaf(ds, kv.x, dq[d]); dq[d + 1] = fmaf(ds, kv.y, dq[d + 1]); dq[d + 2] = fmaf(ds, kv.z, dq[d + 2]); dq[d + 3] = fmaf(ds, kv.w, dq[d + 3]);
       }
-      atomicAdd(&sdtab[(iy - (j >> 3) + 7) * 15 + (ix - (j & 7) + 7)], ds);
+      // for one key j the 32 query rows of a warp hit 32 different table entries
+      sdtab[(i >> 5) * 225 + (iy - (j >> 3) + 7) * 15 + (ix - (j & 7) + 7)] += ds;
+      __syncwarp();
     }
     float* grow = dqkv + t * ldg + h * HD;
 #pragma unroll
@@ -347,13 +349,13 @@ __global__ void __launch_bounds__(64) window_attention_bwd_kernel(const float* _
     for (int d = 0; d < HD; ++d) { grow[C + d] = dk[d]; grow[2 * C + d] = dv[d]; }
   }
   for (int e = i; e < 225; e += 64)
-    if (sdtab[e] != 0.f) atomicAdd(dtable + e * heads + h, sdtab[e]);
+    if (sdtab[e] + sdtab[225 + e] != 0.f) atomicAdd(dtable + e * heads + h, sdtab[e] + sdtab[225 + e]);
 }
 
 template <int HD>
 static void launch_wattn_bwd(dim3 grid, cudaStream_t st, const float* qkv, int64_t ldq, const float* table, const float* dout,
                              int64_t ldo, float* dqkv, int64_t ldg, float* dtable, int H, int W, int C, int heads, int shift) {
-  const size_t smem = (size_t)(4 * 64 * ((HD + 3) / 4 * 4) + 2 * 64 * 65 + 2 * 225 + 64) * sizeof(float);
+  const size_t smem = (size_t)(4 * 64 * ((HD + 3) / 4 * 4) + 2 * 64 * 65 + 3 * 225 + 64) * sizeof(float);
   cudaFuncSetAttribute(window_attention_bwd_kernel<HD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   window_attention_bwd_kernel<HD><<<grid, 64, smem, st>>>(qkv, ldq, table, dout, ldo, dqkv, ldg, dtable, H, W, C, heads, shift);
 }
