@@ -23,6 +23,18 @@ class PackDesc(C.Structure):
                [("q_scale", C.c_float), ("_pad", C.c_int)]
 
 
+_PACK_PTR_FIELDS = ("W", "b", "gamma", "beta", "Wp", "bp", "dWp", "dbp", "dW", "db", "dgamma", "dbeta")
+
+
+def pack_desc_array(descs):
+    """list of dicts (tensors / None under the pointer fields of RdstPackDesc, ints and a float otherwise) -> ctypes array."""
+    arr = (PackDesc * len(descs))()
+    for a, d in zip(arr, descs):
+        for k, v in d.items():
+            setattr(a, k, (None if v is None else v.data_ptr()) if k in _PACK_PTR_FIELDS else v)
+    return arr
+
+
 _SIGNATURES = {
     "rdst_abi_version": (C.c_int, []),
     "rdst_last_error": (C.c_char_p, []),

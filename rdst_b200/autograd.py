@@ -12,6 +12,7 @@ parameters; every activation-sized computation, forward and backward, is a kerne
 Gradient of: RDSTSR.forward (rdst_variations.py:1342-1360) and everything it calls; checked against torch.autograd
 through the CPU oracle in tests/test_gpu_backward.py (fp32) and tests/test_gpu_train_tc.py (bf16 tensor-core GEMMs).
 """
+import contextlib
 import threading
 
 import torch
@@ -271,20 +272,19 @@ def pack_conv64(conv, device, n_pad=64):
 
 def _pack_batch(lins, P, W, G, GP, backward):
     """All Linears of one RDSTB in one rdst_pack_linear_batch launch (forward: P -> W; backward: G -> GP)."""
-    arr = (_lib.PackDesc * len(lins))()
-    dp = lambda t: None if t is None else t.data_ptr()
-    for d, l in zip(arr, lins):
+    descs = []
+    for l in lins:
         ln = l["g"] is not None
-        d.W, d.b = dp(P[l["w"]]), dp(P[l["b"]])
-        d.gamma, d.beta = (dp(P[l["g"]]), dp(P[l["be"]])) if ln else (None, None)
+        d = dict(W=P[l["w"]], b=P[l["b"]], gamma=P[l["g"]] if ln else None, beta=P[l["be"]] if ln else None,
+                 N=l["N"], K=l["K"], ldp=l["ldp"], scatter_rows=l["srows"], scatter_cols=l["scols"], q_rows=l["q_rows"],
+                 q_scale=l["q_scale"])
         if backward:
-            d.dWp, d.dbp, d.dW, d.db = dp(G[l["sw"]]), dp(G[l["sb"]]), dp(GP[l["w"]]), dp(GP[l["b"]])
-            d.dgamma, d.dbeta = (dp(GP[l["g"]]), dp(GP[l["be"]])) if ln else (None, None)
+            d.update(dWp=G[l["sw"]], dbp=G[l["sb"]], dW=GP[l["w"]], db=GP[l["b"]],
+                     dgamma=GP[l["g"]] if ln else None, dbeta=GP[l["be"]] if ln else None)
         else:
-            d.Wp, d.bp = dp(W[l["sw"]]), dp(W[l["sb"]])
-        d.N, d.K, d.ldp, d.scatter_rows, d.scatter_cols = l["N"], l["K"], l["ldp"], l["srows"], l["scols"]
-        d.q_rows, d.q_scale = l["q_rows"], l["q_scale"]
-    _call("rdst_pack_linear_batch", arr, len(lins), 1 if backward else 0, _lib.stream_ptr())
+            d.update(Wp=W[l["sw"]], bp=W[l["sb"]])
+        descs.append(d)
+    _call("rdst_pack_linear_batch", _lib.pack_desc_array(descs), len(descs), 1 if backward else 0, _lib.stream_ptr())
 
 
 def pack_head(m, device):
@@ -345,6 +345,12 @@ def frozen_scalars(m):
 # parameter gradients of RDSTB i (link backward, then its packing graph, then AccumulateGrad) before it starts
 # RDSTB i-1: gradient buckets become ready block by block and a data-parallel all-reduce (torch DDP, or
 # rdst_b200.ddp.BucketedAllReduce) overlaps with the rest of the backward pass.
+def _on(dev):
+    """Make the tensors' device current for the launches (kernels take the current device); CPU tensors only get here in the
+    `-m "not gpu"` tests, where the C ABI is replaced by its contract restatements."""
+    return torch.cuda.device(dev) if dev.type == "cuda" else contextlib.nullcontext()
+
+
 def _f32(dev):
     return (lambda *s: torch.empty(*s, dtype=torch.float32, device=dev),
             lambda *s: torch.zeros(*s, dtype=torch.float32, device=dev))
@@ -361,7 +367,7 @@ class HeadFunction(torch.autograd.Function):
         T = B * H * Wd
         e, z = _f32(dev)
         _MODE.tc = sc["tc"]
-        with torch.cuda.device(dev):
+        with _on(dev):
             img = z(T, 16)
             img[:, 0] = x.reshape(-1) * sc["in_scale"] + sc["in_bias"]
             F0 = e(T, 64)
@@ -382,7 +388,7 @@ class HeadFunction(torch.autograd.Function):
         e, z = _f32(dev)
         G = [None] * len(W)
         _MODE.tc = ctx.tc
-        with torch.cuda.device(dev):
+        with _on(dev):
             dF = dF0.contiguous().clone()
             dE = z(T, 64)
             gg, gb = z(60), z(60)
@@ -407,7 +413,7 @@ class BlockFunction(torch.autograd.Function):
         dev = X.device
         e, z = _f32(dev)
         _MODE.tc = tc = bs["tc"]
-        with torch.cuda.device(dev):
+        with _on(dev):
             # packed weights of the block: one zeroed buffer, one rdst_pack_linear_fwd per Linear (csrc/pack.cu)
             W = _views(z(bs["packed_floats"]), bs["slots"])
             _pack_batch(bs["lins"], P, W, None, None, backward=False)
@@ -450,7 +456,7 @@ class BlockFunction(torch.autograd.Function):
             return G[i]
 
         _MODE.tc = bs["tc"]
-        with torch.cuda.device(dev):
+        with _on(dev):
             dX = dXn.contiguous()
             dys = dX if bs["res_scale"] == 1.0 else dX * bs["res_scale"]
             gemm_tn(dys, D, gz(bs["lff_w"]), gz(bs["lff_b"]), 64, 9 * 160, (B, H, Wd, 160))
@@ -503,7 +509,7 @@ class TailFunction(torch.autograd.Function):
         dev = X.device
         e, z = _f32(dev)
         _MODE.tc = sc["tc"]
-        with torch.cuda.device(dev):
+        with _on(dev):
             if sc.get("tail_only"):                          # RDSTSR_N: X already is the map that feeds the up-sampler
                 FN, F1 = None, X.contiguous()
             else:
@@ -544,7 +550,7 @@ class TailFunction(torch.autograd.Function):
             return G[i]
 
         _MODE.tc = sc["tc"]
-        with torch.cuda.device(dev):
+        with _on(dev):
             n_up = len(spec["up"])
             h, w_ = H * (2 ** n_up), Wd * (2 ** n_up)
             # ---- last conv (64 -> 1) + add_mean ----
@@ -687,7 +693,7 @@ class RSTBFunction(torch.autograd.Function):
         T = B * H * Wd
         e, z = _f32(X.device)
         _MODE.tc = tc = bs["tc"]
-        with torch.cuda.device(X.device):
+        with _on(X.device):
             W = _link_packed(bs, P, conv_w, conv_b)
             src, saved = X.contiguous(), []
             for st in bs["stl"]:
@@ -706,7 +712,7 @@ class RSTBFunction(torch.autograd.Function):
         T = B * H * Wd
         e, z = _f32(dXn.device)
         _MODE.tc = bs["tc"]
-        with torch.cuda.device(dXn.device):
+        with _on(dXn.device):
             G = _link_grad_buffers(bs, W, P)
             gz = lambda i: G[i]
             dX = dXn.contiguous()
@@ -731,7 +737,7 @@ class SwinIRTailFunction(torch.autograd.Function):
         T = B * H * Wd
         e, z = _f32(X.device)
         _MODE.tc = tc
-        with torch.cuda.device(X.device):
+        with _on(X.device):
             X = X.contiguous()
             FN = z(T, 64)
             _call("rdst_layernorm_fwd", _p(X), 64, _p(norm_g), _p(norm_b), _p(FN), 64, T, 60, 1.0, F32, _lib.stream_ptr())
@@ -749,7 +755,7 @@ class SwinIRTailFunction(torch.autograd.Function):
         X, FN, F1, norm_g, cab_w, up_w = ctx.saved
         e, z = _f32(dup.device)
         _MODE.tc = ctx.tc
-        with torch.cuda.device(dup.device):
+        with _on(dup.device):
             dup = dup.contiguous()
             g_upw, g_upb = z(16, 9, 64), z(16)
             gemm_tn(dup, F1, g_upw, g_upb, 16, 9 * 64, (B, H, Wd, 64))
@@ -809,7 +815,7 @@ class BottleneckFunction(torch.autograd.Function):
         T, K = cat.shape
         e, _ = _f32(cat.device)
         _MODE.tc = tc
-        with torch.cuda.device(cat.device):
+        with _on(cat.device):
             cat = cat.contiguous()
             tmp, F1 = e(T, 64), e(T, 64)
             linear(cat, w1, b1, tmp, K, 64)
@@ -823,7 +829,7 @@ class BottleneckFunction(torch.autograd.Function):
         T, K = cat.shape
         e, z = _f32(dF1.device)
         _MODE.tc = ctx.tc
-        with torch.cuda.device(dF1.device):
+        with _on(dF1.device):
             dF1 = dF1.contiguous()
             dy = dF1 if ctx.grs == 1.0 else dF1 * ctx.grs
             gw2, gb2, gw1, gb1 = z(64, 64), z(64), z(64, K), z(64)

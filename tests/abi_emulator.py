@@ -100,6 +100,152 @@ def rdst_last_conv_fwd(x, ldx, w, bias, out_scale, out_bias, img, B, H, W, Cin, 
     img.copy_((F.conv2d(a, wt, None, padding=1) + bias) * out_scale + out_bias)
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# training-path entry points (fp32 contract; the tensor-core variants compute the same thing on bf16-rounded operands)
+# ---------------------------------------------------------------------------------------------------------------
+def _dense_real(k):
+    idx = torch.arange(k)
+    return (idx < 60) | ((idx >= 64) & (((idx - 64) % 32) < 30))
+
+
+def _real_mask(K, creal, dense_layout):
+    return _dense_real(K) if dense_layout else (torch.arange(K) < creal)
+
+
+def rdst_gelu_fwd(x, ldx, y, ldy, T, N, st):
+    _store(y, F.gelu(x[:, :N].float()))
+
+
+@torch.enable_grad()          # called from inside autograd.Function.backward, where grad mode is off
+def rdst_gelu_bwd(x, ldx, dy, ldd, dx, ldo, T, N, st):
+    xv = x[:, :N].double().clone().requires_grad_(True)
+    g, = torch.autograd.grad(F.gelu(xv), xv, dy[:, :N].double())
+    _store(dx, g)
+
+
+def _conv_cols(x, B, H, W, Cin):
+    xi = x[:, :Cin].double().reshape(B, H, W, Cin).permute(0, 3, 1, 2)
+    return F.unfold(xi, 3, padding=1).reshape(B, Cin, 9, H * W).permute(0, 3, 2, 1).reshape(B * H * W, 9 * Cin)   # [t][tap][ci]
+
+
+def rdst_gemm_tn_acc(dy, ldy, x, ldx, dw, db, T, N, K, conv, B, H, W, Cin, st):
+    xs = _conv_cols(x, B, H, W, Cin) if conv else x[:, :K].double()
+    g = dy[:, :N].double().t() @ xs
+    dw.view(N, K).add_(g.to(dw.dtype))
+    if db is not None:
+        db[:N].add_(dy[:, :N].double().sum(0).to(db.dtype))
+
+
+def rdst_lnhat_fwd(x, ldx, y, ldy, T, K, creal, dense_layout, st):
+    _store(y, _lnhat(x[:, :K].float(), creal) * _real_mask(K, creal, dense_layout))
+
+
+@torch.enable_grad()          # called from inside autograd.Function.backward, where grad mode is off
+def rdst_lnhat_bwd(dxh, ldd, x, ldx, resid, ldr, resid2, ldr2, dx, ldo, T, K, creal, dense_layout, st):
+    real = _real_mask(K, creal, dense_layout).double()
+    xv = x[:, :K].double().clone().requires_grad_(True)
+    xh = _lnhat(xv, creal) * real
+    g, = torch.autograd.grad(xh, xv, dxh[:, :K].double() * real)
+    v = g * real                      # pad outputs are 0 (the kernel does not propagate into pad channels)
+    if resid is not None:
+        v = v + resid[:, :K].double()
+    if resid2 is not None:
+        v = v + resid2[:, :K].double()
+    _store(dx, v)
+
+
+@torch.enable_grad()          # called from inside autograd.Function.backward, where grad mode is off
+def rdst_layernorm_bwd(dy, ldd, x, ldx, gamma, dx, ldo, dgamma, dbeta, T, creal, scale, st):
+    xv = x[:, :creal].double().clone().requires_grad_(True)
+    gv = gamma.double().clone().requires_grad_(True)
+    bv = torch.zeros(creal, dtype=torch.float64, requires_grad=True)
+    y = F.layer_norm(xv, (creal,), gv, bv, 1e-5) * scale
+    gx, gg, gb = torch.autograd.grad(y, (xv, gv, bv), dy[:, :creal].double())
+    _store(dx, gx)
+    dgamma.add_(gg.to(dgamma.dtype))
+    dbeta.add_(gb.to(dbeta.dtype))
+
+
+@torch.enable_grad()          # called from inside autograd.Function.backward, where grad mode is off
+def rdst_window_attention_bwd(qkv, ldq, table, dout, ldo, dqkv, ldg, dtable, B, H, W, C, heads, shift, st):
+    q = qkv[:, :3 * C].double().clone().requires_grad_(True)
+    t = table.double().clone().requires_grad_(True)
+    o = torch.zeros(q.shape[0], C, dtype=torch.float64)
+    o = _attention_core(q, t, B, H, W, C, heads, shift)
+    gq, gt = torch.autograd.grad(o, (q, t), dout[:, :C].double())
+    _store(dqkv, gq)
+    dtable.add_(gt.to(dtable.dtype))
+
+
+def _attention_core(qkv, table, B, H, W, C, heads, shift):
+    hd = C // heads
+    t = qkv.reshape(B, H, W, 3 * C)
+    if shift:
+        t = torch.roll(t, (-shift, -shift), (1, 2))
+    win = t.reshape(B, H // 8, 8, W // 8, 8, 3 * C).permute(0, 1, 3, 2, 4, 5).reshape(-1, 64, 3, heads, hd)
+    q, k, v = (win[:, :, i].permute(0, 2, 1, 3) for i in range(3))
+    att = q @ k.transpose(-1, -2)
+    r = torch.arange(8)
+    ih, iw = (g.reshape(-1) for g in torch.meshgrid(r, r, indexing="ij"))
+    idx = (ih[:, None] - ih[None, :] + 7) * 15 + (iw[:, None] - iw[None, :] + 7)
+    att = att + table[idx.reshape(-1)].reshape(64, 64, heads).permute(2, 0, 1)[None]
+    if shift:
+        hs = torch.arange(H)[:, None].expand(H, W)
+        ws = torch.arange(W)[None, :].expand(H, W)
+        reg = (torch.where(hs < H - 8, 0, torch.where(hs < H - shift, 1, 2)) * 3 +
+               torch.where(ws < W - 8, 0, torch.where(ws < W - shift, 1, 2)))
+        rw = reg.reshape(H // 8, 8, W // 8, 8).permute(0, 2, 1, 3).reshape(-1, 64)
+        mask = torch.where(rw[:, :, None] != rw[:, None, :], -100.0, 0.0).to(att.dtype)
+        att = att + mask.repeat(B, 1, 1)[:, None]
+    o = (torch.softmax(att, -1) @ v).permute(0, 2, 1, 3).reshape(-1, 64, C)
+    o = o.reshape(B, H // 8, W // 8, 8, 8, C).permute(0, 1, 3, 2, 4, 5).reshape(B, H, W, C)
+    if shift:
+        o = torch.roll(o, (shift, shift), (1, 2))
+    return o.reshape(-1, C)
+
+
+def rdst_axpy(x, ldx, y, ldy, T, N, alpha, st):
+    y[:, :N].add_(x[:, :N], alpha=alpha)
+
+
+def rdst_pixel_unshuffle2(u, ldu, z, ldz, B, H, W, G, st):
+    v = u[:, :G].reshape(B, H, 2, W, 2, G).permute(0, 1, 3, 2, 4, 5).reshape(B * H * W, 4 * G)     # [t][s = 2dy+dx][c]
+    _store(z, v)
+
+
+def _chan_pos(n, scatter):
+    idx = torch.arange(n)
+    if not scatter:
+        return idx
+    g = torch.clamp((idx - 60) // 30, min=0)
+    return torch.where(idx < 60, idx, 64 + 32 * g + (idx - 60) % 30)
+
+
+def rdst_pack_linear_batch(descs, n, backward, st):
+    """descs: list of dicts with TENSORS under the RdstPackDesc field names (the emulator replaces _lib.pack_desc_array)."""
+    for d in descs[:n]:
+        N, K = d["N"], d["K"]
+        W = d["W"].double().reshape(N, K)
+        rs = torch.ones(N, dtype=torch.float64)
+        rs[:d["q_rows"]] = d["q_scale"]
+        pn, pk = _chan_pos(N, d["scatter_rows"]), _chan_pos(K, d["scatter_cols"])
+        g = d["gamma"].double() if d["gamma"] is not None else torch.ones(K, dtype=torch.float64)
+        be = d["beta"].double() if d["beta"] is not None else torch.zeros(K, dtype=torch.float64)
+        if not backward:
+            Wp = d["Wp"]
+            Wp[pn[:, None], pk[None, :]] = (rs[:, None] * W * g[None, :]).to(Wp.dtype)
+            d["bp"][pn] = (rs * ((d["b"].double() if d["b"] is not None else 0) + W @ be)).to(d["bp"].dtype)
+        else:
+            gw = d["dWp"].double()[pn[:, None], pk[None, :]]
+            gb = d["dbp"].double()[pn]
+            d["dW"].copy_((rs[:, None] * (g[None, :] * gw + gb[:, None] * be[None, :])).reshape(d["dW"].shape))
+            if d["db"] is not None:
+                d["db"].copy_(rs * gb)
+            if d["dgamma"] is not None:
+                d["dgamma"].add_(((rs[:, None] * W * gw).sum(0)).to(d["dgamma"].dtype))
+                d["dbeta"].add_(((rs[:, None] * W) * gb[:, None]).sum(0).to(d["dbeta"].dtype))
+
+
 _TABLE = {k: v for k, v in globals().items() if k.startswith("rdst_")}
 
 
@@ -113,9 +259,9 @@ def emulated_abi(record=None):
             record.append(name)
         _TABLE[name](*args)
 
-    saved = (_lib.call, _lib.ptr, _lib.stream_ptr)
-    _lib.call, _lib.ptr, _lib.stream_ptr = call, (lambda t: t), (lambda: None)
+    saved = (_lib.call, _lib.ptr, _lib.stream_ptr, _lib.pack_desc_array)
+    _lib.call, _lib.ptr, _lib.stream_ptr, _lib.pack_desc_array = call, (lambda t: t), (lambda: None), (lambda descs: descs)
     try:
         yield
     finally:
-        _lib.call, _lib.ptr, _lib.stream_ptr = saved
+        _lib.call, _lib.ptr, _lib.stream_ptr, _lib.pack_desc_array = saved
