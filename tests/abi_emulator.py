@@ -246,6 +246,68 @@ def rdst_pack_linear_batch(descs, n, backward, st):
                 d["dbeta"].add_(((rs[:, None] * W) * gb[:, None]).sum(0).to(d["dbeta"].dtype))
 
 
+# ---- tensor-core entry points of the bf16 training mode: same contracts, evaluated here WITHOUT the bf16 operand rounding
+#      (the rounding is a property of the kernels, checked on the GPU; the host logic -- padded strides, fused operands,
+#      saved log-sum-exp, descriptor plumbing -- is what these stand-ins let the CPU tests exercise)
+def _gelu_grad(x):
+    return 0.5 * (1 + torch.erf(x * 0.7071067811865476)) + x * torch.exp(-0.5 * x * x) * 0.3989422804014327
+
+
+def rdst_gemm_tc(x, ldx, w, ldw, w_mn, bias, resid, ldr, aux, lda, y, ldy, T, K, N, a_op, ln_creal, scale, conv, B, H, W, Cin,
+                 shuffle, st):
+    assert x.stride(0) == ldx and y.stride(0) == ldy and x.data_ptr() % 16 == 0 and y.data_ptr() % 16 == 0
+    assert ldx % 4 == 0 and ldy % 4 == 0 and (conv or ldx >= (K + 7) // 8 * 8)
+    if conv:
+        assert not w_mn and not a_op
+        a = _conv_cols(x, B, H, W, Cin)
+        wm = w.double().reshape(-1, 9 * Cin)[:N]
+    else:
+        a = x[:, :K].double()
+        if a_op == 1:
+            a = _lnhat(a, ln_creal)
+        elif a_op == 2:
+            a = F.gelu(a)
+        wm = (w.double()[:K, :N].t() if w_mn else w.double().reshape(-1, w.shape[-1])[:N, :K])
+    v = a @ wm.t()
+    if bias is not None:
+        v = v + bias.double()[:N]
+    v = v * scale
+    if aux is not None:
+        v = v * _gelu_grad(aux[:, :N].double())
+    if shuffle == 2:
+        G = N // 4
+        v = v.reshape(B, H, W, 2, 2, G).permute(0, 1, 3, 2, 4, 5).reshape(B * 2 * H * 2 * W, G)
+    elif resid is not None:
+        v = v + resid[:, :N].double()
+    _store(y, v)
+
+
+def rdst_gemm_tc_lnbwd(dy, ldy, w, ldw, x, ldx, resid, ldr, resid2, ldr2, dx, ldo, T, K, N, creal, scale, st):
+    assert N <= 128 and N % 16 == 0 and dy.stride(0) == ldy and dx.stride(0) == ldo
+    dxh = (dy[:, :K].double() @ w.double()[:K, :N]) * scale
+    rdst_lnhat_bwd(dxh, N, x, ldx, resid, ldr, resid2, ldr2, dx, ldo, T, N, creal, 1, st)
+
+
+def rdst_gemm_tn_tc(dy, ldy, x, ldx, dw, db, T, N, K, conv, B, H, W, Cin, x_op, x_creal, st):
+    assert dy.stride(0) == ldy and ldy % 4 == 0 and ldy >= (N + 7) // 8 * 8 and dw.data_ptr() % 16 == 0
+    if x_op:
+        xs = x[:, :K].double()
+        x = (_lnhat(xs, x_creal) if x_op == 1 else F.gelu(xs)).contiguous()
+    rdst_gemm_tn_acc(dy, ldy, x, x.stride(0), dw, db, T, N, K, conv, B, H, W, Cin, st)
+
+
+def rdst_window_attention_tc_fwd(qkv, ldq, table, out, ldo, lse, B, H, W, C, shift, st):
+    assert ldq >= 3 * C and ldo >= C
+    rdst_window_attention_fwd(qkv, ldq, table, out, ldo, B, H, W, C, 6, shift, 0, st)
+    if lse is not None:
+        lse.fill_(float("nan"))          # the stand-in backward recomputes the softmax; a real lse must never be needed here
+
+
+def rdst_window_attention_tc_bwd(qkv, ldq, table, lse, dout, ldo, dqkv, ldg, dtable, B, H, W, C, shift, st):
+    assert lse is not None and lse.shape == (qkv.shape[0], 6)
+    rdst_window_attention_bwd(qkv, ldq, table, dout, ldo, dqkv, ldg, dtable, B, H, W, C, 6, shift, st)
+
+
 _TABLE = {k: v for k, v in globals().items() if k.startswith("rdst_")}
 
 
@@ -259,9 +321,11 @@ def emulated_abi(record=None):
             record.append(name)
         _TABLE[name](*args)
 
-    saved = (_lib.call, _lib.ptr, _lib.stream_ptr, _lib.pack_desc_array)
+    import types
+    saved = (_lib.call, _lib.ptr, _lib.stream_ptr, _lib.pack_desc_array, _lib.load)
     _lib.call, _lib.ptr, _lib.stream_ptr, _lib.pack_desc_array = call, (lambda t: t), (lambda: None), (lambda descs: descs)
+    _lib.load = lambda: types.SimpleNamespace(rdst_has_tcgen05=lambda: 1)     # capability probe of the bf16 training mode
     try:
         yield
     finally:
-        _lib.call, _lib.ptr, _lib.stream_ptr, _lib.pack_desc_array = saved
+        _lib.call, _lib.ptr, _lib.stream_ptr, _lib.pack_desc_array, _lib.load = saved

@@ -37,32 +37,42 @@ def _check(m, fwd, sd, x, target, oracle, skip=("mean.", "attn_mask")):
     return calls
 
 
-def test_rdst_training_chain_on_cpu():
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_rdst_training_chain_on_cpu(precision):
+    """precision='bf16' takes the tensor-core entry points (padded q|k|v rows, fused GELU / LayerNorm operands, saved
+    log-sum-exp, LayerNorm backward in the GEMM epilogue); their stand-ins do not round, so the same tolerance applies."""
     from rdst_b200 import autograd
     sd = fill_state_dict(helpers.skeleton_state_dict(1, 4), 11, True)
-    m = helpers.make_module(1, 4, "fp32")
+    m = helpers.make_module(1, 4, precision)
     x = torch.rand(2, 1, 16, 24, generator=torch.Generator().manual_seed(4))
     target = torch.rand(2, 1, 64, 96, generator=torch.Generator().manual_seed(5))
     calls = _check(m, lambda mod, xx: autograd.forward_with_grad(mod._exec, xx), sd, x, target,
                    lambda p, xx: O.forward(p, xx, 4))
     assert calls.count("rdst_pack_linear_batch") == 2            # one forward + one backward launch per RDSTB
-    assert calls.count("rdst_window_attention_bwd") == 6 and "rdst_gelu_fwd" in calls
+    if precision == "fp32":
+        assert calls.count("rdst_window_attention_bwd") == 6 and "rdst_gelu_fwd" in calls and "rdst_gemm_tc" not in calls
+    else:
+        assert calls.count("rdst_window_attention_tc_bwd") == 6 and calls.count("rdst_gemm_tc_lnbwd") == 15
+        assert not {"rdst_linear_fwd", "rdst_gemm_tn_acc", "rdst_gelu_fwd", "rdst_gelu_bwd", "rdst_lnhat_fwd", "rdst_lnhat_bwd",
+                    "rdst_conv3x3_fwd", "rdst_window_attention_fwd"} & set(calls)      # nothing falls back to CUDA cores
     assert m.sub_mean.weight.grad is None and m.add_mean.bias.grad is None
 
 
-def test_swinir_training_chain_on_cpu():
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_swinir_training_chain_on_cpu(precision):
     from rdst_b200 import autograd
     c = helpers.load_swinir_case("swinir_x2_16x24_b2")
-    m = helpers.make_swinir(c)
+    m = helpers.make_swinir(c, precision)
     target = torch.rand(2, 1, 32, 48, generator=torch.Generator().manual_seed(5))
     _check(m, lambda mod, xx: autograd.forward_with_grad_swinir(mod._exec, xx), c["sd"], c["x"], target,
            lambda p, xx: SO.forward(p, xx, 2), skip=("attn_mask",))
 
 
-def test_rdstn_training_chain_on_cpu():
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_rdstn_training_chain_on_cpu(precision):
     from rdst_b200 import autograd
     c = helpers.load_rdstn_case("rdstn_2blk_x2_16x24_b2")
-    m = helpers.make_rdstn(c)
+    m = helpers.make_rdstn(c, precision)
     target = torch.rand(2, 1, 32, 48, generator=torch.Generator().manual_seed(5))
     _check(m, lambda mod, xx: autograd.forward_with_grad(mod._exec, xx), c["sd"], c["x"], target,
            lambda p, xx: O.forward(p, xx, 2))
