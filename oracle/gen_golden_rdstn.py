@@ -1,4 +1,4 @@
-"""Generate tests/golden/rdstn_*.npz from the REAL reference RDSTSR_N (global bottleneck 'mlp'; build container only).
+"""Generate tests/golden/rdstn_*.npz from the REAL reference RDSTSR_N (global bottleneck 'mlp' / 'conv'; build container only).
 
     python oracle/gen_golden_rdstn.py
 """
@@ -19,17 +19,18 @@ from synth_weights import fill_state_dict, synth_input     # noqa: E402
 
 INI = "/root/reference/config_files/RDST_E1_OASIS_example_SRx4.ini"
 OUT = os.path.join(HERE, "..", "tests", "golden")
-CASES = [("rdstn_e1_x4_40x32", 8, 4, (1, 1, 40, 32), 8, 9), ("rdstn_2blk_x2_16x24_b2", 2, 2, (2, 1, 16, 24), 9, 10)]
+CASES = [("rdstn_e1_x4_40x32", 8, 4, (1, 1, 40, 32), 8, 9, "mlp"), ("rdstn_2blk_x2_16x24_b2", 2, 2, (2, 1, 16, 24), 9, 10, "mlp"),
+         ("rdstn_conv_3blk_x4_16x16", 3, 4, (2, 1, 16, 16), 10, 11, "conv")]
 
 
 def main():
     torch.set_num_threads(8)
-    for name, blocks, scale, shape, wseed, xseed in CASES:
+    for name, blocks, scale, shape, wseed, xseed, mode in CASES:
         p = ParametersLoader(INI)
         for k in ("rdst_dense_layer_depths", "rdst_num_heads", "rdst_window_size", "rdst_rdb_depths"):
             setattr(p, k, list(getattr(p, k))[:blocks])
         p.sr_scale = float(scale)
-        p.rdst_global_bottleneck, p.rdst_global_bottleneck_mode = True, "mlp"
+        p.rdst_global_bottleneck, p.rdst_global_bottleneck_mode = True, mode
         torch.manual_seed(0)
         m = make_RDSTSR(p).eval()
         assert type(m).__name__ == "RDSTSR_N"

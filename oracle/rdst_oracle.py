@@ -185,9 +185,14 @@ def forward(sd, x, sr_scale=4, rnd=None, taps=None, global_res_scale=1.0, featur
         # RDSTSR_N, global bottleneck 'mlp' [rdst_variations.py:1071-1079,1092-1093]: cat of all RDSTB outputs -> two Linears;
         # `norm` and `conv_after_body` exist in the state_dict but are not used by that forward
         t = torch.cat(feats, 2)
-        t = F.linear(t, sd["bottleneck.0.weight"], sd["bottleneck.0.bias"])
-        t = F.linear(t, sd["bottleneck.1.weight"], sd["bottleneck.1.bias"])
-        res = tokens_to_map(t, H, W) * global_res_scale
+        if sd["bottleneck.0.weight"].dim() == 4:     # 'conv' mode [:1080-1082]: 1x1 conv, then 3x3 conv, on the NCHW map
+            fm = tokens_to_map(t, H, W)
+            fm = F.conv2d(fm, sd["bottleneck.0.weight"], sd["bottleneck.0.bias"])
+            res = conv3x3(fm, sd, "bottleneck.1.") * global_res_scale
+        else:
+            t = F.linear(t, sd["bottleneck.0.weight"], sd["bottleneck.0.bias"])
+            t = F.linear(t, sd["bottleneck.1.weight"], sd["bottleneck.1.bias"])
+            res = tokens_to_map(t, H, W) * global_res_scale
     else:
         t = F.layer_norm(t, (t.shape[-1],), sd["norm.weight"], sd["norm.bias"], 1e-5)
         res = tokens_to_map(t, H, W) * global_res_scale

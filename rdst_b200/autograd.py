@@ -811,7 +811,8 @@ class BottleneckFunction(torch.autograd.Function):
     outputs:  F1 = grs * Linear2(Linear1(cat)) + F0."""
 
     @staticmethod
-    def forward(ctx, tc, grs, cat, F0, w1, b1, w2, b2):
+    def forward(ctx, tc, grs, geom, cat, F0, w1, b1, w2, b2):
+        """geom = (B, H, W) selects the 'conv' mode (w2 is a packed 3x3 filter [64][9][64]); None = 'mlp' (w2 [64][64])."""
         T, K = cat.shape
         e, _ = _f32(cat.device)
         _MODE.tc = tc
@@ -819,8 +820,11 @@ class BottleneckFunction(torch.autograd.Function):
             cat = cat.contiguous()
             tmp, F1 = e(T, 64), e(T, 64)
             linear(cat, w1, b1, tmp, K, 64)
-            linear(tmp, w2, b2, F1, 64, 64, scale=grs, resid=F0)
-        ctx.tc, ctx.grs, ctx.saved = tc, grs, (cat, tmp, w1, w2)
+            if geom is None:
+                linear(tmp, w2, b2, F1, 64, 64, scale=grs, resid=F0)
+            else:
+                conv(tmp, w2, b2, F1, *geom, 64, 64, scale=grs, resid=F0)
+        ctx.tc, ctx.grs, ctx.geom, ctx.saved = tc, grs, geom, (cat, tmp, w1, w2)
         return F1
 
     @staticmethod
@@ -832,15 +836,19 @@ class BottleneckFunction(torch.autograd.Function):
         with _on(dF1.device):
             dF1 = dF1.contiguous()
             dy = dF1 if ctx.grs == 1.0 else dF1 * ctx.grs
-            gw2, gb2, gw1, gb1 = z(64, 64), z(64), z(64, K), z(64)
-            gemm_tn(dy, tmp, gw2, gb2, 64, 64)
+            gw2, gb2, gw1, gb1 = torch.zeros_like(w2), z(64), z(64, K), z(64)
             dtmp = e(T, 64)
-            linear_t(dy, w2, dtmp, 64, 64)
+            if ctx.geom is None:
+                gemm_tn(dy, tmp, gw2, gb2, 64, 64)
+                linear_t(dy, w2, dtmp, 64, 64)
+            else:
+                gemm_tn(dy, tmp, gw2, gb2, 64, 9 * 64, (*ctx.geom, 64))
+                conv(dy, conv_dgrad_weight(w2), z(64), dtmp, *ctx.geom, 64, 64)
             gemm_tn(dtmp, cat, gw1, gb1, 64, K)
             dcat = e(T, K)
             linear_t(dtmp, w1, dcat, 64, K)
         ctx.saved = None
-        return None, None, dcat, dF1, gw1, gb1, gw2, gb2
+        return None, None, None, dcat, dF1, gw1, gb1, gw2, gb2
 
 
 def forward_with_grad(executor, x):
@@ -869,13 +877,17 @@ def forward_with_grad(executor, x):
             f = packing._f
             pos = torch.cat([torch.arange(60, device=dev) + 64 * i for i in range(n)])
             w1 = torch.zeros(64, 64 * n, device=dev)
-            w1[:60, pos] = f(m.bottleneck[0].weight)
+            w1[:60, pos] = f(m.bottleneck[0].weight).reshape(60, 60 * n)          # Linear weight or 1x1 conv filter
             b1 = torch.zeros(64, device=dev)
             b1[:60] = f(m.bottleneck[0].bias)
-            w2 = torch.zeros(64, 64, device=dev)
-            w2[:60, :60] = f(m.bottleneck[1].weight)
-            b2 = torch.zeros(64, device=dev)
-            b2[:60] = f(m.bottleneck[1].bias)
-        F1 = BottleneckFunction.apply(tc, float(m.global_res_scale), torch.cat(feats, 1), F0, w1, b1, w2, b2)
+            if m.global_bottleneck_mode == "conv":
+                w2, b2 = packing.pack_conv(m.bottleneck[1].weight, m.bottleneck[1].bias, torch.arange(60, device=dev), 64, 64)
+            else:
+                w2 = torch.zeros(64, 64, device=dev)
+                w2[:60, :60] = f(m.bottleneck[1].weight)
+                b2 = torch.zeros(64, device=dev)
+                b2[:60] = f(m.bottleneck[1].bias)
+        F1 = BottleneckFunction.apply(tc, float(m.global_res_scale), geom if m.global_bottleneck_mode == "conv" else None,
+                                      torch.cat(feats, 1), F0, w1, b1, w2, b2)
         return TailFunction.apply(spec, dict(sc, tail_only=True), geom, F1, F0, *flat)
     return TailFunction.apply(spec, sc, geom, X, F0, *flat)

@@ -251,7 +251,7 @@ class Executor:
 
 class ExecutorN(Executor):
     """RDSTSR_N (rdst_variations.py:824-1112) with the global bottleneck in 'mlp' mode: the outputs of all RDSTBs are
-    concatenated channel-wise and reduced by two Linears (:1071-1079); `norm` / `conv_after_body` are not on its path."""
+    concatenated channel-wise and reduced by two Linears ('mlp', :1071-1079) or a 1x1 + a 3x3 conv ('conv', :1080-1082); `norm` / `conv_after_body` are not on its path."""
 
     def _weights(self, device):
         fresh = self._packed is None
@@ -263,14 +263,20 @@ class ExecutorN(Executor):
                 f = lambda t: t.detach().float()
                 pos = torch.cat([torch.arange(60, device=device) + 64 * i for i in range(n)])     # real channel -> cat column
                 w1 = torch.zeros(64, 64 * n, device=device)
-                w1[:60, pos] = f(m.bottleneck[0].weight)
+                w1[:60, pos] = f(m.bottleneck[0].weight).reshape(60, 60 * n)      # Linear weight or 1x1 conv filter
                 b1 = torch.zeros(64, device=device)
                 b1[:60] = f(m.bottleneck[0].bias)
-                w2 = torch.zeros(64, 64, device=device)
-                w2[:60, :60] = f(m.bottleneck[1].weight)
-                b2 = torch.zeros(64, device=device)
-                b2[:60] = f(m.bottleneck[1].bias)
-                P["bn_w1"], P["bn_b1"], P["bn_w2"], P["bn_b2"] = w1.contiguous(), b1, w2.contiguous(), b2
+                P["bn_w1"], P["bn_b1"] = w1.contiguous(), b1
+                if m.global_bottleneck_mode == "conv":
+                    id60 = torch.arange(60, device=device)
+                    P["bn_w2"], P["bn_b2"] = packing.pack_conv(m.bottleneck[1].weight, m.bottleneck[1].bias, id60, 64, 64)
+                    P["bn_img2"] = packing.conv_tc_image(P["bn_w2"])
+                else:
+                    w2 = torch.zeros(64, 64, device=device)
+                    w2[:60, :60] = f(m.bottleneck[1].weight)
+                    b2 = torch.zeros(64, device=device)
+                    b2[:60] = f(m.bottleneck[1].bias)
+                    P["bn_w2"], P["bn_b2"] = w2.contiguous(), b2
         return P
 
     def _block_done(self, index, trunk, T):
@@ -286,6 +292,10 @@ class ExecutorN(Executor):
         tmp = ws["FN"]
         call("rdst_linear_fwd", ptr(self._cat), 64 * n, ptr(P["bn_w1"]), ptr(P["bn_b1"]), None, 0, ptr(tmp), 64,
              T, 64 * n, 64, 0, 0, 1.0, dt, st)
-        call("rdst_linear_fwd", ptr(tmp), 64, ptr(P["bn_w2"]), ptr(P["bn_b2"]), ptr(ws["F0"]), 64, ptr(ws["F1"]), 64,
-             T, 64, 64, 0, 0, float(m.global_res_scale), dt, st)
+        if m.global_bottleneck_mode == "conv":
+            self._conv(tmp, 64, P["bn_w2"], P["bn_img2"], P["bn_b2"], ws["F0"], 64, ws["F1"], 64,
+                       B, H, W, 64, 64, float(m.global_res_scale), 0, dt, st)
+        else:
+            call("rdst_linear_fwd", ptr(tmp), 64, ptr(P["bn_w2"]), ptr(P["bn_b2"]), ptr(ws["F0"]), 64, ptr(ws["F1"]), 64,
+                 T, 64, 64, 0, 0, float(m.global_res_scale), dt, st)
         return ws["F1"]

@@ -253,8 +253,8 @@ class RDSTSR(nn.Module):
 
 class RDSTSR_N(RDSTSR):
     """Same constructor signature as the reference RDSTSR_N (rdst_variations.py:850-867).  Supported: the E1 envelope of
-    RDSTSR plus global_bottleneck=True, global_bottleneck_ratio=1, global_bottleneck_mode='mlp' (cat of all RDSTB outputs
-    -> Linear(60n, 60) -> Linear(60, 60), :995-1002, :1071-1079).  As in the reference, `norm` and `conv_after_body` are
+    RDSTSR plus global_bottleneck=True, global_bottleneck_ratio=1, global_bottleneck_mode 'mlp' (cat of all RDSTB outputs
+    -> Linear(60n, 60) -> Linear(60, 60), :995-1002, :1071-1079) or 'conv' (-> 1x1 conv 60n->60 -> 3x3 conv 60->60, :1003-1007, :1080-1082).  As in the reference, `norm` and `conv_after_body` are
     registered (they are in the state_dict) but not used by the forward, so they receive no gradient."""
 
     def __init__(self, img_size=48, patch_size=1, in_chans=1, sr_scale=2, embed_dim=60,
@@ -284,10 +284,14 @@ class RDSTSR_N(RDSTSR):
                          precision=precision)
         if not global_bottleneck: _unsupported("RDSTSR_N with global_bottleneck=False")
         if float(global_bottleneck_ratio) != 1.0: _unsupported(f"global_bottleneck_ratio={global_bottleneck_ratio}")
-        if global_bottleneck_mode != 'mlp': _unsupported(f"global_bottleneck_mode={global_bottleneck_mode!r}")
+        if global_bottleneck_mode not in ('mlp', 'conv'): _unsupported(f"global_bottleneck_mode={global_bottleneck_mode!r}")
         self.global_bottleneck_mode, self.do_global_bottleneck = global_bottleneck_mode, True
         del self.feature_last_operation                       # not an attribute of the reference RDSTSR_N
-        self.bottleneck = nn.Sequential(nn.Linear(embed_dim * self.num_blocks, embed_dim), nn.Linear(embed_dim, embed_dim))
+        if global_bottleneck_mode == 'mlp':                   # :998-1002
+            self.bottleneck = nn.Sequential(nn.Linear(embed_dim * self.num_blocks, embed_dim), nn.Linear(embed_dim, embed_dim))
+        else:                                                 # :1003-1007: 1x1 conv, then 3x3 conv (default_conv: same padding)
+            self.bottleneck = nn.Sequential(nn.Conv2d(embed_dim * self.num_blocks, embed_dim, 1),
+                                            nn.Conv2d(embed_dim, embed_dim, 3, padding=1))
         self.bottleneck.apply(self._init_weights)
         # registration order of the reference: ... body, norm, bottleneck, conv_after_body, tail
         order = list(self._modules)

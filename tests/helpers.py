@@ -91,7 +91,7 @@ def make_swinir(c, precision="fp32"):
 
 
 # ---- RDSTSR_N (global bottleneck): fixtures from oracle/gen_golden_rdstn.py ----
-RDSTN_CASES = ["rdstn_e1_x4_40x32", "rdstn_2blk_x2_16x24_b2"]
+RDSTN_CASES = ["rdstn_e1_x4_40x32", "rdstn_2blk_x2_16x24_b2", "rdstn_conv_3blk_x4_16x16"]
 
 
 def load_rdstn_case(name):
@@ -108,11 +108,13 @@ def load_rdstn_case(name):
     sd["add_mean.weight"][:] = 1
     sd = fill_state_dict(sd, int(g["meta_wseed"]), True)
     x = synth_input(tuple(int(v) for v in g["shape"]), int(g["meta_xseed"]))
-    return dict(g=g, sd=sd, x=x, blocks=blocks, scale=scale)
+    mode = "conv" if sd["bottleneck.0.weight"].dim() == 4 else "mlp"
+    return dict(g=g, sd=sd, x=x, blocks=blocks, scale=scale, mode=mode)
 
 
 def make_rdstn(c, precision="fp32"):
     from rdst_b200 import network
     b = c["blocks"]
     return network.RDSTSR_N(img_size=24, sr_scale=c["scale"], dense_layer_depths=[2] * b, num_heads=[6] * b,
-                            window_size=[8] * b, rdb_depths=[3] * b, mlp_ratio=2., pre_norm=True, precision=precision)
+                            window_size=[8] * b, rdb_depths=[3] * b, mlp_ratio=2., pre_norm=True,
+                            global_bottleneck_mode=c.get("mode", "mlp"), precision=precision)

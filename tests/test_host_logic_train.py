@@ -69,11 +69,13 @@ def test_swinir_training_chain_on_cpu(precision):
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_rdstn_training_chain_on_cpu(precision):
+@pytest.mark.parametrize("name", ["rdstn_2blk_x2_16x24_b2", "rdstn_conv_3blk_x4_16x16"])
+def test_rdstn_training_chain_on_cpu(name, precision):
     from rdst_b200 import autograd
-    c = helpers.load_rdstn_case("rdstn_2blk_x2_16x24_b2")
+    c = helpers.load_rdstn_case(name)
     m = helpers.make_rdstn(c, precision)
-    target = torch.rand(2, 1, 32, 48, generator=torch.Generator().manual_seed(5))
-    _check(m, lambda mod, xx: autograd.forward_with_grad(mod._exec, xx), c["sd"], c["x"], target,
-           lambda p, xx: O.forward(p, xx, 2))
+    s, x = c["scale"], c["x"]
+    target = torch.rand(x.shape[0], 1, x.shape[2] * s, x.shape[3] * s, generator=torch.Generator().manual_seed(5))
+    _check(m, lambda mod, xx: autograd.forward_with_grad(mod._exec, xx), c["sd"], x, target,
+           lambda p, xx: O.forward(p, xx, s))
     assert m.norm.weight.grad is None and m.conv_after_body.weight.grad is None      # unused by this forward

@@ -49,8 +49,10 @@ def test_factory_selects_variant():
     m = rdst_b200.make_RDSTSR(types.SimpleNamespace(**base))
     assert isinstance(m, network.RDSTSR_N)
     assert [k for k, _, _ in helpers.swinir_manifest("rdstn_e1_x4_40x32")] == list(m.state_dict().keys())
-    with pytest.raises(NotImplementedError, match="global_bottleneck_mode"):
-        rdst_b200.make_RDSTSR(types.SimpleNamespace(**dict(base, rdst_global_bottleneck_mode='conv')))
+    mc = rdst_b200.make_RDSTSR(types.SimpleNamespace(**dict(base, rdst_global_bottleneck_mode='conv')))
+    assert tuple(mc.bottleneck[0].weight.shape) == (60, 480, 1, 1) and tuple(mc.bottleneck[1].weight.shape) == (60, 60, 3, 3)
+    with pytest.raises(NotImplementedError, match="global_bottleneck_ratio"):
+        rdst_b200.make_RDSTSR(types.SimpleNamespace(**dict(base, rdst_global_bottleneck_ratio=0.5)))
     m2 = rdst_b200.make_RDSTSR(types.SimpleNamespace(**dict(base, rdst_global_bottleneck=False)))
     assert type(m2) is network.RDSTSR
 
@@ -73,10 +75,11 @@ def test_gpu_matches_reference_golden(name, precision, tol):
 
 @pytest.mark.gpu
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
-def test_gpu_training_gradients_match_oracle_autograd(precision):
+@pytest.mark.parametrize("name", ["rdstn_2blk_x2_16x24_b2", "rdstn_conv_3blk_x4_16x16"])
+def test_gpu_training_gradients_match_oracle_autograd(name, precision):
     """Gradients through the bottleneck branch; `norm` / `conv_after_body` are unused by this forward and get none."""
     from test_swinir import _grad_check
-    c = helpers.load_rdstn_case("rdstn_2blk_x2_16x24_b2")
+    c = helpers.load_rdstn_case(name)
     x, s = c["x"], c["scale"]
     target = torch.rand(x.shape[0], 1, x.shape[2] * s, x.shape[3] * s, generator=torch.Generator().manual_seed(5))
     p = {k: (v.clone().double().requires_grad_(True) if v.is_floating_point() else v) for k, v in c["sd"].items()}
