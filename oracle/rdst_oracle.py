@@ -159,7 +159,8 @@ def count_blocks(sd):
     return n
 
 
-def forward(sd, x, sr_scale=4, rnd=None, taps=None, global_res_scale=1.0, feature_last_operation=True):
+def forward(sd, x, sr_scale=4, rnd=None, taps=None, global_res_scale=1.0, feature_last_operation=True,
+            rrdb_residual_scale=1.0):
     """Whole network, E1 envelope.  sd: reference state_dict (any float dtype); x: (B,1,H,W).
     `rnd(t, tag)` optionally emulates reduced-precision storage points; `taps` (dict) collects intermediates.
     [rdst_variations.py:1326-1360]"""
@@ -176,7 +177,18 @@ def forward(sd, x, sr_scale=4, rnd=None, taps=None, global_res_scale=1.0, featur
         taps["head"] = x0.clone()
         taps["embed"] = t.clone()
     feats = []
-    for i in range(count_blocks(sd)):
+    estsr = "body.0.body.0.conv.weight" in sd
+    if estsr:
+        # ESTSR [rdst_variations.py:783-812]: body.i = RRDSTB = RDSTBs + 3x3 conv * rrdb_residual_scale + shortcut [:548-555];
+        # conv_after_body exists in the state_dict but is not used by that forward
+        feature_last_operation = False
+        for i in range(count_blocks(sd)):
+            short, j = t, 0
+            while f"body.{i}.body.{j}.conv.weight" in sd:
+                t = rdstb(t, H, W, sd, f"body.{i}.body.{j}.", rnd=rnd)
+                j += 1
+            t = map_to_tokens(conv3x3(tokens_to_map(t, H, W), sd, f"body.{i}.conv.")) * rrdb_residual_scale + short
+    for i in range(0 if estsr else count_blocks(sd)):
         t = rdstb(t, H, W, sd, f"body.{i}.", rnd=rnd)
         feats.append(t)
         if taps is not None:

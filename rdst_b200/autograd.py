@@ -806,6 +806,36 @@ def forward_with_grad_swinir(executor, x):
     return out / rng + mean
 
 
+class ConvResidualFunction(torch.autograd.Function):
+    """Closing step of an RRDSTB (rdst_variations.py:553-555):  out = scale * conv3x3(X) + S  on [T][64] maps."""
+
+    @staticmethod
+    def forward(ctx, tc, scale, geom, X, S, w, b):
+        e, _ = _f32(X.device)
+        _MODE.tc = tc
+        with _on(X.device):
+            X = X.contiguous()
+            out = e(X.shape[0], 64)
+            conv(X, w, b, out, *geom, 64, 64, scale=scale, resid=S.contiguous())
+        ctx.tc, ctx.scale, ctx.geom, ctx.saved = tc, scale, geom, (X, w)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        X, w = ctx.saved
+        e, z = _f32(dout.device)
+        _MODE.tc = ctx.tc
+        with _on(dout.device):
+            dout = dout.contiguous()
+            dy = dout if ctx.scale == 1.0 else dout * ctx.scale
+            gw, gb = torch.zeros_like(w), z(64)
+            gemm_tn(dy, X, gw, gb, 64, 9 * 64, (*ctx.geom, 64))
+            dX = e(X.shape[0], 64)
+            conv(dy, conv_dgrad_weight(w), z(64), dX, *ctx.geom, 64, 64)
+        ctx.saved = None
+        return None, None, None, dX, dout, gw, gb
+
+
 class BottleneckFunction(torch.autograd.Function):
     """Global bottleneck 'mlp' of RDSTSR_N (rdst_variations.py:1071-1079, 1092-1093) on the [T][64n] concatenation of the RDSTB
     outputs:  F1 = grs * Linear2(Linear1(cat)) + F0."""
@@ -865,11 +895,17 @@ def forward_with_grad(executor, x):
     flat, spec = pack_head(m, dev)
     F0, X = HeadFunction.apply(spec, sc, x.detach().to(torch.float32).contiguous(), *flat)
     feats = []
-    for blk in m.body:
-        bs = dict(block_layout(m, blk), tc=tc)
-        lff_w, lff_b = pack_lff(blk, dev)
-        X = BlockFunction.apply(bs, geom, X, lff_w, lff_b, *block_params(blk))
-        feats.append(X)
+    nested = hasattr(m.body[0], "residual_scale")            # ESTSR: body.i is an RRDSTB = RDSTBs + conv + shortcut
+    for grp in m.body:
+        short = X
+        for blk in (grp.body if nested else [grp]):
+            bs = dict(block_layout(m, blk), tc=tc)
+            lff_w, lff_b = pack_lff(blk, dev)
+            X = BlockFunction.apply(bs, geom, X, lff_w, lff_b, *block_params(blk))
+            feats.append(X)
+        if nested:
+            cw, cb = pack_conv64(grp.conv, dev)
+            X = ConvResidualFunction.apply(tc, float(grp.residual_scale), geom, X, short, cw, cb)
     flat, spec = pack_tail(m, dev)
     if getattr(m, "do_global_bottleneck", False):            # RDSTSR_N: cat -> two Linears; norm / conv_after_body unused
         n = len(feats)

@@ -55,7 +55,7 @@ class Executor:
             return self._packed
         with torch.no_grad():
             P = {"blocks": []}
-            for blk in m.body:
+            for blk in self._rdstbs(m):
                 B = {"dstl": []}
                 c = packing.EMBED
                 for dstl in blk.body:
@@ -161,6 +161,7 @@ class Executor:
         call("rdst_head_fwd", ptr(xin), P["in_scale"], P["in_bias"], ptr(P["head_w"]), ptr(P["head_b"]),
              ptr(P["pe_g"]), ptr(P["pe_b"]), ptr(ws["F0"]), 64, ptr(D[cur]), 160, B, H, W, dt, st)
         for bi, blk in enumerate(P["blocks"]):
+            self._block_start(bi, D[cur], T, ws)
             for j, ds in enumerate(blk["dstl"]):
                 src, lds = D[cur], 160
                 t = ds["tail"]
@@ -179,7 +180,7 @@ class Executor:
             self._conv(D[cur], 160, blk["lff_w"], blk["lff_img"], blk["lff_b"], D[cur], 160, D[1 - cur], 160,
                        B, H, W, 160, 64, float(m.rdb_residual_scale), 0, dt, st)
             cur = 1 - cur
-            self._block_done(bi, D[cur], T)
+            self._block_done(bi, D[cur], dict(P=P, ws=ws, B=B, H=H, W=W, T=T, dt=dt, st=st))
         feat = self._deep_features(D[cur], P, ws, B, H, W, T, dt, st)
         h, w_ = H, W
         for (uw, ub), uimg, buf in zip(P["up"], P["up_img"], ws["UP"]):
@@ -196,8 +197,15 @@ class Executor:
                  ptr(out), B, h, w_, 64, dt, st)
         return out if (given or x.dtype == torch.float32) else out.to(x.dtype)
 
-    def _block_done(self, index, trunk, T):
-        """Hook after RDSTB `index` (trunk = dense buffer whose first 64 columns hold the block output)."""
+    def _rdstbs(self, m):
+        """The RDSTB modules of the network in execution order."""
+        return list(m.body)
+
+    def _block_start(self, index, trunk, T, ws):
+        """Hook before RDSTB `index` reads the trunk."""
+
+    def _block_done(self, index, trunk, c):
+        """Hook after RDSTB `index` (trunk = dense buffer whose first 64 columns hold the block output; c = launch context)."""
 
     def _deep_features(self, trunk, P, ws, B, H, W, T, dt, st):
         """norm * global_res_scale -> conv_after_body -> + head output  (rdst_variations.py:1337-1350); returns the map
@@ -279,7 +287,8 @@ class ExecutorN(Executor):
                     P["bn_w2"], P["bn_b2"] = w2.contiguous(), b2
         return P
 
-    def _block_done(self, index, trunk, T):
+    def _block_done(self, index, trunk, c):
+        T = c["T"]
         n = len(self._module().body)
         cat = getattr(self, "_cat", None)
         if cat is None or cat.shape != (T, 64 * n) or cat.dtype != trunk.dtype or cat.device != trunk.device:
@@ -299,3 +308,49 @@ class ExecutorN(Executor):
             call("rdst_linear_fwd", ptr(tmp), 64, ptr(P["bn_w2"]), ptr(P["bn_b2"]), ptr(ws["F0"]), 64, ptr(ws["F1"]), 64,
                  T, 64, 64, 0, 0, float(m.global_res_scale), dt, st)
         return ws["F1"]
+
+
+class ExecutorE(Executor):
+    """ESTSR (rdst_variations.py:574-822): RDSTBs grouped into RRDSTBs, each group closed by a 3x3 conv, * rrdb_residual_scale,
+    + the group's input (:548-555); the deep features are norm * global_res_scale + head output (no conv_after_body)."""
+
+    def _rdstbs(self, m):
+        return [r for rr in m.body for r in rr.body]
+
+    def _weights(self, device):
+        fresh = self._packed is None
+        P = super()._weights(device)
+        if fresh or "rr_conv" not in P:
+            m = self._module()
+            with torch.no_grad():
+                id60 = torch.arange(60, device=device)
+                P["rr_conv"], P["rr_end"], P["rr_start"], i = [], {}, set(), 0
+                for g, rr in enumerate(m.body):
+                    w, b = packing.pack_conv(rr.conv.weight, rr.conv.bias, id60, 64, 64)
+                    P["rr_conv"].append((w, packing.conv_tc_image(w), b, float(rr.residual_scale)))
+                    P["rr_start"].add(i)
+                    i += len(rr.body)
+                    P["rr_end"][i - 1] = g
+        return P
+
+    def _block_start(self, index, trunk, T, ws):
+        if index in self._packed["rr_start"]:            # keep the group's input: the RRDSTB shortcut
+            self._short = self._rr_short(T, trunk)               # own buffers: the Swin-block workspaces are in use inside a group
+            self._short.copy_(trunk[:, :64])
+
+    def _rr_short(self, T, like):
+        buf = getattr(self, "_short_buf", None)
+        if buf is None or buf.shape != (T, 64) or buf.dtype != like.dtype or buf.device != like.device:
+            buf = self._short_buf = torch.empty(T, 64, dtype=like.dtype, device=like.device)
+            self._tmp_buf = torch.empty(T, 64, dtype=like.dtype, device=like.device)
+            self._in_buf = torch.empty(T, 64, dtype=like.dtype, device=like.device)
+        return buf
+
+    def _block_done(self, index, trunk, c):
+        P = c["P"]
+        if index in P["rr_end"]:
+            w, img, b, scale = P["rr_conv"][P["rr_end"][index]]
+            self._in_buf.copy_(trunk[:, :64])            # compact [T][64] map, the layout conv_after_body runs on
+            self._conv(self._in_buf, 64, w, img, b, self._short, 64, self._tmp_buf, 64, c["B"], c["H"], c["W"], 64, 64, scale, 0,
+                       c["dt"], c["st"])
+            trunk[:, :64].copy_(self._tmp_buf)

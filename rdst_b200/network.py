@@ -309,6 +309,65 @@ class RDSTSR_N(RDSTSR):
         return self._exec.forward(x, out)
 
 
+class RRDSTB(nn.Module):
+    """Parameter container of rdst_variations.py:464-555: RDSTBs + 3x3 conv ('1conv'), * rrdb_residual_scale, + input."""
+
+    def __init__(self, input_dim, input_resolution, layer_depth, num_heads, mlp_ratio, qkv_bias, qk_scale, growth_rate,
+                 num_blocks_in_rdb, num_blocks_in_rrdb, rrdb_residual_scale):
+        super().__init__()
+        self.residual_scale = rrdb_residual_scale
+        self.body = nn.ModuleList([RDSTB(input_dim, input_resolution, layer_depth, num_heads, mlp_ratio, qkv_bias, qk_scale,
+                                         growth_rate, num_blocks_in_rdb) for _ in range(int(num_blocks_in_rrdb))])
+        self.conv = nn.Conv2d(input_dim, input_dim, 3, 1, 1)
+
+
+class ESTSR(RDSTSR):
+    """Same constructor signature as the reference ESTSR (rdst_variations.py:602-619): residual-in-residual RDSTBs.
+    body.i is an RRDSTB (rrdb_depths[i] RDSTBs + conv); the forward is head -> RRDSTBs -> norm * global_res_scale + head
+    output -> tail (:783-812) -- `conv_after_body` is registered, as in the reference, but not used.  The reference has
+    no factory for this class; it is exported as rdst_b200.ESTSR."""
+
+    def __init__(self, img_size=48, patch_size=1, in_chans=1, sr_scale=2, embed_dim=60,
+                 dense_layer_depths=[2, 2, 2, 2], num_heads=[6, 6, 6, 6],
+                 window_size=[4, 4, 4, 4], rdb_depths=[3, 3, 3, 3],
+                 rrdb_depths=[3, 3, 3, 3], num_rrdb_blocks=4,
+                 mlp_ratio=4., qkv_bias=True, qk_scale=None,
+                 drop_rate=0., attn_drop=0., drop_path_rate=0.,
+                 norm_layer=nn.LayerNorm, ape=False, patch_norm=True,
+                 use_checkpoint=False, resi_connection='1conv',
+                 growth_rate=30, dense_scale=1., dim_modify_mode='tail',
+                 rdb_residual_scale=1., rrdb_residual_scale=1., global_res_scale=1.,
+                 mean=None, std=None,
+                 act_in_conv='leaky_relu', bn_in_conv=None,
+                 scale_free=False, pre_norm=False, precision=None):
+        n = int(num_rrdb_blocks)
+        if not (len(dense_layer_depths) >= n and len(num_heads) >= n and len(window_size) >= n and len(rdb_depths) >= n and
+                len(rrdb_depths) >= n):
+            raise AssertionError("per-RRDSTB lists are shorter than num_rrdb_blocks")
+        super().__init__(img_size=img_size, patch_size=patch_size, in_chans=in_chans, sr_scale=sr_scale, embed_dim=embed_dim,
+                         dense_layer_depths=list(dense_layer_depths)[:n], num_heads=list(num_heads)[:n],
+                         window_size=list(window_size)[:n], rdb_depths=list(rdb_depths)[:n], mlp_ratio=mlp_ratio,
+                         qkv_bias=qkv_bias, qk_scale=qk_scale, drop_rate=drop_rate, attn_drop=attn_drop,
+                         drop_path_rate=drop_path_rate, norm_layer=norm_layer, ape=ape, patch_norm=patch_norm,
+                         use_checkpoint=use_checkpoint, resi_connection=resi_connection, growth_rate=growth_rate,
+                         dense_scale=dense_scale, dim_modify_mode=dim_modify_mode, rdb_residual_scale=rdb_residual_scale,
+                         global_res_scale=global_res_scale, mean=mean, std=std, act_in_conv=act_in_conv,
+                         bn_in_conv=bn_in_conv, scale_free=scale_free, pre_norm=pre_norm, feature_last_operation=False,
+                         precision=precision)
+        img = (img_size, img_size) if isinstance(img_size, int) else tuple(img_size)
+        self.body = nn.ModuleList([
+            RRDSTB(embed_dim, img, dense_layer_depths[i], num_heads[i], mlp_ratio, qkv_bias, qk_scale, growth_rate,
+                   rdb_depths[i], rrdb_depths[i], rrdb_residual_scale) for i in range(n)])
+        self.body.apply(self._init_weights)
+        self.rrdb_residual_scale = rrdb_residual_scale
+        self._exec = executor.ExecutorE(self)
+
+    def forward(self, x, sr_scale=None, out=None):
+        if not self._exec.bound_to(self):
+            self._exec = executor.ExecutorE(self)
+        return self._exec.forward(x, out)
+
+
 def make_RDSTSR(paras, mean=None, std=None):
     """Same contract as the reference factory (rdst_variations.py:1369-1457): reads the same `paras.*` names."""
     norm_layer = nn.LayerNorm if paras.rdst_layer_norm else nn.Identity

@@ -118,3 +118,31 @@ def make_rdstn(c, precision="fp32"):
     return network.RDSTSR_N(img_size=24, sr_scale=c["scale"], dense_layer_depths=[2] * b, num_heads=[6] * b,
                             window_size=[8] * b, rdb_depths=[3] * b, mlp_ratio=2., pre_norm=True,
                             global_bottleneck_mode=c.get("mode", "mlp"), precision=precision)
+
+
+# ---- ESTSR (residual-in-residual RDSTBs): fixtures from oracle/gen_golden_estsr.py ----
+ESTSR_CASES = ["estsr_2x2_x4_16x16_b2", "estsr_1x3_x2_8x16"]
+
+
+def load_estsr_case(name):
+    g = np.load(os.path.join(GOLDEN, name + ".npz"))
+    sd = {}
+    for k, shape, dt in swinir_manifest(name):
+        sd[k] = torch.zeros(shape, dtype=dt)
+        if k.endswith("relative_position_index"):
+            sd[k] = O.rel_pos_index()
+        if k.endswith("attn_mask"):
+            sd[k] = O.shift_mask(24, 24)
+    sd["sub_mean.weight"][:] = 1
+    sd["add_mean.weight"][:] = 1
+    sd = fill_state_dict(sd, int(g["meta_wseed"]), True)
+    x = synth_input(tuple(int(v) for v in g["shape"]), int(g["meta_xseed"]))
+    return dict(g=g, sd=sd, x=x, n_rr=int(g["meta_n_rr"]), n_rd=int(g["meta_n_rd"]), scale=int(g["meta_scale"]))
+
+
+def make_estsr(c, precision="fp32"):
+    import rdst_b200
+    n = c["n_rr"]
+    return rdst_b200.ESTSR(img_size=24, sr_scale=c["scale"], dense_layer_depths=[2] * n, num_heads=[6] * n, window_size=[8] * n,
+                           rdb_depths=[3] * n, rrdb_depths=[c["n_rd"]] * n, num_rrdb_blocks=n, mlp_ratio=2., pre_norm=True,
+                           precision=precision)
