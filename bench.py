@@ -5,10 +5,17 @@ per GPU per step = 176 LR slices of 1x40x32 -> 176 x 160x128 HR pixels (3.60 Mpi
 Multi-GPU: every rank super-resolves its own volume (slices are independent; no data-path collective) => weak scaling.
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--precision bf16|fp32]
+                    [--no-extras] [--no-cpu-baseline]
     python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...
 
 Prints ONE JSON line (rank 0).  `value` times the forward with inputs resident in HBM; `e2e` times the module's
-public call with pinned HOST input and a device->host read of the HR result inside the timed region.
+public call (`rdst_b200.make_RDSTSR(paras)` with the reference's E1 paras) with pinned HOST input and a device->host
+read of the HR result inside the timed region.  Before anything is timed, sampled slices of the bench batch are
+checked against the CPU oracle (`parity_max_abs`; the run aborts above the north_star tolerance).  Extra keys (not the
+headline): `rdst_e_cfg3` = the 4-RDSTB "RDST-E" variant on the same batch; `train_cfg4` = one data-parallel training
+step (32 x 1x24x24 per GPU, L1, Adam, NCCL gradient all-reduce inside the step's CUDA graph when N > 1).
+`--impl reference` times the reference's own module on the host cores (the real networks/rdst_variations.py when
+/root/reference is importable, else the oracle port) on the full 176-slice batch.
 """
 import argparse
 import json
@@ -16,7 +23,6 @@ import os
 import subprocess
 import sys
 import tempfile
-import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
@@ -26,7 +32,25 @@ for _p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
 
 import torch  # noqa: E402
 
+import types  # noqa: E402
+
 SLICES, LR_H, LR_W, SCALE = 176, 40, 32, 4
+PARITY_SLICES = [0, 59, 117, 175]                 # sampled slices checked against the oracle before timing
+
+
+def e1_paras(precision=None, blocks=8):
+    """The reference's E1 configuration (config_files/RDST_E1_OASIS_example_SRx4.ini as read by its own
+    utils/param_loader.ParametersLoader; committed as tests/golden/e1_paras.json by oracle/gen_paras.py).
+    blocks=4 gives the light "RDST-E" variant of BASELINE cfg3."""
+    with open(os.path.join(ROOT, "tests", "golden", "e1_paras.json")) as f:
+        p = types.SimpleNamespace(**json.load(f)["paras"])
+    for name in ("rdst_dense_layer_depths", "rdst_num_heads", "rdst_window_size", "rdst_rdb_depths"):
+        setattr(p, name, list(getattr(p, name))[:blocks])
+    if precision is not None:
+        p.rdst_b200_precision = precision
+    return p
+
+
 HR_PIX_PER_VOLUME = SLICES * LR_H * SCALE * LR_W * SCALE
 FLOP_PER_LR_PX = 10_592_280                       # algorithmic, SURVEY 8(d)
 ATTN_FLOP_PER_WINDOW = {60: 2_826_240, 90: 5_621_760, 120: 9_338_880}   # 512 C^2 + 16384 C
@@ -101,23 +125,53 @@ def _dist_setup(n_gpus):
     return world, rank, local
 
 
-def cpu_reference_run(sd, steps, warmup, sample_slices):
-    """Times the CPU restatement of the reference (oracle, PyTorch CPU fp32 -- the same aten ops the reference
-    module executes) on a bounded sample of the workload.  Returns (Mpix/s, seconds per step, threads)."""
+def _reference_module():
+    """The reference's own RDSTSR built by its own factory, if /root/reference is importable here (build container);
+    None on the GPU box.  Returns (module, kind)."""
+    ref = "/root/reference"
+    if not os.path.isdir(os.path.join(ref, "networks")):
+        return None
+    try:
+        for p_ in (os.path.join(ROOT, "oracle", "_shim"), ref):
+            if p_ not in sys.path:
+                sys.path.insert(0, p_)
+        from networks.rdst_variations import make_RDSTSR as ref_make          # noqa: E402
+        torch.manual_seed(0)
+        return ref_make(e1_paras()).eval()
+    except Exception as e:  # noqa: BLE001
+        sys.stderr.write(f"bench.py: reference module not importable ({e!r}); using the oracle port\n")
+        return None
+
+
+def cpu_reference_run(sd, steps, warmup, sample_slices, module=None, budget_s=None):
+    """Times the reference on the host cores: the real module when given, else the CPU restatement (oracle, PyTorch CPU
+    fp32 -- the same aten ops the reference module executes).  With `budget_s`, one probe forward decides how many of
+    the requested slices a step can hold so that warmup + steps stay inside the budget (the batch is halved until it
+    fits; never below 8 slices).  Returns (Mpix/s, seconds per step, threads, slices per step)."""
     import rdst_oracle as O
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
-    x = torch.rand(sample_slices, 1, LR_H, LR_W, generator=torch.Generator().manual_seed(1))
+    xs = torch.rand(sample_slices, 1, LR_H, LR_W, generator=torch.Generator().manual_seed(1))
+    fwd = (lambda x: module(x)) if module is not None else (lambda x: O.forward(sd, x, SCALE))
+    n = sample_slices
     with torch.no_grad():
+        if budget_s is not None:
+            fwd(xs[:4])                                  # first-touch costs (thread pool, allocator) out of the probe
+            t0 = time.perf_counter()
+            fwd(xs[:8])
+            per_slice = (time.perf_counter() - t0) / 8
+            while n > 8 and per_slice * n * (steps + warmup) > budget_s:
+                n = (n + 1) // 2
+        x = xs[:n]
         for _ in range(warmup):
-            O.forward(sd, x, SCALE)
+            fwd(x)
         ts = []
         for _ in range(steps):
             t0 = time.perf_counter()
-            O.forward(sd, x, SCALE)
+            fwd(x)
             ts.append(time.perf_counter() - t0)
     sec = sum(ts) / len(ts)
-    return sample_slices * LR_H * SCALE * LR_W * SCALE / sec / 1e6, sec, threads
+    return n * LR_H * SCALE * LR_W * SCALE / sec / 1e6, sec, threads, n
 
 
 def main():
@@ -128,10 +182,11 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true", help="skip the rdst_e_cfg3 / train_cfg4 extra keys")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
 
-    import helpers
+    import rdst_b200
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     config = {"workload": f"RDST-E1 x4 inference, {SLICES} synthetic OASIS LR slices 1x{LR_H}x{LR_W} per GPU per step "
@@ -144,18 +199,26 @@ def main():
     if args.impl == "reference":
         if rank != 0:
             return
-        m = helpers.make_module(8, SCALE, "fp32")
-        sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
-        sample = 8
-        steps, warm = max(1, min(args.steps, 5)), max(1, min(args.warmup, 2))
-        val, sec, threads = cpu_reference_run(sd, steps, warm, sample)
+        ref_m = _reference_module()
+        torch.manual_seed(0)
+        sd = None
+        if ref_m is None:
+            m = rdst_b200.make_RDSTSR(e1_paras("fp32"))
+            sd = {k: v.detach().clone() for k, v in m.state_dict().items()}
+        steps, warm = max(1, args.steps), max(0, args.warmup)
+        val, sec, threads, n_used = cpu_reference_run(sd, steps, warm, SLICES, ref_m,
+                                                       budget_s=float(os.environ.get("RDST_BENCH_REF_BUDGET_S", "240")))
+        kind = "reference" if ref_m is not None else "port"
         line = {"impl": "reference", "metric": "HR output Mpix/s (RDST-E1 x4 inference)", "value": round(val, 4),
                 "unit": "Mpix/s", "n_gpus": args.gpus, "steps": steps, "warmup": warm,
                 "ms_per_step": round(sec * 1e3, 2), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic", "config": config,
-                "cpu_baseline": {"value": round(val, 4), "unit": "Mpix/s", "cores": threads, "kind": "port",
-                                 "sample": f"{sample} of {SLICES} slices per step (oracle = PyTorch-CPU restatement of "
-                                           "the reference module; the Python reference itself cannot travel to the box)"},
+                "cpu_baseline": {"value": round(val, 4), "unit": "Mpix/s", "cores": threads, "kind": kind,
+                                 "sample": f"{n_used} of {SLICES} slices per step, one forward of batch {n_used} ("
+                                           + ("the reference module networks/rdst_variations.py built by its own make_RDSTSR"
+                                              if kind == "reference" else
+                                              "oracle = PyTorch-CPU restatement of the reference module; the Python "
+                                              "reference itself cannot travel to the box") + ")"},
                 "e2e": {"value": round(val, 4), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
         print(json.dumps(line))
         return
@@ -166,11 +229,25 @@ def main():
     torch.cuda.set_device(dev)
     from rdst_b200 import executor as ex_mod
     torch.manual_seed(0)
-    m = helpers.make_module(8, SCALE, args.precision).to(dev).eval()
+    m = rdst_b200.make_RDSTSR(e1_paras(args.precision)).to(dev).eval()      # the reference-facing factory call
     x_host = torch.rand(SLICES, 1, LR_H, LR_W, generator=torch.Generator().manual_seed(1 + rank)).pin_memory()
     x_dev = x_host.to(dev)
     y_host = torch.empty(SLICES, 1, LR_H * SCALE, LR_W * SCALE).pin_memory()
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+
+    # ---- parity gate: sampled slices of THIS batch against the CPU oracle (checker only; nothing here is timed)
+    parity = None
+    if rank == 0:
+        import rdst_oracle as O
+        with torch.no_grad():
+            y_chk = m(x_dev).cpu()
+            sd_cpu = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
+            ref_chk = O.forward(sd_cpu, x_host[PARITY_SLICES].clone(), SCALE)
+        parity = float((y_chk[PARITY_SLICES] - ref_chk).abs().max())
+        tol = 1e-2 if args.precision == "bf16" else 1e-4
+        if not (parity < tol):
+            raise SystemExit(f"bench.py: parity gate failed: max|y - oracle| = {parity:.3e} >= {tol} on slices {PARITY_SLICES}")
+        del y_chk
 
     launches = [0]
     ktime = {"events": [], "on": False}
@@ -242,11 +319,16 @@ def main():
     ms_e2e = run(step_e2e, args.steps)
     barrier()
 
-    t = torch.tensor([ms_total, ms_e2e], device=dev, dtype=torch.float64)
+    # ---- extra keys (not the headline): RDST-E (cfg3 model) on the same batch, and the cfg4 training step
+    extras = {}
+    if not args.no_extras and args.precision == "bf16":
+        extras = _extras(args, world, rank, dev, x_dev, run, barrier)
+
+    t = torch.tensor([ms_total, ms_e2e] + [extras.get(k, 0.0) for k in ("_e_ms", "_train_ms")], device=dev, dtype=torch.float64)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e = float(t[0]), float(t[1])
+    ms_total, ms_e2e, e_ms, train_ms = (float(v) for v in t)
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
@@ -267,12 +349,14 @@ def main():
         ach = ATTN_FLOP_PER_WINDOW[120] * nwin / avg_s / 1e12
         alg_bytes = 2 * nwin * 64 * 128 * 2                  # read + write of [T][128] bf16 rows
         traffic = None
-        try:
-            with open(os.path.join(ROOT, "profiles", "r1_traffic.json")) as f:
-                tj = json.load(f)["stl_attn_kernel<120>"]
-            traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
-        except Exception:  # noqa: BLE001
-            pass
+        for tf_name in ("r2_traffic.json", "r1_traffic.json"):
+            try:
+                with open(os.path.join(ROOT, "profiles", tf_name)) as f:
+                    tj = json.load(f)["stl_attn_kernel<120>"]
+                traffic = tj["dram_read_bytes"] + tj["dram_write_bytes"]
+                break
+            except Exception:  # noqa: BLE001
+                pass
         roof = {"bound": "tensor", "kernel": "stl_attn_kernel<120> (fused LN+QKV+QK^T+softmax+PV+proj, one launch)",
                 "achieved": round(ach, 2), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(ach / tf_peak, 4),
                 "traffic": traffic, "peak_source": f"{which} (bf16_tflops_sustained)",
@@ -287,21 +371,79 @@ def main():
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if args.precision == "bf16" else "f32", "data": "synthetic", "config": config,
             "clocks": clocks, "gpu_launches": n_launch,
+            "parity_max_abs": parity, "parity_slices": PARITY_SLICES,
             "e2e": {"value": round(e2e_val, 2), "unit": "Mpix/s", "h2d_bytes_per_step": x_host.numel() * 4,
                     "d2h_bytes_per_step": y_host.numel() * 4},
             "whole_net_tflops": round(whole, 2), "whole_net_frac_of_tensor_peak": round(whole / tf_peak / world, 4)}
     if roof:
         line["roofline"] = roof
+    if e_ms > 0:
+        line["rdst_e_cfg3"] = {"what": "RDST-E (4 RDSTBs) x4 bf16, same 176-slice batch per GPU, inputs resident",
+                               "ms_per_step": round(e_ms, 3),
+                               "value": round(world * HR_PIX_PER_VOLUME / (e_ms * 1e-3) / 1e6, 2), "unit": "Mpix/s"}
+    if train_ms > 0:
+        line["train_cfg4"] = dict(extras["_train_info"], ms_per_step=round(train_ms, 3),
+                                  value=round(world * 32 * 96 * 96 / (train_ms * 1e-3) / 1e6, 3), unit="HR Mpix/s")
     if world == 1 and not args.no_cpu_baseline:
         sd = {k: v.detach().cpu().clone() for k, v in m.state_dict().items()}
-        val, sec, threads = cpu_reference_run(sd, 3, 1, 8)
+        val, sec, threads, n_used = cpu_reference_run(sd, 2, 1, 32, budget_s=25.0)
         line["cpu_baseline"] = {"value": round(val, 4), "unit": "Mpix/s", "cores": threads, "kind": "port",
-                                "sample": f"8 of {SLICES} slices per step, 3 steps, {sec:.2f} s/step "
+                                "sample": f"{n_used} of {SLICES} slices per step, 2 steps, {sec:.2f} s/step "
                                           "(oracle = PyTorch-CPU restatement of the reference module)"}
     print(json.dumps(line))
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()
+
+
+def _extras(args, world, rank, dev, x_dev, run, barrier):
+    """cfg3 model on the bench batch and the cfg4 training step (device time, ms per step, this rank)."""
+    import rdst_b200
+    out = {}
+    torch.manual_seed(0)
+    me = rdst_b200.make_RDSTSR(e1_paras("bf16", blocks=4)).to(dev).eval()
+
+    def step_e():
+        with torch.no_grad():
+            me(x_dev)
+
+    for _ in range(3):
+        step_e()
+    barrier()
+    out["_e_ms"] = run(step_e, args.steps) / args.steps
+    del me
+    # ---- cfg4: one data-parallel training step, whole step (fwd, L1, bwd, NCCL all-reduce, Adam) as one CUDA graph
+    from rdst_b200 import ddp as rddp, train as rtrain
+    torch.manual_seed(0)
+    mt = rdst_b200.make_RDSTSR(e1_paras("bf16")).to(dev).train()
+    g = torch.Generator(device=dev).manual_seed(100 + rank)
+    xb = torch.rand(32, 1, 24, 24, device=dev, generator=g)
+    yb = torch.rand(32, 1, 96, 96, device=dev, generator=g)
+    opt = torch.optim.Adam([p for p in mt.parameters() if p.requires_grad], lr=1e-4, betas=(0.9, 0.99), eps=1e-8,
+                           capturable=True, fused=True)
+    reducer = rddp.BucketedAllReduce(mt) if world > 1 else None
+    stepper = rtrain.GraphedTrainStep(mt, opt, xb, yb, reducer=reducer)
+    losses = []
+    for _ in range(3):
+        losses.append(float(stepper(xb, yb)))
+    barrier()
+    steps = max(args.steps, 5)
+    e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+    e0.record()
+    for _ in range(steps):
+        loss = stepper(xb, yb)
+    e1.record()
+    torch.cuda.synchronize()
+    losses.append(float(loss))
+    out["_train_ms"] = e0.elapsed_time(e1) / steps
+    out["_train_info"] = {"what": "RDST-E1 x4 training step, 32 x 1x24x24 per GPU, L1 loss, Adam, bf16 tensor-core GEMMs, "
+                                  "whole step one CUDA graph" + (", NCCL gradient all-reduce per link inside the graph"
+                                                                 if world > 1 else ""),
+                          "steps": steps, "loss_first": round(losses[0], 5), "loss_last": round(losses[-1], 5)}
+    if reducer is not None:
+        reducer.remove()
+    barrier()
+    return out
 
 
 if __name__ == "__main__":

@@ -772,9 +772,25 @@ class SwinIRTailFunction(torch.autograd.Function):
         return None, None, dX, dF1, gg, gb, g_cabw, g_cabb, g_upw, g_upb
 
 
+def _check_trainable(m):
+    """The training kernels read the parameters through raw pointers as contiguous fp32: anything else (a model cast with
+    .half() / .bfloat16() / .double(), a non-contiguous view) must fail loudly instead of being reinterpreted."""
+    for name, p in m.named_parameters():
+        if p.dtype != torch.float32 or not p.is_contiguous():
+            raise TypeError(f"rdst_b200: training needs contiguous float32 parameters; {name} is {p.dtype}"
+                            f"{'' if p.is_contiguous() else ', non-contiguous'} (keep the module in fp32: precision='bf16' "
+                            "selects bf16 tensor-core GEMMs with fp32 master weights)")
+
+
 def forward_with_grad_swinir(executor, x):
     """Training forward of rdst_b200.SwinIR: head -> RSTB chain -> tail, same machinery as forward_with_grad."""
     m = executor._module()
+    _check_trainable(m)
+    if m.training and float(m.drop_path_rate) > 0:
+        # the reference applies per-sample stochastic depth (DropPath, swin_transformer_sr.py:199,271-272,686) in train()
+        # mode; silently training without it would be a different regularisation
+        raise NotImplementedError("rdst_b200.SwinIR: stochastic depth (drop_path_rate > 0) is not implemented for training; "
+                                  "construct with drop_path_rate=0 (ini: sir_drop_path_rate = 0.) or call .eval()")
     tc = m.precision == "bf16"
     if tc and not _lib.load().rdst_has_tcgen05():
         raise RuntimeError("rdst_b200: precision='bf16' training needs the tcgen05 kernels (sm_100a device)")
@@ -883,6 +899,7 @@ class BottleneckFunction(torch.autograd.Function):
 
 def forward_with_grad(executor, x):
     m = executor._module()
+    _check_trainable(m)
     tc = m.precision == "bf16"
     if tc and not _lib.load().rdst_has_tcgen05():
         raise RuntimeError("rdst_b200: precision='bf16' training needs the tcgen05 kernels (sm_100a device)")

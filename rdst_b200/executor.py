@@ -32,6 +32,7 @@ class Executor:
         self._packed = None
         self._packed_key = None
         self._ws = {}
+        self.last_workspace = None  # the workspace dict of the most recent forward (held by graph owners)
         self.use_tc = True          # bf16 mode: tcgen05 kernels (False = CUDA-core kernels on bf16 storage)
 
     def __deepcopy__(self, memo):
@@ -41,6 +42,7 @@ class Executor:
         self._module = lambda: None
         self._packed = self._packed_key = None
         self._ws = {}
+        self.last_workspace = None
         self.use_tc = True
         return self
 
@@ -111,9 +113,13 @@ class Executor:
                 ups.append(e(t, 64))
                 s //= 2
             ws["UP"] = ups
-            if len(self._ws) > 8:
-                self._ws.clear()
+            # Bounded cache: drop only the oldest shape.  A CUDA graph captured over a workspace keeps its own reference
+            # to the dict (infer.GraphedRDST stores `last_workspace`), so eviction here can never free memory that a live
+            # graph still addresses; every auxiliary buffer of the subclasses lives INSIDE the dict for the same reason.
+            while len(self._ws) > 8:
+                self._ws.pop(next(iter(self._ws)))
             self._ws[key] = ws
+        self.last_workspace = ws
         return ws
 
     # ------------------------------------------------------------------ forward
@@ -288,18 +294,18 @@ class ExecutorN(Executor):
         return P
 
     def _block_done(self, index, trunk, c):
-        T = c["T"]
+        T, ws = c["T"], c["ws"]
         n = len(self._module().body)
-        cat = getattr(self, "_cat", None)
-        if cat is None or cat.shape != (T, 64 * n) or cat.dtype != trunk.dtype or cat.device != trunk.device:
-            cat = self._cat = torch.empty(T, 64 * n, dtype=trunk.dtype, device=trunk.device)
+        cat = ws.get("cat")                # per-workspace (shape, dtype, device) buffer: lives as long as the workspace
+        if cat is None:
+            cat = ws["cat"] = torch.empty(T, 64 * n, dtype=trunk.dtype, device=trunk.device)
         cat[:, 64 * index:64 * index + 64].copy_(trunk[:, :64])       # the reference's torch.cat of the RDSTB outputs
 
     def _deep_features(self, trunk, P, ws, B, H, W, T, dt, st):
         m = self._module()
         n = len(m.body)
         tmp = ws["FN"]
-        call("rdst_linear_fwd", ptr(self._cat), 64 * n, ptr(P["bn_w1"]), ptr(P["bn_b1"]), None, 0, ptr(tmp), 64,
+        call("rdst_linear_fwd", ptr(ws["cat"]), 64 * n, ptr(P["bn_w1"]), ptr(P["bn_b1"]), None, 0, ptr(tmp), 64,
              T, 64 * n, 64, 0, 0, 1.0, dt, st)
         if m.global_bottleneck_mode == "conv":
             self._conv(tmp, 64, P["bn_w2"], P["bn_img2"], P["bn_b2"], ws["F0"], 64, ws["F1"], 64,
@@ -335,22 +341,16 @@ class ExecutorE(Executor):
 
     def _block_start(self, index, trunk, T, ws):
         if index in self._packed["rr_start"]:            # keep the group's input: the RRDSTB shortcut
-            self._short = self._rr_short(T, trunk)               # own buffers: the Swin-block workspaces are in use inside a group
-            self._short.copy_(trunk[:, :64])
-
-    def _rr_short(self, T, like):
-        buf = getattr(self, "_short_buf", None)
-        if buf is None or buf.shape != (T, 64) or buf.dtype != like.dtype or buf.device != like.device:
-            buf = self._short_buf = torch.empty(T, 64, dtype=like.dtype, device=like.device)
-            self._tmp_buf = torch.empty(T, 64, dtype=like.dtype, device=like.device)
-            self._in_buf = torch.empty(T, 64, dtype=like.dtype, device=like.device)
-        return buf
+            if "rr_short" not in ws:                     # own buffers (the Swin-block workspaces are in use inside a group),
+                for k in ("rr_short", "rr_tmp", "rr_in"):        # owned by the workspace dict so that they share its lifetime
+                    ws[k] = torch.empty(T, 64, dtype=trunk.dtype, device=trunk.device)
+            ws["rr_short"].copy_(trunk[:, :64])
 
     def _block_done(self, index, trunk, c):
-        P = c["P"]
+        P, ws = c["P"], c["ws"]
         if index in P["rr_end"]:
             w, img, b, scale = P["rr_conv"][P["rr_end"][index]]
-            self._in_buf.copy_(trunk[:, :64])            # compact [T][64] map, the layout conv_after_body runs on
-            self._conv(self._in_buf, 64, w, img, b, self._short, 64, self._tmp_buf, 64, c["B"], c["H"], c["W"], 64, 64, scale, 0,
+            ws["rr_in"].copy_(trunk[:, :64])             # compact [T][64] map, the layout conv_after_body runs on
+            self._conv(ws["rr_in"], 64, w, img, b, ws["rr_short"], 64, ws["rr_tmp"], 64, c["B"], c["H"], c["W"], 64, 64, scale, 0,
                        c["dt"], c["st"])
-            trunk[:, :64].copy_(self._tmp_buf)
+            trunk[:, :64].copy_(ws["rr_tmp"])

@@ -90,9 +90,12 @@ class GraphedRDST:
             graph = torch.cuda.CUDAGraph()
             with torch.cuda.graph(graph):
                 static_out = self.model(static_in)
-            entry = (graph, static_in, static_out)
+            # the graph addresses the executor's workspace buffers by raw pointer: hold the dict so that the executor's
+            # bounded workspace cache can evict the shape without freeing memory this graph replays on
+            held = getattr(getattr(self.model, "_exec", None), "last_workspace", None)
+            entry = (graph, static_in, static_out, held)
             self._graphs[key] = entry
-        graph, static_in, static_out = entry
+        graph, static_in, static_out, _ = entry
         static_in.copy_(x)
         graph.replay()
         return static_out.clone()

@@ -183,6 +183,8 @@ class RDSTSR(nn.Module):
         if bn_in_conv: _unsupported("bn_in_conv")
         if drop_rate or attn_drop: _unsupported("dropout > 0")
         if not qkv_bias: _unsupported("qkv_bias=False")
+        # the fused MLP kernels and their packed weight images are built for hidden = 2C (Hp = 128 / 192 / 240)
+        if float(mlp_ratio) != 2.0: _unsupported(f"mlp_ratio={mlp_ratio} (the E1 family uses swin_hidden_ratio = 2)")
 
         img = (img_size, img_size) if isinstance(img_size, int) else tuple(img_size)
         self.input_resolution, self.patch_size, self.input_channel = img_size, patch_size, in_chans

@@ -48,6 +48,13 @@ def load_case(name):
     return dict(g=g, blocks=blocks, scale=scale, sd=sd, x=x)
 
 
+def realistic_target(ref, seed=123, sigma=0.0224):
+    """A ground-truth stand-in at realistic SR quality: the reference output + Gaussian noise at ~33 dB PSNR.  Against
+    such a target a 0.01 dB PSNR tolerance bounds the RMS error of the tested output near 1e-3 (against a uniform-random
+    target the check could never fail)."""
+    return ref + sigma * torch.randn(ref.shape, generator=torch.Generator().manual_seed(seed))
+
+
 def make_module(blocks=8, scale=4, precision="fp32", img_size=24):
     import rdst_b200
     return rdst_b200.RDSTSR(img_size=img_size, sr_scale=scale, dense_layer_depths=[2] * blocks,
@@ -87,7 +94,8 @@ def make_swinir(c, precision="fp32"):
     from rdst_b200 import swinir
     return swinir.SwinIR(img_size=c["img_size"], patch_size=1, in_chans=1, embed_dim=60, depths=c["depths"],
                          num_heads=[6] * len(c["depths"]), window_size=8, mlp_ratio=2., upscale=c["upscale"], img_range=1.,
-                         upsampler="pixelshuffledirect", resi_connection="1conv", precision=precision)
+                         upsampler="pixelshuffledirect", resi_connection="1conv", precision=precision,
+                         drop_path_rate=c.get("drop_path_rate", 0.0))
 
 
 # ---- RDSTSR_N (global bottleneck): fixtures from oracle/gen_golden_rdstn.py ----

@@ -67,7 +67,9 @@ def _padded_input(T, c, seed):
     return x.to(torch.bfloat16), cp
 
 
-@pytest.mark.parametrize("c,T", [(60, 128), (60, 1000), (90, 640), (120, 128), (120, 19 * 128 + 64)])
+# the last three cases have more tiles than SMs (148): the persistent multi-tile path, incl. a ragged last tile
+@pytest.mark.parametrize("c,T", [(60, 128), (60, 1000), (90, 640), (120, 128), (120, 19 * 128 + 64),
+                                 (60, 128 * 333 + 17), (90, 128 * 401 + 64), (120, 128 * 590 + 100)])
 @pytest.mark.parametrize("exact", [0, 1])
 def test_fused_mlp(c, T, exact):
     from rdst_b200 import packing
@@ -99,7 +101,12 @@ def test_fused_mlp(c, T, exact):
 
 
 @pytest.mark.parametrize("c,B,H,W,shift", [(60, 2, 16, 24, 0), (60, 2, 16, 24, 4), (90, 1, 24, 24, 4), (120, 1, 8, 8, 4),
-                                            (120, 3, 40, 32, 4), (120, 3, 40, 32, 0), (90, 5, 8, 16, 0)])
+                                            (120, 3, 40, 32, 4), (120, 3, 40, 32, 0), (90, 5, 8, 16, 0),
+                                            # more tiles than SMs (148), shifted and not, odd window counts: the
+                                            # persistent multi-tile path (next-tile prefetch, C=120 landing zone)
+                                            (120, 43, 40, 24, 4), (120, 43, 40, 24, 0), (90, 37, 24, 40, 4),
+                                            (90, 37, 24, 40, 0), (60, 51, 24, 24, 4), (60, 51, 24, 24, 0),
+                                            (120, 1, 264, 264, 4), (90, 1, 264, 264, 4)])
 def test_fused_attention(c, B, H, W, shift):
     from rdst_b200 import packing
     L = _L()

@@ -79,3 +79,28 @@ def test_rdstn_training_chain_on_cpu(name, precision):
     _check(m, lambda mod, xx: autograd.forward_with_grad(mod._exec, xx), c["sd"], x, target,
            lambda p, xx: O.forward(p, xx, s))
     assert m.norm.weight.grad is None and m.conv_after_body.weight.grad is None      # unused by this forward
+
+
+def test_training_guards_fail_loudly():
+    """parameters that are not contiguous fp32 and SwinIR stochastic depth must raise, not train differently."""
+    from rdst_b200 import autograd
+    m = helpers.make_module(1, 4, "bf16").train()
+    m.body[0].conv.weight.data = m.body[0].conv.weight.data.to(torch.bfloat16)
+    with pytest.raises(TypeError, match="contiguous float32"):
+        autograd.forward_with_grad(m._exec, torch.rand(1, 1, 8, 8))
+    c = helpers.load_swinir_case("swinir_x2_16x24_b2")
+    ms = helpers.make_swinir(dict(c, drop_path_rate=0.1), "fp32").train()
+    with pytest.raises(NotImplementedError, match="stochastic depth"):
+        autograd.forward_with_grad_swinir(ms._exec, c["x"])
+    ms.eval()
+    assert ms.drop_path_rate == 0.1          # stored for interface parity; identity at inference, as in the reference
+
+
+def test_mlp_ratio_outside_envelope_raises():
+    import rdst_b200
+    ok = dict(img_size=24, sr_scale=4, dense_layer_depths=[2] * 2, num_heads=[6] * 2, window_size=[8] * 2,
+              rdb_depths=[3] * 2, pre_norm=True, feature_last_operation=True)
+    with pytest.raises(NotImplementedError, match="mlp_ratio"):
+        rdst_b200.RDSTSR(mlp_ratio=4., **ok)
+    with pytest.raises(NotImplementedError, match="mlp_ratio"):
+        rdst_b200.network.RDSTSR_N(mlp_ratio=4., global_bottleneck=True, **{k: v for k, v in ok.items() if k != "feature_last_operation"})
