@@ -277,6 +277,12 @@ int rdst_last_conv_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, flo
 /* Debug hook: when given a device buffer of 128 uint64, CTA 0 of every following rdst_stl_attn_fwd_bf16 launch records
  * clock64() at its phase boundaries (64 stamps per warpgroup).  Pass NULL to switch it off (the default). */
 int rdst_debug_attn_timing(void* device_buffer_128_u64);
+/* Selects the kernel behind rdst_stl_attn_fwd_bf16: 2 (default) = warp-specialised pipeline (csrc/tc_attn2.cu),
+ * 1 = the round-1 lock-step kernel (csrc/tc_attn.cu), kept for A/B timing.  Same arguments, same contract. */
+int rdst_debug_attn_variant(int variant);
+/* Role timelines of CTA 0 of the warp-specialised attention kernel: 5 roles x 256 uint64 (slot 0 unused, then
+ * clock64() stamps in program order of one thread of the role).  NULL switches it off. */
+int rdst_debug_attn2_timing(void* device_buffer_1280_u64);
 int rdst_debug_mlp_timing(void* device_buffer_128_u64);     /* same for rdst_stl_mlp_*_fwd_bf16 */
 int rdst_debug_conv_timing(void* device_buffer_128_u64);    /* same for rdst_conv3x3_fwd_bf16_tc (128 stamps, CTA 0) */
 

@@ -69,6 +69,8 @@ _SIGNATURES = {
     "rdst_last_conv_fwd_bf16_tc": (C.c_int, [_vp, _i64, _vp, _f, _f, _f, _vp, _i, _i, _i, _vp]),
     "rdst_stl_mlp_tail_fwd_bf16": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f, _i64, _i, _i, _vp]),
     "rdst_debug_attn_timing": (C.c_int, [_vp]),
+    "rdst_debug_attn_variant": (C.c_int, [_i]),
+    "rdst_debug_attn2_timing": (C.c_int, [_vp]),
     "rdst_debug_mlp_timing": (C.c_int, [_vp]),
     "rdst_debug_conv_timing": (C.c_int, [_vp]),
     "rdst_umma_selftest": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),

@@ -777,30 +777,17 @@ extern "C" int rdst_debug_attn_timing(void* device_buffer_128_u64) {
   return RDST_OK;
 }
 
-extern "C" int rdst_stl_attn_fwd_bf16(const void* x, int64_t ldx, void* y, int64_t ldy, const void* wqkv_img,
-                                      const void* wproj_img, const float* bqkv, const float* bproj, const float* table,
-                                      int B, int H, int W, int C, int shift, void* stream) {
-  using namespace rdst;
-  RDST_REQUIRE(x && y && wqkv_img && wproj_img && bqkv && bproj && table, "rdst_stl_attn_fwd_bf16: null pointer");
-  RDST_REQUIRE(H > 0 && W > 0 && H % 8 == 0 && W % 8 == 0,
-               "rdst_stl_attn_fwd_bf16: H=%d W=%d must be positive multiples of the window size 8", H, W);
-  RDST_REQUIRE(shift == 0 || shift == 4, "rdst_stl_attn_fwd_bf16: shift must be 0 or 4");
-  RDST_REQUIRE(((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ldx % 8 == 0 && ldy % 8 == 0,
-               "rdst_stl_attn_fwd_bf16: x/y must be 16-byte aligned with row strides multiple of 8 elements");
-  RDST_REQUIRE(x != y, "rdst_stl_attn_fwd_bf16: in-place operation is not supported (windows read shifted neighbours)");
-  if (B <= 0) return RDST_OK;
-  int dev = 0, sms = 148;
-  cudaGetDevice(&dev);
-  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-  cudaStream_t st = (cudaStream_t)stream;
-  int rc;
+namespace rdst {
+// entry used by tc_attn2.cu when the lock-step kernel is selected (rdst_debug_attn_variant(1)); arguments validated there
+int attn_v1_dispatch(const void* x, int64_t ldx, void* y, int64_t ldy, const void* wqkv_img, const void* wproj_img,
+                     const float* bqkv, const float* bproj, const float* table, int B, int H, int W, int C, int shift,
+                     int sms, cudaStream_t st) {
   switch (C) {
-    case 60:  RDST_REQUIRE(ldx >= 64 && ldy >= 64, "ld too small");   rc = launch_attn<60>(x, ldx, y, ldy, wqkv_img, wproj_img, bqkv, bproj, table, B, H, W, shift, sms, st); break;
-    case 90:  RDST_REQUIRE(ldx >= 96 && ldy >= 96, "ld too small");   rc = launch_attn<90>(x, ldx, y, ldy, wqkv_img, wproj_img, bqkv, bproj, table, B, H, W, shift, sms, st); break;
-    case 120: RDST_REQUIRE(ldx >= 128 && ldy >= 128, "ld too small"); rc = launch_attn<120>(x, ldx, y, ldy, wqkv_img, wproj_img, bqkv, bproj, table, B, H, W, shift, sms, st); break;
-    default: set_error("rdst_stl_attn_fwd_bf16: C=%d unsupported (60, 90, 120 with 6 heads)", C); return RDST_E_UNSUPPORTED;
+    case 60:  return launch_attn<60>(x, ldx, y, ldy, wqkv_img, wproj_img, bqkv, bproj, table, B, H, W, shift, sms, st);
+    case 90:  return launch_attn<90>(x, ldx, y, ldy, wqkv_img, wproj_img, bqkv, bproj, table, B, H, W, shift, sms, st);
+    case 120: return launch_attn<120>(x, ldx, y, ldy, wqkv_img, wproj_img, bqkv, bproj, table, B, H, W, shift, sms, st);
   }
-  if (rc) return rc;
-  RDST_CHECK_LAUNCH("rdst_stl_attn_fwd_bf16");
-  return RDST_OK;
+  set_error("rdst_stl_attn_fwd_bf16: C=%d unsupported (60, 90, 120 with 6 heads)", C);
+  return RDST_E_UNSUPPORTED;
 }
+}  // namespace rdst
