@@ -286,6 +286,11 @@ int rdst_debug_attn2_timing(void* device_buffer_1280_u64);
 int rdst_debug_mlp_timing(void* device_buffer_128_u64);     /* same for rdst_stl_mlp_*_fwd_bf16 */
 int rdst_debug_conv_timing(void* device_buffer_128_u64);    /* same for rdst_conv3x3_fwd_bf16_tc (128 stamps, CTA 0) */
 
+/* tcgen05 issue-pattern microbenchmark (timing only, zero operands): `count` MMAs M=128 x N x K=16 issued round-robin over
+ * `chains` accumulators by one lane, then one commit.  out[0] = cycles first issue -> completion, out[1] = issue cycles.
+ * a_tmem: A from TMEM (else shared memory); masked: disable-output-lane form.  Used by tools/umma_bench.py only. */
+int rdst_umma_bench(int N, int chains, int count, int a_tmem, int masked, void* out_2_u64, void* stream);
+
 /* Self-test of the UMMA plumbing: D[M=128][N] = A[128][K] . B[N][K]^T with bf16 inputs, fp32 output.
  * b_mn_major != 0 feeds B from an MN-major shared-memory image.  Used by tests/ only. */
 int rdst_umma_selftest(const void* a_bf16, const void* b_bf16, float* d, int N, int K, int b_mn_major,

@@ -555,7 +555,11 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     }
     fence_proxy_async();
     __syncwarp();
-    if (elect_one()) {
+    {
+      // The whole warp runs the issue loop with warp-uniform values (shuffle / vote results, kernel parameters), and only
+      // the tcgen05 instructions themselves sit under elect.sync: descriptors then live in uniform registers.  Running
+      // the loop on one lane of a divergent branch costs a broadcast "waterfall" per MMA (~60 cycles each, measured).
+      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
       const uint32_t aWqkv = smem_u32(smem + K::OFF_WQKV), aWproj = smem_u32(smem + K::OFF_WPROJ);
       const uint32_t aKV = smem_u32(smem + K::OFF_KV);
       constexpr uint32_t idq = make_idesc_bf16(128, NH, false, false);
@@ -571,51 +575,61 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       // only when ready (probe, no wait): they must never hold up the PV -> S chain.
       int next_q = 0;                  // next head whose qkv has to be issued
       int next_p = 0;                  // next proj block (tile * NHALF + block)
+      auto probe = [&](uint64_t* bar, uint32_t parity) { return __all_sync(0xffffffffu, mbar_test(bar, parity)) != 0; };
       auto qkv_ready = [&](int g) {
         const int n = g / 6, h = g - 6 * n;
-        return h != 0 || mbar_test(&bars[B_XH_READY], n & 1);
+        return h != 0 || probe(&bars[B_XH_READY], n & 1);
       };
       auto issue_qkv = [&](int g) {    // caller guarantees qkv_ready(g) or blocks here
         const int s = g & 1, n = g / 6, h = g - 6 * n;
         if (h == 0) mbar_wait(&bars[B_XH_READY], n & 1);                           // x^ of this tile is in TMEM
         fence_after_sync();
-        const uint32_t wb = aWqkv + h * (NH * CP * 2);
+        if (elect_one()) {
+          const uint32_t wb = aWqkv + h * (NH * CP * 2);
 #pragma unroll
-        for (int ks = 0; ks < CP / 16; ++ks)
-          mma_ts(tmem + K::TM_QKV + 64 * s, tmem + K::TM_XH + ks * 8, make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128), idq, ks > 0);
-        commit(&bars[B_QKV_FULL + s]);
-        if (h == 5) commit(&bars[B_XH_FREE]);                    // x^ may be replaced by the next tile's
+          for (int ks = 0; ks < CP / 16; ++ks)
+            mma_ts(tm + K::TM_QKV + 64 * s, tm + K::TM_XH + ks * 8, make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128), idq, ks > 0);
+          commit(&bars[B_QKV_FULL + s]);
+          if (h == 5) commit(&bars[B_XH_FREE]);                  // x^ may be replaced by the next tile's
+        }
+        __syncwarp();
       };
       auto proj_ready = [&](int k) {
         const int pn = k / K::NHALF, hf = k - pn * K::NHALF;
-        if (hf == 0 && !mbar_test(&bars[B_AP_READY], pn & 1)) return false;
-        return k == 0 || mbar_test(&bars[B_PROJ_DRAINED], (k - 1) & 1);
+        if (hf == 0 && !probe(&bars[B_AP_READY], pn & 1)) return false;
+        return k == 0 || probe(&bars[B_PROJ_DRAINED], (k - 1) & 1);
       };
       auto issue_proj = [&](int k) {
         const int pn = k / K::NHALF, hf = k - pn * K::NHALF;
         if (hf == 0) mbar_wait(&bars[B_AP_READY], pn & 1);
         if (k >= 1) mbar_wait(&bars[B_PROJ_DRAINED], (k - 1) & 1);               // previous block is in registers
         fence_after_sync();
+        if (elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < K::KPROJ / 16; ++ks)
-          mma_ts(tmem + K::TM_PROJ, tmem + K::TM_AP + ks * 8,
-                 make_smem_desc(aWproj + hf * K::NPC * 16 + ks * 2 * (CP * 16), CP * 16, 128), idp, ks > 0);
-        commit(&bars[B_PROJ_FULL]);
-        if (hf == K::NHALF - 1) commit(&bars[B_AP_FREE]);        // the normalised O of this tile has been read
+          for (int ks = 0; ks < K::KPROJ / 16; ++ks)
+            mma_ts(tm + K::TM_PROJ, tm + K::TM_AP + ks * 8,
+                   make_smem_desc(aWproj + hf * K::NPC * 16 + ks * 2 * (CP * 16), CP * 16, 128), idp, ks > 0);
+          commit(&bars[B_PROJ_FULL]);
+          if (hf == K::NHALF - 1) commit(&bars[B_AP_FREE]);      // the normalised O of this tile has been read
+        }
+        __syncwarp();
       };
       auto issue_s = [&](int g) {
         const int s = g & 1;
         mbar_wait(&bars[B_QK_DRAINED + s], (g >> 1) & 1);
         fence_after_sync();
-        const uint32_t aBk = aKV + s * K::KV_BYTES;
+        if (elect_one()) {
+          const uint32_t aBk = aKV + s * K::KV_BYTES;
 #pragma unroll
-        for (int w = 0; w < 2; ++w)
+          for (int w = 0; w < 2; ++w)
 #pragma unroll
-          for (int ks = 0; ks < K::HDP / 16; ++ks)
-            mma_bf16_ts_masked(tmem + K::TM_S + 64 * s, tmem + K::TM_QKV + 64 * s + ks * 8,
-                               make_smem_desc(aBk + w * 1024 + ks * 4096, 2048, 128), ids, ks > 0,
-                               w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
-        commit(&bars[B_S_FULL + s]);
+            for (int ks = 0; ks < K::HDP / 16; ++ks)
+              mma_bf16_ts_masked(tm + K::TM_S + 64 * s, tm + K::TM_QKV + 64 * s + ks * 8,
+                                 make_smem_desc(aBk + w * 1024 + ks * 4096, 2048, 128), ids, ks > 0,
+                                 w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
+          commit(&bars[B_S_FULL + s]);
+        }
+        __syncwarp();
       };
       auto issue_pv = [&](int g) {
         const int s = g & 1;
@@ -623,15 +637,18 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         mbar_wait(&bars[B_V_DRAINED + s], (g >> 1) & 1);                         // V image of this head is in shared memory
         if (g >= 2) mbar_wait(&bars[B_O_FREE + s], ((g - 2) >> 1) & 1);          // O of head g-2 is in registers
         fence_after_sync();
-        const uint32_t aBv = aKV + s * K::KV_BYTES + K::BK_BYTES;
+        if (elect_one()) {
+          const uint32_t aBv = aKV + s * K::KV_BYTES + K::BK_BYTES;
 #pragma unroll
-        for (int w = 0; w < 2; ++w)
+          for (int w = 0; w < 2; ++w)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            mma_bf16_ts_masked(tmem + K::TM_O + 32 * s, tmem + K::TM_S + 64 * s + ks * 8,
-                               make_smem_desc(aBv + w * 1024 + ks * 256, 128, 2048), idv, ks > 0,
-                               w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
-        commit(&bars[B_O_FULL + s]);
+            for (int ks = 0; ks < 4; ++ks)
+              mma_bf16_ts_masked(tm + K::TM_O + 32 * s, tm + K::TM_S + 64 * s + ks * 8,
+                                 make_smem_desc(aBv + w * 1024 + ks * 256, 128, 2048), idv, ks > 0,
+                                 w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
+          commit(&bars[B_O_FULL + s]);
+        }
+        __syncwarp();
       };
       const int NPB = NT * K::NHALF;
       issue_qkv(next_q++);

@@ -134,3 +134,90 @@ extern "C" int rdst_umma_selftest(const void* a_bf16, const void* b_bf16, float*
   RDST_CHECK_LAUNCH("rdst_umma_selftest");
   return RDST_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// tcgen05 issue-pattern microbenchmark (timing only; operands are zeros).  One CTA, one issuing lane: `count` MMAs of
+// M=128, N, K=16 are issued round-robin over `chains` different accumulators (chain c at TMEM column c * N), then one
+// commit; out[0] = cycles from the first issue to the completion barrier, out[1] = cycles spent issuing.
+//   a_tmem != 0: A operand from TMEM (TS mode), else from shared memory (SS);  masked != 0: disable-output-lane form.
+// Answers "what does a short dependent accumulate chain cost" for the window-attention kernel.
+namespace rdst {
+using namespace umma;
+template <int N, int CHAINS, bool TS, bool MASKED>
+__global__ void __launch_bounds__(128) umma_bench_kernel(int reps, unsigned long long* __restrict__ out) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __shared__ uint64_t bar;
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  if (tid == 0) { mbar_init(&bar, 1); fence_mbar_init(); }
+  for (int i = tid; i < 65536 / 16; i += 128) *reinterpret_cast<uint4*>(smem + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  {
+    uint32_t z[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int c = 0; c < 512; c += 8) tmem_st_x8(tmem + ((uint32_t)(warp * 32) << 16) + c, z);
+    wait_st();
+  }
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  if (warp == 0) {
+    // warp-uniform loop, constant descriptors, only the MMAs under elect.sync (the issue pattern of the fused kernels)
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(128, N, false, false);
+    const uint32_t sa = smem_u32(smem), sb = smem_u32(smem) + 32768;
+    const unsigned long long t0 = clock64();
+    for (int r = 0; r < reps; ++r) {
+      if (elect_one()) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          const uint32_t d = tm + (i % CHAINS) * N;
+          const uint64_t db = make_smem_desc(sb + (i & 3) * 4096, N * 16, 128);
+          if (TS) {
+            if (MASKED) mma_bf16_ts_masked(d, tm + 448 + (i & 3) * 8, db, idesc, 1u, (i & 1) ? 0xFFFFFFFFu : 0u, (i & 1) ? 0xFFFFFFFFu : 0u,
+                                           (i & 1) ? 0u : 0xFFFFFFFFu, (i & 1) ? 0u : 0xFFFFFFFFu);
+            else mma_ts(d, tm + 448 + (i & 3) * 8, db, idesc, 1u);
+          } else {
+            mma_bf16_ss(d, make_smem_desc(sa + (i & 3) * 4096, 2048, 128), db, idesc, 1u);
+          }
+        }
+      }
+      __syncwarp();
+    }
+    const unsigned long long t1 = clock64();
+    if (elect_one()) commit(&bar);
+    __syncwarp();
+    mbar_wait(&bar, 0);
+    const unsigned long long t2 = clock64();
+    if ((tid & 31) == 0) { out[0] = t2 - t0; out[1] = t1 - t0; }
+  }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+}  // namespace rdst
+
+extern "C" int rdst_umma_bench(int N, int chains, int count, int a_tmem, int masked, void* out_2_u64, void* stream) {
+  using namespace rdst;
+  RDST_REQUIRE(out_2_u64 && chains >= 1 && chains * N <= 448 && count >= 16 && count % 16 == 0,
+               "rdst_umma_bench: need chains*N<=448, count a multiple of 16");
+  void (*k)(int, unsigned long long*) = nullptr;
+#define RDST_UB(NN, CC, TT, MM) if (N == NN && chains == CC && (a_tmem != 0) == TT && (masked != 0) == MM) k = umma_bench_kernel<NN, CC, TT, MM>;
+#define RDST_UB_N(NN) RDST_UB(NN, 1, true, false) RDST_UB(NN, 2, true, false) RDST_UB(NN, 1, true, true) RDST_UB(NN, 2, true, true) \
+                      RDST_UB(NN, 1, false, false) RDST_UB(NN, 2, false, false)
+  RDST_UB_N(16) RDST_UB_N(32) RDST_UB_N(64) RDST_UB_N(128)
+  RDST_UB(32, 4, true, false) RDST_UB(64, 4, true, false) RDST_UB(32, 4, true, true) RDST_UB(64, 4, true, true)
+  RDST_UB(256, 1, true, false) RDST_UB(256, 1, false, false) RDST_UB(192, 1, true, false) RDST_UB(192, 2, true, false)
+#undef RDST_UB_N
+#undef RDST_UB
+  RDST_REQUIRE(k != nullptr, "rdst_umma_bench: combination N=%d chains=%d not instantiated", N, chains);
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+  if (e != cudaSuccess) { set_error("rdst_umma_bench: smem attr: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
+  k<<<1, 128, 65536, (cudaStream_t)stream>>>(count / 16, (unsigned long long*)out_2_u64);
+  RDST_CHECK_LAUNCH("rdst_umma_bench");
+  return RDST_OK;
+}

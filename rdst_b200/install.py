@@ -3,17 +3,51 @@
 The reference trainer/tester do `from networks.swinIR_variations import make_RDSTSR`
 (models/trans_sr_trainer.py:3, models/trans_sr_tester.py:3).  `install()` rebinds that name (and the copy in
 networks.rdst_variations) to this package's factory, and patches trainer/tester modules that were already
-imported.  Call it once before constructing TransSRTrainer / TransSRTester, e.g. from a sitecustomize or at the
-top of train.py / test.py:   `import rdst_b200; rdst_b200.install()`.
+imported.  It also replaces the tester's one-slice-per-call inference loop (models/basic_tester.py:104-115) by the batched
+driver of rdst_b200.infer.  Call it once before constructing TransSRTrainer / TransSRTester, e.g. from a sitecustomize or
+at the top of train.py / test.py:   `import rdst_b200; rdst_b200.install()`.
 """
 import importlib
 import sys
 
+import torch
+
+from .infer import super_resolve_slices
 from .network import RDSTSR, make_RDSTSR
 from .swinir import SwinIR, swinir_make_model
 
 _TARGETS = ("networks.swinIR_variations", "networks.rdst_variations")
 _CALLERS = ("models.trans_sr_trainer", "models.trans_sr_tester")
+_TESTER_BASE = "models.basic_tester"
+
+
+def batched_inference(tester, D, return_sample=False, batch_size=176, _orig=None):
+    """Drop-in body for BasicTester.inference (models/basic_tester.py:104-115) when the tester's network is an rdst_b200
+    module.  The reference loop feeds ONE LR slice per forward call and synchronises device->host after each
+    (models/trans_sr_tester.py:124-166); slices never interact, so all slices of a case that share (scale, LR shape) go
+    through `infer.super_resolve_slices` in large batches.  Returns exactly what the loop returns: per test pair a dict
+    {scale: HxWxC numpy array} (tensor_2_numpy(rec)[0], :163)."""
+    model = getattr(tester, "single_scale_model", None)
+    if not isinstance(model, (RDSTSR, SwinIR)) or getattr(tester, "sr_generator", None) in ("bicubic",):
+        return _orig(tester, D, return_sample)
+    samples = [D.get_test_pair(i) for i in range(D.test_len())]
+    groups = {}
+    for i, smp in enumerate(samples):
+        for s, case in smp.items():
+            groups.setdefault((s, tuple(case["in"].shape)), []).append(i)
+    preds = [dict() for _ in samples]
+    model.eval()
+    for (s, _shape), idx in groups.items():
+        lr = torch.cat([samples[i][s]["in"] for i in idx], dim=0).float()
+        if torch.cuda.is_available() and next(model.parameters()).is_cuda and not lr.is_cuda:
+            lr = lr.pin_memory()
+        hr = super_resolve_slices(model, lr, batch_size=batch_size)
+        n_per = samples[idx[0]][s]["in"].shape[0]                    # slices per test pair (1 for the OASIS loaders)
+        for k, i in enumerate(idx):
+            preds[i][s] = tester.tensor_2_numpy(hr[k * n_per:(k + 1) * n_per])[0]
+    # keep the dict order of the reference loop (scales in sample order)
+    preds = [{s: p[s] for s in smp} for p, smp in zip(preds, samples)]
+    return (preds, samples) if return_sample else preds
 
 
 def install(strict=False):
@@ -52,4 +86,22 @@ def install(strict=False):
             if hasattr(mod, "swinir_make_model"):
                 mod.swinir_make_model = swinir_make_model
             patched.append(name)
+    # the tester's per-slice inference loop -> batched driver
+    mod = sys.modules.get(_TESTER_BASE)
+    if mod is None:
+        try:
+            mod = importlib.import_module(_TESTER_BASE)
+        except Exception:
+            if strict:
+                raise
+            mod = None
+    if mod is not None and hasattr(mod, "BasicTester"):
+        orig = mod.BasicTester.inference
+        if not getattr(orig, "_rdst_b200_batched", False):
+            def inference(self, D, return_sample=False, _orig=orig):
+                return batched_inference(self, D, return_sample, _orig=_orig)
+            inference._rdst_b200_batched = True
+            inference.__doc__ = batched_inference.__doc__
+            mod.BasicTester.inference = inference
+        patched.append(_TESTER_BASE + ".BasicTester.inference")
     return patched
