@@ -130,8 +130,8 @@ __device__ __forceinline__ int win_region(const Geom& g, int wy, int wx, int iy,
 constexpr int THREADS = 640;
 enum Bar {
   B_W = 0, B_LFULL, B_EFULL, B_XH_READY, B_XH_FREE, B_AP_READY, B_PROJ_FULL, B_PROJ_DRAINED,
-  B_QKV_FULL = 8, B_QK_DRAINED = 10, B_V_DRAINED = 12, B_S_FULL = 14, B_P_READY = 16, B_O_FULL = 18, B_O_FREE = 20, B_AP_FREE = 22,
-  NBARS = 23
+  B_QKV_FULL = 8, B_QK_DRAINED = 10, B_V_DRAINED = 12, B_S_FULL = 14, B_P_READY = 16, B_O_FULL = 18, B_AP_FREE = 20, B_WREADY = 21,
+  NBARS = 22
 };
 
 __device__ __forceinline__ void wgA_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -164,8 +164,8 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
   if (tid == 0) {
     for (int i = 0; i < NBARS; ++i) {
       const bool w4 = i == B_XH_READY || i == B_AP_READY || i == B_PROJ_DRAINED || (i >= B_QK_DRAINED && i < B_S_FULL) ||
-                      (i >= B_P_READY && i < B_O_FULL) || i == B_O_FREE || i == B_O_FREE + 1;
-      mbar_init(&bars[i], w4 ? 4 : 1);
+                      (i >= B_P_READY && i < B_O_FULL);
+      mbar_init(&bars[i], w4 ? 4 : (i == B_XH_FREE ? 2 : 1));      // x^ is free when BOTH slot issuers are past their last qkv
     }
     fence_mbar_init();
     mbar_arrive_expect_tx(&bars[B_W], K::WQKV_BYTES + K::WPROJ_BYTES);
@@ -423,8 +423,8 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 #pragma unroll
           for (int e = 0; e < 8; ++e) fo[c0 + e] = t[e];
         }
-        wait_ld();
-        warp_arrive(&bars[B_O_FREE + s], lane);
+        wait_ld();                                               // (the V_DRAINED arrival below also tells the issuer that O is free)
+        fence_before_sync();
         if (hp == 0 && np >= 1) {                               // proj of the previous tile has read the normalised O
           mbar_wait(&bars[B_AP_FREE], (np - 1) & 1);            // (one completion per tile: a waiter never lags two phases)
           fence_after_sync();
@@ -536,9 +536,9 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       A2_STAMP();   // C/D: P written
     }
   } else if (warp == 16) {
-    // =============================== MMA warp: every tcgen05.mma, one static order ===============================
+    // fold the biases into the resident images (K rows 60/61 of every qkv head, spare K rows of proj), then release the
+    // three issuer warps
     mbar_wait(&bars[B_W], 0);
-    // fold the biases into the resident images: K rows 60/61 of every qkv head, spare K rows of proj
     for (int i = lane; i < 6 * NH; i += 32) {
       const int hh = i / NH, nn = i - hh * NH;
       *reinterpret_cast<uint32_t*>(smem + K::OFF_WQKV + hh * (NH * CP * 2) + (7 * NH + nn) * 16 + 8) = bias_hi_lo(bqkv[i]);
@@ -555,51 +555,32 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     }
     fence_proxy_async();
     __syncwarp();
-    {
-      // The whole warp runs the issue loop with warp-uniform values (shuffle / vote results, kernel parameters), and only
-      // the tcgen05 instructions themselves sit under elect.sync: descriptors then live in uniform registers.  Running
-      // the loop on one lane of a divergent branch costs a broadcast "waterfall" per MMA (~60 cycles each, measured).
-      const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
-      const uint32_t aWqkv = smem_u32(smem + K::OFF_WQKV), aWproj = smem_u32(smem + K::OFF_WPROJ);
-      const uint32_t aKV = smem_u32(smem + K::OFF_KV);
-      constexpr uint32_t idq = make_idesc_bf16(128, NH, false, false);
-      constexpr uint32_t ids = make_idesc_bf16(128, 64, false, false);
-      constexpr uint32_t idv = make_idesc_f16(128, K::HDV, false, true);
-      constexpr uint32_t idp = make_idesc_bf16(128, K::NPC, false, false);
-      // Program order of the tensor pipe (it executes in issue order, so every "X before Y" below is free):
-      //     iteration j:   PV(j) ;  S(j+2) ;  qkv(j+4) ;  [a proj block of the previous tile when its operands are ready]
-      // PV(j) waits for the softmax of head j; S(j+2) right behind it reuses the S/P columns PV(j) has just read and
-      // overwrites nothing else, so the softmax warpgroup of that slot gets its next logits one MMA round trip after it
-      // delivered P.  qkv(j+4) reuses the accumulator slot whose Q operand S(j+2) has just read; role B copied the rest
-      // into registers before it released q/k.  qkv of the next tile's first heads and the proj blocks are issued
-      // only when ready (probe, no wait): they must never hold up the PV -> S chain.
-      int next_q = 0;                  // next head whose qkv has to be issued
-      int next_p = 0;                  // next proj block (tile * NHALF + block)
-      auto probe = [&](uint64_t* bar, uint32_t parity) { return __all_sync(0xffffffffu, mbar_test(bar, parity)) != 0; };
-      auto qkv_ready = [&](int g) {
-        const int n = g / 6, h = g - 6 * n;
-        return h != 0 || probe(&bars[B_XH_READY], n & 1);
-      };
-      auto issue_qkv = [&](int g) {    // caller guarantees qkv_ready(g) or blocks here
-        const int s = g & 1, n = g / 6, h = g - 6 * n;
-        if (h == 0) mbar_wait(&bars[B_XH_READY], n & 1);                           // x^ of this tile is in TMEM
-        fence_after_sync();
-        if (elect_one()) {
-          const uint32_t wb = aWqkv + h * (NH * CP * 2);
-#pragma unroll
-          for (int ks = 0; ks < CP / 16; ++ks)
-            mma_ts(tm + K::TM_QKV + 64 * s, tm + K::TM_XH + ks * 8, make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128), idq, ks > 0);
-          commit(&bars[B_QKV_FULL + s]);
-          if (h == 5) commit(&bars[B_XH_FREE]);                  // x^ may be replaced by the next tile's
-        }
-        __syncwarp();
-      };
-      auto proj_ready = [&](int k) {
-        const int pn = k / K::NHALF, hf = k - pn * K::NHALF;
-        if (hf == 0 && !probe(&bars[B_AP_READY], pn & 1)) return false;
-        return k == 0 || probe(&bars[B_PROJ_DRAINED], (k - 1) & 1);
-      };
-      auto issue_proj = [&](int k) {
+    if (lane == 0) mbar_arrive(&bars[B_WREADY]);
+  }
+  if (wg == 4 && warp <= 18) {
+    // =============================== MMA issue: three warps, each with its own static program ===============================
+    // The tensor pipe executes MMAs in the order they are issued, whoever issues them.  All MMAs that touch the resources
+    // of head slot s (its qkv accumulator / packed Q, its S / P columns, its O columns, its K / V images) are issued by
+    // ONE warp (16 + s), so every "X before Y" on a slot holds by that warp's program order:
+    //     iteration j (heads of this slot):  PV(j) ;  S(j+2) ;  qkv(j+4)
+    // PV(j) waits for the softmax of head j; S(j+2) right behind it reuses the S/P columns PV(j) has just read, so the
+    // softmax warpgroup of the slot gets its next logits one MMA round trip after it delivered P; qkv(j+4) reuses the
+    // accumulator whose Q operand S(j+2) has just read (role B copied the rest into registers before it released q/k).
+    // Warp 18 issues the proj blocks.  Splitting the issue role matters because the control path of an issuer (barrier
+    // probes at ~100-150 cycles each, elect, commit) costs ~2000 cycles per head when one warp does everything (measured),
+    // i.e. it, not the tensor pipe (~650 cycles of MMAs per head), paced the first version of this kernel.
+    // The whole warp runs the loop with warp-uniform values and only the tcgen05 instructions sit under elect.sync:
+    // descriptors then live in uniform registers (one lane of a divergent branch costs a ~60-cycle waterfall per MMA).
+    mbar_wait(&bars[B_WREADY], 0);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t aWqkv = smem_u32(smem + K::OFF_WQKV), aWproj = smem_u32(smem + K::OFF_WPROJ);
+    const uint32_t aKV = smem_u32(smem + K::OFF_KV);
+    constexpr uint32_t idq = make_idesc_bf16(128, NH, false, false);
+    constexpr uint32_t ids = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idv = make_idesc_f16(128, K::HDV, false, true);
+    constexpr uint32_t idp = make_idesc_bf16(128, K::NPC, false, false);
+    if (warp == 18) {
+      for (int k = 0; k < NT * K::NHALF; ++k) {
         const int pn = k / K::NHALF, hf = k - pn * K::NHALF;
         if (hf == 0) mbar_wait(&bars[B_AP_READY], pn & 1);
         if (k >= 1) mbar_wait(&bars[B_PROJ_DRAINED], (k - 1) & 1);               // previous block is in registers
@@ -613,70 +594,91 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
           if (hf == K::NHALF - 1) commit(&bars[B_AP_FREE]);      // the normalised O of this tile has been read
         }
         __syncwarp();
-      };
-      auto issue_s = [&](int g) {
-        const int s = g & 1;
-        mbar_wait(&bars[B_QK_DRAINED + s], (g >> 1) & 1);
-        fence_after_sync();
-        if (elect_one()) {
-          const uint32_t aBk = aKV + s * K::KV_BYTES;
-#pragma unroll
-          for (int w = 0; w < 2; ++w)
-#pragma unroll
-            for (int ks = 0; ks < K::HDP / 16; ++ks)
-              mma_bf16_ts_masked(tm + K::TM_S + 64 * s, tm + K::TM_QKV + 64 * s + ks * 8,
-                                 make_smem_desc(aBk + w * 1024 + ks * 4096, 2048, 128), ids, ks > 0,
-                                 w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
-          commit(&bars[B_S_FULL + s]);
-        }
-        __syncwarp();
-      };
-      auto issue_pv = [&](int g) {
-        const int s = g & 1;
-        mbar_wait(&bars[B_P_READY + s], (g >> 1) & 1);
-        mbar_wait(&bars[B_V_DRAINED + s], (g >> 1) & 1);                         // V image of this head is in shared memory
-        if (g >= 2) mbar_wait(&bars[B_O_FREE + s], ((g - 2) >> 1) & 1);          // O of head g-2 is in registers
-        fence_after_sync();
-        if (elect_one()) {
-          const uint32_t aBv = aKV + s * K::KV_BYTES + K::BK_BYTES;
-#pragma unroll
-          for (int w = 0; w < 2; ++w)
-#pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              mma_bf16_ts_masked(tm + K::TM_O + 32 * s, tm + K::TM_S + 64 * s + ks * 8,
-                                 make_smem_desc(aBv + w * 1024 + ks * 256, 128, 2048), idv, ks > 0,
-                                 w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
-          commit(&bars[B_O_FULL + s]);
-        }
-        __syncwarp();
-      };
-      const int NPB = NT * K::NHALF;
-      issue_qkv(next_q++);
-      issue_qkv(next_q++);
-      issue_s(0); issue_qkv(next_q++);
-      issue_s(1); issue_qkv(next_q++);
-      for (int j = 0; j < G; ++j) {
-        issue_pv(j);
-        A2_STAMP();   // MMA: PV(j) issued
-        if (j + 2 < G) {
-          while (next_q <= j + 2) {                              // (only after a skipped probe) its qkv has to exist
-            // blocking on x^ of tile nt = waiting for role A, which first finishes the epilogue of tile nt-2: make
-            // sure every proj block it needs has been issued, or the two would wait for each other
-            if (next_q % 6 == 0)
-              while (next_p < (next_q / 6 - 1) * K::NHALF) issue_proj(next_p++);
-            issue_qkv(next_q++);
-          }
-          issue_s(j + 2);
-          A2_STAMP();   // MMA: S(j+2) issued
-        }
-        // the accumulator slot of head j+4 was released by S(j+2); x^ of a new tile may still be on its way
-        while (next_q < G && next_q <= j + 4 && qkv_ready(next_q)) issue_qkv(next_q++);
-        // proj blocks of finished tiles (heads of tile pn are complete once PV(6 pn + 5) has been issued)
-        while (next_p < NPB && 6 * (next_p / K::NHALF) + 5 <= j && proj_ready(next_p)) issue_proj(next_p++);
       }
-      while (next_p < NPB) issue_proj(next_p++);
+    } else {
+      const int s = warp - 16;                                   // head slot of this issuer
+      const uint32_t tQ = tm + K::TM_QKV + 64 * s, tS = tm + K::TM_S + 64 * s, tO = tm + K::TM_O + 32 * s;
+      const uint32_t aBk = aKV + s * K::KV_BYTES, aBv = aBk + K::BK_BYTES;
+      uint64_t* const bQKV = &bars[B_QKV_FULL + s];
+      uint64_t* const bQK = &bars[B_QK_DRAINED + s];
+      uint64_t* const bV = &bars[B_V_DRAINED + s];
+      uint64_t* const bS = &bars[B_S_FULL + s];
+      uint64_t* const bP = &bars[B_P_READY + s];
+      uint64_t* const bO = &bars[B_O_FULL + s];
+      auto qkv_mmas = [&](int h) {                               // elected lane only
+        const uint32_t wb = aWqkv + h * (NH * CP * 2);
+#pragma unroll
+        for (int ks = 0; ks < CP / 16; ++ks)
+          mma_ts(tQ, tm + K::TM_XH + ks * 8, make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128), idq, ks > 0);
+        commit(bQKV);
+        if (h >= 4) commit(&bars[B_XH_FREE]);                    // last qkv of this slot in the tile (two arrivals free x^)
+      };
+      auto s_mmas = [&]() {
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+          for (int ks = 0; ks < K::HDP / 16; ++ks)
+            mma_bf16_ts_masked(tS, tQ + ks * 8, make_smem_desc(aBk + w * 1024 + ks * 4096, 2048, 128), ids, ks > 0,
+                               w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
+        commit(bS);
+      };
+      auto pv_mmas = [&]() {
+#pragma unroll
+        for (int w = 0; w < 2; ++w)
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks)
+            mma_bf16_ts_masked(tO, tS + ks * 8, make_smem_desc(aBv + w * 1024 + ks * 256, 128, 2048), idv, ks > 0,
+                               w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
+        commit(bO);
+      };
+      // head g of this slot is its (g >> 1)-th: that is the phase index of all per-slot barriers
+      // prologue: qkv(s) ; S(s) ; qkv(s+2)
+      mbar_wait(&bars[B_XH_READY], 0);
+      fence_after_sync();
+      if (elect_one()) qkv_mmas(s);
+      __syncwarp();
+      mbar_wait(bQK, 0);
+      fence_after_sync();
+      if (elect_one()) { s_mmas(); qkv_mmas(s + 2); }
+      __syncwarp();
+      int q_next = s + 4;              // next head of this slot whose qkv has to be issued
+      for (int j = s; j < G; j += 2) {
+        const uint32_t ph = (j >> 1) & 1;
+        // softmax of head j delivered P; role B wrote V (which also means O of head j-2 is in its registers)
+        while (true) {
+          const bool p_ok = mbar_try_wait(bP, ph), v_ok = mbar_try_wait(bV, ph);
+          if (p_ok && v_ok) break;
+        }
+        fence_after_sync();
+        A2_STAMP();   // MMA: P, V ready
+        if (elect_one()) pv_mmas();
+        __syncwarp();
+        A2_STAMP();   // MMA: PV issued
+        if (j + 2 < G) {
+          if (q_next == j + 2) {                                 // its qkv was held back by a tile boundary: now it must exist
+            mbar_wait(&bars[B_XH_READY], ((j + 2) / 6) & 1);
+            fence_after_sync();
+            if (elect_one()) qkv_mmas((j + 2) % 6);
+            __syncwarp();
+            q_next += 2;
+          }
+          mbar_wait(bQK, ph ^ 1);
+          fence_after_sync();
+          const int g4 = j + 4, h4 = g4 % 6;
+          // qkv(j+4) goes out in the same breath unless it opens a new tile whose x^ is not in TMEM yet
+          const bool q_go = q_next == g4 && g4 < G &&
+                            (h4 >= 2 || __all_sync(0xffffffffu, mbar_test(&bars[B_XH_READY], (g4 / 6) & 1)) != 0);
+          if (q_go && h4 < 2) fence_after_sync();
+          if (elect_one()) {
+            s_mmas();
+            if (q_go) qkv_mmas(h4);
+          }
+          __syncwarp();
+          if (q_go) q_next += 2;
+          A2_STAMP();   // MMA: S (+ qkv) issued
+        }
+      }
     }
-    __syncwarp();
   }
 #undef A2_STAMP
   fence_before_sync();

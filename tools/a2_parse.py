@@ -14,7 +14,10 @@ ev = []
 def lab(r, i):
     if r == "C": return f"C {'S ready' if i % 2 == 0 else 'P written'} g={2 * (i // 2)}"
     if r == "D": return f"D {'S ready' if i % 2 == 0 else 'P written'} g={2 * (i // 2) + 1}"
-    if r == "M": return f"M {'PV issued j=' + str(i // 2) if i % 2 == 0 else 'S issued g=' + str(i // 2 + 2)}"
+    if r == "M":          # issuer of slot 0 (even heads): 3 stamps per iteration
+        it, k = divmod(i, 3)
+        j = 2 * it
+        return f"M0 j={j}: " + ["P,V ready", "PV issued", f"S({j + 2}) (+qkv({j + 4})) issued"][k]
     if r == "B":
         per = 13
         t, k = divmod(i, per)
