@@ -131,7 +131,7 @@ constexpr int THREADS = 640;
 enum Bar {
   B_W = 0, B_LFULL, B_EFULL, B_XH_READY, B_XH_FREE, B_AP_READY, B_PROJ_FULL, B_PROJ_DRAINED,
   B_QKV_FULL = 8, B_QK_DRAINED = 10, B_V_DRAINED = 12, B_S_FULL = 14, B_P_READY = 16, B_O_FULL = 18, B_AP_FREE = 20, B_WREADY = 21,
-  NBARS = 22
+  B_STAGED = 22, NBARS = 23
 };
 
 __device__ __forceinline__ void wgA_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -238,122 +238,178 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 
   if (wg == 0) {
     // =============================== role A: LayerNorm (one tile ahead), proj epilogue, TMA ===============================
-    if (warp == 0) {
-      if (elect_one()) load_tile(blockIdx.x, sL, &bars[B_LFULL]);
-      __syncwarp();
-    }
+    // Per period t the role touches two tiles: LayerNorm of tile t+1 (its x^ must be in TMEM before the issuers reach
+    // heads 0/1 of that tile, i.e. about two thirds into tile t) and the epilogue of tile t-1 (its proj blocks arrive
+    // early in tile t).  The two are interleaved in the order their inputs become available:
+    //     statistics(t+1)  ->  epilogue block 0 (t-1)  ->  normalise(t+1) -> x^, next landing  ->  epilogue block 1 (t-1), store
+    // (doing the whole epilogue first left x^ ~4000 cycles late at every tile boundary, measured.)
     const float inv_c = 1.0f / (float)C_;
-    for (int n = 0; n <= NT; ++n) {
-      const int tile = blockIdx.x + n * gridDim.x;
-      if (n < NT) {
-        mbar_wait(&bars[B_LFULL], n & 1);
-        A2_STAMP();   // A: tile landed
-        // two passes over the landed row (shared memory reads are conflict-free and cheap; holding the whole row in
-        // registers between the passes costs more registers than this role has): statistics, then normalise -> TMEM
-        float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+    float ln_rstd = 0.f, ln_nb = 0.f;
+    auto ln_stats = [&](int n) {                           // pass 1 over the landed rows of tile n
+      mbar_wait(&bars[B_LFULL], n & 1);
+      A2_STAMP();   // A: tile landed
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
 #pragma unroll
-        for (int c = 0; c < K::NCH; ++c) {
-          const uint4 v = *reinterpret_cast<const uint4*>(sL + xt_off(row, c));
+      for (int c = 0; c < K::NCH; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(sL + xt_off(row, c));
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = up2(w4[q]);
+          s0 += f.x; s1 += f.y;
+          q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+        }
+      }
+      const float mean = (s0 + s1) * inv_c;
+      const float var = (q0 + q1) * inv_c - mean * mean;
+      ln_rstd = rsqrtf(fmaxf(var, 0.f) + 1e-5f);
+      ln_nb = -mean * ln_rstd;
+    };
+    auto ln_write = [&](int n) {                           // pass 2: normalised bf16 rows of tile n -> TMEM, then L is free
+      if (n >= 1) { mbar_wait(&bars[B_XH_FREE], (n - 1) & 1); fence_after_sync(); }   // both issuers are past the previous tile's last qkv
+      A2_STAMP();   // A: XH free
+#pragma unroll
+      for (int c0 = 0; c0 < K::NCH; c0 += 4) {             // 4 chunks = 32 channels = 16 packed columns per store
+        uint32_t a[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(sL + xt_off(row, c0 + c));
           const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float2 f = up2(w4[q]);
-            s0 += f.x; s1 += f.y;
-            q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+            a[4 * c + q] = pk2(fmaf(f.x, ln_rstd, ln_nb), fmaf(f.y, ln_rstd, ln_nb));
           }
         }
-        const float mean = (s0 + s1) * inv_c;
-        const float var = (q0 + q1) * inv_c - mean * mean;
-        const float rstd = rsqrtf(fmaxf(var, 0.f) + 1e-5f);
-        const float nb = -mean * rstd;
-        if (n >= 1) { mbar_wait(&bars[B_XH_FREE], (n - 1) & 1); fence_after_sync(); }   // qkv of the previous tile's last head is done
-        A2_STAMP();   // A: statistics done, XH free
-#pragma unroll
-        for (int c0 = 0; c0 < K::NCH; c0 += 4) {           // 4 chunks = 32 channels = 16 packed columns per store
-          uint32_t a[16];
-#pragma unroll
-          for (int c = 0; c < 4; ++c) {
-            const uint4 v = *reinterpret_cast<const uint4*>(sL + xt_off(row, c0 + c));
-            const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-              const float2 f = up2(w4[q]);
-              a[4 * c + q] = pk2(fmaf(f.x, rstd, nb), fmaf(f.y, rstd, nb));
-            }
-          }
-          if (c0 == 4) a[14] = 0x3F803F80u;                // pad channels 60, 61 carry the ones of the folded qkv bias
-          tmem_st_x16(lane_addr + K::TM_XH + 4 * c0, a);
-        }
-        wgA_sync();                                        // every row of L has been read twice: the next tile may land
-        if (warp == 0 && n + 1 < NT) {
-          if (elect_one()) load_tile(tile + gridDim.x, sL, &bars[B_LFULL]);
-          __syncwarp();
-        }
-        wait_st();
-        warp_arrive(&bars[B_XH_READY], lane);
+        if (c0 == 4) a[14] = 0x3F803F80u;                  // pad channels 60, 61 carry the ones of the folded qkv bias
+        tmem_st_x16(lane_addr + K::TM_XH + 4 * c0, a);
       }
-      if (n >= 1) {
-        // ---- epilogue of the previous tile: y = proj + bias + x, in place in the staging tile, NHALF column blocks ----
-        const int pn = n - 1;
-        if (warp == 0) {
-          // residual rows of tile n-1 -> E (second fetch, an L2 hit).  The store of tile n-2 left E a whole tile ago:
-          // waiting for it here is free, while waiting right after issuing it would stall the next LayerNorm.
-          if (elect_one()) {
-            if (n >= 2) bulk_wait_read();
-            load_tile(tile - gridDim.x, sE, &bars[B_EFULL]);
-          }
-          __syncwarp();
+      wgA_sync();                                          // every row of L has been read twice: the next tile may land
+      if (warp == 0 && n + 1 < NT) {
+        if (elect_one()) load_tile(blockIdx.x + (n + 1) * gridDim.x, sL, &bars[B_LFULL]);
+        __syncwarp();
+      }
+      wait_st();
+      warp_arrive(&bars[B_XH_READY], lane);
+    };
+    auto epi_block = [&](int pn, int hf) {                 // y = proj + bias + x for one column block, in place in the staging tile
+      mbar_wait(&bars[B_PROJ_FULL], (pn * K::NHALF + hf) & 1);
+      fence_after_sync();
+      A2_STAMP();   // A: proj block ready
+      uint32_t acc[K::NPC];
+#pragma unroll
+      for (int c0 = 0; c0 < K::NPC; c0 += 16) {
+        uint32_t t[16];
+        tmem_ld_x16(lane_addr + K::TM_PROJ + c0, t);
+#pragma unroll
+        for (int e = 0; e < 16; ++e) acc[c0 + e] = t[e];
+      }
+      wait_ld();
+      warp_arrive(&bars[B_PROJ_DRAINED], lane);            // the accumulator may be overwritten by the next block
+      if (hf == 0) mbar_wait(&bars[B_EFULL], pn & 1);
+#pragma unroll
+      for (int c0 = 0; c0 < K::NPC; c0 += 8) {
+        uint8_t* xp = sE + xt_off(row, (hf * K::NPC + c0) >> 3);
+        const uint4 xv = *reinterpret_cast<const uint4*>(xp);
+        const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+        uint32_t y[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 xf = up2(xw[e]);
+          y[e] = pk2(__uint_as_float(acc[c0 + 2 * e]) + xf.x, __uint_as_float(acc[c0 + 2 * e + 1]) + xf.y);
         }
-#pragma unroll
-        for (int hf = 0; hf < K::NHALF; ++hf) {
-          mbar_wait(&bars[B_PROJ_FULL], (pn * K::NHALF + hf) & 1);
-          fence_after_sync();
-          A2_STAMP();   // A: proj half ready
-          uint32_t acc[K::NPC];
-#pragma unroll
-          for (int c0 = 0; c0 < K::NPC; c0 += 16) {
-            uint32_t t[16];
-            tmem_ld_x16(lane_addr + K::TM_PROJ + c0, t);
-#pragma unroll
-            for (int e = 0; e < 16; ++e) acc[c0 + e] = t[e];
-          }
-          wait_ld();
-          warp_arrive(&bars[B_PROJ_DRAINED], lane);    // the accumulator may be overwritten by the next block
-          if (hf == 0) mbar_wait(&bars[B_EFULL], pn & 1);
-#pragma unroll
-          for (int c0 = 0; c0 < K::NPC; c0 += 8) {
-            uint8_t* xp = sE + xt_off(row, (hf * K::NPC + c0) >> 3);
-            const uint4 xv = *reinterpret_cast<const uint4*>(xp);
-            const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
-            uint32_t y[4];
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 xf = up2(xw[e]);
-              y[e] = pk2(__uint_as_float(acc[c0 + 2 * e]) + xf.x, __uint_as_float(acc[c0 + 2 * e + 1]) + xf.y);
-            }
-            *reinterpret_cast<uint4*>(xp) = make_uint4(y[0], y[1], y[2], y[3]);
-          }
-        }
-        fence_proxy_async();                           // the finished rows are read by the TMA store (async proxy)
+        *reinterpret_cast<uint4*>(xp) = make_uint4(y[0], y[1], y[2], y[3]);
+      }
+    };
+    if (warp == 0) {
+      if (elect_one()) load_tile(blockIdx.x, sL, &bars[B_LFULL]);
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int t = -1; t <= NT; ++t) {                       // t = -1: LayerNorm of the first tile only
+      if (t + 1 < NT) ln_stats(t + 1);
+      if (t >= 1) epi_block(t - 1, 0);
+      if (t + 1 < NT) ln_write(t + 1);
+      if (t >= 1) {
+        if (K::NHALF == 2) epi_block(t - 1, 1);
+        fence_proxy_async();                               // the finished rows are read by the TMA store (async proxy)
         wgA_sync();
         A2_STAMP();   // A: y staged
-        if (warp == 0) {
-          if (elect_one()) store_tile(tile - gridDim.x, sE);
-          __syncwarp();
-        }
       }
-    }
-    if (warp == 0) {
-      if (elect_one()) bulk_wait_read();
-      __syncwarp();
+      if (t >= 1 && tid == 0) mbar_arrive(&bars[B_STAGED]);     // warp 19 stores the tile and refills E (below)
     }
   } else if (wg == 1) {
     // =============================== role B: qkv drain (head g), O / rowsum (head g-2) ===============================
+    // Iteration g:  drain(g)  ->  [PV(g-2) complete]  load O(g-2)  ->  write V(g), release it  ->  normalise O(g-2) -> AP.
+    // V is released before the normalised O is stored because that store may have to wait for the proj of the previous
+    // tile (AP is single-buffered) and PV(g) must not wait with it.  When O(g-2) is already there at the top of the
+    // iteration (qkv(g) late, e.g. at a tile boundary) it is handled first, so that the last head of a tile -- which
+    // triggers the proj chain everybody downstream waits for -- never queues behind a late qkv.
     uint4 vimg[K::VCH];
+    constexpr int NCO = (HD + 8) / 8 * 8;                      // head_dim values + the row-sum column: 16 / 16 / 24
+    uint32_t fo[NCO];
+    auto o_load = [&](int gp) {
+      const int s = gp & 1;
+#pragma unroll
+      for (int c0 = 0; c0 < NCO; c0 += 8) {
+        uint32_t t[8];
+        tmem_ld_x8(lane_addr + K::TM_O + 32 * s + c0, t);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) fo[c0 + e] = t[e];
+      }
+      wait_ld();                                               // (the V_DRAINED arrival of head gp+2 also tells the issuer that O is free)
+      fence_before_sync();
+    };
+    auto o_store = [&](int gp) {
+      const int np = gp / 6, hp = gp - 6 * np;
+      if (hp == 0 && np >= 1) {                                 // proj of the previous tile has read the normalised O
+        mbar_wait(&bars[B_AP_FREE], (np - 1) & 1);              // (one completion per tile: a waiter never lags two phases)
+        fence_after_sync();
+      }
+      const float inv = 1.0f / __uint_as_float(fo[HD]);
+      auto ov = [&](int d) { return __uint_as_float(fo[d]) * inv; };
+      if (K::HDO == 16) {
+        uint32_t a[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          const int d0 = 2 * e, d1 = d0 + 1;
+          a[e] = pk2(d0 < HD ? ov(d0) : 0.f, d1 < HD ? ov(d1) : 0.f);
+        }
+        // ones of the folded proj bias: C=60 k = 10, 11 (head 0); C=90 k = 15 and 31 (heads 0, 1)
+        if (C_ == 60 && hp == 0) a[5] = 0x3F803F80u;
+        if (C_ == 90 && hp < 2) a[7] = (a[7] & 0xFFFFu) | 0x3F800000u;
+        tmem_st_x8(lane_addr + K::TM_AP + 8 * hp, a);
+      } else {                                                   // head_dim 20: 10 packed columns per head
+        uint32_t a[8], b[2];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) a[e] = pk2(ov(2 * e), ov(2 * e + 1));
+        b[0] = pk2(ov(16), ov(17));
+        b[1] = pk2(ov(18), ov(19));
+        tmem_st_x8(lane_addr + K::TM_AP + 10 * hp, a);
+        tmem_st_x2(lane_addr + K::TM_AP + 10 * hp + 8, b);
+        if (hp == 5) {                                           // k = 120, 121: ones of the folded proj bias; rest of the pad zero
+          uint32_t zz[4] = {0x3F803F80u, 0, 0, 0};
+          tmem_st_x4(lane_addr + K::TM_AP + 60, zz);
+        }
+      }
+      if (hp == 5) {
+        wait_st();
+        warp_arrive(&bars[B_AP_READY], lane);
+        A2_STAMP();   // B: normalised O complete
+      }
+    };
+#pragma unroll 1
     for (int g = 0; g < G + 2; ++g) {
       const int s = g & 1;
       uint8_t* sBk = smem + K::OFF_KV + s * K::KV_BYTES;
       uint8_t* sBv = sBk + K::BK_BYTES;
+      bool o_early = false;
+      if (g >= 2 && g < G && __all_sync(0xffffffffu, mbar_test(&bars[B_O_FULL + s], ((g - 2) >> 1) & 1))) {
+        fence_after_sync();
+        o_load(g - 2);
+        o_store(g - 2);
+        o_early = true;
+      }
       if (g < G) {
         mbar_wait(&bars[B_QKV_FULL + s], (g >> 1) & 1);
         fence_after_sync();
@@ -410,56 +466,10 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         warp_arrive(&bars[B_QK_DRAINED + s], lane);
         A2_STAMP();   // B: q, k drained
       }
-      if (g >= 2) {
-        const int gp = g - 2, np = gp / 6, hp = gp - 6 * np;
-        mbar_wait(&bars[B_O_FULL + s], (gp >> 1) & 1);            // PV(g-2) complete: O ready, the V image is free
+      if (g >= 2 && !o_early) {
+        mbar_wait(&bars[B_O_FULL + s], ((g - 2) >> 1) & 1);      // PV(g-2) complete: O ready, the V image is free
         fence_after_sync();
-        constexpr int NCO = (HD + 8) / 8 * 8;                    // head_dim values + the row-sum column: 16 / 16 / 24
-        uint32_t fo[NCO];
-#pragma unroll
-        for (int c0 = 0; c0 < NCO; c0 += 8) {
-          uint32_t t[8];
-          tmem_ld_x8(lane_addr + K::TM_O + 32 * s + c0, t);
-#pragma unroll
-          for (int e = 0; e < 8; ++e) fo[c0 + e] = t[e];
-        }
-        wait_ld();                                               // (the V_DRAINED arrival below also tells the issuer that O is free)
-        fence_before_sync();
-        if (hp == 0 && np >= 1) {                               // proj of the previous tile has read the normalised O
-          mbar_wait(&bars[B_AP_FREE], (np - 1) & 1);            // (one completion per tile: a waiter never lags two phases)
-          fence_after_sync();
-        }
-        const float inv = 1.0f / __uint_as_float(fo[HD]);
-        auto ov = [&](int d) { return __uint_as_float(fo[d]) * inv; };
-        if (K::HDO == 16) {
-          uint32_t a[8];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) {
-            const int d0 = 2 * e, d1 = d0 + 1;
-            a[e] = pk2(d0 < HD ? ov(d0) : 0.f, d1 < HD ? ov(d1) : 0.f);
-          }
-          // ones of the folded proj bias: C=60 k = 10, 11 (head 0); C=90 k = 15 and 31 (heads 0, 1)
-          if (C_ == 60 && hp == 0) a[5] = 0x3F803F80u;
-          if (C_ == 90 && hp < 2) a[7] = (a[7] & 0xFFFFu) | 0x3F800000u;
-          tmem_st_x8(lane_addr + K::TM_AP + 8 * hp, a);
-        } else {                                                 // head_dim 20: 10 packed columns per head
-          uint32_t a[8], b[2];
-#pragma unroll
-          for (int e = 0; e < 8; ++e) a[e] = pk2(ov(2 * e), ov(2 * e + 1));
-          b[0] = pk2(ov(16), ov(17));
-          b[1] = pk2(ov(18), ov(19));
-          tmem_st_x8(lane_addr + K::TM_AP + 10 * hp, a);
-          tmem_st_x2(lane_addr + K::TM_AP + 10 * hp + 8, b);
-          if (hp == 5) {                                         // k = 120, 121: ones of the folded proj bias; rest of the pad zero
-            uint32_t zz[4] = {0x3F803F80u, 0, 0, 0};
-            tmem_st_x4(lane_addr + K::TM_AP + 60, zz);
-          }
-        }
-        if (hp == 5) {
-          wait_st();
-          warp_arrive(&bars[B_AP_READY], lane);
-          A2_STAMP();   // B: normalised O complete
-        }
+        o_load(g - 2);
       }
       if (g < G) {
 #pragma unroll
@@ -468,6 +478,7 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_V_DRAINED + s]);
       }
+      if (g >= 2 && !o_early) o_store(g - 2);
     }
   } else if (wg < 4) {
     // =============================== roles C / D: softmax of even / odd heads, thread = one row x 64 keys ===============================
@@ -557,6 +568,21 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars[B_WREADY]);
   }
+  if (warp == 19) {
+    // =============================== E-side TMA: store of finished tiles, second fetch of the residual rows ===============================
+    // A TMA store needs ~3000 cycles before it has read its 32 KB out of shared memory (16 small boxes; measured), and E
+    // cannot take the next tile's residual rows earlier.  On the LayerNorm/epilogue role that wait delayed every proj
+    // drain behind it; here it costs nothing.
+    for (int t = 0; t <= NT; ++t) {
+      const int tile = blockIdx.x + t * gridDim.x;
+      if (t >= 1) mbar_wait(&bars[B_STAGED], (t - 1) & 1);   // y of tile t-1 is complete in E (writers fenced the async proxy)
+      if (elect_one()) {
+        if (t >= 1) { store_tile(tile - gridDim.x, sE); bulk_wait_read(); }
+        if (t < NT) load_tile(tile, sE, &bars[B_EFULL]);     // residual rows of tile t (an L2 hit) for its epilogue
+      }
+      __syncwarp();
+    }
+  }
   if (wg == 4 && warp <= 18) {
     // =============================== MMA issue: three warps, each with its own static program ===============================
     // The tensor pipe executes MMAs in the order they are issued, whoever issues them.  All MMAs that touch the resources
@@ -641,7 +667,6 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       fence_after_sync();
       if (elect_one()) { s_mmas(); qkv_mmas(s + 2); }
       __syncwarp();
-      int q_next = s + 4;              // next head of this slot whose qkv has to be issued
       for (int j = s; j < G; j += 2) {
         const uint32_t ph = (j >> 1) & 1;
         // softmax of head j delivered P; role B wrote V (which also means O of head j-2 is in its registers)
@@ -655,27 +680,26 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         __syncwarp();
         A2_STAMP();   // MMA: PV issued
         if (j + 2 < G) {
-          if (q_next == j + 2) {                                 // its qkv was held back by a tile boundary: now it must exist
-            mbar_wait(&bars[B_XH_READY], ((j + 2) / 6) & 1);
-            fence_after_sync();
-            if (elect_one()) qkv_mmas((j + 2) % 6);
-            __syncwarp();
-            q_next += 2;
-          }
           mbar_wait(bQK, ph ^ 1);
           fence_after_sync();
           const int g4 = j + 4, h4 = g4 % 6;
-          // qkv(j+4) goes out in the same breath unless it opens a new tile whose x^ is not in TMEM yet
-          const bool q_go = q_next == g4 && g4 < G &&
-                            (h4 >= 2 || __all_sync(0xffffffffu, mbar_test(&bars[B_XH_READY], (g4 / 6) & 1)) != 0);
-          if (q_go && h4 < 2) fence_after_sync();
+          const bool q_fused = g4 < G && h4 >= 2;                // qkv(j+4) of the same tile: goes out in the same breath
           if (elect_one()) {
             s_mmas();
-            if (q_go) qkv_mmas(h4);
+            if (q_fused) qkv_mmas(h4);
           }
           __syncwarp();
-          if (q_go) q_next += 2;
           A2_STAMP();   // MMA: S (+ qkv) issued
+          if (g4 < G && h4 < 2) {
+            // first head of this slot in the next tile: x^ of that tile has to be in TMEM.  This warp has nothing else
+            // to do until the softmax of head j+2 delivers (> 1000 cycles), so it simply waits here; everything the
+            // LayerNorm role needs on the way (both issuers past head 5's qkv, the proj blocks of the tile before) is
+            // issued by other warps or earlier in this program.
+            mbar_wait(&bars[B_XH_READY], (g4 / 6) & 1);
+            fence_after_sync();
+            if (elect_one()) qkv_mmas(h4);
+            __syncwarp();
+          }
         }
       }
     }
