@@ -291,6 +291,10 @@ int rdst_debug_conv_timing(void* device_buffer_128_u64);    /* same for rdst_con
  * a_tmem: A from TMEM (else shared memory); masked: disable-output-lane form.  Used by tools/umma_bench.py only. */
 int rdst_umma_bench(int N, int chains, int count, int a_tmem, int masked, void* out_2_u64, void* stream);
 
+/* TMEM <-> register bandwidth probe (one CTA): nwarps warps each move 16 KB per round with four tcgen05.ld.32x32b.x32
+ * (store != 0: tcgen05.st).  out[0] = cycles of the slowest warp, out[1] = bytes moved.  tools/tmem_bw.py only. */
+int rdst_tmem_bw_bench(int nwarps, int reps, int store, void* out_3_u64, void* stream);
+
 /* Self-test of the UMMA plumbing: D[M=128][N] = A[128][K] . B[N][K]^T with bf16 inputs, fp32 output.
  * b_mn_major != 0 feeds B from an MN-major shared-memory image.  Used by tests/ only. */
 int rdst_umma_selftest(const void* a_bf16, const void* b_bf16, float* d, int N, int K, int b_mn_major,

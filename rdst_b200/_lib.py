@@ -74,6 +74,7 @@ _SIGNATURES = {
     "rdst_debug_mlp_timing": (C.c_int, [_vp]),
     "rdst_debug_conv_timing": (C.c_int, [_vp]),
     "rdst_umma_bench": (C.c_int, [_i, _i, _i, _i, _i, _vp, _vp]),
+    "rdst_tmem_bw_bench": (C.c_int, [_i, _i, _i, _vp, _vp]),
     "rdst_umma_selftest": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _i, _vp]),
     "rdst_tma_selftest": (C.c_int, [_vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _i, _vp, _vp]),
 }

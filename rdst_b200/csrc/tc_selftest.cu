@@ -221,3 +221,61 @@ extern "C" int rdst_umma_bench(int N, int chains, int count, int a_tmem, int mas
   RDST_CHECK_LAUNCH("rdst_umma_bench");
   return RDST_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------------------------
+// TMEM <-> register bandwidth probe: `nwarps` warps (1..16; warp w reads lane quadrant w % 4) each run `reps` rounds of
+// four tcgen05.ld.32x32b.x32 (128 columns = 16 KB per warp and round) -- or tcgen05.st when `store` != 0 -- and wait.
+// out[0] = cycles of the slowest warp, out[1] = bytes moved in total.
+namespace rdst {
+using namespace umma;
+__global__ void __launch_bounds__(512) tmem_bw_kernel(int nwarps, int reps, int store, unsigned long long* __restrict__ out) {
+  __shared__ uint32_t tmem_base_s;
+  __shared__ unsigned long long tmax;
+  const int tid = threadIdx.x, warp = tid >> 5;
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  if (tid == 0) tmax = 0;
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t base = tmem_base_s + ((uint32_t)((warp & 3) * 32) << 16) + (warp >> 2) * 128;
+  uint32_t v[32];
+#pragma unroll
+  for (int i = 0; i < 32; ++i) v[i] = i;
+  tmem_st_x32(base, v); tmem_st_x32(base + 32, v); tmem_st_x32(base + 64, v); tmem_st_x32(base + 96, v);
+  wait_st();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  uint32_t acc = 0;
+  const unsigned long long t0 = clock64();
+  if (warp < nwarps) {
+    for (int r = 0; r < reps; ++r) {
+      if (store) {
+        tmem_st_x32(base, v); tmem_st_x32(base + 32, v); tmem_st_x32(base + 64, v); tmem_st_x32(base + 96, v);
+        wait_st();
+      } else {
+        uint32_t a[32], b[32], c[32], d[32];
+        tmem_ld_x32(base, a); tmem_ld_x32(base + 32, b); tmem_ld_x32(base + 64, c); tmem_ld_x32(base + 96, d);
+        wait_ld();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) acc += a[i] ^ b[i] ^ c[i] ^ d[i];
+      }
+    }
+  }
+  const unsigned long long t1 = clock64();
+  if (warp < nwarps && (tid & 31) == 0) atomicMax(&tmax, t1 - t0);
+  __syncthreads();
+  if (tid == 0) { out[0] = tmax; out[1] = (unsigned long long)nwarps * reps * 16384ull; out[2] = acc; }
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem_base_s);
+}
+}  // namespace rdst
+
+extern "C" int rdst_tmem_bw_bench(int nwarps, int reps, int store, void* out_3_u64, void* stream) {
+  using namespace rdst;
+  RDST_REQUIRE(out_3_u64 && nwarps >= 1 && nwarps <= 16 && reps >= 1, "rdst_tmem_bw_bench: 1 <= nwarps <= 16");
+  tmem_bw_kernel<<<1, 512, 0, (cudaStream_t)stream>>>(nwarps, reps, store, (unsigned long long*)out_3_u64);
+  RDST_CHECK_LAUNCH("rdst_tmem_bw_bench");
+  return RDST_OK;
+}
