@@ -21,8 +21,9 @@
 //
 // A head needs no barrier wider than four warps: softmax rows are thread-private (no max exchange), hand-offs are
 // mbarrier arrivals (one per warp) on the consumer side and tcgen05.commit on the MMA side.
-// TMEM (512 columns, all variants):  x^ [0,64) | qkv acc / packed Q, 2 slots [64,192) | S / P, 2 slots [192,320) |
+// TMEM (512 columns; C = 120):  x^ [0,64) | qkv acc / packed Q, 2 slots [64,192) | S / P, 2 slots [192,320) |
 // O, 2 slots [320,384) | normalised O = A of proj [384,448) | proj accumulator (one N-half at a time) [448,512).
+// C = 60 / 90 are narrower and run THREE head slots (Cfg::NS) with a separate output staging tile.
 // Shared memory: resident weight images | landing tile L (LayerNorm source of the NEXT tile) | staging tile E (the
 // residual rows of the CURRENT tile, fetched a second time from L2 right before its epilogue, then output staging) |
 // K / V images (2 slots) | bias table.  C = 120 has no room for a third tile buffer: the second fetch (an L2 hit, the
@@ -91,20 +92,31 @@ struct Cfg {
   static constexpr int BK_BYTES = KCH * 2048;
   static constexpr int BV_BYTES = VCH * 2048;
   static constexpr int KV_BYTES = BK_BYTES + BV_BYTES;      // per slot
-  static constexpr int NHALF = CP == 64 ? 1 : 2;            // proj runs as NHALF column blocks through one accumulator
-  static constexpr int NPC = CP / NHALF;                    // 64 / 48 / 64
+  // Head slots in flight (qkv accumulator + S/P columns + O columns + K/V images each).  P is written in place over S, so
+  // a slot's next S can only follow its PV: with two slots a softmax warpgroup waits one MMA round trip (~1100 cycles)
+  // per head for its next logits.  C = 60 / 90 have the TMEM and shared memory for a third slot, which hides that round
+  // trip (the next S of a warpgroup then sits on a slot whose PV was issued half a softmax earlier).
+  // Measured (176 x 40 x 32, us per launch, 2 vs 3 slots): C = 60: 61.4 vs 59.7; C = 90: 67.0 vs 79.5 (its proj then needs
+  // three 32-column blocks to fit TMEM, and the role-B chain drain(g+1) <- PV(g-NS) gets longer) -> three slots only at C = 60.
+  static constexpr int NS = C == 60 ? 3 : 2;
+  static constexpr int NBLK = CP == 64 ? 1 : (CP == 96 && NS == 3 ? 3 : 2);   // proj runs as NBLK column blocks through one accumulator
+  static constexpr int NPC = CP / NBLK;                     // 64 / 48 (32 with three slots) / 64
+  static constexpr bool YBUF = NS == 3;                     // room for a separate output staging tile (else E is reused)
   static constexpr int OFF_WQKV = 0;
   static constexpr int OFF_WPROJ = OFF_WQKV + WQKV_BYTES;
   static constexpr int OFF_L = OFF_WPROJ + WPROJ_BYTES;     // landing tile (LayerNorm source)
-  static constexpr int OFF_E = OFF_L + XT_BYTES;            // residual rows / output staging
-  static constexpr int OFF_KV = OFF_E + XT_BYTES;           // [2 slots][K | V]
-  static constexpr int OFF_TAB = OFF_KV + 2 * KV_BYTES;
+  static constexpr int OFF_E = OFF_L + XT_BYTES;            // residual rows (and output staging when there is no Y)
+  static constexpr int OFF_Y = OFF_E + XT_BYTES;            // output staging
+  static constexpr int OFF_KV = OFF_Y + (YBUF ? XT_BYTES : 0);     // [NS slots][K | V]
+  static constexpr int OFF_TAB = OFF_KV + NS * KV_BYTES;
   static constexpr int OFF_BARS = OFF_TAB + 6 * TBL * 4;    // mbarriers + TMEM base live in dynamic shared memory too: a static
   static constexpr int SMEM = OFF_BARS + 32 * 8;            // __shared__ would cost a whole 1024-byte alignment unit
-  static constexpr int TM_XH = 0, TM_QKV = 64, TM_S = 192, TM_O = 320, TM_AP = 384, TM_PROJ = 448;
+  // TMEM columns: x^ | qkv accumulators / packed Q | S / P | O | normalised O (A of proj) | proj accumulator (one block)
+  static constexpr int TM_XH = 0, TM_QKV = CP / 2, TM_S = TM_QKV + NS * NH, TM_O = TM_S + NS * 64, TM_AP = TM_O + NS * HDV,
+                       TM_PROJ = TM_AP + KPROJ / 2;
   static_assert(SMEM <= 232448, "shared memory budget");
-  static_assert(OFF_L % 1024 == 0 && OFF_E % 1024 == 0 && OFF_KV % 1024 == 0, "TMA tiles need 1024-byte alignment");
-  static_assert(CP / 2 <= 64 && NH <= 64 && HDV <= 32 && KPROJ / 2 <= 64 && NPC <= 64, "TMEM map");
+  static_assert(OFF_L % 1024 == 0 && OFF_E % 1024 == 0 && OFF_Y % 1024 == 0 && OFF_KV % 1024 == 0, "TMA tiles need 1024-byte alignment");
+  static_assert(TM_PROJ + NPC <= 512 && NPC % 16 == 0, "TMEM map");
 };
 
 __device__ __forceinline__ uint32_t xt_off(int row, int c) {          // 16-byte chunk c of token row `row` (SWIZZLE_128B panels)
@@ -130,8 +142,8 @@ __device__ __forceinline__ int win_region(const Geom& g, int wy, int wx, int iy,
 constexpr int THREADS = 640;
 enum Bar {
   B_W = 0, B_LFULL, B_EFULL, B_XH_READY, B_XH_FREE, B_AP_READY, B_PROJ_FULL, B_PROJ_DRAINED,
-  B_QKV_FULL = 8, B_QK_DRAINED = 10, B_V_DRAINED = 12, B_S_FULL = 14, B_P_READY = 16, B_O_FULL = 18, B_AP_FREE = 20, B_WREADY = 21,
-  B_STAGED = 22, NBARS = 23
+  B_QKV_FULL = 8, B_QK_DRAINED = 11, B_V_DRAINED = 14, B_S_FULL = 17, B_P_READY = 20, B_O_FULL = 23,      // one per slot (<= 3)
+  B_AP_FREE = 26, B_WREADY = 27, B_STAGED = 28, NBARS = 29
 };
 
 __device__ __forceinline__ void wgA_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -159,13 +171,14 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
   const int row = tid & 127;
   uint8_t* const sL = smem + K::OFF_L;
   uint8_t* const sE = smem + K::OFF_E;
+  uint8_t* const sY = smem + (K::YBUF ? K::OFF_Y : K::OFF_E);      // output staging (= E when there is no room for both)
 
   if (warp == 0) tmem_alloc<512>(&tmem_base_s);
   if (tid == 0) {
     for (int i = 0; i < NBARS; ++i) {
       const bool w4 = i == B_XH_READY || i == B_AP_READY || i == B_PROJ_DRAINED || (i >= B_QK_DRAINED && i < B_S_FULL) ||
                       (i >= B_P_READY && i < B_O_FULL);
-      mbar_init(&bars[i], w4 ? 4 : (i == B_XH_FREE ? 2 : 1));      // x^ is free when BOTH slot issuers are past their last qkv
+      mbar_init(&bars[i], w4 ? 4 : (i == B_XH_FREE ? K::NS : 1));  // x^ is free when ALL slot issuers are past their last qkv
     }
     fence_mbar_init();
     mbar_arrive_expect_tx(&bars[B_W], K::WQKV_BYTES + K::WPROJ_BYTES);
@@ -175,7 +188,7 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       bulk_g2s(smem + K::OFF_WPROJ + off, wproj_img + off, min(32768, K::WPROJ_BYTES - off), &bars[B_W]);
   }
   // K / V images start as zeros (pads must be, and stay, zero / finite); bias table -> shared memory
-  for (int i = tid; i < 2 * K::KV_BYTES / 16; i += THREADS)
+  for (int i = tid; i < K::NS * K::KV_BYTES / 16; i += THREADS)
     *reinterpret_cast<uint4*>(smem + K::OFF_KV + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
   for (int i = tid; i < 6 * K::TBL; i += THREADS)
     reinterpret_cast<uint32_t*>(smem + K::OFF_TAB)[i] = reinterpret_cast<const uint32_t*>(table)[i];
@@ -292,8 +305,8 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       wait_st();
       warp_arrive(&bars[B_XH_READY], lane);
     };
-    auto epi_block = [&](int pn, int hf) {                 // y = proj + bias + x for one column block, in place in the staging tile
-      mbar_wait(&bars[B_PROJ_FULL], (pn * K::NHALF + hf) & 1);
+    auto epi_block = [&](int pn, int hf) {                 // y = proj + bias + x for one column block -> staging tile
+      mbar_wait(&bars[B_PROJ_FULL], (pn * K::NBLK + hf) & 1);
       fence_after_sync();
       A2_STAMP();   // A: proj block ready
       uint32_t acc[K::NPC];
@@ -306,11 +319,20 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       }
       wait_ld();
       warp_arrive(&bars[B_PROJ_DRAINED], lane);            // the accumulator may be overwritten by the next block
-      if (hf == 0) mbar_wait(&bars[B_EFULL], pn & 1);
+      if (hf == 0) {
+        mbar_wait(&bars[B_EFULL], pn & 1);
+        if (K::YBUF && pn >= 1) {                          // the store of the previous tile (issued a whole tile ago) has left Y
+          if (warp == 0) {
+            if (elect_one()) bulk_wait_read();
+            __syncwarp();
+          }
+          wgA_sync();
+        }
+      }
 #pragma unroll
       for (int c0 = 0; c0 < K::NPC; c0 += 8) {
-        uint8_t* xp = sE + xt_off(row, (hf * K::NPC + c0) >> 3);
-        const uint4 xv = *reinterpret_cast<const uint4*>(xp);
+        const uint32_t off = xt_off(row, (hf * K::NPC + c0) >> 3);
+        const uint4 xv = *reinterpret_cast<const uint4*>(sE + off);
         const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
         uint32_t y[4];
 #pragma unroll
@@ -318,7 +340,7 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
           const float2 xf = up2(xw[e]);
           y[e] = pk2(__uint_as_float(acc[c0 + 2 * e]) + xf.x, __uint_as_float(acc[c0 + 2 * e + 1]) + xf.y);
         }
-        *reinterpret_cast<uint4*>(xp) = make_uint4(y[0], y[1], y[2], y[3]);
+        *reinterpret_cast<uint4*>(sY + off) = make_uint4(y[0], y[1], y[2], y[3]);
       }
     };
     if (warp == 0) {
@@ -328,15 +350,34 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 #pragma unroll 1
     for (int t = -1; t <= NT; ++t) {                       // t = -1: LayerNorm of the first tile only
       if (t + 1 < NT) ln_stats(t + 1);
-      if (t >= 1) epi_block(t - 1, 0);
+      // two slots: x^ of tile t+1 can only be written once head 5 of tile t has its qkv (about a third into tile t), the
+      // first proj block of tile t-1 arrives earlier.  Three slots: all qkv of tile t are issued during tile t-1, x^ first.
+      if (K::NS == 2 && t >= 1) epi_block(t - 1, 0);
       if (t + 1 < NT) ln_write(t + 1);
       if (t >= 1) {
-        if (K::NHALF == 2) epi_block(t - 1, 1);
+#pragma unroll
+        for (int hf = (K::NS == 2 ? 1 : 0); hf < K::NBLK; ++hf) epi_block(t - 1, hf);
         fence_proxy_async();                               // the finished rows are read by the TMA store (async proxy)
         wgA_sync();
         A2_STAMP();   // A: y staged
       }
-      if (t >= 1 && tid == 0) mbar_arrive(&bars[B_STAGED]);     // warp 19 stores the tile and refills E (below)
+      if (K::YBUF) {
+        // E and Y are separate: the store needs no wait here (Y is written again a whole tile later), and the residual rows
+        // of tile t (second fetch, an L2 hit) can land in E right away
+        if (warp == 0) {
+          if (elect_one()) {
+            if (t >= 1) store_tile(blockIdx.x + (t - 1) * gridDim.x, sY);
+            if (t >= 0 && t < NT) load_tile(blockIdx.x + t * gridDim.x, sE, &bars[B_EFULL]);
+          }
+          __syncwarp();
+        }
+      } else {
+        if (t >= 1 && tid == 0) mbar_arrive(&bars[B_STAGED]);   // warp 19 stores the tile and refills E (below)
+      }
+    }
+    if (K::YBUF && warp == 0) {
+      if (elect_one()) bulk_wait_read();
+      __syncwarp();
     }
   } else if (wg == 1) {
     // =============================== role B: qkv drain (head g), O / rowsum (head g-2) ===============================
@@ -349,11 +390,11 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     constexpr int NCO = (HD + 8) / 8 * 8;                      // head_dim values + the row-sum column: 16 / 16 / 24
     uint32_t fo[NCO];
     auto o_load = [&](int gp) {
-      const int s = gp & 1;
+      const int s = gp % K::NS;
 #pragma unroll
       for (int c0 = 0; c0 < NCO; c0 += 8) {
         uint32_t t[8];
-        tmem_ld_x8(lane_addr + K::TM_O + 32 * s + c0, t);
+        tmem_ld_x8(lane_addr + K::TM_O + K::HDV * s + c0, t);
 #pragma unroll
         for (int e = 0; e < 8; ++e) fo[c0 + e] = t[e];
       }
@@ -399,19 +440,20 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       }
     };
 #pragma unroll 1
-    for (int g = 0; g < G + 2; ++g) {
-      const int s = g & 1;
+    for (int g = 0; g < G + K::NS; ++g) {
+      const int s = g % K::NS;                                   // slot of head g (and of head g - NS, whose O is handled here)
+      const uint32_t ph = (g / K::NS) & 1;
       uint8_t* sBk = smem + K::OFF_KV + s * K::KV_BYTES;
       uint8_t* sBv = sBk + K::BK_BYTES;
       bool o_early = false;
-      if (g >= 2 && g < G && __all_sync(0xffffffffu, mbar_test(&bars[B_O_FULL + s], ((g - 2) >> 1) & 1))) {
+      if (g >= K::NS && g < G && __all_sync(0xffffffffu, mbar_test(&bars[B_O_FULL + s], ph ^ 1))) {
         fence_after_sync();
-        o_load(g - 2);
-        o_store(g - 2);
+        o_load(g - K::NS);
+        o_store(g - K::NS);
         o_early = true;
       }
       if (g < G) {
-        mbar_wait(&bars[B_QKV_FULL + s], (g >> 1) & 1);
+        mbar_wait(&bars[B_QKV_FULL + s], ph);
         fence_after_sync();
         A2_STAMP();   // B: qkv ready
         constexpr int NC = (3 * HD + 7) / 8 * 8;                // 32 / 48 / 64 accumulator columns: q | k | v
@@ -419,7 +461,7 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 #pragma unroll
         for (int c0 = 0; c0 < NC; c0 += 16) {
           uint32_t t[16];
-          tmem_ld_x16(lane_addr + K::TM_QKV + 64 * s + c0, t);
+          tmem_ld_x16(lane_addr + K::TM_QKV + NH * s + c0, t);
 #pragma unroll
           for (int e = 0; e < 16; ++e) f[c0 + e] = t[e];
         }
@@ -433,9 +475,9 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
           qp[e] = pk2(d0 < HD ? val(d0) : 0.f, d1 < HD ? val(d1) : 0.f);
         }
         if constexpr (K::HDP / 2 == 8) {
-          tmem_st_x8(lane_addr + K::TM_QKV + 64 * s, qp);
+          tmem_st_x8(lane_addr + K::TM_QKV + NH * s, qp);
         } else {
-          tmem_st_x16(lane_addr + K::TM_QKV + 64 * s, qp);
+          tmem_st_x16(lane_addr + K::TM_QKV + NH * s, qp);
         }
         // k -> K-major bf16 image (the previous S of this slot completed before this head's qkv did)
 #pragma unroll
@@ -466,10 +508,10 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         warp_arrive(&bars[B_QK_DRAINED + s], lane);
         A2_STAMP();   // B: q, k drained
       }
-      if (g >= 2 && !o_early) {
-        mbar_wait(&bars[B_O_FULL + s], ((g - 2) >> 1) & 1);      // PV(g-2) complete: O ready, the V image is free
+      if (g >= K::NS && !o_early) {
+        mbar_wait(&bars[B_O_FULL + s], ph ^ 1);                  // PV(g-NS) complete: O ready, the V image is free
         fence_after_sync();
-        o_load(g - 2);
+        o_load(g - K::NS);
       }
       if (g < G) {
 #pragma unroll
@@ -478,19 +520,20 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(&bars[B_V_DRAINED + s]);
       }
-      if (g >= 2 && !o_early) o_store(g - 2);
+      if (g >= K::NS && !o_early) o_store(g - K::NS);
     }
   } else if (wg < 4) {
     // =============================== roles C / D: softmax of even / odd heads, thread = one row x 64 keys ===============================
-    const int s = wg - 2;
+    const int wsm = wg - 2;                                      // this warpgroup takes heads g = wsm (mod 2)
     const uint32_t* sTab2 = reinterpret_cast<const uint32_t*>(smem + K::OFF_TAB);
     const int wsel = row >> 6, irow = row & 63, iy = row_iy(irow), ix = row_ix(irow);
-    const uint32_t tS = lane_addr + K::TM_S + 64 * s;
     __half2 mk[4];
     bool masked = false;
-    for (int g = s; g < G; g += 2) {
+    for (int g = wsm; g < G; g += 2) {
       const int n = g / 6, h = g - 6 * n;
-      if (h == s) {
+      const int s = g % K::NS;                                   // head slot
+      const uint32_t tS = lane_addr + K::TM_S + 64 * s;
+      if (h == wsm) {
         // shift mask of this tile (edge windows only): the region borders of calculate_mask (:321-341) cut a window
         // exactly between the 4x4 boxes that define the row order, so the mask of 64 keys is four per-box constants
         masked = false;
@@ -507,7 +550,7 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
           }
         }
       }
-      mbar_wait(&bars[B_S_FULL + s], (g >> 1) & 1);
+      mbar_wait(&bars[B_S_FULL + s], (g / K::NS) & 1);
       fence_after_sync();
       A2_STAMP();   // C/D: S ready
       uint32_t v0[32], v1[32];
@@ -568,7 +611,7 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     __syncwarp();
     if (lane == 0) mbar_arrive(&bars[B_WREADY]);
   }
-  if (warp == 19) {
+  if (!K::YBUF && warp == 19) {
     // =============================== E-side TMA: store of finished tiles, second fetch of the residual rows ===============================
     // A TMA store needs ~3000 cycles before it has read its 32 KB out of shared memory (16 small boxes; measured), and E
     // cannot take the next tile's residual rows earlier.  On the LayerNorm/epilogue role that wait delayed every proj
@@ -583,16 +626,15 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       __syncwarp();
     }
   }
-  if (wg == 4 && warp <= 18) {
+  if (wg == 4 && warp <= 16 + K::NS) {
     // =============================== MMA issue: three warps, each with its own static program ===============================
     // The tensor pipe executes MMAs in the order they are issued, whoever issues them.  All MMAs that touch the resources
     // of head slot s (its qkv accumulator / packed Q, its S / P columns, its O columns, its K / V images) are issued by
     // ONE warp (16 + s), so every "X before Y" on a slot holds by that warp's program order:
-    //     iteration j (heads of this slot):  PV(j) ;  S(j+2) ;  qkv(j+4)
-    // PV(j) waits for the softmax of head j; S(j+2) right behind it reuses the S/P columns PV(j) has just read, so the
-    // softmax warpgroup of the slot gets its next logits one MMA round trip after it delivered P; qkv(j+4) reuses the
-    // accumulator whose Q operand S(j+2) has just read (role B copied the rest into registers before it released q/k).
-    // Warp 18 issues the proj blocks.  Splitting the issue role matters because the control path of an issuer (barrier
+    //     iteration j (heads of this slot, NS apart):  PV(j) ;  S(j+NS) ;  qkv(j+2 NS)
+    // PV(j) waits for the softmax of head j; S(j+NS) right behind it reuses the S/P columns PV(j) has just read; qkv(j+2 NS)
+    // reuses the accumulator whose Q operand S(j+NS) has just read (role B copied the rest into registers before it
+    // released q/k).  Warp 16 + NS issues the proj blocks.  Splitting the issue role matters because the control path of an issuer (barrier
     // probes at ~100-150 cycles each, elect, commit) costs ~2000 cycles per head when one warp does everything (measured),
     // i.e. it, not the tensor pipe (~650 cycles of MMAs per head), paced the first version of this kernel.
     // The whole warp runs the loop with warp-uniform values and only the tcgen05 instructions sit under elect.sync:
@@ -605,9 +647,9 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     constexpr uint32_t ids = make_idesc_bf16(128, 64, false, false);
     constexpr uint32_t idv = make_idesc_f16(128, K::HDV, false, true);
     constexpr uint32_t idp = make_idesc_bf16(128, K::NPC, false, false);
-    if (warp == 18) {
-      for (int k = 0; k < NT * K::NHALF; ++k) {
-        const int pn = k / K::NHALF, hf = k - pn * K::NHALF;
+    if (warp == 16 + K::NS) {
+      for (int k = 0; k < NT * K::NBLK; ++k) {
+        const int pn = k / K::NBLK, hf = k - pn * K::NBLK;
         if (hf == 0) mbar_wait(&bars[B_AP_READY], pn & 1);
         if (k >= 1) mbar_wait(&bars[B_PROJ_DRAINED], (k - 1) & 1);               // previous block is in registers
         fence_after_sync();
@@ -617,13 +659,14 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
             mma_ts(tm + K::TM_PROJ, tm + K::TM_AP + ks * 8,
                    make_smem_desc(aWproj + hf * K::NPC * 16 + ks * 2 * (CP * 16), CP * 16, 128), idp, ks > 0);
           commit(&bars[B_PROJ_FULL]);
-          if (hf == K::NHALF - 1) commit(&bars[B_AP_FREE]);      // the normalised O of this tile has been read
+          if (hf == K::NBLK - 1) commit(&bars[B_AP_FREE]);       // the normalised O of this tile has been read
         }
         __syncwarp();
       }
     } else {
       const int s = warp - 16;                                   // head slot of this issuer
-      const uint32_t tQ = tm + K::TM_QKV + 64 * s, tS = tm + K::TM_S + 64 * s, tO = tm + K::TM_O + 32 * s;
+      constexpr int NS = K::NS;
+      const uint32_t tQ = tm + K::TM_QKV + NH * s, tS = tm + K::TM_S + 64 * s, tO = tm + K::TM_O + K::HDV * s;
       const uint32_t aBk = aKV + s * K::KV_BYTES, aBv = aBk + K::BK_BYTES;
       uint64_t* const bQKV = &bars[B_QKV_FULL + s];
       uint64_t* const bQK = &bars[B_QK_DRAINED + s];
@@ -637,7 +680,7 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         for (int ks = 0; ks < CP / 16; ++ks)
           mma_ts(tQ, tm + K::TM_XH + ks * 8, make_smem_desc(wb + ks * 2 * (NH * 16), NH * 16, 128), idq, ks > 0);
         commit(bQKV);
-        if (h >= 4) commit(&bars[B_XH_FREE]);                    // last qkv of this slot in the tile (two arrivals free x^)
+        if (h >= 6 - NS) commit(&bars[B_XH_FREE]);               // last qkv of this slot in the tile (NS arrivals free x^)
       };
       auto s_mmas = [&]() {
 #pragma unroll
@@ -657,19 +700,20 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                                w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
         commit(bO);
       };
-      // head g of this slot is its (g >> 1)-th: that is the phase index of all per-slot barriers
-      // prologue: qkv(s) ; S(s) ; qkv(s+2)
+      // head g of this slot is its (g / NS)-th: that is the phase index of all per-slot barriers.
+      //     iteration j:  PV(j) ;  S(j+NS) ;  qkv(j+2 NS)
+      // prologue: qkv(s) ; S(s) ; qkv(s+NS)
       mbar_wait(&bars[B_XH_READY], 0);
       fence_after_sync();
       if (elect_one()) qkv_mmas(s);
       __syncwarp();
       mbar_wait(bQK, 0);
       fence_after_sync();
-      if (elect_one()) { s_mmas(); qkv_mmas(s + 2); }
+      if (elect_one()) { s_mmas(); qkv_mmas(s + NS); }
       __syncwarp();
-      for (int j = s; j < G; j += 2) {
-        const uint32_t ph = (j >> 1) & 1;
-        // softmax of head j delivered P; role B wrote V (which also means O of head j-2 is in its registers)
+      for (int j = s; j < G; j += NS) {
+        const uint32_t ph = (j / NS) & 1;
+        // softmax of head j delivered P; role B wrote V (which also means O of head j-NS is in its registers)
         while (true) {
           const bool p_ok = mbar_try_wait(bP, ph), v_ok = mbar_try_wait(bV, ph);
           if (p_ok && v_ok) break;
@@ -679,22 +723,22 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         if (elect_one()) pv_mmas();
         __syncwarp();
         A2_STAMP();   // MMA: PV issued
-        if (j + 2 < G) {
+        if (j + NS < G) {
           mbar_wait(bQK, ph ^ 1);
           fence_after_sync();
-          const int g4 = j + 4, h4 = g4 % 6;
-          const bool q_fused = g4 < G && h4 >= 2;                // qkv(j+4) of the same tile: goes out in the same breath
+          const int g4 = j + 2 * NS, h4 = g4 % 6;
+          const bool q_fused = g4 < G && h4 >= NS;               // qkv of the same tile as S(j+NS): goes out in the same breath
           if (elect_one()) {
             s_mmas();
             if (q_fused) qkv_mmas(h4);
           }
           __syncwarp();
           A2_STAMP();   // MMA: S (+ qkv) issued
-          if (g4 < G && h4 < 2) {
+          if (g4 < G && h4 < NS) {
             // first head of this slot in the next tile: x^ of that tile has to be in TMEM.  This warp has nothing else
-            // to do until the softmax of head j+2 delivers (> 1000 cycles), so it simply waits here; everything the
-            // LayerNorm role needs on the way (both issuers past head 5's qkv, the proj blocks of the tile before) is
-            // issued by other warps or earlier in this program.
+            // to do until the softmax of head j+NS delivers (> 1000 cycles), so it simply waits here; everything the
+            // LayerNorm role needs on the way (all issuers past their last qkv of the tile, the proj blocks of the tile
+            // before) is issued by other warps or earlier in this program.
             mbar_wait(&bars[B_XH_READY], (g4 / 6) & 1);
             fence_after_sync();
             if (elect_one()) qkv_mmas(h4);
