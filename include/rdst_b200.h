@@ -83,6 +83,13 @@ int rdst_conv3x3_fwd(const void* x, int64_t ldx, const float* w, const float* bi
                      int B, int H, int W, int Cin, int N, float out_scale, int shuffle,
                      int dtype, void* stream);
 
+/* 3x3 same-padding convolution followed by an activation (act: 0 none, 1 GELU, 2 LeakyReLU(0.2)); same layout rules as
+ * rdst_conv3x3_fwd, no residual / scale / shuffle:  y[t][n] = act(conv + bias).  Rows n >= the real output channels must be
+ * zero in w / bias so that pad channels stay zero.  rdst_linear_fwd accepts the same act codes (1x1 convolution).
+ * Replaces the Conv2d + LeakyReLU pairs of RDSTB's '3conv' fusion (rdst_variations.py:422-427). */
+int rdst_conv3x3_act_fwd(const void* x, int64_t ldx, const float* w, const float* bias, void* y, int64_t ldy,
+                         int B, int H, int W, int Cin, int N, int act, int dtype, void* stream);
+
 /* Shallow feature extraction: img (B,1,H,W) fp32 NCHW -> feat0[t][0:64] = conv3x3(1->60) (kept for the global
  * residual) and dense[t][0:64] = LayerNorm_60(feat0) * gamma + beta (patch_embed.norm), pads zero.
  * `in_scale`/`in_bias` fold sub_mean (MeanShift 1x1).  w : [60][9], bias/gamma/beta : [60].

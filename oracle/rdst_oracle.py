@@ -145,7 +145,14 @@ def rdstb(x, H, W, sd, pfx, n_dstl=3, res_scale=1.0, dense_scale=1.0, rnd=None):
     short = x
     for j in range(n_dstl):
         x = dense_st_layer(x, H, W, sd, f"{pfx}body.{j}.", dense_scale, rnd)
-    y = map_to_tokens(conv3x3(tokens_to_map(x, H, W), sd, pfx + "conv.")) * res_scale
+    m = tokens_to_map(x, H, W)
+    if pfx + "conv.0.weight" in sd:          # resi_connection = '3conv' (rdst_variations.py:422-427)
+        m = F.leaky_relu(conv3x3(m, sd, pfx + "conv.0."), 0.2)
+        m = F.leaky_relu(F.conv2d(m, sd[pfx + "conv.2.weight"], sd[pfx + "conv.2.bias"]), 0.2)
+        m = conv3x3(m, sd, pfx + "conv.4.")
+    else:
+        m = conv3x3(m, sd, pfx + "conv.")
+    y = map_to_tokens(m) * res_scale
     y = y + short
     if rnd is not None:
         y = rnd(y, "trunk")
@@ -154,7 +161,7 @@ def rdstb(x, H, W, sd, pfx, n_dstl=3, res_scale=1.0, dense_scale=1.0, rnd=None):
 
 def count_blocks(sd):
     n = 0
-    while f"body.{n}.conv.weight" in sd:
+    while f"body.{n}.conv.weight" in sd or f"body.{n}.conv.0.weight" in sd:
         n += 1
     return n
 
@@ -209,7 +216,12 @@ def forward(sd, x, sr_scale=4, rnd=None, taps=None, global_res_scale=1.0, featur
         t = F.layer_norm(t, (t.shape[-1],), sd["norm.weight"], sd["norm.bias"], 1e-5)
         res = tokens_to_map(t, H, W) * global_res_scale
         if feature_last_operation:
-            res = conv3x3(res, sd, "conv_after_body.")
+            if "conv_after_body.0.weight" in sd:     # '3conv' (rdst_variations.py:1286-1292)
+                res = F.leaky_relu(conv3x3(res, sd, "conv_after_body.0."), 0.2)
+                res = F.leaky_relu(F.conv2d(res, sd["conv_after_body.2.weight"], sd["conv_after_body.2.bias"]), 0.2)
+                res = conv3x3(res, sd, "conv_after_body.4.")
+            else:
+                res = conv3x3(res, sd, "conv_after_body.")
     res = res + x0
     if rnd is not None:
         res = rnd(res, "feat")

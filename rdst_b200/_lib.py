@@ -42,6 +42,7 @@ _SIGNATURES = {
     "rdst_linear_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i64, _i, _i, _i, _i, _f, _i, _vp]),
     "rdst_window_attention_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rdst_conv3x3_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _i, _i, _vp]),
+    "rdst_conv3x3_act_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i, _i, _i, _i, _i, _i, _i, _vp]),
     "rdst_head_fwd": (C.c_int, [_vp, _f, _f, _vp, _vp, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _vp]),
     "rdst_layernorm_fwd": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _i64, _i, _f, _i, _vp]),
     "rdst_last_conv_fwd": (C.c_int, [_vp, _i64, _vp, _f, _f, _f, _vp, _i, _i, _i, _i, _i, _vp]),

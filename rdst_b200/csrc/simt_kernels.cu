@@ -153,6 +153,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(GemmArgs a) {
       if (n >= a.N) continue;
       float v = acc[i][j] + (a.bias ? __ldg(a.bias + n) : 0.f);
       if (a.act == 1) v = gelu_erf(v);
+      else if (a.act == 2) v = v > 0.f ? v : 0.2f * v;      // nn.LeakyReLU(0.2) of the '3conv' fusion (rdst_variations.py:424-426)
       v *= a.out_scale;
       if (CONV && a.shuffle) {
         const int G = a.N >> 2;
@@ -441,7 +442,7 @@ extern "C" int rdst_linear_fwd(const void* x, int64_t ldx, const float* w, const
   RDST_REQUIRE(T >= 0 && K > 0 && N > 0 && ldx >= K && ldy >= N, "rdst_linear_fwd: bad shape T=%lld K=%d N=%d ldx=%lld ldy=%lld",
                (long long)T, K, N, (long long)ldx, (long long)ldy);
   RDST_REQUIRE(ln_creal >= 0 && ln_creal <= K, "rdst_linear_fwd: ln_creal=%d out of range for K=%d", ln_creal, K);
-  RDST_REQUIRE(act == 0 || act == 1, "rdst_linear_fwd: act must be 0 or 1");
+  RDST_REQUIRE(act >= 0 && act <= 2, "rdst_linear_fwd: act must be 0 (none), 1 (GELU) or 2 (LeakyReLU 0.2)");
   RDST_REQUIRE(dtype == RDST_F32 || dtype == RDST_BF16, "rdst_linear_fwd: bad dtype %d", dtype);
   if (T == 0) return RDST_OK;
   GemmArgs a{};
@@ -472,6 +473,25 @@ extern "C" int rdst_conv3x3_fwd(const void* x, int64_t ldx, const float* w, cons
   if (dtype == RDST_F32) gemm_simt_kernel<float, true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   else gemm_simt_kernel<__nv_bfloat16, true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
   RDST_CHECK_LAUNCH("rdst_conv3x3_fwd");
+  return RDST_OK;
+}
+
+extern "C" int rdst_conv3x3_act_fwd(const void* x, int64_t ldx, const float* w, const float* bias, void* y, int64_t ldy,
+                                    int B, int H, int W, int Cin, int N, int act, int dtype, void* stream) {
+  RDST_REQUIRE(x && w && y, "rdst_conv3x3_act_fwd: null pointer");
+  RDST_REQUIRE(B >= 0 && H > 0 && W > 0 && Cin > 0 && N > 0, "rdst_conv3x3_act_fwd: bad shape");
+  RDST_REQUIRE(Cin % 16 == 0 && ldx >= Cin && ldy >= N, "rdst_conv3x3_act_fwd: Cin (%d) must be a multiple of 16 and <= ldx", Cin);
+  RDST_REQUIRE(act >= 0 && act <= 2, "rdst_conv3x3_act_fwd: act must be 0 (none), 1 (GELU) or 2 (LeakyReLU 0.2)");
+  RDST_REQUIRE(dtype == RDST_F32 || dtype == RDST_BF16, "rdst_conv3x3_act_fwd: bad dtype %d", dtype);
+  if (B == 0) return RDST_OK;
+  GemmArgs a{};
+  a.x = x; a.ldx = ldx; a.w = w; a.bias = bias; a.r = nullptr; a.ldr = 0; a.y = y; a.ldy = ldy;
+  a.T = (int64_t)B * H * W; a.K = 9 * Cin; a.N = N; a.out_scale = 1.0f; a.act = act;
+  a.B = B; a.H = H; a.W = W; a.Cin = Cin; a.shuffle = 0;
+  dim3 grid((unsigned)((a.T + BM - 1) / BM), (unsigned)((N + BN - 1) / BN));
+  if (dtype == RDST_F32) gemm_simt_kernel<float, true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  else gemm_simt_kernel<__nv_bfloat16, true><<<grid, 256, 0, (cudaStream_t)stream>>>(a);
+  RDST_CHECK_LAUNCH("rdst_conv3x3_act_fwd");
   return RDST_OK;
 }
 

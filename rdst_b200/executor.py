@@ -26,6 +26,21 @@ def ptr(t):
     return _lib.ptr(t)
 
 
+def _pack_3conv(seq, cin_pos, cin_width, device):
+    """Conv 3x3 (Cin -> mid) + LeakyReLU, conv 1x1 (mid -> mid) + LeakyReLU, conv 3x3 (mid -> 60): the '3conv' fusion of
+    RDSTB / conv_after_body (rdst_variations.py:422-427, :1286-1292).  mid real channels are stored 16-aligned, pads zero."""
+    c0, c2, c4 = seq[0], seq[2], seq[4]
+    mid = c0.weight.shape[0]
+    midp = (mid + 15) // 16 * 16
+    w0, b0 = packing.pack_conv(c0.weight, c0.bias, cin_pos, cin_width, midp)
+    w2 = torch.zeros(midp, midp, device=device)
+    w2[:mid, :mid] = c2.weight.detach().float().reshape(mid, mid)
+    b2 = torch.zeros(midp, device=device)
+    b2[:mid] = c2.bias.detach().float()
+    w4, b4 = packing.pack_conv(c4.weight, c4.bias, torch.arange(mid, device=device), midp, 64)
+    return dict(w0=w0, b0=b0, w2=w2.contiguous(), b2=b2, w4=w4, b4=b4, midp=midp)
+
+
 class Executor:
     def __init__(self, module):
         self._module = weakref.ref(module)
@@ -68,8 +83,11 @@ class Executor:
                         tail=packing.pack_dstl_tail(dstl, c, m.dense_scale)))
                     c += packing.GROWTH
                 pos = packing.channel_positions(c, device)
-                B["lff_w"], B["lff_b"] = packing.pack_conv(blk.conv.weight, blk.conv.bias, pos, packing.DENSE_LD, 64)
-                B["lff_img"] = packing.conv_tc_image(B["lff_w"])
+                if getattr(blk, "resi_connection", "1conv") == "3conv":
+                    B["c3"] = _pack_3conv(blk.conv, pos, packing.DENSE_LD, device)     # 150 -> 37 (stored 48) -> 37 -> 60
+                else:
+                    B["lff_w"], B["lff_b"] = packing.pack_conv(blk.conv.weight, blk.conv.bias, pos, packing.DENSE_LD, 64)
+                    B["lff_img"] = packing.conv_tc_image(B["lff_w"])
                 P["blocks"].append(B)
             f = lambda t: t.detach().float().contiguous()
             id60 = torch.arange(60, device=device)
@@ -77,9 +95,13 @@ class Executor:
             P["head_b"] = f(m.head.bias)
             P["pe_g"], P["pe_b"] = f(m.patch_embed.norm.weight), f(m.patch_embed.norm.bias)
             P["norm_g"], P["norm_b"] = f(m.norm.weight), f(m.norm.bias)
-            P["cab_w"], P["cab_b"] = packing.pack_conv(m.conv_after_body.weight, m.conv_after_body.bias, id60, 64, 64)
+            if isinstance(m.conv_after_body, torch.nn.Sequential):
+                P["cab3"] = _pack_3conv(m.conv_after_body, id60, 64, device)                 # 60 -> 15 (stored 16) -> 15 -> 60
+                P["cab_w"] = P["cab_b"] = None
+            else:
+                P["cab_w"], P["cab_b"] = packing.pack_conv(m.conv_after_body.weight, m.conv_after_body.bias, id60, 64, 64)
             P["up"] = [packing.pack_upconv(l.weight, l.bias) for l in m.tail[0] if isinstance(l, torch.nn.Conv2d)]
-            P["cab_img"] = packing.conv_tc_image(P["cab_w"])
+            P["cab_img"] = packing.conv_tc_image(P["cab_w"]) if P["cab_w"] is not None else None
             P["up_img"] = [packing.conv_tc_image(w) for w, _ in P["up"]]
             last = m.tail[1]
             lw = last.weight.new_zeros(9, 64, dtype=torch.float32)
@@ -183,8 +205,11 @@ class Executor:
                 if not fuse_tail:
                     call("rdst_linear_fwd", ptr(src), lds, ptr(t["w"]), ptr(t["b"]), None, 0,
                          ptr(D[cur][:, off:]), 160, T, ds["stl"][0]["cp"], 32, ds["c"], 0, t["scale"], dt, st)
-            self._conv(D[cur], 160, blk["lff_w"], blk["lff_img"], blk["lff_b"], D[cur], 160, D[1 - cur], 160,
-                       B, H, W, 160, 64, float(m.rdb_residual_scale), 0, dt, st)
+            if "c3" in blk:
+                self._conv3(blk["c3"], D[cur], 160, 160, D[cur], 160, D[1 - cur], 160, B, H, W, float(m.rdb_residual_scale), ws, dt, st)
+            else:
+                self._conv(D[cur], 160, blk["lff_w"], blk["lff_img"], blk["lff_b"], D[cur], 160, D[1 - cur], 160,
+                           B, H, W, 160, 64, float(m.rdb_residual_scale), 0, dt, st)
             cur = 1 - cur
             self._block_done(bi, D[cur], dict(P=P, ws=ws, B=B, H=H, W=W, T=T, dt=dt, st=st))
         feat = self._deep_features(D[cur], P, ws, B, H, W, T, dt, st)
@@ -203,6 +228,18 @@ class Executor:
                  ptr(out), B, h, w_, 64, dt, st)
         return out if (given or x.dtype == torch.float32) else out.to(x.dtype)
 
+    def _conv3(self, c3, x, ldx, cin, r, ldr, y, ldy, B, H, W, scale, ws, dt, st):
+        """y = scale * conv3x3(lrelu(conv1x1(lrelu(conv3x3(x))))) + r  -- the '3conv' fusion on the generic CUDA-core kernels."""
+        T, mp = B * H * W, c3["midp"]
+        key = ("c3", mp)
+        if key not in ws:
+            ws[key] = [torch.empty(T, mp, dtype=x.dtype, device=x.device) for _ in range(2)]
+        ta, tb = ws[key]
+        call("rdst_conv3x3_act_fwd", ptr(x), ldx, ptr(c3["w0"]), ptr(c3["b0"]), ptr(ta), mp, B, H, W, cin, mp, 2, dt, st)
+        call("rdst_linear_fwd", ptr(ta), mp, ptr(c3["w2"]), ptr(c3["b2"]), None, 0, ptr(tb), mp, T, mp, mp, 0, 2, 1.0, dt, st)
+        call("rdst_conv3x3_fwd", ptr(tb), mp, ptr(c3["w4"]), ptr(c3["b4"]), ptr(r), ldr, ptr(y), ldy,
+             B, H, W, mp, 64, scale, 0, dt, st)
+
     def _rdstbs(self, m):
         """The RDSTB modules of the network in execution order."""
         return list(m.body)
@@ -219,7 +256,9 @@ class Executor:
         m = self._module()
         call("rdst_layernorm_fwd", ptr(trunk), 160, ptr(P["norm_g"]), ptr(P["norm_b"]), ptr(ws["FN"]), 64,
              T, 60, float(m.global_res_scale), dt, st)
-        if m.feature_last_operation:
+        if m.feature_last_operation and P.get("cab3") is not None:
+            self._conv3(P["cab3"], ws["FN"], 64, 64, ws["F0"], 64, ws["F1"], 64, B, H, W, 1.0, ws, dt, st)
+        elif m.feature_last_operation:
             self._conv(ws["FN"], 64, P["cab_w"], P["cab_img"], P["cab_b"], ws["F0"], 64, ws["F1"], 64,
                        B, H, W, 64, 64, 1.0, 0, dt, st)
         else:

@@ -100,7 +100,7 @@ class RDSTB(nn.Module):
     """rdst_variations.py:354-445: dense Swin layers + 3x3 local-feature-fusion conv + residual."""
 
     def __init__(self, input_dim, input_resolution, layer_depth, num_heads, mlp_ratio, qkv_bias, qk_scale,
-                 growth_rate, num_blocks):
+                 growth_rate, num_blocks, resi_connection='1conv'):
         super().__init__()
         self.body = nn.ModuleList()
         dim = input_dim
@@ -108,7 +108,13 @@ class RDSTB(nn.Module):
             self.body.append(DenseSTLayer(dim, input_resolution, layer_depth, num_heads, mlp_ratio,
                                           qkv_bias, qk_scale, growth_rate))
             dim += growth_rate
-        self.conv = nn.Conv2d(dim, input_dim, 3, 1, 1)
+        if resi_connection == '1conv':
+            self.conv = nn.Conv2d(dim, input_dim, 3, 1, 1)
+        else:                                       # '3conv' (rdst_variations.py:422-427): bottleneck fusion, dim // 4 channels
+            self.conv = nn.Sequential(nn.Conv2d(dim, dim // 4, 3, 1, 1), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                                      nn.Conv2d(dim // 4, dim // 4, 1, 1, 0), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                                      nn.Conv2d(dim // 4, input_dim, 3, 1, 1))
+        self.resi_connection = resi_connection
 
 
 class PatchEmbed(nn.Module):
@@ -176,7 +182,7 @@ class RDSTSR(nn.Module):
         if norm_layer is not nn.LayerNorm: _unsupported("norm_layer other than nn.LayerNorm")
         if ape: _unsupported("absolute position embedding")
         if not patch_norm: _unsupported("patch_norm=False")
-        if resi_connection != '1conv': _unsupported(f"resi_connection={resi_connection!r}")
+        if resi_connection not in ('1conv', '3conv'): _unsupported(f"resi_connection={resi_connection!r}")
         if dim_modify_mode != 'tail' or not pre_norm: _unsupported("dim_modify_mode != 'tail' or pre_norm=False")
         if scale_free or scale_embedding: _unsupported("scale_free / scale_embedding")
         if int(sr_scale) not in (2, 4): _unsupported(f"sr_scale={sr_scale}")
@@ -208,9 +214,15 @@ class RDSTSR(nn.Module):
         self.patch_embed = PatchEmbed(embed_dim, patch_norm)
         self.body = nn.ModuleList([
             RDSTB(embed_dim, img, dense_layer_depths[i], num_heads[i], mlp_ratio, qkv_bias, qk_scale,
-                  growth_rate, rdb_depths[i]) for i in range(n)])
+                  growth_rate, rdb_depths[i], resi_connection) for i in range(n)])
+        self.resi_connection = resi_connection
         self.norm = nn.LayerNorm(embed_dim)
-        self.conv_after_body = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
+        if resi_connection == '1conv':
+            self.conv_after_body = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
+        else:                                       # '3conv' (rdst_variations.py:1286-1292)
+            self.conv_after_body = nn.Sequential(nn.Conv2d(embed_dim, embed_dim // 4, 3, 1, 1), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                                                 nn.Conv2d(embed_dim // 4, embed_dim // 4, 1, 1, 0), nn.LeakyReLU(negative_slope=0.2, inplace=True),
+                                                 nn.Conv2d(embed_dim // 4, embed_dim, 3, 1, 1))
         up = []
         s = self.sr_scale
         while s > 1:
@@ -356,6 +368,7 @@ class ESTSR(RDSTSR):
                          global_res_scale=global_res_scale, mean=mean, std=std, act_in_conv=act_in_conv,
                          bn_in_conv=bn_in_conv, scale_free=scale_free, pre_norm=pre_norm, feature_last_operation=False,
                          precision=precision)
+        if resi_connection != '1conv': _unsupported("ESTSR with resi_connection other than '1conv'")
         img = (img_size, img_size) if isinstance(img_size, int) else tuple(img_size)
         self.body = nn.ModuleList([
             RRDSTB(embed_dim, img, dense_layer_depths[i], num_heads[i], mlp_ratio, qkv_bias, qk_scale, growth_rate,

@@ -32,6 +32,8 @@ def rdst_linear_fwd(x, ldx, w, bias, resid, ldr, y, ldy, T, K, N, ln_creal, act,
     v = a @ w.t() + bias
     if act == 1:
         v = F.gelu(v)
+    elif act == 2:
+        v = F.leaky_relu(v, 0.2)
     v = v * out_scale
     if resid is not None:
         assert resid.stride(0) == ldr
@@ -64,6 +66,14 @@ def rdst_window_attention_fwd(qkv, ldq, table, out, ldo, B, H, W, C, heads, shif
     if shift:
         o = torch.roll(o, (shift, shift), (1, 2))
     _store(out, o.reshape(-1, C))
+
+
+def rdst_conv3x3_act_fwd(x, ldx, w, bias, y, ldy, B, H, W, Cin, N, act, dt, st):
+    a = x[:, :Cin].float().reshape(B, H, W, Cin).permute(0, 3, 1, 2)
+    assert w.shape == (N, 9, Cin)
+    v = F.conv2d(a, w.reshape(N, 3, 3, Cin).permute(0, 3, 1, 2), bias, padding=1)
+    v = F.gelu(v) if act == 1 else (F.leaky_relu(v, 0.2) if act == 2 else v)
+    _store(y, v.permute(0, 2, 3, 1).reshape(-1, N))
 
 
 def rdst_conv3x3_fwd(x, ldx, w, bias, resid, ldr, y, ldy, B, H, W, Cin, N, out_scale, shuffle, dt, st):

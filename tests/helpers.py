@@ -119,7 +119,7 @@ def load_rdstn_case(name):
     sd["add_mean.weight"][:] = 1
     sd = fill_state_dict(sd, int(g["meta_wseed"]), True)
     x = synth_input(tuple(int(v) for v in g["shape"]), int(g["meta_xseed"]))
-    mode = "conv" if sd["bottleneck.0.weight"].dim() == 4 else "mlp"
+    mode = None if "bottleneck.0.weight" not in sd else ("conv" if sd["bottleneck.0.weight"].dim() == 4 else "mlp")
     return dict(g=g, sd=sd, x=x, blocks=blocks, scale=scale, mode=mode)
 
 
@@ -157,3 +157,21 @@ def make_estsr(c, precision="fp32"):
     return rdst_b200.ESTSR(img_size=24, sr_scale=c["scale"], dense_layer_depths=[2] * n, num_heads=[6] * n, window_size=[8] * n,
                            rdb_depths=[3] * n, rrdb_depths=[c["n_rd"]] * n, num_rrdb_blocks=n, mlp_ratio=2., pre_norm=True,
                            precision=precision)
+
+
+# ---- RDSTSR with resi_connection = '3conv' (SURVEY 8f row 3): fixtures from oracle/gen_golden_3conv.py ----
+C3_CASES = ["rdst3conv_2blk_x4_16x24_b2", "rdst3conv_3blk_x2_24x24"]
+
+
+def load_3conv_case(name):
+    c = load_rdstn_case(name)           # same fixture format (manifest + npz)
+    c.pop("mode", None)
+    return c
+
+
+def make_3conv(c, precision="fp32"):
+    import rdst_b200
+    b = c["blocks"]
+    return rdst_b200.RDSTSR(img_size=24, sr_scale=c["scale"], dense_layer_depths=[2] * b, num_heads=[6] * b, window_size=[8] * b,
+                            rdb_depths=[3] * b, mlp_ratio=2., pre_norm=True, feature_last_operation=True,
+                            resi_connection="3conv", precision=precision)
