@@ -281,6 +281,20 @@ int rdst_conv3x3_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, const
 int rdst_last_conv_fwd_bf16_tc(const void* x, int64_t ldx, const void* wimg, float bias, float out_scale,
                                float out_bias, float* img, int B, int H, int W, void* stream);
 
+/* ---- LR synthesis and image metrics (rdst_b200/csrc/imaging.cu) -------------------------------------- */
+/* cv2.resize(img, dsize, interpolation=cv2.INTER_CUBIC) of B single-channel fp32 images [B][Hs][Ws] -> [B][Hd][Wd], as
+ * MedicalImageBasicDataset.resize uses it for LR synthesis and the bicubic "res" images (datasets/basic_dataset.py:65-123,
+ * :258-301).  ix/cx ([Wd][4]) and iy/cy ([Hd][4]) are the clamped tap indices and cubic weights (A = -0.75) of every output
+ * column / row, built by the host (rdst_b200/imaging.py) exactly as OpenCV derives them; 16-byte aligned. */
+int rdst_bicubic_resize_f32(const float* src, float* dst, const int* ix, const float* cx, const int* iy, const float* cy,
+                            int B, int Hs, int Ws, int Hd, int Wd, void* stream);
+/* out[b] += sum_i (a[b][i] - b[b][i])^2 in fp64 (out pre-zeroed): MSE / PSNR of metrics/sr_metrics.py:8-9. */
+int rdst_sqdiff_sum_f64(const float* a, const float* b, double* out_zeroed, int B, int64_t n_per_image, void* stream);
+/* out[b] += sum of the SSIM map over the valid region [3,H-3) x [3,W-3) (7x7 uniform window, sample covariance, K1 = 0.01,
+ * K2 = 0.03, data_range 1): skimage.metrics.structural_similarity as metrics/sr_metrics.py:12-13 calls it; the caller
+ * divides by (H-6)(W-6). */
+int rdst_ssim_sum_f64(const float* a, const float* b, double* out_zeroed, int B, int H, int W, void* stream);
+
 /* Debug hook: when given a device buffer of 128 uint64, CTA 0 of every following rdst_stl_attn_fwd_bf16 launch records
  * clock64() at its phase boundaries (64 stamps per warpgroup).  Pass NULL to switch it off (the default). */
 int rdst_debug_attn_timing(void* device_buffer_128_u64);

@@ -69,6 +69,9 @@ _SIGNATURES = {
     "rdst_conv3x3_fwd_bf16_tc": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _i64, _vp, _i64, _i, _i, _i, _i, _i, _f, _i, _vp]),
     "rdst_last_conv_fwd_bf16_tc": (C.c_int, [_vp, _i64, _vp, _f, _f, _f, _vp, _i, _i, _i, _vp]),
     "rdst_stl_mlp_tail_fwd_bf16": (C.c_int, [_vp, _i64, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i64, _f, _i64, _i, _i, _vp]),
+    "rdst_bicubic_resize_f32": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _vp, _i, _i, _i, _i, _i, _vp]),
+    "rdst_sqdiff_sum_f64": (C.c_int, [_vp, _vp, _vp, _i, _i64, _vp]),
+    "rdst_ssim_sum_f64": (C.c_int, [_vp, _vp, _vp, _i, _i, _i, _vp]),
     "rdst_debug_attn_timing": (C.c_int, [_vp]),
     "rdst_debug_attn_variant": (C.c_int, [_i]),
     "rdst_debug_attn2_timing": (C.c_int, [_vp]),
