@@ -114,8 +114,15 @@ def swin_block(x, H, W, sd, pfx, shift, rnd=None):
 
 
 def dense_st_layer(x, H, W, sd, pfx, dense_scale=1.0, rnd=None):
-    """'tail' mode with pre_norm: body(2 STL) -> LN -> Linear(C,growth) -> cat  [rdst_variations.py:335-341]"""
+    """'tail' mode with pre_norm: body(2 STL) -> LN -> Linear(C,growth) -> cat  [rdst_variations.py:335-341];
+    'head' mode [:288-295]: LN -> Linear(C,growth) -> body(2 STL at width growth) -> cat."""
     C = x.shape[-1]
+    if pfx + "head.0.weight" in sd:
+        y = F.layer_norm(x, (C,), sd[pfx + "head.0.weight"], sd[pfx + "head.0.bias"], 1e-5)
+        y = F.linear(y, sd[pfx + "head.1.weight"], sd[pfx + "head.1.bias"])
+        y = swin_block(y, H, W, sd, pfx + "body.blocks.0.", 0, rnd)
+        y = swin_block(y, H, W, sd, pfx + "body.blocks.1.", WS // 2, rnd) * dense_scale
+        return torch.cat((x, y), dim=2)
     y = swin_block(x, H, W, sd, pfx + "body.blocks.0.", 0, rnd)
     if rnd is not None:
         y = rnd(y, "stl_out")

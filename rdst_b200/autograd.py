@@ -900,9 +900,9 @@ class BottleneckFunction(torch.autograd.Function):
 def forward_with_grad(executor, x):
     m = executor._module()
     _check_trainable(m)
-    if getattr(m, "resi_connection", "1conv") != "1conv":
-        raise NotImplementedError("rdst_b200: training with resi_connection='3conv' is not implemented (inference only); "
-                                  "the E1 configuration trains with '1conv'")
+    if getattr(m, "resi_connection", "1conv") != "1conv" or getattr(m, "dim_modify_mode", "tail") != "tail":
+        raise NotImplementedError("rdst_b200: training with resi_connection='3conv' or dim_modify_mode='head' is not implemented "
+                                  "(inference only); the E1 configuration trains with '1conv' / 'tail'")
     tc = m.precision == "bf16"
     if tc and not _lib.load().rdst_has_tcgen05():
         raise RuntimeError("rdst_b200: precision='bf16' training needs the tcgen05 kernels (sm_100a device)")

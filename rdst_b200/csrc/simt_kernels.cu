@@ -502,11 +502,12 @@ static int launch_wattn(const void* qkv, int64_t ldq, const float* table, void* 
   const TA* q = reinterpret_cast<const TA*>(qkv);
   TA* o = reinterpret_cast<TA*>(out);
   switch (C / heads) {
+    case 5:  window_attention_simt_kernel<TA, 5><<<grid, 64, 0, st>>>(q, ldq, table, o, ldo, H, W, C, heads, shift); break;
     case 10: window_attention_simt_kernel<TA, 10><<<grid, 64, 0, st>>>(q, ldq, table, o, ldo, H, W, C, heads, shift); break;
     case 15: window_attention_simt_kernel<TA, 15><<<grid, 64, 0, st>>>(q, ldq, table, o, ldo, H, W, C, heads, shift); break;
     case 20: window_attention_simt_kernel<TA, 20><<<grid, 64, 0, st>>>(q, ldq, table, o, ldo, H, W, C, heads, shift); break;
     case 30: window_attention_simt_kernel<TA, 30><<<grid, 64, 0, st>>>(q, ldq, table, o, ldo, H, W, C, heads, shift); break;
-    default: set_error("rdst_window_attention_fwd: head_dim %d unsupported (10,15,20,30)", C / heads); return RDST_E_UNSUPPORTED;
+    default: set_error("rdst_window_attention_fwd: head_dim %d unsupported (5,10,15,20,30)", C / heads); return RDST_E_UNSUPPORTED;
   }
   return RDST_OK;
 }

@@ -76,11 +76,19 @@ class Executor:
                 B = {"dstl": []}
                 c = packing.EMBED
                 for dstl in blk.body:
-                    B["dstl"].append(dict(
-                        c=c,
-                        stl=[packing.pack_stl_tc(packing.pack_stl(b, c)) for b in dstl.body.blocks],
-                        shifts=[b.shift_size for b in dstl.body.blocks],
-                        tail=packing.pack_dstl_tail(dstl, c, m.dense_scale)))
+                    if getattr(dstl, "dim_modify_mode", "tail") == "head":
+                        # LN + Linear(C -> 30) first, then the Swin blocks at width 30 (6 heads x 5): generic CUDA-core
+                        # kernels (the tcgen05 kernels are built for 60 / 90 / 120)
+                        B["dstl"].append(dict(
+                            c=c, mode="head", head=packing.pack_dstl_head(dstl, c),
+                            stl=[packing.pack_stl(b, packing.GROWTH) for b in dstl.body.blocks],
+                            shifts=[b.shift_size for b in dstl.body.blocks], scale=float(m.dense_scale)))
+                    else:
+                        B["dstl"].append(dict(
+                            c=c, mode="tail",
+                            stl=[packing.pack_stl_tc(packing.pack_stl(b, c)) for b in dstl.body.blocks],
+                            shifts=[b.shift_size for b in dstl.body.blocks],
+                            tail=packing.pack_dstl_tail(dstl, c, m.dense_scale)))
                     c += packing.GROWTH
                 pos = packing.channel_positions(c, device)
                 if getattr(blk, "resi_connection", "1conv") == "3conv":
@@ -192,8 +200,11 @@ class Executor:
             self._block_start(bi, D[cur], T, ws)
             for j, ds in enumerate(blk["dstl"]):
                 src, lds = D[cur], 160
-                t = ds["tail"]
                 off = 64 + 32 * j
+                if ds["mode"] == "head":
+                    self._dstl_head_mode(ds, D[cur], off, B, H, W, ws, dt, st)
+                    continue
+                t = ds["tail"]
                 fuse_tail = dt == _lib.BF16 and self.use_tc
                 for k, (w, shift) in enumerate(zip(ds["stl"], ds["shifts"])):
                     cp = w["cp"]
@@ -273,13 +284,34 @@ class Executor:
             call("rdst_conv3x3_fwd", ptr(x), ldx, ptr(w), ptr(b), ptr(r), ldr, ptr(y), ldy,
                  B, H, W, cin, n, scale, shuffle, dt, st)
 
-    def _stl(self, src, lds, dst, w, shift, B, H, W, ws, dt, st, tail=None):
+    def _dstl_head_mode(self, ds, dense, off, B, H, W, ws, dt, st):
+        """DenseSTLayer in 'head' mode (rdst_variations.py:288-295, :335-340): growth = body(Linear(LN(x))) * dense_scale."""
+        T = B * H * W
+        c, hd = ds["c"], ds["head"]
+        v = lambda buf, ld: buf.view(-1)[:T * ld].view(T, ld)
+        h0 = v(ws["Y1"], 32)
+        call("rdst_linear_fwd", ptr(dense), 160, ptr(hd["w"]), ptr(hd["b"]), None, 0, ptr(h0), 32,
+             T, packing.padded_width(c), 32, c, 0, 1.0, dt, st)
+        mid = v(ws["Y0"], 32)
+        direct = ds["scale"] == 1.0                       # the last block writes the 32-wide slice of the dense buffer itself
+        last_dst = dense[:, off:] if direct else v(ws["F1"], 32)
+        srcs = [(h0, 32), (mid, 32)]
+        for k, (w, shift) in enumerate(zip(ds["stl"], ds["shifts"])):
+            last = k == len(ds["stl"]) - 1
+            src, lds = srcs[k % 2]
+            dst, ldd = (last_dst, 160 if direct else 32) if last else srcs[(k + 1) % 2]
+            self._stl(src, lds, dst, w, shift, B, H, W, ws, dt, st, generic=True, ldd=ldd)
+        if not direct:
+            dense[:, off:off + 32].copy_(last_dst * ds["scale"])
+
+    def _stl(self, src, lds, dst, w, shift, B, H, W, ws, dt, st, tail=None, generic=False, ldd=None):
         """One Swin block: x1 = x + proj(attn(LN1 x)); y = x1 + fc2(gelu(fc1(LN2 x1)))."""
         T = B * H * W
         c, cp, hp = w["c"], w["cp"], w["hp"]
+        ldd = cp if ldd is None else ldd
         v = lambda buf, ld: buf.view(-1)[:T * ld].view(T, ld)       # compact [T][ld] view of a max-sized buffer
         qkv, o, x1, hid = v(ws["QKV"], 3 * c), v(ws["O"], c), v(ws["X1"], cp), v(ws["HID"], hp)
-        if dt == _lib.BF16 and self.use_tc:
+        if dt == _lib.BF16 and self.use_tc and not generic:
             call("rdst_stl_attn_fwd_bf16", ptr(src), lds, ptr(x1), cp, ptr(w["wqkv_img"]), ptr(w["wproj_img"]),
                  ptr(w["bqkv_tc"]), ptr(w["bproj"]), ptr(w["table_tc"]), B, H, W, c, shift, st)
             if tail is None:
@@ -298,7 +330,7 @@ class Executor:
              T, c, cp, 0, 0, 1.0, dt, st)
         call("rdst_linear_fwd", ptr(x1), cp, ptr(w["w1"]), ptr(w["b1"]), None, 0, ptr(hid), hp,
              T, cp, hp, c, 1, 1.0, dt, st)
-        call("rdst_linear_fwd", ptr(hid), hp, ptr(w["w2"]), ptr(w["b2"]), ptr(x1), cp, ptr(dst), cp,
+        call("rdst_linear_fwd", ptr(hid), hp, ptr(w["w2"]), ptr(w["b2"]), ptr(x1), cp, ptr(dst), ldd,
              T, hp, cp, 0, 0, 1.0, dt, st)
 
 

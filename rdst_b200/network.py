@@ -87,26 +87,32 @@ class BasicLayer(nn.Module):
 
 
 class DenseSTLayer(nn.Module):
-    """rdst_variations.py:246-341, 'tail' mode with pre_norm: body (2 Swin blocks) -> LN -> Linear(C, growth)."""
+    """rdst_variations.py:246-341 with pre_norm.  'tail' mode: body (2 Swin blocks at the input width) -> LN -> Linear(C, growth).
+    'head' mode (:288-304): LN -> Linear(C, growth) -> body (2 Swin blocks at width `growth`)."""
 
-    def __init__(self, input_dim, input_resolution, depth, num_heads, mlp_ratio, qkv_bias, qk_scale, growth_rate):
+    def __init__(self, input_dim, input_resolution, depth, num_heads, mlp_ratio, qkv_bias, qk_scale, growth_rate,
+                 dim_modify_mode='tail'):
         super().__init__()
-        self.input_dim, self.growth_rate = input_dim, growth_rate
-        self.tail = nn.Sequential(nn.LayerNorm(input_dim), nn.Linear(input_dim, growth_rate))
-        self.body = BasicLayer(input_dim, input_resolution, depth, num_heads, mlp_ratio, qkv_bias, qk_scale)
+        self.input_dim, self.growth_rate, self.dim_modify_mode = input_dim, growth_rate, dim_modify_mode
+        if dim_modify_mode == 'head':
+            self.head = nn.Sequential(nn.LayerNorm(input_dim), nn.Linear(input_dim, growth_rate))
+            self.body = BasicLayer(growth_rate, input_resolution, depth, num_heads, mlp_ratio, qkv_bias, qk_scale)
+        else:
+            self.tail = nn.Sequential(nn.LayerNorm(input_dim), nn.Linear(input_dim, growth_rate))
+            self.body = BasicLayer(input_dim, input_resolution, depth, num_heads, mlp_ratio, qkv_bias, qk_scale)
 
 
 class RDSTB(nn.Module):
     """rdst_variations.py:354-445: dense Swin layers + 3x3 local-feature-fusion conv + residual."""
 
     def __init__(self, input_dim, input_resolution, layer_depth, num_heads, mlp_ratio, qkv_bias, qk_scale,
-                 growth_rate, num_blocks, resi_connection='1conv'):
+                 growth_rate, num_blocks, resi_connection='1conv', dim_modify_mode='tail'):
         super().__init__()
         self.body = nn.ModuleList()
         dim = input_dim
         for _ in range(num_blocks):
             self.body.append(DenseSTLayer(dim, input_resolution, layer_depth, num_heads, mlp_ratio,
-                                          qkv_bias, qk_scale, growth_rate))
+                                          qkv_bias, qk_scale, growth_rate, dim_modify_mode))
             dim += growth_rate
         if resi_connection == '1conv':
             self.conv = nn.Conv2d(dim, input_dim, 3, 1, 1)
@@ -183,7 +189,7 @@ class RDSTSR(nn.Module):
         if ape: _unsupported("absolute position embedding")
         if not patch_norm: _unsupported("patch_norm=False")
         if resi_connection not in ('1conv', '3conv'): _unsupported(f"resi_connection={resi_connection!r}")
-        if dim_modify_mode != 'tail' or not pre_norm: _unsupported("dim_modify_mode != 'tail' or pre_norm=False")
+        if dim_modify_mode not in ('tail', 'head') or not pre_norm: _unsupported("dim_modify_mode other than 'tail' / 'head', or pre_norm=False")
         if scale_free or scale_embedding: _unsupported("scale_free / scale_embedding")
         if int(sr_scale) not in (2, 4): _unsupported(f"sr_scale={sr_scale}")
         if bn_in_conv: _unsupported("bn_in_conv")
@@ -214,8 +220,8 @@ class RDSTSR(nn.Module):
         self.patch_embed = PatchEmbed(embed_dim, patch_norm)
         self.body = nn.ModuleList([
             RDSTB(embed_dim, img, dense_layer_depths[i], num_heads[i], mlp_ratio, qkv_bias, qk_scale,
-                  growth_rate, rdb_depths[i], resi_connection) for i in range(n)])
-        self.resi_connection = resi_connection
+                  growth_rate, rdb_depths[i], resi_connection, dim_modify_mode) for i in range(n)])
+        self.resi_connection, self.dim_modify_mode = resi_connection, dim_modify_mode
         self.norm = nn.LayerNorm(embed_dim)
         if resi_connection == '1conv':
             self.conv_after_body = nn.Conv2d(embed_dim, embed_dim, 3, 1, 1)
@@ -368,7 +374,8 @@ class ESTSR(RDSTSR):
                          global_res_scale=global_res_scale, mean=mean, std=std, act_in_conv=act_in_conv,
                          bn_in_conv=bn_in_conv, scale_free=scale_free, pre_norm=pre_norm, feature_last_operation=False,
                          precision=precision)
-        if resi_connection != '1conv': _unsupported("ESTSR with resi_connection other than '1conv'")
+        if resi_connection != '1conv' or dim_modify_mode != 'tail':
+            _unsupported("ESTSR with resi_connection other than '1conv' or dim_modify_mode other than 'tail'")
         img = (img_size, img_size) if isinstance(img_size, int) else tuple(img_size)
         self.body = nn.ModuleList([
             RRDSTB(embed_dim, img, dense_layer_depths[i], num_heads[i], mlp_ratio, qkv_bias, qk_scale, growth_rate,

@@ -39,7 +39,10 @@ def _f(t):
 
 
 def padded_width(c):
-    """Stored width of a dense-block activation with c = 60 + 30*j real channels."""
+    """Stored width of a dense-block activation with c = 60 + 30*j real channels (c = 30: the Swin blocks of a
+    'head'-mode DenseSTLayer run at the growth width, stored 32 wide)."""
+    if c == GROWTH:
+        return 32
     j = (c - EMBED) // GROWTH
     assert c == EMBED + GROWTH * j and 0 <= j <= 3, f"unsupported channel count {c}"
     return 64 + 32 * j
@@ -48,6 +51,8 @@ def padded_width(c):
 def channel_positions(c, device=None):
     """Stored position of every real channel: trunk at [0,60), growth block g at [64+32g, +30)."""
     idx = torch.arange(c, device=device)
+    if c == GROWTH:
+        return idx
     g = torch.clamp((idx - EMBED) // GROWTH, min=0)
     return torch.where(idx < EMBED, idx, 64 + 32 * g + (idx - EMBED) % GROWTH)
 
@@ -113,6 +118,18 @@ def pack_dstl_tail(dstl, c, dense_scale):
     wp = w.new_zeros(32, cp); wp[:g] = scatter_cols(w, pos, cp)
     bp = b.new_zeros(32); bp[:g] = b
     return dict(w=wp.contiguous(), b=bp.contiguous(), scale=float(dense_scale), wimg=kmajor_image(wp))
+
+
+def pack_dstl_head(dstl, c):
+    """'head' mode (rdst_variations.py:288-295): LN(C) -> Linear(C, growth) in FRONT of the Swin blocks; output stored 32 wide."""
+    f = _f
+    cp = padded_width(c)
+    pos = channel_positions(c, dstl.head[0].weight.device)
+    w, b = fold_ln(f(dstl.head[1].weight), f(dstl.head[1].bias), f(dstl.head[0].weight), f(dstl.head[0].bias))
+    g = w.shape[0]
+    wp = w.new_zeros(32, cp); wp[:g] = scatter_cols(w, pos, cp)
+    bp = b.new_zeros(32); bp[:g] = b
+    return dict(w=wp.contiguous(), b=bp.contiguous())
 
 
 def pack_conv(weight, bias, cin_pos, cin_width, n_pad):

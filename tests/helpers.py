@@ -175,3 +175,15 @@ def make_3conv(c, precision="fp32"):
     return rdst_b200.RDSTSR(img_size=24, sr_scale=c["scale"], dense_layer_depths=[2] * b, num_heads=[6] * b, window_size=[8] * b,
                             rdb_depths=[3] * b, mlp_ratio=2., pre_norm=True, feature_last_operation=True,
                             resi_connection="3conv", precision=precision)
+
+
+# ---- RDSTSR with dim_modify_mode = 'head' (SURVEY 8f row 3): fixtures from oracle/gen_golden_headmode.py ----
+HEADMODE_CASES = ["rdsthead_2blk_x4_16x24_b2", "rdsthead_3blk_x2_24x24"]
+
+
+def make_headmode(c, precision="fp32"):
+    import rdst_b200
+    b = c["blocks"]
+    return rdst_b200.RDSTSR(img_size=24, sr_scale=c["scale"], dense_layer_depths=[2] * b, num_heads=[6] * b, window_size=[8] * b,
+                            rdb_depths=[3] * b, mlp_ratio=2., pre_norm=True, feature_last_operation=True,
+                            dim_modify_mode="head", precision=precision)

@@ -1,0 +1,58 @@
+"""RDSTSR with dim_modify_mode = 'head' (LN + Linear(C, 30) in front of two Swin blocks at width 30 = 6 heads x 5;
+rdst_variations.py:288-304) -- SURVEY 8f row 3.  Oracle vs reference goldens, wire format and host logic on CPU; fp32 / bf16
+parity of the CUDA path on the GPU."""
+import pytest
+import torch
+
+import helpers
+import rdst_oracle as O
+from abi_emulator import emulated_abi
+
+
+@pytest.mark.parametrize("name", helpers.HEADMODE_CASES)
+def test_oracle_matches_reference_golden(name):
+    c = helpers.load_3conv_case(name)
+    y = O.forward(c["sd"], c["x"], c["scale"])
+    assert (y - torch.from_numpy(c["g"]["y"])).abs().max().item() < 2e-5
+
+
+@pytest.mark.parametrize("name", helpers.HEADMODE_CASES)
+def test_state_dict_manifest_and_host_logic(name):
+    c = helpers.load_3conv_case(name)
+    m = helpers.make_headmode(c)
+    man = helpers.swinir_manifest(name)
+    sd = m.state_dict()
+    assert [k for k, _, _ in man] == list(sd.keys())
+    for k, shape, dt in man:
+        assert tuple(sd[k].shape) == tuple(shape) and sd[k].dtype == dt, k
+    m.load_state_dict(c["sd"], strict=True)
+    calls = []
+    with emulated_abi(calls), torch.no_grad():
+        y = m._exec._forward_impl(c["x"])
+    ref = torch.from_numpy(c["g"]["y"])
+    assert y.shape == ref.shape and (y - ref).abs().max().item() < 2e-5
+    assert calls.count("rdst_window_attention_fwd") == 6 * c["blocks"]
+
+
+def test_training_raises():
+    from rdst_b200 import autograd
+    c = helpers.load_3conv_case(helpers.HEADMODE_CASES[0])
+    m = helpers.make_headmode(c).train()
+    with pytest.raises(NotImplementedError, match="head"):
+        autograd.forward_with_grad(m._exec, c["x"])
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", helpers.HEADMODE_CASES)
+@pytest.mark.parametrize("precision,tol", [("fp32", 1e-4), ("bf16", 1e-2)])
+def test_gpu_matches_reference_golden(name, precision, tol):
+    c = helpers.load_3conv_case(name)
+    m = helpers.make_headmode(c, precision).cuda().eval()
+    m.load_state_dict(c["sd"], strict=True)
+    with torch.no_grad():
+        y = m(c["x"].cuda()).cpu()
+    ref = torch.from_numpy(c["g"]["y"])
+    assert y.shape == ref.shape and (y - ref).abs().max().item() < tol
+    if precision == "bf16":
+        target = helpers.realistic_target(ref)
+        assert abs(O.psnr(y, target) - O.psnr(ref, target)) < 0.01

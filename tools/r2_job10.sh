@@ -1,0 +1,4 @@
+#!/bin/bash
+cd "$GRAFT_REPO_ROOT" 2>/dev/null || cd /root/repo
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests/test_imaging.py tests/test_3conv.py tests/test_swinir.py tests/test_rdstn.py -m gpu -q --timeout 600 2>&1 | tail -6
