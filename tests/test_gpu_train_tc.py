@@ -300,8 +300,9 @@ def _oracle_grads(sd, x, target, scale):
     return loss.item(), dict(zip(names, grads)), out.detach()
 
 
+# the last case is BASELINE cfg4 itself: RDST-E1 (8 RDSTBs), one GPU's batch of 32 x 1x24x24 (all 4.46 M parameters checked)
 @pytest.mark.parametrize("blocks,shape,scale", [(1, (2, 1, 16, 24), 4), (2, (1, 1, 24, 24), 2), (1, (3, 1, 40, 32), 4),
-                                                (1, (1, 1, 8, 8), 2)])
+                                                (1, (1, 1, 8, 8), 2), (8, (32, 1, 24, 24), 4)])
 def test_bf16_training_gradients_close_to_fp32_autograd(blocks, shape, scale):
     """precision='bf16' training: GEMM operands are rounded to bf16, so gradients agree with the exact fp32 autograd of
     the oracle to bf16 accuracy: per-tensor relative L2 error <= 3e-2 (<= 1e-1 for the tiny relative-position tables), output within the bf16 inference bar (1e-2)."""
