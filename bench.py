@@ -174,7 +174,25 @@ def cpu_reference_run(sd, steps, warmup, sample_slices, module=None, budget_s=No
     return n * LR_H * SCALE * LR_W * SCALE / sec / 1e6, sec, threads, n
 
 
+_JSON_FD = None
+
+
+def _protect_stdout():
+    """Exactly ONE JSON line may reach stdout: libraries (NCCL prints its version banner there) get stderr instead."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def _emit(line):
+    sys.stdout.flush()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, (json.dumps(line) + "\n").encode())
+
+
 def main():
+    _protect_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
@@ -220,7 +238,7 @@ def main():
                                               "oracle = PyTorch-CPU restatement of the reference module; the Python "
                                               "reference itself cannot travel to the box") + ")"},
                 "e2e": {"value": round(val, 4), "unit": "Mpix/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line))
+        _emit(line)
         return
 
     # ------------------------------------------------------------------ our arm (GPU)
@@ -390,7 +408,7 @@ def main():
         line["cpu_baseline"] = {"value": round(val, 4), "unit": "Mpix/s", "cores": threads, "kind": "port",
                                 "sample": f"{n_used} of {SLICES} slices per step, 2 steps, {sec:.2f} s/step "
                                           "(oracle = PyTorch-CPU restatement of the reference module)"}
-    print(json.dumps(line))
+    _emit(line)
     if world > 1:
         import torch.distributed as dist
         dist.destroy_process_group()

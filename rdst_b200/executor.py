@@ -285,24 +285,34 @@ class Executor:
                  B, H, W, cin, n, scale, shuffle, dt, st)
 
     def _dstl_head_mode(self, ds, dense, off, B, H, W, ws, dt, st):
-        """DenseSTLayer in 'head' mode (rdst_variations.py:288-295, :335-340): growth = body(Linear(LN(x))) * dense_scale."""
+        """DenseSTLayer in 'head' mode (rdst_variations.py:288-295, :335-340): growth = body(Linear(LN(x))) * dense_scale.
+        The Swin blocks at width 30 run on the generic CUDA-core kernels with fp32 intermediates in BOTH precision modes
+        (in bf16 mode only the dense buffer is bf16: storing qkv / hidden activations of this narrow path in bf16 as well
+        costs ~0.03 dB, measured)."""
         T = B * H * W
         c, hd = ds["c"], ds["head"]
-        v = lambda buf, ld: buf.view(-1)[:T * ld].view(T, ld)
-        h0 = v(ws["Y1"], 32)
-        call("rdst_linear_fwd", ptr(dense), 160, ptr(hd["w"]), ptr(hd["b"]), None, 0, ptr(h0), 32,
-             T, packing.padded_width(c), 32, c, 0, 1.0, dt, st)
-        mid = v(ws["Y0"], 32)
-        direct = ds["scale"] == 1.0                       # the last block writes the 32-wide slice of the dense buffer itself
-        last_dst = dense[:, off:] if direct else v(ws["F1"], 32)
-        srcs = [(h0, 32), (mid, 32)]
+        cpi = packing.padded_width(c)
+        key = ("head_mode", T)
+        if key not in ws:
+            f = lambda n: torch.empty(T, n, dtype=torch.float32, device=dense.device)
+            ws[key] = dict(xin=f(128), h0=f(32), mid=f(32), out=f(32), QKV=f(96), O=f(32), X1=f(32), HID=f(64))
+        w32 = ws[key]
+        if dense.dtype == torch.float32:
+            xin, ldx = dense, 160
+        else:
+            xin, ldx = w32["xin"].view(-1)[:T * cpi].view(T, cpi), cpi
+            xin.copy_(dense[:, :cpi])
+        call("rdst_linear_fwd", ptr(xin), ldx, ptr(hd["w"]), ptr(hd["b"]), None, 0, ptr(w32["h0"]), 32,
+             T, cpi, 32, c, 0, 1.0, _lib.F32, st)
+        srcs = [w32["h0"], w32["mid"]]
+        n = len(ds["stl"])
         for k, (w, shift) in enumerate(zip(ds["stl"], ds["shifts"])):
-            last = k == len(ds["stl"]) - 1
-            src, lds = srcs[k % 2]
-            dst, ldd = (last_dst, 160 if direct else 32) if last else srcs[(k + 1) % 2]
-            self._stl(src, lds, dst, w, shift, B, H, W, ws, dt, st, generic=True, ldd=ldd)
-        if not direct:
-            dense[:, off:off + 32].copy_(last_dst * ds["scale"])
+            dst = w32["out"] if k == n - 1 else srcs[(k + 1) % 2]
+            self._stl(srcs[k % 2], 32, dst, w, shift, B, H, W, w32, _lib.F32, st, generic=True)
+        if ds["scale"] == 1.0:
+            dense[:, off:off + 32].copy_(w32["out"])
+        else:
+            dense[:, off:off + 32].copy_(w32["out"] * ds["scale"])
 
     def _stl(self, src, lds, dst, w, shift, B, H, W, ws, dt, st, tail=None, generic=False, ldd=None):
         """One Swin block: x1 = x + proj(attn(LN1 x)); y = x1 + fc2(gelu(fc1(LN2 x1)))."""
