@@ -713,26 +713,35 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       __syncwarp();
       for (int j = s; j < G; j += NS) {
         const uint32_t ph = (j / NS) & 1;
-        // softmax of head j delivered P; role B wrote V (which also means O of head j-NS is in its registers)
-        while (true) {
-          const bool p_ok = mbar_try_wait(bP, ph), v_ok = mbar_try_wait(bV, ph);
-          if (p_ok && v_ok) break;
-        }
+        const bool has_s = j + NS < G;
+        const int g4 = j + 2 * NS, h4 = g4 % 6;
+        const bool q_fused = g4 < G && h4 >= NS;                 // qkv of the same tile as S(j+NS): goes out in the same breath
+        // Everything that is normally long complete is waited for FIRST (V of head j -- which also means O of head j-NS is
+        // in role B's registers -- and q/k of head j+NS), so that the only wait left on the softmax -> PV -> S chain is P.
+        mbar_wait(bV, ph);
+        const bool qk_early = has_s && __all_sync(0xffffffffu, mbar_test(bQK, ph ^ 1)) != 0;
+        mbar_wait(bP, ph);                                       // softmax of head j delivered P
         fence_after_sync();
         A2_STAMP();   // MMA: P, V ready
-        if (elect_one()) pv_mmas();
-        __syncwarp();
-        A2_STAMP();   // MMA: PV issued
-        if (j + NS < G) {
-          mbar_wait(bQK, ph ^ 1);
-          fence_after_sync();
-          const int g4 = j + 2 * NS, h4 = g4 % 6;
-          const bool q_fused = g4 < G && h4 >= NS;               // qkv of the same tile as S(j+NS): goes out in the same breath
-          if (elect_one()) {
+        if (elect_one()) {
+          pv_mmas();
+          if (qk_early) {                                        // PV(j), S(j+NS) (+ qkv) in one go
             s_mmas();
             if (q_fused) qkv_mmas(h4);
           }
-          __syncwarp();
+        }
+        __syncwarp();
+        A2_STAMP();   // MMA: PV (+ S) issued
+        if (has_s) {
+          if (!qk_early) {                                       // role B was late with q/k of head j+NS
+            mbar_wait(bQK, ph ^ 1);
+            fence_after_sync();
+            if (elect_one()) {
+              s_mmas();
+              if (q_fused) qkv_mmas(h4);
+            }
+            __syncwarp();
+          }
           A2_STAMP();   // MMA: S (+ qkv) issued
           if (g4 < G && h4 < NS) {
             // first head of this slot in the next tile: x^ of that tile has to be in TMEM.  This warp has nothing else
