@@ -110,7 +110,7 @@ struct Cfg {
   static constexpr int OFF_KV = OFF_Y + (YBUF ? XT_BYTES : 0);     // [NS slots][K | V]
   static constexpr int OFF_TAB = OFF_KV + NS * KV_BYTES;
   static constexpr int OFF_BARS = OFF_TAB + 6 * TBL * 4;    // mbarriers + TMEM base live in dynamic shared memory too: a static
-  static constexpr int SMEM = OFF_BARS + 32 * 8;            // __shared__ would cost a whole 1024-byte alignment unit
+  static constexpr int SMEM = OFF_BARS + 40 * 8;            // __shared__ would cost a whole 1024-byte alignment unit
   // TMEM columns: x^ | qkv accumulators / packed Q | S / P | O | normalised O (A of proj) | proj accumulator (one block)
   static constexpr int TM_XH = 0, TM_QKV = CP / 2, TM_S = TM_QKV + NS * NH, TM_O = TM_S + NS * 64, TM_AP = TM_O + NS * HDV,
                        TM_PROJ = TM_AP + KPROJ / 2;
@@ -143,7 +143,7 @@ constexpr int THREADS = 640;
 enum Bar {
   B_W = 0, B_LFULL, B_EFULL, B_XH_READY, B_XH_FREE, B_AP_READY, B_PROJ_FULL, B_PROJ_DRAINED,
   B_QKV_FULL = 8, B_QK_DRAINED = 11, B_V_DRAINED = 14, B_S_FULL = 17, B_P_READY = 20, B_O_FULL = 23,      // one per slot (<= 3)
-  B_AP_FREE = 26, B_WREADY = 27, B_STAGED = 28, NBARS = 29
+  B_AP_FREE = 26, B_WPROJ = 27, B_STAGED = 28, B_WHEAD = 29 /* 6: qkv weights of one head each */, NBARS = 35
 };
 
 __device__ __forceinline__ void wgA_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
@@ -164,8 +164,8 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
   constexpr int CP = K::CP, HD = K::HD, NH = K::NH;
   extern __shared__ __align__(1024) uint8_t smem[];
   uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BARS);
-  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(smem + K::OFF_BARS + 30 * 8);
-  static_assert(NBARS <= 30, "barrier block");
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(smem + K::OFF_BARS + 38 * 8);
+  static_assert(NBARS <= 38, "barrier block");
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int wg = warp >> 2;                         // 0 = A, 1 = B, 2 = C, 3 = D, 4 = MMA warp
   const int row = tid & 127;
@@ -181,11 +181,16 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       mbar_init(&bars[i], w4 ? 4 : (i == B_XH_FREE ? K::NS : 1));  // x^ is free when ALL slot issuers are past their last qkv
     }
     fence_mbar_init();
-    mbar_arrive_expect_tx(&bars[B_W], K::WQKV_BYTES + K::WPROJ_BYTES);
-    for (int off = 0; off < K::WQKV_BYTES; off += 32768)
-      bulk_g2s(smem + K::OFF_WQKV + off, wqkv_img + off, min(32768, K::WQKV_BYTES - off), &bars[B_W]);
-    for (int off = 0; off < K::WPROJ_BYTES; off += 32768)
-      bulk_g2s(smem + K::OFF_WPROJ + off, wproj_img + off, min(32768, K::WPROJ_BYTES - off), &bars[B_W]);
+    // resident weights: one bulk copy and one barrier PER HEAD, so that the first tile starts as soon as head 0's 16 KB are
+    // there instead of after all 130 KB (every CTA pulls the same image out of L2 at launch: ~8000 cycles at C = 120)
+    constexpr int WH = NH * CP * 2;
+    static_assert(WH <= 32768 && K::WPROJ_BYTES <= 32768, "one bulk copy each");
+    for (int h = 0; h < 6; ++h) {
+      mbar_arrive_expect_tx(&bars[B_WHEAD + h], WH);
+      bulk_g2s(smem + K::OFF_WQKV + h * WH, wqkv_img + h * WH, WH, &bars[B_WHEAD + h]);
+    }
+    mbar_arrive_expect_tx(&bars[B_WPROJ], K::WPROJ_BYTES);
+    bulk_g2s(smem + K::OFF_WPROJ, wproj_img, K::WPROJ_BYTES, &bars[B_WPROJ]);
   }
   // K / V images start as zeros (pads must be, and stay, zero / finite); bias table -> shared memory
   for (int i = tid; i < K::NS * K::KV_BYTES / 16; i += THREADS)
@@ -589,27 +594,6 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       warp_arrive(&bars[B_P_READY + s], lane);
       A2_STAMP();   // C/D: P written
     }
-  } else if (warp == 16) {
-    // fold the biases into the resident images (K rows 60/61 of every qkv head, spare K rows of proj), then release the
-    // three issuer warps
-    mbar_wait(&bars[B_W], 0);
-    for (int i = lane; i < 6 * NH; i += 32) {
-      const int hh = i / NH, nn = i - hh * NH;
-      *reinterpret_cast<uint32_t*>(smem + K::OFF_WQKV + hh * (NH * CP * 2) + (7 * NH + nn) * 16 + 8) = bias_hi_lo(bqkv[i]);
-    }
-    for (int nn = lane; nn < CP; nn += 32) {
-      const uint32_t hl = bias_hi_lo(bproj[nn]);
-      uint8_t* wp = smem + K::OFF_WPROJ;
-      if (C_ == 60) *reinterpret_cast<uint32_t*>(wp + (1 * CP + nn) * 16 + 4) = hl;            // k = 10, 11
-      else if (C_ == 120) *reinterpret_cast<uint32_t*>(wp + (15 * CP + nn) * 16) = hl;         // k = 120, 121
-      else {                                                                                   // k = 15, 31
-        *reinterpret_cast<uint16_t*>(wp + (1 * CP + nn) * 16 + 14) = (uint16_t)(hl & 0xFFFFu);
-        *reinterpret_cast<uint16_t*>(wp + (3 * CP + nn) * 16 + 14) = (uint16_t)(hl >> 16);
-      }
-    }
-    fence_proxy_async();
-    __syncwarp();
-    if (lane == 0) mbar_arrive(&bars[B_WREADY]);
   }
   if (!K::YBUF && warp == 19) {
     // =============================== E-side TMA: store of finished tiles, second fetch of the residual rows ===============================
@@ -639,7 +623,6 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     // i.e. it, not the tensor pipe (~650 cycles of MMAs per head), paced the first version of this kernel.
     // The whole warp runs the loop with warp-uniform values and only the tcgen05 instructions sit under elect.sync:
     // descriptors then live in uniform registers (one lane of a divergent branch costs a ~60-cycle waterfall per MMA).
-    mbar_wait(&bars[B_WREADY], 0);
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t aWqkv = smem_u32(smem + K::OFF_WQKV), aWproj = smem_u32(smem + K::OFF_WPROJ);
     const uint32_t aKV = smem_u32(smem + K::OFF_KV);
@@ -648,6 +631,20 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     constexpr uint32_t idv = make_idesc_f16(128, K::HDV, false, true);
     constexpr uint32_t idp = make_idesc_bf16(128, K::NPC, false, false);
     if (warp == 16 + K::NS) {
+      // proj weights landed: fold the bias into the spare K rows of the resident image (bf16 hi/lo pair, see tc_attn.cu)
+      mbar_wait(&bars[B_WPROJ], 0);
+      for (int nn = lane; nn < CP; nn += 32) {
+        const uint32_t hl = bias_hi_lo(bproj[nn]);
+        uint8_t* wp = smem + K::OFF_WPROJ;
+        if (C_ == 60) *reinterpret_cast<uint32_t*>(wp + (1 * CP + nn) * 16 + 4) = hl;            // k = 10, 11
+        else if (C_ == 120) *reinterpret_cast<uint32_t*>(wp + (15 * CP + nn) * 16) = hl;         // k = 120, 121
+        else {                                                                                   // k = 15, 31
+          *reinterpret_cast<uint16_t*>(wp + (1 * CP + nn) * 16 + 14) = (uint16_t)(hl & 0xFFFFu);
+          *reinterpret_cast<uint16_t*>(wp + (3 * CP + nn) * 16 + 14) = (uint16_t)(hl >> 16);
+        }
+      }
+      fence_proxy_async();
+      __syncwarp();
       for (int k = 0; k < NT * K::NBLK; ++k) {
         const int pn = k / K::NBLK, hf = k - pn * K::NBLK;
         if (hf == 0) mbar_wait(&bars[B_AP_READY], pn & 1);
@@ -700,13 +697,22 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
                                w ? 0xFFFFFFFFu : 0u, w ? 0xFFFFFFFFu : 0u, w ? 0u : 0xFFFFFFFFu, w ? 0u : 0xFFFFFFFFu);
         commit(bO);
       };
+      auto prep_head = [&](int h) {                              // whole warp, first tile only: head h's weights landed ->
+        mbar_wait(&bars[B_WHEAD + h], 0);                        // fold its qkv bias into K rows 60 / 61 of the resident image
+        for (int nn = lane; nn < NH; nn += 32)
+          *reinterpret_cast<uint32_t*>(smem + K::OFF_WQKV + h * (NH * CP * 2) + (7 * NH + nn) * 16 + 8) = bias_hi_lo(bqkv[h * NH + nn]);
+        fence_proxy_async();
+        __syncwarp();
+      };
       // head g of this slot is its (g / NS)-th: that is the phase index of all per-slot barriers.
       //     iteration j:  PV(j) ;  S(j+NS) ;  qkv(j+2 NS)
       // prologue: qkv(s) ; S(s) ; qkv(s+NS)
+      prep_head(s);
       mbar_wait(&bars[B_XH_READY], 0);
       fence_after_sync();
       if (elect_one()) qkv_mmas(s);
       __syncwarp();
+      prep_head(s + NS);
       mbar_wait(bQK, 0);
       fence_after_sync();
       if (elect_one()) { s_mmas(); qkv_mmas(s + NS); }
@@ -716,6 +722,7 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
         const bool has_s = j + NS < G;
         const int g4 = j + 2 * NS, h4 = g4 % 6;
         const bool q_fused = g4 < G && h4 >= NS;                 // qkv of the same tile as S(j+NS): goes out in the same breath
+        if (g4 < 6) prep_head(g4);                               // (first tile: that head's weights and bias)
         // Everything that is normally long complete is waited for FIRST (V of head j -- which also means O of head j-NS is
         // in role B's registers -- and q/k of head j+NS), so that the only wait left on the softmax -> PV -> S chain is P.
         mbar_wait(bV, ph);
