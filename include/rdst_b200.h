@@ -305,6 +305,11 @@ int rdst_debug_attn_variant(int variant);
  * clock64() stamps in program order of one thread of the role).  NULL switches it off. */
 int rdst_debug_attn2_timing(void* device_buffer_1280_u64);
 int rdst_debug_mlp_timing(void* device_buffer_128_u64);     /* same for rdst_stl_mlp_*_fwd_bf16 */
+/* Kernel behind rdst_stl_mlp_fwd_bf16 / rdst_stl_mlp_tail_fwd_bf16: 2 (default) = warp-specialised pipeline (csrc/tc_mlp2.cu),
+ * 1 = the round-1 lock-step kernel (csrc/tc_mlp.cu), kept for A/B timing; rdst_debug_mlp2_timing: role timelines of CTA 0 of the
+ * warp-specialised kernel (5 x 256 uint64, like rdst_debug_attn2_timing). */
+int rdst_debug_mlp_variant(int variant);
+int rdst_debug_mlp2_timing(void* device_buffer_1280_u64);
 int rdst_debug_conv_timing(void* device_buffer_128_u64);    /* same for rdst_conv3x3_fwd_bf16_tc (128 stamps, CTA 0) */
 
 /* tcgen05 issue-pattern microbenchmark (timing only, zero operands): `count` MMAs M=128 x N x K=16 issued round-robin over

@@ -76,6 +76,8 @@ _SIGNATURES = {
     "rdst_debug_attn_variant": (C.c_int, [_i]),
     "rdst_debug_attn2_timing": (C.c_int, [_vp]),
     "rdst_debug_mlp_timing": (C.c_int, [_vp]),
+    "rdst_debug_mlp_variant": (C.c_int, [_i]),
+    "rdst_debug_mlp2_timing": (C.c_int, [_vp]),
     "rdst_debug_conv_timing": (C.c_int, [_vp]),
     "rdst_umma_bench": (C.c_int, [_i, _i, _i, _i, _i, _vp, _vp]),
     "rdst_tmem_bw_bench": (C.c_int, [_i, _i, _i, _vp, _vp]),

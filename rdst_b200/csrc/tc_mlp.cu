@@ -492,6 +492,12 @@ static int launch_mlp(const void* x, int64_t ldx, void* y, int64_t ldy, const vo
   return RDST_OK;
 }
 
+// warp-specialised kernel (tc_mlp2.cu), the default
+int mlp_v2_dispatch(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w1img, const void* w2img, const float* b1,
+                    const float* b2, int64_t T, int C, int exact_gelu, const void* wtimg, const float* bt, void* dense, int64_t ldd,
+                    float scale, int has_tail, int sms, cudaStream_t st);
+static int g_mlp_variant = 2;
+
 static int mlp_dispatch(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w1img, const void* w2img,
                         const float* b1, const float* b2, int64_t T, int C, int exact_gelu, const TailArgs* tail,
                         void* stream) {
@@ -499,6 +505,10 @@ static int mlp_dispatch(const void* x, int64_t ldx, void* y, int64_t ldy, const 
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   cudaStream_t st = (cudaStream_t)stream;
+  if (g_mlp_variant == 2)
+    return mlp_v2_dispatch(x, ldx, y, ldy, w1img, w2img, b1, b2, T, C, exact_gelu, tail ? tail->wtimg : nullptr,
+                           tail ? tail->bt : nullptr, tail ? (void*)tail->dense : nullptr, tail ? tail->ldd : 0,
+                           tail ? tail->scale : 0.f, tail != nullptr, sms, st);
   switch (C) {
     case 60:  return launch_mlp<64, 128>(x, ldx, y, ldy, w1img, w2img, b1, b2, T, 60, exact_gelu, tail, sms, st);
     case 90:  return launch_mlp<96, 192>(x, ldx, y, ldy, w1img, w2img, b1, b2, T, 90, exact_gelu, tail, sms, st);
@@ -508,6 +518,12 @@ static int mlp_dispatch(const void* x, int64_t ldx, void* y, int64_t ldy, const 
 }
 
 }  // namespace rdst
+
+extern "C" int rdst_debug_mlp_variant(int variant) {
+  if (variant != 1 && variant != 2) { rdst::set_error("rdst_debug_mlp_variant: 1 (lock-step kernel) or 2 (warp-specialised)"); return RDST_E_INVALID; }
+  rdst::g_mlp_variant = variant;
+  return RDST_OK;
+}
 
 extern "C" int rdst_debug_mlp_timing(void* device_buffer_128_u64) {
   rdst::g_mlp_dbg = (unsigned long long*)device_buffer_128_u64;

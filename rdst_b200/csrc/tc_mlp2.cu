@@ -1,0 +1,542 @@
+// Fused Swin MLP on tcgen05, warp-specialised pipeline (round 2):
+//     Y = X + fc2( GELU( fc1( LNhat(X) ) ) )       [TAIL: D[:, slice] = scale * (Linear_t( LNhat(Y) ) + b_t), Y never stored]
+// Replaces norm2 + Mlp + residual of SwinTransformerBlock.forward (reference swin_transformer_sr.py:272, :23-29) and, in
+// the TAIL variant, the DenseSTLayer tail LN + Linear + cat (rdst_variations.py:339-340).
+//
+// Same arithmetic and operand images as the first kernel (tc_mlp.cu), which ran every phase on all 512 threads in lock step
+// (LayerNorm -> fc1 chunks / GELU -> fc2 -> epilogue: 8800 cycles per 128-token tile at C = 120).  The floors of one tile
+// are ~2000 cycles each on three different units -- MUFU (30720 tanh at 16 per clock), the tensor pipe (fc1 + fc2 at the
+// M = 128 rate) and the LayerNorm warpgroup -- so the phases have to overlap.  One persistent CTA per SM, five roles that
+// only meet at mbarriers:
+//   warpgroup A   (warps 0-3,  thread = token row)   LayerNorm of tile t+1 -> x^ (TMEM); landing-tile TMA
+//   warpgroups G0, G1 (warps 4-11, thread = row)     GELU of alternate 64-wide hidden chunks: fc1 accumulator -> packed fp16
+//                                                     A operand of fc2 (TMEM).  The accumulator slot is released right
+//                                                     after it has been loaded, so the NEXT fc1 chunk of that slot runs
+//                                                     under the GELU of this one: the two warpgroups never wait for MMAs
+//   warpgroup E   (warps 12-15, thread = row)        epilogue of tile t-1: fc2 accumulator + b2 + residual -> staging tile
+//                                                     -> TMA store;  TAIL: + LayerNorm -> x^' (TMEM) -> growth Linear -> slice
+//   warp 16 / 17  one elected lane each               fc1 chunks / fc2 K-slices (+ the TAIL Linear), each in one static order
+// TMEM (512 columns at C = 120): x^ [0,64) | fc1 accumulator, 2 slots [64,192) | packed hidden, 2 slots [192,256) |
+// fc2 accumulator, 2 tiles [256,512).  Shared memory: W1 | W2 | (W_tail) | landing tile L | residual tile E (second fetch,
+// an L2 hit) | staging tile Y | b2 | b_tail | barriers.
+#include "common.cuh"
+#include "umma.cuh"
+#include "tma.cuh"
+
+namespace rdst {
+using namespace umma;
+
+namespace m2 {
+
+__device__ __forceinline__ uint32_t pk2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+__device__ __forceinline__ float2 up2(uint32_t u) {
+  __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
+  return __bfloat1622float2(v);
+}
+__device__ __forceinline__ uint32_t bias_hi_lo(float b) {          // b1 rides inside fc1 as a bf16 hi/lo pair (see tc_mlp.cu)
+  const __nv_bfloat16 hi = __float2bfloat16_rn(b);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
+  return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+}
+// GELU(x) = x*Phi(x), Phi(x) ~ 0.5*(1+tanh(x*(a+b x^2+c x^4))) fitted to the erf form (max abs deviation 2.6e-5 on |x|<=8),
+// two values per instruction on packed fp16; EXACT evaluates erff.  Same function as tc_mlp.cu.
+template <bool EXACT>
+__device__ __forceinline__ uint32_t gelu_pair(float a, float b) {
+  if (EXACT) {
+    __half2 r = __floats2half2_rn(gelu_erf(a), gelu_erf(b));
+    return *reinterpret_cast<uint32_t*>(&r);
+  }
+  const __half2 x = __floats2half2_rn(a, b);
+  const __half2 u = __hmin2(__hmul2(x, x), __float2half2_rn(64.0f));
+  __half2 p = __hfma2(u, __float2half2_rn(-3.53076214e-04f), __float2half2_rn(3.70152568e-02f));
+  p = __hfma2(u, p, __float2half2_rn(7.97497252e-01f));
+  const __half2 inner = __hmul2(x, p);
+  uint32_t t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&inner)));
+  const __half2 hx = __hmul2(x, __float2half2_rn(0.5f));
+  const __half2 r = __hfma2(hx, *reinterpret_cast<const __half2*>(&t), hx);
+  return *reinterpret_cast<const uint32_t*>(&r);
+}
+
+template <int CP_, int HP_, bool TAIL>
+struct Cfg {
+  static constexpr int CP = CP_, HP = HP_;
+  static constexpr int NCH = CP / 8;                       // 16-byte chunks per activation row
+  static constexpr int NCHK = (HP + 63) / 64;              // fc1 N-chunks (= fc2 K-slices) of 64 hidden units: 2 / 3 / 4
+  static constexpr int LASTW = HP - 64 * (NCHK - 1);       // width of the last chunk: 64 / 64 / 48
+  static constexpr int W1_BYTES = HP * CP * 2, W2_BYTES = CP * HP * 2, WT_BYTES = 32 * CP * 2;
+  static constexpr int NP = CP > 64 ? 2 : 1;
+  static constexpr int PANEL = 128 * 128;
+  static constexpr int XT_BYTES = NP * PANEL;
+  static constexpr int OFF_W1 = 0;
+  static constexpr int OFF_W2 = OFF_W1 + W1_BYTES;
+  static constexpr int OFF_WT = OFF_W2 + W2_BYTES;
+  static constexpr int OFF_L = (OFF_WT + (TAIL ? WT_BYTES : 0) + 1023) / 1024 * 1024;      // landing tile (LayerNorm source)
+  static constexpr int OFF_E = OFF_L + XT_BYTES;           // residual rows (second fetch)
+  static constexpr int OFF_Y = OFF_E + XT_BYTES;           // output staging (not in the TAIL variant)
+  static constexpr int OFF_B2 = OFF_Y + (TAIL ? 0 : XT_BYTES);
+  static constexpr int OFF_BT = OFF_B2 + CP * 4;
+  static constexpr int OFF_BARS = OFF_BT + 32 * 4;
+  static constexpr int SMEM = OFF_BARS + 32 * 8;
+  // TMEM columns
+  static constexpr int TM_XH = 0;                          // normalised input, CP/2 packed columns
+  static constexpr int TM_H = CP / 2;                      // fc1 accumulator, 2 slots x 64
+  static constexpr int TM_HP = TM_H + 128;                 // GELU(hidden) packed fp16, 2 slots x 32
+  static constexpr int TM_OUT = TM_HP + 64;                // fc2 accumulator, 2 tiles x CP (TAIL: later x^' in [0,CP/2) and the
+                                                           // 32-column tail accumulator in [CP/2, CP/2+32) of the same tile)
+  static_assert(TM_OUT + 2 * CP <= 512, "TMEM budget");
+  static_assert(SMEM <= 232448, "shared memory budget");
+  static_assert(OFF_L % 1024 == 0, "TMA tiles need 1024-byte alignment");
+  static_assert(LASTW % 16 == 0 && CP % 32 == 0, "tile shape");
+};
+
+__device__ __forceinline__ uint32_t xt_off(int row, int c) {          // 16-byte chunk c of token row `row` (SWIZZLE_128B panels)
+  return (uint32_t)((c >> 3) * (128 * 128) + row * 128 + (((c & 7) ^ (row & 7)) << 4));
+}
+
+struct TailArgs {
+  const uint8_t* wtimg;      // [CP/8][32][8] bf16, LN gamma folded
+  const float* bt;           // [32]
+  __nv_bfloat16* dense;      // &D[0][64 + 32 j]
+  int64_t ldd;
+  float scale;               // dense_scale
+};
+
+constexpr int THREADS = 640;
+enum Bar {
+  B_W1 = 0, B_W2, B_LFULL, B_EFULL, B_XH_READY, B_XH_FREE, B_XT_READY, B_TAIL_FULL,
+  B_H_FULL = 8, B_H_DRAINED = 10, B_HP_READY = 12, B_HP_FREE = 14, B_OUT_FULL = 16, B_OUT_FREE = 18, NBARS = 20
+};
+__device__ __forceinline__ void wg_sync(int id) { asm volatile("bar.sync %0, 128;" ::"r"(id) : "memory"); }
+__device__ __forceinline__ void warp_arrive(uint64_t* bar, int lane) {
+  fence_before_sync();
+  __syncwarp();
+  if (lane == 0) mbar_arrive(bar);
+}
+
+template <int CP, int HP, bool EXACT, bool TAIL, bool DBG>
+__global__ void __launch_bounds__(THREADS, 1)
+stl_mlp2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__ CUtensorMap mapY,
+                const uint8_t* __restrict__ w1img, const uint8_t* __restrict__ w2img, const float* __restrict__ b1,
+                const float* __restrict__ b2, int64_t T, int creal, TailArgs ta, unsigned long long* __restrict__ dbg) {
+  using K = Cfg<CP, HP, TAIL>;
+  constexpr int NCHK = K::NCHK;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint64_t* const bars = reinterpret_cast<uint64_t*>(smem + K::OFF_BARS);
+  uint32_t& tmem_base_s = *reinterpret_cast<uint32_t*>(smem + K::OFF_BARS + 30 * 8);
+  static_assert(NBARS <= 30, "barrier block");
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int wg = warp >> 2;                          // 0 = A (LayerNorm), 1, 2 = GELU, 3 = E (epilogue), 4 = issuers
+  const int row = tid & 127;
+  uint8_t* const sL = smem + K::OFF_L;
+  uint8_t* const sE = smem + K::OFF_E;
+  uint8_t* const sY = smem + K::OFF_Y;
+  float* const sB2 = reinterpret_cast<float*>(smem + K::OFF_B2);
+  float* const sBT = reinterpret_cast<float*>(smem + K::OFF_BT);
+
+  if (warp == 0) tmem_alloc<512>(&tmem_base_s);
+  if (tid == 0) {
+    for (int i = 0; i < NBARS; ++i) {
+      const bool w4 = i == B_XH_READY || i == B_XT_READY || i == B_H_DRAINED || i == B_H_DRAINED + 1 || i == B_HP_READY ||
+                      i == B_HP_READY + 1 || i == B_OUT_FREE || i == B_OUT_FREE + 1;
+      mbar_init(&bars[i], w4 ? 4 : 1);
+    }
+    fence_mbar_init();
+    // resident weights: fc1 only needs W1 before the first tile can start; W2 (and the tail image) follow
+    mbar_arrive_expect_tx(&bars[B_W1], K::W1_BYTES);
+    for (int off = 0; off < K::W1_BYTES; off += 32768)
+      bulk_g2s(smem + K::OFF_W1 + off, w1img + off, min(32768, K::W1_BYTES - off), &bars[B_W1]);
+    mbar_arrive_expect_tx(&bars[B_W2], K::W2_BYTES + (TAIL ? K::WT_BYTES : 0));
+    for (int off = 0; off < K::W2_BYTES; off += 32768)
+      bulk_g2s(smem + K::OFF_W2 + off, w2img + off, min(32768, K::W2_BYTES - off), &bars[B_W2]);
+    if (TAIL) bulk_g2s(smem + K::OFF_WT, ta.wtimg, K::WT_BYTES, &bars[B_W2]);
+  }
+  for (int i = tid; i < CP; i += THREADS) sB2[i] = b2[i];
+  if (TAIL) {
+    for (int i = tid; i < 32; i += THREADS) sBT[i] = ta.bt[i];
+  }
+  fence_proxy_async();
+  fence_before_sync();
+  __syncthreads();
+  fence_after_sync();
+  const uint32_t tmem = tmem_base_s;
+  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+  const int64_t ntiles = (T + 127) / 128;
+  const int NT = (int)((ntiles - (int64_t)blockIdx.x + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x);   // tiles of this CTA (>= 1)
+  const int NK = NT * NCHK;                                                                             // hidden chunks of this CTA
+  int dbg_n = 0;
+  const bool dbg_on = DBG && dbg != nullptr && blockIdx.x == 0 && (tid & 127) == 0;
+#define M2_STAMP()                                                                            \
+  do {                                                                                        \
+    if (DBG && dbg_on && dbg_n < 255) dbg[wg * 256 + 1 + dbg_n++] = clock64();                \
+  } while (0)
+
+  auto load_tile = [&](int lt, uint8_t* dst, uint64_t* bar) {           // rows beyond T are out of range -> zero fill
+    const int64_t tile = (int64_t)blockIdx.x + (int64_t)lt * gridDim.x;
+    mbar_arrive_expect_tx(bar, K::XT_BYTES);
+#pragma unroll
+    for (int pnl = 0; pnl < K::NP; ++pnl)
+      tma::load_4d(dst + pnl * K::PANEL, &mapX, pnl * 64, (int)(tile * 128), 0, 0, bar);
+  };
+
+  pdl_launch_dependents();
+  pdl_wait();                    // everything above touched only weights; from here on we read the producer's output
+
+  if (wg == 0) {
+    // =============================== role A: LayerNorm, one tile ahead of the GELU warpgroups ===============================
+    if (warp == 0) {
+      if (elect_one()) load_tile(0, sL, &bars[B_LFULL]);
+      __syncwarp();
+    }
+    const float inv_c = 1.0f / (float)creal;
+#pragma unroll 1
+    for (int t = 0; t < NT; ++t) {
+      mbar_wait(&bars[B_LFULL], t & 1);
+      M2_STAMP();   // A: tile landed
+      float s0 = 0.f, s1 = 0.f, q0 = 0.f, q1 = 0.f;
+#pragma unroll
+      for (int c = 0; c < K::NCH; ++c) {
+        const uint4 v = *reinterpret_cast<const uint4*>(sL + xt_off(row, c));
+        const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float2 f = up2(w4[q]);
+          s0 += f.x; s1 += f.y;
+          q0 = fmaf(f.x, f.x, q0); q1 = fmaf(f.y, f.y, q1);
+        }
+      }
+      const float mean = (s0 + s1) * inv_c;
+      const float var = (q0 + q1) * inv_c - mean * mean;
+      const float rstd = rsqrtf(fmaxf(var, 0.f) + 1e-5f);
+      const float nb = -mean * rstd;
+      if (t >= 1) { mbar_wait(&bars[B_XH_FREE], (t - 1) & 1); fence_after_sync(); }   // last fc1 chunk of the previous tile is done
+      M2_STAMP();   // A: XH free
+#pragma unroll
+      for (int c0 = 0; c0 < K::NCH; c0 += 4) {             // 4 chunks = 32 channels = 16 packed columns per store
+        uint32_t a[16];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const uint4 v = *reinterpret_cast<const uint4*>(sL + xt_off(row, c0 + c));
+          const uint32_t w4[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float2 f = up2(w4[q]);
+            a[4 * c + q] = pk2(fmaf(f.x, rstd, nb), fmaf(f.y, rstd, nb));
+          }
+        }
+        if (c0 == 4) a[14] = 0x3F803F80u;                  // ones at pad channels 60, 61 (folded fc1 bias)
+        tmem_st_x16(lane_addr + K::TM_XH + 4 * c0, a);
+      }
+      wg_sync(1);                                          // every row of L has been read twice: the next tile may land
+      if (warp == 0 && t + 1 < NT) {
+        if (elect_one()) load_tile(t + 1, sL, &bars[B_LFULL]);
+        __syncwarp();
+      }
+      wait_st();
+      warp_arrive(&bars[B_XH_READY], lane);
+    }
+  } else if (wg == 1 || wg == 2) {
+    // =============================== roles G0 / G1: GELU of alternate hidden chunks ===============================
+    const int w = wg - 1;
+    const uint32_t tH = lane_addr + K::TM_H + 64 * w, tHP = lane_addr + K::TM_HP + 32 * w;
+#pragma unroll 1
+    for (int k = w; k < NK; k += 2) {
+      const int c = k % NCHK;
+      const uint32_t ph = (k >> 1) & 1;
+      mbar_wait(&bars[B_H_FULL + w], ph);
+      fence_after_sync();
+      M2_STAMP();   // G: fc1 chunk ready
+      uint32_t v[64];
+      if (c == NCHK - 1 && K::LASTW < 64) {
+#pragma unroll
+        for (int c0 = 0; c0 < K::LASTW; c0 += 16) {
+          uint32_t t16[16];
+          tmem_ld_x16(tH + c0, t16);
+#pragma unroll
+          for (int e = 0; e < 16; ++e) v[c0 + e] = t16[e];
+        }
+      } else {
+        uint32_t a[32], b[32];
+        tmem_ld_x32(tH, a);
+        tmem_ld_x32(tH + 32, b);
+#pragma unroll
+        for (int e = 0; e < 32; ++e) { v[e] = a[e]; v[32 + e] = b[e]; }
+      }
+      wait_ld();
+      warp_arrive(&bars[B_H_DRAINED + w], lane);           // the next fc1 chunk of this slot may run under this GELU
+      uint32_t o[32];
+#pragma unroll
+      for (int j = 0; j < 32; ++j)
+        o[j] = (c == NCHK - 1 && 2 * j >= K::LASTW) ? 0u : gelu_pair<EXACT>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+      if (k >= 2) { mbar_wait(&bars[B_HP_FREE + w], ((k - 2) >> 1) & 1); fence_after_sync(); }   // fc2 of chunk k-2 has read the slot
+      if (c == NCHK - 1 && K::LASTW < 64) {
+        uint32_t t16[16], t8[8];
+#pragma unroll
+        for (int e = 0; e < 16; ++e) t16[e] = o[e];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) t8[e] = o[16 + e];
+        tmem_st_x16(tHP, t16);
+        if (K::LASTW > 32) tmem_st_x8(tHP + 16, t8);
+      } else {
+        tmem_st_x32(tHP, o);
+      }
+      wait_st();
+      warp_arrive(&bars[B_HP_READY + w], lane);
+      M2_STAMP();   // G: hidden chunk written
+    }
+  } else if (wg == 3) {
+    // =============================== role E: epilogue (+ DenseSTLayer tail) of finished tiles, E / Y TMA ===============================
+    const float inv_c = 1.0f / (float)creal;
+    if (warp == 12) {
+      if (elect_one()) load_tile(0, sE, &bars[B_EFULL]);
+      __syncwarp();
+    }
+#pragma unroll 1
+    for (int t = 0; t < NT; ++t) {
+      const int64_t t0 = ((int64_t)blockIdx.x + (int64_t)t * gridDim.x) * 128;
+      const uint32_t tO = lane_addr + K::TM_OUT + CP * (t & 1);
+      mbar_wait(&bars[B_OUT_FULL + (t & 1)], (t >> 1) & 1);
+      fence_after_sync();
+      mbar_wait(&bars[B_EFULL], t & 1);
+      M2_STAMP();   // E: fc2 done, residual rows landed
+      if (!TAIL && t >= 1) {                               // the store of the previous tile (issued a whole tile ago) has left Y
+        if (warp == 12) {
+          if (elect_one()) bulk_wait_read();
+          __syncwarp();
+        }
+        wg_sync(2);
+      }
+      float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+      for (int cb = 0; cb < CP; cb += 32) {                // y = acc + b2 + x, 32 columns at a time
+        uint32_t acc[32];
+        tmem_ld_x32(tO + cb, acc);
+        wait_ld();
+#pragma unroll
+        for (int c0 = 0; c0 < 32; c0 += 8) {
+          const uint32_t off = xt_off(row, (cb + c0) >> 3);
+          const uint4 xv = *reinterpret_cast<const uint4*>(sE + off);
+          const uint32_t xw[4] = {xv.x, xv.y, xv.z, xv.w};
+          uint32_t o[4];
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            const float2 xf = up2(xw[e]);
+            const int kk = c0 + 2 * e;
+            const float y0 = __uint_as_float(acc[kk]) + sB2[cb + kk] + xf.x;
+            const float y1 = __uint_as_float(acc[kk + 1]) + sB2[cb + kk + 1] + xf.y;
+            if (TAIL) {
+              s1 += y0 + y1;
+              s2 = fmaf(y0, y0, fmaf(y1, y1, s2));
+              acc[kk] = __float_as_uint(y0); acc[kk + 1] = __float_as_uint(y1);
+            } else {
+              o[e] = pk2(y0, y1);
+            }
+          }
+          if (!TAIL) *reinterpret_cast<uint4*>(sY + off) = make_uint4(o[0], o[1], o[2], o[3]);
+        }
+        if (TAIL) tmem_st_x32(tO + cb, acc);               // y (fp32) back in place: the row is normalised in a second pass
+      }
+      if (!TAIL) {
+        warp_arrive(&bars[B_OUT_FREE + (t & 1)], lane);    // the accumulator may take tile t+2
+        fence_proxy_async();                               // the finished rows are read by the TMA store (async proxy)
+        wg_sync(2);
+        M2_STAMP();   // E: y staged
+        if (warp == 12) {
+          if (elect_one()) {
+            tma::store_4d(&mapY, 0, (int)t0, 0, 0, sY);
+            if (K::NP > 1) tma::store_4d(&mapY, 64, (int)t0, 0, 0, sY + K::PANEL);
+            bulk_commit();
+            if (t + 1 < NT) load_tile(t + 1, sE, &bars[B_EFULL]);       // every row of E has been read (wg_sync above)
+          }
+          __syncwarp();
+        }
+      } else {
+        // LayerNorm of the block output (pads are exact zeros: they add nothing) -> packed bf16 over the first CP/2 columns
+        wait_st();
+        const float mean = s1 * inv_c;
+        const float var = fmaxf(s2 * inv_c - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + 1e-5f);
+#pragma unroll
+        for (int cb = 0; cb < CP; cb += 32) {
+          uint32_t y[32], o[16];
+          tmem_ld_x32(tO + cb, y);
+          wait_ld();
+#pragma unroll
+          for (int e = 0; e < 16; ++e) o[e] = pk2((__uint_as_float(y[2 * e]) - mean) * rstd, (__uint_as_float(y[2 * e + 1]) - mean) * rstd);
+          tmem_st_x16(tO + cb / 2, o);                     // columns [cb/2, cb/2+16) were consumed by an earlier block
+        }
+        wait_st();
+        warp_arrive(&bars[B_XT_READY], lane);
+        wg_sync(2);                                        // every row of E has been read
+        if (warp == 12 && t + 1 < NT) {
+          if (elect_one()) load_tile(t + 1, sE, &bars[B_EFULL]);
+          __syncwarp();
+        }
+        mbar_wait(&bars[B_TAIL_FULL], t & 1);
+        fence_after_sync();
+        uint32_t g[32];
+        tmem_ld_x32(tO + CP / 2, g);                       // growth projection, 32 columns (30 real), behind the packed x^'
+        wait_ld();
+        warp_arrive(&bars[B_OUT_FREE + (t & 1)], lane);
+        const int64_t tr = t0 + row;
+        if (tr < T) {
+          uint4* dst = reinterpret_cast<uint4*>(ta.dense + tr * ta.ldd);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            uint32_t o[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              o[j] = pk2((__uint_as_float(g[8 * q + 2 * j]) + sBT[8 * q + 2 * j]) * ta.scale,
+                         (__uint_as_float(g[8 * q + 2 * j + 1]) + sBT[8 * q + 2 * j + 1]) * ta.scale);
+            dst[q] = make_uint4(o[0], o[1], o[2], o[3]);
+          }
+        }
+        M2_STAMP();   // E: slice written
+      }
+    }
+    if (!TAIL && warp == 12) {
+      if (elect_one()) bulk_wait_read();
+      __syncwarp();
+    }
+  } else if (warp == 16) {
+    // =============================== fc1 issuer: chunk k -> accumulator slot k & 1 ===============================
+    mbar_wait(&bars[B_W1], 0);
+    for (int n = lane; n < HP; n += 32)                    // fold b1 into K rows 60 / 61 of the resident image
+      *reinterpret_cast<uint32_t*>(smem + K::OFF_W1 + (7 * HP + n) * 16 + 8) = bias_hi_lo(b1[n]);
+    fence_proxy_async();
+    __syncwarp();
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t aW1 = smem_u32(smem + K::OFF_W1);
+    constexpr uint32_t idw = make_idesc_bf16(128, 64, false, false);
+    constexpr uint32_t idl = make_idesc_bf16(128, K::LASTW, false, false);
+#pragma unroll 1
+    for (int k = 0; k < NK; ++k) {
+      const int t = k / NCHK, c = k - t * NCHK, s = k & 1;
+      if (c == 0) mbar_wait(&bars[B_XH_READY], t & 1);                           // x^ of this tile is in TMEM
+      if (k >= 2) mbar_wait(&bars[B_H_DRAINED + s], ((k - 2) >> 1) & 1);         // the slot's previous chunk is in registers
+      fence_after_sync();
+      if (elect_one()) {
+        const uint32_t d = tm + K::TM_H + 64 * s;
+        const uint32_t wb = aW1 + 64 * c * 16;
+        if (c == NCHK - 1) {
+#pragma unroll
+          for (int ks = 0; ks < CP / 16; ++ks)
+            mma_ts(d, tm + K::TM_XH + ks * 8, make_smem_desc(wb + ks * 2 * (HP * 16), HP * 16, 128), idl, ks > 0);
+        } else {
+#pragma unroll
+          for (int ks = 0; ks < CP / 16; ++ks)
+            mma_ts(d, tm + K::TM_XH + ks * 8, make_smem_desc(wb + ks * 2 * (HP * 16), HP * 16, 128), idw, ks > 0);
+        }
+        commit(&bars[B_H_FULL + s]);
+        if (c == NCHK - 1) commit(&bars[B_XH_FREE]);       // x^ may be replaced by the next tile's
+      }
+      __syncwarp();
+      M2_STAMP();   // I: fc1 chunk issued
+    }
+  } else if (warp == 17) {
+    // =============================== fc2 issuer: K-slice k out of hidden slot k & 1 (+ the TAIL Linear) ===============================
+    mbar_wait(&bars[B_W2], 0);
+    const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t aW2 = smem_u32(smem + K::OFF_W2), aWT = smem_u32(smem + K::OFF_WT);
+    constexpr uint32_t id2 = make_idesc_f16(128, CP, false, false);              // hidden and W2 are fp16
+    constexpr uint32_t idt = make_idesc_bf16(128, 32, false, false);
+    auto issue_tail = [&](int t) {
+      mbar_wait(&bars[B_XT_READY], t & 1);
+      fence_after_sync();
+      if (elect_one()) {
+        const uint32_t o = tm + K::TM_OUT + CP * (t & 1);
+#pragma unroll
+        for (int ks = 0; ks < CP / 16; ++ks)
+          mma_ts(o + CP / 2, o + ks * 8, make_smem_desc(aWT + ks * 2 * (32 * 16), 32 * 16, 128), idt, ks > 0);
+        commit(&bars[B_TAIL_FULL]);
+      }
+      __syncwarp();
+    };
+#pragma unroll 1
+    for (int k = 0; k < NK; ++k) {
+      const int t = k / NCHK, c = k - t * NCHK, s = k & 1;
+      mbar_wait(&bars[B_HP_READY + s], (k >> 1) & 1);
+      if (c == 0 && t >= 2) mbar_wait(&bars[B_OUT_FREE + (t & 1)], ((t - 2) >> 1) & 1);    // the accumulator of tile t-2 has been read
+      fence_after_sync();
+      if (elect_one()) {
+        const uint32_t d = tm + K::TM_OUT + CP * (t & 1), a = tm + K::TM_HP + 32 * s;
+        const int nks = (c == NCHK - 1 ? K::LASTW : 64) / 16;
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+          if (i < nks)
+            mma_ts(d, a + i * 8, make_smem_desc(aW2 + (4 * c + i) * 2 * (CP * 16), CP * 16, 128), id2, (c > 0 || i > 0) ? 1u : 0u);
+        commit(&bars[B_HP_FREE + s]);
+        if (c == NCHK - 1) commit(&bars[B_OUT_FULL + (t & 1)]);
+      }
+      __syncwarp();
+      // the tail Linear of the previous tile goes out one chunk into this tile: by then role E has normalised its rows
+      if (TAIL && t >= 1 && c == (NCHK > 1 ? 1 : 0)) issue_tail(t - 1);
+      M2_STAMP();   // I: fc2 slice issued
+    }
+    if (TAIL) issue_tail(NT - 1);
+  }
+#undef M2_STAMP
+  fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tmem_dealloc<512>(tmem);
+}
+
+static unsigned long long* g_dbg = nullptr;
+
+template <int CP, int HP>
+static int launch(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w1, const void* w2, const float* b1,
+                  const float* b2, int64_t T, int creal, int exact_gelu, const TailArgs* tail, int sms, cudaStream_t st) {
+  const int64_t ntiles = (T + 127) / 128;
+  const int grid = (int)(ntiles < sms ? ntiles : sms);
+  TailArgs ta{};
+  // activations as [T][CP] "images" of one row: box = 128 tokens x 64 channels
+  const CUtensorMap* mx = get_act_tmap(x, ldx, 1, 1, (int)T, CP, 128, 1);
+  const CUtensorMap* my = tail ? mx : get_act_tmap(y, ldy, 1, 1, (int)T, CP, 128, 1);
+  if (!mx || !my) return RDST_E_CUDA;
+  void (*k)(const CUtensorMap, const CUtensorMap, const uint8_t*, const uint8_t*, const float*, const float*, int64_t, int,
+            TailArgs, unsigned long long*);
+  int smem;
+  if (tail) {
+    ta = *tail;
+    smem = Cfg<CP, HP, true>::SMEM;
+    k = exact_gelu ? stl_mlp2_kernel<CP, HP, true, true, false> : stl_mlp2_kernel<CP, HP, false, true, false>;
+    if (g_dbg && !exact_gelu) k = stl_mlp2_kernel<CP, HP, false, true, true>;
+  } else {
+    smem = Cfg<CP, HP, false>::SMEM;
+    k = exact_gelu ? stl_mlp2_kernel<CP, HP, true, false, false> : stl_mlp2_kernel<CP, HP, false, false, false>;
+    if (g_dbg && !exact_gelu) k = stl_mlp2_kernel<CP, HP, false, false, true>;
+  }
+  cudaError_t e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+  if (e != cudaSuccess) { set_error("rdst_stl_mlp_fwd_bf16: smem attr (%d B): %s", smem, cudaGetErrorString(e)); return RDST_E_CUDA; }
+  e = launch_pdl(k, dim3(grid), dim3(THREADS), (size_t)smem, st, *mx, *my, (const uint8_t*)w1, (const uint8_t*)w2, b1, b2, T,
+                 creal, ta, g_dbg);
+  if (e != cudaSuccess) { set_error("rdst_stl_mlp_fwd_bf16: launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
+  return RDST_OK;
+}
+
+}  // namespace m2
+
+// entry used by tc_mlp.cu when the warp-specialised kernel is selected (the default); tail == nullptr: plain block
+int mlp_v2_dispatch(const void* x, int64_t ldx, void* y, int64_t ldy, const void* w1img, const void* w2img, const float* b1,
+                    const float* b2, int64_t T, int C, int exact_gelu, const void* wtimg, const float* bt, void* dense, int64_t ldd,
+                    float scale, int has_tail, int sms, cudaStream_t st) {
+  m2::TailArgs ta{(const uint8_t*)wtimg, bt, (__nv_bfloat16*)dense, ldd, scale};
+  const m2::TailArgs* tp = has_tail ? &ta : nullptr;
+  switch (C) {
+    case 60:  return m2::launch<64, 128>(x, ldx, y, ldy, w1img, w2img, b1, b2, T, 60, exact_gelu, tp, sms, st);
+    case 90:  return m2::launch<96, 192>(x, ldx, y, ldy, w1img, w2img, b1, b2, T, 90, exact_gelu, tp, sms, st);
+    case 120: return m2::launch<128, 240>(x, ldx, y, ldy, w1img, w2img, b1, b2, T, 120, exact_gelu, tp, sms, st);
+  }
+  set_error("rdst_stl_mlp_fwd_bf16: C=%d unsupported (60, 90, 120 with mlp_ratio 2)", C);
+  return RDST_E_UNSUPPORTED;
+}
+
+}  // namespace rdst
+
+extern "C" int rdst_debug_mlp2_timing(void* device_buffer_1280_u64) {
+  rdst::m2::g_dbg = (unsigned long long*)device_buffer_1280_u64;
+  return RDST_OK;
+}
