@@ -375,7 +375,7 @@ def main():
                 break
             except Exception:  # noqa: BLE001
                 pass
-        roof = {"bound": "tensor", "kernel": "stl_attn_kernel<120> (fused LN+QKV+QK^T+softmax+PV+proj, one launch)",
+        roof = {"bound": "tensor", "kernel": "a2::stl_attn2_kernel<120> (fused LN+QKV+QK^T+softmax+PV+proj, one launch, warp-specialised)",
                 "achieved": round(ach, 2), "peak": tf_peak, "unit": "TFLOP/s", "frac": round(ach / tf_peak, 4),
                 "traffic": traffic, "peak_source": f"{which} (bf16_tflops_sustained)",
                 "algorithmic_flop_per_launch": ATTN_FLOP_PER_WINDOW[120] * nwin, "algorithmic_bytes_per_launch": alg_bytes,
