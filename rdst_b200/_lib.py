@@ -9,7 +9,7 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "librdst_b200.so")
+LIB_PATH = os.environ.get("RDST_B200_LIB") or os.path.join(_HERE, "lib", "librdst_b200.so")   # (override: probe builds)
 
 F32, BF16 = 0, 1
 ABI_VERSION = 1

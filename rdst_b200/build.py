@@ -14,6 +14,9 @@ LIB = os.path.join(HERE, "lib", "librdst_b200.so")
 # no --use_fast_math: the fp32 (1e-4 parity) path relies on IEEE erff / expf / division
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xptxas", "-v"]
+# probe builds (timing experiments): RDST_NVCC_EXTRA="-DFOO" applies to the one source RDST_NVCC_EXTRA_FILE names
+EXTRA = os.environ.get("RDST_NVCC_EXTRA", "").split()
+EXTRA_FILE = os.environ.get("RDST_NVCC_EXTRA_FILE", "tc_attn2.cu")
 
 
 def _nvcc():
@@ -29,6 +32,8 @@ def _sources():
 
 def _stamp(src):
     h = hashlib.sha1()
+    if EXTRA and os.path.basename(src) == EXTRA_FILE:
+        h.update(" ".join(EXTRA).encode())
     for f in [src] + sorted(os.path.join(CSRC, x) for x in os.listdir(CSRC) if x.endswith((".cuh", ".h"))) + \
             [os.path.join(HERE, "..", "include", "rdst_b200.h")]:
         with open(f, "rb") as fh:
@@ -44,7 +49,7 @@ def _compile(name, verbose):
     stamp = _stamp(src)
     if os.path.exists(obj) and os.path.exists(stamp_file) and open(stamp_file).read() == stamp:
         return obj, ""
-    cmd = [_nvcc()] + NVCC_FLAGS + ["-c", src, "-o", obj]
+    cmd = [_nvcc()] + NVCC_FLAGS + (EXTRA if name == EXTRA_FILE else []) + ["-c", src, "-o", obj]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError(f"nvcc failed for {name}:\n{r.stdout}\n{r.stderr}")
