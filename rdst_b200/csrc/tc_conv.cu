@@ -10,6 +10,7 @@
 // convs + PixelShuffle (networks/common.py:129-132).
 #include "common.cuh"
 #include "umma.cuh"
+#include "tma.cuh"
 
 namespace rdst {
 using namespace umma;
@@ -238,150 +239,151 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
 
 // ------------------------------------------------------------------------------------------------------------------
 // Final 64 -> 1 convolution as a "tap GEMM": P[pos][tap] = sum_c x[pos][c] * w[tap][c] for every staged halo position
-// (one K = 64 GEMM with the 9 taps as N, padded to 16: 8 MMAs per tile instead of the 36 of the implicit-GEMM form,
-// which spent the tensor pipe on 15 zero output columns and was bound by its A reads), then the 9-point sum
+// (one K = 64 GEMM with the 9 taps as N, padded to 16: 4 MMAs per 128 positions instead of the 36 of the implicit-GEMM
+// form, which spent the tensor pipe on 15 zero output columns and was bound by its A reads), then the 9-point sum
 // out[y][x] = sum_tap P[(y+dy, x+dx)][tap] on the CUDA cores from shared memory.  HBM-bound: 128 B read per pixel.
+// Round 2: (a) the halo tile ((TH+2) x (TW+2) positions x 64 channels, up to 512 positions = 64 KB) arrives as ONE TMA
+// box, SWIZZLE_128B, i.e. directly as a K-major A operand (row = position); out-of-range coordinates zero-fill = the
+// convolution's padding.  The round-1 form staged it with 16-byte cp.async per thread and got 1.8 TB/s: with the loads
+// removed the same kernel ran in 80 us, with the epilogue removed in 259 of 262 us (probe builds) -- per-thread async
+// copies top out at ~10 B/clk/SM.  (b) a tile is up to four 128-position MMA blocks instead of two (halo over-read
+// 1.23x instead of 1.77x, the fixed per-tile chain is paid per ~416 pixels).  (c) warp 8 is producer + MMA issuer on
+// mbarriers (3-stage ring, two accumulator sets), warps 0-7 the epilogue: no CTA-wide barrier in the loop.
 // ------------------------------------------------------------------------------------------------------------------
 struct LastCfg {
-  static constexpr int NCH = 8;
-  static constexpr int W_BYTES = 64 * 16 * 2;                        // [8][16 taps][8] bf16
-  static constexpr int OFF_W = 0;
-  static constexpr int OFF_A = W_BYTES;
-  static constexpr int NSTAGE = 3;                                   // halo tiles in flight (two tiles of loads outstanding)
-  // staging buffers and the tap-product array are sized by the actual number of staged positions NP (<= CONV_NP_MAX)
-  __host__ __device__ static constexpr int a_bytes(int np) { return NCH * np * 16; }
-  __host__ __device__ static constexpr int off_p(int np) { return OFF_A + NSTAGE * a_bytes(np); }     // [9][NP] fp32 tap products
-  __host__ __device__ static constexpr int smem(int np) { return off_p(np) + 9 * np * 4; }
-  static constexpr int TMEM_COLS = 64;                               // 2 accumulator sets x 2 position blocks x 16 taps
+  static constexpr int NBLK_MAX = 4;                                 // blocks of 128 halo positions per tile
+  static constexpr int NP_MAX = 128 * NBLK_MAX;
+  static constexpr int W_BYTES = 64 * 16 * 2;                        // [8][16 taps][8] bf16 (SWIZZLE_NONE B operand)
+  static constexpr int NSTAGE = 3;                                   // halo tiles in flight
+  // per launch: nblk position blocks -> stage = nblk * 16 KB (1024-byte aligned), [9][nblk*128] fp32 tap products
+  __host__ __device__ static constexpr int a_bytes(int nblk) { return nblk * 128 * 128; }
+  __host__ __device__ static constexpr int off_w(int nblk) { return NSTAGE * a_bytes(nblk); }
+  __host__ __device__ static constexpr int off_p(int nblk) { return off_w(nblk) + W_BYTES; }
+  __host__ __device__ static constexpr int smem(int nblk) { return off_p(nblk) + 9 * nblk * 128 * 4; }
+  static constexpr int TMEM_COLS = 128;                              // 2 accumulator sets x 4 position blocks x 16 taps
 };
 
+// K-major SWIZZLE_128B operand (rows of 128 bytes = 64 bf16, 8-row groups of 1024 bytes): what a TMA box with a
+// 64-element inner extent and CU_TENSOR_MAP_SWIZZLE_128B leaves in shared memory.  A k-step of 16 advances the start by 32 B.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
 __global__ void __launch_bounds__(CONV_THREADS)
-last_conv_tap_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_t* __restrict__ wimg,
-                     float* __restrict__ img, ConvGeom g) {
+last_conv_tap_kernel(const __grid_constant__ CUtensorMap mapX, const uint8_t* __restrict__ wimg, float* __restrict__ img, ConvGeom g) {
   using K = LastCfg;
   extern __shared__ __align__(1024) uint8_t smem[];
-  __shared__ uint64_t bar[2];
+  __shared__ uint64_t full[K::NSTAGE], freeb[K::NSTAGE], tfull[2], tempty[2];
   __shared__ uint64_t wbar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  uint8_t* sW = smem + K::OFF_W;
-  uint8_t* sA = smem + K::OFF_A;
-  const int a_bytes = K::a_bytes(g.NP);
-  float* sP = reinterpret_cast<float*>(smem + K::off_p(g.NP));
+  const int nps = (g.TH + 2) * g.LW;                       // staged halo positions
+  const int nblk = (nps + 127) >> 7;                       // MMA blocks of 128 positions (the last one reads past nps: rows are
+  const int NPp = nblk * 128;                              //   independent, those products are never summed)
+  const int a_bytes = K::a_bytes(nblk);
+  uint8_t* sA = smem;
+  uint8_t* sW = smem + K::off_w(nblk);
+  float* sP = reinterpret_cast<float*>(smem + K::off_p(nblk));
 
   if (warp == 0) tmem_alloc<K::TMEM_COLS>(&tmem_base_s);
   if (tid == 0) {
-    mbar_init(&bar[0], 1);
-    mbar_init(&bar[1], 1);
+    for (int i = 0; i < K::NSTAGE; ++i) { mbar_init(&full[i], 1); mbar_init(&freeb[i], 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(&tfull[i], 1); mbar_init(&tempty[i], 8); }
     mbar_init(&wbar, 1);
     fence_mbar_init();
     mbar_arrive_expect_tx(&wbar, K::W_BYTES);
     bulk_g2s(sW, wimg, K::W_BYTES, &wbar);
   }
-  for (int i = tid; i < K::NSTAGE * a_bytes / 16; i += CONV_THREADS) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
-  fence_proxy_async();
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
-  const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
-  const uint32_t lboA = (uint32_t)g.NP * 16;
-  const int nps = (g.TH + 2) * g.LW;                       // staged halo positions (>= 128 for every tile shape)
-  const int blk1 = nps - 128;                              // second (overlapping) block of 128 positions
-  const int row = tid & 127, part = tid >> 7;
-  const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
   const int64_t ntiles = (int64_t)g.B * g.nty * g.ntx;
-  const int warp_u = __shfl_sync(0xffffffffu, warp, 0);
-  const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
-
-  auto stage = [&](int64_t tile, int buf) {      // always commits a (possibly empty) group: uniform group counting
-    if (warp >= 8 || tile >= ntiles) { cp_async_commit(); return; }
-    const int b = (int)(tile / (g.nty * g.ntx));
-    const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
-    const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
-    uint8_t* dst = sA + (size_t)buf * a_bytes;
-#pragma unroll 1
-    for (int pg = warp; pg * 8 < nps; pg += 8) {
-      const int pos = pg * 8 + (lane & 7);
-      if (pos >= nps) continue;
-      const int hy = pos / g.LW, hx = pos - hy * g.LW;
-      const int y = y0 - 1 + hy, x = x0 - 1 + hx;
-      const bool ok = y >= 0 && y < g.H && x >= 0 && x < g.W;
-      const __nv_bfloat16* src = X + (ok ? (((int64_t)b * g.H + y) * g.W + x) * ldx : 0);
-#pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j)
-        cp_async16(dst + (size_t)((lane >> 3) + 4 * j) * lboA + pos * 16, reinterpret_cast<const uint4*>(src) + (lane >> 3) + 4 * j,
-                   ok ? 16u : 0u);
-    }
-    cp_async_commit();
-  };
-  auto issue = [&](int sbuf, int buf) {        // warp 8, one elected lane: staging buffer sbuf -> accumulator set buf
-    constexpr uint32_t idesc = make_idesc_bf16(128, 16, false, false);
-    const uint32_t ab = aA + sbuf * a_bytes;
-#pragma unroll
-    for (int blk = 0; blk < 2; ++blk) {
-      const uint32_t a0 = ab + (uint32_t)(blk ? blk1 : 0) * 16;
-#pragma unroll
-      for (int ks = 0; ks < 4; ++ks)
-        mma_bf16_ss(tmem_u + buf * 32 + blk * 16, make_smem_desc(a0 + ks * 2 * lboA, lboA, 128),
-                    make_smem_desc(aW + ks * 2 * (16 * 16), 16 * 16, 128), idesc, ks > 0);
-    }
-    commit(&bar[buf]);
-  };
+  const int ntl = (int)((ntiles - (int64_t)blockIdx.x + (int64_t)gridDim.x - 1) / (int64_t)gridDim.x);   // tiles of this CTA
+  const int tpi = g.nty * g.ntx;
 
   pdl_launch_dependents();
   pdl_wait();
-  int buf = 0, sbuf = 0;
-  uint32_t par0 = 0, par1 = 0;
-  stage(blockIdx.x, 0);
-  stage((int64_t)blockIdx.x + gridDim.x, 1);
-  if ((int64_t)blockIdx.x < ntiles) {
-    cp_async_wait_group<1>();
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();
-    if (warp_u == 8) {
-      mbar_wait(&wbar, 0);
+  if (warp == 8) {
+    // ------------------------------- producer + MMA issuer -------------------------------
+    const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
+    const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
+    auto tma_tile = [&](int k) {                             // elected lane: halo box of this CTA's k-th tile -> stage k % NSTAGE
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)k * gridDim.x;
+      const int b = (int)(tile / tpi);
+      const int tr = (int)(tile - (int64_t)b * tpi);
+      const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
+      const int s = k % K::NSTAGE;
+      mbar_arrive_expect_tx(&full[s], (uint32_t)nps * 128u);
+      tma::load_4d(sA + (size_t)s * a_bytes, &mapX, 0, x0 - 1, y0 - 1, b, &full[s]);
+    };
+    if (elect_one())
+      for (int k = 0; k < ntl && k < K::NSTAGE; ++k) tma_tile(k);
+    __syncwarp();
+    mbar_wait(&wbar, 0);
+    constexpr uint32_t idesc = make_idesc_bf16(128, 16, false, false);
+    for (int i = 0; i < ntl; ++i) {
+      const int s = i % K::NSTAGE, set = i & 1;
+      mbar_wait(&full[s], (uint32_t)(i / K::NSTAGE) & 1u);
+      if (i >= 2) mbar_wait(&tempty[set], (uint32_t)((i >> 1) - 1) & 1u);     // epilogue of tile i-2 has read this accumulator set
       fence_after_sync();
-      if (elect_one()) issue(0, 0);
-      __syncwarp();
-    }
-  }
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1, sbuf = (sbuf + 1) % K::NSTAGE) {
-    const int b = (int)(tile / (g.nty * g.ntx));
-    const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
-    const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
-    const int64_t next = tile + gridDim.x;
-    stage(next + gridDim.x, (sbuf + 2) % K::NSTAGE);      // two tiles ahead; that buffer fed tile-1's MMAs (complete)
-    if (buf == 0) { mbar_wait(&bar[0], par0); par0 ^= 1; } else { mbar_wait(&bar[1], par1); par1 ^= 1; }
-    cp_async_wait_group<1>();                             // the next tile's halo has landed
-    fence_proxy_async();
-    fence_before_sync();
-    __syncthreads();          // next halo tile staged; previous tile's 9-point sums have read sP
-    fence_after_sync();
-    if (next < ntiles && warp_u == 8) {
-      if (elect_one()) issue((sbuf + 1) % K::NSTAGE, buf ^ 1);
-      __syncwarp();
-    }
-    if (warp < 8) {           // tap products of this thread's position -> shared memory, tap-major
-      uint32_t v[16];
-      tmem_ld_x16(lane_addr + buf * 32 + part * 16, v);
-      wait_ld();
-      const int pos = part ? blk1 + row : row;
+      if (elect_one()) {
+        const uint32_t ab = aA + (uint32_t)s * (uint32_t)a_bytes;
+#pragma unroll 1
+        for (int blk = 0; blk < nblk; ++blk)
 #pragma unroll
-      for (int t = 0; t < 9; ++t) sP[t * g.NP + pos] = __uint_as_float(v[t]);
-    }
-    fence_before_sync();
-    __syncthreads();
-    if (tid < 128) {
-      const int oy = row / g.LW, ox = row - oy * g.LW;
-      const int y = y0 + oy, x = x0 + ox;
-      if (ox < g.TW && oy < g.TH && y < g.H && x < g.W) {
-        float acc = 0.f;
-#pragma unroll
-        for (int t = 0; t < 9; ++t) acc += sP[t * g.NP + row + (t / 3) * g.LW + (t % 3)];
-        img[((int64_t)b * g.H + y) * g.W + x] = acc * g.out_scale + g.out_bias;
+          for (int ks = 0; ks < 4; ++ks)
+            mma_bf16_ss(tmem_u + set * 64 + blk * 16, make_smem_desc_sw128(ab + blk * (128 * 128) + ks * 32),
+                        make_smem_desc(aW + ks * 2 * (16 * 16), 16 * 16, 128), idesc, ks > 0);
+        commit(&tfull[set]);
+        commit(&freeb[s]);
       }
+      __syncwarp();
+      if (i >= 1 && i + 2 < ntl) {                           // refill the stage of tile i-1 (its MMAs were issued an iteration ago)
+        mbar_wait(&freeb[(i - 1) % K::NSTAGE], (uint32_t)((i - 1) / K::NSTAGE) & 1u);
+        if (elect_one()) tma_tile(i + 2);
+        __syncwarp();
+      }
+    }
+  } else {
+    // ------------------------------- epilogue: tap products -> shared memory -> 9-point sums -------------------------------
+    const int row = tid & 127, part = tid >> 7;
+    const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int nout = g.TH * g.TW;
+    const int twsh = 31 - __clz(g.TW);                       // TW is a power of two
+    for (int i = 0; i < ntl; ++i) {
+      const int64_t tile = (int64_t)blockIdx.x + (int64_t)i * gridDim.x;
+      const int b = (int)(tile / tpi);
+      const int tr = (int)(tile - (int64_t)b * tpi);
+      const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
+      const int set = i & 1;
+      mbar_wait(&tfull[set], (uint32_t)(i >> 1) & 1u);
+      fence_after_sync();
+      for (int blk = part; blk < nblk; blk += 2) {
+        uint32_t v[16];
+        tmem_ld_x16(lane_addr + set * 64 + blk * 16, v);
+        wait_ld();
+        const int pos = blk * 128 + row;
+#pragma unroll
+        for (int t = 0; t < 9; ++t) sP[t * NPp + pos] = __uint_as_float(v[t]);
+      }
+      fence_before_sync();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty[set]);
+      asm volatile("bar.sync 1, 256;" ::: "memory");
+      for (int o = tid; o < nout; o += 256) {
+        const int oy = o >> twsh, ox = o & (g.TW - 1);
+        const int y = y0 + oy, x = x0 + ox;
+        if (y < g.H && x < g.W) {
+          const float* pp = sP + oy * g.LW + ox;
+          float acc = 0.f;
+#pragma unroll
+          for (int t = 0; t < 9; ++t) acc += pp[t * NPp + (t / 3) * g.LW + (t % 3)];
+          img[((int64_t)b * g.H + y) * g.W + x] = acc * g.out_scale + g.out_bias;
+        }
+      }
+      asm volatile("bar.sync 1, 256;" ::: "memory");        // sP may be overwritten by the next tile
     }
   }
   fence_before_sync();
@@ -613,14 +615,21 @@ extern "C" int rdst_last_conv_fwd_bf16_tc(const void* x, int64_t ldx, const void
   if (B == 0) return RDST_OK;
   ConvGeom g{};
   g.B = B; g.H = H; g.W = W; g.shuffle = 0; g.out_scale = out_scale; g.out_bias = out_bias;
+  // tile: TW in {8,16,32,64} output columns, TH rows with (TH+2)*(TW+2) <= 512 staged halo positions (and >= 128: one full
+  // MMA block); pick the shape that stages the fewest positions for the whole image (halo over-read + ragged edges)
   int64_t best = -1;
-  for (int tw = 8; tw <= 32; tw += 8) {
-    const int th = (128 - tw) / (tw + 2) + 1;
-    const int64_t nt = (int64_t)((W + tw - 1) / tw) * ((H + th - 1) / th);
-    if (best < 0 || nt < best) { best = nt; g.TW = tw; g.TH = th; }
+  for (int tw = 8; tw <= 64; tw *= 2) {
+    const int lw = tw + 2;
+    int th = LastCfg::NP_MAX / lw - 2;
+    if (th > H) th = H;
+    while ((th + 2) * lw < 128) ++th;                   // tiny images: pad the tile downwards (rows beyond H are masked)
+    if (th < 1 || (th + 2) * lw > LastCfg::NP_MAX) continue;
+    const int64_t cost = (int64_t)((W + tw - 1) / tw) * ((H + th - 1) / th) * ((th + 2) * lw + 64);
+    if (best < 0 || cost <= best) { best = cost; g.TW = tw; g.TH = th; }
   }
+  RDST_REQUIRE(best >= 0, "rdst_last_conv_fwd_bf16_tc: no tile shape for H=%d W=%d", H, W);
   g.LW = g.TW + 2;
-  g.NP = (2 * g.LW + 2 + 128 + 7) / 8 * 8;
+  g.NP = ((g.TH + 2) * g.LW + 127) / 128 * 128;
   g.ntx = (W + g.TW - 1) / g.TW;
   g.nty = (H + g.TH - 1) / g.TH;
   int dev = 0, sms = 148;
@@ -630,18 +639,20 @@ extern "C" int rdst_last_conv_fwd_bf16_tc(const void* x, int64_t ldx, const void
   {
     using K = LastCfg;
     cudaStream_t st = (cudaStream_t)stream;
-    const int smem_bytes = K::smem(g.NP);
-    cudaError_t e = cudaFuncSetAttribute(last_conv_tap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::smem(CONV_NP_MAX));
+    const int nblk = ((g.TH + 2) * g.LW + 127) / 128;
+    const int smem_bytes = K::smem(nblk) + 1024;          // + slack: the dynamic segment is aligned to 1024 B by the kernel's declaration
+    const CUtensorMap* mx = get_act_tmap(x, ldx, B, H, W, 64, g.LW, g.TH + 2);     // halo box: 64 channels x LW x (TH+2)
+    if (!mx) return RDST_E_CUDA;
+    cudaError_t e = cudaFuncSetAttribute(last_conv_tap_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, K::smem(K::NBLK_MAX) + 1024);
     if (e != cudaSuccess) { set_error("rdst_last_conv_fwd_bf16_tc: smem attr: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
     int occ = (int)(232448 / (smem_bytes + 2048));
     if (occ > 512 / K::TMEM_COLS) occ = 512 / K::TMEM_COLS;
-    if (occ > 4) occ = 4;
     if (occ < 1) occ = 1;
     const int64_t ntiles = (int64_t)g.B * g.nty * g.ntx;
     int64_t gx = (int64_t)occ * sms;
     if (gx > ntiles) gx = ntiles;
     e = launch_pdl(last_conv_tap_kernel, dim3((unsigned)gx), dim3(CONV_THREADS), (size_t)smem_bytes, st,
-                   (const __nv_bfloat16*)x, ldx, (const uint8_t*)wimg, img, g);
+                   *mx, (const uint8_t*)wimg, img, g);
     if (e != cudaSuccess) { set_error("rdst_last_conv_fwd_bf16_tc: launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   }
   RDST_CHECK_LAUNCH("rdst_last_conv_fwd_bf16_tc");

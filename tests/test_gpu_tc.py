@@ -199,10 +199,11 @@ def test_fused_mlp_with_dense_tail(c, T):
     assert (d[:, 126:128] == 0).all()
 
 
-def test_last_conv_tc():
+@pytest.mark.parametrize("B,H,W", [(2, 32, 48), (1, 8, 8), (3, 160, 128), (2, 50, 70), (1, 16, 200), (5, 96, 24)])
+def test_last_conv_tc(B, H, W):
+    """tap-GEMM reconstruction conv: tiles of up to four 128-position blocks, ragged right / bottom tiles, tiny images"""
     from rdst_b200 import packing
     L = _L()
-    B, H, W = 2, 32, 48
     T = B * H * W
     x = _rand((T, 64), 41).to(torch.bfloat16)
     lw = torch.zeros(9, 64); lw[:, :60] = _rand((9, 60), 42, 0.1)
