@@ -342,11 +342,11 @@ def main():
     if not args.no_extras and args.precision == "bf16":
         extras = _extras(args, world, rank, dev, x_dev, run, barrier)
 
-    t = torch.tensor([ms_total, ms_e2e] + [extras.get(k, 0.0) for k in ("_e_ms", "_train_ms")], device=dev, dtype=torch.float64)
+    t = torch.tensor([ms_total, ms_e2e] + [extras.get(k, 0.0) for k in ("_e_ms", "_train_ms", "_strong_ms")], device=dev, dtype=torch.float64)
     if world > 1:
         import torch.distributed as dist
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, ms_e2e, e_ms, train_ms = (float(v) for v in t)
+    ms_total, ms_e2e, e_ms, train_ms, strong_ms = (float(v) for v in t)
     if rank != 0:
         if world > 1:
             import torch.distributed as dist
@@ -399,6 +399,11 @@ def main():
         line["rdst_e_cfg3"] = {"what": "RDST-E (4 RDSTBs) x4 bf16, same 176-slice batch per GPU, inputs resident",
                                "ms_per_step": round(e_ms, 3),
                                "value": round(world * HR_PIX_PER_VOLUME / (e_ms * 1e-3) / 1e6, 2), "unit": "Mpix/s"}
+    if strong_ms > 0:
+        line["rdst_e_cfg3_strong"] = {"what": f"ONE {SLICES}-slice RDST-E volume split over {world} GPU(s) (contiguous slice shares, no "
+                                              "collective), one CUDA-graph replay per rank, inputs resident, max over ranks",
+                                      "scaling": "strong", "ms_per_volume": round(strong_ms, 3),
+                                      "value": round(HR_PIX_PER_VOLUME / (strong_ms * 1e-3) / 1e6, 2), "unit": "Mpix/s"}
     if train_ms > 0:
         line["train_cfg4"] = dict(extras["_train_info"], ms_per_step=round(train_ms, 3),
                                   value=round(world * 32 * 96 * 96 / (train_ms * 1e-3) / 1e6, 3), unit="HR Mpix/s")
@@ -429,6 +434,20 @@ def _extras(args, world, rank, dev, x_dev, run, barrier):
         step_e()
     barrier()
     out["_e_ms"] = run(step_e, args.steps) / args.steps
+    # ---- cfg3 strong scaling: ONE 176-slice RDST-E volume over all ranks (contiguous slice shares, no collective), each
+    # rank replaying one CUDA graph of its share (rdst_b200.infer: super_resolve_volume_sharded(use_graph=True))
+    from rdst_b200 import infer as rinfer
+    b0, b1 = rinfer.shard_range(SLICES, world, rank)
+    xs = x_dev[b0:b1].contiguous()
+    ys = torch.empty(b1 - b0, 1, LR_H * SCALE, LR_W * SCALE, device=dev)
+
+    def step_strong():
+        rinfer.super_resolve_slices(me, xs, batch_size=SLICES, out=ys, use_graph=True)
+
+    for _ in range(3):
+        step_strong()
+    barrier()
+    out["_strong_ms"] = run(step_strong, args.steps) / args.steps
     del me
     # ---- cfg4: one data-parallel training step, whole step (fwd, L1, bwd, NCCL all-reduce, Adam) as one CUDA graph
     from rdst_b200 import ddp as rddp, train as rtrain

@@ -20,9 +20,11 @@ def shard_range(n_items, world_size, rank):
 
 
 @torch.no_grad()
-def super_resolve_slices(model, lr_slices, batch_size=176, out=None):
+def super_resolve_slices(model, lr_slices, batch_size=176, out=None, use_graph=False):
     """lr_slices: (N,1,H,W) float tensor on the HOST (ideally pinned) or on the model's device.
-    Returns (N,1,sH,sW) on the same side as the input.  One H2D + one D2H per batch, both asynchronous."""
+    Returns (N,1,sH,sW) on the same side as the input.  One H2D + one D2H per batch, both asynchronous.
+    use_graph: replay one captured CUDA graph per batch shape (`GraphedRDST`, cached on the model) instead of ~110 eager
+    launches -- what a rank wants when its share of a volume is a few dozen slices (launch-latency bound)."""
     dev = next(model.parameters()).device
     n = lr_slices.shape[0]
     s = model.sr_scale
@@ -33,11 +35,19 @@ def super_resolve_slices(model, lr_slices, batch_size=176, out=None):
     # pinned host output: the reconstruction kernel writes the HR slices straight into it (no separate D2H copy)
     direct = (on_host and out.is_pinned() and out.dtype == torch.float32 and out.is_contiguous() and
               getattr(model, "_exec", None) is not None and "out" in model.forward.__code__.co_varnames)
+    graphed = None
+    if use_graph:
+        graphed = getattr(model, "_graphed_forward", None)
+        if graphed is None:
+            graphed = GraphedRDST(model)
+            object.__setattr__(model, "_graphed_forward", graphed)      # plain attribute: not a submodule, not in the state_dict
     for b0 in range(0, n, batch_size):
         x = lr_slices[b0:b0 + batch_size]
         if on_host:
             x = x.to(dev, non_blocking=True)
-        if direct:
+        if graphed is not None:
+            out[b0:b0 + batch_size].copy_(graphed(x, clone=False), non_blocking=True)
+        elif direct:
             model(x, out=out[b0:b0 + batch_size])
         else:
             out[b0:b0 + batch_size].copy_(model(x), non_blocking=True)
@@ -46,10 +56,13 @@ def super_resolve_slices(model, lr_slices, batch_size=176, out=None):
     return out
 
 
-def super_resolve_volume_sharded(model, lr_volume, rank=0, world_size=1, batch_size=176):
-    """Each rank super-resolves its contiguous share of the slice axis; returns (begin, end, hr_slices)."""
+def super_resolve_volume_sharded(model, lr_volume, rank=0, world_size=1, batch_size=176, use_graph=None):
+    """Each rank super-resolves its contiguous share of the slice axis; returns (begin, end, hr_slices).
+    use_graph=None: graph replay when the share is smaller than one batch and the model sits on a GPU."""
     b, e = shard_range(lr_volume.shape[0], world_size, rank)
-    return b, e, super_resolve_slices(model, lr_volume[b:e], batch_size)
+    if use_graph is None:
+        use_graph = world_size > 1 and next(model.parameters()).is_cuda
+    return b, e, super_resolve_slices(model, lr_volume[b:e], batch_size, use_graph=use_graph)
 
 
 class GraphedRDST:
@@ -70,7 +83,8 @@ class GraphedRDST:
         return tuple((p.data_ptr(), p._version) for p in self.model.parameters())
 
     @torch.no_grad()
-    def __call__(self, x):
+    def __call__(self, x, clone=True):
+        """clone=False returns the graph's static output buffer (valid until the next replay of the same shape)."""
         if not x.is_cuda:
             raise RuntimeError("GraphedRDST: input must be a CUDA tensor")
         wkey = self._weights_key()
@@ -98,4 +112,4 @@ class GraphedRDST:
         graph, static_in, static_out, _ = entry
         static_in.copy_(x)
         graph.replay()
-        return static_out.clone()
+        return static_out.clone() if clone else static_out

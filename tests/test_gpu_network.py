@@ -112,6 +112,14 @@ def test_graphed_inference_driver_matches_eager():
     with torch.no_grad():
         ref = m(vol.cuda()).cpu()
     assert out.shape == (10, 1, 160, 128) and torch.equal(out, ref)
+    # graph replay per batch shape (the sharded driver's mode for small per-rank shares): same bits, host and device inputs
+    from rdst_b200.infer import super_resolve_volume_sharded
+    for src in (vol, vol.cuda()):
+        for _ in range(2):
+            og = super_resolve_slices(m, src, batch_size=4, use_graph=True)
+            assert og.is_cuda == src.is_cuda and torch.equal(og.cpu(), ref)
+    b0, b1, part = super_resolve_volume_sharded(m, vol.cuda(), rank=1, world_size=3)
+    assert (b0, b1) == (4, 7) and torch.equal(part.cpu(), ref[4:7])
 
 
 @pytest.mark.parametrize("precision", ["fp32", "bf16"])
