@@ -4,9 +4,12 @@ kernels of the earlier RDSTBs are still running.
 
 The training path (rdst_b200/autograd.py) is a chain of autograd.Functions (head, RDSTB 0..n-1, tail) with the weight
 packing of each link interleaved, so the engine finishes the parameter gradients link by link in reverse order.
-`BucketedAllReduce` keeps every bucket's gradients in ONE flat fp32 buffer (`p.grad` are views into it, so autograd
-accumulates in place and the collective needs no copy), counts accumulations with post-accumulate-grad hooks and
-launches `all_reduce(AVG)` asynchronously: ProcessGroupNCCL runs it on its own stream after an event on the compute
+`BucketedAllReduce` keeps every bucket's gradients in ONE flat fp32 buffer, counts accumulations with
+post-accumulate-grad hooks and, when a bucket's last gradient has landed, gathers the bucket with one multi-tensor copy
+(`torch._foreach_copy_`), re-points `p.grad` at the views of the flat buffer (what the optimizer then reads) and
+launches `all_reduce(AVG)` asynchronously.  (Round 1 pre-set `p.grad` to the zeroed views so that autograd accumulated in
+place "without a copy" -- but AccumulateGrad then runs one `add_` kernel per parameter, 826 launches = 1.85 ms of a
+22 ms step, measured with the reducer forced on ONE GPU; that, not NCCL, was the whole 1 -> 8 GPU scaling loss.) ProcessGroupNCCL runs it on its own stream after an event on the compute
 stream, and `finish()` makes the compute stream wait for all of them before the optimizer reads the gradients.
 Everything here is stream-ordered (no host sync), so a whole step -- forward, backward, the all-reduces and the
 optimizer -- can be captured into one CUDA graph (rdst_b200/train.py).
@@ -62,8 +65,23 @@ class BucketedAllReduce:
         def hook(_param):
             b["pending"] -= 1
             if b["pending"] == 0:
+                self._gather(b)
                 self._launch(b)
         return hook
+
+    @torch.no_grad()
+    def _gather(self, b):
+        """The bucket's gradients (fresh tensors autograd has just assigned to p.grad) -> the flat buffer, one multi-tensor
+        copy; afterwards p.grad ARE the views (parameters without a gradient keep zeros)."""
+        src, dst = [], []
+        for p, v in zip(b["params"], b["views"]):
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                src.append(p.grad)
+                dst.append(v)
+        if src:
+            torch._foreach_copy_(dst, src)
+        for p, v in zip(b["params"], b["views"]):
+            p.grad = v
 
     def _launch(self, b):
         b["fired"] = True
@@ -78,14 +96,14 @@ class BucketedAllReduce:
             self._works.append(dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True))
 
     def begin_step(self):
-        """Replaces optimizer.zero_grad(): zero the flat buffers and (re)attach the gradient views."""
+        """Replaces optimizer.zero_grad(): zero the flat buffers and drop the gradients (autograd then ASSIGNS the new
+        ones instead of launching an add per parameter)."""
         self._works, self.launch_order = [], []
         for b in self.buckets:
             b["flat"].zero_()
             b["pending"], b["fired"] = len(b["params"]), False
-            for p, v in zip(b["params"], b["views"]):
-                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
-                    p.grad = v
+            for p in b["params"]:
+                p.grad = None
 
     def finish(self):
         """Call after backward(): the current stream waits for every bucket's all-reduce."""
@@ -94,6 +112,7 @@ class BucketedAllReduce:
             raise RuntimeError(f"rdst_b200.ddp: buckets {[b['key'] for b in missing]} received no gradient in this backward "
                                "pass (pass allow_unused=True if the model has parameters its forward never uses)")
         for b in missing:                   # same set on every rank: the collective stays matched
+            self._gather(b)
             self._launch(b)
         for w in self._works:
             w.wait()

@@ -67,7 +67,15 @@ def main():
 
     def run(model, mode, steps, timed):
         opt = make_opt(model, mode == "graph")
-        reducer = rddp.BucketedAllReduce(model) if (world > 1 and ddp == "bucket") else None
+        nb = int(os.environ.get("RDST_DDP_BUCKETS", "0"))      # experiment: 1 = one all-reduce at the end, 3 = tail+body.4-7 | body.0-3 | head
+        def coarse(name):
+            k = rddp.rdst_link_of(name)
+            if nb == 1:
+                return "all"
+            if k.startswith("body."):
+                return "hi" if int(k.split(".")[1]) >= 4 else "lo"
+            return "hi" if k == "tail" else "lo2"
+        reducer = (rddp.BucketedAllReduce(model, bucket_of=coarse) if nb else rddp.BucketedAllReduce(model)) if ((world > 1 and ddp == "bucket") or os.environ.get("RDST_FORCE_REDUCER")) else None
         wrapped = model
         if world > 1 and ddp == "torch":
             wrapped = torch.nn.parallel.DistributedDataParallel(model, device_ids=[local], bucket_cap_mb=4)
