@@ -69,6 +69,15 @@ __device__ __forceinline__ uint32_t op(uint32_t v) {
     asm volatile("fma.rn.f16x2 %0, %0, %0, %1;" : "+r"(d) : "r"(0x3C003C00u));
     r = a ^ b ^ c ^ d;
   }
+  else if (OP == 30) {   // the MLP kernel's GELU stage on one pair: F2FP, x*x, fma, mul, 2 MUFU + PRMT, fma
+    uint32_t x, u, p, in, t;
+    asm volatile("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(x) : "f"(__uint_as_float(v)), "f"(__uint_as_float(v ^ 0x1234u)));
+    asm volatile("mul.f16x2 %0, %1, %1;" : "=r"(u) : "r"(x));
+    asm volatile("fma.rn.f16x2 %0, %1, %2, %3;" : "=r"(p) : "r"(u), "r"(0x28712871u), "r"(0x3A673A67u));
+    asm volatile("mul.f16x2 %0, %1, %2;" : "=r"(in) : "r"(x), "r"(p));
+    asm volatile("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(in));
+    asm volatile("fma.rn.f16x2 %0, %1, %2, %1;" : "=r"(r) : "r"(x), "r"(t));
+  }
   else if (OP == 15) asm volatile("cvt.rn.f16.f32 %0, %1;" : "=h"(*reinterpret_cast<unsigned short*>(&r)) : "f"(__uint_as_float(v)));
   else {  // OP 5: half2 polynomial exp2 (x <= 0): clamp, round via magic add, cubic, scale by exponent bits
     uint32_t x, t, n, f, p, sc;
@@ -121,6 +130,7 @@ int main() {
   run<6>("cvt f16x2.f32", 1); run<7>("cvt bf16x2.f32", 1); run<8>("fma.f16x2", 1); run<9>("min.f16x2", 1); run<10>("prmt", 1);
   run<11>("fma.f32", 1); run<12>("add.f16x2", 1); run<13>("max.f16x2", 1); run<14>("cvt f32.f16", 1); run<15>("cvt f16.f32", 1);
   run<16>("max.f32", 1); run<17>("lop3", 1); run<18>("shf", 1); run<19>("imad", 1);
+  run<30>("gelu pair", 2);
   run<20>("mufu+6ffma+3lop", 1); run<21>("mufu+3hfma2+3lop", 1); run<22>("mufu+2prmt+lop", 1); run<23>("2prmt+4hfma2+2lop", 1); run<24>("4ffma+4hfma2+3lop", 1);
   return 0;
 }
