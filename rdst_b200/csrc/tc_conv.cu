@@ -270,6 +270,12 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
          ((uint64_t)2 << 61);
 }
 
+// same for 64-byte rows (32 bf16): SWIZZLE_64B, 8-row groups of 512 bytes
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
+}
+
 __global__ void __launch_bounds__(CONV_THREADS)
 last_conv_tap_kernel(const __grid_constant__ CUtensorMap mapX, const uint8_t* __restrict__ wimg, float* __restrict__ img, ConvGeom g) {
   using K = LastCfg;
@@ -403,21 +409,27 @@ struct PairCfg {
   static constexpr int CIN = 160, NT = 32, NOUT = 64;
   static constexpr int NCH = CIN / 8;
   static constexpr int W_BYTES = 9 * CIN * NT * 2;               // this CTA's half of the filter
-  static constexpr int A_BYTES = NCH * CONV_NP_MAX * 16;
+  // halo tile = three TMA boxes: channels [0,64) and [64,128) as SWIZZLE_128B panels (128-byte rows = positions),
+  // channels [128,160) as a SWIZZLE_64B panel (64-byte rows).  Each IS a K-major A operand; tap (dy,dx) = start + rows.
+  static constexpr int PANEL = CONV_NP_MAX * 128;                // 25 600 B (a multiple of 1024)
+  static constexpr int A_BYTES = (2 * PANEL + CONV_NP_MAX * 64 + 1023) / 1024 * 1024;
   static constexpr int OFF_W = 0;
   static constexpr int OFF_A = W_BYTES;
   static constexpr int OFF_BIAS = OFF_A + 2 * A_BYTES;
+  static_assert(OFF_A % 1024 == 0 && PANEL % 1024 == 0, "swizzled panels need 1024-byte alignment");
   static constexpr int SMEM = OFF_BIAS + NOUT * 4;
   static constexpr int TMEM_COLS = 128;                           // two accumulators of 64 columns
 };
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(CONV_THREADS)
-conv3x3_pair_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_t* __restrict__ wimg,
+conv3x3_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_constant__ CUtensorMap mapB,
+                    const uint8_t* __restrict__ wimg,
                     const float* __restrict__ bias, const __nv_bfloat16* __restrict__ R, int64_t ldr,
                     __nv_bfloat16* __restrict__ Y, int64_t ldy, ConvGeom g) {
   using K = PairCfg;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar[2];
+  __shared__ uint64_t full[2];           // halo tile of staging buffer b has landed (TMA complete_tx)
   __shared__ uint64_t wbar;
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -430,13 +442,16 @@ conv3x3_pair_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
     mbar_init(&wbar, 1);
     fence_mbar_init();
     const uint8_t* src = wimg + (size_t)rank * K::W_BYTES;
     mbar_arrive_expect_tx(&wbar, K::W_BYTES);
     for (int off = 0; off < K::W_BYTES; off += 32768) bulk_g2s(sW + off, src + off, min(32768, K::W_BYTES - off), &wbar);
   }
-  for (int i = tid; i < 2 * K::A_BYTES / 16; i += CONV_THREADS) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+  // (no zero fill of the staging buffers: MMA rows beyond the staged positions only feed accumulator rows that are never
+  // stored -- rows are independent -- and the padding ring is the TMA's out-of-range zero fill)
   for (int i = tid; i < K::NOUT; i += CONV_THREADS) sBias[i] = bias[i];
   fence_proxy_async();
   fence_before_sync();
@@ -444,7 +459,6 @@ conv3x3_pair_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint
   fence_after_sync();
   const uint32_t tmem = tmem_base_s;
   const uint32_t aA = smem_u32(sA), aW = smem_u32(sW);
-  const uint32_t lboA = (uint32_t)g.NP * 16;
   const int nps = (g.TH + 2) * g.LW;
   const int row = tid & 127, part = tid >> 7;
   const uint32_t lane_addr = tmem + ((uint32_t)((warp & 3) * 32) << 16);
@@ -455,26 +469,18 @@ conv3x3_pair_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint
   const uint32_t tmem_u = __shfl_sync(0xffffffffu, tmem, 0);
   const bool leader = rank == 0;
 
-  auto stage = [&](int64_t tile, int buf) {
-    if (warp >= 8 || tile >= ntiles) { cp_async_commit(); return; }
+  // round 2: the halo tile arrives by TMA (round 1 staged it with 16-byte cp.async per thread, ~10 B/clk/SM: the kernel ran
+  // in 58 us with the loads removed and 81 us with them -- probe builds)
+  auto stage = [&](int64_t tile, int buf) {      // warp 0, one elected lane; returns whether a tile was requested
+    if (tile >= ntiles) return;
     const int b = (int)(tile / (g.nty * g.ntx));
     const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
     const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
     uint8_t* dst = sA + (size_t)buf * K::A_BYTES;
-#pragma unroll 1
-    for (int pg = warp; pg * 8 < nps; pg += 8) {
-      const int pos = pg * 8 + (lane & 7);
-      if (pos >= nps) continue;
-      const int hy = pos / g.LW, hx = pos - hy * g.LW;
-      const int y = y0 - 1 + hy, x = x0 - 1 + hx;
-      const bool ok = y >= 0 && y < g.H && x >= 0 && x < g.W;
-      const __nv_bfloat16* src = X + (ok ? (((int64_t)b * g.H + y) * g.W + x) * ldx : 0);
-#pragma unroll
-      for (int j = 0; j < K::NCH / 4; ++j)
-        cp_async16(dst + (size_t)((lane >> 3) + 4 * j) * lboA + pos * 16, reinterpret_cast<const uint4*>(src) + (lane >> 3) + 4 * j,
-                   ok ? 16u : 0u);
-    }
-    cp_async_commit();
+    mbar_arrive_expect_tx(&full[buf], (uint32_t)nps * 320u);
+    tma::load_4d(dst, &mapA, 0, x0 - 1, y0 - 1, b, &full[buf]);
+    tma::load_4d(dst + K::PANEL, &mapA, 64, x0 - 1, y0 - 1, b, &full[buf]);
+    tma::load_4d(dst + 2 * K::PANEL, &mapB, 128, x0 - 1, y0 - 1, b, &full[buf]);
   };
   auto issue = [&](int buf) {        // leader CTA, warp 8, one elected lane
     constexpr uint32_t idesc = make_idesc_bf16(256, K::NOUT, false, false);
@@ -482,12 +488,14 @@ conv3x3_pair_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint
     const uint32_t acc = tmem_u + buf * K::NOUT;
 #pragma unroll 1
     for (int tap = 0; tap < 9; ++tap) {
-      const uint32_t a0 = ab + (uint32_t)((tap / 3) * g.LW + (tap % 3)) * 16;
+      const uint32_t r0 = (uint32_t)((tap / 3) * g.LW + (tap % 3));        // first halo row of this tap
       const uint32_t w0 = aW + tap * (K::CIN * K::NT * 2);
 #pragma unroll
-      for (int ks = 0; ks < K::CIN / 16; ++ks)
-        mma_bf16_ss_pair(acc, make_smem_desc(a0 + ks * 2 * lboA, lboA, 128),
-                         make_smem_desc(w0 + ks * 2 * (K::NT * 16), K::NT * 16, 128), idesc, (tap | ks) > 0);
+      for (int ks = 0; ks < K::CIN / 16; ++ks) {
+        const uint64_t da = ks < 8 ? make_smem_desc_sw128(ab + (ks >> 2) * K::PANEL + r0 * 128 + (ks & 3) * 32)
+                                   : make_smem_desc_sw64(ab + 2 * K::PANEL + r0 * 64 + (ks & 1) * 32);
+        mma_bf16_ss_pair(acc, da, make_smem_desc(w0 + ks * 2 * (K::NT * 16), K::NT * 16, 128), idesc, (tap | ks) > 0);
+      }
     }
     commit_pair(&bar[buf]);
   };
@@ -496,8 +504,12 @@ conv3x3_pair_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint
   pdl_wait();
   int buf = 0;
   uint32_t par0 = 0, par1 = 0;
-  stage(2 * cid + rank, 0);
-  cp_async_wait_all();
+  uint32_t fpar0 = 0, fpar1 = 0;
+  if (warp == 0) {
+    if (elect_one()) stage(2 * cid + rank, 0);
+    __syncwarp();
+  }
+  if (2 * cid + rank < ntiles) { mbar_wait(&full[0], fpar0); fpar0 ^= 1; }
   if (warp_u == 8) mbar_wait(&wbar, 0);          // this CTA's half of the filter has landed
   fence_proxy_async();
   fence_before_sync();
@@ -514,9 +526,14 @@ conv3x3_pair_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint
     const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
     const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
     const int64_t npr = pr + ncl;
-    stage(2 * npr + rank, buf ^ 1);              // in flight under the MMAs of the current pair
+    if (warp == 0) {                             // in flight under the MMAs of the current pair
+      if (elect_one()) stage(2 * npr + rank, buf ^ 1);
+      __syncwarp();
+    }
     if (buf == 0) { mbar_wait(&bar[0], par0); par0 ^= 1; } else { mbar_wait(&bar[1], par1); par1 ^= 1; }
-    cp_async_wait_all();
+    if (2 * npr + rank < ntiles) {               // the next halo tile has landed
+      if (buf == 0) { mbar_wait(&full[1], fpar1); fpar1 ^= 1; } else { mbar_wait(&full[0], fpar0); fpar0 ^= 1; }
+    }
     fence_proxy_async();
     fence_before_sync();
     cluster_sync();           // both CTAs: next halo tiles staged, other accumulator drained
@@ -569,8 +586,11 @@ static int launch_conv_pair(const void* x, int64_t ldx, const void* wimg, const 
   int64_t ncl = sms / 2;
   if (ncl > npairs) ncl = npairs;
   if (ncl < 1) ncl = 1;
+  const CUtensorMap* ma = get_act_tmap(x, ldx, g.B, g.H, g.W, K::CIN, g.LW, g.TH + 2, 64);
+  const CUtensorMap* mb = get_act_tmap(x, ldx, g.B, g.H, g.W, K::CIN, g.LW, g.TH + 2, 32);
+  if (!ma || !mb) return RDST_E_CUDA;
   e = launch_pdl(conv3x3_pair_kernel, dim3((unsigned)(2 * ncl)), dim3(CONV_THREADS), (size_t)K::SMEM, st,
-                 (const __nv_bfloat16*)x, ldx, (const uint8_t*)wimg, bias, (const __nv_bfloat16*)r, ldr, (__nv_bfloat16*)y, ldy, g);
+                 *ma, *mb, (const uint8_t*)wimg, bias, (const __nv_bfloat16*)r, ldr, (__nv_bfloat16*)y, ldy, g);
   if (e != cudaSuccess) { set_error("rdst_conv3x3_fwd_bf16_tc (pair): launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   return RDST_OK;
 }

@@ -27,9 +27,9 @@ EncodeTiledFn encode_fn() {
 }
 
 struct MapKey {
-  const void* base; int64_t ld; int B, H, W, C, bw, bh;
+  const void* base; int64_t ld; int B, H, W, C, bw, bh, bc;
   bool operator==(const MapKey& o) const {
-    return base == o.base && ld == o.ld && B == o.B && H == o.H && W == o.W && C == o.C && bw == o.bw && bh == o.bh;
+    return base == o.base && ld == o.ld && B == o.B && H == o.H && W == o.W && C == o.C && bw == o.bw && bh == o.bh && bc == o.bc;
   }
 };
 struct MapEntry { MapKey key; CUtensorMap map; };
@@ -37,8 +37,9 @@ std::mutex g_mu;
 std::vector<MapEntry*> g_maps;       // entries are never freed or moved: callers keep the returned pointers
 }  // namespace
 
-const CUtensorMap* get_act_tmap(const void* base, int64_t ld, int B, int H, int W, int C, int bw, int bh) {
-  const MapKey key{base, ld, B, H, W, C, bw, bh};
+const CUtensorMap* get_act_tmap(const void* base, int64_t ld, int B, int H, int W, int C, int bw, int bh, int bc) {
+  if (bc != 64 && bc != 32) { set_error("get_act_tmap: box channel width must be 64 (SWIZZLE_128B) or 32 (SWIZZLE_64B)"); return nullptr; }
+  const MapKey key{base, ld, B, H, W, C, bw, bh, bc};
   std::lock_guard<std::mutex> lk(g_mu);
   for (MapEntry* e : g_maps)
     if (e->key == key) return &e->map;
@@ -48,10 +49,11 @@ const CUtensorMap* get_act_tmap(const void* base, int64_t ld, int B, int H, int 
   e->key = key;
   const cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t strides[3] = {(cuuint64_t)ld * 2, (cuuint64_t)W * ld * 2, (cuuint64_t)H * W * ld * 2};
-  const cuuint32_t box[4] = {64, (cuuint32_t)bw, (cuuint32_t)bh, 1};
+  const cuuint32_t box[4] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, 1};
   const cuuint32_t estr[4] = {1, 1, 1, 1};
   CUresult r = fn(&e->map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<void*>(base), dims, strides, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, bc == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {
     set_error("cuTensorMapEncodeTiled failed (%d) for base=%p ld=%lld B=%d H=%d W=%d C=%d", (int)r, base, (long long)ld, B, H, W, C);

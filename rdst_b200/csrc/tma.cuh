@@ -12,9 +12,9 @@
 
 namespace rdst {
 
-// host: encode (and cache) the map of a [B][H][W][C<=ld] bf16 activation with box {64 ch, bw, bh, 1}
-// returns nullptr (and sets the error string) on failure
-const CUtensorMap* get_act_tmap(const void* base, int64_t ld, int B, int H, int W, int C, int bw, int bh);
+// host: encode (and cache) the map of a [B][H][W][C<=ld] bf16 activation with box {bc ch, bw, bh, 1}; bc = 64 ->
+// SWIZZLE_128B (128-byte rows), bc = 32 -> SWIZZLE_64B (64-byte rows).  Returns nullptr (and sets the error string) on failure
+const CUtensorMap* get_act_tmap(const void* base, int64_t ld, int B, int H, int W, int C, int bw, int bh, int bc = 64);
 
 namespace tma {
 
