@@ -40,14 +40,28 @@ struct ConvGeom {
   float out_bias;      // NT == 16 ("last conv" mode): img = (acc + bias0) * out_scale + out_bias, fp32 NCHW, 1 channel
 };
 
+// K-major SWIZZLE_128B operand (rows of 128 bytes = 64 bf16, 8-row groups of 1024 bytes): what a TMA box with a
+// 64-element inner extent and CU_TENSOR_MAP_SWIZZLE_128B leaves in shared memory.  A k-step of 16 advances the start by 32 B.
+__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)2 << 61);
+}
+
+// same for 64-byte rows (32 bf16): SWIZZLE_64B, 8-row groups of 512 bytes
+__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
+  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
+         ((uint64_t)4 << 61);
+}
+
 template <int CIN, int NT>
 struct ConvCfg {
   static constexpr int NCH = CIN / 8;
   static constexpr int W_BYTES = 9 * CIN * NT * 2;
   static constexpr int A_BYTES = NCH * CONV_NP_MAX * 16;
   static constexpr int OFF_W = 0;
-  static constexpr int OFF_A = W_BYTES;                  // two staging buffers: tile n+1 is staged while tile n's MMAs run
-  static constexpr int OFF_BIAS = OFF_A + 2 * A_BYTES;
+  static constexpr int OFF_A = W_BYTES;                  // staging buffers: tile n+1 is staged while tile n's MMAs run
+  static constexpr int NSTG = CIN == 64 ? 3 : 2;         // Cin = 64 (TMA staging): a ring of three, loads run two tiles ahead
+  static constexpr int OFF_BIAS = OFF_A + NSTG * A_BYTES;
   static constexpr int SMEM = OFF_BIAS + NT * 4;
   static constexpr int TMEM_COLS = NT <= 16 ? 32 : 2 * NT;   // two accumulators: tile n+1 runs under tile n's epilogue
   static_assert(NCH % 4 == 0 && (NT == 16 || NT == 32 || NT == 64 || NT == 128), "shape");
@@ -57,12 +71,19 @@ constexpr int CONV_THREADS = 288;     // warps 0..7 stage and run the epilogue, 
 
 template <int CIN, int NT, bool DBG>       // DBG: clock64() phase stamps (rdst_debug_conv_timing)
 __global__ void __launch_bounds__(CONV_THREADS)
-conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_t* __restrict__ wimg,
+conv3x3_tc_kernel(const __grid_constant__ CUtensorMap mapX, const __nv_bfloat16* __restrict__ X, int64_t ldx,
+                  const uint8_t* __restrict__ wimg,
                   const float* __restrict__ bias, const __nv_bfloat16* __restrict__ R, int64_t ldr,
                   __nv_bfloat16* __restrict__ Y, int64_t ldy, ConvGeom g, unsigned long long* __restrict__ dbg) {
   using K = ConvCfg<CIN, NT>;
+  // Cin = 64 (round 2): the halo tile is ONE TMA box, SWIZZLE_128B = the K-major A operand (row = halo position, tap (dy,dx)
+  // = descriptor start advanced by (dy*LW+dx) rows; the hardware derives the swizzle phase from the address, so unaligned
+  // row offsets need no base offset -- verified with the reconstruction conv).  Probe builds without the loads: the 16-byte
+  // cp.async staging cost 152 of 369 us in the 80x64 up-conv, 35 of 96 us and 16 of 64 us in the 40x32 convs.
+  constexpr bool TMA_A = CIN == 64;
   extern __shared__ __align__(1024) uint8_t smem[];
   __shared__ uint64_t bar[2];           // accumulator b complete
+  __shared__ uint64_t full[3];          // TMA_A: halo tile of staging buffer b has landed
   __shared__ uint64_t wbar;             // weights landed (bulk async copies)
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -75,6 +96,9 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
   if (tid == 0) {
     mbar_init(&bar[0], 1);
     mbar_init(&bar[1], 1);
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    mbar_init(&full[2], 1);
     mbar_init(&wbar, 1);
     fence_mbar_init();
     // the filter slice arrives by bulk async copies that overlap the staging of the first halo tile
@@ -83,7 +107,8 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
     for (int off = 0; off < K::W_BYTES; off += 32768) bulk_g2s(sW + off, src + off, min(32768, K::W_BYTES - off), &wbar);
   }
   {
-    for (int i = tid; i < 2 * K::A_BYTES / 16; i += CONV_THREADS) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
+    if (!TMA_A)         // (TMA_A: stale rows beyond the staged positions only feed accumulator rows that are never stored)
+      for (int i = tid; i < 2 * K::A_BYTES / 16; i += CONV_THREADS) *reinterpret_cast<uint4*>(sA + (size_t)i * 16) = make_uint4(0, 0, 0, 0);
     for (int i = tid; i < NT; i += CONV_THREADS) sBias[i] = (NT == 16) ? 0.f : bias[slice * NT + i];
   }
   fence_proxy_async();
@@ -104,6 +129,19 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
   // the padding ring: nothing waits on the loads until the tile's MMAs are about to be issued (a register-staged copy
   // serialised three L2 round trips per warp, and the warp that also issued MMAs started its share last)
   auto stage = [&](int64_t tile, int buf) {
+    if (TMA_A) {
+      if (warp == 0) {
+        if (elect_one()) {
+          const int b = (int)(tile / (g.nty * g.ntx));
+          const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
+          const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
+          mbar_arrive_expect_tx(&full[buf], (uint32_t)nps * 128u);
+          tma::load_4d(sA + (size_t)buf * K::A_BYTES, &mapX, 0, x0 - 1, y0 - 1, b, &full[buf]);
+        }
+        __syncwarp();
+      }
+      return;
+    }
     if (warp >= 8) return;
     const int b = (int)(tile / (g.nty * g.ntx));
     const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
@@ -124,17 +162,18 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
     }
     cp_async_commit();
   };
-  auto issue = [&](int buf) {        // warp 8, one elected lane: staging buffer `buf` -> accumulator `buf`
+  auto issue = [&](int sb, int buf) {        // warp 8, one elected lane: staging buffer `sb` -> accumulator `buf`
     constexpr uint32_t idesc = make_idesc_bf16(128, NT, false, false);
-    const uint32_t ab = aA + buf * K::A_BYTES;
+    const uint32_t ab = aA + sb * K::A_BYTES;
     const uint32_t acc = tmem_u + buf * NT;
 #pragma unroll 1
     for (int tap = 0; tap < 9; ++tap) {
-      const uint32_t a0 = ab + (uint32_t)((tap / 3) * g.LW + (tap % 3)) * 16;
+      const uint32_t r0 = (uint32_t)((tap / 3) * g.LW + (tap % 3));
+      const uint32_t a0 = ab + r0 * 16;
       const uint32_t w0 = aW + tap * (CIN * NT * 2);
 #pragma unroll
       for (int ks = 0; ks < CIN / 16; ++ks)
-        mma_bf16_ss(acc, make_smem_desc(a0 + ks * 2 * lboA, lboA, 128),
+        mma_bf16_ss(acc, TMA_A ? make_smem_desc_sw128(ab + r0 * 128 + ks * 32) : make_smem_desc(a0 + ks * 2 * lboA, lboA, 128),
                     make_smem_desc(w0 + ks * 2 * (NT * 16), NT * 16, 128), idesc, (tap | ks) > 0);
     }
     commit(&bar[buf]);
@@ -148,10 +187,15 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
   } while (0)
   pdl_launch_dependents();
   pdl_wait();                    // only the filter slice was touched so far; activations come from the previous kernel
-  int buf = 0;
-  uint32_t par0 = 0, par1 = 0;
+  int buf = 0, sb = 0;                   // accumulator / staging buffer of the current tile (sb == buf unless TMA_A)
+  uint32_t par0 = 0, par1 = 0, fpar = 0; // fpar: bit s = phase parity of full[s]
   if ((int64_t)blockIdx.x < ntiles) {
     stage(blockIdx.x, 0);
+    if (TMA_A) {
+      if ((int64_t)blockIdx.x + gridDim.x < ntiles) stage((int64_t)blockIdx.x + gridDim.x, 1);
+      mbar_wait(&full[0], 0);
+      fpar ^= 1u;
+    }
     cp_async_wait_all();
     fence_proxy_async();
     fence_before_sync();
@@ -159,27 +203,36 @@ conv3x3_tc_kernel(const __nv_bfloat16* __restrict__ X, int64_t ldx, const uint8_
     if (warp_u == 8) {
       mbar_wait(&wbar, 0);             // filter slice has landed
       fence_after_sync();
-      if (elect_one()) issue(0);
+      if (elect_one()) issue(0, 0);
       __syncwarp();
     }
   }
-  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1) {
+  for (int64_t tile = blockIdx.x; tile < ntiles; tile += gridDim.x, buf ^= 1, sb = TMA_A ? (sb + 1) % 3 : sb ^ 1) {
     const int b = (int)(tile / (g.nty * g.ntx));
     const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
     const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
     const int64_t next = tile + gridDim.x;
     RDST_TSTAMP();   // tile start
-    if (next < ntiles) stage(next, buf ^ 1);       // in flight under the MMAs of the current tile
+    const int sn = TMA_A ? (sb + 1) % 3 : sb ^ 1;  // staging buffer of the next tile
+    if (TMA_A) {                                   // two tiles ahead, into the buffer the previous tile's (complete) MMAs read
+      if (next + gridDim.x < ntiles) stage(next + gridDim.x, (sb + 2) % 3);
+    } else if (next < ntiles) {
+      stage(next, sn);                             // in flight under the MMAs of the current tile
+    }
     RDST_TSTAMP();   // next staged
     if (buf == 0) { mbar_wait(&bar[0], par0); par0 ^= 1; } else { mbar_wait(&bar[1], par1); par1 ^= 1; }
     RDST_TSTAMP();   // MMAs done
+    if (TMA_A && next < ntiles) {
+      mbar_wait(&full[sn], (fpar >> sn) & 1u);
+      fpar ^= 1u << sn;
+    }
     cp_async_wait_all();
     fence_proxy_async();
     fence_before_sync();
     __syncthreads();          // next halo tile staged; every thread has drained the other accumulator (previous epilogue)
     fence_after_sync();
     if (next < ntiles && warp_u == 8) {            // the next tile's MMAs run under this tile's epilogue
-      if (elect_one()) issue(buf ^ 1);
+      if (elect_one()) issue(sn, buf ^ 1);
       __syncwarp();
     }
     if (warp >= 8) continue;
@@ -262,19 +315,6 @@ struct LastCfg {
   __host__ __device__ static constexpr int smem(int nblk) { return off_p(nblk) + 9 * nblk * 128 * 4; }
   static constexpr int TMEM_COLS = 128;                              // 2 accumulator sets x 4 position blocks x 16 taps
 };
-
-// K-major SWIZZLE_128B operand (rows of 128 bytes = 64 bf16, 8-row groups of 1024 bytes): what a TMA box with a
-// 64-element inner extent and CU_TENSOR_MAP_SWIZZLE_128B leaves in shared memory.  A k-step of 16 advances the start by 32 B.
-__device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)2 << 61);
-}
-
-// same for 64-byte rows (32 bf16): SWIZZLE_64B, 8-row groups of 512 bytes
-__device__ __forceinline__ uint64_t make_smem_desc_sw64(uint32_t saddr) {
-  return (uint64_t)((saddr >> 4) & 0x3FFFu) | ((uint64_t)1 << 16) | ((uint64_t)(512 >> 4) << 32) | ((uint64_t)1 << 46) |
-         ((uint64_t)4 << 61);
-}
 
 __global__ void __launch_bounds__(CONV_THREADS)
 last_conv_tap_kernel(const __grid_constant__ CUtensorMap mapX, const uint8_t* __restrict__ wimg, float* __restrict__ img, ConvGeom g) {
@@ -432,7 +472,7 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   __shared__ uint64_t full[2];           // halo tile of staging buffer b has landed (TMA complete_tx)
   __shared__ uint64_t wbar;
   __shared__ uint32_t tmem_base_s;
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, warp = tid >> 5;
   const int rank = (int)cluster_ctarank();
   uint8_t* sW = smem + K::OFF_W;
   uint8_t* sA = smem + K::OFF_A;
@@ -613,7 +653,9 @@ static int launch_conv(const void* x, int64_t ldx, const void* wimg, const float
   if (gx < 1) gx = 1;
   if (gx > ntiles) gx = ntiles;
   dim3 grid((unsigned)gx, (unsigned)nslices);
-  e = launch_pdl(k, grid, dim3(CONV_THREADS), (size_t)K::SMEM, st, (const __nv_bfloat16*)x, ldx, (const uint8_t*)wimg, bias,
+  const CUtensorMap* mx = get_act_tmap(x, ldx, g.B, g.H, g.W, CIN == 64 ? 64 : CIN, g.LW, g.TH + 2, 64);   // (used when CIN == 64)
+  if (!mx) return RDST_E_CUDA;
+  e = launch_pdl(k, grid, dim3(CONV_THREADS), (size_t)K::SMEM, st, *mx, (const __nv_bfloat16*)x, ldx, (const uint8_t*)wimg, bias,
                  (const __nv_bfloat16*)r, ldr, (__nv_bfloat16*)y, ldy, g, g_conv_dbg);
   if (e != cudaSuccess) { set_error("rdst_conv3x3_fwd_bf16_tc: launch: %s", cudaGetErrorString(e)); return RDST_E_CUDA; }
   return RDST_OK;
