@@ -268,8 +268,9 @@ def main():
         del y_chk
 
     launches = [0]
-    ktime = {"events": [], "on": False}
+    ktime = {"events": [], "on": False, "hbm_events": []}
     TOP = "rdst_stl_attn_fwd_bf16"
+    HBM_KERNEL = "rdst_last_conv_fwd_bf16_tc"        # the step's HBM-bound kernel (reads the 64-channel HR feature map once)
     orig_call = ex_mod.call
 
     def counting_call(name, *a):
@@ -280,6 +281,12 @@ def main():
             orig_call(name, *a)
             e1.record()
             ktime["events"].append((e0, e1, a[12]))          # a[12] = C of this launch
+        elif ktime["on"] and name == HBM_KERNEL:
+            e0, e1 = torch.cuda.Event(True), torch.cuda.Event(True)
+            e0.record()
+            orig_call(name, *a)
+            e1.record()
+            ktime["hbm_events"].append((e0, e1))
         else:
             orig_call(name, *a)
 
@@ -383,6 +390,17 @@ def main():
                              "frac": round(alg_bytes / avg_s / 1e9 / hbm_peak, 4)},
                 "launches_timed": n_ev, "avg_launch_us": round(avg_s * 1e6, 2),
                 "share_of_step": round(tot_ms / ms_instr, 4), "ms_per_step_instrumented": round(ms_instr / args.steps, 3)}
+    hbm_roof = None
+    if ktime["hbm_events"]:
+        # reconstruction conv (64 -> 1 channels, 3x3) on the x4 feature map: algorithmic bytes = the bf16 input read once
+        # (128 B per HR pixel) + the fp32 image written once (4 B per HR pixel)
+        hr_px = SLICES * LR_H * SCALE * LR_W * SCALE
+        bytes_alg = hr_px * (64 * 2 + 4)
+        avg_s2 = sum(a.elapsed_time(b) for a, b in ktime["hbm_events"]) * 1e-3 / len(ktime["hbm_events"])
+        hbm_roof = {"bound": "hbm", "kernel": "last_conv_tap_kernel (3x3 reconstruction conv as a tap GEMM, TMA-fed)",
+                    "achieved": round(bytes_alg / avg_s2 / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
+                    "frac": round(bytes_alg / avg_s2 / 1e9 / hbm_peak, 4), "algorithmic_bytes_per_launch": bytes_alg,
+                    "avg_launch_us": round(avg_s2 * 1e6, 2), "launches_timed": len(ktime["hbm_events"]), "traffic": None}
     whole = FLOP_PER_LR_PX * SLICES * LR_H * LR_W * world / (ms_step * 1e-3) / 1e12
     line = {"metric": "HR output Mpix/s (RDST-E1 x4 inference)", "value": round(value, 2), "unit": "Mpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
@@ -395,6 +413,8 @@ def main():
             "whole_net_tflops": round(whole, 2), "whole_net_frac_of_tensor_peak": round(whole / tf_peak / world, 4)}
     if roof:
         line["roofline"] = roof
+    if hbm_roof:
+        line["roofline_hbm_kernel"] = hbm_roof
     if e_ms > 0:
         line["rdst_e_cfg3"] = {"what": "RDST-E (4 RDSTBs) x4 bf16, same 176-slice batch per GPU, inputs resident",
                                "ms_per_step": round(e_ms, 3),
