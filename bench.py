@@ -401,6 +401,12 @@ def main():
                     "achieved": round(bytes_alg / avg_s2 / 1e9, 1), "peak": hbm_peak, "unit": "GB/s",
                     "frac": round(bytes_alg / avg_s2 / 1e9 / hbm_peak, 4), "algorithmic_bytes_per_launch": bytes_alg,
                     "avg_launch_us": round(avg_s2 * 1e6, 2), "launches_timed": len(ktime["hbm_events"]), "traffic": None}
+        try:
+            with open(os.path.join(ROOT, "profiles", "r2_traffic.json")) as f:
+                tj = json.load(f)["last_conv_tap_kernel"]
+            hbm_roof["traffic"] = tj["dram_read_bytes"] + tj["dram_write_bytes"]
+        except Exception:  # noqa: BLE001
+            pass
     whole = FLOP_PER_LR_PX * SLICES * LR_H * LR_W * world / (ms_step * 1e-3) / 1e12
     line = {"metric": "HR output Mpix/s (RDST-E1 x4 inference)", "value": round(value, 2), "unit": "Mpix/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms_step, 3),
