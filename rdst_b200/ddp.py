@@ -65,6 +65,7 @@ class BucketedAllReduce:
         def hook(_param):
             b["pending"] -= 1
             if b["pending"] == 0:
+                b["pending"] = len(b["params"])      # re-armed for the next backward, with or without begin_step()
                 self._gather(b)
                 self._launch(b)
         return hook
@@ -117,6 +118,9 @@ class BucketedAllReduce:
         for w in self._works:
             w.wait()
         self._works = []
+        for b in self.buckets:              # a loop that calls optimizer.zero_grad() instead of begin_step() keeps working: the
+            b["fired"] = False              # next backward assigns fresh gradients and the hooks gather them again
+            b["pending"] = len(b["params"])
 
     def remove(self):
         for h in self._hooks:
