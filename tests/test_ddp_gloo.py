@@ -105,9 +105,22 @@ def _worker(rank, world, port, ret):
     red2.finish()
     unused_ok = red2.launch_order[0] == "body.0" and set(red2.launch_order) == {"body.0", "body.1", "body.2", "head", "tail"} \
         and float(net.tail.weight.grad.abs().max()) == 0.0
+    red2.remove()
+    # a training loop that keeps optimizer.zero_grad(set_to_none=True) instead of begin_step(): autograd assigns fresh gradients,
+    # the hooks gather them into the flat buffers; two steps, averaged gradients as above both times
+    red3 = ddp.BucketedAllReduce(net)
+    opt = torch.optim.SGD([p for p in net.parameters() if p.requires_grad], lr=0.0)
+    zg_err = 0.0
+    for step in range(2):
+        opt.zero_grad(set_to_none=True)
+        torch.nn.functional.l1_loss(net(x), y).backward()
+        red3.finish()
+        got3 = [p.grad for p in net.parameters() if p.requires_grad]
+        zg_err = max(zg_err, max((g - a).abs().max().item() for g, a in zip(got3, acc)))
+    red3.remove()
     if rank == 0:
         ret.update(ok=bool(ok), err=err, raised=raised, frozen_grad=net.frozen.grad is None, unused_ok=bool(unused_ok),
-                   keys=[b["key"] for b in red.buckets])
+                   keys=[b["key"] for b in red.buckets], zg_err=zg_err)
     dist.barrier()
     dist.destroy_process_group()
 
@@ -121,6 +134,7 @@ def test_bucketed_allreduce_two_ranks():
     assert ret["err"] < 1e-6, ret["err"]
     assert ret["raised"] and ret["frozen_grad"] and ret["unused_ok"]
     assert sorted(ret["keys"]) == ["body.0", "body.1", "body.2", "head", "tail"]
+    assert ret["zg_err"] < 1e-6, ret["zg_err"]      # optimizer.zero_grad() in place of begin_step()
 
 
 def test_rdst_link_of_maps_state_dict_names():

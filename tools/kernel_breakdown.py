@@ -6,7 +6,8 @@ for p in (ROOT, os.path.join(ROOT, "oracle"), os.path.join(ROOT, "tests")):
     sys.path.insert(0, p)
 import helpers
 from rdst_b200 import executor as ex
-m = helpers.make_module(8, 4, "bf16").cuda().eval()
+PREC = sys.argv[1] if len(sys.argv) > 1 else "bf16"
+m = helpers.make_module(8, 4, PREC).cuda().eval()
 x = torch.rand(176, 1, 40, 32, device="cuda")
 with torch.no_grad():
     for _ in range(3): m(x)
