@@ -477,7 +477,7 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 #pragma unroll
         for (int e = 0; e < K::HDP / 2; ++e) {
           const int d0 = 2 * e, d1 = d0 + 1;
-          qp[e] = pk2(d0 < HD ? val(d0) : 0.f, d1 < HD ? val(d1) : 0.f);
+          qp[e] = pk2h(d0 < HD ? val(d0) : 0.f, d1 < HD ? val(d1) : 0.f);      // fp16: S accumulates in fp16 (below)
         }
         if constexpr (K::HDP / 2 == 8) {
           tmem_st_x8(lane_addr + K::TM_QKV + NH * s, qp);
@@ -491,7 +491,7 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const int d0 = c8 * 8 + 2 * q, d1 = d0 + 1;
-            w4[q] = pk2(d0 < HD ? val(HD + d0) : 0.f, d1 < HD ? val(HD + d1) : 0.f);
+            w4[q] = pk2h(d0 < HD ? val(HD + d0) : 0.f, d1 < HD ? val(HD + d1) : 0.f);
           }
           *reinterpret_cast<uint4*>(sBk + c8 * 2048 + row * 16) = make_uint4(w4[0], w4[1], w4[2], w4[3]);
         }
@@ -558,21 +558,17 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
       mbar_wait(&bars[B_S_FULL + s], (g / K::NS) & 1);
       fence_after_sync();
       A2_STAMP();   // C/D: S ready
-      uint32_t v0[32], v1[32];
-      tmem_ld_x32(tS, v0);
-      tmem_ld_x32(tS + 32, v1);
+      uint32_t p[32];                                            // half2 logits, then probabilities, in place
+      tmem_ld_x32_pack16(tS, p);                                 // 64 fp16 logits, keys 2j / 2j+1 in register j
       wait_ld();
       // logits -> half2, + relative-position bias pair (one 32-bit table read per two keys), + mask
       const uint32_t* tb = sTab2 + h * K::TBL + (iy + 7) * 24 + ix + 7;
-      uint32_t p[32];                                            // half2 logits, then probabilities, in place
 #pragma unroll
       for (int j = 0; j < 32; ++j) {
         const int kk = 2 * j, q = kk >> 4;                       // keys 2j, 2j+1 in box order
         const int jy = (q >> 1) * 4 + ((kk >> 2) & 3), jx = (q & 1) * 4 + (kk & 3);
         const uint32_t bp = tb[-(jy * 24 + jx)];
-        const float a = __uint_as_float(j < 16 ? v0[2 * j] : v1[2 * j - 32]);
-        const float b = __uint_as_float(j < 16 ? v0[2 * j + 1] : v1[2 * j - 31]);
-        __half2 t = __hadd2(__floats2half2_rn(a, b), *reinterpret_cast<const __half2*>(&bp));
+        __half2 t = __hadd2(*reinterpret_cast<const __half2*>(&p[j]), *reinterpret_cast<const __half2*>(&bp));
         if (masked) t = __hadd2(t, mk[j >> 3]);
         p[j] = *reinterpret_cast<const uint32_t*>(&t);
       }
@@ -627,7 +623,10 @@ stl_attn2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant
     const uint32_t aWqkv = smem_u32(smem + K::OFF_WQKV), aWproj = smem_u32(smem + K::OFF_WPROJ);
     const uint32_t aKV = smem_u32(smem + K::OFF_KV);
     constexpr uint32_t idq = make_idesc_bf16(128, NH, false, false);
-    constexpr uint32_t ids = make_idesc_bf16(128, 64, false, false);
+    // S = Q K^T on fp16 operands with an fp16 accumulator: the softmax needs its logits as fp16 pairs anyway, and an fp16
+    // accumulator comes back from TMEM two values per register (tcgen05.ld .pack::16b) -- no 32 F2FP per row and head, half
+    // the registers.  K = 32 is two k-steps, i.e. two fp16 roundings instead of one.
+    constexpr uint32_t ids = make_idesc_f16_acc16(128, 64);
     constexpr uint32_t idv = make_idesc_f16(128, K::HDV, false, true);
     constexpr uint32_t idp = make_idesc_bf16(128, K::NPC, false, false);
     if (warp == 16 + K::NS) {
