@@ -229,7 +229,7 @@ int rdst_window_attention_tc_bwd(const float* qkv, int64_t ldq, const float* tab
 
 /* Fused Swin MLP:  Y[t] = X[t] + fc2( GELU( fc1( LNhat(X[t]) ) ) ),  bf16 storage, T tokens, C in {60,90,120}
  * (stored width Cp = 64/96/128, hidden 2C padded to Hp = 128/192/240).  LNhat as in rdst_linear_fwd.
- *   w1img: fc1 weight (gamma folded) as a ready-made UMMA K-major operand image  [Cp/8][Hp][8] bf16
+ *   w1img: fc1 weight (gamma folded) as a ready-made UMMA K-major operand image  [Cp/8][Hp][8] fp16
  *   w2img: HALF the fc2 weight (the GELU stage emits 2*GELU; exact scaling)    [Hp/8][Cp][8] fp16 (hidden is fp16)
  *   b1 [Hp] (beta folded), b2 [Cp] fp32.  exact_gelu != 0 evaluates erff instead of the fitted tanh form.
  * Replaces norm2 + Mlp + residual, swin_transformer_sr.py:272 and :23-29.  X and Y may not alias. */

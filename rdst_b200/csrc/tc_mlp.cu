@@ -91,11 +91,15 @@ __device__ __forceinline__ uint32_t mlp_xt_off(int row, int c) {
 }
 
 // b1 rides inside fc1: x-hat carries ones at pad channels 60/61 and rows 60/61 of the resident W1 image hold b1 as a
-// bf16 hi/lo pair (error <= 2^-17 |b1|), patched once per CTA
+// fp16 hi/lo pair (error <= 2^-22 |b1|), patched once per CTA.  (Round 2: fc1 runs on fp16 operands in both kernels.)
 __device__ __forceinline__ uint32_t mlp_bias_hi_lo(float b) {
-  const __nv_bfloat16 hi = __float2bfloat16_rn(b);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
-  return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+  const __half hi = __float2half_rn(b);
+  const __half lo = __float2half_rn(b - __half2float(hi));
+  return (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+}
+__device__ __forceinline__ uint32_t mlp_pack_f16x2(float a, float b) {
+  const __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
 }
 
 // store 8 packed columns held in a larger register array
@@ -187,8 +191,8 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
   // issuing warp rotates (an issuer that also owns token rows would otherwise be late for every barrier).
   // All fc1 chunks are issued before the first fc2 chunk: the fc2 accumulator aliases the normalised input.
   auto issue_fc1 = [&](int c) {
-    constexpr uint32_t idw = make_idesc_bf16(128, 64, false, false);
-    constexpr uint32_t idl = make_idesc_bf16(128, C::LASTW, false, false);
+    constexpr uint32_t idw = make_idesc_f16(128, 64, false, false);
+    constexpr uint32_t idl = make_idesc_f16(128, C::LASTW, false, false);
 #pragma unroll
     for (int ks = 0; ks < CP / 16; ++ks)
       mma_ts(tmem_u + C::TM_FC1 + 64 * c, tmem_u + C::TM_XH + ks * 8,
@@ -247,8 +251,8 @@ stl_mlp_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant__
       const float nb = -mean * rstd;
       uint32_t o[NCQ * 4];
 #pragma unroll
-      for (int e = 0; e < NCQ * 4; ++e) o[e] = pack_bf16x2(fmaf(fv[2 * e], rstd, nb), fmaf(fv[2 * e + 1], rstd, nb));
-      if (qtr == 7 / NCQ) o[(7 % NCQ) * 4 + 2] = 0x3F803F80u;      // ones at pad channels 60, 61 (folded fc1 bias)
+      for (int e = 0; e < NCQ * 4; ++e) o[e] = mlp_pack_f16x2(fmaf(fv[2 * e], rstd, nb), fmaf(fv[2 * e + 1], rstd, nb));
+      if (qtr == 7 / NCQ) o[(7 % NCQ) * 4 + 2] = 0x3C003C00u;      // ones at pad channels 60, 61 (folded fc1 bias)
       const uint32_t dst = lane_addr + C::TM_XH + qtr * NCQ * 4;
 #pragma unroll
       for (int c0 = 0; c0 + 8 <= NCQ * 4; c0 += 8) tmem_st8(dst + c0, o + c0);

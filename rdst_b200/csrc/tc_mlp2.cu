@@ -36,10 +36,25 @@ __device__ __forceinline__ float2 up2(uint32_t u) {
   __nv_bfloat162 v = *reinterpret_cast<__nv_bfloat162*>(&u);
   return __bfloat1622float2(v);
 }
-__device__ __forceinline__ uint32_t bias_hi_lo(float b) {          // b1 rides inside fc1 as a bf16 hi/lo pair (see tc_mlp.cu)
-  const __nv_bfloat16 hi = __float2bfloat16_rn(b);
-  const __nv_bfloat16 lo = __float2bfloat16_rn(b - __bfloat162float(hi));
-  return (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+__device__ __forceinline__ uint32_t bias_hi_lo(float b) {          // b1 rides inside fc1 as an fp16 hi/lo pair (see tc_mlp.cu)
+  const __half hi = __float2half_rn(b);
+  const __half lo = __float2half_rn(b - __half2float(hi));
+  return (uint32_t)__half_as_ushort(hi) | ((uint32_t)__half_as_ushort(lo) << 16);
+}
+__device__ __forceinline__ uint32_t pk2h(float a, float b) {
+  const __half2 v = __floats2half2_rn(a, b);
+  return *reinterpret_cast<const uint32_t*>(&v);
+}
+// GELU stage on an already packed fp16 pair (fc1 accumulates in fp16 and comes back packed: tcgen05.ld .pack::16b)
+__device__ __forceinline__ uint32_t gelu_h2(uint32_t xin) {
+  const __half2 x = *reinterpret_cast<const __half2*>(&xin);
+  const __half2 u = __hmul2(x, x);
+  const __half2 p = __hfma2(u, __float2half2_rn(3.470089e-02f), __float2half2_rn(8.0015708e-01f));
+  const __half2 inner = __hmul2(x, p);
+  uint32_t t;
+  asm("tanh.approx.f16x2 %0, %1;" : "=r"(t) : "r"(*reinterpret_cast<const uint32_t*>(&inner)));
+  const __half2 r = __hfma2(x, *reinterpret_cast<const __half2*>(&t), x);
+  return *reinterpret_cast<const uint32_t*>(&r);
 }
 // The GELU stage emits 2*GELU(x) = x*(1 + tanh(x*(a + b x^2))) on packed fp16 pairs; the factor 1/2 is folded into the fc2
 // weight image (exact: a power of two).  (a, b) are fitted to the erf form (max abs deviation 2.7e-4 in exact arithmetic;
@@ -227,10 +242,10 @@ stl_mlp2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
 #pragma unroll
           for (int q = 0; q < 4; ++q) {
             const float2 f = up2(w4[q]);
-            a[4 * c + q] = pk2(fmaf(f.x, rstd, nb), fmaf(f.y, rstd, nb));
+            a[4 * c + q] = pk2h(fmaf(f.x, rstd, nb), fmaf(f.y, rstd, nb));      // fp16: fc1 runs on fp16 operands
           }
         }
-        if (c0 == 4) a[14] = 0x3F803F80u;                  // ones at pad channels 60, 61 (folded fc1 bias)
+        if (c0 == 4) a[14] = 0x3C003C00u;                  // ones at pad channels 60, 61 (folded fc1 bias)
         tmem_st_x16(lane_addr + K::TM_XH + 4 * c0, a);
       }
       wg_sync(1);                                          // every row of L has been read twice: the next tile may land
@@ -252,28 +267,36 @@ stl_mlp2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
       mbar_wait(&bars[B_H_FULL + w], ph);
       fence_after_sync();
       M2_STAMP();   // G: fc1 chunk ready
-      uint32_t v[64];
-      if (c == NCHK - 1 && K::LASTW < 64) {
-#pragma unroll
-        for (int c0 = 0; c0 < K::LASTW; c0 += 16) {
-          uint32_t t16[16];
-          tmem_ld_x16(tH + c0, t16);
-#pragma unroll
-          for (int e = 0; e < 16; ++e) v[c0 + e] = t16[e];
-        }
-      } else {
-        uint32_t a[32], b[32];
-        tmem_ld_x32(tH, a);
-        tmem_ld_x32(tH + 32, b);
-#pragma unroll
-        for (int e = 0; e < 32; ++e) { v[e] = a[e]; v[32 + e] = b[e]; }
-      }
-      wait_ld();
-      warp_arrive(&bars[B_H_DRAINED + w], lane);           // the next fc1 chunk of this slot may run under this GELU
       uint32_t o[32];
+      if (EXACT) {
+        uint32_t v[64];
+        if (c == NCHK - 1 && K::LASTW < 64) {
 #pragma unroll
-      for (int j = 0; j < 32; ++j)
-        o[j] = (c == NCHK - 1 && 2 * j >= K::LASTW) ? 0u : gelu_pair<EXACT>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+          for (int c0 = 0; c0 < K::LASTW; c0 += 16) {
+            uint32_t t16[16];
+            tmem_ld_x16(tH + c0, t16);
+#pragma unroll
+            for (int e = 0; e < 16; ++e) v[c0 + e] = t16[e];
+          }
+        } else {
+          uint32_t a[32], b[32];
+          tmem_ld_x32(tH, a);
+          tmem_ld_x32(tH + 32, b);
+#pragma unroll
+          for (int e = 0; e < 32; ++e) { v[e] = a[e]; v[32 + e] = b[e]; }
+        }
+        wait_ld();
+        warp_arrive(&bars[B_H_DRAINED + w], lane);         // the next fc1 chunk of this slot may run under this GELU
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          o[j] = (c == NCHK - 1 && 2 * j >= K::LASTW) ? 0u : gelu_pair<EXACT>(__uint_as_float(v[2 * j]), __uint_as_float(v[2 * j + 1]));
+      } else {
+        tmem_ld_x32_pack16(tH, o);                           // 64 fp16 pre-activations as 32 packed pairs (columns beyond the
+        wait_ld();                                           // last chunk's width are stale and zeroed below)
+        warp_arrive(&bars[B_H_DRAINED + w], lane);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) o[j] = (c == NCHK - 1 && 2 * j >= K::LASTW) ? 0u : gelu_h2(o[j]);
+      }
       if (k >= 2) { mbar_wait(&bars[B_HP_FREE + w], ((k - 2) >> 1) & 1); fence_after_sync(); }   // fc2 of chunk k-2 has read the slot
       if (c == NCHK - 1 && K::LASTW < 64) {
         uint32_t t16[16], t8[8];
@@ -413,8 +436,10 @@ stl_mlp2_kernel(const __grid_constant__ CUtensorMap mapX, const __grid_constant_
     __syncwarp();
     const uint32_t tm = __shfl_sync(0xffffffffu, tmem, 0);
     const uint32_t aW1 = smem_u32(smem + K::OFF_W1);
-    constexpr uint32_t idw = make_idesc_bf16(128, 64, false, false);
-    constexpr uint32_t idl = make_idesc_bf16(128, K::LASTW, false, false);
+    // fc1 on fp16 operands with an fp16 accumulator (EXACT: fp32): the GELU wants packed fp16 pairs, which is how an fp16
+    // accumulator comes back from TMEM -- no conversion, half the registers per chunk
+    constexpr uint32_t idw = EXACT ? make_idesc_f16(128, 64, false, false) : make_idesc_f16_acc16(128, 64);
+    constexpr uint32_t idl = EXACT ? make_idesc_f16(128, K::LASTW, false, false) : make_idesc_f16_acc16(128, K::LASTW);
 #pragma unroll 1
     for (int k = 0; k < NK; ++k) {
       const int t = k / NCHK, c = k - t * NCHK, s = k & 1;

@@ -169,6 +169,12 @@ def kmajor_image(w, dtype=torch.bfloat16):
     return w.to(dtype).reshape(r, k // 8, 8).permute(1, 0, 2).contiguous().reshape(-1)
 
 
+def fc1_image(w1):
+    """fc1 weight image: fp16 (fc1 runs on fp16 operands; the warp-specialised kernel accumulates it in fp16 so that the GELU
+    gets its pre-activations as packed pairs straight out of TMEM)."""
+    return kmajor_image(w1, torch.float16)
+
+
 def fc2_image(w2):
     """fc2 weight image: fp16 (the GELU hidden activations are kept in fp16, see tc_mlp.cu), scaled by 1/2: the kernels'
     GELU stage emits x*(1 + tanh(..)) = 2*GELU(x) (one instruction less per pair; the scaling is exact)."""
@@ -219,7 +225,7 @@ def pack_attn_tc(wqkv, bqkv, wproj, bproj, table, c):
 
 def pack_stl_tc(p):
     """Add tensor-core operand images to a pack_stl() dict."""
-    p["w1img"] = kmajor_image(p["w1"])
+    p["w1img"] = fc1_image(p["w1"])
     p["w2img"] = fc2_image(p["w2"])
     p.update(pack_attn_tc(p["wqkv"], p["bqkv"], p["wproj"], p["bproj"], p["table"], p["c"]))
     return p

@@ -89,7 +89,7 @@ def test_fused_mlp(c, T, exact):
     E.rdst_linear_fwd(hid, hp, w2b, b2, x, cp, ref, cp, T, hp, cp, 0, 0, 1.0, 0, None)
     xd = x.cuda()
     yd = torch.full((T, cp), float("nan"), dtype=torch.bfloat16, device="cuda")
-    dev = [packing.kmajor_image(w1).cuda(), packing.fc2_image(w2).cuda(), b1.cuda(), b2.cuda()]
+    dev = [packing.fc1_image(w1).cuda(), packing.fc2_image(w2).cuda(), b1.cuda(), b2.cuda()]
     L.call("rdst_stl_mlp_fwd_bf16", L.ptr(xd), cp, L.ptr(yd), cp, L.ptr(dev[0]), L.ptr(dev[1]), L.ptr(dev[2]),
            L.ptr(dev[3]), T, c, exact, L.stream_ptr())
     y = yd.cpu().float()
@@ -189,7 +189,7 @@ def test_fused_mlp_with_dense_tail(c, T):
     ref = torch.zeros(T, 32)
     E.rdst_linear_fwd(y, cp, rb(wt), bt, None, 0, ref, 32, T, cp, 32, c, 0, 0.5, 0, None)
     dense = torch.full((T, 160), 7.0, dtype=torch.bfloat16, device="cuda")
-    dev = [t.cuda() for t in (x, packing.kmajor_image(w1), packing.fc2_image(w2), b1, b2, packing.kmajor_image(wt), bt)]
+    dev = [t.cuda() for t in (x, packing.fc1_image(w1), packing.fc2_image(w2), b1, b2, packing.kmajor_image(wt), bt)]
     L.call("rdst_stl_mlp_tail_fwd_bf16", L.ptr(dev[0]), cp, L.ptr(dev[1]), L.ptr(dev[2]), L.ptr(dev[3]), L.ptr(dev[4]),
            L.ptr(dev[5]), L.ptr(dev[6]), L.ptr(dense[:, 96:]), 160, 0.5, T, c, 0, L.stream_ptr())
     d = dense.cpu().float()

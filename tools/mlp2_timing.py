@@ -17,7 +17,7 @@ x = x.to(torch.bfloat16).cuda()
 w1 = torch.zeros(hp, cp); w1[:2 * c, pos] = torch.randn(2 * c, c, generator=g) * 0.08
 w2 = torch.zeros(cp, hp); w2[pos, :2 * c] = torch.randn(c, 2 * c, generator=g) * 0.08
 wt = torch.zeros(32, cp); wt[:30, pos] = torch.randn(30, c, generator=g) * 0.1
-dev = [packing.kmajor_image(w1).cuda(), packing.fc2_image(w2).cuda(), torch.zeros(hp).cuda(), torch.zeros(cp).cuda(),
+dev = [packing.fc1_image(w1).cuda(), packing.fc2_image(w2).cuda(), torch.zeros(hp).cuda(), torch.zeros(cp).cuda(),
        packing.kmajor_image(wt).cuda(), torch.zeros(32).cuda()]
 y = torch.empty_like(x)
 dense = torch.zeros(T, 160, dtype=torch.bfloat16, device="cuda")

@@ -12,7 +12,7 @@ g = torch.Generator().manual_seed(0)
 x = torch.zeros(T, cp); x[:, pos] = torch.randn(T, c, generator=g); x = x.to(torch.bfloat16).cuda()
 w1 = torch.zeros(hp, cp); w1[:2 * c, pos] = torch.randn(2 * c, c, generator=g) * 0.08
 w2 = torch.zeros(cp, hp); w2[pos, :2 * c] = torch.randn(c, 2 * c, generator=g) * 0.08
-d = [packing.kmajor_image(w1).cuda(), packing.fc2_image(w2).cuda(), torch.zeros(hp).cuda(), torch.zeros(cp).cuda()]
+d = [packing.fc1_image(w1).cuda(), packing.fc2_image(w2).cuda(), torch.zeros(hp).cuda(), torch.zeros(cp).cuda()]
 y = torch.empty_like(x)
 dbg = torch.zeros(128, dtype=torch.int64, device="cuda")
 run = lambda: _lib.call("rdst_stl_mlp_fwd_bf16", _lib.ptr(x), cp, _lib.ptr(y), cp, _lib.ptr(d[0]), _lib.ptr(d[1]), _lib.ptr(d[2]),
