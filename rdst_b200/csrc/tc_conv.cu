@@ -545,8 +545,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
   int buf = 0;
   uint32_t par0 = 0, par1 = 0;
   uint32_t fpar0 = 0, fpar1 = 0;
-  if (warp == 0) {
-    if (elect_one()) stage(2 * cid + rank, 0);
+  if (warp == 0) {                               // both staging buffers are requested up front; afterwards a buffer is refilled
+    if (elect_one()) {                           // (pair k+2) the moment the MMAs that read it (pair k) have completed
+      stage(2 * cid + rank, 0);
+      stage(2 * (cid + ncl) + rank, 1);
+    }
     __syncwarp();
   }
   if (2 * cid + rank < ntiles) { mbar_wait(&full[0], fpar0); fpar0 ^= 1; }
@@ -566,11 +569,11 @@ conv3x3_pair_kernel(const __grid_constant__ CUtensorMap mapA, const __grid_const
     const int tr = (int)(tile - (int64_t)b * g.nty * g.ntx);
     const int y0 = (tr / g.ntx) * g.TH, x0 = (tr % g.ntx) * g.TW;
     const int64_t npr = pr + ncl;
-    if (warp == 0) {                             // in flight under the MMAs of the current pair
-      if (elect_one()) stage(2 * npr + rank, buf ^ 1);
+    if (buf == 0) { mbar_wait(&bar[0], par0); par0 ^= 1; } else { mbar_wait(&bar[1], par1); par1 ^= 1; }
+    if (warp == 0) {                             // this pair's MMAs are done with buffer `buf`: request the pair after next
+      if (elect_one()) stage(2 * (npr + ncl) + rank, buf);
       __syncwarp();
     }
-    if (buf == 0) { mbar_wait(&bar[0], par0); par0 ^= 1; } else { mbar_wait(&bar[1], par1); par1 ^= 1; }
     if (2 * npr + rank < ntiles) {               // the next halo tile has landed
       if (buf == 0) { mbar_wait(&full[1], fpar1); fpar1 ^= 1; } else { mbar_wait(&full[0], fpar0); fpar0 ^= 1; }
     }
