@@ -12,8 +12,11 @@ Prints ONE JSON line (rank 0).  `value` times the forward with inputs resident i
 public call (`rdst_b200.make_RDSTSR(paras)` with the reference's E1 paras) with pinned HOST input and a device->host
 read of the HR result inside the timed region.  Before anything is timed, sampled slices of the bench batch are
 checked against the CPU oracle (`parity_max_abs`; the run aborts above the north_star tolerance).  Extra keys (not the
-headline): `rdst_e_cfg3` = the 4-RDSTB "RDST-E" variant on the same batch; `train_cfg4` = one data-parallel training
-step (32 x 1x24x24 per GPU, L1, Adam, NCCL gradient all-reduce inside the step's CUDA graph when N > 1).
+headline): `rdst_e_cfg3` = the 4-RDSTB "RDST-E" variant on the same batch; `rdst_e_cfg3_strong` = ONE such volume split
+over the N ranks, one CUDA-graph replay per rank (strong scaling); `train_cfg4` = one data-parallel training
+step (32 x 1x24x24 per GPU, L1, Adam, NCCL gradient all-reduce inside the step's CUDA graph when N > 1);
+`roofline_hbm_kernel` = the step's HBM-bound kernel (reconstruction conv) against the measured HBM peak, next to
+`roofline` (the dominant kernel, fused window attention at C = 120, against the measured bf16 tensor peak).
 `--impl reference` times the reference's own module on the host cores (the real networks/rdst_variations.py when
 /root/reference is importable, else the oracle port) on the full 176-slice batch.
 """
